@@ -1,0 +1,301 @@
+// agf_math.h -- deterministic elementary functions shared by host and device.
+//
+// Why this exists (hard part 1; DESIGN.md "Parity definition"):
+// the reference's closed loop is sensitive to last-bit differences of the float
+// libm calls made by its onboard logic (Common/Common/Math/Rotation.hpp:262-316:
+// sinf cosf asinf acosf atan2f) and, much more weakly, of the double sin/cos of
+// the plant's attitude update (Rotation.hpp:291-296).  glibc's and CUDA's libm
+// differ in the last bit, so bit-level parity between a CPU run and a GPU run is
+// only possible if both sides call the *same* routines.  Every routine below is
+// built only from IEEE-754 binary64 add, subtract, multiply, divide and sqrt in
+// a fixed order (no fused multiply-add, no vendor libm inside), so gcc on x86-64
+// and nvcc on sm_100a produce bit-identical results by construction:
+//   * on the device each operation is an explicit round-to-nearest intrinsic
+//     (__dadd_rn, __dmul_rn, ...), which the compiler never contracts into FMA;
+//   * on the host the file must be compiled with -ffp-contract=off (the oracle
+//     Makefile and the test fixtures do so; x86-64 baseline has no FMA anyway).
+// The float entry points evaluate in binary64 and round once to binary32.
+//
+// The polynomial / rational coefficients are the classical fdlibm ones
+// (Sun Microsystems, freely redistributable); accuracy is < 1 ulp (binary64)
+// for |x| < 1e5 and is checked against glibc in tests/test_agf_math.py.
+//
+// Users:  the CUDA step kernels (parity variant), the oracle port (oracle/port)
+// and the "sharedmath" build of the unmodified reference (oracle/Makefile),
+// which redirects the reference's libm calls here with a forced include.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AGF_HD __host__ __device__ __forceinline__
+#else
+#define AGF_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define AGF_DADD(a, b) __dadd_rn((a), (b))
+#define AGF_DSUB(a, b) __dsub_rn((a), (b))
+#define AGF_DMUL(a, b) __dmul_rn((a), (b))
+#define AGF_DDIV(a, b) __ddiv_rn((a), (b))
+#define AGF_DSQRT(a) __dsqrt_rn((a))
+#else
+#define AGF_DADD(a, b) ((a) + (b))
+#define AGF_DSUB(a, b) ((a) - (b))
+#define AGF_DMUL(a, b) ((a) * (b))
+#define AGF_DDIV(a, b) ((a) / (b))
+#define AGF_DSQRT(a) sqrt((a))
+#endif
+
+// ---------------------------------------------------------------------------
+// argument reduction: x = k*(pi/2) + r, |r| <= pi/4 (+ a hair), returns k mod 4
+// three-term Cody-Waite; exact products for |k| < 2^20
+// ---------------------------------------------------------------------------
+AGF_HD int agf_rem_pio2(double x, double* r) {
+  const double invpio2 = 6.36619772367581382433e-01;
+  const double p1 = 1.57079632673412561417e+00;   // first 33 bits of pi/2
+  const double p2 = 6.07710050630396597660e-11;   // next 33 bits
+  const double p3 = 2.02226624871116645580e-21;   // next 33 bits
+  const double p3t = 8.47842766036889956997e-32;  // tail
+  const double magic = 6755399441055744.0;        // 1.5 * 2^52: rounds to nearest integer
+  double t = AGF_DADD(AGF_DMUL(x, invpio2), magic);
+  double fk = AGF_DSUB(t, magic);
+  double y = AGF_DSUB(x, AGF_DMUL(fk, p1));
+  y = AGF_DSUB(y, AGF_DMUL(fk, p2));
+  y = AGF_DSUB(y, AGF_DMUL(fk, p3));
+  y = AGF_DSUB(y, AGF_DMUL(fk, p3t));
+  *r = y;
+  long long k = (long long)fk;
+  return (int)(k & 3);
+}
+
+// sin on |r| <= pi/4: r + r^3*(S1 + r^2*(S2 + ...))
+AGF_HD double agf_ksin(double r) {
+  const double S1 = -1.66666666666666324348e-01;
+  const double S2 = 8.33333333332248946124e-03;
+  const double S3 = -1.98412698298579493134e-04;
+  const double S4 = 2.75573137070700676789e-06;
+  const double S5 = -2.50507602534068634195e-08;
+  const double S6 = 1.58969099521155010221e-10;
+  double z = AGF_DMUL(r, r);
+  double p = AGF_DADD(S5, AGF_DMUL(z, S6));
+  p = AGF_DADD(S4, AGF_DMUL(z, p));
+  p = AGF_DADD(S3, AGF_DMUL(z, p));
+  p = AGF_DADD(S2, AGF_DMUL(z, p));
+  p = AGF_DADD(S1, AGF_DMUL(z, p));
+  double r3 = AGF_DMUL(z, r);
+  return AGF_DADD(r, AGF_DMUL(r3, p));
+}
+
+// cos on |r| <= pi/4: 1 - r^2/2 + r^4*(C1 + r^2*(C2 + ...))
+AGF_HD double agf_kcos(double r) {
+  const double C1 = 4.16666666666666019037e-02;
+  const double C2 = -1.38888888888741095749e-03;
+  const double C3 = 2.48015872894767294178e-05;
+  const double C4 = -2.75573143513906633035e-07;
+  const double C5 = 2.08757232129817482790e-09;
+  const double C6 = -1.13596475577881948265e-11;
+  double z = AGF_DMUL(r, r);
+  double p = AGF_DADD(C5, AGF_DMUL(z, C6));
+  p = AGF_DADD(C4, AGF_DMUL(z, p));
+  p = AGF_DADD(C3, AGF_DMUL(z, p));
+  p = AGF_DADD(C2, AGF_DMUL(z, p));
+  p = AGF_DADD(C1, AGF_DMUL(z, p));
+  double hz = AGF_DMUL(0.5, z);
+  double w = AGF_DSUB(1.0, hz);
+  // 1 - hz is inexact; recover the rounding error (fdlibm trick) before adding the tail
+  double e = AGF_DSUB(AGF_DSUB(1.0, w), hz);
+  double tail = AGF_DADD(AGF_DMUL(AGF_DMUL(z, z), p), e);
+  return AGF_DADD(w, tail);
+}
+
+AGF_HD double agf_sin(double x) {
+  if (!(x == x) || x - x != 0.0) return x - x;  // NaN, +-inf -> NaN
+  double r;
+  int q = agf_rem_pio2(x, &r);
+  switch (q) {
+    case 0: return agf_ksin(r);
+    case 1: return agf_kcos(r);
+    case 2: return -agf_ksin(r);
+    default: return -agf_kcos(r);
+  }
+}
+
+AGF_HD double agf_cos(double x) {
+  if (!(x == x) || x - x != 0.0) return x - x;
+  double r;
+  int q = agf_rem_pio2(x, &r);
+  switch (q) {
+    case 0: return agf_kcos(r);
+    case 1: return -agf_ksin(r);
+    case 2: return -agf_kcos(r);
+    default: return agf_ksin(r);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// asin / acos (fdlibm rational approximation of (asin(x)-x)/x^3 on [0, 0.5])
+// ---------------------------------------------------------------------------
+AGF_HD double agf_asin_R(double z) {
+  const double pS0 = 1.66666666666666657415e-01;
+  const double pS1 = -3.25565818622400915405e-01;
+  const double pS2 = 2.01212532134862925881e-01;
+  const double pS3 = -4.00555345006794114027e-02;
+  const double pS4 = 7.91534994289814532176e-04;
+  const double pS5 = 3.47933107596021167570e-05;
+  const double qS1 = -2.40339491173441421878e+00;
+  const double qS2 = 2.02094576023350569471e+00;
+  const double qS3 = -6.88283971605453293030e-01;
+  const double qS4 = 7.70381505559019352791e-02;
+  double p = AGF_DADD(pS4, AGF_DMUL(z, pS5));
+  p = AGF_DADD(pS3, AGF_DMUL(z, p));
+  p = AGF_DADD(pS2, AGF_DMUL(z, p));
+  p = AGF_DADD(pS1, AGF_DMUL(z, p));
+  p = AGF_DADD(pS0, AGF_DMUL(z, p));
+  p = AGF_DMUL(z, p);
+  double q = AGF_DADD(qS3, AGF_DMUL(z, qS4));
+  q = AGF_DADD(qS2, AGF_DMUL(z, q));
+  q = AGF_DADD(qS1, AGF_DMUL(z, q));
+  q = AGF_DADD(1.0, AGF_DMUL(z, q));
+  return AGF_DDIV(p, q);
+}
+
+// returns NaN for |x| > 1 (callers that emulate errno test the argument themselves)
+AGF_HD double agf_asin(double x) {
+  const double pio2_hi = 1.57079632679489655800e+00;
+  const double pio2_lo = 6.12323399573676603587e-17;
+  double ax = x < 0 ? -x : x;
+  if (!(ax <= 1.0)) return (x - x) / (x - x);  // NaN in, or |x| > 1 -> NaN
+  if (ax < 0.5) {
+    double z = AGF_DMUL(x, x);
+    return AGF_DADD(x, AGF_DMUL(x, agf_asin_R(z)));
+  }
+  // asin(x) = pi/2 - 2*asin(sqrt((1-|x|)/2))
+  double z = AGF_DMUL(AGF_DSUB(1.0, ax), 0.5);
+  double s = AGF_DSQRT(z);
+  double rr = agf_asin_R(z);
+  double t = AGF_DADD(s, AGF_DMUL(s, rr));  // asin(s)
+  double res = AGF_DSUB(pio2_hi, AGF_DSUB(AGF_DMUL(2.0, t), pio2_lo));
+  return x < 0 ? -res : res;
+}
+
+AGF_HD double agf_acos(double x) {
+  const double pio2_hi = 1.57079632679489655800e+00;
+  const double pio2_lo = 6.12323399573676603587e-17;
+  double ax = x < 0 ? -x : x;
+  if (!(ax <= 1.0)) return (x - x) / (x - x);
+  if (ax < 0.5) {
+    double z = AGF_DMUL(x, x);
+    double a = AGF_DADD(x, AGF_DMUL(x, agf_asin_R(z)));  // asin(x)
+    return AGF_DSUB(pio2_hi, AGF_DSUB(a, pio2_lo));
+  }
+  double z = AGF_DMUL(AGF_DSUB(1.0, ax), 0.5);
+  double s = AGF_DSQRT(z);
+  double t = AGF_DADD(s, AGF_DMUL(s, agf_asin_R(z)));  // asin(sqrt((1-|x|)/2))
+  if (x > 0) return AGF_DMUL(2.0, t);
+  // x <= -0.5: pi - 2*t
+  return AGF_DSUB(AGF_DMUL(2.0, pio2_hi), AGF_DSUB(AGF_DMUL(2.0, t), AGF_DMUL(2.0, pio2_lo)));
+}
+
+// ---------------------------------------------------------------------------
+// atan / atan2 (fdlibm: reduce to [0, 7/16] with 4 break points, odd polynomial)
+// ---------------------------------------------------------------------------
+AGF_HD double agf_atan_poly(double x) {
+  const double a0 = 3.33333333333329318027e-01;
+  const double a1 = -1.99999999998764832476e-01;
+  const double a2 = 1.42857142725034663711e-01;
+  const double a3 = -1.11111104054623557880e-01;
+  const double a4 = 9.09088713343650656196e-02;
+  const double a5 = -7.69187620504482999495e-02;
+  const double a6 = 6.66107313738753120669e-02;
+  const double a7 = -5.83357013379057348645e-02;
+  const double a8 = 4.97687799461593236017e-02;
+  const double a9 = -3.65315727442169155270e-02;
+  const double a10 = 1.62858201153657823623e-02;
+  double z = AGF_DMUL(x, x);
+  double p = AGF_DADD(a9, AGF_DMUL(z, a10));
+  p = AGF_DADD(a8, AGF_DMUL(z, p));
+  p = AGF_DADD(a7, AGF_DMUL(z, p));
+  p = AGF_DADD(a6, AGF_DMUL(z, p));
+  p = AGF_DADD(a5, AGF_DMUL(z, p));
+  p = AGF_DADD(a4, AGF_DMUL(z, p));
+  p = AGF_DADD(a3, AGF_DMUL(z, p));
+  p = AGF_DADD(a2, AGF_DMUL(z, p));
+  p = AGF_DADD(a1, AGF_DMUL(z, p));
+  p = AGF_DADD(a0, AGF_DMUL(z, p));
+  // atan(x) = x - x*z*p
+  return AGF_DMUL(AGF_DMUL(x, z), p);
+}
+
+AGF_HD double agf_atan(double x) {
+  const double hi0 = 4.63647609000806093515e-01, lo0 = 2.26987774529616870924e-17;  // atan(0.5)
+  const double hi1 = 7.85398163397448278999e-01, lo1 = 3.06161699786838301793e-17;  // atan(1)
+  const double hi2 = 9.82793723247329054082e-01, lo2 = 1.39033110312309984516e-17;  // atan(1.5)
+  const double hi3 = 1.57079632679489655800e+00, lo3 = 6.12323399573676603587e-17;  // atan(inf)
+  if (!(x == x)) return x;
+  double ax = x < 0 ? -x : x;
+  double res;
+  if (ax < 0.4375) {
+    res = AGF_DSUB(ax, agf_atan_poly(ax));
+  } else {
+    double t, hi, lo;
+    if (ax < 0.6875) {
+      t = AGF_DDIV(AGF_DSUB(AGF_DMUL(2.0, ax), 1.0), AGF_DADD(2.0, ax));
+      hi = hi0; lo = lo0;
+    } else if (ax < 1.1875) {
+      t = AGF_DDIV(AGF_DSUB(ax, 1.0), AGF_DADD(ax, 1.0));
+      hi = hi1; lo = lo1;
+    } else if (ax < 2.4375) {
+      t = AGF_DDIV(AGF_DSUB(ax, 1.5), AGF_DADD(1.0, AGF_DMUL(1.5, ax)));
+      hi = hi2; lo = lo2;
+    } else {
+      t = AGF_DDIV(-1.0, ax);
+      hi = hi3; lo = lo3;
+    }
+    // hi - ((t*z*p - lo) - t)
+    res = AGF_DSUB(hi, AGF_DSUB(AGF_DSUB(agf_atan_poly(t), lo), t));
+  }
+  return x < 0 ? -res : res;
+}
+
+AGF_HD double agf_atan2(double y, double x) {
+  const double pi = 3.14159265358979311600e+00;
+  const double pi_lo = 1.22464679914735317723e-16;
+  const double pio2 = 1.57079632679489655800e+00;
+  if (!(x == x) || !(y == y)) return x + y;
+  if (y == 0.0) {
+    // sign of zero: follow IEEE atan2 for the cases the path can hit
+    if (x > 0 || (x == 0 && !signbit(x))) return y;  // +-0
+    return signbit(y) ? -pi : pi;
+  }
+  if (x == 0.0) return y > 0 ? pio2 : -pio2;
+  double ay = y < 0 ? -y : y;
+  double ax = x < 0 ? -x : x;
+  if (ax - ax != 0.0) {  // x infinite
+    if (ay - ay != 0.0) {
+      double v = x > 0 ? AGF_DMUL(0.5, pio2) : AGF_DMUL(1.5, pio2);
+      return y > 0 ? v : -v;
+    }
+    double v = x > 0 ? 0.0 : pi;
+    return y > 0 ? v : -v;
+  }
+  if (ay - ay != 0.0) return y > 0 ? pio2 : -pio2;
+  double z = agf_atan(AGF_DDIV(ay, ax));  // in [0, pi/2]
+  double res;
+  if (x > 0) {
+    res = z;
+  } else {
+    res = AGF_DSUB(pi, AGF_DSUB(z, pi_lo));
+  }
+  return y < 0 ? -res : res;
+}
+
+// ---------------------------------------------------------------------------
+// binary32 entry points: evaluate in binary64, round once
+// ---------------------------------------------------------------------------
+AGF_HD float agf_sinf(float x) { return (float)agf_sin((double)x); }
+AGF_HD float agf_cosf(float x) { return (float)agf_cos((double)x); }
+AGF_HD float agf_asinf(float x) { return (float)agf_asin((double)x); }
+AGF_HD float agf_acosf(float x) { return (float)agf_acos((double)x); }
+AGF_HD float agf_atan2f(float y, float x) { return (float)agf_atan2((double)y, (double)x); }

@@ -1,0 +1,136 @@
+"""Scenario definitions shared by tests, golden-vector generation and bench.py.
+
+A scenario is (vehicle config edits, initial state, UWB anchors, command schedule); the same
+schedule drives the CUDA batch (agf_batch_set_cmd_schedule) and the CPU oracles.  The timing
+reproduces the offboard loop of Simulator/Rappids_Simulator/main.cpp:471-739: a command is
+computed right after the Run() of tick g (the first g whose elapsed time exceeds the loop period,
+strict '>'), queued with the uplink delay (CommunicationsDelay.hpp:18-39) and therefore delivered
+before the Run() of tick g + delay_ticks + 1.
+"""
+import numpy as np
+
+DT_US = 2000
+
+
+def command_ticks(nticks, period_ticks, delay_ticks):
+    """(generation tick g, delivery tick) pairs.  g = period, 2*period, ... (strict '>' on the
+    stopwatch: with Run() before Advance() the first generation is after the Run of tick `period`)."""
+    out = []
+    g = period_ticks
+    while g + delay_ticks + 1 < nticks:
+        out.append((g, g + delay_ticks + 1))
+        g += period_ticks
+    return out
+
+
+def rates_scenario(codec, nticks=5000):
+    """SURVEY section 8c "Rates mode": external rates command, thrust 1.05 g, a short body-rate
+    doublet at t in (2.0, 2.2) s, 100 Hz commands, 30 ms uplink delay."""
+    sched = []
+    for g, d in command_ticks(nticks, 5, 15):
+        t = (g + 1) * DT_US * 1e-6
+        if 2.0 < t < 2.1:
+            w = (1.0, 0.5, 0.2)
+        elif 2.1 <= t < 2.2:
+            w = (-1.0, -0.5, -0.2)
+        else:
+            w = (0.0, 0.0, 0.0)
+        sched.append((d, codec.encode_rates(0, np.float32(1.05 * 9.81), w), -1))
+    return dict(name="rates", quad_type=5, vehicle_id=1, motor_time_const=0.0, motor_inertia=0.0,
+                pos=(0.0, 0.0, 0.0), att=(1.0, 0.0, 0.0, 0.0), anchors=[], uwb_comm_period=0.0,
+                sched=sched, nticks=nticks)
+
+
+ANCHORS_8 = [(101 + i, (x, y, z)) for i, (x, y, z) in enumerate(
+    [(sx * 3.0, sy * 3.0, z) for z in (0.1, 3.0) for sx in (1, -1) for sy in (1, -1)])]
+
+
+def full_scenario(codec, nticks=5000, start=(0.5, -0.3, 0.0), wp1=None, wp2=None, motor_time_const=0.015):
+    """SURVEY section 8c "Full mode": onboard position control with the 9-state EKF and an 8-anchor
+    UWB network; idle commands for the first second, then a hover set-point, then a step."""
+    wp1 = (start[0], start[1], 1.5) if wp1 is None else wp1
+    wp2 = (start[0] + 1.0, start[1] + 1.0, 2.0) if wp2 is None else wp2
+    sched = []
+    zero = (0.0, 0.0, 0.0)
+    for g, d in command_ticks(nticks, 10, 10):
+        t = (g + 1) * DT_US * 1e-6
+        if t < 1.0:
+            raw = codec.encode_idle(0)
+        elif t < 5.0:
+            raw = codec.encode_position(0, wp1, zero, zero)
+        else:
+            raw = codec.encode_position(0, wp2, zero, zero)
+        sched.append((d, raw, -1))
+    return dict(name="full", quad_type=5, vehicle_id=1, motor_time_const=motor_time_const,
+                motor_inertia=0.0, pos=tuple(start), att=(1.0, 0.0, 0.0, 0.0), anchors=ANCHORS_8,
+                uwb_comm_period=0.004, sched=sched, nticks=nticks)
+
+
+def accel_scenario(codec, nticks=2500):
+    """External acceleration command mode (QuadcopterLogic.cpp:459-526): climb, then a lateral
+    acceleration pulse with yaw rate; exercises ToEulerYPR / FromEulerYPR (atan2f, asinf)."""
+    sched = []
+    for g, d in command_ticks(nticks, 10, 10):
+        t = (g + 1) * DT_US * 1e-6
+        if t < 0.5:
+            raw = codec.encode_idle(0)
+        elif t < 2.0:
+            raw = codec.encode_acceleration(0, (0.0, 0.0, 1.0), 0.0)
+        elif t < 3.0:
+            raw = codec.encode_acceleration(0, (1.5, -0.8, 0.0), 0.6)
+        else:
+            raw = codec.encode_acceleration(0, (-1.0, 0.5, -0.5), -0.3)
+        sched.append((d, raw, -1))
+    return dict(name="accel", quad_type=4, vehicle_id=13, motor_time_const=0.02, motor_inertia=1e-6,
+                pos=(0.0, 0.0, 0.0), att=(1.0, 0.0, 0.0, 0.0), anchors=[], uwb_comm_period=0.0,
+                sched=sched, nticks=nticks)
+
+
+def waypoint_square_schedule(codec, nticks=5000, z=1.5, leg_s=2.5, idle_s=0.5):
+    """4-waypoint square (+-1, +-1, z), leg_s seconds each, 50 Hz position commands with
+    20 ms uplink delay, shared by the whole population."""
+    wps = [(1.0, 1.0, z), (-1.0, 1.0, z), (-1.0, -1.0, z), (1.0, -1.0, z)]
+    zero = (0.0, 0.0, 0.0)
+    sched = []
+    for g, d in command_ticks(nticks, 10, 10):
+        t = (g + 1) * DT_US * 1e-6
+        if t < idle_s:
+            raw = codec.encode_idle(0)
+        else:
+            raw = codec.encode_position(0, wps[int((t - idle_s) / leg_s) % 4], zero, zero)
+        sched.append((d, raw, -1))
+    return sched
+
+
+def hover_slot_schedule(nticks=5000, idle_s=0.5):
+    """every vehicle hovers at its own set-point (per-vehicle packets in command slot 0,
+    idle packets in slot 1 are not needed: idle is a broadcast)."""
+    sched = []
+    for g, d in command_ticks(nticks, 10, 10):
+        t = (g + 1) * DT_US * 1e-6
+        sched.append((d, None, -2 if t < idle_s else 0))  # -2: caller substitutes an idle broadcast
+    return sched
+
+
+def monte_carlo_initial_states(n, seed=1234):
+    """SURVEY C2 initial conditions: p_xy ~ U(-1,1) m, p_z = 0, yaw ~ U(-pi,pi), roll/pitch ~
+    U(-5,5) deg, v = w = 0.  Returns [n][13] (pos3 vel3 att4 angvel3), float64.
+    numpy's Philox bit generator keyed by `seed` (counter-based, reproducible anywhere)."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    u = rng.random((n, 5))
+    px = -1.0 + 2.0 * u[:, 0]
+    py = -1.0 + 2.0 * u[:, 1]
+    yaw = -np.pi + 2.0 * np.pi * u[:, 2]
+    roll = np.deg2rad(-5.0 + 10.0 * u[:, 3])
+    pitch = np.deg2rad(-5.0 + 10.0 * u[:, 4])
+    cy, sy = np.cos(0.5 * yaw), np.sin(0.5 * yaw)
+    cp, sp = np.cos(0.5 * pitch), np.sin(0.5 * pitch)
+    cr, sr = np.cos(0.5 * roll), np.sin(0.5 * roll)
+    # Rotation::FromEulerYPR (Rotation.hpp:99-110)
+    q = np.stack([cy * cp * cr + sy * sp * sr, cy * cp * sr - sy * sp * cr,
+                  cy * sp * cr + sy * cp * sr, sy * cp * cr - cy * sp * sr], axis=1)
+    out = np.zeros((n, 13))
+    out[:, 0] = px
+    out[:, 1] = py
+    out[:, 6:10] = q
+    return out

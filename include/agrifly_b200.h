@@ -1,0 +1,351 @@
+/* agrifly_b200.h -- C ABI of the B200-native batched quadrotor simulation step.
+ *
+ * Drop-in boundary for ONE path of muellerlab/agri-fly: the per-vehicle
+ * simulation step `Simulation::Quadcopter_T<Onboard::QuadcopterLogic>::Run()`
+ * (Components/Components/Simulation/Quadcopter_T.cpp:86-203) together with the
+ * object API it sits behind, `Simulation::SimulationObject6DOF`
+ * (Components/Components/Simulation/SimulationObject6DOF.hpp:12-86).
+ * The reference has no FFI layer for this path -- the C++ class API *is* the
+ * operator API -- so every entry point below cites the reference member it
+ * replaces.  `agri-fly_b200/host/agf_quadcopter.hpp` layers the reference's
+ * method names (Run, Get/SetPosition, SetCommandRadioMsg, ...) on top of this
+ * header so that a `Rappids_Simulator`-style loop compiles unchanged.
+ *
+ * Conventions: plain C, no exceptions cross the ABI, every function returns an
+ * int (AGF_OK == 0, negative == error), opaque handle, caller-owned host
+ * buffers, one handle per GPU, thread-compatible (external synchronisation per
+ * handle).  There is NO CPU fallback: without a CUDA device agf_batch_create
+ * fails with AGF_ENODEVICE.
+ *
+ * Units: SI.  Attitude is the reference's Rotation quaternion [w,x,y,z] with
+ * <world vector> = att * <body vector> (Common/Common/Math/Rotation.hpp:28).
+ */
+#ifndef AGRIFLY_B200_H_
+#define AGRIFLY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGF_VERSION_MAJOR 0
+#define AGF_VERSION_MINOR 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define AGF_OK 0
+#define AGF_EINVAL (-1)       /* bad argument                                   */
+#define AGF_ENOMEM (-2)       /* host or device allocation failed               */
+#define AGF_ECUDA (-3)        /* CUDA runtime error (see agf_last_error_string) */
+#define AGF_EUNSUPPORTED (-4) /* valid request this build cannot serve          */
+#define AGF_ERANGE (-5)       /* index / count outside the batch                */
+#define AGF_ENODEVICE (-6)    /* no CUDA device: there is no CPU fallback       */
+#define AGF_EFULL (-7)        /* table full (reference returns -1 likewise:
+                                 QuadcopterLogic.hpp:224-227)                   */
+
+/* ---- enums mirrored from the reference --------------------------------- */
+/* Onboard::QuadcopterConstants::QuadcopterType (QuadcopterConstants.hpp:16-24) */
+enum {
+  AGF_QC_TYPE_INVALID = 0,
+  AGF_QC_TYPE_CF_STANDARD = 1,
+  AGF_QC_TYPE_CF_BIGMOTORSPROPS = 2,
+  AGF_QC_TYPE_CF_FEEDTHROUGH = 3,
+  AGF_QC_TYPE_CF_LARGEQUAD = 4,
+  AGF_QC_TYPE_CF_MINIQUAD = 5
+};
+/* Onboard::QuadcopterLogic::FlightState (QuadcopterLogic.hpp:145-154) */
+enum {
+  AGF_FS_UNINITIALIZED = 0,
+  AGF_FS_IDLE = 1,
+  AGF_FS_FULLY_AUTONOMOUS = 2,
+  AGF_FS_PANIC = 3,
+  AGF_FS_KILLED = 4,
+  AGF_FS_EXTERNAL_ACCELERATION_CONTROL = 5,
+  AGF_FS_EXTERNAL_RATES_CONTROL = 6
+};
+/* Onboard::PanicReason (PanicReason.hpp:5-14) */
+enum {
+  AGF_PANIC_NO_PANIC = 0,
+  AGF_PANIC_ONBOARD_ESTIMATE_CRAZY = 1,
+  AGF_PANIC_UWB_TIMEOUT = 2,
+  AGF_PANIC_UPSIDE_DOWN = 3,
+  AGF_PANIC_RADIO_CMD_TIMEOUT = 4,
+  AGF_PANIC_LOW_BATTERY = 5,
+  AGF_PANIC_KILLED_INTERNALLY = 6,
+  AGF_PANIC_KILLED_EXTERNALLY = 7
+};
+/* RadioTypes::Type / ReservedFlags (RadioTypes.hpp:17-37) */
+enum {
+  AGF_RADIO_INVALID = 0,
+  AGF_RADIO_RESERVED_FUTURE = 1,
+  AGF_RADIO_EMERGENCY_KILL = 2,
+  AGF_RADIO_POSITION_CMD = 3,
+  AGF_RADIO_EXTERNAL_ACCELERATION_CMD = 4,
+  AGF_RADIO_EXTERNAL_RATES_CMD = 5,
+  AGF_RADIO_IDLE_CMD = 6
+};
+#define AGF_RADIO_FLAG_CALIBRATE_MOTORS 0x01
+#define AGF_RADIO_FLAG_DISABLE_ONBOARD_SAFETY 0x02
+#define AGF_RADIO_PACKET_SIZE 23 /* RadioMessageDecoded::RAW_PACKET_SIZE (RadioTypes.hpp:50) */
+#define AGF_RADIO_NUM_FLOATS 10
+#define AGF_TELEMETRY_PACKET_SIZE 30 /* sizeof(TelemetryPacket::data_packet_t) (TelemetryPacket.hpp:32-36) */
+/* TelemetryPacket::TelemetryWarnings (TelemetryPacket.hpp:21-30) */
+#define AGF_WARN_LOW_BATT 0x01
+#define AGF_WARN_CMD_RATE 0x02
+#define AGF_WARN_UWB_RESET 0x04
+#define AGF_WARN_ONBOARD_FREQ 0x08
+#define AGF_WARN_CMD_BATCH_DROP 0x10
+
+#define AGF_MAX_UWB_ANCHORS 32 /* QuadcopterLogic::MAX_NUM_RANGING_TARGETS (QuadcopterLogic.hpp:346) */
+
+/* ---- vehicle configuration --------------------------------------------- */
+/* The onboard "firmware" constants, i.e. the members of
+ * Onboard::QuadcopterConstants (QuadcopterConstants.hpp:334-367) that
+ * QuadcopterLogic::Initialise reads (QuadcopterLogic.cpp:97-162).  All float,
+ * as in the reference. */
+typedef struct agf_logic_consts {
+  float mass;
+  float inertia_xx, inertia_zz; /* inertiaMatrix = diag(xx, xx, zz) (QuadcopterConstants.hpp:269-271) */
+  float arm_length;
+  float prop_thrust_from_speed_sqr;
+  float prop_torque_from_thrust;
+  float max_thrust_per_propeller, min_thrust_per_propeller;
+  float max_cmd_total_thrust; /* < 0: mixer default 0.8*4*max (QuadcopterMixer.hpp:45-50) */
+  int32_t prop0_spin_dir;
+  float pos_control_nat_freq, pos_control_damping;
+  float ang_vel_control_time_const_xy, att_control_time_const_xy;
+  float ang_vel_control_time_const_z, att_control_time_const_z;
+  float imu_yaw, imu_pitch, imu_roll;
+  float low_battery_threshold;
+  float lin_drag_coeff_b[3];
+  float motor_time_const, motor_inertia, motor_min_speed, motor_max_speed;
+  int32_t valid; /* 0: Initialise() latches FS_KILLED / PANIC_KILLED_INTERNALLY */
+} agf_logic_consts;
+
+/* One vehicle = the 15 constructor arguments of Simulation::Quadcopter_T
+ * (Quadcopter_T.hpp:24-32) minus the timer, plus the firmware constants the
+ * reference looks up from `quadcopterType` inside the constructor
+ * (Quadcopter_T.cpp:71-82). */
+typedef struct agf_vehicle_cfg {
+  double mass;
+  double inertia[9]; /* row major 3x3 */
+  double arm_length;
+  double com_error[3];
+  double motor_min_speed, motor_max_speed;
+  double prop_thrust_from_speed_sqr;
+  double prop_torque_from_speed_sqr;
+  double motor_time_const;
+  double motor_inertia;
+  double lin_drag_coeff_b[3];
+  int32_t vehicle_id; /* uint8_t id in the reference                     */
+  int32_t quad_type;  /* AGF_QC_TYPE_*                                   */
+  agf_logic_consts logic; /* filled by agf_vehicle_cfg_from_type; may be edited (extension) */
+} agf_vehicle_cfg;
+
+/* QuadcopterConstants::GetVehicleTypeFromID (QuadcopterConstants.hpp:297-332) */
+int agf_quad_type_from_id(unsigned id);
+/* QuadcopterConstants::QuadcopterConstants(t) (QuadcopterConstants.hpp:31-274) */
+int agf_logic_consts_from_type(int quad_type, agf_logic_consts* out);
+/* The widening the reference's apps perform before calling the constructor
+ * (Simulator/Rappids_Simulator/main.cpp:147-218): double(float table value),
+ * inertia_yy = inertia_xx, propTorqueFromSpeedSqr = kTau*kF, comError = 0. */
+int agf_vehicle_cfg_from_type(int quad_type, int vehicle_id, agf_vehicle_cfg* out);
+
+/* ---- radio uplink codec (Common/Common/DataTypes/RadioTypes.hpp) -------- */
+/* CreateRatesCommand :158 */
+void agf_radio_encode_rates(uint8_t flags, float total_thrust, const float ang_vel[3],
+                            uint8_t raw[AGF_RADIO_PACKET_SIZE]);
+/* CreatePositionCommand :137 */
+void agf_radio_encode_position(uint8_t flags, const float pos[3], const float vel[3],
+                               const float acc[3], uint8_t raw[AGF_RADIO_PACKET_SIZE]);
+/* CreateAccelerationCommand :173 */
+void agf_radio_encode_acceleration(uint8_t flags, const float acc[3], float yaw_rate,
+                                   uint8_t raw[AGF_RADIO_PACKET_SIZE]);
+/* CreateIdleCommand :130 / CreateKillCommand :123 (float fields are zero-filled) */
+void agf_radio_encode_idle(uint8_t flags, uint8_t raw[AGF_RADIO_PACKET_SIZE]);
+void agf_radio_encode_kill(uint8_t flags, uint8_t raw[AGF_RADIO_PACKET_SIZE]);
+/* RadioMessageDecoded(raw) :189-240 */
+void agf_radio_decode(const uint8_t raw[AGF_RADIO_PACKET_SIZE], uint8_t* type, uint8_t* flags,
+                      float floats[AGF_RADIO_NUM_FLOATS]);
+
+/* ---- telemetry downlink codec (Common/Common/DataTypes/TelemetryPacket.hpp) */
+typedef struct agf_telemetry { /* TelemetryPacket::TelemetryPacket :100-119 */
+  uint8_t type, packet_number;
+  float accel[3], gyro[3], motor_forces[4], position[3], batt_voltage;
+  float velocity[3], attitude[3], debug_vals[6];
+  uint8_t panic_reason, warnings;
+} agf_telemetry;
+/* DecodeTelemetryPacket :169-207; fills only the fields the packet type carries */
+void agf_telemetry_decode(const uint8_t packet[AGF_TELEMETRY_PACKET_SIZE], agf_telemetry* out);
+
+/* ---- the batched handle -------------------------------------------------- */
+typedef struct agf_batch agf_batch;
+
+/* arithmetic variants */
+#define AGF_PREC_FP64 0 /* the reference's own mixed precision: double plant, float onboard logic */
+#define AGF_PREC_FP32 1 /* plant in float as well (new; tolerance 1e-4)                         */
+#define AGF_MATH_PARITY 0 /* no FMA contraction, agf_math.h shared libm: bit-comparable with the oracle */
+#define AGF_MATH_FAST 1   /* FMA, CUDA fast paths                                                     */
+
+typedef struct agf_batch_opts {
+  int32_t device;    /* CUDA ordinal                                                     */
+  int32_t precision; /* AGF_PREC_*                                                       */
+  int32_t math;      /* AGF_MATH_*                                                       */
+  int32_t block_threads; /* 0 = default                                                  */
+  double onboard_logic_period; /* [s] Quadcopter_T ctor arg (Quadcopter_T.hpp:32); default 1/500 */
+  double uwb_comm_period;      /* [s] UWBNetwork ctor arg (UWBNetwork.hpp:19); <= 0: no network    */
+  /* IMU noise (Quadcopter_T.cpp:5-6: sigma_acc 0.2, sigma_gyro 0.1). Defaults are the
+   * reference's values; a noise-free run sets both to 0.  Bias is an extension (0 = reference). */
+  double sigma_acc, sigma_gyro;
+  double bias_sigma_acc, bias_sigma_gyro;
+  double uwb_noise_std_dev; /* UWBNetwork::SetNoiseProperties (UWBNetwork.hpp:28); outliers unsupported */
+  uint64_t seed;            /* Philox key                                                       */
+  uint64_t first_global_index; /* index of vehicle 0 of this shard in the whole population (RNG counter) */
+  void* stream;             /* cudaStream_t to launch on; NULL = a stream owned by the handle   */
+  int32_t telemetry_warnings; /* 1: maintain TelemetryPacket warnings bitmask (default 1)         */
+  int32_t reserved;
+} agf_batch_opts;
+
+void agf_batch_opts_default(agf_batch_opts* opts);
+
+/* Quadcopter_T::Quadcopter_T (Quadcopter_T.cpp:9-83) for n_vehicles vehicles.
+ * n_cfgs == 1: all vehicles share cfgs[0]; n_cfgs == n_vehicles: one each. */
+int agf_batch_create(const agf_vehicle_cfg* cfgs, size_t n_cfgs, size_t n_vehicles,
+                     const agf_batch_opts* opts, agf_batch** out);
+int agf_batch_destroy(agf_batch* b);
+size_t agf_batch_size(const agf_batch* b);
+void* agf_batch_stream(const agf_batch* b);
+
+/* `nticks` repetitions of [deliver scheduled radio commands] -> Run() -> [UWB network Run()]
+ * -> clock += dt_us, for every vehicle: the loop body of
+ * Simulator/Rappids_Simulator/main.cpp:391-392,737-739.  Asynchronous on the handle's stream. */
+int agf_batch_run(agf_batch* b, uint32_t dt_us, uint32_t nticks);
+int agf_batch_sync(agf_batch* b);
+/* simulation clock (ManualTimer::GetMicroSeconds, ManualTimer.hpp:38) and ticks run so far */
+uint64_t agf_batch_time_us(const agf_batch* b);
+uint64_t agf_batch_ticks(const agf_batch* b);
+
+/* state fields: SimulationObject6DOF getters/setters (SimulationObject6DOF.hpp:26-56) and the
+ * read-outs of Quadcopter_T.hpp:39-83.  Host buffers are [count][ncomp], element type as listed. */
+enum {
+  AGF_F_POSITION = 0,      /* double[3]  Get/SetPosition                                  */
+  AGF_F_VELOCITY = 1,      /* double[3]  Get/SetVelocity                                  */
+  AGF_F_ATTITUDE = 2,      /* double[4]  Get/SetAttitude  [w,x,y,z]                       */
+  AGF_F_ANGULAR_VELOCITY = 3, /* double[3]  Get/SetAngularVelocity                        */
+  AGF_F_MOTOR_SPEED = 4,   /* double[4]  Motor::_speed (Motor.hpp:53)                     */
+  AGF_F_MOTOR_SPEED_CMD = 5, /* float[4]   _motorSpeedCommands (Quadcopter_T.hpp:99)      */
+  AGF_F_EST_POSITION = 6,  /* float[3]   GetEstimate (Quadcopter_T.hpp:53)                */
+  AGF_F_EST_VELOCITY = 7,  /* float[3]                                                    */
+  AGF_F_EST_ATTITUDE = 8,  /* float[4]                                                    */
+  AGF_F_EST_ANGULAR_VELOCITY = 9, /* float[3]                                             */
+  AGF_F_ACCELEROMETER = 10, /* float[3]   GetAccelerometer (LPF output; Quadcopter_T.hpp:74) */
+  AGF_F_RATE_GYRO = 11,    /* float[3]   GetRateGyro                                      */
+  AGF_F_FLIGHT_STATE = 12, /* int32[1]   QuadcopterLogic::GetFlightState                  */
+  AGF_F_PANIC_REASON = 13, /* int32[1]   QuadcopterLogic::GetFirstPanicReason             */
+  AGF_F_MOTOR_FORCE = 14,  /* double[4]  GetMotorForce(i) (Quadcopter_T.hpp:39; z thrust of the last Run) */
+  AGF_F_EST_COVARIANCE = 15, /* float[81] KalmanFilter6DOF::_cov row major (read only)   */
+  AGF_F_CYCLE_COUNTER = 16, /* int32[1]  QuadcopterLogic::GetCycleCounter                 */
+  AGF_F_KF_COUNTERS = 17,  /* int32[4]  {numResets, numMeasRejected, uwbMeasCount, imuInit|uwbInit<<1} (read only) */
+  AGF_F_DES_MOTOR_FORCE = 18, /* float[4] _desMotorForcesForTelemetry (read only)          */
+  AGF_F_COUNT_
+};
+int agf_batch_get_field(agf_batch* b, int field, void* host_dst, size_t first, size_t count);
+int agf_batch_set_field(agf_batch* b, int field, const void* host_src, size_t first, size_t count);
+/* bytes per vehicle of a field's host representation */
+size_t agf_field_size(int field);
+
+/* SimulationObject6DOF::SetCommandRadioMsg (SimulationObject6DOF.hpp:64): deliver now, i.e. before
+ * the next Run().  raw is [count][23], or one packet for all vehicles in [first, first+count) when
+ * broadcast != 0. */
+int agf_batch_set_radio_cmd(agf_batch* b, const uint8_t* raw, size_t first, size_t count,
+                            int broadcast);
+
+/* In-kernel command delivery, replacing the host loop + CommunicationsDelay queue
+ * (CommunicationsDelay.hpp:18-39; main.cpp:737-739).  An entry is delivered before the Run() of
+ * absolute tick `tick` (tick 0 = first Run after create).  slot < 0: `raw` goes to every vehicle;
+ * slot >= 0: vehicle i receives packet i of per-vehicle slot `slot` (agf_batch_set_cmd_slot).
+ * Entries must be sorted by tick; at most one entry per tick (as the reference delivers at most
+ * one message per tick). */
+typedef struct agf_cmd_entry {
+  uint32_t tick;
+  int32_t slot;
+  uint8_t raw[AGF_RADIO_PACKET_SIZE];
+  uint8_t pad_;
+} agf_cmd_entry;
+int agf_batch_set_cmd_schedule(agf_batch* b, const agf_cmd_entry* entries, size_t n);
+#define AGF_MAX_CMD_SLOTS 4
+int agf_batch_set_cmd_slot(agf_batch* b, int slot, const uint8_t* raw /* [n_vehicles][23] */);
+
+/* SimulationObject6DOF::GetTelemetryDataPackets (SimulationObject6DOF.hpp:67;
+ * QuadcopterLogic.cpp:621-679), including its side effects (packet counter++, warnings cleared).
+ * p1, p2: [count][30]. */
+int agf_batch_get_telemetry(agf_batch* b, uint8_t* p1, uint8_t* p2, size_t first, size_t count);
+
+/* Quadcopter_T::SetExternalForce / SetExternalTorque (Quadcopter_T.hpp:45-51), world frame.
+ * force/torque: [count][3] or NULL to leave unchanged. */
+int agf_batch_set_external_wrench(agf_batch* b, const double* force, const double* torque,
+                                  size_t first, size_t count);
+
+/* Quadcopter_T::AddUWBRadioTarget (Quadcopter_T.hpp:58) + an anchor radio at the same place in the
+ * vehicle's private UWBNetwork.  Anchors are shared by all vehicles of the batch. */
+int agf_batch_add_uwb_anchor(agf_batch* b, uint8_t id, const float pos[3]);
+
+/* change noise parameters after creation (see agf_batch_opts) */
+int agf_batch_set_noise(agf_batch* b, uint64_t seed, double sigma_gyro, double sigma_acc,
+                        double bias_sigma_gyro, double bias_sigma_acc);
+
+/* Trajectory logging to HBM (new capability; replaces the CSV logger of main.cpp:676-733).
+ * Every `stride` ticks the step kernel appends one record per vehicle:
+ * 17 values {pos3 vel3 att4 angvel3 motorspeed4} in the plant precision, laid out
+ * [record][field][vehicle] so that each store instruction is a coalesced 128-byte line.
+ * capacity_records bounds the ring; agf_batch_read_log copies records out. */
+#define AGF_LOG_FIELDS 17
+int agf_batch_enable_log(agf_batch* b, uint32_t stride_ticks, uint32_t capacity_records);
+/* number of records written since enable (may exceed capacity: ring) */
+uint64_t agf_batch_log_count(const agf_batch* b);
+/* copies record `rec` (absolute index) for vehicles [first, first+count) as double[count][17] */
+int agf_batch_read_log(agf_batch* b, uint64_t rec, double* host_dst, size_t first, size_t count);
+/* raw device pointer + element size of the log ring, for consumers that stay on the GPU */
+int agf_batch_log_device_ptr(agf_batch* b, void** dev_ptr, size_t* elem_size);
+
+/* Monte-Carlo statistics (new capability): one launch reduces, over the vehicles of this handle,
+ * the tracking error e = position - target, with warp shuffles -> one atomic per block.
+ * target: [n][3] doubles on the host, or NULL for "the position command last delivered".
+ * The device-side result is a vector of AGF_STATS_LEN doubles that sums across shards (all entries
+ * except the last two, which combine with max), so the multi-GPU reduction is one
+ * all-reduce(SUM) + one all-reduce(MAX) on that vector. */
+#define AGF_STATS_LEN 16
+enum {
+  AGF_ST_COUNT = 0,      /* vehicles                                      */
+  AGF_ST_SUM_EX = 1, AGF_ST_SUM_EY = 2, AGF_ST_SUM_EZ = 3,
+  AGF_ST_SUM_E2 = 4,     /* sum |e|^2                                     */
+  AGF_ST_SUM_ENORM = 5,  /* sum |e|                                       */
+  AGF_ST_N_PANIC = 6,    /* vehicles in FS_PANIC                          */
+  AGF_ST_N_KILLED = 7,
+  AGF_ST_N_AUTONOMOUS = 8,
+  AGF_ST_N_NONFINITE = 9, /* vehicles with a non-finite position          */
+  AGF_ST_SUM_SPEED = 10,  /* sum |v|                                      */
+  AGF_ST_SUM_EST_ERR = 11, /* sum |est_pos - pos|                         */
+  AGF_ST_RESERVED12 = 12, AGF_ST_RESERVED13 = 13,
+  AGF_ST_MAX_ENORM = 14,  /* max |e|   (combine with MAX)                 */
+  AGF_ST_MAX_EST_ERR = 15 /* max |est_pos - pos| (combine with MAX)       */
+};
+/* dev_out: device pointer to AGF_STATS_LEN doubles (e.g. a torch tensor later handed to
+ * torch.distributed / ncclAllReduce); asynchronous on the handle's stream. */
+int agf_batch_reduce_stats_device(agf_batch* b, const double* host_target, double* dev_out);
+int agf_batch_reduce_stats(agf_batch* b, const double* host_target, double host_out[AGF_STATS_LEN]);
+
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches claim) */
+uint64_t agf_batch_launch_count(const agf_batch* b);
+/* device time of the step kernels launched since the last call, measured with CUDA events on the
+ * handle's stream: *ms = sum of kernel durations, *launches = how many.  Synchronises. */
+int agf_batch_step_kernel_time(agf_batch* b, double* ms, uint64_t* launches);
+
+const char* agf_last_error_string(void);
+const char* agf_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGRIFLY_B200_H_ */

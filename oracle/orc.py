@@ -1,0 +1,214 @@
+"""oracle/orc.py -- TEST INFRASTRUCTURE: ctypes driver for the CPU oracles (oracle/oracle_api.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this.  Flavours: ref-glibc / ref-shared (unmodified reference sources, oracle/_ref/*.so) and
+port-glibc / port-shared (independent restatement, oracle/libagf_port_*.so).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_abi():
+    import importlib.util
+    p = os.path.join(HERE, "..", "agri-fly_b200", "_abi.py")
+    spec = importlib.util.spec_from_file_location("agf_abi_for_oracle", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+abi = _load_abi()
+NTRAJ = 40
+
+# trajectory record columns
+COL = dict(pos=slice(0, 3), vel=slice(3, 6), att=slice(6, 10), angvel=slice(10, 13),
+           motor=slice(13, 17), motor_cmd=slice(17, 21), est_pos=slice(21, 24),
+           est_vel=slice(24, 27), est_att=slice(27, 31), est_angvel=slice(31, 34),
+           flight_state=34, panic=35, cycle=36, kf_resets=37, kf_rejected=38, uwb_count=39)
+
+
+class OrcOpts(C.Structure):
+    _fields_ = [("onboard_logic_period", C.c_double), ("uwb_comm_period", C.c_double),
+                ("sigma_acc", C.c_double), ("sigma_gyro", C.c_double),
+                ("uwb_noise_std_dev", C.c_double)]
+
+
+class FullState(C.Structure):
+    _fields_ = [
+        ("pos", C.c_double * 3), ("vel", C.c_double * 3), ("att", C.c_double * 4),
+        ("ang_vel", C.c_double * 3), ("motor_speed", C.c_double * 4),
+        ("motor_force_z", C.c_double * 4), ("motor_speed_cmd", C.c_float * 4),
+        ("flight_state", C.c_int32), ("first_panic_reason", C.c_int32),
+        ("cycle_counter", C.c_int32), ("tel_warnings", C.c_int32),
+        ("des_motor_speeds", C.c_float * 4), ("des_motor_forces", C.c_float * 4),
+        ("gyro_lpf", (C.c_float * 3) * 4), ("acc_lpf", (C.c_float * 3) * 4),
+        ("temp_lpf", C.c_float * 4), ("batt_lpf", C.c_float * 4),
+        ("batt_voltage_filtered", C.c_float), ("monitor_cmd_rate_lpdt", C.c_float),
+        ("monitor_main_loop_lpdt", C.c_float), ("des_pos", C.c_float * 3),
+        ("radio_floats", C.c_float * 10), ("radio_type", C.c_int32), ("radio_flags", C.c_int32),
+        ("radio_count", C.c_int32), ("uwb_meas_count", C.c_int32),
+        ("next_ranging_target_idx", C.c_int32),
+        ("kf_pos", C.c_float * 3), ("kf_vel", C.c_float * 3), ("kf_att", C.c_float * 4),
+        ("kf_ang_vel", C.c_float * 3), ("kf_last_corr", C.c_float * 3), ("kf_cov", C.c_float * 81),
+        ("kf_imu_init", C.c_int32), ("kf_uwb_init", C.c_int32), ("kf_num_resets", C.c_int32),
+        ("kf_num_rejected", C.c_int32), ("kf_num_rejected_seq", C.c_int32), ("debug", C.c_float * 6),
+    ]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = np.array(v) if hasattr(v, "__len__") else v
+        return out
+
+
+PATHS = {
+    "ref-glibc": os.path.join(HERE, "_ref", "libagf_ref_glibc.so"),
+    "ref-shared": os.path.join(HERE, "_ref", "libagf_ref_shared.so"),
+    "port-glibc": os.path.join(HERE, "libagf_port_glibc.so"),
+    "port-shared": os.path.join(HERE, "libagf_port_shared.so"),
+}
+
+
+def available(flavour):
+    return os.path.exists(PATHS[flavour])
+
+
+def make_schedule(entries):
+    """entries: list of (tick, raw bytes[23] or None, slot) -> ctypes array of agf_cmd_entry."""
+    arr = (abi.CmdEntry * max(1, len(entries)))()
+    for i, e in enumerate(entries):
+        tick, raw = e[0], e[1]
+        slot = e[2] if len(e) > 2 else -1
+        arr[i].tick = int(tick)
+        arr[i].slot = int(slot)
+        if raw is not None:
+            C.memmove(arr[i].raw, bytes(raw), abi.RADIO_PACKET_SIZE)
+    return arr
+
+
+class Oracle:
+    def __init__(self, flavour):
+        self.flavour = flavour
+        L = C.CDLL(PATHS[flavour])
+        vp, P = C.c_void_p, C.POINTER
+        L.orc_flavour.restype = C.c_char_p
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [P(abi.VehicleCfg), P(OrcOpts)]
+        L.orc_destroy.argtypes = [vp]
+        L.orc_set_state.argtypes = [vp] + [P(C.c_double)] * 4
+        L.orc_set_external.argtypes = [vp, P(C.c_double), P(C.c_double)]
+        L.orc_add_anchor.argtypes = [vp, C.c_uint8, C.c_float, C.c_float, C.c_float]
+        L.orc_add_anchor.restype = C.c_int
+        L.orc_set_radio.argtypes = [vp, C.c_char_p]
+        L.orc_run.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.CmdEntry), C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_get_full.argtypes = [vp, P(FullState)]
+        L.orc_get_telemetry.argtypes = [vp, C.c_void_p, C.c_void_p]
+        L.orc_get_imu.argtypes = [vp, P(C.c_double), P(C.c_double)]
+        L.orc_time_us.restype = C.c_uint64
+        L.orc_time_us.argtypes = [vp]
+        L.orc_run_population.restype = C.c_double
+        L.orc_run_population.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
+                                         C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),
+                                         C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        if flavour.startswith("ref-"):  # codec cross-checks exist only against the real reference
+            L.orc_radio_encode_rates.argtypes = [C.c_uint8, C.c_float, P(C.c_float), C.c_void_p]
+            L.orc_radio_encode_position.argtypes = [C.c_uint8, P(C.c_float), P(C.c_float), P(C.c_float), C.c_void_p]
+            L.orc_radio_encode_acceleration.argtypes = [C.c_uint8, P(C.c_float), C.c_float, C.c_void_p]
+            L.orc_telemetry_decode.argtypes = [C.c_void_p, P(abi.Telemetry)]
+            L.orc_logic_consts.argtypes = [C.c_int, P(abi.LogicConsts)]
+        L.orc_radio_decode.argtypes = [C.c_void_p, P(C.c_uint8), P(C.c_uint8), P(C.c_float)]
+        self.L = L
+        assert L.orc_flavour().decode() == flavour, (L.orc_flavour(), flavour)
+
+    def vehicle(self, cfg, **kw):
+        return OracleVehicle(self, cfg, **kw)
+
+    def run_population(self, cfgs, n, init13=None, anchors=None, dt_us=2000, nticks=1, sched=(),
+                       slot_raw=None, threads=1, onboard_logic_period=1.0 / 500.0, uwb_comm_period=0.0,
+                       sigma_acc=0.0, sigma_gyro=0.0):
+        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, 0.0)
+        if isinstance(cfgs, abi.VehicleCfg):
+            carr = (abi.VehicleCfg * 1)(cfgs)
+            ncfg = 1
+        else:
+            carr = (abi.VehicleCfg * len(cfgs))(*cfgs)
+            ncfg = len(cfgs)
+        out = np.zeros((n, NTRAJ))
+        i13 = None if init13 is None else np.ascontiguousarray(init13, dtype=np.float64)
+        anc = None if anchors is None else np.ascontiguousarray(anchors, dtype=np.float32)
+        sr = None if slot_raw is None else np.ascontiguousarray(slot_raw, dtype=np.uint8)
+        sch = make_schedule(list(sched))
+        secs = self.L.orc_run_population(
+            carr, ncfg, n, C.byref(opts), None if i13 is None else i13.ctypes.data,
+            None if anc is None else anc.ctypes.data, 0 if anc is None else len(anc), dt_us, nticks,
+            sch, len(sched), None if sr is None else sr.ctypes.data, threads, out.ctypes.data)
+        return out, secs
+
+
+class OracleVehicle:
+    def __init__(self, orc, cfg, onboard_logic_period=1.0 / 500.0, uwb_comm_period=0.0,
+                 sigma_acc=0.0, sigma_gyro=0.0, uwb_noise_std_dev=0.0):
+        self.orc = orc
+        self.L = orc.L
+        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, uwb_noise_std_dev)
+        self.h = self.L.orc_create(C.byref(cfg), C.byref(opts))
+
+    def close(self):
+        if self.h:
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, pos=(0, 0, 0), vel=(0, 0, 0), att=(1, 0, 0, 0), ang_vel=(0, 0, 0)):
+        a = lambda x, n: (C.c_double * n)(*[float(v) for v in x])
+        self.L.orc_set_state(self.h, a(pos, 3), a(vel, 3), a(att, 4), a(ang_vel, 3))
+
+    def set_external(self, force=None, torque=None):
+        a = lambda x: None if x is None else (C.c_double * 3)(*[float(v) for v in x])
+        self.L.orc_set_external(self.h, a(force), a(torque))
+
+    def add_anchor(self, id_, pos):
+        return self.L.orc_add_anchor(self.h, id_, float(pos[0]), float(pos[1]), float(pos[2]))
+
+    def set_radio(self, raw):
+        self.L.orc_set_radio(self.h, bytes(raw))
+
+    def run(self, nticks, dt_us=2000, sched=(), slot_raw=None, record=True):
+        sch = make_schedule(list(sched))
+        traj = np.zeros((nticks, NTRAJ)) if record else None
+        sr = None
+        if slot_raw is not None:
+            sr = np.ascontiguousarray(slot_raw, dtype=np.uint8)
+        self.L.orc_run(self.h, dt_us, nticks, sch, len(sched), None if sr is None else sr.ctypes.data,
+                       None if traj is None else traj.ctypes.data)
+        return traj
+
+    def full(self):
+        fs = FullState()
+        self.L.orc_get_full(self.h, C.byref(fs))
+        return fs.as_dict()
+
+    def telemetry(self):
+        p1 = np.zeros(30, np.uint8)
+        p2 = np.zeros(30, np.uint8)
+        self.L.orc_get_telemetry(self.h, p1.ctypes.data, p2.ctypes.data)
+        return p1, p2
+
+    def imu(self):
+        a = (C.c_double * 3)()
+        g = (C.c_double * 3)()
+        self.L.orc_get_imu(self.h, a, g)
+        return np.array(a), np.array(g)
+
+    def time_us(self):
+        return self.L.orc_time_us(self.h)

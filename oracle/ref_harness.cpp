@@ -1,0 +1,364 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE (builds oracle/_ref/libagf_ref_*.so).
+//
+// Drives the UNMODIFIED reference implementation of the hot path
+//   Components/Components/Simulation/{Quadcopter_T,Motor,UWBNetwork}.cpp
+//   Components/Components/Logic/{QuadcopterLogic,KalmanFilter6DOF}.cpp
+// (compiled where they lie under /root/reference by oracle/Makefile, against the header shims in
+// oracle/shim) through the C interface of oracle/oracle_api.h.  No reference source is copied
+// into this repository; this file only *calls* the reference's public classes and, for parity
+// dumps and noise control, reads/writes private members via the access-specifier macro below
+// (class layout is unaffected by access specifiers with GCC).
+//
+// The reference has no noise-free switch: IMU noise sigmas are constructor-initialised private
+// doubles (Quadcopter_T.cpp:5-6,25-26); the harness overwrites them.
+#include <assert.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <queue>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include <Eigen/Dense>
+
+#define private public
+#define protected public
+#include "Common/Time/ManualTimer.hpp"
+#include "Components/Simulation/Quadcopter_T.hpp"
+#include "Components/Simulation/UWBNetwork.hpp"
+#undef private
+#undef protected
+
+#include "oracle_api.h"
+
+#ifndef ORC_FLAVOUR
+#define ORC_FLAVOUR "ref-glibc"
+#endif
+
+struct orc_vehicle {
+  ManualTimer timer;
+  std::shared_ptr<Simulation::Quadcopter> quad;
+  std::unique_ptr<Simulation::UWBNetwork> net;
+  std::vector<std::shared_ptr<Simulation::UWBRadio>> anchors;
+  uint64_t tick;
+};
+
+template<typename LPF>
+static void dump_lpf3(const LPF& f, float out[4][3]) {
+  const Vec3f* s[4] = {&f._xm0, &f._xm1, &f._ym0, &f._ym1};
+  for (int i = 0; i < 4; i++) {
+    out[i][0] = s[i]->x; out[i][1] = s[i]->y; out[i][2] = s[i]->z;
+  }
+}
+
+extern "C" {
+
+const char* orc_flavour(void) { return ORC_FLAVOUR; }
+
+orc_vehicle* orc_create(const agf_vehicle_cfg* cfg, const orc_opts* opts) {
+  orc_vehicle* v = new orc_vehicle();
+  v->tick = 0;
+  Eigen::Matrix<double, 3, 3> inertia;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      inertia(i, j) = cfg->inertia[3 * i + j];
+  v->quad.reset(new Simulation::Quadcopter(
+      &v->timer, cfg->mass, inertia, cfg->arm_length,
+      Vec3d(cfg->com_error[0], cfg->com_error[1], cfg->com_error[2]), cfg->motor_min_speed,
+      cfg->motor_max_speed, cfg->prop_thrust_from_speed_sqr, cfg->prop_torque_from_speed_sqr,
+      cfg->motor_time_const, cfg->motor_inertia,
+      Vec3d(cfg->lin_drag_coeff_b[0], cfg->lin_drag_coeff_b[1], cfg->lin_drag_coeff_b[2]),
+      uint8_t(cfg->vehicle_id),
+      Onboard::QuadcopterConstants::QuadcopterType(cfg->quad_type), opts->onboard_logic_period));
+  v->quad->_stdDevAccNoise = opts->sigma_acc;
+  v->quad->_stdDevRateGyroNoise = opts->sigma_gyro;
+  if (opts->uwb_comm_period > 0) {
+    v->net.reset(new Simulation::UWBNetwork(&v->timer, opts->uwb_comm_period));
+    v->net->SetNoiseProperties(opts->uwb_noise_std_dev, 0, 0);
+    v->net->AddRadio(v->quad->GetRadio());
+  }
+  return v;
+}
+
+void orc_destroy(orc_vehicle* v) { delete v; }
+
+void orc_set_state(orc_vehicle* v, const double pos[3], const double vel[3], const double att[4],
+                   const double ang_vel[3]) {
+  v->quad->SetPosition(Vec3d(pos[0], pos[1], pos[2]));
+  v->quad->SetVelocity(Vec3d(vel[0], vel[1], vel[2]));
+  v->quad->SetAttitude(Rotationd(att[0], att[1], att[2], att[3]));
+  v->quad->SetAngularVelocity(Vec3d(ang_vel[0], ang_vel[1], ang_vel[2]));
+}
+
+void orc_set_external(orc_vehicle* v, const double force[3], const double torque[3]) {
+  if (force) v->quad->SetExternalForce(Vec3d(force[0], force[1], force[2]));
+  if (torque) v->quad->SetExternalTorque(Vec3d(torque[0], torque[1], torque[2]));
+}
+
+int orc_add_anchor(orc_vehicle* v, uint8_t id, float x, float y, float z) {
+  if (v->quad->_logic._numRangingTargets >= 32) return -1;
+  v->quad->AddUWBRadioTarget(id, Vec3f(x, y, z));
+  if (v->net) {
+    std::shared_ptr<Simulation::UWBRadio> r(new Simulation::UWBRadio(&v->timer, id));
+    r->SetPosition(Vec3d(Vec3f(x, y, z)));
+    v->anchors.push_back(r);
+    v->net->AddRadio(r);
+  }
+  return 0;
+}
+
+void orc_set_radio(orc_vehicle* v, const uint8_t raw[AGF_RADIO_PACKET_SIZE]) {
+  RadioTypes::RadioMessageDecoded::RawMessage m;
+  memcpy(m.raw, raw, AGF_RADIO_PACKET_SIZE);
+  v->quad->SetCommandRadioMsg(m);
+}
+
+static void record(orc_vehicle* v, double* r) {
+  Simulation::Quadcopter& q = *v->quad;
+  Vec3d p = q.GetPosition(), vel = q.GetVelocity(), w = q.GetAngularVelocity();
+  Rotationd a = q.GetAttitude();
+  r[0] = p.x; r[1] = p.y; r[2] = p.z;
+  r[3] = vel.x; r[4] = vel.y; r[5] = vel.z;
+  for (int i = 0; i < 4; i++) r[6 + i] = a[i];
+  r[10] = w.x; r[11] = w.y; r[12] = w.z;
+  for (int i = 0; i < 4; i++) r[13 + i] = q._motors[i]._speed;
+  for (int i = 0; i < 4; i++) r[17 + i] = q._motorSpeedCommands[i];
+  Vec3f ep, ev, ew;
+  Rotationf ea;
+  q.GetEstimate(ep, ev, ea, ew);
+  r[21] = ep.x; r[22] = ep.y; r[23] = ep.z;
+  r[24] = ev.x; r[25] = ev.y; r[26] = ev.z;
+  for (int i = 0; i < 4; i++) r[27 + i] = ea[i];
+  r[31] = ew.x; r[32] = ew.y; r[33] = ew.z;
+  r[34] = int(q._logic._state);
+  r[35] = q._logic._firstPanicReason;
+  r[36] = q._logic._cycleCounter;
+  r[37] = q._logic._kf._numResets;
+  r[38] = q._logic._kf._numMeasRejected;
+  r[39] = q._logic._uwbRangeMeas.count;
+}
+
+void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entry* sched,
+             uint32_t nsched, const uint8_t* slot_raw, double* traj) {
+  uint32_t si = 0;
+  while (si < nsched && sched[si].tick < v->tick) si++;
+  for (uint32_t k = 0; k < nticks; k++) {
+    if (si < nsched && sched[si].tick == v->tick) {
+      const uint8_t* raw = sched[si].raw;
+      if (sched[si].slot >= 0 && slot_raw) raw = slot_raw + AGF_RADIO_PACKET_SIZE * sched[si].slot;
+      orc_set_radio(v, raw);
+      si++;
+    }
+    v->quad->Run();
+    if (v->net) v->net->Run();
+    if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
+    v->timer.AdvanceMicroSeconds(dt_us);
+    v->tick++;
+  }
+}
+
+void orc_get_full(orc_vehicle* v, orc_full_state* o) {
+  memset(o, 0, sizeof(*o));
+  Simulation::Quadcopter& q = *v->quad;
+  Onboard::QuadcopterLogic& L = q._logic;
+  Vec3d p = q.GetPosition(), vel = q.GetVelocity(), w = q.GetAngularVelocity();
+  Rotationd a = q.GetAttitude();
+  o->pos[0] = p.x; o->pos[1] = p.y; o->pos[2] = p.z;
+  o->vel[0] = vel.x; o->vel[1] = vel.y; o->vel[2] = vel.z;
+  for (int i = 0; i < 4; i++) o->att[i] = a[i];
+  o->ang_vel[0] = w.x; o->ang_vel[1] = w.y; o->ang_vel[2] = w.z;
+  for (int i = 0; i < 4; i++) {
+    o->motor_speed[i] = q._motors[i]._speed;
+    o->motor_force_z[i] = q.GetMotorForce(i);
+    o->motor_speed_cmd[i] = q._motorSpeedCommands[i];
+    o->des_motor_speeds[i] = L._desMotorSpeeds[i];
+    o->des_motor_forces[i] = L._desMotorForcesForTelemetry[i];
+  }
+  o->flight_state = int(L._state);
+  o->first_panic_reason = L._firstPanicReason;
+  o->cycle_counter = int(L._cycleCounter);
+  o->tel_warnings = L._telWarnings;
+  dump_lpf3(L._imuRateGyro.lowPass, o->gyro_lpf);
+  dump_lpf3(L._imuAccelerometer.lowPass, o->acc_lpf);
+  o->temp_lpf[0] = L._imuTemperature.lowPass._xm0; o->temp_lpf[1] = L._imuTemperature.lowPass._xm1;
+  o->temp_lpf[2] = L._imuTemperature.lowPass._ym0; o->temp_lpf[3] = L._imuTemperature.lowPass._ym1;
+  o->batt_lpf[0] = L._battVoltageLowPass._xm0; o->batt_lpf[1] = L._battVoltageLowPass._xm1;
+  o->batt_lpf[2] = L._battVoltageLowPass._ym0; o->batt_lpf[3] = L._battVoltageLowPass._ym1;
+  o->batt_voltage_filtered = L._battMeas.voltageFiltered;
+  o->monitor_cmd_rate_lpdt = L._monitorCmdRate.lpDt;
+  o->monitor_main_loop_lpdt = L._monitorMainLoopPeriod.lpDt;
+  o->des_pos[0] = L._desPos.x; o->des_pos[1] = L._desPos.y; o->des_pos[2] = L._desPos.z;
+  o->radio_type = L._radioMessage.msg.type;
+  o->radio_flags = L._radioMessage.msg.flags;
+  o->radio_count = L._radioMessage.count;
+  if (L._radioMessage.count)  // floats are uninitialised before the first message (RadioTypes.hpp:118-121)
+    for (int i = 0; i < 10; i++) o->radio_floats[i] = L._radioMessage.msg.floats[i];
+  o->uwb_meas_count = L._uwbRangeMeas.count;
+  o->next_ranging_target_idx = L._nextRangingTargetIdx;
+  Onboard::KalmanFilter6DOF& kf = L._kf;
+  o->kf_pos[0] = kf._pos.x; o->kf_pos[1] = kf._pos.y; o->kf_pos[2] = kf._pos.z;
+  o->kf_vel[0] = kf._vel.x; o->kf_vel[1] = kf._vel.y; o->kf_vel[2] = kf._vel.z;
+  for (int i = 0; i < 4; i++) o->kf_att[i] = kf._att[i];
+  o->kf_ang_vel[0] = kf._angVel.x; o->kf_ang_vel[1] = kf._angVel.y; o->kf_ang_vel[2] = kf._angVel.z;
+  o->kf_last_corr[0] = kf._lastMeasUpdateAttCorrection.x;
+  o->kf_last_corr[1] = kf._lastMeasUpdateAttCorrection.y;
+  o->kf_last_corr[2] = kf._lastMeasUpdateAttCorrection.z;
+  for (int i = 0; i < 9; i++)
+    for (int j = 0; j < 9; j++)
+      o->kf_cov[9 * i + j] = kf._cov(i, j);
+  o->kf_imu_init = kf._IMUInitialized;
+  o->kf_uwb_init = kf._UWBInitialized;
+  o->kf_num_resets = kf._numResets;
+  o->kf_num_rejected = kf._numMeasRejected;
+  o->kf_num_rejected_seq = kf._numMeasRejectedSequentially;
+  for (int i = 0; i < 6; i++) o->debug[i] = L._debug[i];
+}
+
+void orc_get_telemetry(orc_vehicle* v, uint8_t p1[30], uint8_t p2[30]) {
+  TelemetryPacket::data_packet_t a, b;
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  v->quad->GetTelemetryDataPackets(a, b);
+  static_assert(sizeof(a) == 30, "packet size");
+  memcpy(p1, &a, 30);
+  memcpy(p2, &b, 30);
+}
+
+void orc_get_imu(orc_vehicle* v, double acc[3], double gyro[3]) {
+  Vec3d a, g;
+  v->quad->GetAccelerometer(a);
+  v->quad->GetRateGyro(g);
+  acc[0] = a.x; acc[1] = a.y; acc[2] = a.z;
+  gyro[0] = g.x; gyro[1] = g.y; gyro[2] = g.z;
+}
+
+uint64_t orc_time_us(orc_vehicle* v) { return v->timer.GetMicroSeconds(); }
+
+double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t n,
+                          const orc_opts* opts, const double* init13, const float* anchors,
+                          uint32_t n_anchors, uint32_t dt_us, uint32_t nticks,
+                          const agf_cmd_entry* sched, uint32_t nsched, const uint8_t* slot_raw,
+                          uint32_t threads, double* final_out) {
+  std::vector<orc_vehicle*> vs(n);
+  for (uint32_t i = 0; i < n; i++) {
+    vs[i] = orc_create(&cfgs[n_cfgs == 1 ? 0 : i], opts);
+    if (init13) {
+      const double* s = init13 + 13 * size_t(i);
+      orc_set_state(vs[i], s, s + 3, s + 6, s + 10);
+    }
+    for (uint32_t a = 0; a < n_anchors; a++)
+      orc_add_anchor(vs[i], uint8_t(anchors[4 * a]), anchors[4 * a + 1], anchors[4 * a + 2],
+                     anchors[4 * a + 3]);
+  }
+  if (threads < 1) threads = 1;
+  auto work = [&](uint32_t t) {
+    uint32_t lo = uint32_t(uint64_t(n) * t / threads), hi = uint32_t(uint64_t(n) * (t + 1) / threads);
+    uint8_t mine[AGF_MAX_CMD_SLOTS * AGF_RADIO_PACKET_SIZE];
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint8_t* sr = nullptr;
+      if (slot_raw) {
+        for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++)
+          memcpy(mine + s * AGF_RADIO_PACKET_SIZE,
+                 slot_raw + (size_t(s) * n + i) * AGF_RADIO_PACKET_SIZE, AGF_RADIO_PACKET_SIZE);
+        sr = mine;
+      }
+      orc_run(vs[i], dt_us, nticks, sched, nsched, sr, nullptr);
+    }
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  if (threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < threads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (uint32_t i = 0; i < n; i++) {
+    if (final_out) {
+      // state after the last tick (time already advanced; record reads the stored state)
+      record(vs[i], final_out + size_t(i) * ORC_NTRAJ);
+    }
+    orc_destroy(vs[i]);
+  }
+  return secs;
+}
+
+void orc_radio_encode_rates(uint8_t flags, float thrust, const float w[3], uint8_t raw[23]) {
+  memset(raw, 0, 23);
+  RadioTypes::RadioMessageDecoded::CreateRatesCommand(flags, thrust, Vec3f(w[0], w[1], w[2]), raw);
+}
+void orc_radio_encode_position(uint8_t flags, const float p[3], const float vv[3], const float a[3],
+                               uint8_t raw[23]) {
+  memset(raw, 0, 23);
+  RadioTypes::RadioMessageDecoded::CreatePositionCommand(
+      flags, Vec3f(p[0], p[1], p[2]), Vec3f(vv[0], vv[1], vv[2]), Vec3f(a[0], a[1], a[2]), raw);
+}
+void orc_radio_encode_acceleration(uint8_t flags, const float a[3], float yaw_rate,
+                                   uint8_t raw[23]) {
+  memset(raw, 0, 23);
+  RadioTypes::RadioMessageDecoded::CreateAccelerationCommand(flags, Vec3f(a[0], a[1], a[2]),
+                                                             yaw_rate, raw);
+}
+void orc_radio_decode(const uint8_t raw[23], uint8_t* type, uint8_t* flags, float floats[10]) {
+  RadioTypes::RadioMessageDecoded m(raw);
+  *type = m.type;
+  *flags = m.flags;
+  for (int i = 0; i < 10; i++) floats[i] = m.floats[i];
+}
+void orc_telemetry_decode(const uint8_t packet[30], agf_telemetry* out) {
+  TelemetryPacket::data_packet_t p;
+  memcpy(&p, packet, 30);
+  TelemetryPacket::TelemetryPacket t;
+  memset(&t, 0, sizeof(t));
+  TelemetryPacket::DecodeTelemetryPacket(p, t);
+  memset(out, 0, sizeof(*out));
+  out->type = t.type;
+  out->packet_number = t.packetNumber;
+  for (int i = 0; i < 3; i++) {
+    out->accel[i] = t.accel[i]; out->gyro[i] = t.gyro[i]; out->position[i] = t.position[i];
+    out->velocity[i] = t.velocity[i]; out->attitude[i] = t.attitude[i];
+  }
+  for (int i = 0; i < 4; i++) out->motor_forces[i] = t.motorForces[i];
+  for (int i = 0; i < 6; i++) out->debug_vals[i] = t.debugVals[i];
+  out->batt_voltage = t.battVoltage;
+  out->panic_reason = t.panicReason;
+  out->warnings = t.warnings;
+}
+
+void orc_logic_consts(int quad_type, agf_logic_consts* o) {
+  Onboard::QuadcopterConstants c((Onboard::QuadcopterConstants::QuadcopterType)quad_type);
+  memset(o, 0, sizeof(*o));
+  o->mass = c.mass; o->inertia_xx = c.inertia_xx; o->inertia_zz = c.inertia_zz;
+  o->arm_length = c.armLength;
+  o->prop_thrust_from_speed_sqr = c.propellerThrustFromSpeedSqr;
+  o->prop_torque_from_thrust = c.propellerTorqueFromThrust;
+  o->max_thrust_per_propeller = c.maxThrustPerPropeller;
+  o->min_thrust_per_propeller = c.minThrustPerPropeller;
+  o->max_cmd_total_thrust = c.maxCmdTotalThrust;
+  o->prop0_spin_dir = c.prop0SpinDir;
+  o->pos_control_nat_freq = c.posControl_natFreq; o->pos_control_damping = c.posControl_damping;
+  o->ang_vel_control_time_const_xy = c.angVelControl_timeConst_xy;
+  o->att_control_time_const_xy = c.attControl_timeConst_xy;
+  o->ang_vel_control_time_const_z = c.angVelControl_timeConst_z;
+  o->att_control_time_const_z = c.attControl_timeConst_z;
+  o->imu_yaw = c.IMU_yaw; o->imu_pitch = c.IMU_pitch; o->imu_roll = c.IMU_roll;
+  o->low_battery_threshold = c.lowBatteryThreshold;
+  o->lin_drag_coeff_b[0] = c.linDragCoeffBx; o->lin_drag_coeff_b[1] = c.linDragCoeffBy;
+  o->lin_drag_coeff_b[2] = c.linDragCoeffBz;
+  o->motor_time_const = c.motorTimeConst; o->motor_inertia = c.motorInertia;
+  o->motor_min_speed = c.motorMinSpeed; o->motor_max_speed = c.motorMaxSpeed;
+  o->valid = c.valid;
+}
+
+}  // extern "C"
