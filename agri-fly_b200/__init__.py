@@ -1,0 +1,298 @@
+"""agri-fly_b200 -- Python driver (ctypes) for libagrifly_b200.so, the B200-native batched
+implementation of agri-fly's per-vehicle simulation step.
+
+The package directory name carries the reference's hyphen; import it as `agrifly_b200` (alias
+package at the repo root) or with importlib.import_module("agri-fly_b200").
+
+The product is the CUDA library behind include/agrifly_b200.h.  This module only marshals numpy
+arrays across that C ABI; it has no CPU implementation of the step and raises if the library or a
+CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as abi
+from . import scenarios  # noqa: F401
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libagrifly_b200.so")
+_lib = None
+
+
+class AgfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("agrifly_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libagrifly_b200.so (built in-tree by agri-fly_b200/build.py). No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libagrifly_b200.so is not built: run `python agri-fly_b200/build.py` "
+                              "(there is no CPU fallback for the simulation step)")
+        _lib = abi.bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise AgfError(rc, lib().agf_last_error_string().decode(errors="replace"))
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Codec:
+    """RadioTypes / TelemetryPacket codecs of the C ABI."""
+
+    @staticmethod
+    def _raw():
+        return (C.c_uint8 * abi.RADIO_PACKET_SIZE)()
+
+    def encode_rates(self, flags, thrust, w):
+        raw = self._raw()
+        lib().agf_radio_encode_rates(flags, float(thrust), _f3(w), raw)
+        return bytes(raw)
+
+    def encode_position(self, flags, p, v=(0, 0, 0), a=(0, 0, 0)):
+        raw = self._raw()
+        lib().agf_radio_encode_position(flags, _f3(p), _f3(v), _f3(a), raw)
+        return bytes(raw)
+
+    def encode_acceleration(self, flags, a, yaw_rate):
+        raw = self._raw()
+        lib().agf_radio_encode_acceleration(flags, _f3(a), float(yaw_rate), raw)
+        return bytes(raw)
+
+    def encode_idle(self, flags=0):
+        raw = self._raw()
+        lib().agf_radio_encode_idle(flags, raw)
+        return bytes(raw)
+
+    def encode_kill(self, flags=0):
+        raw = self._raw()
+        lib().agf_radio_encode_kill(flags, raw)
+        return bytes(raw)
+
+    def decode(self, raw):
+        buf = (C.c_uint8 * abi.RADIO_PACKET_SIZE)(*bytes(raw))
+        t, f = C.c_uint8(), C.c_uint8()
+        fl = (C.c_float * 10)()
+        lib().agf_radio_decode(buf, C.byref(t), C.byref(f), fl)
+        return t.value, f.value, np.array(fl, dtype=np.float32)
+
+    def decode_telemetry(self, packet):
+        buf = (C.c_uint8 * abi.TELEMETRY_PACKET_SIZE)(*bytes(packet))
+        t = abi.Telemetry()
+        lib().agf_telemetry_decode(buf, C.byref(t))
+        return t
+
+
+codec = Codec()
+
+
+def quad_type_from_id(vehicle_id):
+    return lib().agf_quad_type_from_id(int(vehicle_id))
+
+
+def vehicle_cfg(quad_type=None, vehicle_id=1, **overrides):
+    """agf_vehicle_cfg for an airframe type (default: the type of `vehicle_id`)."""
+    if quad_type is None:
+        quad_type = quad_type_from_id(vehicle_id)
+    c = abi.VehicleCfg()
+    _check(lib().agf_vehicle_cfg_from_type(int(quad_type), int(vehicle_id), C.byref(c)))
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+def make_schedule(entries):
+    """[(tick, raw|None, slot)] -> ctypes array of agf_cmd_entry."""
+    arr = (abi.CmdEntry * max(1, len(entries)))()
+    for i, e in enumerate(entries):
+        arr[i].tick = int(e[0])
+        arr[i].slot = int(e[2]) if len(e) > 2 else -1
+        if e[1] is not None:
+            C.memmove(arr[i].raw, bytes(e[1]), abi.RADIO_PACKET_SIZE)
+    return arr
+
+
+class Batch:
+    """A batch of vehicles on one GPU (opaque agf_batch handle)."""
+
+    def __init__(self, cfgs, n, precision=abi.PREC_FP64, math=abi.MATH_PARITY, device=0,
+                 onboard_logic_period=1.0 / 500.0, uwb_comm_period=0.0, sigma_acc=0.0, sigma_gyro=0.0,
+                 bias_sigma_acc=0.0, bias_sigma_gyro=0.0, uwb_noise_std_dev=0.0, seed=1,
+                 first_global_index=0, stream=None, telemetry_warnings=True, block_threads=0):
+        L = lib()
+        o = abi.BatchOpts()
+        L.agf_batch_opts_default(C.byref(o))
+        o.device, o.precision, o.math, o.block_threads = device, precision, math, block_threads
+        o.onboard_logic_period, o.uwb_comm_period = onboard_logic_period, uwb_comm_period
+        o.sigma_acc, o.sigma_gyro = sigma_acc, sigma_gyro
+        o.bias_sigma_acc, o.bias_sigma_gyro = bias_sigma_acc, bias_sigma_gyro
+        o.uwb_noise_std_dev, o.seed, o.first_global_index = uwb_noise_std_dev, seed, first_global_index
+        o.stream = stream
+        o.telemetry_warnings = 1 if telemetry_warnings else 0
+        if isinstance(cfgs, abi.VehicleCfg):
+            arr, ncfg = (abi.VehicleCfg * 1)(cfgs), 1
+        else:
+            arr, ncfg = (abi.VehicleCfg * len(cfgs))(*cfgs), len(cfgs)
+        h = C.c_void_p()
+        _check(L.agf_batch_create(arr, ncfg, n, C.byref(o), C.byref(h)))
+        self.h, self.n, self.L = h, n, L
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.agf_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # stepping
+    def run(self, nticks, dt_us=2000):
+        _check(self.L.agf_batch_run(self.h, dt_us, nticks))
+
+    def sync(self):
+        _check(self.L.agf_batch_sync(self.h))
+
+    @property
+    def time_us(self):
+        return self.L.agf_batch_time_us(self.h)
+
+    @property
+    def ticks(self):
+        return self.L.agf_batch_ticks(self.h)
+
+    @property
+    def stream(self):
+        return self.L.agf_batch_stream(self.h)
+
+    # state
+    def get(self, name, first=0, count=None):
+        fid, dt, nc = abi.FIELDS[name]
+        count = self.n - first if count is None else count
+        out = np.empty((count, nc), dtype=dt)
+        _check(self.L.agf_batch_get_field(self.h, fid, out.ctypes.data, first, count))
+        return out
+
+    def set(self, name, values, first=0):
+        fid, dt, nc = abi.FIELDS[name]
+        v = np.ascontiguousarray(values, dtype=dt).reshape(-1, nc)
+        _check(self.L.agf_batch_set_field(self.h, fid, v.ctypes.data, first, len(v)))
+
+    def set_state13(self, s13, first=0):
+        s13 = np.asarray(s13, dtype=np.float64).reshape(-1, 13)
+        self.set("position", s13[:, 0:3], first)
+        self.set("velocity", s13[:, 3:6], first)
+        self.set("attitude", s13[:, 6:10], first)
+        self.set("angular_velocity", s13[:, 10:13], first)
+
+    def record(self):
+        """[n][40] in the oracle's trajectory-record column order (oracle/oracle_api.h)."""
+        r = np.zeros((self.n, 40))
+        r[:, 0:3] = self.get("position")
+        r[:, 3:6] = self.get("velocity")
+        r[:, 6:10] = self.get("attitude")
+        r[:, 10:13] = self.get("angular_velocity")
+        r[:, 13:17] = self.get("motor_speed")
+        r[:, 17:21] = self.get("motor_speed_cmd")
+        r[:, 21:24] = self.get("est_position")
+        r[:, 24:27] = self.get("est_velocity")
+        r[:, 27:31] = self.get("est_attitude")
+        r[:, 31:34] = self.get("est_angular_velocity")
+        r[:, 34] = self.get("flight_state")[:, 0]
+        r[:, 35] = self.get("panic_reason")[:, 0]
+        r[:, 36] = self.get("cycle_counter")[:, 0]
+        kc = self.get("kf_counters")
+        r[:, 37], r[:, 38], r[:, 39] = kc[:, 0], kc[:, 1], kc[:, 2]
+        return r
+
+    # commands
+    def set_radio(self, raw, first=0, count=None, broadcast=True):
+        count = self.n - first if count is None else count
+        if broadcast:
+            buf = np.frombuffer(bytes(raw), dtype=np.uint8).copy()
+        else:
+            buf = np.ascontiguousarray(raw, dtype=np.uint8).reshape(count, abi.RADIO_PACKET_SIZE)
+        _check(self.L.agf_batch_set_radio_cmd(self.h, buf.ctypes.data, first, count, 1 if broadcast else 0))
+
+    def set_schedule(self, entries):
+        entries = list(entries)
+        _check(self.L.agf_batch_set_cmd_schedule(self.h, make_schedule(entries), len(entries)))
+
+    def set_slot(self, slot, raw):
+        buf = np.ascontiguousarray(raw, dtype=np.uint8).reshape(self.n, abi.RADIO_PACKET_SIZE)
+        _check(self.L.agf_batch_set_cmd_slot(self.h, slot, buf.ctypes.data))
+
+    def telemetry(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        p1 = np.zeros((count, abi.TELEMETRY_PACKET_SIZE), np.uint8)
+        p2 = np.zeros((count, abi.TELEMETRY_PACKET_SIZE), np.uint8)
+        _check(self.L.agf_batch_get_telemetry(self.h, p1.ctypes.data, p2.ctypes.data, first, count))
+        return p1, p2
+
+    def set_external_wrench(self, force=None, torque=None, first=0, count=None):
+        count = self.n - first if count is None else count
+        f = None if force is None else np.ascontiguousarray(np.broadcast_to(force, (count, 3)), dtype=np.float64)
+        t = None if torque is None else np.ascontiguousarray(np.broadcast_to(torque, (count, 3)), dtype=np.float64)
+        _check(self.L.agf_batch_set_external_wrench(self.h, None if f is None else f.ctypes.data,
+                                                    None if t is None else t.ctypes.data, first, count))
+
+    def add_anchor(self, id_, pos):
+        _check(self.L.agf_batch_add_uwb_anchor(self.h, id_, _f3(pos)))
+
+    def set_noise(self, seed, sigma_gyro, sigma_acc, bias_sigma_gyro=0.0, bias_sigma_acc=0.0):
+        _check(self.L.agf_batch_set_noise(self.h, seed, sigma_gyro, sigma_acc, bias_sigma_gyro, bias_sigma_acc))
+
+    # logging / statistics
+    def enable_log(self, stride, capacity):
+        _check(self.L.agf_batch_enable_log(self.h, stride, capacity))
+
+    @property
+    def log_count(self):
+        return self.L.agf_batch_log_count(self.h)
+
+    def read_log(self, rec, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty((count, abi.LOG_FIELDS))
+        _check(self.L.agf_batch_read_log(self.h, rec, out.ctypes.data, first, count))
+        return out
+
+    def stats(self, target=None):
+        out = np.zeros(abi.STATS_LEN)
+        t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
+        _check(self.L.agf_batch_reduce_stats(self.h, None if t is None else t.ctypes.data, out.ctypes.data))
+        return out
+
+    def stats_device(self, dev_ptr, target=None):
+        t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
+        _check(self.L.agf_batch_reduce_stats_device(self.h, None if t is None else t.ctypes.data, dev_ptr))
+
+    @property
+    def launch_count(self):
+        return self.L.agf_batch_launch_count(self.h)
+
+    def step_kernel_time(self):
+        ms, nl = C.c_double(), C.c_uint64()
+        _check(self.L.agf_batch_step_kernel_time(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+
+def build_info():
+    return lib().agf_build_info().decode()

@@ -1,0 +1,1063 @@
+// agf_batch.cu -- the batched handle behind include/agrifly_b200.h.
+//
+// Host side of the drop-in boundary: construction (Quadcopter_T::Quadcopter_T,
+// Quadcopter_T.cpp:9-83, and QuadcopterLogic::Initialise, QuadcopterLogic.cpp:97-162, evaluated
+// once on the host for the whole batch), state get/set (SimulationObject6DOF.hpp:26-56), radio
+// command delivery, telemetry read-out, and the launch of the step kernels.  Everything that
+// touches vehicle state runs on the GPU; there is no CPU execution path for the step.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "agf_host_params.h"
+#include "agf_launch.h"
+#include "agf_math.h"
+#include "agf_types.h"
+#include "agrifly_b200.h"
+
+namespace agf {
+
+static thread_local std::string g_last_error;
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) {
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  } else {
+    snprintf(buf, sizeof(buf), "%s", what);
+  }
+  g_last_error = buf;
+  return code;
+}
+#define AGF_CUDA(call)                                      \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return fail(AGF_ECUDA, #call, e_); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// small kernels around the step: field gather/scatter, immediate radio delivery, telemetry, stats
+// ---------------------------------------------------------------------------------------------
+template<typename P>
+struct FieldCtx {
+  P* sp; float* sf; uint32_t* su; float* sc;
+  size_t n;
+  P kF_shared;
+  const P* pv;  // per-vehicle plant scalars or null
+};
+
+template<typename P>
+__device__ inline double f_get(const FieldCtx<P>& c, int field, size_t i, int comp, int* as_int, float* as_float, int* kind) {
+  constexpr int VP = VecOf<P>::lanes;
+  *kind = 0;  // 0 double, 1 float, 2 int
+  switch (field) {
+    case AGF_F_POSITION: return double(c.sp[sidx(SP_POS + comp, c.n, i, VP)]);
+    case AGF_F_VELOCITY: return double(c.sp[sidx(SP_VEL + comp, c.n, i, VP)]);
+    case AGF_F_ATTITUDE: return double(c.sp[sidx(SP_ATT + comp, c.n, i, VP)]);
+    case AGF_F_ANGULAR_VELOCITY: return double(c.sp[sidx(SP_W + comp, c.n, i, VP)]);
+    case AGF_F_MOTOR_SPEED: return double(c.sp[sidx(SP_MS + comp, c.n, i, VP)]);
+    case AGF_F_MOTOR_FORCE: {
+      const P sp = c.sp[sidx(SP_MS + comp, c.n, i, VP)];
+      const P kF = c.pv ? c.pv[sidx(PV_KF, c.n, i, VP)] : c.kF_shared;
+      return double((kF * sp) * (sp < 0 ? -sp : sp));
+    }
+    case AGF_F_MOTOR_SPEED_CMD: *kind = 1; *as_float = c.sf[sidx(SF_CMD + comp, c.n, i, 4)]; return 0;
+    case AGF_F_DES_MOTOR_FORCE: *kind = 1; *as_float = c.sf[sidx(SF_DFORCE + comp, c.n, i, 4)]; return 0;
+    case AGF_F_EST_POSITION: *kind = 1; *as_float = c.sf[sidx(SF_KPOS + comp, c.n, i, 4)]; return 0;
+    case AGF_F_EST_VELOCITY: *kind = 1; *as_float = c.sf[sidx(SF_KVEL + comp, c.n, i, 4)]; return 0;
+    case AGF_F_EST_ATTITUDE: *kind = 1; *as_float = c.sf[sidx(SF_KATT + comp, c.n, i, 4)]; return 0;
+    case AGF_F_EST_ANGULAR_VELOCITY: *kind = 1; *as_float = c.sf[sidx(SF_KW + comp, c.n, i, 4)]; return 0;
+    case AGF_F_ACCELEROMETER: *kind = 1; *as_float = c.sf[sidx(SF_ACC_LP + 4 * comp + 3, c.n, i, 4)]; return 0;
+    case AGF_F_RATE_GYRO: *kind = 1; *as_float = c.sf[sidx(SF_GYRO_LP + 4 * comp + 3, c.n, i, 4)]; return 0;
+    case AGF_F_EST_COVARIANCE: *kind = 1; *as_float = c.sc ? c.sc[sidx(comp, c.n, i, 4)] : 0.0f; return 0;
+    case AGF_F_FLIGHT_STATE: *kind = 2; *as_int = int(c.su[sidx(SU_BITS, c.n, i, 4)] & 0x7u); return 0;
+    case AGF_F_PANIC_REASON: *kind = 2; *as_int = int((c.su[sidx(SU_BITS, c.n, i, 4)] >> 3) & 0x7u); return 0;
+    case AGF_F_CYCLE_COUNTER: *kind = 2; *as_int = int(c.su[sidx(SU_CYCLE, c.n, i, 4)]); return 0;
+    case AGF_F_KF_COUNTERS: {
+      *kind = 2;
+      const uint32_t kc = c.su[sidx(SU_KFCNT, c.n, i, 4)], bits = c.su[sidx(SU_BITS, c.n, i, 4)];
+      if (comp == 0) *as_int = int(kc & 0xFFFFu);
+      else if (comp == 1) *as_int = int(kc >> 16);
+      else if (comp == 2) *as_int = int(c.su[sidx(SU_UWB_COUNT, c.n, i, 4)]);
+      else *as_int = int(((bits >> 18) & 1u) | (((bits >> 19) & 1u) << 1));
+      return 0;
+    }
+  }
+  return 0;
+}
+
+template<typename P>
+__global__ void field_get_kernel(FieldCtx<P> c, int field, int ncomp, size_t first, size_t count, void* out) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count * ncomp) return;
+  const size_t v = t / ncomp;
+  const int comp = int(t % ncomp);
+  int ai = 0, kind = 0;
+  float af = 0;
+  const double d = f_get(c, field, first + v, comp, &ai, &af, &kind);
+  if (kind == 0) ((double*)out)[t] = d;
+  else if (kind == 1) ((float*)out)[t] = af;
+  else ((int32_t*)out)[t] = ai;
+}
+
+template<typename P>
+__global__ void field_set_kernel(FieldCtx<P> c, int field, int ncomp, size_t first, size_t count, const void* in) {
+  constexpr int VP = VecOf<P>::lanes;
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count * ncomp) return;
+  const size_t i = first + t / ncomp;
+  const int comp = int(t % ncomp);
+  const double d = ((const double*)in)[t];
+  const float f = ((const float*)in)[t];
+  switch (field) {
+    case AGF_F_POSITION: c.sp[sidx(SP_POS + comp, c.n, i, VP)] = P(d); break;
+    case AGF_F_VELOCITY: c.sp[sidx(SP_VEL + comp, c.n, i, VP)] = P(d); break;
+    case AGF_F_ATTITUDE: c.sp[sidx(SP_ATT + comp, c.n, i, VP)] = P(d); break;
+    case AGF_F_ANGULAR_VELOCITY: c.sp[sidx(SP_W + comp, c.n, i, VP)] = P(d); break;
+    case AGF_F_MOTOR_SPEED: c.sp[sidx(SP_MS + comp, c.n, i, VP)] = P(d); break;
+    case AGF_F_MOTOR_SPEED_CMD: c.sf[sidx(SF_CMD + comp, c.n, i, 4)] = f; break;
+    case AGF_F_EST_POSITION: c.sf[sidx(SF_KPOS + comp, c.n, i, 4)] = f; break;
+    case AGF_F_EST_VELOCITY: c.sf[sidx(SF_KVEL + comp, c.n, i, 4)] = f; break;
+    case AGF_F_EST_ATTITUDE: c.sf[sidx(SF_KATT + comp, c.n, i, 4)] = f; break;
+    case AGF_F_EST_ANGULAR_VELOCITY: c.sf[sidx(SF_KW + comp, c.n, i, 4)] = f; break;
+    default: break;
+  }
+}
+
+// SetCommandRadioMsg now (QuadcopterLogic.hpp:110-116), outside the step kernel
+struct RadioNow {
+  uint32_t type, flags;
+  float f[4];
+};
+__global__ void radio_now_kernel(float* sf, uint32_t* su, size_t n, size_t first, size_t count, int broadcast,
+                                 RadioNow one, const RadioNow* per, float mon_cmd_coef, int hk) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const size_t i = first + t;
+  const RadioNow m = broadcast ? one : per[t];
+  uint32_t bits = su[sidx(SU_BITS, n, i, 4)];
+  bits |= (1u << 17);
+  bits = (bits & ~(0x7u << 6)) | ((m.type & 0x7u) << 6);
+  bits = (bits & ~(0xFFu << 9)) | ((m.flags & 0xFFu) << 9);
+  su[sidx(SU_BITS, n, i, 4)] = bits;
+  for (int k = 0; k < 4; k++) sf[sidx(SF_RADIO + k, n, i, 4)] = m.f[k];
+  su[sidx(SU_AGE_RADIO, n, i, 4)] = 0;
+  if (hk) {
+    const uint32_t age = su[sidx(SU_AGE_MON_CMD, n, i, 4)];
+    const float mdt = float(age) * 1e-6f;
+    const float prev = sf[sidx(SF_MON_CMD, n, i, 4)];
+    sf[sidx(SF_MON_CMD, n, i, 4)] = mon_cmd_coef <= 0.0f ? mdt : __fadd_rn(__fmul_rn(mon_cmd_coef, prev), __fmul_rn(__fsub_rn(1.0f, mon_cmd_coef), mdt));
+    su[sidx(SU_AGE_MON_CMD, n, i, 4)] = age - uint32_t(__fmul_rn(mdt, 1e6f));
+  }
+}
+
+// TelemetryPacket.hpp:39-63: MapToOnesRange + EncodeOnesRange (round-to-nearest ops, never contracted)
+__device__ inline uint16_t tel_encode(float x, float a, float b) {
+  const float t = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, a), __fsub_rn(b, a)), 2.0f), 1.0f);
+  if (t < -1 || t > 1) return 0;
+  const float e = __fadd_rn(32768.0f, __fmul_rn(32767.0f, t));
+  if (!(e == e)) return 0;
+  return uint16_t(int(e));
+}
+
+// GetTelemetryDataPackets (QuadcopterLogic.cpp:621-679)
+__global__ void telemetry_kernel(const float* sf, uint32_t* su, uint32_t* tel_counter, size_t n, size_t first,
+                                 size_t count, float batt_voltage, int hk, uint8_t* p1, uint8_t* p2) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const size_t i = first + t;
+  uint16_t d[14];
+  uint8_t* o1 = p1 + t * AGF_TELEMETRY_PACKET_SIZE;
+  uint8_t* o2 = p2 + t * AGF_TELEMETRY_PACKET_SIZE;
+  const uint32_t ctr = tel_counter[i];
+  for (int k = 0; k < 3; k++) {
+    d[k] = tel_encode(sf[sidx(SF_ACC_LP + 4 * k + 3, n, i, 4)], -30, 30);
+    d[3 + k] = tel_encode(sf[sidx(SF_GYRO_LP + 4 * k + 3, n, i, 4)], -35, 35);
+    d[10 + k] = tel_encode(sf[sidx(SF_KPOS + k, n, i, 4)], -30, 30);
+  }
+  for (int k = 0; k < 4; k++) d[6 + k] = tel_encode(sf[sidx(SF_DFORCE + k, n, i, 4)], 0, 10);
+  d[13] = tel_encode(batt_voltage, 0, 15);
+  o1[0] = 0;
+  o1[1] = uint8_t(ctr % 256);
+  for (int k = 0; k < 14; k++) { o1[2 + 2 * k] = uint8_t(d[k] & 0xFF); o1[3 + 2 * k] = uint8_t(d[k] >> 8); }
+  const float qw = sf[sidx(SF_KATT + 0, n, i, 4)];
+  for (int k = 0; k < 3; k++) {
+    d[k] = tel_encode(sf[sidx(SF_KVEL + k, n, i, 4)], -30, 30);
+    const float a = sf[sidx(SF_KATT + 1 + k, n, i, 4)];
+    d[3 + k] = tel_encode(qw > 0 ? a : -a, -1, 1);  // ToVectorPartOfQuaternion (Rotation.hpp:155-161)
+  }
+  // debug[0] = temperature low-pass output (QuadcopterLogic.cpp:178); others stay 0
+  const float dbg0 = hk ? sf[sidx(SF_TEMP_LP + 3, n, i, 4)] : 25.0f;
+  const uint32_t cyc = su[sidx(SU_CYCLE, n, i, 4)];
+  d[6] = tel_encode(cyc ? dbg0 : 0.0f, -100, 100);
+  for (int k = 1; k < 6; k++) d[6 + k] = tel_encode(0.0f, -100, 100);
+  const uint32_t bits = su[sidx(SU_BITS, n, i, 4)];
+  const uint32_t cnt = su[sidx(SU_CNT, n, i, 4)];
+  d[12] = uint16_t((bits >> 3) & 0x7u);
+  d[13] = uint16_t((cnt >> 24) & 0xFFu);
+  o2[0] = 1;
+  o2[1] = uint8_t(ctr % 256);
+  for (int k = 0; k < 14; k++) { o2[2 + 2 * k] = uint8_t(d[k] & 0xFF); o2[3 + 2 * k] = uint8_t(d[k] >> 8); }
+  tel_counter[i] = ctr + 1;
+  su[sidx(SU_CNT, n, i, 4)] = cnt & 0x00FFFFFFu;  // warnings cleared after sending
+}
+
+// K4: Monte-Carlo statistics. warp shuffle tree -> one atomic per warp leader per quantity.
+__device__ inline double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ inline void atomic_max_double(double* addr, double v) {  // v >= 0
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double((long long)assumed) >= v) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+
+template<typename P>
+__global__ void stats_kernel(const P* sp, const float* sf, const uint32_t* su, size_t n, const double* target, double* out) {
+  constexpr int VP = VecOf<P>::lanes;
+  __shared__ double sh[AGF_STATS_LEN][8];
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  double v[AGF_STATS_LEN];
+  for (int k = 0; k < AGF_STATS_LEN; k++) v[k] = 0;
+  if (i < n) {
+    double p[3], e[3], ee[3];
+    for (int k = 0; k < 3; k++) {
+      p[k] = double(sp[sidx(SP_POS + k, n, i, VP)]);
+      const double tgt = target ? target[3 * i + k] : double(sf[sidx(SF_RADIO + k, n, i, 4)]);
+      e[k] = p[k] - tgt;
+      ee[k] = double(sf[sidx(SF_KPOS + k, n, i, 4)]) - p[k];
+    }
+    const double vx = double(sp[sidx(SP_VEL + 0, n, i, VP)]), vy = double(sp[sidx(SP_VEL + 1, n, i, VP)]), vz = double(sp[sidx(SP_VEL + 2, n, i, VP)]);
+    const bool finite = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+    const uint32_t fs = su[sidx(SU_BITS, n, i, 4)] & 0x7u;
+    v[AGF_ST_COUNT] = 1;
+    v[AGF_ST_N_PANIC] = fs == AGF_FS_PANIC;
+    v[AGF_ST_N_KILLED] = fs == AGF_FS_KILLED;
+    v[AGF_ST_N_AUTONOMOUS] = fs == AGF_FS_FULLY_AUTONOMOUS;
+    v[AGF_ST_N_NONFINITE] = !finite;
+    if (finite) {
+      const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+      const double en = sqrt(e2), est = sqrt(ee[0] * ee[0] + ee[1] * ee[1] + ee[2] * ee[2]);
+      v[AGF_ST_SUM_EX] = e[0]; v[AGF_ST_SUM_EY] = e[1]; v[AGF_ST_SUM_EZ] = e[2];
+      v[AGF_ST_SUM_E2] = e2; v[AGF_ST_SUM_ENORM] = en;
+      v[AGF_ST_SUM_SPEED] = sqrt(vx * vx + vy * vy + vz * vz);
+      v[AGF_ST_SUM_EST_ERR] = isfinite(est) ? est : 0.0;
+      v[AGF_ST_MAX_ENORM] = en;
+      v[AGF_ST_MAX_EST_ERR] = isfinite(est) ? est : 0.0;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  for (int k = 0; k < AGF_STATS_LEN; k++) {
+    const double r = k >= AGF_ST_MAX_ENORM ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) sh[k][warp] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < AGF_STATS_LEN) {
+    const int k = threadIdx.x;
+    double r = sh[k][0];
+    for (int w = 1; w < nwarp; w++) r = k >= AGF_ST_MAX_ENORM ? fmax(r, sh[k][w]) : r + sh[k][w];
+    if (k >= AGF_ST_MAX_ENORM) atomic_max_double(&out[k], r);
+    else atomicAdd(&out[k], r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------------
+struct Batch {
+  virtual ~Batch() {}
+  virtual int run(uint32_t dt_us, uint32_t nticks) = 0;
+  virtual int get_field(int field, void* dst, size_t first, size_t count) = 0;
+  virtual int set_field(int field, const void* src, size_t first, size_t count) = 0;
+  virtual int set_radio(const uint8_t* raw, size_t first, size_t count, int broadcast) = 0;
+  virtual int set_schedule(const agf_cmd_entry* e, size_t n) = 0;
+  virtual int set_slot(int slot, const uint8_t* raw) = 0;
+  virtual int telemetry(uint8_t* p1, uint8_t* p2, size_t first, size_t count) = 0;
+  virtual int set_wrench(const double* f, const double* t, size_t first, size_t count) = 0;
+  virtual int add_anchor(uint8_t id, const float pos[3]) = 0;
+  virtual int enable_log(uint32_t stride, uint32_t cap) = 0;
+  virtual int read_log(uint64_t rec, double* dst, size_t first, size_t count) = 0;
+  virtual int log_ptr(void** p, size_t* es) = 0;
+  virtual int stats(const double* target, double* dev_out) = 0;
+
+  size_t n = 0;
+  agf_batch_opts opts;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t now_us = 0, ticks = 0, launches = 0;
+  uint64_t log_records = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  size_t events_used = 0;
+
+  int sync() {
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+};
+
+static size_t field_ncomp(int field) {
+  switch (field) {
+    case AGF_F_POSITION: case AGF_F_VELOCITY: case AGF_F_ANGULAR_VELOCITY: case AGF_F_EST_POSITION:
+    case AGF_F_EST_VELOCITY: case AGF_F_EST_ANGULAR_VELOCITY: case AGF_F_ACCELEROMETER: case AGF_F_RATE_GYRO:
+      return 3;
+    case AGF_F_ATTITUDE: case AGF_F_MOTOR_SPEED: case AGF_F_MOTOR_SPEED_CMD: case AGF_F_EST_ATTITUDE:
+    case AGF_F_MOTOR_FORCE: case AGF_F_KF_COUNTERS: case AGF_F_DES_MOTOR_FORCE:
+      return 4;
+    case AGF_F_FLIGHT_STATE: case AGF_F_PANIC_REASON: case AGF_F_CYCLE_COUNTER:
+      return 1;
+    case AGF_F_EST_COVARIANCE:
+      return 81;
+  }
+  return 0;
+}
+static size_t field_elem(int field) {
+  switch (field) {
+    case AGF_F_POSITION: case AGF_F_VELOCITY: case AGF_F_ATTITUDE: case AGF_F_ANGULAR_VELOCITY:
+    case AGF_F_MOTOR_SPEED: case AGF_F_MOTOR_FORCE:
+      return 8;
+    default:
+      return 4;
+  }
+}
+
+template<typename P>
+struct BatchImpl : Batch {
+  typedef typename VecOf<P>::type PV;
+  static constexpr int VP = VecOf<P>::lanes;
+
+  StateArrays<P> st{nullptr, nullptr, nullptr, nullptr};
+  PV* d_pv = nullptr;
+  P* d_ext_force = nullptr;
+  P* d_ext_torque = nullptr;
+  uint32_t* d_tel_counter = nullptr;
+  SchedEntryDev* d_sched = nullptr;
+  std::vector<SchedEntryDev> sched;
+  float4* d_slot_f[AGF_MAX_CMD_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t* d_slot_tf[AGF_MAX_CMD_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  P* d_log = nullptr;
+  uint32_t log_stride = 0, log_cap = 0;
+  uint64_t log_base_tick = 0;
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  double* d_target = nullptr;
+
+  StepShared<P> sh;
+  PlantPV<P> pv_shared;
+  Timing ts;
+  bool per_vehicle = false;
+  std::vector<agf_vehicle_cfg> cfgs;  // 1 or n
+  std::vector<double> tau;            // motor time constants (1 or n)
+  uint32_t c_for_dt_us = 0xFFFFFFFFu;
+  bool uwb = false, hk = true, parity = true;
+
+  ~BatchImpl() override {
+    cudaSetDevice(opts.device);
+    cudaFree(st.sp); cudaFree(st.sf); cudaFree(st.su); cudaFree(st.sc);
+    cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter);
+    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target);
+    for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
+    for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  int ensure_stage(size_t bytes) {
+    if (bytes <= stage_bytes) return AGF_OK;
+    cudaFree(d_stage);
+    d_stage = nullptr;
+    stage_bytes = 0;
+    AGF_CUDA(cudaMalloc(&d_stage, bytes));
+    stage_bytes = bytes;
+    return AGF_OK;
+  }
+
+  FieldCtx<P> ctx() const {
+    FieldCtx<P> c;
+    c.sp = (P*)st.sp; c.sf = (float*)st.sf; c.su = (uint32_t*)st.su; c.sc = (float*)st.sc;
+    c.n = n;
+    c.kF_shared = pv_shared.kF;
+    c.pv = per_vehicle ? (const P*)d_pv : nullptr;
+    return c;
+  }
+
+  // ---- construction --------------------------------------------------------------------------
+  int init(const agf_vehicle_cfg* in, size_t n_cfgs, size_t n_vehicles, const agf_batch_opts& o) {
+    n = n_vehicles;
+    opts = o;
+    parity = (o.math == AGF_MATH_PARITY);
+    hk = parity || o.telemetry_warnings != 0;
+    uwb = o.uwb_comm_period > 0;
+    cfgs.assign(in, in + n_cfgs);
+    per_vehicle = n_cfgs > 1;
+    const agf_vehicle_cfg& c0 = cfgs[0];
+    if (per_vehicle) {
+      for (size_t i = 0; i < n_cfgs; i++) {
+        const agf_vehicle_cfg& c = cfgs[i];
+        bool ok = memcmp(&c.logic, &c0.logic, sizeof(c.logic)) == 0 && c.arm_length == c0.arm_length &&
+                  memcmp(c.com_error, c0.com_error, sizeof(c.com_error)) == 0 &&
+                  c.motor_min_speed == c0.motor_min_speed && c.motor_max_speed == c0.motor_max_speed &&
+                  c.motor_inertia == c0.motor_inertia &&
+                  memcmp(c.lin_drag_coeff_b, c0.lin_drag_coeff_b, sizeof(c.lin_drag_coeff_b)) == 0;
+        for (int r = 0; r < 3 && ok; r++)
+          for (int q = 0; q < 3; q++)
+            if (r != q && c.inertia[3 * r + q] != 0.0) ok = false;
+        if (!ok)
+          return fail(AGF_EUNSUPPORTED,
+                      "per-vehicle configs may differ only in mass, diagonal inertia, prop thrust/torque constants and "
+                      "motor time constant (one airframe type per batch)");
+      }
+    }
+    for (const auto& c : cfgs) {
+      if (!(c.prop_thrust_from_speed_sqr >= 0) || !(c.prop_torque_from_speed_sqr >= 0) ||
+          !(c.motor_max_speed > c.motor_min_speed))  // the asserts of Motor.cpp:27-29
+        return fail(AGF_EINVAL, "motor constants violate the reference's constructor assertions (Motor.cpp:27-29)");
+    }
+    // shared parameters
+    build_shared(c0, o.onboard_logic_period, o.uwb_comm_period, sh);
+    set_noise_params(o.seed, o.sigma_gyro, o.sigma_acc, o.bias_sigma_gyro, o.bias_sigma_acc, o.uwb_noise_std_dev);
+    // shared plant
+    fill_plant(c0, pv_shared);
+    tau.resize(cfgs.size());
+    for (size_t i = 0; i < cfgs.size(); i++) tau[i] = cfgs[i].motor_time_const;
+    memset(&ts, 0, sizeof(ts));
+
+    // device allocations
+    AGF_CUDA(cudaMalloc(&st.sp, sizeof(PV) * (NP_PAD / VP) * n));
+    AGF_CUDA(cudaMalloc(&st.sf, sizeof(float4) * (NF_PAD / 4) * n));
+    AGF_CUDA(cudaMalloc(&st.su, sizeof(uint4) * (NU_PAD / 4) * n));
+    if (uwb) AGF_CUDA(cudaMalloc(&st.sc, sizeof(float4) * (NC_PAD / 4) * n));
+    AGF_CUDA(cudaMalloc(&d_tel_counter, sizeof(uint32_t) * n));
+    AGF_CUDA(cudaMemsetAsync(d_tel_counter, 0, sizeof(uint32_t) * n, stream));
+    if (per_vehicle) AGF_CUDA(cudaMalloc(&d_pv, sizeof(PV) * (NPV_PAD / VP) * n));
+    return init_state();
+  }
+
+  void set_noise_params(uint64_t seed, double sg, double sa, double bg, double ba, double su_) {
+    sh.seed = seed;
+    sh.sigma_gyro = float(sg);
+    sh.sigma_acc = float(sa);
+    sh.bias_sigma_gyro = float(bg);
+    sh.bias_sigma_acc = float(ba);
+    sh.uwb_sigma = float(su_);
+    sh.bias_on = (bg != 0.0 || ba != 0.0) ? 1 : 0;
+    sh.noise_on = (sg != 0.0 || sa != 0.0 || sh.bias_on) ? 1 : 0;
+    sh.uwb_noise_on = su_ != 0.0 ? 1 : 0;
+  }
+
+  // constructor-time state (SimulationObject6DOF.hpp:14-19, QuadcopterLogic::ResetCounters/Initialise,
+  // KalmanFilter6DOF::Reset) replicated for every vehicle
+  int init_state() {
+    std::vector<P> hp;
+    std::vector<float> hf, hc;
+    std::vector<uint32_t> hu;
+    initial_state<P>(n, sh.logic, cfgs[0].logic.low_battery_threshold, uwb, hp, hf, hu, hc);
+    AGF_CUDA(cudaMemcpyAsync(st.sp, hp.data(), hp.size() * sizeof(P), cudaMemcpyHostToDevice, stream));
+    AGF_CUDA(cudaMemcpyAsync(st.sf, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    AGF_CUDA(cudaMemcpyAsync(st.su, hu.data(), hu.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    if (uwb) AGF_CUDA(cudaMemcpyAsync(st.sc, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  int refresh_motor_c(uint32_t dt_us) {
+    if (dt_us == c_for_dt_us) return AGF_OK;
+    pv_shared.motor_c = P(motor_c_host(tau[0], dt_us));
+    if (per_vehicle) {
+      std::vector<P> h(size_t(NPV_PAD) * n, P(0));
+      for (size_t i = 0; i < n; i++) {
+        const agf_vehicle_cfg& c = cfgs[i];
+        double I[9] = {c.inertia[0], 0, 0, 0, c.inertia[4], 0, 0, 0, c.inertia[8]}, inv[9];
+        inverse3(I, inv);
+        h[sidx(PV_MASS, n, i, VP)] = P(c.mass);
+        h[sidx(PV_IXX, n, i, VP)] = P(c.inertia[0]);
+        h[sidx(PV_IYY, n, i, VP)] = P(c.inertia[4]);
+        h[sidx(PV_IZZ, n, i, VP)] = P(c.inertia[8]);
+        h[sidx(PV_IIXX, n, i, VP)] = P(inv[0]);
+        h[sidx(PV_IIYY, n, i, VP)] = P(inv[4]);
+        h[sidx(PV_IIZZ, n, i, VP)] = P(inv[8]);
+        h[sidx(PV_KF, n, i, VP)] = P(c.prop_thrust_from_speed_sqr);
+        h[sidx(PV_KTAU, n, i, VP)] = P(c.prop_torque_from_speed_sqr);
+        h[sidx(PV_MOTOR_C, n, i, VP)] = P(motor_c_host(tau[i], dt_us));
+      }
+      AGF_CUDA(cudaMemcpyAsync(d_pv, h.data(), h.size() * sizeof(P), cudaMemcpyHostToDevice, stream));
+      AGF_CUDA(cudaStreamSynchronize(stream));
+    }
+    c_for_dt_us = dt_us;
+    return AGF_OK;
+  }
+
+  // ---- stepping ------------------------------------------------------------------------------
+  int launch(uint32_t dt_us, uint32_t nticks) {
+    StepLaunch<P> L;
+    memset(&L, 0, sizeof(L));
+    sh.ext_force = d_ext_force;
+    sh.ext_torque = d_ext_torque;
+    L.sh = sh;
+    L.st = st;
+    L.pv = per_vehicle ? d_pv : nullptr;
+    L.pv_shared = pv_shared;
+    L.n = n;
+    L.tick0 = ticks;
+    L.nticks = nticks;
+    L.dt_us = dt_us;
+    L.ts = ts;
+    L.sched = d_sched;
+    // entries of this launch: [begin, end) with tick in [ticks, ticks + nticks)
+    auto lo = std::lower_bound(sched.begin(), sched.end(), ticks, [](const SchedEntryDev& e, uint64_t t) { return e.tick < t; });
+    auto hi = std::lower_bound(sched.begin(), sched.end(), ticks + nticks, [](const SchedEntryDev& e, uint64_t t) { return e.tick < t; });
+    L.sched_begin = uint32_t(lo - sched.begin());
+    L.sched_end = uint32_t(hi - sched.begin());
+    for (auto it = lo; it != hi; ++it)
+      if (it->slot >= 0 && !d_slot_f[it->slot]) return fail(AGF_EINVAL, "schedule references a command slot that was never set");
+    for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { L.slots[s].f = d_slot_f[s]; L.slots[s].tf = d_slot_tf[s]; }
+    L.log = d_log;
+    L.log_stride = log_stride ? log_stride : 1;
+    L.log_capacity = log_cap ? log_cap : 1;
+    L.first_global_index = opts.first_global_index;
+
+    if (events_used == events.size()) {
+      cudaEvent_t a, b;
+      AGF_CUDA(cudaEventCreate(&a));
+      AGF_CUDA(cudaEventCreate(&b));
+      events.push_back({a, b});
+    }
+    const int block = opts.block_threads > 0 ? std::min(opts.block_threads, AGF_BLOCK_THREADS) : AGF_BLOCK_THREADS;
+    AGF_CUDA(cudaEventRecord(events[events_used].first, stream));
+    cudaError_t e = do_launch(L, block);
+    if (e != cudaSuccess) return fail(AGF_ECUDA, "step kernel launch", e);
+    AGF_CUDA(cudaEventRecord(events[events_used].second, stream));
+    events_used++;
+    launches++;
+    // carry the clock-only stopwatches across the launch with the same function the device uses
+    for (uint32_t t = 0; t < nticks; t++) {
+      const TickPlan p = timing_plan(ts, sh.tc);
+      timing_advance(ts, sh.tc, p, dt_us);
+    }
+    if (d_log) log_records = (ticks + nticks) / log_stride - log_base_tick / log_stride;
+    ticks += nticks;
+    now_us += uint64_t(dt_us) * nticks;
+    return AGF_OK;
+  }
+
+  cudaError_t do_launch(const StepLaunch<P>& L, int block);
+
+  int run(uint32_t dt_us, uint32_t nticks) override {
+    if (dt_us == 0) return fail(AGF_EINVAL, "dt_us must be > 0");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    while (nticks) {
+      // the plant step of the first tick integrates over the time since the previous Run(); the motor lag
+      // coefficient exp(-dt/tau) is a launch constant, so a launch never mixes two different dt
+      const uint32_t first_dt = ts.integ_age;
+      uint32_t chunk = nticks, c_dt = dt_us;
+      if (first_dt != 0 && first_dt != dt_us) {
+        chunk = 1;
+        c_dt = first_dt;
+      }
+      int rc = refresh_motor_c(c_dt);
+      if (rc) return rc;
+      rc = launch(dt_us, chunk);
+      if (rc) return rc;
+      nticks -= chunk;
+    }
+    return AGF_OK;
+  }
+
+  // ---- field access --------------------------------------------------------------------------
+  int get_field(int field, void* dst, size_t first, size_t count) override {
+    const size_t nc = field_ncomp(field);
+    if (!nc) return fail(AGF_EINVAL, "unknown field");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    const size_t bytes = count * nc * field_elem(field);
+    int rc = ensure_stage(bytes);
+    if (rc) return rc;
+    if (field == AGF_F_EST_COVARIANCE && !uwb) {
+      // no ranging: the covariance stays at its Reset() value (KalmanFilter6DOF.cpp:42-61)
+      float* o = (float*)dst;
+      const float sp = 3.0f, sperp = 10.0f * float(M_PI) / 180.0f, sabout = 30.0f * float(M_PI) / 180.0f;
+      for (size_t v = 0; v < count; v++) {
+        float* m = o + 81 * v;
+        memset(m, 0, 81 * sizeof(float));
+        for (int k = 0; k < 6; k++) m[9 * k + k] = sp * sp;
+        m[9 * 6 + 6] = m[9 * 7 + 7] = sperp * sperp;
+        m[9 * 8 + 8] = sabout * sabout;
+      }
+      return AGF_OK;
+    }
+    const size_t total = count * nc;
+    field_get_kernel<P><<<unsigned((total + 255) / 256), 256, 0, stream>>>(ctx(), field, int(nc), first, count, d_stage);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaMemcpyAsync(dst, d_stage, bytes, cudaMemcpyDeviceToHost, stream));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  int set_field(int field, const void* src, size_t first, size_t count) override {
+    switch (field) {
+      case AGF_F_POSITION: case AGF_F_VELOCITY: case AGF_F_ATTITUDE: case AGF_F_ANGULAR_VELOCITY:
+      case AGF_F_MOTOR_SPEED: case AGF_F_MOTOR_SPEED_CMD: case AGF_F_EST_POSITION: case AGF_F_EST_VELOCITY:
+      case AGF_F_EST_ATTITUDE: case AGF_F_EST_ANGULAR_VELOCITY:
+        break;
+      default:
+        return fail(AGF_EINVAL, "field is read-only or unknown");
+    }
+    const size_t nc = field_ncomp(field);
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    const size_t bytes = count * nc * field_elem(field);
+    int rc = ensure_stage(bytes);
+    if (rc) return rc;
+    AGF_CUDA(cudaMemcpyAsync(d_stage, src, bytes, cudaMemcpyHostToDevice, stream));
+    const size_t total = count * nc;
+    field_set_kernel<P><<<unsigned((total + 255) / 256), 256, 0, stream>>>(ctx(), field, int(nc), first, count, d_stage);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  // ---- radio -----------------------------------------------------------------------------------
+  static RadioNow decode_now(const uint8_t* raw) {
+    RadioNow m;
+    uint8_t type, flags;
+    float f[AGF_RADIO_NUM_FLOATS];
+    agf_radio_decode(raw, &type, &flags, f);
+    m.type = type;
+    m.flags = flags;
+    for (int k = 0; k < 4; k++) m.f[k] = f[k];
+    return m;
+  }
+
+  int set_radio(const uint8_t* raw, size_t first, size_t count, int broadcast) override {
+    if (!raw) return fail(AGF_EINVAL, "raw is null");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    RadioNow one;
+    memset(&one, 0, sizeof(one));
+    const RadioNow* per = nullptr;
+    if (broadcast) {
+      one = decode_now(raw);
+    } else {
+      std::vector<RadioNow> h(count);
+      for (size_t i = 0; i < count; i++) h[i] = decode_now(raw + i * AGF_RADIO_PACKET_SIZE);
+      int rc = ensure_stage(count * sizeof(RadioNow));
+      if (rc) return rc;
+      AGF_CUDA(cudaMemcpyAsync(d_stage, h.data(), count * sizeof(RadioNow), cudaMemcpyHostToDevice, stream));
+      AGF_CUDA(cudaStreamSynchronize(stream));
+      per = (const RadioNow*)d_stage;
+    }
+    radio_now_kernel<<<unsigned((count + 255) / 256), 256, 0, stream>>>((float*)st.sf, (uint32_t*)st.su, n, first, count, broadcast,
+                                                                      one, per, sh.logic.mon_cmd_coef, hk ? 1 : 0);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    if (!broadcast) AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  int set_schedule(const agf_cmd_entry* e, size_t ne) override {
+    std::vector<SchedEntryDev> v(ne);
+    for (size_t i = 0; i < ne; i++) {
+      if (i && e[i].tick <= e[i - 1].tick) return fail(AGF_EINVAL, "schedule must be strictly increasing in tick");
+      if (e[i].slot >= AGF_MAX_CMD_SLOTS) return fail(AGF_EINVAL, "schedule slot out of range");
+      memset(&v[i], 0, sizeof(v[i]));
+      v[i].tick = e[i].tick;
+      v[i].slot = e[i].slot < 0 ? -1 : e[i].slot;
+      if (e[i].slot < 0) {
+        const RadioNow m = decode_now(e[i].raw);
+        v[i].type = m.type;
+        v[i].flags = m.flags;
+        for (int k = 0; k < 4; k++) v[i].f[k] = m.f[k];
+      }
+    }
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_sched);
+    d_sched = nullptr;
+    sched.swap(v);
+    if (ne) {
+      AGF_CUDA(cudaMalloc(&d_sched, ne * sizeof(SchedEntryDev)));
+      AGF_CUDA(cudaMemcpyAsync(d_sched, sched.data(), ne * sizeof(SchedEntryDev), cudaMemcpyHostToDevice, stream));
+      AGF_CUDA(cudaStreamSynchronize(stream));
+    }
+    return AGF_OK;
+  }
+
+  int set_slot(int slot, const uint8_t* raw) override {
+    if (slot < 0 || slot >= AGF_MAX_CMD_SLOTS) return fail(AGF_EINVAL, "slot out of range");
+    if (!raw) return fail(AGF_EINVAL, "raw is null");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    std::vector<float4> hf(n);
+    std::vector<uint32_t> ht(n);
+    for (size_t i = 0; i < n; i++) {
+      const RadioNow m = decode_now(raw + i * AGF_RADIO_PACKET_SIZE);
+      hf[i] = make_float4(m.f[0], m.f[1], m.f[2], m.f[3]);
+      ht[i] = (m.type & 0xFFu) | ((m.flags & 0xFFu) << 8);
+    }
+    if (!d_slot_f[slot]) {
+      AGF_CUDA(cudaMalloc(&d_slot_f[slot], n * sizeof(float4)));
+      AGF_CUDA(cudaMalloc(&d_slot_tf[slot], n * sizeof(uint32_t)));
+    }
+    AGF_CUDA(cudaMemcpyAsync(d_slot_f[slot], hf.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    AGF_CUDA(cudaMemcpyAsync(d_slot_tf[slot], ht.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  int telemetry(uint8_t* p1, uint8_t* p2, size_t first, size_t count) override {
+    if (!p1 || !p2) return fail(AGF_EINVAL, "null packet buffer");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    const size_t bytes = count * AGF_TELEMETRY_PACKET_SIZE;
+    int rc = ensure_stage(2 * bytes);
+    if (rc) return rc;
+    uint8_t* d1 = (uint8_t*)d_stage;
+    uint8_t* d2 = d1 + bytes;
+    telemetry_kernel<<<unsigned((count + 127) / 128), 128, 0, stream>>>((const float*)st.sf, (uint32_t*)st.su, d_tel_counter, n, first,
+                                                                      count, sh.logic.batt_voltage, hk ? 1 : 0, d1, d2);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaMemcpyAsync(p1, d1, bytes, cudaMemcpyDeviceToHost, stream));
+    AGF_CUDA(cudaMemcpyAsync(p2, d2, bytes, cudaMemcpyDeviceToHost, stream));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  int set_wrench(const double* f, const double* t, size_t first, size_t count) override {
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    if (!d_ext_force) {
+      AGF_CUDA(cudaMalloc(&d_ext_force, sizeof(P) * 3 * n));
+      AGF_CUDA(cudaMalloc(&d_ext_torque, sizeof(P) * 3 * n));
+      AGF_CUDA(cudaMemsetAsync(d_ext_force, 0, sizeof(P) * 3 * n, stream));
+      AGF_CUDA(cudaMemsetAsync(d_ext_torque, 0, sizeof(P) * 3 * n, stream));
+    }
+    std::vector<P> h(count);
+    for (int pass = 0; pass < 2; pass++) {
+      const double* src = pass ? t : f;
+      P* dst = pass ? d_ext_torque : d_ext_force;
+      if (!src) continue;
+      for (int k = 0; k < 3; k++) {
+        for (size_t i = 0; i < count; i++) h[i] = P(src[3 * i + k]);
+        AGF_CUDA(cudaMemcpyAsync(dst + size_t(k) * n + first, h.data(), count * sizeof(P), cudaMemcpyHostToDevice, stream));
+        AGF_CUDA(cudaStreamSynchronize(stream));
+      }
+    }
+    return AGF_OK;
+  }
+
+  int add_anchor(uint8_t id, const float pos[3]) override {
+    if (!pos) return fail(AGF_EINVAL, "pos is null");
+    if (sh.n_anchors >= AGF_MAX_UWB_ANCHORS) return fail(AGF_EFULL, "anchor table full (QuadcopterLogic.hpp:224-227)");
+    if (id == 0) return fail(AGF_EINVAL, "anchor id 0 means 'no target' in the reference (UWBRadio.hpp:17-24)");
+    if (!uwb) return fail(AGF_EUNSUPPORTED, "batch was created without a UWB network (uwb_comm_period <= 0)");
+    AnchorDev& a = sh.anchors[sh.n_anchors++];
+    a.id = id;
+    a.x = pos[0]; a.y = pos[1]; a.z = pos[2];
+    sh.tc.n_anchors = int(sh.n_anchors);
+    return AGF_OK;
+  }
+
+  // ---- logging -------------------------------------------------------------------------------
+  int enable_log(uint32_t stride, uint32_t cap) override {
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_log);
+    d_log = nullptr;
+    log_stride = log_cap = 0;
+    log_records = 0;
+    if (!stride || !cap) return AGF_OK;  // disable
+    const size_t bytes = sizeof(P) * size_t(cap) * AGF_LOG_FIELDS * n;
+    cudaError_t e = cudaMalloc(&d_log, bytes);
+    if (e != cudaSuccess) {
+      d_log = nullptr;
+      return fail(AGF_ENOMEM, "log ring allocation", e);
+    }
+    log_stride = stride;
+    log_cap = cap;
+    log_base_tick = ticks;
+    return AGF_OK;
+  }
+
+  int read_log(uint64_t rec, double* dst, size_t first, size_t count) override {
+    if (!d_log) return fail(AGF_EINVAL, "logging is not enabled");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (rec >= log_records || rec + log_cap < log_records) return fail(AGF_ERANGE, "record not in the ring");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    // absolute record index in the kernel's numbering
+    const uint64_t abs_rec = log_base_tick / log_stride + rec;
+    std::vector<P> h(count);
+    for (int f = 0; f < AGF_LOG_FIELDS; f++) {
+      const P* src = d_log + (size_t(abs_rec % log_cap) * AGF_LOG_FIELDS + f) * n + first;
+      AGF_CUDA(cudaMemcpyAsync(h.data(), src, count * sizeof(P), cudaMemcpyDeviceToHost, stream));
+      AGF_CUDA(cudaStreamSynchronize(stream));
+      for (size_t i = 0; i < count; i++) dst[i * AGF_LOG_FIELDS + f] = double(h[i]);
+    }
+    return AGF_OK;
+  }
+
+  int log_ptr(void** p, size_t* es) override {
+    if (p) *p = d_log;
+    if (es) *es = sizeof(P);
+    return d_log ? AGF_OK : fail(AGF_EINVAL, "logging is not enabled");
+  }
+
+  int stats(const double* target, double* dev_out) override {
+    AGF_CUDA(cudaSetDevice(opts.device));
+    const double* dt = nullptr;
+    if (target) {
+      if (!d_target) AGF_CUDA(cudaMalloc(&d_target, sizeof(double) * 3 * n));
+      AGF_CUDA(cudaMemcpyAsync(d_target, target, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream));
+      dt = d_target;
+    }
+    AGF_CUDA(cudaMemsetAsync(dev_out, 0, sizeof(double) * AGF_STATS_LEN, stream));
+    stats_kernel<P><<<unsigned((n + 255) / 256), 256, 0, stream>>>((const P*)st.sp, (const float*)st.sf, (const uint32_t*)st.su, n, dt, dev_out);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    return AGF_OK;
+  }
+};
+
+template<>
+cudaError_t BatchImpl<double>::do_launch(const StepLaunch<double>& L, int block) {
+  if (parity) return launch_step_parity(L, uwb, block, stream);
+  return launch_step_fast_f64(L, uwb, hk, block, stream);
+}
+template<>
+cudaError_t BatchImpl<float>::do_launch(const StepLaunch<float>& L, int block) {
+  return launch_step_fast_f32(L, uwb, hk, block, stream);
+}
+
+}  // namespace agf
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using agf::Batch;
+using agf::fail;
+
+static Batch* B(agf_batch* b) { return reinterpret_cast<Batch*>(b); }
+static const Batch* B(const agf_batch* b) { return reinterpret_cast<const Batch*>(b); }
+
+extern "C" {
+
+void agf_batch_opts_default(agf_batch_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->device = 0;
+  o->precision = AGF_PREC_FP64;
+  o->math = AGF_MATH_PARITY;
+  o->block_threads = 0;
+  o->onboard_logic_period = 1.0 / 500.0;
+  o->uwb_comm_period = 0.0;
+  o->sigma_acc = 0.2;   // Quadcopter_T.cpp:5
+  o->sigma_gyro = 0.1;  // Quadcopter_T.cpp:6
+  o->seed = 1;
+  o->telemetry_warnings = 1;
+}
+
+int agf_batch_create(const agf_vehicle_cfg* cfgs, size_t n_cfgs, size_t n_vehicles, const agf_batch_opts* opts,
+                     agf_batch** out) {
+  if (!out) return fail(AGF_EINVAL, "out is null");
+  *out = nullptr;
+  if (!cfgs || !opts) return fail(AGF_EINVAL, "cfgs/opts is null");
+  if (n_vehicles == 0) return fail(AGF_EINVAL, "n_vehicles must be > 0");
+  if (n_cfgs != 1 && n_cfgs != n_vehicles) return fail(AGF_EINVAL, "n_cfgs must be 1 or n_vehicles");
+  if (opts->precision != AGF_PREC_FP64 && opts->precision != AGF_PREC_FP32) return fail(AGF_EINVAL, "bad precision");
+  if (opts->precision == AGF_PREC_FP32 && opts->math == AGF_MATH_PARITY)
+    return fail(AGF_EUNSUPPORTED, "parity arithmetic exists for the reference's own precision (AGF_PREC_FP64) only");
+  if (!(opts->onboard_logic_period > 0)) return fail(AGF_EINVAL, "onboard_logic_period must be > 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(AGF_ENODEVICE, "no CUDA device available: agrifly_b200 has no CPU execution path");
+  }
+  if (opts->device < 0 || opts->device >= ndev) return fail(AGF_EINVAL, "device ordinal out of range");
+  e = cudaSetDevice(opts->device);
+  if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaSetDevice", e);
+  Batch* b = nullptr;
+  if (opts->precision == AGF_PREC_FP64) {
+    b = new (std::nothrow) agf::BatchImpl<double>();
+  } else {
+    b = new (std::nothrow) agf::BatchImpl<float>();
+  }
+  if (!b) return fail(AGF_ENOMEM, "host allocation");
+  b->opts = *opts;
+  if (opts->stream) {
+    b->stream = (cudaStream_t)opts->stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete b;
+      return fail(AGF_ECUDA, "cudaStreamCreate", e);
+    }
+    b->own_stream = true;
+  }
+  int rc = opts->precision == AGF_PREC_FP64
+               ? static_cast<agf::BatchImpl<double>*>(b)->init(cfgs, n_cfgs, n_vehicles, *opts)
+               : static_cast<agf::BatchImpl<float>*>(b)->init(cfgs, n_cfgs, n_vehicles, *opts);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  *out = reinterpret_cast<agf_batch*>(b);
+  return AGF_OK;
+}
+
+int agf_batch_destroy(agf_batch* b) {
+  if (!b) return AGF_OK;
+  cudaSetDevice(B(b)->opts.device);
+  cudaStreamSynchronize(B(b)->stream);
+  delete B(b);
+  return AGF_OK;
+}
+
+size_t agf_batch_size(const agf_batch* b) { return b ? B(b)->n : 0; }
+void* agf_batch_stream(const agf_batch* b) { return b ? (void*)B(b)->stream : nullptr; }
+int agf_batch_run(agf_batch* b, uint32_t dt_us, uint32_t nticks) { return b ? B(b)->run(dt_us, nticks) : fail(AGF_EINVAL, "null handle"); }
+int agf_batch_sync(agf_batch* b) { return b ? B(b)->sync() : fail(AGF_EINVAL, "null handle"); }
+uint64_t agf_batch_time_us(const agf_batch* b) { return b ? B(b)->now_us : 0; }
+uint64_t agf_batch_ticks(const agf_batch* b) { return b ? B(b)->ticks : 0; }
+
+int agf_batch_get_field(agf_batch* b, int field, void* dst, size_t first, size_t count) {
+  if (!b || !dst) return fail(AGF_EINVAL, "null argument");
+  return B(b)->get_field(field, dst, first, count);
+}
+int agf_batch_set_field(agf_batch* b, int field, const void* src, size_t first, size_t count) {
+  if (!b || !src) return fail(AGF_EINVAL, "null argument");
+  return B(b)->set_field(field, src, first, count);
+}
+size_t agf_field_size(int field) { return agf::field_ncomp(field) * agf::field_elem(field); }
+
+int agf_batch_set_radio_cmd(agf_batch* b, const uint8_t* raw, size_t first, size_t count, int broadcast) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->set_radio(raw, first, count, broadcast);
+}
+int agf_batch_set_cmd_schedule(agf_batch* b, const agf_cmd_entry* e, size_t n) {
+  if (!b || (n && !e)) return fail(AGF_EINVAL, "null argument");
+  return B(b)->set_schedule(e, n);
+}
+int agf_batch_set_cmd_slot(agf_batch* b, int slot, const uint8_t* raw) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->set_slot(slot, raw);
+}
+int agf_batch_get_telemetry(agf_batch* b, uint8_t* p1, uint8_t* p2, size_t first, size_t count) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->telemetry(p1, p2, first, count);
+}
+int agf_batch_set_external_wrench(agf_batch* b, const double* f, const double* t, size_t first, size_t count) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->set_wrench(f, t, first, count);
+}
+int agf_batch_add_uwb_anchor(agf_batch* b, uint8_t id, const float pos[3]) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->add_anchor(id, pos);
+}
+int agf_batch_set_noise(agf_batch* b, uint64_t seed, double sg, double sa, double bg, double ba) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  if (B(b)->opts.precision == AGF_PREC_FP64) {
+    auto* x = static_cast<agf::BatchImpl<double>*>(B(b));
+    x->set_noise_params(seed, sg, sa, bg, ba, x->opts.uwb_noise_std_dev);
+  } else {
+    auto* x = static_cast<agf::BatchImpl<float>*>(B(b));
+    x->set_noise_params(seed, sg, sa, bg, ba, x->opts.uwb_noise_std_dev);
+  }
+  return AGF_OK;
+}
+int agf_batch_enable_log(agf_batch* b, uint32_t stride, uint32_t cap) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->enable_log(stride, cap);
+}
+uint64_t agf_batch_log_count(const agf_batch* b) { return b ? B(b)->log_records : 0; }
+int agf_batch_read_log(agf_batch* b, uint64_t rec, double* dst, size_t first, size_t count) {
+  if (!b || !dst) return fail(AGF_EINVAL, "null argument");
+  return B(b)->read_log(rec, dst, first, count);
+}
+int agf_batch_log_device_ptr(agf_batch* b, void** p, size_t* es) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  return B(b)->log_ptr(p, es);
+}
+int agf_batch_reduce_stats_device(agf_batch* b, const double* target, double* dev_out) {
+  if (!b || !dev_out) return fail(AGF_EINVAL, "null argument");
+  return B(b)->stats(target, dev_out);
+}
+int agf_batch_reduce_stats(agf_batch* b, const double* target, double* host_out) {
+  if (!b || !host_out) return fail(AGF_EINVAL, "null argument");
+  cudaSetDevice(B(b)->opts.device);
+  double* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double) * AGF_STATS_LEN);
+  if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaMalloc", e);
+  int rc = B(b)->stats(target, d);
+  if (!rc) {
+    e = cudaMemcpyAsync(host_out, d, sizeof(double) * AGF_STATS_LEN, cudaMemcpyDeviceToHost, B(b)->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(B(b)->stream);
+    if (e != cudaSuccess) rc = fail(AGF_ECUDA, "stats copy", e);
+  }
+  cudaFree(d);
+  return rc;
+}
+
+uint64_t agf_batch_launch_count(const agf_batch* b) { return b ? B(b)->launches : 0; }
+
+int agf_batch_step_kernel_time(agf_batch* b, double* ms, uint64_t* launches) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  Batch* x = B(b);
+  cudaSetDevice(x->opts.device);
+  cudaError_t e = cudaStreamSynchronize(x->stream);
+  if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaStreamSynchronize", e);
+  double total = 0;
+  for (size_t i = 0; i < x->events_used; i++) {
+    float t = 0;
+    e = cudaEventElapsedTime(&t, x->events[i].first, x->events[i].second);
+    if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaEventElapsedTime", e);
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = x->events_used;
+  x->events_used = 0;
+  return AGF_OK;
+}
+
+const char* agf_last_error_string(void) { return agf::g_last_error.c_str(); }
+
+const char* agf_build_info(void) {
+  static char buf[4096];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int o = snprintf(buf, sizeof(buf), "agrifly_b200 %d.%d sm_100a block=%d | ", AGF_VERSION_MAJOR, AGF_VERSION_MINOR, AGF_BLOCK_THREADS);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+      agf::kernel_attrs_parity(buf + o, sizeof(buf) - o);
+      o = int(strlen(buf));
+      agf::kernel_attrs_fast_f64(buf + o, sizeof(buf) - o);
+      o = int(strlen(buf));
+      agf::kernel_attrs_fast_f32(buf + o, sizeof(buf) - o);
+    } else {
+      cudaGetLastError();
+      snprintf(buf + o, sizeof(buf) - o, "no CUDA device visible");
+    }
+  });
+  return buf;
+}
+
+}  // extern "C"

@@ -1,0 +1,1102 @@
+// agf_step.cuh -- the per-vehicle simulation step as sm_100a device code.
+//
+// One vehicle per thread, the whole vehicle state in registers across all ticks of a launch;
+// state and per-vehicle parameters live in HBM as structure-of-arrays of 16-byte quads
+// (float4 / double2 / uint4), so every load/store instruction of a warp is a run of fully
+// coalesced 128-bit accesses; parameters shared by the population ride in the kernel-parameter
+// constant bank (broadcast reads).
+//
+// What is computed (reference file:line, paths under Components/Components/ unless noted):
+//   motors         Simulation/Motor.cpp:39-84
+//   rigid body     Simulation/Quadcopter_T.cpp:86-156
+//   IMU synthesis  Simulation/Quadcopter_T.cpp:159-183
+//   IMU intake     Logic/QuadcopterLogic.hpp:32-59  (+ Common/Common/Math/LowPassFilterSecondOrder.hpp:51-63)
+//   estimator      Logic/KalmanFilter6DOF.cpp:33-309
+//   state machine  Logic/QuadcopterLogic.cpp:164-391
+//   controllers    Logic/QuadcopterLogic.cpp:393-588, Logic/Quadcopter{Position,Attitude,AngularVelocity}Controller.hpp,
+//                  Logic/QuadcopterMixer.hpp:63-99
+//   UWB exchange   Simulation/Quadcopter_T.cpp:191-199, Simulation/UWBNetwork.cpp:22-89
+//   time base      Common/Common/Time/Timer.hpp:27-53 (integer microseconds)
+//
+// Template axes:  P = plant real (double = the reference's mixed precision, float = FP32 mode);
+// PARITY = bit-comparable arithmetic (TU compiled with -fmad=false, agf_math.h libm) vs fast;
+// UWB = the vehicle ranges against anchors, so the 9x9 covariance is live (81 more registers);
+// HK = full housekeeping (telemetry warnings, battery/temperature filters, rate monitors,
+// propeller calibration).
+//
+// The EKF covariance algebra exploits the structural zeros/ones of the transition matrix f and of
+// the measurement row H but keeps the reference's sequential-k summation order for the remaining
+// terms, so it is bit-identical to the dense products of KalmanFilter6DOF.cpp:232,267-269,296
+// for finite inputs (adding an exact +-0 never changes a sum); tests/test_parity_gpu.py checks it.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agf_math.h"
+#include "agf_types.h"
+#include "agf_launch.h"
+
+namespace agf {
+
+#define AGF_DEV __host__ __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------
+// libm policy
+// ---------------------------------------------------------------------------------------------
+template<bool PARITY>
+struct Mf;
+template<>
+struct Mf<true> {
+  static AGF_DEV float sin(float x) { return agf_sinf(x); }
+  static AGF_DEV float cos(float x) { return agf_cosf(x); }
+  static AGF_DEV float asin(float x) { return agf_asinf(x); }
+  static AGF_DEV float acos(float x) { return agf_acosf(x); }
+  static AGF_DEV float atan2(float y, float x) { return agf_atan2f(y, x); }
+  static AGF_DEV double sin(double x) { return agf_sin(x); }
+  static AGF_DEV double cos(double x) { return agf_cos(x); }
+};
+template<>
+struct Mf<false> {
+  static AGF_DEV float sin(float x) { return ::sinf(x); }
+  static AGF_DEV float cos(float x) { return ::cosf(x); }
+  static AGF_DEV float asin(float x) { return ::asinf(x); }
+  static AGF_DEV float acos(float x) { return ::acosf(x); }
+  static AGF_DEV float atan2(float y, float x) { return ::atan2f(y, x); }
+  static AGF_DEV double sin(double x) { return ::sin(x); }
+  static AGF_DEV double cos(double x) { return ::cos(x); }
+};
+AGF_DEV float rsqrt_(float x) { return ::sqrtf(x); }
+AGF_DEV double rsqrt_(double x) { return ::sqrt(x); }
+AGF_DEV float rabs_(float x) { return ::fabsf(x); }
+AGF_DEV double rabs_(double x) { return ::fabs(x); }
+
+// ---------------------------------------------------------------------------------------------
+// Vec3 / Rotation with the reference's operation order
+// (Common/Common/Math/Vec3.hpp, Common/Common/Math/Rotation.hpp)
+// ---------------------------------------------------------------------------------------------
+template<typename R>
+struct V3 {
+  R x, y, z;
+  AGF_DEV V3() {}
+  AGF_DEV V3(R a, R b, R c) : x(a), y(b), z(c) {}
+};
+template<typename R> AGF_DEV V3<R> operator+(const V3<R>& a, const V3<R>& b) { return V3<R>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template<typename R> AGF_DEV V3<R> operator-(const V3<R>& a, const V3<R>& b) { return V3<R>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template<typename R> AGF_DEV V3<R> operator*(R s, const V3<R>& v) { return V3<R>(s * v.x, s * v.y, s * v.z); }
+template<typename R> AGF_DEV V3<R> operator*(const V3<R>& v, R s) { return V3<R>(s * v.x, s * v.y, s * v.z); }
+template<typename R> AGF_DEV V3<R> operator/(const V3<R>& v, R s) { return V3<R>(v.x / s, v.y / s, v.z / s); }
+template<typename R> AGF_DEV R dot(const V3<R>& a, const V3<R>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template<typename R> AGF_DEV V3<R> cross(const V3<R>& a, const V3<R>& b) {
+  return V3<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template<typename R> AGF_DEV R norm(const V3<R>& a) { return rsqrt_(dot(a, a)); }
+
+// Matrix<Real,3,3> * Vec3 (Vec3.hpp:202-210): accumulate from 0 in column order
+template<typename R>
+AGF_DEV V3<R> matvec(const R* m, const V3<R>& v) {
+  R o0 = R(0), o1 = R(0), o2 = R(0);
+  o0 += m[0] * v.x; o0 += m[1] * v.y; o0 += m[2] * v.z;
+  o1 += m[3] * v.x; o1 += m[4] * v.y; o1 += m[5] * v.z;
+  o2 += m[6] * v.x; o2 += m[7] * v.y; o2 += m[8] * v.z;
+  return V3<R>(o0, o1, o2);
+}
+
+template<typename R>
+struct Q4 {
+  R w, x, y, z;
+  AGF_DEV Q4() {}
+  AGF_DEV Q4(R a, R b, R c, R d) : w(a), x(b), y(c), z(d) {}
+};
+template<typename R> AGF_DEV Q4<R> qinv(const Q4<R>& q) { return Q4<R>(q.w, -q.x, -q.y, -q.z); }
+// Rotation::operator* (Rotation.hpp:124-131): a * r1
+template<typename R>
+AGF_DEV Q4<R> qmul(const Q4<R>& a, const Q4<R>& r1) {
+  R c0 = r1.w * a.w - r1.x * a.x - r1.y * a.y - r1.z * a.z;
+  R c1 = r1.x * a.w + r1.w * a.x + r1.z * a.y - r1.y * a.z;
+  R c2 = r1.y * a.w - r1.z * a.x + r1.w * a.y + r1.x * a.z;
+  R c3 = r1.z * a.w + r1.y * a.x - r1.x * a.y + r1.w * a.z;
+  return Q4<R>(c0, c1, c2, c3);
+}
+// GetRotationMatrix (Rotation.hpp:196-217)
+template<typename R>
+AGF_DEV void qmatrix(const Q4<R>& q, R* Rm) {
+  const R r0 = q.w * q.w, r1 = q.x * q.x, r2 = q.y * q.y, r3 = q.z * q.z;
+  Rm[0] = r0 + r1 - r2 - r3;
+  Rm[1] = 2 * q.x * q.y - 2 * q.w * q.z;
+  Rm[2] = 2 * q.x * q.z + 2 * q.w * q.y;
+  Rm[3] = 2 * q.x * q.y + 2 * q.w * q.z;
+  Rm[4] = r0 - r1 + r2 - r3;
+  Rm[5] = 2 * q.y * q.z - 2 * q.w * q.x;
+  Rm[6] = 2 * q.x * q.z - 2 * q.w * q.y;
+  Rm[7] = 2 * q.y * q.z + 2 * q.w * q.x;
+  Rm[8] = r0 - r1 - r2 + r3;
+}
+// Rotate (Rotation.hpp:236-245)
+template<typename R>
+AGF_DEV V3<R> qrot(const Q4<R>& q, const V3<R>& in) {
+  R Rm[9];
+  qmatrix(q, Rm);
+  return V3<R>(Rm[0] * in.x + Rm[1] * in.y + Rm[2] * in.z, Rm[3] * in.x + Rm[4] * in.y + Rm[5] * in.z,
+               Rm[6] * in.x + Rm[7] * in.y + Rm[8] * in.z);
+}
+// third row of the rotation matrix applied to e3: (att * (0,0,1)).z, with the exact-zero products kept out
+template<typename R>
+AGF_DEV R qrot_e3_z(const Q4<R>& q) {
+  // Rm[6]*0 + Rm[7]*0 + Rm[8]*1 == Rm[8] for finite Rm
+  return q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z;
+}
+// FromAxisAngle (Rotation.hpp:92-97)
+template<bool PARITY, typename R>
+AGF_DEV Q4<R> q_from_axis_angle(const V3<R>& u, R angle) {
+  const R h = angle * R(0.5);
+  const R s = Mf<PARITY>::sin(h);
+  return Q4<R>(Mf<PARITY>::cos(h), s * u.x, s * u.y, s * u.z);
+}
+// FromRotationVector (Rotation.hpp:84-89); returns false (identity) below MIN_ANGLE
+template<bool PARITY, typename R>
+AGF_DEV bool q_from_rotvec(const V3<R>& rv, Q4<R>& out) {
+  const R theta = norm(rv);
+  if (theta < R(4.84813681e-6)) return false;
+  out = q_from_axis_angle<PARITY>(rv / theta, theta);
+  return true;
+}
+template<bool PARITY, typename R>
+AGF_DEV Q4<R> q_apply_rotvec(const Q4<R>& a, const V3<R>& rv) {  // a * FromRotationVector(rv)
+  Q4<R> d;
+  if (!q_from_rotvec<PARITY>(rv, d)) return a;  // a * Identity == a exactly
+  return qmul(a, d);
+}
+// FromEulerYPR (Rotation.hpp:99-110)
+template<bool PARITY>
+AGF_DEV Q4<float> q_from_euler_ypr(float y, float p, float r) {
+  typedef Mf<PARITY> M;
+  const float h = 0.5f;
+  Q4<float> o;
+  o.w = M::cos(h * y) * M::cos(h * p) * M::cos(h * r) + M::sin(h * y) * M::sin(h * p) * M::sin(h * r);
+  o.x = M::cos(h * y) * M::cos(h * p) * M::sin(h * r) - M::sin(h * y) * M::sin(h * p) * M::cos(h * r);
+  o.y = M::cos(h * y) * M::sin(h * p) * M::cos(h * r) + M::sin(h * y) * M::cos(h * p) * M::sin(h * r);
+  o.z = M::sin(h * y) * M::cos(h * p) * M::cos(h * r) - M::cos(h * y) * M::sin(h * p) * M::sin(h * r);
+  return o;
+}
+// ToVectorPartOfQuaternion / ToRotationVector (Rotation.hpp:144-161)
+template<bool PARITY>
+AGF_DEV V3<float> q_to_rotvec(const Q4<float>& q) {
+  V3<float> n = q.w > 0 ? V3<float>(q.x, q.y, q.z) : V3<float>(-q.x, -q.y, -q.z);
+  const float nn = norm(n);
+  const float angle = Mf<PARITY>::asin(nn) * 2;
+  if (angle < 4.84813681e-6f) return V3<float>(0, 0, 0);
+  return n * (angle / nn);
+}
+// acosf with the reference's errno fallback (KalmanFilter6DOF.cpp:95-103)
+template<bool PARITY>
+AGF_DEV float acos_guarded(float c) {
+  float a = Mf<PARITY>::acos(c);
+  if (c > 1.0f || c < -1.0f) a = c < 0 ? 3.14159274f : 0.0f;  // float(M_PI)
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LowPassFilterSecondOrder::Apply (LowPassFilterSecondOrder.hpp:51-63); st = {xm0, xm1, ym0, ym1}
+// ---------------------------------------------------------------------------------------------
+AGF_DEV float lpf2(const Lpf2Coef& c, float* st, int stride, float in) {
+  float out = c.b2 * in;
+  out = out + (c.b0 * st[0] + c.b1 * st[stride]);
+  out = out + ((-c.a1) * st[2 * stride] - c.a2 * st[3 * stride]);
+  st[0] = st[stride];
+  st[stride] = in;
+  st[2 * stride] = st[3 * stride];
+  st[3 * stride] = out;
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator and Box-Muller normals (replaces the per-object
+// std::default_random_engine of Quadcopter_T.hpp:122-123 and the global mt19937 of UWBNetwork.cpp:4)
+// ---------------------------------------------------------------------------------------------
+AGF_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return uint32_t((uint64_t(a) * uint64_t(b)) >> 32);
+#endif
+}
+AGF_DEV uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+AGF_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = (float(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+  const float u2 = float(b >> 8) * (1.0f / 16777216.0f);           // [0, 1)
+  const float r = ::sqrtf(-2.0f * ::logf(u1));
+#if defined(__CUDA_ARCH__)
+  float s, c;
+  ::sincospif(2.0f * u2, &s, &c);
+#else
+  const float s = ::sinf(6.28318530718f * u2), c = ::cosf(6.28318530718f * u2);
+#endif
+  n0 = r * c;
+  n1 = r * s;
+}
+// 6 standard normals for (vehicle, cycle, stream)
+AGF_DEV void normals6(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream, float* n) {
+  const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
+  const uint4 a = philox4x32_10(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u), key);
+  const uint4 b = philox4x32_10(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u + 1u), key);
+  box_muller(a.x, a.y, n[0], n[1]);
+  box_muller(a.z, a.w, n[2], n[3]);
+  box_muller(b.x, b.y, n[4], n[5]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-resident vehicle state
+// ---------------------------------------------------------------------------------------------
+template<typename P, bool UWB, bool HK>
+struct VState {
+  // plant
+  P pos[3], vel[3], att[4], w[3], ms[4];
+  // logic
+  float cmd[4];      // _desMotorSpeeds == _motorSpeedCommands after every logic run
+  float dforce[4];   // _desMotorForcesForTelemetry
+  float radio_f[4];  // floats[0..3] of the last radio message (the only ones any controller reads)
+  float gyro_lp[12], acc_lp[12];  // [xm0 xm1 ym0 ym1] x 3 components, component-major: [4*c + k]
+  float kpos[3], kvel[3], kw[3], katt[4], kcorr[3];
+  float uwb_range;    // range held by the vehicle's radio (UWBRadio::_meas.range)
+  float logic_range;  // range handed to the logic (QuadcopterLogic::_uwbRangeMeas.range)
+  uint32_t bits;      // see B_* below
+  uint32_t cnt;       // numMeasRejectedSequentially (bits 0-7) | telemetry warnings (bits 24-31)
+  uint32_t cycle;
+  uint32_t kfcnt;     // numResets (lo 16) | numMeasRejected (hi 16)
+  uint32_t uwb_count;
+  uint32_t uwbw;      // anchor indices: network responder | radio meas responder | logic meas target | next target
+  uint32_t age_radio, age_uwb, age_est_reset;
+  // housekeeping (HK)
+  float temp_lp[4], batt_lp[4];
+  float batt_vfilt, mon_cmd_lpdt, mon_loop_lpdt;
+  float pc_accum[4], pc_corr[4];
+  uint32_t pc_count, age_mon_cmd, age_mon_loop;
+  // estimator covariance (UWB)
+  float cov[UWB ? 81 : 1];
+  // radio true position latched at the last logic run (UWBRadio::_uwbTruePosition)
+  P rpos[UWB ? 3 : 1];
+};
+
+// bit layout of VState::bits
+enum : uint32_t {
+  B_FS_SHIFT = 0, B_FS_MASK = 0x7u,            // flight state
+  B_PANIC_SHIFT = 3, B_PANIC_MASK = 0x7u,      // first panic reason
+  B_RTYPE_SHIFT = 6, B_RTYPE_MASK = 0x7u,      // radio message type
+  B_RFLAGS_SHIFT = 9, B_RFLAGS_MASK = 0xFFu,   // radio message flags
+  B_RADIO_NEW = 1u << 17,
+  B_IMU_INIT = 1u << 18,
+  B_UWB_INIT = 1u << 19,
+  B_UWB_NEW = 1u << 20,        // logic's _uwbRangeMeas.isNew
+  B_KF_RESET_SEEN = 1u << 21,  // _numResets != _lastCheckNumResets
+  B_PC_RUNNING = 1u << 22,     // propeller calibration running
+  B_RADIO_MEAS_NEW = 1u << 23  // UWBRadio::_meas.haveNew
+};
+// byte lanes of VState::uwbw
+enum : uint32_t { W_NET_RESP = 0, W_RADIO_RESP = 8, W_LOGIC_TARGET = 16, W_NEXT_TARGET = 24 };
+AGF_DEV uint32_t bget(uint32_t w, uint32_t shift, uint32_t mask) { return (w >> shift) & mask; }
+AGF_DEV uint32_t bset(uint32_t w, uint32_t shift, uint32_t mask, uint32_t v) {
+  return (w & ~(mask << shift)) | ((v & mask) << shift);
+}
+
+// --- flat (de)serialisation order; the host get/set kernels use the same tables (agf_types.h) ---
+template<typename P, bool UWB, bool HK>
+AGF_DEV void state_load(VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i) {
+  typedef typename VecOf<P>::type PV;
+  constexpr int VP = VecOf<P>::lanes;
+  P rp[NP_PAD];
+#pragma unroll
+  for (int q = 0; q < NP_PAD / VP; q++) {
+    PV v = a.sp[size_t(q) * n + i];
+    VecOf<P>::unpack(v, &rp[q * VP]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.pos[k] = rp[SP_POS + k]; s.vel[k] = rp[SP_VEL + k]; s.w[k] = rp[SP_W + k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { s.att[k] = rp[SP_ATT + k]; s.ms[k] = rp[SP_MS + k]; }
+  if (UWB) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) s.rpos[k] = rp[SP_RPOS + k];
+  }
+  float rf[NF_PAD];
+#pragma unroll
+  for (int q = 0; q < NF_PAD / 4; q++) {
+    if (!HK && q >= NF_CORE / 4) break;
+    float4 v = a.sf[size_t(q) * n + i];
+    rf[4 * q] = v.x; rf[4 * q + 1] = v.y; rf[4 * q + 2] = v.z; rf[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { s.cmd[k] = rf[SF_CMD + k]; s.dforce[k] = rf[SF_DFORCE + k]; s.radio_f[k] = rf[SF_RADIO + k]; s.katt[k] = rf[SF_KATT + k]; }
+#pragma unroll
+  for (int k = 0; k < 12; k++) { s.gyro_lp[k] = rf[SF_GYRO_LP + k]; s.acc_lp[k] = rf[SF_ACC_LP + k]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.kpos[k] = rf[SF_KPOS + k]; s.kvel[k] = rf[SF_KVEL + k]; s.kw[k] = rf[SF_KW + k]; s.kcorr[k] = rf[SF_KCORR + k]; }
+  s.uwb_range = rf[SF_UWB_RANGE];
+  s.logic_range = rf[SF_LOGIC_RANGE];
+  if (HK) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) { s.temp_lp[k] = rf[SF_TEMP_LP + k]; s.batt_lp[k] = rf[SF_BATT_LP + k]; s.pc_accum[k] = rf[SF_PC_ACCUM + k]; s.pc_corr[k] = rf[SF_PC_CORR + k]; }
+    s.batt_vfilt = rf[SF_BATT_VFILT]; s.mon_cmd_lpdt = rf[SF_MON_CMD]; s.mon_loop_lpdt = rf[SF_MON_LOOP];
+  }
+  uint32_t ru[NU_PAD];
+#pragma unroll
+  for (int q = 0; q < NU_PAD / 4; q++) {
+    if (!HK && q >= NU_CORE / 4) break;
+    uint4 v = a.su[size_t(q) * n + i];
+    ru[4 * q] = v.x; ru[4 * q + 1] = v.y; ru[4 * q + 2] = v.z; ru[4 * q + 3] = v.w;
+  }
+  s.bits = ru[SU_BITS]; s.cnt = ru[SU_CNT]; s.cycle = ru[SU_CYCLE]; s.kfcnt = ru[SU_KFCNT];
+  s.uwb_count = ru[SU_UWB_COUNT]; s.age_radio = ru[SU_AGE_RADIO]; s.age_uwb = ru[SU_AGE_UWB];
+  s.uwbw = ru[SU_UWBW];
+  if (HK) { s.age_est_reset = ru[SU_AGE_EST_RESET]; s.pc_count = ru[SU_PC_COUNT]; s.age_mon_cmd = ru[SU_AGE_MON_CMD]; s.age_mon_loop = ru[SU_AGE_MON_LOOP]; }
+  if (UWB) {
+#pragma unroll
+    for (int q = 0; q < NC_PAD / 4; q++) {
+      float4 v = a.sc[size_t(q) * n + i];
+      if (4 * q + 0 < 81) s.cov[4 * q + 0] = v.x;
+      if (4 * q + 1 < 81) s.cov[4 * q + 1] = v.y;
+      if (4 * q + 2 < 81) s.cov[4 * q + 2] = v.z;
+      if (4 * q + 3 < 81) s.cov[4 * q + 3] = v.w;
+    }
+  }
+}
+
+template<typename P, bool UWB, bool HK>
+AGF_DEV void state_store(const VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i) {
+  typedef typename VecOf<P>::type PV;
+  constexpr int VP = VecOf<P>::lanes;
+  P rp[NP_PAD];
+#pragma unroll
+  for (int k = 0; k < NP_PAD; k++) rp[k] = P(0);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { rp[SP_POS + k] = s.pos[k]; rp[SP_VEL + k] = s.vel[k]; rp[SP_W + k] = s.w[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { rp[SP_ATT + k] = s.att[k]; rp[SP_MS + k] = s.ms[k]; }
+  if (UWB) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) rp[SP_RPOS + k] = s.rpos[k];
+  }
+#pragma unroll
+  for (int q = 0; q < NP_PAD / VP; q++) {
+    if (!UWB && q * VP >= SP_RPOS) break;  // nothing beyond the plant proper changes
+    a.sp[size_t(q) * n + i] = VecOf<P>::pack(&rp[q * VP]);
+  }
+  float rf[NF_PAD];
+#pragma unroll
+  for (int k = 0; k < NF_PAD; k++) rf[k] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { rf[SF_CMD + k] = s.cmd[k]; rf[SF_DFORCE + k] = s.dforce[k]; rf[SF_RADIO + k] = s.radio_f[k]; rf[SF_KATT + k] = s.katt[k]; }
+#pragma unroll
+  for (int k = 0; k < 12; k++) { rf[SF_GYRO_LP + k] = s.gyro_lp[k]; rf[SF_ACC_LP + k] = s.acc_lp[k]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { rf[SF_KPOS + k] = s.kpos[k]; rf[SF_KVEL + k] = s.kvel[k]; rf[SF_KW + k] = s.kw[k]; rf[SF_KCORR + k] = s.kcorr[k]; }
+  rf[SF_UWB_RANGE] = s.uwb_range;
+  rf[SF_LOGIC_RANGE] = s.logic_range;
+  if (HK) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) { rf[SF_TEMP_LP + k] = s.temp_lp[k]; rf[SF_BATT_LP + k] = s.batt_lp[k]; rf[SF_PC_ACCUM + k] = s.pc_accum[k]; rf[SF_PC_CORR + k] = s.pc_corr[k]; }
+    rf[SF_BATT_VFILT] = s.batt_vfilt; rf[SF_MON_CMD] = s.mon_cmd_lpdt; rf[SF_MON_LOOP] = s.mon_loop_lpdt;
+  }
+#pragma unroll
+  for (int q = 0; q < NF_PAD / 4; q++) {
+    if (!HK && q >= NF_CORE / 4) break;
+    a.sf[size_t(q) * n + i] = make_float4(rf[4 * q], rf[4 * q + 1], rf[4 * q + 2], rf[4 * q + 3]);
+  }
+  uint32_t ru[NU_PAD];
+#pragma unroll
+  for (int k = 0; k < NU_PAD; k++) ru[k] = 0;
+  ru[SU_BITS] = s.bits; ru[SU_CNT] = s.cnt; ru[SU_CYCLE] = s.cycle; ru[SU_KFCNT] = s.kfcnt;
+  ru[SU_UWB_COUNT] = s.uwb_count; ru[SU_AGE_RADIO] = s.age_radio; ru[SU_AGE_UWB] = s.age_uwb;
+  ru[SU_UWBW] = s.uwbw;
+  if (HK) { ru[SU_AGE_EST_RESET] = s.age_est_reset; ru[SU_PC_COUNT] = s.pc_count; ru[SU_AGE_MON_CMD] = s.age_mon_cmd; ru[SU_AGE_MON_LOOP] = s.age_mon_loop; }
+  if (HK) {
+#pragma unroll
+    for (int q = 0; q < NU_PAD / 4; q++)
+      a.su[size_t(q) * n + i] = make_uint4(ru[4 * q], ru[4 * q + 1], ru[4 * q + 2], ru[4 * q + 3]);
+  } else {
+    // the housekeeping words are not maintained by this variant: keep what is stored
+#pragma unroll
+    for (int q = 0; q < NU_CORE / 4; q++)
+      a.su[size_t(q) * n + i] = make_uint4(ru[4 * q], ru[4 * q + 1], ru[4 * q + 2], ru[4 * q + 3]);
+  }
+  if (UWB) {
+#pragma unroll
+    for (int q = 0; q < NC_PAD / 4; q++) {
+      float4 v;
+      v.x = 4 * q + 0 < 81 ? s.cov[4 * q + 0] : 0.0f;
+      v.y = 4 * q + 1 < 81 ? s.cov[4 * q + 1] : 0.0f;
+      v.z = 4 * q + 2 < 81 ? s.cov[4 * q + 2] : 0.0f;
+      v.w = 4 * q + 3 < 81 ? s.cov[4 * q + 3] : 0.0f;
+      a.sc[size_t(q) * n + i] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// estimator: KalmanFilter6DOF
+// ---------------------------------------------------------------------------------------------
+#define AGF_COV(i, j) s.cov[9 * (i) + (j)]
+
+template<typename P, bool UWB, bool HK>
+AGF_DEV void kf_reset(VState<P, UWB, HK>& s) {  // KalmanFilter6DOF.cpp:33-68
+  s.kfcnt = (s.kfcnt & 0xFFFF0000u) | ((s.kfcnt + 1u) & 0xFFFFu);
+  s.bits &= ~(B_IMU_INIT | B_UWB_INIT);
+  s.bits |= B_KF_RESET_SEEN;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.kpos[k] = 0; s.kvel[k] = 0; s.kw[k] = 0; s.kcorr[k] = 0; }
+  s.katt[0] = 1; s.katt[1] = 0; s.katt[2] = 0; s.katt[3] = 0;
+  if (UWB) {
+#pragma unroll
+    for (int k = 0; k < 81; k++) s.cov[k] = 0;
+    const float sp = 3.0f, sv = 3.0f;
+    const float sperp = 10.0f * 3.14159274f / 180.0f, sabout = 30.0f * 3.14159274f / 180.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { AGF_COV(k, k) = sp * sp; AGF_COV(3 + k, 3 + k) = sv * sv; }
+    AGF_COV(6, 6) = sperp * sperp;
+    AGF_COV(7, 7) = sperp * sperp;
+    AGF_COV(8, 8) = sabout * sabout;
+  }
+}
+
+// gravity alignment shared by the first Predict and the complementary filter (:77-108, :123-145)
+template<bool PARITY>
+AGF_DEV void gravity_axis_angle(const Q4<float>& att, const V3<float>& acc, V3<float>& ax, float& ang) {
+  const V3<float> expAcc = qrot(qinv(att), V3<float>(0, 0, 1));
+  const float n = norm(acc);  // GetUnitVector, Vec3.hpp:126-129
+  const V3<float> accUnit = acc / n;
+  const float cosErr = dot(expAcc, accUnit);
+  V3<float> rotAx = cross(accUnit, expAcc);
+  const float rn = norm(rotAx);
+  if (rn > 1e-6f) {
+    rotAx = rotAx / rn;
+  } else {
+    rotAx = V3<float>(1, 0, 0);
+  }
+  ax = rotAx;
+  ang = acos_guarded<PARITY>(cosErr);
+}
+
+template<bool PARITY, typename P, bool UWB, bool HK>
+AGF_DEV void kf_predict(VState<P, UWB, HK>& s, const V3<float>& gyro, const V3<float>& acc, float dt) {
+  if (!(s.bits & B_IMU_INIT)) {  // :71-108
+    kf_reset(s);
+    s.bits |= B_IMU_INIT;
+    Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+    V3<float> ax;
+    float ang;
+    gravity_axis_angle<PARITY>(att, acc, ax, ang);
+    att = qmul(att, q_from_axis_angle<PARITY>(ax, ang));
+    s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
+    return;
+  }
+  Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+  if (!UWB || !(s.bits & B_UWB_INIT)) {  // :114-147 complementary filter
+    s.kw[0] = gyro.x; s.kw[1] = gyro.y; s.kw[2] = gyro.z;
+    att = q_apply_rotvec<PARITY>(att, gyro * dt);
+    V3<float> ax;
+    float ang;
+    gravity_axis_angle<PARITY>(att, acc, ax, ang);
+    const float corr = (dt / 4.0f) * ang;
+    att = qmul(att, q_from_axis_angle<PARITY>(ax, corr));
+    s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
+    return;
+  }
+  if (UWB) {  // :149-241
+    const V3<float> p0(s.kpos[0], s.kpos[1], s.kpos[2]), v0(s.kvel[0], s.kvel[1], s.kvel[2]);
+    float Rm[9];
+    qmatrix(att, Rm);
+    const V3<float> a_w = V3<float>(Rm[0] * acc.x + Rm[1] * acc.y + Rm[2] * acc.z, Rm[3] * acc.x + Rm[4] * acc.y + Rm[5] * acc.z,
+                                    Rm[6] * acc.x + Rm[7] * acc.y + Rm[8] * acc.z) + V3<float>(0, 0, -9.81f);
+    const V3<float> p1 = p0 + v0 * dt, v1 = v0 + a_w * dt;
+    s.kpos[0] = p1.x; s.kpos[1] = p1.y; s.kpos[2] = p1.z;
+    s.kvel[0] = v1.x; s.kvel[1] = v1.y; s.kvel[2] = v1.z;
+    const Q4<float> att1 = q_apply_rotvec<PARITY>(att, gyro * dt);
+    s.katt[0] = att1.w; s.katt[1] = att1.x; s.katt[2] = att1.y; s.katt[3] = att1.z;
+    s.kw[0] = gyro.x; s.kw[1] = gyro.y; s.kw[2] = gyro.z;
+
+    // vel <- att block of f, :184-209   A[r][c]
+    float A[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      A[r][0] = dt * (+acc.y * Rm[3 * r + 2] - acc.z * Rm[3 * r + 1]);
+      A[r][1] = dt * (-acc.x * Rm[3 * r + 2] + acc.z * Rm[3 * r + 0]);
+      A[r][2] = dt * (+acc.x * Rm[3 * r + 1] - acc.y * Rm[3 * r + 0]);
+    }
+    // att <- att block, :212-228   S[r][c]
+    const float gx = dt * gyro.x + s.kcorr[0] / 2.0f;
+    const float gy = dt * gyro.y + s.kcorr[1] / 2.0f;
+    const float gz = dt * gyro.z + s.kcorr[2] / 2.0f;
+    const float S[3][3] = {{1.0f, +gz, -gy}, {-gz, 1.0f, +gx}, {+gy, -gx, 1.0f}};
+    s.kcorr[0] = 0; s.kcorr[1] = 0; s.kcorr[2] = 0;
+
+    // FP = f * P, in place, row blocks in an order that only reads not-yet-overwritten rows
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) AGF_COV(r, j) = AGF_COV(r, j) + dt * AGF_COV(3 + r, j);
+      const float p6 = AGF_COV(6, j), p7 = AGF_COV(7, j), p8 = AGF_COV(8, j);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        AGF_COV(3 + r, j) = ((AGF_COV(3 + r, j) + A[r][0] * p6) + A[r][1] * p7) + A[r][2] * p8;
+#pragma unroll
+      for (int r = 0; r < 3; r++) AGF_COV(6 + r, j) = (S[r][0] * p6 + S[r][1] * p7) + S[r][2] * p8;
+    }
+    // P' = FP * f^T, in place, column blocks likewise
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) AGF_COV(i, r) = AGF_COV(i, r) + AGF_COV(i, 3 + r) * dt;
+      const float p6 = AGF_COV(i, 6), p7 = AGF_COV(i, 7), p8 = AGF_COV(i, 8);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        AGF_COV(i, 3 + r) = ((AGF_COV(i, 3 + r) + p6 * A[r][0]) + p7 * A[r][1]) + p8 * A[r][2];
+#pragma unroll
+      for (int r = 0; r < 3; r++) AGF_COV(i, 6 + r) = (p6 * S[r][0] + p7 * S[r][1]) + p8 * S[r][2];
+    }
+    // process noise :234-239
+    const float qa = 5.0f * 5.0f * dt * dt, qg = 0.1f * 0.1f * dt * dt;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { AGF_COV(3 + k, 3 + k) += qa; AGF_COV(6 + k, 6 + k) += qg; }
+  }
+}
+
+template<bool PARITY, typename P, bool UWB, bool HK>
+AGF_DEV void kf_update_range(VState<P, UWB, HK>& s, const V3<float>& target, float range) {  // :243-301
+  if (!UWB) return;
+  if (!(s.bits & B_IMU_INIT)) return;
+  if (!(range == range)) return;
+  s.bits |= B_UWB_INIT;
+  const V3<float> d = V3<float>(s.kpos[0], s.kpos[1], s.kpos[2]) - target;
+  const float expRange = norm(d);
+  const V3<float> H = d / expRange;
+  float PHt[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) PHt[i] = (AGF_COV(i, 0) * H.x + AGF_COV(i, 1) * H.y) + AGF_COV(i, 2) * H.z;
+  const float hph = (H.x * PHt[0] + H.y * PHt[1]) + H.z * PHt[2];
+  const float innovCov = hph + 0.14f * 0.14f;
+  const float inv = 1 / innovCov;
+  float L[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) L[i] = PHt[i] * inv;
+  const float innov = range - expRange;
+  const float d2 = innov * innov / innovCov;
+  if (d2 > 3.0f * 3.0f) {
+    uint32_t rej = (s.kfcnt >> 16) + 1u;
+    s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
+    uint32_t seq = (s.cnt & 0xFFu) + 1u;
+    s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
+    if (seq >= 5u) kf_reset(s);
+    return;
+  }
+  s.cnt &= ~0xFFu;
+  float dx[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) dx[i] = L[i] * innov;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.kpos[k] = s.kpos[k] + dx[k]; s.kvel[k] = s.kvel[k] + dx[3 + k]; s.kcorr[k] = dx[6 + k]; }
+  Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+  att = q_apply_rotvec<PARITY>(att, V3<float>(dx[6], dx[7], dx[8]));
+  s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
+  // P <- (I - L H) P ; rows 3..8 first (they read the old rows 0..2), then rows 0..2
+  const float h[3] = {H.x, H.y, H.z};
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const float p0 = AGF_COV(0, j), p1 = AGF_COV(1, j), p2 = AGF_COV(2, j);
+#pragma unroll
+    for (int i = 3; i < 9; i++)
+      AGF_COV(i, j) = (((0.0f - L[i] * h[0]) * p0 + (0.0f - L[i] * h[1]) * p1) + (0.0f - L[i] * h[2]) * p2) + AGF_COV(i, j);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float a0 = (i == 0 ? 1.0f : 0.0f) - L[i] * h[0];
+      const float a1 = (i == 1 ? 1.0f : 0.0f) - L[i] * h[1];
+      const float a2 = (i == 2 ? 1.0f : 0.0f) - L[i] * h[2];
+      AGF_COV(i, j) = (a0 * p0 + a1 * p1) + a2 * p2;
+    }
+  }
+  // MakeCovarianceSymmetric :303-309
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+#pragma unroll
+    for (int j = i + 1; j < 9; j++) AGF_COV(i, j) = AGF_COV(j, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// controllers and mixer
+// ---------------------------------------------------------------------------------------------
+// QuadcopterAngularVelocityController::GetDesiredTorques (:25-37); inertia = diag(ixx, ixx, izz) as
+// QuadcopterConstants builds it (the zero off-diagonal products are exact and dropped)
+AGF_DEV V3<float> ctl_torques(const LogicParams& k, const V3<float>& des, const V3<float>& est) {
+  const V3<float> err = des - est;
+  const V3<float> acc(err.x / k.tc_w_xy, err.y / k.tc_w_xy, err.z / k.tc_w_z);
+  const V3<float> Iw(k.ixx * est.x, k.ixx * est.y, k.izz * est.z);
+  const V3<float> nonlin = cross(est, Iw);
+  return V3<float>(k.ixx * acc.x, k.ixx * acc.y, k.izz * acc.z) + nonlin;
+}
+
+// QuadcopterAttitudeController::GetDesiredAngularVelocity (:35-68)
+template<bool PARITY>
+AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q4<float>& estAtt) {
+  const Q4<float> err = qmul(qinv(desAtt), estAtt);
+  const V3<float> rotVec = q_to_rotvec<PARITY>(err);
+  const V3<float> e3b = qrot(qinv(err), V3<float>(0, 0, 1));
+  V3<float> redAx = cross(e3b, V3<float>(0, 0, 1));
+  const float c = dot(e3b, V3<float>(0, 0, 1));
+  float redAn;
+  if (c >= 1.0f) {
+    redAn = 0;
+  } else if (c <= -1.0f) {
+    redAn = 3.14159274f;
+  } else {
+    redAn = Mf<PARITY>::acos(c);
+  }
+  const float n = norm(redAx);
+  if (n < 1e-12f) {
+    redAx = V3<float>(0, 0, 0);
+  } else {
+    redAx = redAx / n;
+  }
+  const float k3 = 1.0f / k.tc_att_z, k12 = 1.0f / k.tc_att_xy;
+  return (-k3) * rotVec - ((k12 - k3) * redAn) * redAx;
+}
+
+// QuadcopterMixer::GetMotorForces + PropellerSpeedsFromThrust (:63-99)
+template<typename P, bool UWB, bool HK>
+AGF_DEV void ctl_mix(VState<P, UWB, HK>& s, const LogicParams& k, float totF, const V3<float>& t) {
+  const float desF = totF > k.max_cmd_total ? k.max_cmd_total : totF;
+  float f[4];
+  f[0] = (-t.x / k.mix_d - t.y / k.mix_d - t.z / k.mix_kt + desF) / 4.0f;
+  f[1] = (-t.x / k.mix_d + t.y / k.mix_d + t.z / k.mix_kt + desF) / 4.0f;
+  f[2] = (+t.x / k.mix_d + t.y / k.mix_d - t.z / k.mix_kt + desF) / 4.0f;
+  f[3] = (+t.x / k.mix_d - t.y / k.mix_d + t.z / k.mix_kt + desF) / 4.0f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (f[i] < k.min_thrust) {
+      f[i] = k.min_thrust;
+    } else if (f[i] > k.max_thrust) {
+      f[i] = k.max_thrust;
+    }
+    s.dforce[i] = f[i];
+    const float corr = HK ? s.pc_corr[i] : 1.0f;
+    s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(f[i] / (corr * k.mix_kf));
+  }
+}
+
+// thrust direction -> attitude (QuadcopterLogic.cpp:423-445)
+template<bool PARITY>
+AGF_DEV Q4<float> att_from_thrust_dir(const V3<float>& dir) {
+  const V3<float> e3(0, 0, 1);
+  const float cosAngle = dot(dir, e3);
+  const float angle = acos_guarded<PARITY>(cosAngle);
+  const V3<float> rotAx = cross(e3, dir);
+  const float n = norm(rotAx);
+  Q4<float> out(1, 0, 0, 0);
+  if (!(n < 1e-6f)) {
+    Q4<float> d;
+    if (q_from_rotvec<PARITY>(rotAx * (angle / n), d)) out = d;
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// QuadcopterLogic::Run (QuadcopterLogic.cpp:164-219) with its intake setters
+// ---------------------------------------------------------------------------------------------
+template<bool PARITY, typename P, bool UWB, bool HK>
+AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<float>& gyroMeas,
+                       const V3<float>& accMeas, float kf_dt) {
+  const LogicParams& k = p.logic;
+  // --- intake (QuadcopterLogic.hpp:32-59) ---
+  if (HK) {
+    s.batt_vfilt = lpf2(k.lp_batt, s.batt_lp, 1, k.batt_voltage);
+    lpf2(k.lp_temp, s.temp_lp, 1, 25.0f);
+  }
+  V3<float> g = gyroMeas, a = accMeas;
+  if (!k.imu_identity) {
+    g = matvec(k.R_imu, g);
+    a = matvec(k.R_imu, a);
+  }
+  // gyro calibration bias is always (0,0,0) behind this API: rawMeas - bias == rawMeas
+  const V3<float> gf(lpf2(k.lp_gyro, &s.gyro_lp[0], 1, g.x), lpf2(k.lp_gyro, &s.gyro_lp[4], 1, g.y),
+                     lpf2(k.lp_gyro, &s.gyro_lp[8], 1, g.z));
+  const V3<float> af(lpf2(k.lp_acc, &s.acc_lp[0], 1, a.x), lpf2(k.lp_acc, &s.acc_lp[4], 1, a.y),
+                     lpf2(k.lp_acc, &s.acc_lp[8], 1, a.z));
+
+  uint32_t fs = bget(s.bits, B_FS_SHIFT, B_FS_MASK);
+  if (fs == AGF_FS_UNINITIALIZED) return;
+  s.cycle++;
+  if (HK) {  // MonitorSimplePeriod::Update (QuadcopterLogic.hpp:390-394)
+    const float mdt = float(s.age_mon_loop) * 1e-6f;
+    s.mon_loop_lpdt = k.mon_loop_coef <= 0.0f ? mdt : k.mon_loop_coef * s.mon_loop_lpdt + (1 - k.mon_loop_coef) * mdt;
+    s.age_mon_loop -= uint32_t(mdt * 1e6f);
+  }
+  // --- UpdateEstimator :221-273 ---
+  kf_predict<PARITY>(s, gf, af, kf_dt);
+  if (UWB && (s.bits & B_UWB_NEW)) {
+    s.bits &= ~B_UWB_NEW;
+    s.uwb_count++;  // failure is never set by the simulated network (UWBNetwork.cpp:77)
+    const uint32_t resp = (s.uwbw >> W_LOGIC_TARGET) & 0xFFu;  // anchor that produced the range
+    uint32_t nxt = (s.uwbw >> W_NEXT_TARGET) & 0xFFu;
+    nxt = (nxt + 1u) % p.n_anchors;
+    s.uwbw = (s.uwbw & ~(0xFFu << W_NEXT_TARGET)) | (nxt << W_NEXT_TARGET);
+    const V3<float> tp(p.anchors[resp].x, p.anchors[resp].y, p.anchors[resp].z);
+    kf_update_range<PARITY>(s, tp, s.logic_range);
+  }
+  // --- ParseIncomingCommunications :275-303 ---
+  if (s.bits & B_RADIO_NEW) {
+    s.bits &= ~B_RADIO_NEW;
+    if (fs != AGF_FS_PANIC && fs != AGF_FS_KILLED) {
+      const uint32_t ty = bget(s.bits, B_RTYPE_SHIFT, B_RTYPE_MASK);
+      if (ty == AGF_RADIO_EMERGENCY_KILL) {
+        fs = AGF_FS_KILLED;
+        if (!bget(s.bits, B_PANIC_SHIFT, B_PANIC_MASK)) s.bits = bset(s.bits, B_PANIC_SHIFT, B_PANIC_MASK, AGF_PANIC_KILLED_EXTERNALLY);
+      } else if (ty == AGF_RADIO_POSITION_CMD) {
+        fs = AGF_FS_FULLY_AUTONOMOUS;
+      } else if (ty == AGF_RADIO_EXTERNAL_ACCELERATION_CMD) {
+        fs = AGF_FS_EXTERNAL_ACCELERATION_CONTROL;
+      } else if (ty == AGF_RADIO_EXTERNAL_RATES_CMD) {
+        fs = AGF_FS_EXTERNAL_RATES_CONTROL;
+      } else if (ty == AGF_RADIO_IDLE_CMD) {
+        fs = AGF_FS_IDLE;
+      }
+    }
+  }
+  const uint32_t rflags = bget(s.bits, B_RFLAGS_SHIFT, B_RFLAGS_MASK);
+  // --- UpdateWarnings :305-342 ---
+  if (HK) {
+    uint32_t w = (s.cnt >> 24) & 0xFFu;
+    if (s.batt_vfilt <= k.batt_warning) w |= AGF_WARN_LOW_BATT;
+    if (::fabsf(s.mon_cmd_lpdt - 0.02f) > (0.1f * 0.02f)) w |= AGF_WARN_CMD_RATE;
+    if (float(s.age_radio) * 1e-6f > 3 * 0.02f) w |= AGF_WARN_CMD_BATCH_DROP;
+    if (::fabsf(s.mon_loop_lpdt - k.onboard_period) > (0.05f * k.onboard_period)) w |= AGF_WARN_ONBOARD_FREQ;
+    if (s.bits & B_KF_RESET_SEEN) s.age_est_reset = 0;
+    if (float(s.age_est_reset) * 1e-6f < 0.02f) w |= AGF_WARN_UWB_RESET;
+    s.cnt = (s.cnt & 0x00FFFFFFu) | (w << 24);
+  }
+  s.bits &= ~B_KF_RESET_SEEN;
+  // --- CheckPanicReasons :344-391 ---
+  {
+    const bool running = s.cmd[0] > 0 || s.cmd[1] > 0 || s.cmd[2] > 0 || s.cmd[3] > 0;
+    uint32_t unsafe = 0;
+    if (running) {
+      const bool nochk = (rflags & AGF_RADIO_FLAG_DISABLE_ONBOARD_SAFETY) != 0;
+      if (s.kpos[2] < -2.0f && !nochk) unsafe = AGF_PANIC_ONBOARD_ESTIMATE_CRAZY;
+      if (s.age_uwb > 1500u * 1000u && fs == AGF_FS_FULLY_AUTONOMOUS) unsafe = AGF_PANIC_UWB_TIMEOUT;
+      const Q4<float> ea(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+      if (qrot_e3_z(ea) < 0 && !nochk) unsafe = AGF_PANIC_UPSIDE_DOWN;
+      if (s.age_radio > 1500u * 1000u) unsafe = AGF_PANIC_RADIO_CMD_TIMEOUT;
+      if (HK && s.batt_vfilt <= k.batt_critical) unsafe = AGF_PANIC_LOW_BATTERY;
+    }
+    const bool critical = !(fs == AGF_FS_UNINITIALIZED || fs == AGF_FS_IDLE || fs == AGF_FS_PANIC || fs == AGF_FS_KILLED);
+    if (unsafe && critical) {
+      fs = AGF_FS_PANIC;
+      s.bits = bset(s.bits, B_PANIC_SHIFT, B_PANIC_MASK, unsafe);
+    }
+  }
+  s.bits = bset(s.bits, B_FS_SHIFT, B_FS_MASK, fs);
+
+  // --- controllers :194-217 ---
+  const V3<float> estW(s.kw[0], s.kw[1], s.kw[2]);
+  if (fs == AGF_FS_EXTERNAL_RATES_CONTROL) {  // :528-588
+    const V3<float> tq = ctl_torques(k, V3<float>(s.radio_f[1], s.radio_f[2], s.radio_f[3]), estW);
+    ctl_mix(s, k, s.radio_f[0] * k.mass, tq);
+    if (HK) {
+      if (rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) {
+        if (!(s.bits & B_PC_RUNNING)) {
+          s.bits |= B_PC_RUNNING;
+          s.pc_count = 0;
+#pragma unroll
+          for (int i = 0; i < 4; i++) s.pc_accum[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) s.pc_accum[i] += k.mix_kf * s.cmd[i] * s.cmd[i];
+        s.pc_count++;
+      } else if (s.bits & B_PC_RUNNING) {
+        s.bits &= ~B_PC_RUNNING;
+        if (s.pc_count >= 750u) {
+          const float truePer = k.mass * 9.81f / 4.0f;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            float f = (s.pc_count * truePer) / s.pc_accum[i];
+            const float fmin = 0.7f, fmax = 1.0f / fmin;
+            if (f > fmax) f = fmax;
+            if (f < fmin) f = fmin;
+            s.pc_corr[i] = f;
+          }
+        }
+      }
+    }
+  } else if (fs == AGF_FS_FULLY_AUTONOMOUS) {  // :393-457
+    const V3<float> estPos(s.kpos[0], s.kpos[1], s.kpos[2]), estVel(s.kvel[0], s.kvel[1], s.kvel[2]);
+    const Q4<float> estAtt(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+    const V3<float> desPos(s.radio_f[0], s.radio_f[1], s.radio_f[2]);
+    // GetDesAcceleration (QuadcopterPositionController.hpp:22-27), desVel = desAcc = 0
+    const V3<float> zero(0, 0, 0);
+    const V3<float> dv = zero - estVel;
+    const V3<float> desAcc = (((desPos - estPos) * k.nat_freq) * k.nat_freq +
+                              ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * k.nat_freq) * k.damping)) + zero;
+    const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
+    const float nProper = norm(proper);
+    const V3<float> dir = proper / nProper;
+    const float corr = qrot_e3_z(estAtt);
+    const float corrSat = corr < 1.00f ? 1.00f : corr;
+    const float thrust = nProper / corrSat;
+    const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
+    const V3<float> desW = ctl_att<PARITY>(k, desAtt, estAtt);
+    ctl_mix(s, k, thrust * k.mass, ctl_torques(k, desW, estW));
+  } else if (fs == AGF_FS_EXTERNAL_ACCELERATION_CONTROL) {  // :459-526
+    const Q4<float> estAtt(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+    const V3<float> desAcc(s.radio_f[0], s.radio_f[1], s.radio_f[2]);
+    if (desAcc.z < -9.81f / 2) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { s.cmd[i] = 0; s.dforce[i] = 0; }
+    } else {
+      const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
+      const float thrust = norm(proper);
+      const V3<float> dir = proper / thrust;
+      const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
+      // ToEulerYPR (Rotation.hpp:163-169); yaw is computed by the reference but unused
+      const Q4<float>& q = estAtt;
+      const float pch = -Mf<PARITY>::asin(2.0f * q.x * q.z - 2.0f * q.w * q.y);
+      const float rll = Mf<PARITY>::atan2(2.0f * q.y * q.z + 2.0f * q.w * q.x, q.z * q.z - q.y * q.y - q.x * q.x + q.w * q.w);
+      const Q4<float> noYaw = q_from_euler_ypr<PARITY>(0.0f, pch, rll);
+      V3<float> desW = ctl_att<PARITY>(k, desAtt, noYaw);
+      desW.z = s.radio_f[3];
+      ctl_mix(s, k, thrust * k.mass, ctl_torques(k, desW, estW));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s.cmd[i] = 0; s.dforce[i] = 0; }
+  }
+}
+
+// SetRadioMessage (QuadcopterLogic.hpp:110-116)
+template<typename P, bool UWB, bool HK>
+AGF_DEV void radio_deliver(VState<P, UWB, HK>& s, const LogicParams& k, uint32_t type, uint32_t flags, const float f[4]) {
+  s.bits |= B_RADIO_NEW;
+  s.bits = bset(s.bits, B_RTYPE_SHIFT, B_RTYPE_MASK, type);
+  s.bits = bset(s.bits, B_RFLAGS_SHIFT, B_RFLAGS_MASK, flags);
+#pragma unroll
+  for (int i = 0; i < 4; i++) s.radio_f[i] = f[i];
+  s.age_radio = 0;
+  if (HK) {
+    const float mdt = float(s.age_mon_cmd) * 1e-6f;
+    s.mon_cmd_lpdt = k.mon_cmd_coef <= 0.0f ? mdt : k.mon_cmd_coef * s.mon_cmd_lpdt + (1 - k.mon_cmd_coef) * mdt;
+    s.age_mon_cmd -= uint32_t(mdt * 1e6f);
+  }
+}
+
+AGF_DEV uint32_t sat_add(uint32_t a, uint32_t d) { return a > 0xF0000000u ? a : a + d; }
+
+// ---------------------------------------------------------------------------------------------
+// one tick: [radio delivery] -> Quadcopter_T::Run -> UWBNetwork::Run -> clock advance
+// ---------------------------------------------------------------------------------------------
+template<typename P, bool PARITY, bool UWB, bool HK>
+AGF_DEV void tick(VState<P, UWB, HK>& s, const StepShared<P>& p, const PlantPV<P>& pv, Timing& ts,
+                  uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
+  const TickPlan plan = timing_plan(ts, p.tc);
+  if (plan.run_plant) {
+    const P dt = P(double(plan.plant_dt_us) * 1e-6);
+    // ---- motors (Motor.cpp:39-84).  Axes are (0,0,+-1) and thrust is (0,0,f): the products with
+    // the exact-zero components are dropped, the rest keeps the reference's order.
+    P Fz = P(0), Tx = P(0), Ty = P(0), Tz = P(0);
+    const P c = pv.motor_c;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const P sgn = (m & 1) ? P(-1) : P(1);  // spin axis z component
+      P cmd = P(s.cmd[m]);
+      if (cmd < 0) cmd = 0;
+      const P old = s.ms[m];
+      P sp = c * old + (1 - c) * cmd;
+      if (sp > p.motor_max) {
+        sp = p.motor_max;
+      } else if (sp < p.motor_min) {
+        sp = p.motor_min;
+      }
+      s.ms[m] = sp;
+      const P fz = (pv.kF * sp) * rabs_(sp);
+      const P aero = (((-pv.kTau) * sp) * rabs_(sp)) * sgn;
+      const P angAcc = (sp - old) / dt;
+      const P tz = (aero + P(0)) - ((angAcc * p.motor_J) * sgn);
+      const P tx = p.motor_pos[m][1] * fz;   // (r x T).x = ry*fz - rz*0
+      const P ty = P(0) - p.motor_pos[m][0] * fz;  // (r x T).y = rz*0 - rx*fz
+      Fz = Fz + fz; Tx = Tx + tx; Ty = Ty + ty; Tz = Tz + tz;
+    }
+    Q4<P> att(s.att[0], s.att[1], s.att[2], s.att[3]);
+    V3<P> w(s.w[0], s.w[1], s.w[2]);
+    V3<P> F(P(0), P(0), Fz), T(Tx, Ty, Tz);
+    V3<P> extF(P(0), P(0), P(0));
+    if (p.ext_force) {
+      extF = V3<P>(p.ext_force[i], p.ext_force[n + i], p.ext_force[2 * n + i]);
+      const V3<P> extT(p.ext_torque[i], p.ext_torque[n + i], p.ext_torque[2 * n + i]);
+      T = T + qrot(qinv(att), extT);
+    }
+    // angular momentum: I*w + sum of rotor momenta (Quadcopter_T.cpp:113-117)
+    V3<P> L = matvec(pv.I, w);
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const P sgn = (m & 1) ? P(-1) : P(1);
+      L.z = L.z + (s.ms[m] * p.motor_J) * sgn;
+    }
+    const V3<P> angAcc = matvec(pv.Iinv, T - cross(w, L));
+    if (p.has_drag) {  // :123-128
+      const V3<P> vb = qrot(qinv(att), V3<P>(s.vel[0], s.vel[1], s.vel[2]));
+      F = F + V3<P>(p.drag[0] * (-vb.x), p.drag[1] * (-vb.y), p.drag[2] * (-vb.z));
+    }
+    V3<P> acc(P(0), P(0), P(-9.81));
+    acc = acc + (qrot(att, F) + extF) / pv.mass;
+    const V3<P> pos(s.pos[0], s.pos[1], s.pos[2]), vel(s.vel[0], s.vel[1], s.vel[2]);
+    V3<P> npos = (pos + vel * dt) + ((P(0.5) * acc) * dt) * dt;
+    V3<P> nvel = vel + acc * dt;
+    const Q4<P> natt = q_apply_rotvec<PARITY>(att, w * dt);
+    V3<P> nw = w + angAcc * dt;
+    if ((npos.z <= 0) && (nvel.z < 0)) {  // ground contact :146-151
+      npos.z = 0;
+      nvel.z = 0;
+      acc.z = 0;
+      nw = V3<P>(P(0), P(0), P(0));
+    }
+    s.pos[0] = npos.x; s.pos[1] = npos.y; s.pos[2] = npos.z;
+    s.vel[0] = nvel.x; s.vel[1] = nvel.y; s.vel[2] = nvel.z;
+    s.att[0] = natt.w; s.att[1] = natt.x; s.att[2] = natt.y; s.att[3] = natt.z;
+    s.w[0] = nw.x; s.w[1] = nw.y; s.w[2] = nw.z;
+
+    if (plan.run_logic) {  // :159-199
+      V3<float> g(float(nw.x), float(nw.y), float(nw.z));
+      const V3<P> sf = qrot(qinv(natt), acc + V3<P>(P(0), P(0), P(9.81)));
+      V3<float> a(float(sf.x), float(sf.y), float(sf.z));
+      if (!p.logic.imu_identity) {
+        g = matvec(p.logic.R_imu_inv, g);
+        a = matvec(p.logic.R_imu_inv, a);
+      }
+      if (p.noise_on) {
+        float nrm[6];
+        normals6(p.seed, gidx, s.cycle, 0u, nrm);
+        g = g + V3<float>(nrm[0], nrm[1], nrm[2]) * p.sigma_gyro;
+        a = a + V3<float>(nrm[3], nrm[4], nrm[5]) * p.sigma_acc;
+        if (p.bias_on) {
+          float b[6];
+          normals6(p.seed, gidx, 0xFFFFFFFFu, 1u, b);
+          g = g + V3<float>(b[0], b[1], b[2]) * p.bias_sigma_gyro;
+          a = a + V3<float>(b[3], b[4], b[5]) * p.bias_sigma_acc;
+        }
+      }
+      logic_run<PARITY>(s, p, g, a, float(plan.kf_dt_us) * 1e-6f);
+      if (UWB) {  // radio exchange :191-199
+        s.rpos[0] = s.pos[0]; s.rpos[1] = s.pos[1]; s.rpos[2] = s.pos[2];
+        if (s.bits & B_RADIO_MEAS_NEW) {  // SetUWBMeasurement (QuadcopterLogic.hpp:61-69)
+          s.bits &= ~B_RADIO_MEAS_NEW;
+          s.age_uwb = 0;
+          s.bits |= B_UWB_NEW;
+          s.logic_range = s.uwb_range;
+          const uint32_t rr = (s.uwbw >> W_RADIO_RESP) & 0xFFu;
+          s.uwbw = (s.uwbw & ~(0xFFu << W_LOGIC_TARGET)) | (rr << W_LOGIC_TARGET);
+        }
+      }
+    }
+  }
+  // ---- UWBNetwork::Run (UWBNetwork.cpp:22-89), private network: this vehicle + the anchors.
+  // When it runs, and whether it starts or completes a transaction, depends on the clock only
+  // (TickPlan); which anchor answers and the measured range are per vehicle.
+  if (UWB) {
+    if (plan.net_start) {  // :32-41 responder = the requester's next ranging target
+      const uint32_t nxt = (s.uwbw >> W_NEXT_TARGET) & 0xFFu;
+      s.uwbw = (s.uwbw & ~(0xFFu << W_NET_RESP)) | (nxt << W_NET_RESP);
+    }
+    if (plan.net_complete) {  // :47-82
+      const uint32_t resp = (s.uwbw >> W_NET_RESP) & 0xFFu;
+      const V3<P> d = V3<P>(s.rpos[0], s.rpos[1], s.rpos[2]) -
+                      V3<P>(P(p.anchors[resp].x), P(p.anchors[resp].y), P(p.anchors[resp].z));
+      P r = norm(d);
+      if (p.uwb_noise_on) {
+        float nrm[6];
+        normals6(p.seed, gidx, uint32_t(abs_tick), 2u, nrm);
+        r = r + P(nrm[0]) * P(p.uwb_sigma);
+      } else {
+        r = r + P(0);
+      }
+      s.uwb_range = float(r);
+      s.uwbw = (s.uwbw & ~(0xFFu << W_RADIO_RESP)) | (resp << W_RADIO_RESP);
+      s.bits |= B_RADIO_MEAS_NEW;
+    }
+  }
+  timing_advance(ts, p.tc, plan, dt_us);
+  s.age_radio = sat_add(s.age_radio, dt_us);
+  s.age_uwb = sat_add(s.age_uwb, dt_us);
+  if (HK) {
+    s.age_est_reset = sat_add(s.age_est_reset, dt_us);
+    s.age_mon_cmd = sat_add(s.age_mon_cmd, dt_us);
+    s.age_mon_loop = sat_add(s.age_mon_loop, dt_us);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2/K3: the step kernel.  One vehicle per thread; nticks ticks per launch with the state in
+// registers; optional trajectory log [record][field][vehicle] (every store a coalesced line).
+// ---------------------------------------------------------------------------------------------
+template<typename P>
+AGF_DEV void plant_params_load(PlantPV<P>& pv, const StepLaunch<P>& L, size_t i) {
+  pv = L.pv_shared;
+  if (L.pv) {
+    constexpr int VP = VecOf<P>::lanes;
+    P r[NPV_PAD];
+#pragma unroll
+    for (int q = 0; q < NPV_PAD / VP; q++) VecOf<P>::unpack(L.pv[size_t(q) * L.n + i], &r[q * VP]);
+    pv.mass = r[PV_MASS];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { pv.I[k] = P(0); pv.Iinv[k] = P(0); }
+    pv.I[0] = r[PV_IXX]; pv.I[4] = r[PV_IYY]; pv.I[8] = r[PV_IZZ];
+    pv.Iinv[0] = r[PV_IIXX]; pv.Iinv[4] = r[PV_IIYY]; pv.Iinv[8] = r[PV_IIZZ];
+    pv.kF = r[PV_KF]; pv.kTau = r[PV_KTAU]; pv.motor_c = r[PV_MOTOR_C];
+  }
+}
+
+template<typename P, bool PARITY, bool UWB, bool HK>
+__global__ void __launch_bounds__(AGF_BLOCK_THREADS) step_kernel(const __grid_constant__ StepLaunch<P> L) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  VState<P, UWB, HK> s;
+  state_load(s, L.st, L.n, i);
+  PlantPV<P> pv;
+  plant_params_load(pv, L, i);
+  Timing ts = L.ts;
+  uint32_t si = L.sched_begin;
+  const uint64_t gidx = L.first_global_index + i;
+  for (uint32_t t = 0; t < L.nticks; t++) {
+    const uint64_t abs_tick = L.tick0 + t;
+    // radio delivery before Run() (main.cpp:737-739 of the previous loop iteration)
+    if (si < L.sched_end && L.sched[si].tick == abs_tick) {
+      const SchedEntryDev& e = L.sched[si];
+      if (e.slot < 0) {
+        radio_deliver(s, L.sh.logic, e.type, e.flags, e.f);
+      } else {
+        const float4 f = L.slots[e.slot].f[i];
+        const uint32_t tf = L.slots[e.slot].tf[i];
+        const float ff[4] = {f.x, f.y, f.z, f.w};
+        radio_deliver(s, L.sh.logic, tf & 0xFFu, (tf >> 8) & 0xFFu, ff);
+      }
+      si++;
+    }
+    tick<P, PARITY, UWB, HK>(s, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
+    if (L.log && ((abs_tick + 1) % L.log_stride) == 0) {
+      const uint64_t rec = (abs_tick + 1) / L.log_stride - 1;
+      P* base = L.log + (size_t(rec % L.log_capacity) * AGF_LOG_FIELDS) * L.n + i;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { base[size_t(k) * L.n] = s.pos[k]; base[size_t(3 + k) * L.n] = s.vel[k]; base[size_t(10 + k) * L.n] = s.w[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { base[size_t(6 + k) * L.n] = s.att[k]; base[size_t(13 + k) * L.n] = s.ms[k]; }
+    }
+  }
+  state_store(s, L.st, L.n, i);
+}
+
+}  // namespace agf

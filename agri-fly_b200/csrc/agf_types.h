@@ -1,0 +1,223 @@
+// agf_types.h -- data layout and launch-parameter types shared by the host handle and the kernels.
+//
+// HBM layout of a batch of N vehicles (DESIGN.md "Data layout"): four structure-of-arrays
+// groups, each an array of 16-byte quads indexed [quad][vehicle]:
+//   sp  plant state            NP_PAD scalars of the plant precision P  (double2 or float4 quads)
+//   sf  onboard-logic floats   NF_PAD floats                             (float4 quads)
+//   su  flags/counters/ages    NU_PAD uint32                             (uint4 quads)
+//   sc  EKF covariance         NC_PAD floats, only for UWB batches       (float4 quads)
+// A warp reading quad q of 32 consecutive vehicles touches 512 (or 1024) contiguous bytes.
+#pragma once
+
+#include <stdint.h>
+#include <stddef.h>
+
+#include "agrifly_b200.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define AGF_HDI __host__ __device__ __forceinline__
+#else
+#define AGF_HDI inline
+#endif
+
+namespace agf {
+
+// ---- flat state tables ------------------------------------------------------------------------
+enum {  // plant scalars (precision P)
+  SP_POS = 0, SP_VEL = 3, SP_ATT = 6, SP_W = 10, SP_MS = 13, /* 17..19 pad */
+  SP_RPOS = 20,  // UWB radio's latched true position (UWBRadio::_uwbTruePosition)
+  NP_CORE = 20, NP_PAD = 24
+};
+enum {  // logic floats; the HK block follows the core block
+  SF_CMD = 0, SF_DFORCE = 4, SF_RADIO = 8, SF_KATT = 12, SF_GYRO_LP = 16, SF_ACC_LP = 28,
+  SF_KPOS = 40, SF_KVEL = 43, SF_KW = 46, SF_KCORR = 49, SF_UWB_RANGE = 52, SF_LOGIC_RANGE = 53,
+  NF_CORE = 56,
+  SF_TEMP_LP = 56, SF_BATT_LP = 60, SF_PC_ACCUM = 64, SF_PC_CORR = 68, SF_BATT_VFILT = 72,
+  SF_MON_CMD = 73, SF_MON_LOOP = 74,
+  NF_PAD = 76
+};
+enum {  // uint32 words
+  SU_BITS = 0, SU_CNT = 1, SU_CYCLE = 2, SU_KFCNT = 3, SU_UWB_COUNT = 4, SU_AGE_RADIO = 5,
+  SU_AGE_UWB = 6, SU_UWBW = 7,
+  NU_CORE = 8,
+  SU_AGE_EST_RESET = 8, SU_PC_COUNT = 9, SU_AGE_MON_CMD = 10, SU_AGE_MON_LOOP = 11,
+  NU_PAD = 12
+};
+enum { NC_PAD = 84 };
+
+template<typename P> struct VecOf;
+#if defined(__CUDACC__)
+template<> struct VecOf<double> {
+  typedef double2 type;
+  static constexpr int lanes = 2;
+  static AGF_HDI void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+  static AGF_HDI double2 pack(const double* o) { return make_double2(o[0], o[1]); }
+};
+template<> struct VecOf<float> {
+  typedef float4 type;
+  static constexpr int lanes = 4;
+  static AGF_HDI void unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  static AGF_HDI float4 pack(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
+};
+
+template<typename P>
+struct StateArrays {
+  typename VecOf<P>::type* sp;
+  float4* sf;
+  uint4* su;
+  float4* sc;  // null unless the batch ranges against UWB anchors
+};
+#endif
+
+// ---- shared (per batch) parameters -----------------------------------------------------------
+struct Lpf2Coef {  // LowPassFilterSecondOrder coefficients, computed on the host in float
+  float a1, a2, b0, b1, b2;
+};
+
+struct LogicParams {  // what QuadcopterLogic::Initialise derives from QuadcopterConstants
+  Lpf2Coef lp_gyro, lp_acc, lp_temp, lp_batt;
+  float R_imu[9], R_imu_inv[9];
+  int imu_identity;
+  float mass, ixx, izz;
+  float nat_freq, damping;
+  float tc_att_xy, tc_att_z, tc_w_xy, tc_w_z;
+  float mix_d, mix_kt, mix_kf, max_cmd_total, min_thrust, max_thrust;
+  float batt_voltage, batt_warning, batt_critical;
+  float onboard_period;
+  float mon_cmd_coef, mon_loop_coef;  // LowPassFilterFirstOrder coefficients (expf on the host)
+  int valid;
+};
+
+struct TimingConsts {
+  double logic_period;    // Quadcopter_T::_onboardLogicPeriod
+  uint32_t logic_adj_us;  // uint64_t(period * 1e6) of Timer::AdjustTimeBySeconds
+  double comm_period;     // UWBNetwork::_commPeriod
+  int net_enabled;
+  int n_anchors;
+};
+
+// Stopwatch readings that are identical for every vehicle of a batch (they depend on the clock
+// only): Quadcopter_T::_integrationTimer, ::_timerOnboardLogic, KalmanFilter6DOF::_estimateTimer,
+// UWBNetwork::_timeSinceLastRange and the network's transaction flag.  Evolved by the same
+// function on the host (to carry them across launches) and on the device (per tick).
+struct Timing {
+  uint32_t integ_age, logic_age, kf_age, net_age;
+  uint32_t net_active, has_target;
+};
+
+struct TickPlan {
+  uint32_t plant_dt_us, kf_dt_us;
+  bool run_plant, run_logic, run_net, net_start, net_complete, net_reset, has_target;
+};
+
+AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc) {
+  TickPlan p;
+  p.plant_dt_us = ts.integ_age;
+  p.kf_dt_us = ts.kf_age;
+  // Quadcopter_T.cpp:87-90: dt = GetSeconds<double>(); if (dt < 1e-6) return;
+  p.run_plant = !(double(ts.integ_age) * double(1e-6) < 1e-6);
+  // Quadcopter_T.cpp:159: if (_timerOnboardLogic.GetSeconds<double>() > _onboardLogicPeriod)
+  p.run_logic = p.run_plant && (double(ts.logic_age) * double(1e-6) > tc.logic_period);
+  p.has_target = ts.has_target || (p.run_logic && tc.n_anchors > 0);
+  // UWBNetwork.cpp:28: if (_timeSinceLastRange.GetSeconds<double>() < _commPeriod) return;
+  p.run_net = tc.net_enabled && !(double(ts.net_age) * double(1e-6) < tc.comm_period);
+  p.net_start = p.net_complete = p.net_reset = false;
+  if (p.run_net) {
+    if (!ts.net_active) {
+      p.net_start = p.has_target;  // :32-41 a requester with a target exists
+      p.net_reset = true;          // :43 the stopwatch restarts whether or not one was found
+    } else {
+      p.net_complete = true;
+    }
+  }
+  return p;
+}
+
+AGF_HDI void timing_advance(Timing& ts, const TimingConsts& tc, const TickPlan& p, uint32_t dt_us) {
+  if (p.run_plant) ts.integ_age = 0;
+  if (p.run_logic) {
+    ts.logic_age -= tc.logic_adj_us;
+    ts.kf_age = 0;
+  }
+  ts.has_target = p.has_target;
+  if (p.net_start) ts.net_active = 1;
+  if (p.net_complete) ts.net_active = 0;
+  if (p.net_reset) ts.net_age = 0;
+  ts.integ_age += dt_us;
+  ts.logic_age += dt_us;
+  ts.kf_age += dt_us;
+  ts.net_age += dt_us;
+}
+
+struct AnchorDev {
+  float x, y, z;
+  uint32_t id;
+};
+
+template<typename P>
+struct StepShared {
+  LogicParams logic;
+  TimingConsts tc;
+  P motor_min, motor_max, motor_J;
+  P motor_pos[4][3];
+  P drag[3];
+  int has_drag;
+  const P* ext_force;   // [3][N] world frame, or null
+  const P* ext_torque;  // [3][N]
+  AnchorDev anchors[AGF_MAX_UWB_ANCHORS];
+  uint32_t n_anchors;
+  uint64_t seed;
+  int noise_on, bias_on, uwb_noise_on;
+  float sigma_gyro, sigma_acc, bias_sigma_gyro, bias_sigma_acc, uwb_sigma;
+};
+
+// plant parameters that may vary per vehicle (parameter sweeps)
+template<typename P>
+struct PlantPV {
+  P mass;
+  P I[9], Iinv[9];
+  P kF, kTau;
+  P motor_c;  // exp(-dt/tau) of Motor.cpp:53-57 for the dt of this launch, evaluated on the host
+};
+
+#if defined(__CUDACC__)
+// per-vehicle plant parameters in HBM: 3 quads of P-lanes... stored as plain component arrays
+// grouped in 16-byte quads like the state: {mass, ixx, iyy, izz}, {iinv_xx, iinv_yy, iinv_zz, kF},
+// {kTau, motor_c, 0, 0}  -> NPV_PAD scalars
+enum { PV_MASS = 0, PV_IXX = 1, PV_IYY = 2, PV_IZZ = 3, PV_IIXX = 4, PV_IIYY = 5, PV_IIZZ = 6, PV_KF = 7,
+       PV_KTAU = 8, PV_MOTOR_C = 9, NPV_PAD = 12 };
+
+struct SchedEntryDev {
+  uint64_t tick;
+  int32_t slot;
+  uint32_t type, flags;
+  float f[4];
+  uint32_t pad_;
+};
+
+struct SlotArrays {
+  const float4* f;      // [N] floats[0..3] of each vehicle's packet
+  const uint32_t* tf;   // [N] type | flags << 8
+};
+
+template<typename P>
+struct StepLaunch {
+  StepShared<P> sh;
+  StateArrays<P> st;
+  const typename VecOf<P>::type* pv;  // per-vehicle plant parameters [NPV_PAD/lanes][N], or null
+  PlantPV<P> pv_shared;
+  size_t n;
+  uint64_t tick0;
+  uint32_t nticks, dt_us;
+  Timing ts;
+  const SchedEntryDev* sched;
+  uint32_t sched_begin, sched_end;
+  SlotArrays slots[AGF_MAX_CMD_SLOTS];
+  P* log;  // [capacity][AGF_LOG_FIELDS][N] or null
+  uint32_t log_stride, log_capacity;
+  uint64_t first_global_index;
+};
+#endif
+
+}  // namespace agf

@@ -1,0 +1,192 @@
+// oracle/hostsim/agf_hostsim.cu -- TEST INFRASTRUCTURE: the product's device step header
+// (agri-fly_b200/csrc/agf_step.cuh) compiled for the HOST and driven through oracle/oracle_api.h.
+//
+// Purpose: separates "is the re-formulated step (sparse EKF algebra, packed flags, uniform timing,
+// quad-packed state serialisation) logically identical to the reference?" -- answerable in the
+// build container, which has no GPU, by comparing this library with oracle/_ref bit for bit --
+// from "does the GPU execute the same arithmetic?" (the -m gpu parity tests).
+// It is NOT a product path: nothing in agri-fly_b200/ loads it, and agf_batch_create refuses to
+// run without a CUDA device.
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../oracle_api.h"
+#include "../../agri-fly_b200/csrc/agf_host_params.h"
+#include "../../agri-fly_b200/csrc/agf_step.cuh"
+
+using namespace agf;
+
+#ifndef ORC_FLAVOUR
+#define ORC_FLAVOUR "hostsim-shared"
+#endif
+
+struct orc_vehicle {
+  agf_vehicle_cfg cfg;
+  orc_opts opts;
+  StepShared<double> sh;
+  PlantPV<double> pv;
+  Timing ts;
+  bool uwb;
+  std::vector<double> hp, ext_f, ext_t;
+  std::vector<float> hf, hc;
+  std::vector<uint32_t> hu;
+  uint64_t tick, now_us;
+  StateArrays<double> arrays() {
+    StateArrays<double> a;
+    a.sp = (double2*)hp.data();
+    a.sf = (float4*)hf.data();
+    a.su = (uint4*)hu.data();
+    a.sc = uwb ? (float4*)hc.data() : nullptr;
+    return a;
+  }
+};
+
+template<bool UWB>
+static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entry* sched, uint32_t nsched,
+                     const uint8_t* slot_raw, double* traj) {
+  VState<double, UWB, true> s;
+  StateArrays<double> a = v->arrays();
+  state_load(s, a, 1, 0);
+  v->sh.ext_force = v->ext_f.empty() ? nullptr : v->ext_f.data();
+  v->sh.ext_torque = v->ext_t.empty() ? nullptr : v->ext_t.data();
+  uint32_t si = 0;
+  while (si < nsched && sched[si].tick < v->tick) si++;
+  for (uint32_t k = 0; k < nticks; k++) {
+    // the launch-constant motor coefficient for the dt the plant will integrate over
+    const uint32_t plant_dt = v->ts.integ_age ? v->ts.integ_age : dt_us;
+    v->pv.motor_c = motor_c_host(v->cfg.motor_time_const, plant_dt);
+    if (si < nsched && sched[si].tick == v->tick) {
+      const uint8_t* raw = sched[si].raw;
+      if (sched[si].slot >= 0 && slot_raw) raw = slot_raw + AGF_RADIO_PACKET_SIZE * sched[si].slot;
+      uint8_t type, flags;
+      float f[10];
+      agf_radio_decode(raw, &type, &flags, f);
+      radio_deliver(s, v->sh.logic, type, flags, f);
+      si++;
+    }
+    tick<double, true, UWB, true>(s, v->sh, v->pv, v->ts, dt_us, v->tick, 0, 0, 1);
+    if (traj) {
+      double* r = traj + size_t(k) * ORC_NTRAJ;
+      for (int c = 0; c < 3; c++) { r[c] = s.pos[c]; r[3 + c] = s.vel[c]; r[10 + c] = s.w[c]; r[21 + c] = s.kpos[c]; r[24 + c] = s.kvel[c]; r[31 + c] = s.kw[c]; }
+      for (int c = 0; c < 4; c++) { r[6 + c] = s.att[c]; r[13 + c] = s.ms[c]; r[17 + c] = s.cmd[c]; r[27 + c] = s.katt[c]; }
+      r[34] = s.bits & 7u;
+      r[35] = (s.bits >> 3) & 7u;
+      r[36] = s.cycle;
+      r[37] = s.kfcnt & 0xFFFFu;
+      r[38] = s.kfcnt >> 16;
+      r[39] = s.uwb_count;
+    }
+    v->tick++;
+    v->now_us += dt_us;
+  }
+  state_store(s, a, 1, 0);
+}
+
+extern "C" {
+
+const char* orc_flavour(void) { return ORC_FLAVOUR; }
+
+orc_vehicle* orc_create(const agf_vehicle_cfg* cfg, const orc_opts* opts) {
+  orc_vehicle* v = new orc_vehicle();
+  v->cfg = *cfg;
+  v->opts = *opts;
+  v->uwb = opts->uwb_comm_period > 0;
+  build_shared(*cfg, opts->onboard_logic_period, opts->uwb_comm_period, v->sh);
+  fill_plant(*cfg, v->pv);
+  memset(&v->ts, 0, sizeof(v->ts));
+  initial_state<double>(1, v->sh.logic, cfg->logic.low_battery_threshold, v->uwb, v->hp, v->hf, v->hu, v->hc);
+  v->tick = 0;
+  v->now_us = 0;
+  return v;
+}
+void orc_destroy(orc_vehicle* v) { delete v; }
+
+void orc_set_state(orc_vehicle* v, const double p[3], const double vel[3], const double a[4], const double w[3]) {
+  for (int k = 0; k < 3; k++) {
+    v->hp[sidx(SP_POS + k, 1, 0, 2)] = p[k];
+    v->hp[sidx(SP_VEL + k, 1, 0, 2)] = vel[k];
+    v->hp[sidx(SP_W + k, 1, 0, 2)] = w[k];
+  }
+  for (int k = 0; k < 4; k++) v->hp[sidx(SP_ATT + k, 1, 0, 2)] = a[k];
+}
+void orc_set_external(orc_vehicle* v, const double f[3], const double t[3]) {
+  if (v->ext_f.empty()) { v->ext_f.assign(3, 0.0); v->ext_t.assign(3, 0.0); }
+  if (f) for (int k = 0; k < 3; k++) v->ext_f[k] = f[k];
+  if (t) for (int k = 0; k < 3; k++) v->ext_t[k] = t[k];
+}
+int orc_add_anchor(orc_vehicle* v, uint8_t id, float x, float y, float z) {
+  if (v->sh.n_anchors >= AGF_MAX_UWB_ANCHORS) return -1;
+  AnchorDev& a = v->sh.anchors[v->sh.n_anchors++];
+  a.id = id; a.x = x; a.y = y; a.z = z;
+  v->sh.tc.n_anchors = int(v->sh.n_anchors);
+  return 0;
+}
+void orc_set_radio(orc_vehicle* v, const uint8_t raw[23]) {
+  agf_cmd_entry e;
+  memset(&e, 0, sizeof(e));
+  e.tick = uint32_t(v->tick);
+  e.slot = -1;
+  memcpy(e.raw, raw, 23);
+  // deliver through a zero-tick run: load, deliver, store
+  if (v->uwb) {
+    VState<double, true, true> s; StateArrays<double> a = v->arrays(); state_load(s, a, 1, 0);
+    uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0);
+  } else {
+    VState<double, false, true> s; StateArrays<double> a = v->arrays(); state_load(s, a, 1, 0);
+    uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0);
+  }
+}
+void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entry* sched, uint32_t nsched,
+             const uint8_t* slot_raw, double* traj) {
+  if (v->uwb) run_impl<true>(v, dt_us, nticks, sched, nsched, slot_raw, traj);
+  else run_impl<false>(v, dt_us, nticks, sched, nsched, slot_raw, traj);
+}
+
+void orc_get_full(orc_vehicle* v, orc_full_state* o) {
+  memset(o, 0, sizeof(*o));
+  auto P_ = [&](int k) { return v->hp[sidx(k, 1, 0, 2)]; };
+  auto F_ = [&](int k) { return v->hf[sidx(k, 1, 0, 4)]; };
+  auto U_ = [&](int k) { return v->hu[sidx(k, 1, 0, 4)]; };
+  for (int k = 0; k < 3; k++) { o->pos[k] = P_(SP_POS + k); o->vel[k] = P_(SP_VEL + k); o->ang_vel[k] = P_(SP_W + k); }
+  for (int k = 0; k < 4; k++) {
+    o->att[k] = P_(SP_ATT + k);
+    o->motor_speed[k] = P_(SP_MS + k);
+    o->motor_force_z[k] = (v->pv.kF * o->motor_speed[k]) * fabs(o->motor_speed[k]);
+    o->motor_speed_cmd[k] = F_(SF_CMD + k);
+    o->des_motor_speeds[k] = F_(SF_CMD + k);
+    o->des_motor_forces[k] = F_(SF_DFORCE + k);
+    o->kf_att[k] = F_(SF_KATT + k);
+    o->temp_lpf[k] = F_(SF_TEMP_LP + k);
+    o->batt_lpf[k] = F_(SF_BATT_LP + k);
+  }
+  const uint32_t bits = U_(SU_BITS), cnt = U_(SU_CNT), kc = U_(SU_KFCNT), w = U_(SU_UWBW);
+  o->flight_state = bits & 7u;
+  o->first_panic_reason = (bits >> 3) & 7u;
+  o->cycle_counter = int(U_(SU_CYCLE));
+  o->tel_warnings = (cnt >> 24) & 0xFFu;
+  for (int c = 0; c < 3; c++)
+    for (int k = 0; k < 4; k++) { o->gyro_lpf[k][c] = F_(SF_GYRO_LP + 4 * c + k); o->acc_lpf[k][c] = F_(SF_ACC_LP + 4 * c + k); }
+  o->batt_voltage_filtered = F_(SF_BATT_VFILT);
+  o->monitor_cmd_rate_lpdt = F_(SF_MON_CMD);
+  o->monitor_main_loop_lpdt = F_(SF_MON_LOOP);
+  o->radio_type = (bits >> 6) & 7u;
+  o->radio_flags = (bits >> 9) & 0xFFu;
+  for (int k = 0; k < 4; k++) o->radio_floats[k] = F_(SF_RADIO + k);
+  o->uwb_meas_count = int(U_(SU_UWB_COUNT));
+  o->next_ranging_target_idx = (w >> 24) & 0xFFu;
+  for (int k = 0; k < 3; k++) { o->kf_pos[k] = F_(SF_KPOS + k); o->kf_vel[k] = F_(SF_KVEL + k); o->kf_ang_vel[k] = F_(SF_KW + k); o->kf_last_corr[k] = F_(SF_KCORR + k); }
+  if (v->uwb) for (int k = 0; k < 81; k++) o->kf_cov[k] = v->hc[sidx(k, 1, 0, 4)];
+  o->kf_imu_init = (bits >> 18) & 1u;
+  o->kf_uwb_init = (bits >> 19) & 1u;
+  o->kf_num_resets = kc & 0xFFFFu;
+  o->kf_num_rejected = kc >> 16;
+  o->kf_num_rejected_seq = cnt & 0xFFu;
+  o->debug[0] = o->cycle_counter ? F_(SF_TEMP_LP + 3) : 0.0f;
+}
+
+uint64_t orc_time_us(orc_vehicle* v) { return v->now_us; }
+
+}  // extern "C"

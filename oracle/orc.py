@@ -13,12 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _load_abi():
-    import importlib.util
-    p = os.path.join(HERE, "..", "agri-fly_b200", "_abi.py")
-    spec = importlib.util.spec_from_file_location("agf_abi_for_oracle", p)
-    m = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(m)
-    return m
+    # struct layouts come from the product's ABI mirror (a header-like module; loading it does not
+    # load the CUDA library)
+    import sys
+    root = os.path.dirname(HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import agrifly_b200
+    return agrifly_b200.abi
 
 
 abi = _load_abi()
@@ -71,6 +73,7 @@ PATHS = {
     "ref-shared": os.path.join(HERE, "_ref", "libagf_ref_shared.so"),
     "port-glibc": os.path.join(HERE, "libagf_port_glibc.so"),
     "port-shared": os.path.join(HERE, "libagf_port_shared.so"),
+    "hostsim-shared": os.path.join(HERE, "libagf_hostsim_shared.so"),
 }
 
 
@@ -107,21 +110,23 @@ class Oracle:
         L.orc_set_radio.argtypes = [vp, C.c_char_p]
         L.orc_run.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.CmdEntry), C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_get_full.argtypes = [vp, P(FullState)]
-        L.orc_get_telemetry.argtypes = [vp, C.c_void_p, C.c_void_p]
-        L.orc_get_imu.argtypes = [vp, P(C.c_double), P(C.c_double)]
         L.orc_time_us.restype = C.c_uint64
         L.orc_time_us.argtypes = [vp]
-        L.orc_run_population.restype = C.c_double
-        L.orc_run_population.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
-                                         C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),
-                                         C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        if not flavour.startswith("hostsim"):
+            L.orc_get_telemetry.argtypes = [vp, C.c_void_p, C.c_void_p]
+            L.orc_get_imu.argtypes = [vp, P(C.c_double), P(C.c_double)]
+            L.orc_run_population.restype = C.c_double
+            L.orc_run_population.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
+                                             C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),
+                                             C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         if flavour.startswith("ref-"):  # codec cross-checks exist only against the real reference
             L.orc_radio_encode_rates.argtypes = [C.c_uint8, C.c_float, P(C.c_float), C.c_void_p]
             L.orc_radio_encode_position.argtypes = [C.c_uint8, P(C.c_float), P(C.c_float), P(C.c_float), C.c_void_p]
             L.orc_radio_encode_acceleration.argtypes = [C.c_uint8, P(C.c_float), C.c_float, C.c_void_p]
             L.orc_telemetry_decode.argtypes = [C.c_void_p, P(abi.Telemetry)]
             L.orc_logic_consts.argtypes = [C.c_int, P(abi.LogicConsts)]
-        L.orc_radio_decode.argtypes = [C.c_void_p, P(C.c_uint8), P(C.c_uint8), P(C.c_float)]
+        if not flavour.startswith("hostsim"):
+            L.orc_radio_decode.argtypes = [C.c_void_p, P(C.c_uint8), P(C.c_uint8), P(C.c_float)]
         self.L = L
         assert L.orc_flavour().decode() == flavour, (L.orc_flavour(), flavour)
 
