@@ -1,0 +1,52 @@
+"""Shared helpers for the parity tests: run a scenario on an oracle or on the CUDA batch."""
+import numpy as np
+
+
+def cfg_for(agf, sc, **extra):
+    kw = dict(motor_time_const=sc["motor_time_const"], motor_inertia=sc["motor_inertia"])
+    kw.update(extra)
+    return agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], **kw)
+
+
+def run_oracle(O, agf, sc, nticks=None, record=True, cfg=None, **kw):
+    v = O.vehicle(cfg if cfg is not None else cfg_for(agf, sc), uwb_comm_period=sc["uwb_comm_period"], **kw)
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    for i, p in sc["anchors"]:
+        v.add_anchor(i, p)
+    tr = v.run(nticks or sc["nticks"], sched=sc["sched"], record=record)
+    return tr, v
+
+
+def make_batch(agf, sc, n=1, cfg=None, **kw):
+    b = agf.Batch(cfg if cfg is not None else cfg_for(agf, sc), n, uwb_comm_period=sc["uwb_comm_period"], **kw)
+    for i, p in sc["anchors"]:
+        b.add_anchor(i, p)
+    s13 = np.zeros((n, 13))
+    s13[:, 0:3] = sc["pos"]
+    s13[:, 6:10] = sc["att"]
+    b.set_state13(s13)
+    b.set_schedule(sc["sched"])
+    return b
+
+
+def run_batch_traj(b, nticks, every=1):
+    """Step the batch `every` ticks at a time and record vehicle 0 after each chunk -> [k][40]."""
+    out = []
+    done = 0
+    while done < nticks:
+        c = min(every, nticks - done)
+        b.run(c)
+        done += c
+        out.append(b.record()[0])
+    return np.array(out)
+
+
+def rel_err(a, b, floor=1.0):
+    """max |a-b| / max(|b|, floor) -- relative where the quantity is large, absolute near zero."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def bit_equal(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))

@@ -1,0 +1,141 @@
+"""CPU tests of the oracle: the literal port (oracle/port) against golden vectors recorded from the
+unmodified reference (tests/golden/reference_vectors.npz, made by tests/golden/make_golden.py), against
+the live reference build when oracle/_ref is present, and against the host-compiled product step."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import bit_equal, run_oracle
+from conftest import ROOT, oracle_or_skip
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+SCENARIOS = ["rates", "full", "accel"]
+
+
+def scenario(agf, name):
+    s = agf.scenarios
+    return {"rates": s.rates_scenario, "full": s.full_scenario, "accel": s.accel_scenario}[name](agf.codec)
+
+
+FULL_SKIP = {"radio_floats"}  # floats beyond those a message type decodes are uninitialised in the reference
+
+
+@pytest.mark.parametrize("math", ["glibc", "shared"])
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_port_matches_reference_golden(agf, orc_mod, math, name):
+    O = oracle_or_skip(orc_mod, "port-" + math)
+    tr, v = run_oracle(O, agf, scenario(agf, name))
+    key = "ref-%s/%s" % (math, name)
+    idx = GOLD[key + "/ticks"]
+    assert bit_equal(tr[idx], GOLD[key + "/traj"]), "port trajectory differs from the reference's"
+    full = v.full()
+    for k, val in full.items():
+        if k in FULL_SKIP:
+            continue
+        assert bit_equal(np.asarray(val), GOLD[key + "/full/" + k]), k
+    p1, p2 = v.telemetry()
+    assert np.array_equal(p1, GOLD[key + "/tel1"]) and np.array_equal(p2, GOLD[key + "/tel2"])
+
+
+@pytest.mark.parametrize("math", ["glibc", "shared"])
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_port_matches_live_reference(agf, orc_mod, math, name):
+    R = oracle_or_skip(orc_mod, "ref-" + math)
+    P = oracle_or_skip(orc_mod, "port-" + math)
+    sc = scenario(agf, name)
+    a, _ = run_oracle(R, agf, sc)
+    b, _ = run_oracle(P, agf, sc)
+    assert bit_equal(a, b)
+
+
+def test_reference_golden_still_reproducible(agf, orc_mod):
+    """The committed vectors are what the reference build in this container produces today."""
+    R = oracle_or_skip(orc_mod, "ref-glibc")
+    tr, _ = run_oracle(R, agf, scenario(agf, "rates"))
+    assert bit_equal(tr[GOLD["ref-glibc/rates/ticks"]], GOLD["ref-glibc/rates/traj"])
+
+
+def test_survey_sanity_vectors(agf, port_glibc):
+    """SURVEY.md section 8c probe values for the rates-mode scenario (recorded independently)."""
+    tr, _ = run_oracle(port_glibc, agf, scenario(agf, "rates"))
+    assert tr[999, 0] == 0 and tr[999, 1] == 0
+    assert abs(tr[999, 2] - 0.939083617525108) < 1e-14
+    assert abs(tr[999, 5] - 0.960208197878) < 1e-11
+    assert abs(tr[999, 13] - 2909.44384766) < 1e-7
+    np.testing.assert_allclose(tr[4999, 0:3], [0.342036496412748, -0.886737158754551, 24.3015536037538], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(tr[4999, 6:10], [0.999999946981528, 1.30944008436e-4, -1.00535276674e-4, 2.80683562528e-4], rtol=0, atol=1e-12)
+
+
+def test_full_mode_counters(agf, port_glibc):
+    tr, _ = run_oracle(port_glibc, agf, scenario(agf, "full"))
+    assert tr[-1, 39] == 1665 and tr[-1, 38] == 0 and tr[-1, 37] == 2 and tr[-1, 35] == 0 and tr[-1, 34] == 2
+    # closed-loop tracking of the last set-point
+    assert np.linalg.norm(tr[-1, 0:3] - np.array([1.5, 0.7, 2.0])) < 0.02
+
+
+def test_hostsim_matches_port(agf, orc_mod, port_shared):
+    """The product's device step header compiled for the host == the literal port, bit for bit."""
+    if not orc_mod.available("hostsim-shared"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "hostsim"], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("hostsim does not build here: " + r.stderr[-300:])
+    H = orc_mod.Oracle("hostsim-shared")
+    for name in SCENARIOS:
+        sc = scenario(agf, name)
+        a, va = run_oracle(port_shared, agf, sc)
+        b, vb = run_oracle(H, agf, sc)
+        assert bit_equal(a, b), name
+        fa, fb = va.full(), vb.full()
+        keys = ["pos", "vel", "att", "ang_vel", "motor_speed", "motor_force_z", "motor_speed_cmd", "flight_state",
+                "first_panic_reason", "cycle_counter", "tel_warnings", "des_motor_forces", "gyro_lpf", "acc_lpf",
+                "temp_lpf", "batt_lpf", "batt_voltage_filtered", "monitor_cmd_rate_lpdt", "monitor_main_loop_lpdt",
+                "uwb_meas_count", "next_ranging_target_idx", "kf_pos", "kf_vel", "kf_att", "kf_ang_vel", "kf_last_corr",
+                "kf_imu_init", "kf_uwb_init", "kf_num_resets", "kf_num_rejected", "kf_num_rejected_seq"]
+        if sc["uwb_comm_period"] > 0:
+            keys.append("kf_cov")
+        for k in keys:
+            assert bit_equal(fa[k], fb[k]), (name, k)
+
+
+def test_hostsim_chunked_runs_equal_single_run(agf, orc_mod):
+    """Serialising the state to the HBM layout between launches loses nothing."""
+    if not orc_mod.available("hostsim-shared"):
+        pytest.skip("hostsim not built")
+    H = orc_mod.Oracle("hostsim-shared")
+    sc = scenario(agf, "full")
+    a, _ = run_oracle(H, agf, sc, nticks=1500)
+    v = H.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"]),
+                  uwb_comm_period=sc["uwb_comm_period"])
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    for i, p in sc["anchors"]:
+        v.add_anchor(i, p)
+    parts = [v.run(c, sched=sc["sched"]) for c in (1, 1, 7, 91, 400, 1000)]
+    assert bit_equal(a, np.concatenate(parts))
+
+
+# ---- physics properties of the oracle (the same ones the GPU tests use at full size) -------------
+def test_hover_equilibrium_speed(agf, port_glibc):
+    """omega_hover = sqrt(m g / (4 kF)) holds the vehicle still."""
+    cfg = agf.vehicle_cfg(vehicle_id=1)
+    v = port_glibc.vehicle(cfg)
+    v.set_state(pos=(0, 0, 1.0))
+    # rates command with thrust exactly g: the mixer asks each motor for m g / 4
+    raw = agf.codec.encode_rates(0, 9.81, (0, 0, 0))
+    sched = [(k, raw, -1) for k in range(0, 1000, 10)]
+    tr = v.run(1000, sched=sched)
+    w_hover = np.sqrt(cfg.mass * 9.81 / (4 * cfg.prop_thrust_from_speed_sqr))
+    assert abs(tr[-1, 13] / w_hover - 1) < 2e-4  # 16-bit thrust quantisation
+    assert abs(tr[-1, 5]) < 0.05
+
+
+def test_quaternion_norm_drift_is_bounded(agf, port_glibc):
+    tr, _ = run_oracle(port_glibc, agf, scenario(agf, "rates"))
+    assert np.max(np.abs(np.linalg.norm(tr[:, 6:10], axis=1) - 1)) < 1e-12
+
+
+def test_time_base_latencies(agf, port_glibc):
+    """Run() before Advance(): tick 0 is a no-op, logic first runs at tick 2."""
+    tr, _ = run_oracle(port_glibc, agf, scenario(agf, "rates"), nticks=10)
+    assert list(tr[:5, 36]) == [0, 0, 1, 2, 3]

@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (oracle/port) on
+identical initial states and command sequences, and against the committed reference vectors.
+
+Tolerances (north_star): FP64 mode (the reference's own mixed precision) noise-free: <= 1e-9 relative
+on position, velocity, attitude and motor speed over the 10 s horizon.  The parity arithmetic variant
+is in fact required to be BIT-IDENTICAL to the oracle built with the same shared libm; the 1e-9 bound
+is asserted separately so a last-bit regression is told apart from a real one.
+FP32 / fast variants: see test_fast_variants_tolerance for the stated (looser, sensitivity-limited) bounds.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import bit_equal, cfg_for, make_batch, rel_err, run_oracle
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+PLANT_COLS = slice(0, 17)
+
+
+def scenario(agf, name):
+    s = agf.scenarios
+    return {"rates": s.rates_scenario, "full": s.full_scenario, "accel": s.accel_scenario}[name](agf.codec)
+
+
+def gpu_traj(agf, sc, n=1, sample_every=250, **kw):
+    """Runs the scenario on the GPU: plant columns of every tick from the HBM trajectory log, all 40
+    columns at every `sample_every`-th tick from the field getters."""
+    b = make_batch(agf, sc, n=n, **kw)
+    nt = sc["nticks"]
+    b.enable_log(1, nt)
+    samples, ticks = [], []
+    done = 0
+    while done < nt:
+        c = min(sample_every, nt - done)
+        b.run(c)
+        done += c
+        samples.append(b.record())
+        ticks.append(done - 1)
+    b.sync()
+    assert b.log_count == nt
+    log = np.stack([b.read_log(r) for r in range(nt)])  # [tick][vehicle][17]
+    return b, log, np.array(ticks), np.stack(samples)    # samples [k][vehicle][40]
+
+
+@pytest.mark.parametrize("name", ["rates", "full", "accel"])
+def test_parity_variant_is_bit_identical_to_oracle(agf, port_shared, name):
+    sc = scenario(agf, name)
+    ref, v = run_oracle(port_shared, agf, sc)
+    b, log, ticks, samples = gpu_traj(agf, sc, n=3)
+    for veh in range(3):  # identical vehicles must stay identical
+        # stated tolerance first (1e-9 relative), then the stronger bit-level claim
+        assert rel_err(log[:, veh, :], ref[:, PLANT_COLS]) <= 1e-9
+        assert bit_equal(log[:, veh, :], ref[:, PLANT_COLS]), "plant trajectory differs in the last bit"
+        assert bit_equal(samples[:, veh, :], ref[ticks]), "estimator / logic read-outs differ"
+    # telemetry packets, including warnings and the packet counter side effect
+    p1, p2 = b.telemetry()
+    o1, o2 = v.telemetry()
+    assert np.array_equal(p1[0], o1) and np.array_equal(p2[0], o2)
+    p1b, _ = b.telemetry()
+    assert p1b[0][1] == 1
+    b.close()
+
+
+@pytest.mark.parametrize("name", ["rates", "full", "accel"])
+def test_parity_variant_matches_reference_golden(agf, name):
+    """Same check against vectors recorded from the unmodified reference (sharedmath build)."""
+    sc = scenario(agf, name)
+    key = "ref-shared/" + name
+    idx = GOLD[key + "/ticks"]
+    b, log, _, _ = gpu_traj(agf, sc, n=1, sample_every=sc["nticks"])
+    assert bit_equal(log[idx, 0, :], GOLD[key + "/traj"][:, PLANT_COLS])
+    # unmodified reference with the platform libm: reported, sensitivity-limited
+    g = GOLD["ref-glibc/" + name + "/traj"]
+    err = rel_err(log[idx, 0, 0:3], g[:, 0:3])
+    print("GPU parity variant vs reference(glibc) %s: max rel position error %.3e" % (name, err))
+    assert err < (1e-9 if name == "rates" else 5e-3)
+    b.close()
+
+
+def test_launch_chunking_is_invisible(agf):
+    """5000 ticks in one launch == the same ticks split over many launches (state round-trips HBM)."""
+    sc = scenario(agf, "full")
+    sc["nticks"] = 1500
+    b1 = make_batch(agf, sc, n=2)
+    b1.run(1500)
+    b2 = make_batch(agf, sc, n=2)
+    for c in (1, 1, 7, 91, 400, 1000):
+        b2.run(c)
+    assert bit_equal(b1.record(), b2.record())
+    assert bit_equal(b1.get("est_covariance"), b2.get("est_covariance"))
+    assert b1.ticks == b2.ticks == 1500 and b1.time_us == 3000000
+    b1.close()
+    b2.close()
+
+
+def test_monte_carlo_population_parity(agf, port_shared):
+    """BASELINE config 2 at a size the oracle finishes in seconds: randomized initial states, per-vehicle
+    hover set-points (command slot), full onboard mode, noise-free, FP64 parity -> bit-identical."""
+    n, nt = 192, 2500
+    s = agf.scenarios
+    sc = s.full_scenario(agf.codec, nticks=nt)
+    init = s.monte_carlo_initial_states(n, seed=1234)
+    idle = agf.codec.encode_idle(0)
+    slot = np.array([np.frombuffer(agf.codec.encode_position(0, (p[0], p[1], 1.5)), np.uint8) for p in init])
+    sched = [(d, idle, -1) if sl == -2 else (d, None, 0) for d, _, sl in s.hover_slot_schedule(nt)]
+    cfg = cfg_for(agf, sc)
+    anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
+    slots = np.zeros((4, n, 23), np.uint8)
+    slots[0] = slot
+    ref, _ = port_shared.run_population(cfg, n, init13=init, anchors=anchors, nticks=nt, sched=sched, slot_raw=slots,
+                                        threads=os.cpu_count() or 1, uwb_comm_period=sc["uwb_comm_period"])
+    b = agf.Batch(cfg, n, uwb_comm_period=sc["uwb_comm_period"])
+    for i, p in sc["anchors"]:
+        b.add_anchor(i, p)
+    b.set_state13(init)
+    b.set_slot(0, slot)
+    b.set_schedule(sched)
+    b.run(nt)
+    got = b.record()
+    assert rel_err(got[:, 0:17], ref[:, 0:17]) <= 1e-9
+    assert bit_equal(got, ref)
+    # every vehicle hovers at its own set-point
+    assert np.all(np.abs(got[:, 2] - 1.5) < 0.1) and np.all(got[:, 35] == 0)
+    b.close()
+
+
+def test_per_vehicle_parameter_sweep_parity(agf, port_shared):
+    """BASELINE config 4's parameter sweep (mass, inertia, motor constants per vehicle), FP64 parity."""
+    n = 24
+    sc = scenario(agf, "rates")
+    sc["nticks"] = 1500
+    rng = np.random.default_rng(5)
+    cfgs = []
+    for i in range(n):
+        c = cfg_for(agf, sc)
+        c.mass *= rng.uniform(0.8, 1.2)
+        c.inertia[0] *= rng.uniform(0.7, 1.3)
+        c.inertia[4] = c.inertia[0]
+        c.inertia[8] *= rng.uniform(0.7, 1.3)
+        c.prop_thrust_from_speed_sqr *= rng.uniform(0.9, 1.1)
+        c.prop_torque_from_speed_sqr *= rng.uniform(0.8, 1.2)
+        c.motor_time_const = rng.uniform(0.0, 0.05) if i else 0.0
+        cfgs.append(c)
+    b = agf.Batch(cfgs, n)
+    b.set_schedule(sc["sched"])
+    b.run(sc["nticks"])
+    got = b.record()
+    for i in (0, 1, 7, n - 1):
+        ref, _ = run_oracle(port_shared, agf, sc, cfg=cfgs[i])
+        assert bit_equal(got[i], ref[-1]), i
+    assert np.std(got[:, 2]) > 0.05  # the sweep really produced different vehicles
+    b.close()
+
+
+def test_immediate_radio_command_and_external_wrench(agf, port_shared):
+    sc = scenario(agf, "rates")
+    cfg = cfg_for(agf, sc)
+    raw1 = agf.codec.encode_rates(0, 10.5, (0.1, -0.2, 0.05))
+    raw2 = agf.codec.encode_rates(0, 9.0, (0.0, 0.0, 0.0))
+    v = port_shared.vehicle(cfg)
+    v.set_state(pos=(0, 0, 2.0))
+    b = agf.Batch(cfg, 2)
+    b.set("position", [[0, 0, 2.0], [0, 0, 2.0]])
+    for who in (v, b):
+        who.run(5)
+        who.set_radio(raw1)
+        who.run(200)
+        (who.set_external(force=(0.05, 0, 0), torque=(0, 0, 1e-4)) if who is v else
+         who.set_external_wrench(force=(0.05, 0, 0), torque=(0, 0, 1e-4)))
+        who.run(100)
+        who.set_radio(raw2)
+        who.run(300)
+    ref = v.run(1)[-1]
+    b.run(1)
+    assert bit_equal(b.record()[0], ref) and bit_equal(b.record()[1], ref)
+    b.close()
+
+
+def test_radio_timeout_panic_and_kill_latch(agf, port_shared):
+    """1.5 s without a radio command while motors run -> FS_PANIC (QuadcopterLogic.cpp:372-376)."""
+    cfg = agf.vehicle_cfg(vehicle_id=1)
+    raw = agf.codec.encode_rates(0, 10.0, (0, 0, 0))
+    v = port_shared.vehicle(cfg)
+    b = agf.Batch(cfg, 4)
+    for who in (v, b):
+        who.set_radio(raw)
+        who.run(900)
+    ref = v.run(1)[-1]
+    b.run(1)
+    got = b.record()
+    assert ref[34] == agf.abi.FS_PANIC and ref[35] == 4
+    assert bit_equal(got[0], ref)
+    b.set_radio(agf.codec.encode_kill(0), first=1, count=2)
+    b.run(3)
+    fs = b.get("flight_state")[:, 0]
+    assert list(fs) == [3, 3, 3, 3]  # PANIC is a sink: kill does not leave it
+    b.close()
+
+
+def test_field_get_set_round_trip(agf):
+    n = 1000
+    b = agf.Batch(agf.vehicle_cfg(vehicle_id=13), n, math=agf.abi.MATH_FAST, precision=agf.abi.PREC_FP32)
+    rng = np.random.default_rng(0)
+    for name in ("position", "velocity", "attitude", "angular_velocity", "motor_speed"):
+        nc = agf.abi.FIELDS[name][2]
+        x = rng.normal(size=(n, nc)).astype(np.float32).astype(np.float64)
+        b.set(name, x)
+        assert np.array_equal(b.get(name), x)
+        y = rng.normal(size=(10, nc)).astype(np.float32).astype(np.float64)
+        b.set(name, y, first=500)
+        assert np.array_equal(b.get(name, 500, 10), y) and np.array_equal(b.get(name, 0, 500), x[:500])
+    with pytest.raises(agf.AgfError):
+        b.get("position", first=990, count=20)
+    with pytest.raises(agf.AgfError):
+        b.set("flight_state", np.zeros((n, 1), np.int32))
+    assert np.all(b.get("flight_state") == agf.abi.FS_IDLE)
+    b.close()
+
+
+def test_fast_variants_tolerance(agf, port_glibc):
+    """Fast arithmetic (FMA contraction, CUDA libm) in FP64 and FP32 plant precision against the oracle.
+    Stated tolerances: rates mode is open loop in attitude, errors integrate: 1e-9 (FP64-fast, FMA only
+    reorders plant arithmetic) / 1e-4 relative (FP32).  Full mode closes the loop through the float EKF and
+    is sensitivity-limited (a last-bit float difference moves the 10 s position by ~1e-4..1e-3 even between
+    two builds of the reference itself): 2e-3 (FP64-fast) / 5e-3 m (FP32)."""
+    out = {}
+    for name, tol64, tol32 in (("rates", 1e-9, 1e-4), ("full", 2e-3, 5e-3)):
+        sc = scenario(agf, name)
+        ref, _ = run_oracle(port_glibc, agf, sc)
+        for prec, tol in ((agf.abi.PREC_FP64, tol64), (agf.abi.PREC_FP32, tol32)):
+            b = make_batch(agf, sc, n=2, precision=prec, math=agf.abi.MATH_FAST)
+            b.run(sc["nticks"])
+            got = b.record()[0]
+            e_pos = rel_err(got[0:3], ref[-1, 0:3])
+            e_all = rel_err(got[0:17], ref[-1, 0:17])
+            out[(name, prec)] = (e_pos, e_all)
+            print("fast %s prec=%d: rel err pos %.3e, plant state %.3e" % (name, prec, e_pos, e_all))
+            assert e_pos <= tol, (name, prec, e_pos)
+            assert got[35] == 0
+            b.close()
+
+
+def test_imu_noise_statistics(agf):
+    """Noise on: the synthesized IMU noise has the reference's stated distribution (Quadcopter_T.cpp:5-6:
+    sigma_gyro 0.1 rad/s, sigma_acc 0.2 m/s^2, zero mean, white, independent across axes and vehicles).
+    Observed through the onboard 2nd-order low-pass outputs of vehicles resting on the ground."""
+    n, nt = 8192, 400
+    cfg = agf.vehicle_cfg(vehicle_id=1)
+    b = agf.Batch(cfg, n, sigma_gyro=0.1, sigma_acc=0.2, seed=99)
+    b.run(300)
+    gy, ac = [], []
+    for _ in range(nt // 40):
+        b.run(40)  # 40 ticks apart: far beyond the filters' memory -> independent samples
+        gy.append(b.get("rate_gyro"))
+        ac.append(b.get("accelerometer"))
+    gy, ac = np.array(gy, np.float64), np.array(ac, np.float64)
+
+    def gain(wc, dt=0.002):  # noise gain sqrt(sum h^2) of LowPassFilterSecondOrder.hpp:39-63
+        s2 = np.sqrt(2.0)
+        den = dt * dt * wc * wc + 2 * s2 * dt * wc + 4
+        a1, a2 = (dt * dt * wc * wc - 2 * s2 * dt * wc + 4) / den, 2 * (dt * dt * wc * wc - 4) / den
+        b0 = b1 = dt * dt * wc * wc / den
+        b2 = 2 * b0
+        x = np.zeros(2000)
+        x[0] = 1
+        y = np.zeros(2000)
+        for k in range(2000):
+            y[k] = b2 * x[k] + b0 * (x[k - 2] if k >= 2 else 0) + b1 * (x[k - 1] if k >= 1 else 0) \
+                - a1 * (y[k - 2] if k >= 2 else 0) - a2 * (y[k - 1] if k >= 1 else 0)
+        return np.sqrt(np.sum(y * y)), np.sum(y)
+
+    gg, dc_g = gain(200.0)
+    ga, dc_a = gain(100.0)
+    assert abs(dc_g - 1) < 1e-6 and abs(dc_a - 1) < 1e-6  # LPF DC gain = 1
+    m = gy.size // 3
+    for ax in range(3):
+        g = gy[:, :, ax].ravel()
+        a = ac[:, :, ax].ravel() - (9.81 if ax == 2 else 0.0)
+        assert abs(g.mean()) < 5 * 0.1 * gg / np.sqrt(m) and abs(a.mean()) < 5 * 0.2 * ga / np.sqrt(m) + 2e-5
+        assert abs(g.std() / (0.1 * gg) - 1) < 0.02 and abs(a.std() / (0.2 * ga) - 1) < 0.02
+        kurt = np.mean((g - g.mean()) ** 4) / g.var() ** 2
+        assert abs(kurt - 3) < 0.1  # Gaussian
+    c = np.corrcoef(gy.reshape(-1, 3).T)
+    assert np.max(np.abs(c - np.eye(3))) < 0.02  # axes independent
+    # vehicles independent, and successive samples of one vehicle independent (white at this spacing)
+    assert abs(np.corrcoef(gy[:, 0:n // 2, 0].ravel(), gy[:, n // 2:, 0].ravel())[0, 1]) < 0.02
+    assert abs(np.corrcoef(gy[:-1, :, 1].ravel(), gy[1:, :, 1].ravel())[0, 1]) < 0.02
+    # a different seed gives a different realisation, the same seed the same one
+    b2 = agf.Batch(cfg, 64, sigma_gyro=0.1, sigma_acc=0.2, seed=99)
+    b3 = agf.Batch(cfg, 64, sigma_gyro=0.1, sigma_acc=0.2, seed=100)
+    b4 = agf.Batch(cfg, 64, sigma_gyro=0.1, sigma_acc=0.2, seed=99, first_global_index=32)
+    for x in (b2, b3, b4):
+        x.run(340)
+    assert np.array_equal(b2.get("rate_gyro"), gy[0, :64].astype(np.float32))
+    assert not np.array_equal(b2.get("rate_gyro"), b3.get("rate_gyro"))
+    assert np.array_equal(b4.get("rate_gyro")[:32], b2.get("rate_gyro")[32:])  # shard offset = global index
+    for x in (b, b2, b3, b4):
+        x.close()
+
+
+def test_imu_bias_extension(agf):
+    n = 4096
+    b = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, sigma_gyro=1e-9, sigma_acc=1e-9, bias_sigma_gyro=0.01, bias_sigma_acc=0.05)
+    b.run(800)
+    g, a = b.get("rate_gyro").astype(np.float64), b.get("accelerometer").astype(np.float64)
+    a[:, 2] -= 9.81
+    assert abs(g.std() / 0.01 - 1) < 0.05 and abs(a.std() / 0.05 - 1) < 0.05 and abs(g.mean()) < 1e-3
+    b.run(100)
+    assert np.allclose(b.get("rate_gyro"), g, atol=1e-5)  # a bias is constant in time
+    b.close()
+
+
+def test_full_size_population_properties(agf):
+    """BASELINE config 3's per-GPU shard at full size (131072 vehicles, FP32, full onboard mode with EKF
+    and UWB, IMU noise on, 4-waypoint square): size-independent properties + the statistics kernel."""
+    n, nt = 131072, 1500
+    s = agf.scenarios
+    cfg = agf.vehicle_cfg(vehicle_id=1, motor_time_const=0.015)
+    b = agf.Batch(cfg, n, precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST, uwb_comm_period=0.004,
+                  sigma_gyro=0.1, sigma_acc=0.2, seed=7, telemetry_warnings=False)
+    for i, p in s.ANCHORS_8:
+        b.add_anchor(i, p)
+    init = s.monte_carlo_initial_states(n, seed=1234)
+    b.set_state13(init)
+    b.set_schedule(s.waypoint_square_schedule(agf.codec, nticks=nt))
+    b.run(nt)
+    rec = b.record()
+    assert np.all(np.isfinite(rec))
+    assert np.max(np.abs(np.linalg.norm(rec[:, 6:10], axis=1) - 1)) < 1e-3   # plant attitude stays unit (FP32)
+    assert np.all(rec[:, 35] == 0) and np.all(rec[:, 34] == agf.abi.FS_FULLY_AUTONOMOUS)
+    assert np.all(rec[:, 36] == nt - 2)                                      # logic ran on every tick from tick 2
+    assert np.all(rec[:, 39] == rec[0, 39]) and rec[0, 39] > 400             # UWB ranges: clock-driven, identical count
+    target = np.array([1.0, 1.0, 1.5])
+    err = np.linalg.norm(rec[:, 0:3] - target, axis=1)
+    assert np.median(err) < 0.15 and err.max() < 1.0                         # tracking the first waypoint with noise
+    est_err = np.linalg.norm(rec[:, 21:24] - rec[:, 0:3], axis=1)
+    assert np.median(est_err) < 0.1
+    st = b.stats()
+    assert st[0] == n and st[6] == 0 and st[8] == n and st[9] == 0
+    tq = np.array(agf.codec.decode(agf.codec.encode_position(0, target))[2][:3], np.float64)
+    e = rec[:, 0:3] - tq
+    np.testing.assert_allclose(st[1:4], e.sum(axis=0), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(st[4], np.sum(e * e), rtol=1e-9)
+    np.testing.assert_allclose(st[14], np.linalg.norm(e, axis=1).max(), rtol=1e-12)
+    np.testing.assert_allclose(st[15], est_err.max(), rtol=1e-6)
+    st2 = b.stats(target=np.tile(target, (n, 1)))
+    np.testing.assert_allclose(st2[5], err.sum(), rtol=1e-9)
+    b.close()
+
+
+def test_trajectory_log_ring(agf):
+    n = 300
+    b = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST)
+    b.set_radio(agf.codec.encode_rates(0, 11.0, (0.3, 0.0, 0.1)))
+    b.run(7)
+    b.enable_log(5, 8)   # every 5th tick, ring of 8 records
+    snaps = {}
+    for k in range(12):
+        b.run(5)
+        if b.ticks % 5 == 0:
+            snaps[b.log_count - 1] = b.record()[:, 0:17]
+    assert b.log_count == (7 + 60) // 5 - 7 // 5
+    for rec in range(b.log_count - 8, b.log_count):
+        if rec in snaps:
+            assert np.array_equal(b.read_log(rec), snaps[rec]), rec
+    with pytest.raises(agf.AgfError):
+        b.read_log(0)  # overwritten
+    b.close()
