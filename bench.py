@@ -116,6 +116,7 @@ class ClockSampler:
 
 
 def workload(agf, n, first, precision, ticks_total, seed=7, device=0, stream=None, hk=False, uwb=True, noise=True):
+    import numpy as np
     s = agf.scenarios
     cfg = agf.vehicle_cfg(vehicle_id=1, motor_time_const=0.015)
     prec = agf.abi.PREC_FP32 if precision == "fp32" else agf.abi.PREC_FP64
@@ -125,7 +126,7 @@ def workload(agf, n, first, precision, ticks_total, seed=7, device=0, stream=Non
     if uwb:
         for i, p in s.ANCHORS_8:
             b.add_anchor(i, p)
-    init = s.monte_carlo_initial_states(first + n, seed=1234)[first:]
+    init = s.monte_carlo_initial_states(first + n, seed=1234, yaw_max=np.pi / 3)[first:]
     b.set_state13(init)
     if uwb:
         b.set_schedule(s.waypoint_square_schedule(agf.codec, nticks=ticks_total))
@@ -153,7 +154,7 @@ def cpu_baseline(args, n_threads=None, seconds=12.0):
     # calibrate: ~4e5 vehicle-steps/s/core for the full mode at -O3
     n = int(seconds * cores * 4e5 / nticks)
     n = max(cores * 4, min(n, cores * 8192))
-    init = s.monte_carlo_initial_states(n, seed=1234)
+    init = s.monte_carlo_initial_states(n, seed=1234, yaw_max=np.pi / 3)
     _, secs = O.run_population(cfg, n, init13=init, anchors=anchors, nticks=nticks, sched=sched, threads=cores,
                                uwb_comm_period=0.004, sigma_acc=0.2 if kind == "reference" else 0.0,
                                sigma_gyro=0.1 if kind == "reference" else 0.0)

@@ -1,0 +1,26 @@
+"""Workload driver for the ncu captures in profiles/ (see profiles/README.md for the commands).
+Usage: python profiles/prof_step.py [fp32|fp64] [uwb|rates] [vehicles] [ticks] [launches]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import agrifly_b200 as agf  # noqa: E402
+import bench  # noqa: E402
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+uwb = (sys.argv[2] if len(sys.argv) > 2 else "uwb") == "uwb"
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 131072
+ticks = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+launches = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+b, _ = bench.workload(agf, n, 0, prec, ticks * (launches + 1) + 600, uwb=uwb)
+b.run(500)  # warm-up launch: take-off, EKF initialised, UWB ranging active
+for _ in range(launches):
+    b.run(ticks)
+b.sync()
+ms, nl = b.step_kernel_time()
+print("step kernel: %d launches, %.3f ms total; last %d: %.3e vehicle-steps/s" %
+      (nl, ms, launches, 0 if nl == 0 else n * (500 + ticks * launches) / (ms * 1e-3)))
+st = b.stats()
+print("panic", st[6], "nonfinite", st[9], "rms err", np.sqrt(st[4] / st[0]))
