@@ -23,8 +23,8 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (source, extra flags).  The parity kernels must not be FMA-contracted.
 UNITS = [
     ("agf_kernels_parity.cu", ["-fmad=false"]),
-    ("agf_kernels_fast_f64.cu", []),
-    ("agf_kernels_fast_f32.cu", []),
+    ("agf_kernels_fast_f64.cu", ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
+    ("agf_kernels_fast_f32.cu", ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
     ("agf_batch.cu", ["-fmad=false"]),
     ("agf_config.cpp", []),
 ]

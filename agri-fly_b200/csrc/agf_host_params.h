@@ -85,6 +85,13 @@ inline void derive_logic(const agf_logic_consts& k, float onboard_period, LogicP
   o.onboard_period = onboard_period;
   o.mon_cmd_coef = expf(-0.02f * 1.0f);             // QuadcopterLogic.cpp:14, LowPassFilterFirstOrder.hpp:31
   o.mon_loop_coef = expf(-onboard_period * 50.0f);  // QuadcopterLogic.cpp:15
+  o.inv_mix_d = 1.0f / o.mix_d;
+  o.inv_mix_kt = 1.0f / o.mix_kt;
+  o.inv_mix_kf = 1.0f / o.mix_kf;
+  o.inv_tc_w_xy = 1.0f / o.tc_w_xy;
+  o.inv_tc_w_z = 1.0f / o.tc_w_z;
+  o.k3_att = 1.0f / o.tc_att_z;
+  o.k12_att = 1.0f / o.tc_att_xy;
   o.valid = k.valid;
 }
 
@@ -132,6 +139,7 @@ inline void build_shared(const agf_vehicle_cfg& c0, double onboard_logic_period,
   sh.tc.comm_period = uwb_comm_period;
   sh.tc.net_enabled = uwb_comm_period > 0 ? 1 : 0;
   sh.tc.n_anchors = 0;
+  timing_thresholds(sh.tc);
   sh.motor_min = P(c0.motor_min_speed);
   sh.motor_max = P(c0.motor_max_speed);
   sh.motor_J = P(c0.motor_inertia);

@@ -8,12 +8,18 @@ namespace agf {
 
 cudaError_t launch_step_fast_f64(const StepLaunch<double>& L, bool uwb, bool hk, int block, cudaStream_t stream) {
   const unsigned grid = unsigned((L.n + block - 1) / block);
+  static bool carveout_set = false;
+  if (!carveout_set) {  // the scratch of 4 resident blocks needs most of the SM's shared memory
+    cudaFuncSetAttribute(step_kernel<double, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(step_kernel<double, false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
   if (uwb) {
-    if (hk) step_kernel<double, false, true, true><<<grid, block, 0, stream>>>(L);
-    else step_kernel<double, false, true, false><<<grid, block, 0, stream>>>(L);
+    if (hk) step_kernel<double, false, true, true><<<grid, block, step_smem_bytes<false, true>(block), stream>>>(L);
+    else step_kernel<double, false, true, false><<<grid, block, step_smem_bytes<false, true>(block), stream>>>(L);
   } else {
-    if (hk) step_kernel<double, false, false, true><<<grid, block, 0, stream>>>(L);
-    else step_kernel<double, false, false, false><<<grid, block, 0, stream>>>(L);
+    if (hk) step_kernel<double, false, false, true><<<grid, block, step_smem_bytes<false, false>(block), stream>>>(L);
+    else step_kernel<double, false, false, false><<<grid, block, step_smem_bytes<false, false>(block), stream>>>(L);
   }
   return cudaGetLastError();
 }

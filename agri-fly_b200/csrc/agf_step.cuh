@@ -56,16 +56,71 @@ struct Mf<true> {
   static AGF_DEV double sin(double x) { return agf_sin(x); }
   static AGF_DEV double cos(double x) { return agf_cos(x); }
 };
+// Fast variants: the step only ever takes sin/cos of HALF rotation angles per tick (|x| << 1), so a
+// short odd/even polynomial (error < 1e-9 relative for |x| <= 0.5) serves the hot path and the
+// general libm routine is an out-of-line fallback that keeps the code small.
+static __device__ __noinline__ float slow_sinf(float x) { return ::sinf(x); }
+static __device__ __noinline__ float slow_cosf(float x) { return ::cosf(x); }
+static __device__ __noinline__ double slow_sin(double x) { return ::sin(x); }
+static __device__ __noinline__ double slow_cos(double x) { return ::cos(x); }
 template<>
 struct Mf<false> {
+#if defined(__CUDA_ARCH__)
+  static AGF_DEV float sin(float x) {
+    if (::fabsf(x) > 0.5f) return slow_sinf(x);
+    const float z = x * x;
+    float p = ::fmaf(z, 2.75573192e-6f, -1.98412698e-4f);
+    p = ::fmaf(z, p, 8.33333333e-3f);
+    p = ::fmaf(z, p, -1.66666667e-1f);
+    return ::fmaf(x * z, p, x);
+  }
+  static AGF_DEV float cos(float x) {
+    if (::fabsf(x) > 0.5f) return slow_cosf(x);
+    const float z = x * x;
+    float p = ::fmaf(z, 2.48015873e-5f, -1.38888889e-3f);
+    p = ::fmaf(z, p, 4.16666667e-2f);
+    p = ::fmaf(z, p, -0.5f);
+    return ::fmaf(z, p, 1.0f);
+  }
+  static AGF_DEV double sin(double x) {
+    if (::fabs(x) > 0.5) return slow_sin(x);
+    const double z = x * x;
+    double p = ::fma(z, 1.6059043836821613e-10, -2.5052108385441720e-8);
+    p = ::fma(z, p, 2.7557319223985893e-6);
+    p = ::fma(z, p, -1.9841269841269841e-4);
+    p = ::fma(z, p, 8.3333333333333333e-3);
+    p = ::fma(z, p, -1.6666666666666667e-1);
+    return ::fma(x * z, p, x);
+  }
+  static AGF_DEV double cos(double x) {
+    if (::fabs(x) > 0.5) return slow_cos(x);
+    const double z = x * x;
+    double p = ::fma(z, -1.1470745597729725e-11, 2.0876756987868099e-9);
+    p = ::fma(z, p, -2.7557319223985888e-7);
+    p = ::fma(z, p, 2.4801587301587302e-5);
+    p = ::fma(z, p, -1.3888888888888889e-3);
+    p = ::fma(z, p, 4.1666666666666664e-2);
+    p = ::fma(z, p, -0.5);
+    return ::fma(z, p, 1.0);
+  }
+#else
   static AGF_DEV float sin(float x) { return ::sinf(x); }
   static AGF_DEV float cos(float x) { return ::cosf(x); }
+  static AGF_DEV double sin(double x) { return ::sin(x); }
+  static AGF_DEV double cos(double x) { return ::cos(x); }
+#endif
   static AGF_DEV float asin(float x) { return ::asinf(x); }
   static AGF_DEV float acos(float x) { return ::acosf(x); }
   static AGF_DEV float atan2(float y, float x) { return ::atan2f(y, x); }
-  static AGF_DEV double sin(double x) { return ::sin(x); }
-  static AGF_DEV double cos(double x) { return ::cos(x); }
 };
+// division: IEEE in the parity variant, reciprocal-multiply in the fast ones
+template<bool PARITY> AGF_DEV float fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  if (!PARITY) return __fdividef(a, b);
+#endif
+  return a / b;
+}
+template<bool PARITY> AGF_DEV double fdiv(double a, double b) { return a / b; }
 AGF_DEV float rsqrt_(float x) { return ::sqrtf(x); }
 AGF_DEV double rsqrt_(double x) { return ::sqrt(x); }
 AGF_DEV float rabs_(float x) { return ::fabsf(x); }
@@ -91,6 +146,11 @@ template<typename R> AGF_DEV V3<R> cross(const V3<R>& a, const V3<R>& b) {
   return V3<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 template<typename R> AGF_DEV R norm(const V3<R>& a) { return rsqrt_(dot(a, a)); }
+template<bool PARITY, typename R> AGF_DEV V3<R> vdiv(const V3<R>& v, R s) {
+  if (PARITY) return V3<R>(v.x / s, v.y / s, v.z / s);
+  const R inv = fdiv<false>(R(1), s);
+  return V3<R>(v.x * inv, v.y * inv, v.z * inv);
+}
 
 // Matrix<Real,3,3> * Vec3 (Vec3.hpp:202-210): accumulate from 0 in column order
 template<typename R>
@@ -158,7 +218,7 @@ template<bool PARITY, typename R>
 AGF_DEV bool q_from_rotvec(const V3<R>& rv, Q4<R>& out) {
   const R theta = norm(rv);
   if (theta < R(4.84813681e-6)) return false;
-  out = q_from_axis_angle<PARITY>(rv / theta, theta);
+  out = q_from_axis_angle<PARITY>(vdiv<PARITY>(rv, theta), theta);
   return true;
 }
 template<bool PARITY, typename R>
@@ -186,7 +246,7 @@ AGF_DEV V3<float> q_to_rotvec(const Q4<float>& q) {
   const float nn = norm(n);
   const float angle = Mf<PARITY>::asin(nn) * 2;
   if (angle < 4.84813681e-6f) return V3<float>(0, 0, 0);
-  return n * (angle / nn);
+  return n * fdiv<PARITY>(angle, nn);
 }
 // acosf with the reference's errno fallback (KalmanFilter6DOF.cpp:95-103)
 template<bool PARITY>
@@ -221,9 +281,10 @@ AGF_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
   return uint32_t((uint64_t(a) * uint64_t(b)) >> 32);
 #endif
 }
-AGF_DEV uint4 philox4x32_10(uint4 ctr, uint2 key) {
+template<int ROUNDS>
+AGF_DEV uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
-  for (int r = 0; r < 10; r++) {
+  for (int r = 0; r < ROUNDS; r++) {
     const uint32_t hi0 = mulhi32(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
     const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -235,11 +296,12 @@ AGF_DEV uint4 philox4x32_10(uint4 ctr, uint2 key) {
 AGF_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   const float u1 = (float(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
   const float u2 = float(b >> 8) * (1.0f / 16777216.0f);           // [0, 1)
-  const float r = ::sqrtf(-2.0f * ::logf(u1));
 #if defined(__CUDA_ARCH__)
+  const float r = ::sqrtf(-2.0f * __logf(u1));
   float s, c;
-  ::sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.28318530718f * u2, &s, &c);
 #else
+  const float r = ::sqrtf(-2.0f * ::logf(u1));
   const float s = ::sinf(6.28318530718f * u2), c = ::cosf(6.28318530718f * u2);
 #endif
   n0 = r * c;
@@ -248,8 +310,8 @@ AGF_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
 // 6 standard normals for (vehicle, cycle, stream)
 AGF_DEV void normals6(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream, float* n) {
   const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
-  const uint4 a = philox4x32_10(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u), key);
-  const uint4 b = philox4x32_10(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u + 1u), key);
+  const uint4 a = philox4x32<10>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u), key);
+  const uint4 b = philox4x32<10>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u + 1u), key);
   box_muller(a.x, a.y, n[0], n[1]);
   box_muller(a.z, a.w, n[2], n[3]);
   box_muller(b.x, b.y, n[4], n[5]);
@@ -258,15 +320,17 @@ AGF_DEV void normals6(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t 
 // ---------------------------------------------------------------------------------------------
 // register-resident vehicle state
 // ---------------------------------------------------------------------------------------------
-template<typename P, bool UWB, bool HK>
+template<typename P, bool PARITY, bool UWB, bool HK>
 struct VState {
   // plant
   P pos[3], vel[3], att[4], w[3], ms[4];
   // logic
   float cmd[4];      // _desMotorSpeeds == _motorSpeedCommands after every logic run
-  float dforce[4];   // _desMotorForcesForTelemetry
+  float dforce[(PARITY || HK) ? 4 : 1];   // _desMotorForcesForTelemetry (fast, no HK: derived from cmd)
   float radio_f[4];  // floats[0..3] of the last radio message (the only ones any controller reads)
-  float gyro_lp[12], acc_lp[12];  // [xm0 xm1 ym0 ym1] x 3 components, component-major: [4*c + k]
+  // IMU low-pass states [xm0 xm1 ym0 ym1] x 3 components, component-major [4*c + k]: in registers in the
+  // parity variant, in the thread's shared-memory scratch in the fast variants (Scratch below)
+  float gyro_lp[PARITY ? 12 : 1], acc_lp[PARITY ? 12 : 1];
   float kpos[3], kvel[3], kw[3], katt[4], kcorr[3];
   float uwb_range;    // range held by the vehicle's radio (UWBRadio::_meas.range)
   float logic_range;  // range handed to the logic (QuadcopterLogic::_uwbRangeMeas.range)
@@ -282,8 +346,9 @@ struct VState {
   float batt_vfilt, mon_cmd_lpdt, mon_loop_lpdt;
   float pc_accum[4], pc_corr[4];
   uint32_t pc_count, age_mon_cmd, age_mon_loop;
-  // estimator covariance (UWB)
-  float cov[UWB ? 81 : 1];
+  // estimator covariance (UWB): full 9x9 in registers in the parity variant (the reference's predict step
+  // does not keep it exactly symmetric); packed upper triangle in shared-memory scratch in the fast variants
+  float cov[(UWB && PARITY) ? 81 : 1];
   // radio true position latched at the last logic run (UWBRadio::_uwbTruePosition)
   P rpos[UWB ? 3 : 1];
 };
@@ -309,9 +374,41 @@ AGF_DEV uint32_t bset(uint32_t w, uint32_t shift, uint32_t mask, uint32_t v) {
   return (w & ~(mask << shift)) | ((v & mask) << shift);
 }
 
+// Thread-private scratch in shared memory (fast variants): quads laid out [quad][thread] so that a
+// warp's 128-bit accesses are conflict free.  Holds what is touched once per tick but would otherwise
+// pin ~70 registers for the whole tick: the six IMU low-pass states and the packed EKF covariance.
+struct Scratch {
+  float4* q;   // already offset by the thread index
+  int stride;  // threads per block
+};
+enum { SQ_LPF = 0, SQ_COV = 6, SQ_QUADS_NOUWB = 6, SQ_QUADS_UWB = 18 };
+// packed upper triangle of a symmetric 9x9
+AGF_DEV constexpr int SI(int i, int j) {
+  return i <= j ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
+}
+AGF_DEV void cov_load(const Scratch& sc, float* P) {
+#pragma unroll
+  for (int q = 0; q < 12; q++) {
+    const float4 v = sc.q[(SQ_COV + q) * sc.stride];
+    P[4 * q] = v.x; P[4 * q + 1] = v.y; P[4 * q + 2] = v.z; P[4 * q + 3] = v.w;
+  }
+}
+AGF_DEV void cov_store(const Scratch& sc, const float* P) {
+#pragma unroll
+  for (int q = 0; q < 12; q++) sc.q[(SQ_COV + q) * sc.stride] = make_float4(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3]);
+}
+AGF_DEV float lpf2_scratch(const Lpf2Coef& c, const Scratch& sc, int quad, float in) {
+  float4 st = sc.q[(SQ_LPF + quad) * sc.stride];  // {xm0, xm1, ym0, ym1}
+  float out = c.b2 * in;
+  out = out + (c.b0 * st.x + c.b1 * st.y);
+  out = out + ((-c.a1) * st.z - c.a2 * st.w);
+  sc.q[(SQ_LPF + quad) * sc.stride] = make_float4(st.y, in, st.w, out);
+  return out;
+}
+
 // --- flat (de)serialisation order; the host get/set kernels use the same tables (agf_types.h) ---
-template<typename P, bool UWB, bool HK>
-AGF_DEV void state_load(VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i) {
+template<typename P, bool PARITY, bool UWB, bool HK>
+AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i, const Scratch& sc) {
   typedef typename VecOf<P>::type PV;
   constexpr int VP = VecOf<P>::lanes;
   P rp[NP_PAD];
@@ -324,7 +421,7 @@ AGF_DEV void state_load(VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n
   for (int k = 0; k < 3; k++) { s.pos[k] = rp[SP_POS + k]; s.vel[k] = rp[SP_VEL + k]; s.w[k] = rp[SP_W + k]; }
 #pragma unroll
   for (int k = 0; k < 4; k++) { s.att[k] = rp[SP_ATT + k]; s.ms[k] = rp[SP_MS + k]; }
-  if (UWB) {
+  if constexpr (UWB) {
 #pragma unroll
     for (int k = 0; k < 3; k++) s.rpos[k] = rp[SP_RPOS + k];
   }
@@ -336,14 +433,26 @@ AGF_DEV void state_load(VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n
     rf[4 * q] = v.x; rf[4 * q + 1] = v.y; rf[4 * q + 2] = v.z; rf[4 * q + 3] = v.w;
   }
 #pragma unroll
-  for (int k = 0; k < 4; k++) { s.cmd[k] = rf[SF_CMD + k]; s.dforce[k] = rf[SF_DFORCE + k]; s.radio_f[k] = rf[SF_RADIO + k]; s.katt[k] = rf[SF_KATT + k]; }
+  for (int k = 0; k < 4; k++) { s.cmd[k] = rf[SF_CMD + k]; s.radio_f[k] = rf[SF_RADIO + k]; s.katt[k] = rf[SF_KATT + k]; }
+  if constexpr (PARITY || HK) {
 #pragma unroll
-  for (int k = 0; k < 12; k++) { s.gyro_lp[k] = rf[SF_GYRO_LP + k]; s.acc_lp[k] = rf[SF_ACC_LP + k]; }
+    for (int k = 0; k < 4; k++) s.dforce[k] = rf[SF_DFORCE + k];
+  }
+  if constexpr (PARITY) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) { s.gyro_lp[k] = rf[SF_GYRO_LP + k]; s.acc_lp[k] = rf[SF_ACC_LP + k]; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      sc.q[(SQ_LPF + c) * sc.stride] = make_float4(rf[SF_GYRO_LP + 4 * c], rf[SF_GYRO_LP + 4 * c + 1], rf[SF_GYRO_LP + 4 * c + 2], rf[SF_GYRO_LP + 4 * c + 3]);
+      sc.q[(SQ_LPF + 3 + c) * sc.stride] = make_float4(rf[SF_ACC_LP + 4 * c], rf[SF_ACC_LP + 4 * c + 1], rf[SF_ACC_LP + 4 * c + 2], rf[SF_ACC_LP + 4 * c + 3]);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 3; k++) { s.kpos[k] = rf[SF_KPOS + k]; s.kvel[k] = rf[SF_KVEL + k]; s.kw[k] = rf[SF_KW + k]; s.kcorr[k] = rf[SF_KCORR + k]; }
   s.uwb_range = rf[SF_UWB_RANGE];
   s.logic_range = rf[SF_LOGIC_RANGE];
-  if (HK) {
+  if constexpr (HK) {
 #pragma unroll
     for (int k = 0; k < 4; k++) { s.temp_lp[k] = rf[SF_TEMP_LP + k]; s.batt_lp[k] = rf[SF_BATT_LP + k]; s.pc_accum[k] = rf[SF_PC_ACCUM + k]; s.pc_corr[k] = rf[SF_PC_CORR + k]; }
     s.batt_vfilt = rf[SF_BATT_VFILT]; s.mon_cmd_lpdt = rf[SF_MON_CMD]; s.mon_loop_lpdt = rf[SF_MON_LOOP];
@@ -359,20 +468,31 @@ AGF_DEV void state_load(VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n
   s.uwb_count = ru[SU_UWB_COUNT]; s.age_radio = ru[SU_AGE_RADIO]; s.age_uwb = ru[SU_AGE_UWB];
   s.uwbw = ru[SU_UWBW];
   if (HK) { s.age_est_reset = ru[SU_AGE_EST_RESET]; s.pc_count = ru[SU_PC_COUNT]; s.age_mon_cmd = ru[SU_AGE_MON_CMD]; s.age_mon_loop = ru[SU_AGE_MON_LOOP]; }
-  if (UWB) {
+  if constexpr (UWB) {
+    float full[NC_PAD];
 #pragma unroll
     for (int q = 0; q < NC_PAD / 4; q++) {
       float4 v = a.sc[size_t(q) * n + i];
-      if (4 * q + 0 < 81) s.cov[4 * q + 0] = v.x;
-      if (4 * q + 1 < 81) s.cov[4 * q + 1] = v.y;
-      if (4 * q + 2 < 81) s.cov[4 * q + 2] = v.z;
-      if (4 * q + 3 < 81) s.cov[4 * q + 3] = v.w;
+      full[4 * q + 0] = v.x; full[4 * q + 1] = v.y; full[4 * q + 2] = v.z; full[4 * q + 3] = v.w;
+    }
+    if constexpr (PARITY) {
+#pragma unroll
+      for (int k = 0; k < 81; k++) s.cov[k] = full[k];
+    } else {
+      float Ps[48];
+#pragma unroll
+      for (int k = 45; k < 48; k++) Ps[k] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 9; r++)
+#pragma unroll
+        for (int c = r; c < 9; c++) Ps[SI(r, c)] = full[9 * r + c];
+      cov_store(sc, Ps);
     }
   }
 }
 
-template<typename P, bool UWB, bool HK>
-AGF_DEV void state_store(const VState<P, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i) {
+template<typename P, bool PARITY, bool UWB, bool HK>
+AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i, const Scratch& sc, float mix_kf) {
   typedef typename VecOf<P>::type PV;
   constexpr int VP = VecOf<P>::lanes;
   P rp[NP_PAD];
@@ -382,7 +502,7 @@ AGF_DEV void state_store(const VState<P, UWB, HK>& s, const StateArrays<P>& a, s
   for (int k = 0; k < 3; k++) { rp[SP_POS + k] = s.pos[k]; rp[SP_VEL + k] = s.vel[k]; rp[SP_W + k] = s.w[k]; }
 #pragma unroll
   for (int k = 0; k < 4; k++) { rp[SP_ATT + k] = s.att[k]; rp[SP_MS + k] = s.ms[k]; }
-  if (UWB) {
+  if constexpr (UWB) {
 #pragma unroll
     for (int k = 0; k < 3; k++) rp[SP_RPOS + k] = s.rpos[k];
   }
@@ -395,14 +515,28 @@ AGF_DEV void state_store(const VState<P, UWB, HK>& s, const StateArrays<P>& a, s
 #pragma unroll
   for (int k = 0; k < NF_PAD; k++) rf[k] = 0.0f;
 #pragma unroll
-  for (int k = 0; k < 4; k++) { rf[SF_CMD + k] = s.cmd[k]; rf[SF_DFORCE + k] = s.dforce[k]; rf[SF_RADIO + k] = s.radio_f[k]; rf[SF_KATT + k] = s.katt[k]; }
+  for (int k = 0; k < 4; k++) {
+    rf[SF_CMD + k] = s.cmd[k]; rf[SF_RADIO + k] = s.radio_f[k]; rf[SF_KATT + k] = s.katt[k];
+    // fast variant without housekeeping: the commanded force is not carried, it is the mixer's thrust<->speed map inverted
+    if constexpr (PARITY || HK) rf[SF_DFORCE + k] = s.dforce[k];
+    else rf[SF_DFORCE + k] = mix_kf * s.cmd[k] * s.cmd[k];
+  }
+  if constexpr (PARITY) {
 #pragma unroll
-  for (int k = 0; k < 12; k++) { rf[SF_GYRO_LP + k] = s.gyro_lp[k]; rf[SF_ACC_LP + k] = s.acc_lp[k]; }
+    for (int k = 0; k < 12; k++) { rf[SF_GYRO_LP + k] = s.gyro_lp[k]; rf[SF_ACC_LP + k] = s.acc_lp[k]; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float4 g = sc.q[(SQ_LPF + c) * sc.stride], a4 = sc.q[(SQ_LPF + 3 + c) * sc.stride];
+      rf[SF_GYRO_LP + 4 * c] = g.x; rf[SF_GYRO_LP + 4 * c + 1] = g.y; rf[SF_GYRO_LP + 4 * c + 2] = g.z; rf[SF_GYRO_LP + 4 * c + 3] = g.w;
+      rf[SF_ACC_LP + 4 * c] = a4.x; rf[SF_ACC_LP + 4 * c + 1] = a4.y; rf[SF_ACC_LP + 4 * c + 2] = a4.z; rf[SF_ACC_LP + 4 * c + 3] = a4.w;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 3; k++) { rf[SF_KPOS + k] = s.kpos[k]; rf[SF_KVEL + k] = s.kvel[k]; rf[SF_KW + k] = s.kw[k]; rf[SF_KCORR + k] = s.kcorr[k]; }
   rf[SF_UWB_RANGE] = s.uwb_range;
   rf[SF_LOGIC_RANGE] = s.logic_range;
-  if (HK) {
+  if constexpr (HK) {
 #pragma unroll
     for (int k = 0; k < 4; k++) { rf[SF_TEMP_LP + k] = s.temp_lp[k]; rf[SF_BATT_LP + k] = s.batt_lp[k]; rf[SF_PC_ACCUM + k] = s.pc_accum[k]; rf[SF_PC_CORR + k] = s.pc_corr[k]; }
     rf[SF_BATT_VFILT] = s.batt_vfilt; rf[SF_MON_CMD] = s.mon_cmd_lpdt; rf[SF_MON_LOOP] = s.mon_loop_lpdt;
@@ -429,16 +563,24 @@ AGF_DEV void state_store(const VState<P, UWB, HK>& s, const StateArrays<P>& a, s
     for (int q = 0; q < NU_CORE / 4; q++)
       a.su[size_t(q) * n + i] = make_uint4(ru[4 * q], ru[4 * q + 1], ru[4 * q + 2], ru[4 * q + 3]);
   }
-  if (UWB) {
+  if constexpr (UWB) {
+    float full[NC_PAD];
 #pragma unroll
-    for (int q = 0; q < NC_PAD / 4; q++) {
-      float4 v;
-      v.x = 4 * q + 0 < 81 ? s.cov[4 * q + 0] : 0.0f;
-      v.y = 4 * q + 1 < 81 ? s.cov[4 * q + 1] : 0.0f;
-      v.z = 4 * q + 2 < 81 ? s.cov[4 * q + 2] : 0.0f;
-      v.w = 4 * q + 3 < 81 ? s.cov[4 * q + 3] : 0.0f;
-      a.sc[size_t(q) * n + i] = v;
+    for (int k = 81; k < NC_PAD; k++) full[k] = 0.0f;
+    if constexpr (PARITY) {
+#pragma unroll
+      for (int k = 0; k < 81; k++) full[k] = s.cov[k];
+    } else {
+      float Ps[48];
+      cov_load(sc, Ps);
+#pragma unroll
+      for (int r = 0; r < 9; r++)
+#pragma unroll
+        for (int c = 0; c < 9; c++) full[9 * r + c] = Ps[SI(r, c)];
     }
+#pragma unroll
+    for (int q = 0; q < NC_PAD / 4; q++)
+      a.sc[size_t(q) * n + i] = make_float4(full[4 * q], full[4 * q + 1], full[4 * q + 2], full[4 * q + 3]);
   }
 }
 
@@ -447,24 +589,36 @@ AGF_DEV void state_store(const VState<P, UWB, HK>& s, const StateArrays<P>& a, s
 // ---------------------------------------------------------------------------------------------
 #define AGF_COV(i, j) s.cov[9 * (i) + (j)]
 
-template<typename P, bool UWB, bool HK>
-AGF_DEV void kf_reset(VState<P, UWB, HK>& s) {  // KalmanFilter6DOF.cpp:33-68
+template<typename P, bool PARITY, bool UWB, bool HK>
+AGF_DEV void kf_reset(VState<P, PARITY, UWB, HK>& s, const Scratch& sc) {  // KalmanFilter6DOF.cpp:33-68
   s.kfcnt = (s.kfcnt & 0xFFFF0000u) | ((s.kfcnt + 1u) & 0xFFFFu);
   s.bits &= ~(B_IMU_INIT | B_UWB_INIT);
   s.bits |= B_KF_RESET_SEEN;
 #pragma unroll
   for (int k = 0; k < 3; k++) { s.kpos[k] = 0; s.kvel[k] = 0; s.kw[k] = 0; s.kcorr[k] = 0; }
   s.katt[0] = 1; s.katt[1] = 0; s.katt[2] = 0; s.katt[3] = 0;
-  if (UWB) {
-#pragma unroll
-    for (int k = 0; k < 81; k++) s.cov[k] = 0;
+  if constexpr (UWB) {
     const float sp = 3.0f, sv = 3.0f;
     const float sperp = 10.0f * 3.14159274f / 180.0f, sabout = 30.0f * 3.14159274f / 180.0f;
+    if constexpr (PARITY) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) { AGF_COV(k, k) = sp * sp; AGF_COV(3 + k, 3 + k) = sv * sv; }
-    AGF_COV(6, 6) = sperp * sperp;
-    AGF_COV(7, 7) = sperp * sperp;
-    AGF_COV(8, 8) = sabout * sabout;
+      for (int k = 0; k < 81; k++) s.cov[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { AGF_COV(k, k) = sp * sp; AGF_COV(3 + k, 3 + k) = sv * sv; }
+      AGF_COV(6, 6) = sperp * sperp;
+      AGF_COV(7, 7) = sperp * sperp;
+      AGF_COV(8, 8) = sabout * sabout;
+    } else {
+      float Ps[48];
+#pragma unroll
+      for (int k = 0; k < 48; k++) Ps[k] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Ps[SI(k, k)] = sp * sp; Ps[SI(3 + k, 3 + k)] = sv * sv; }
+      Ps[SI(6, 6)] = sperp * sperp;
+      Ps[SI(7, 7)] = sperp * sperp;
+      Ps[SI(8, 8)] = sabout * sabout;
+      cov_store(sc, Ps);
+    }
   }
 }
 
@@ -473,12 +627,12 @@ template<bool PARITY>
 AGF_DEV void gravity_axis_angle(const Q4<float>& att, const V3<float>& acc, V3<float>& ax, float& ang) {
   const V3<float> expAcc = qrot(qinv(att), V3<float>(0, 0, 1));
   const float n = norm(acc);  // GetUnitVector, Vec3.hpp:126-129
-  const V3<float> accUnit = acc / n;
+  const V3<float> accUnit = vdiv<PARITY>(acc, n);
   const float cosErr = dot(expAcc, accUnit);
   V3<float> rotAx = cross(accUnit, expAcc);
   const float rn = norm(rotAx);
   if (rn > 1e-6f) {
-    rotAx = rotAx / rn;
+    rotAx = vdiv<PARITY>(rotAx, rn);
   } else {
     rotAx = V3<float>(1, 0, 0);
   }
@@ -487,9 +641,9 @@ AGF_DEV void gravity_axis_angle(const Q4<float>& att, const V3<float>& acc, V3<f
 }
 
 template<bool PARITY, typename P, bool UWB, bool HK>
-AGF_DEV void kf_predict(VState<P, UWB, HK>& s, const V3<float>& gyro, const V3<float>& acc, float dt) {
+AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const V3<float>& gyro, const V3<float>& acc, float dt) {
   if (!(s.bits & B_IMU_INIT)) {  // :71-108
-    kf_reset(s);
+    kf_reset(s, sc);
     s.bits |= B_IMU_INIT;
     Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
     V3<float> ax;
@@ -511,7 +665,7 @@ AGF_DEV void kf_predict(VState<P, UWB, HK>& s, const V3<float>& gyro, const V3<f
     s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
     return;
   }
-  if (UWB) {  // :149-241
+  if constexpr (UWB) {  // :149-241
     const V3<float> p0(s.kpos[0], s.kpos[1], s.kpos[2]), v0(s.kvel[0], s.kvel[1], s.kvel[2]);
     float Rm[9];
     qmatrix(att, Rm);
@@ -538,6 +692,66 @@ AGF_DEV void kf_predict(VState<P, UWB, HK>& s, const V3<float>& gyro, const V3<f
     const float gz = dt * gyro.z + s.kcorr[2] / 2.0f;
     const float S[3][3] = {{1.0f, +gz, -gy}, {-gz, 1.0f, +gx}, {+gy, -gx, 1.0f}};
     s.kcorr[0] = 0; s.kcorr[1] = 0; s.kcorr[2] = 0;
+    const float qa = 5.0f * 5.0f * dt * dt, qg = 0.1f * 0.1f * dt * dt;  // process noise :234-239
+    if constexpr (!PARITY) {
+      // Fast variants: P is kept exactly symmetric (packed upper triangle, 45 values) and propagated block-wise,
+      // f = [[I, dt I, 0], [0, I, A], [0, 0, S]] = F2 * F1 with F1 the position/velocity coupling.  Same algebra
+      // as the dense f P f^T of KalmanFilter6DOF.cpp:232 up to rounding (about half the multiply-adds).
+      float Pm[48];
+      cov_load(sc, Pm);
+#define PS(i, j) Pm[SI((i), (j))]
+      // F1: Ppp += dt (Ppv + Ppv^T) + dt^2 Pvv ; Ppv += dt Pvv ; Ppa += dt Pva
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++) PS(i, j) = PS(i, j) + dt * ((PS(i, 3 + j) + PS(j, 3 + i)) + dt * PS(3 + i, 3 + j));
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          PS(i, 3 + j) = PS(i, 3 + j) + dt * PS(3 + i, 3 + j);
+          PS(i, 6 + j) = PS(i, 6 + j) + dt * PS(3 + i, 6 + j);
+        }
+      // F2: T = Pva + A Paa ; U = Pva A^T ; Pvv += U^T + T A^T
+      float T[3][3], U[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          T[i][j] = PS(3 + i, 6 + j) + (A[i][0] * PS(6, 6 + j) + A[i][1] * PS(7, 6 + j) + A[i][2] * PS(8, 6 + j));
+          U[i][j] = PS(3 + i, 6) * A[j][0] + PS(3 + i, 7) * A[j][1] + PS(3 + i, 8) * A[j][2];
+        }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++)
+          PS(3 + i, 3 + j) = PS(3 + i, 3 + j) + U[j][i] + (T[i][0] * A[j][0] + T[i][1] * A[j][1] + T[i][2] * A[j][2]);
+      // Ppv += Ppa A^T ; Ppa = Ppa S^T ; Pva = T S^T
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const float a0 = PS(i, 6), a1 = PS(i, 7), a2 = PS(i, 8);
+#pragma unroll
+        for (int j = 0; j < 3; j++) PS(i, 3 + j) = PS(i, 3 + j) + (a0 * A[j][0] + a1 * A[j][1] + a2 * A[j][2]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) PS(i, 6 + j) = a0 * S[j][0] + a1 * S[j][1] + a2 * S[j][2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) PS(3 + i, 6 + j) = T[i][0] * S[j][0] + T[i][1] * S[j][1] + T[i][2] * S[j][2];
+      }
+      // Paa = S Paa S^T
+      float W[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) W[i][j] = PS(6 + i, 6) * S[j][0] + PS(6 + i, 7) * S[j][1] + PS(6 + i, 8) * S[j][2];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++) PS(6 + i, 6 + j) = S[i][0] * W[0][j] + S[i][1] * W[1][j] + S[i][2] * W[2][j];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { PS(3 + k, 3 + k) += qa; PS(6 + k, 6 + k) += qg; }
+#undef PS
+      cov_store(sc, Pm);
+    } else {
 
     // FP = f * P, in place, row blocks in an order that only reads not-yet-overwritten rows
 #pragma unroll
@@ -563,22 +777,56 @@ AGF_DEV void kf_predict(VState<P, UWB, HK>& s, const V3<float>& gyro, const V3<f
 #pragma unroll
       for (int r = 0; r < 3; r++) AGF_COV(i, 6 + r) = (p6 * S[r][0] + p7 * S[r][1]) + p8 * S[r][2];
     }
-    // process noise :234-239
-    const float qa = 5.0f * 5.0f * dt * dt, qg = 0.1f * 0.1f * dt * dt;
 #pragma unroll
     for (int k = 0; k < 3; k++) { AGF_COV(3 + k, 3 + k) += qa; AGF_COV(6 + k, 6 + k) += qg; }
+    }
   }
 }
 
 template<bool PARITY, typename P, bool UWB, bool HK>
-AGF_DEV void kf_update_range(VState<P, UWB, HK>& s, const V3<float>& target, float range) {  // :243-301
-  if (!UWB) return;
+AGF_DEV void kf_update_range(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const V3<float>& target, float range) {  // :243-301
+  if constexpr (UWB) {
   if (!(s.bits & B_IMU_INIT)) return;
   if (!(range == range)) return;
   s.bits |= B_UWB_INIT;
   const V3<float> d = V3<float>(s.kpos[0], s.kpos[1], s.kpos[2]) - target;
   const float expRange = norm(d);
-  const V3<float> H = d / expRange;
+  const V3<float> H = vdiv<PARITY>(d, expRange);
+  const float innov = range - expRange;
+  if constexpr (!PARITY) {
+    // fast variants: symmetric P, P <- P - (P H^T)(P H^T)^T / S  (== (I - L H) P for symmetric P)
+    float Pm[48];
+    cov_load(sc, Pm);
+#define PS(i, j) Pm[SI((i), (j))]
+    float PHt[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) PHt[i] = PS(i, 0) * H.x + PS(i, 1) * H.y + PS(i, 2) * H.z;
+    const float innovCov = (H.x * PHt[0] + H.y * PHt[1] + H.z * PHt[2]) + 0.14f * 0.14f;
+    const float inv = fdiv<false>(1.0f, innovCov);
+    if (innov * innov * inv > 3.0f * 3.0f) {
+      const uint32_t rej = (s.kfcnt >> 16) + 1u;
+      s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
+      const uint32_t seq = (s.cnt & 0xFFu) + 1u;
+      s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
+      if (seq >= 5u) kf_reset(s, sc);
+      return;
+    }
+    s.cnt &= ~0xFFu;
+    float L[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) L[i] = PHt[i] * inv;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { s.kpos[k] += L[k] * innov; s.kvel[k] += L[3 + k] * innov; s.kcorr[k] = L[6 + k] * innov; }
+    Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+    att = q_apply_rotvec<PARITY>(att, V3<float>(s.kcorr[0], s.kcorr[1], s.kcorr[2]));
+    s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+#pragma unroll
+      for (int j = i; j < 9; j++) PS(i, j) = PS(i, j) - L[i] * PHt[j];
+#undef PS
+    cov_store(sc, Pm);
+  } else {
   float PHt[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) PHt[i] = (AGF_COV(i, 0) * H.x + AGF_COV(i, 1) * H.y) + AGF_COV(i, 2) * H.z;
@@ -588,14 +836,13 @@ AGF_DEV void kf_update_range(VState<P, UWB, HK>& s, const V3<float>& target, flo
   float L[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) L[i] = PHt[i] * inv;
-  const float innov = range - expRange;
   const float d2 = innov * innov / innovCov;
   if (d2 > 3.0f * 3.0f) {
     uint32_t rej = (s.kfcnt >> 16) + 1u;
     s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
     uint32_t seq = (s.cnt & 0xFFu) + 1u;
     s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
-    if (seq >= 5u) kf_reset(s);
+    if (seq >= 5u) kf_reset(s, sc);
     return;
   }
   s.cnt &= ~0xFFu;
@@ -628,6 +875,8 @@ AGF_DEV void kf_update_range(VState<P, UWB, HK>& s, const V3<float>& target, flo
   for (int i = 0; i < 9; i++)
 #pragma unroll
     for (int j = i + 1; j < 9; j++) AGF_COV(i, j) = AGF_COV(j, i);
+  }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -635,9 +884,11 @@ AGF_DEV void kf_update_range(VState<P, UWB, HK>& s, const V3<float>& target, flo
 // ---------------------------------------------------------------------------------------------
 // QuadcopterAngularVelocityController::GetDesiredTorques (:25-37); inertia = diag(ixx, ixx, izz) as
 // QuadcopterConstants builds it (the zero off-diagonal products are exact and dropped)
+template<bool PARITY>
 AGF_DEV V3<float> ctl_torques(const LogicParams& k, const V3<float>& des, const V3<float>& est) {
   const V3<float> err = des - est;
-  const V3<float> acc(err.x / k.tc_w_xy, err.y / k.tc_w_xy, err.z / k.tc_w_z);
+  const V3<float> acc = PARITY ? V3<float>(err.x / k.tc_w_xy, err.y / k.tc_w_xy, err.z / k.tc_w_z)
+                               : V3<float>(err.x * k.inv_tc_w_xy, err.y * k.inv_tc_w_xy, err.z * k.inv_tc_w_z);
   const V3<float> Iw(k.ixx * est.x, k.ixx * est.y, k.izz * est.z);
   const V3<float> nonlin = cross(est, Iw);
   return V3<float>(k.ixx * acc.x, k.ixx * acc.y, k.izz * acc.z) + nonlin;
@@ -648,9 +899,18 @@ template<bool PARITY>
 AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q4<float>& estAtt) {
   const Q4<float> err = qmul(qinv(desAtt), estAtt);
   const V3<float> rotVec = q_to_rotvec<PARITY>(err);
-  const V3<float> e3b = qrot(qinv(err), V3<float>(0, 0, 1));
-  V3<float> redAx = cross(e3b, V3<float>(0, 0, 1));
-  const float c = dot(e3b, V3<float>(0, 0, 1));
+  V3<float> e3b, redAx;
+  float c;
+  if (PARITY) {
+    e3b = qrot(qinv(err), V3<float>(0, 0, 1));
+    redAx = cross(e3b, V3<float>(0, 0, 1));
+    c = dot(e3b, V3<float>(0, 0, 1));
+  } else {  // third column of R(err^-1), cross/dot with e3 written out
+    const Q4<float> qi = qinv(err);
+    e3b = V3<float>(2 * qi.x * qi.z + 2 * qi.w * qi.y, 2 * qi.y * qi.z - 2 * qi.w * qi.x, qi.w * qi.w - qi.x * qi.x - qi.y * qi.y + qi.z * qi.z);
+    redAx = V3<float>(e3b.y, -e3b.x, 0.0f);
+    c = e3b.z;
+  }
   float redAn;
   if (c >= 1.0f) {
     redAn = 0;
@@ -663,21 +923,29 @@ AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q
   if (n < 1e-12f) {
     redAx = V3<float>(0, 0, 0);
   } else {
-    redAx = redAx / n;
+    redAx = vdiv<PARITY>(redAx, n);
   }
-  const float k3 = 1.0f / k.tc_att_z, k12 = 1.0f / k.tc_att_xy;
+  const float k3 = PARITY ? 1.0f / k.tc_att_z : k.k3_att, k12 = PARITY ? 1.0f / k.tc_att_xy : k.k12_att;
   return (-k3) * rotVec - ((k12 - k3) * redAn) * redAx;
 }
 
 // QuadcopterMixer::GetMotorForces + PropellerSpeedsFromThrust (:63-99)
-template<typename P, bool UWB, bool HK>
-AGF_DEV void ctl_mix(VState<P, UWB, HK>& s, const LogicParams& k, float totF, const V3<float>& t) {
+template<typename P, bool PARITY, bool UWB, bool HK>
+AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float totF, const V3<float>& t) {
   const float desF = totF > k.max_cmd_total ? k.max_cmd_total : totF;
   float f[4];
-  f[0] = (-t.x / k.mix_d - t.y / k.mix_d - t.z / k.mix_kt + desF) / 4.0f;
-  f[1] = (-t.x / k.mix_d + t.y / k.mix_d + t.z / k.mix_kt + desF) / 4.0f;
-  f[2] = (+t.x / k.mix_d + t.y / k.mix_d - t.z / k.mix_kt + desF) / 4.0f;
-  f[3] = (+t.x / k.mix_d - t.y / k.mix_d + t.z / k.mix_kt + desF) / 4.0f;
+  if (PARITY) {
+    f[0] = (-t.x / k.mix_d - t.y / k.mix_d - t.z / k.mix_kt + desF) / 4.0f;
+    f[1] = (-t.x / k.mix_d + t.y / k.mix_d + t.z / k.mix_kt + desF) / 4.0f;
+    f[2] = (+t.x / k.mix_d + t.y / k.mix_d - t.z / k.mix_kt + desF) / 4.0f;
+    f[3] = (+t.x / k.mix_d - t.y / k.mix_d + t.z / k.mix_kt + desF) / 4.0f;
+  } else {
+    const float tx = t.x * k.inv_mix_d, ty = t.y * k.inv_mix_d, tz = t.z * k.inv_mix_kt;
+    f[0] = (-tx - ty - tz + desF) * 0.25f;
+    f[1] = (-tx + ty + tz + desF) * 0.25f;
+    f[2] = (+tx + ty - tz + desF) * 0.25f;
+    f[3] = (+tx - ty + tz + desF) * 0.25f;
+  }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     if (f[i] < k.min_thrust) {
@@ -685,9 +953,14 @@ AGF_DEV void ctl_mix(VState<P, UWB, HK>& s, const LogicParams& k, float totF, co
     } else if (f[i] > k.max_thrust) {
       f[i] = k.max_thrust;
     }
-    s.dforce[i] = f[i];
-    const float corr = HK ? s.pc_corr[i] : 1.0f;
-    s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(f[i] / (corr * k.mix_kf));
+    if constexpr (PARITY || HK) s.dforce[i] = f[i];
+    float corr = 1.0f;
+    if constexpr (HK) corr = s.pc_corr[i];
+    if (PARITY || HK) {
+      s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(fdiv<PARITY>(f[i], corr * k.mix_kf));
+    } else {
+      s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(f[i] * k.inv_mix_kf);
+    }
   }
 }
 
@@ -702,7 +975,7 @@ AGF_DEV Q4<float> att_from_thrust_dir(const V3<float>& dir) {
   Q4<float> out(1, 0, 0, 0);
   if (!(n < 1e-6f)) {
     Q4<float> d;
-    if (q_from_rotvec<PARITY>(rotAx * (angle / n), d)) out = d;
+    if (q_from_rotvec<PARITY>(rotAx * fdiv<PARITY>(angle, n), d)) out = d;
   }
   return out;
 }
@@ -711,11 +984,11 @@ AGF_DEV Q4<float> att_from_thrust_dir(const V3<float>& dir) {
 // QuadcopterLogic::Run (QuadcopterLogic.cpp:164-219) with its intake setters
 // ---------------------------------------------------------------------------------------------
 template<bool PARITY, typename P, bool UWB, bool HK>
-AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<float>& gyroMeas,
+AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const V3<float>& gyroMeas,
                        const V3<float>& accMeas, float kf_dt) {
   const LogicParams& k = p.logic;
   // --- intake (QuadcopterLogic.hpp:32-59) ---
-  if (HK) {
+  if constexpr (HK) {
     s.batt_vfilt = lpf2(k.lp_batt, s.batt_lp, 1, k.batt_voltage);
     lpf2(k.lp_temp, s.temp_lp, 1, 25.0f);
   }
@@ -725,10 +998,14 @@ AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<f
     a = matvec(k.R_imu, a);
   }
   // gyro calibration bias is always (0,0,0) behind this API: rawMeas - bias == rawMeas
-  const V3<float> gf(lpf2(k.lp_gyro, &s.gyro_lp[0], 1, g.x), lpf2(k.lp_gyro, &s.gyro_lp[4], 1, g.y),
-                     lpf2(k.lp_gyro, &s.gyro_lp[8], 1, g.z));
-  const V3<float> af(lpf2(k.lp_acc, &s.acc_lp[0], 1, a.x), lpf2(k.lp_acc, &s.acc_lp[4], 1, a.y),
-                     lpf2(k.lp_acc, &s.acc_lp[8], 1, a.z));
+  V3<float> gf, af;
+  if constexpr (PARITY) {
+    gf = V3<float>(lpf2(k.lp_gyro, &s.gyro_lp[0], 1, g.x), lpf2(k.lp_gyro, &s.gyro_lp[4], 1, g.y), lpf2(k.lp_gyro, &s.gyro_lp[8], 1, g.z));
+    af = V3<float>(lpf2(k.lp_acc, &s.acc_lp[0], 1, a.x), lpf2(k.lp_acc, &s.acc_lp[4], 1, a.y), lpf2(k.lp_acc, &s.acc_lp[8], 1, a.z));
+  } else {
+    gf = V3<float>(lpf2_scratch(k.lp_gyro, sc, 0, g.x), lpf2_scratch(k.lp_gyro, sc, 1, g.y), lpf2_scratch(k.lp_gyro, sc, 2, g.z));
+    af = V3<float>(lpf2_scratch(k.lp_acc, sc, 3, a.x), lpf2_scratch(k.lp_acc, sc, 4, a.y), lpf2_scratch(k.lp_acc, sc, 5, a.z));
+  }
 
   uint32_t fs = bget(s.bits, B_FS_SHIFT, B_FS_MASK);
   if (fs == AGF_FS_UNINITIALIZED) return;
@@ -739,7 +1016,7 @@ AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<f
     s.age_mon_loop -= uint32_t(mdt * 1e6f);
   }
   // --- UpdateEstimator :221-273 ---
-  kf_predict<PARITY>(s, gf, af, kf_dt);
+  kf_predict<PARITY>(s, sc, gf, af, kf_dt);
   if (UWB && (s.bits & B_UWB_NEW)) {
     s.bits &= ~B_UWB_NEW;
     s.uwb_count++;  // failure is never set by the simulated network (UWBNetwork.cpp:77)
@@ -748,7 +1025,7 @@ AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<f
     nxt = (nxt + 1u) % p.n_anchors;
     s.uwbw = (s.uwbw & ~(0xFFu << W_NEXT_TARGET)) | (nxt << W_NEXT_TARGET);
     const V3<float> tp(p.anchors[resp].x, p.anchors[resp].y, p.anchors[resp].z);
-    kf_update_range<PARITY>(s, tp, s.logic_range);
+    kf_update_range<PARITY>(s, sc, tp, s.logic_range);
   }
   // --- ParseIncomingCommunications :275-303 ---
   if (s.bits & B_RADIO_NEW) {
@@ -806,9 +1083,9 @@ AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<f
   // --- controllers :194-217 ---
   const V3<float> estW(s.kw[0], s.kw[1], s.kw[2]);
   if (fs == AGF_FS_EXTERNAL_RATES_CONTROL) {  // :528-588
-    const V3<float> tq = ctl_torques(k, V3<float>(s.radio_f[1], s.radio_f[2], s.radio_f[3]), estW);
+    const V3<float> tq = ctl_torques<PARITY>(k, V3<float>(s.radio_f[1], s.radio_f[2], s.radio_f[3]), estW);
     ctl_mix(s, k, s.radio_f[0] * k.mass, tq);
-    if (HK) {
+    if constexpr (HK) {
       if (rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) {
         if (!(s.bits & B_PC_RUNNING)) {
           s.bits |= B_PC_RUNNING;
@@ -845,23 +1122,26 @@ AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<f
                               ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * k.nat_freq) * k.damping)) + zero;
     const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
     const float nProper = norm(proper);
-    const V3<float> dir = proper / nProper;
+    const V3<float> dir = vdiv<PARITY>(proper, nProper);
     const float corr = qrot_e3_z(estAtt);
     const float corrSat = corr < 1.00f ? 1.00f : corr;
-    const float thrust = nProper / corrSat;
+    const float thrust = fdiv<PARITY>(nProper, corrSat);
     const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
     const V3<float> desW = ctl_att<PARITY>(k, desAtt, estAtt);
-    ctl_mix(s, k, thrust * k.mass, ctl_torques(k, desW, estW));
+    ctl_mix(s, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
   } else if (fs == AGF_FS_EXTERNAL_ACCELERATION_CONTROL) {  // :459-526
     const Q4<float> estAtt(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
     const V3<float> desAcc(s.radio_f[0], s.radio_f[1], s.radio_f[2]);
     if (desAcc.z < -9.81f / 2) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) { s.cmd[i] = 0; s.dforce[i] = 0; }
+      for (int i = 0; i < 4; i++) {
+        s.cmd[i] = 0;
+        if constexpr (PARITY || HK) s.dforce[i] = 0;
+      }
     } else {
       const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
       const float thrust = norm(proper);
-      const V3<float> dir = proper / thrust;
+      const V3<float> dir = vdiv<PARITY>(proper, thrust);
       const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
       // ToEulerYPR (Rotation.hpp:163-169); yaw is computed by the reference but unused
       const Q4<float>& q = estAtt;
@@ -870,17 +1150,20 @@ AGF_DEV void logic_run(VState<P, UWB, HK>& s, const StepShared<P>& p, const V3<f
       const Q4<float> noYaw = q_from_euler_ypr<PARITY>(0.0f, pch, rll);
       V3<float> desW = ctl_att<PARITY>(k, desAtt, noYaw);
       desW.z = s.radio_f[3];
-      ctl_mix(s, k, thrust * k.mass, ctl_torques(k, desW, estW));
+      ctl_mix(s, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) { s.cmd[i] = 0; s.dforce[i] = 0; }
+    for (int i = 0; i < 4; i++) {
+      s.cmd[i] = 0;
+      if constexpr (PARITY || HK) s.dforce[i] = 0;
+    }
   }
 }
 
 // SetRadioMessage (QuadcopterLogic.hpp:110-116)
-template<typename P, bool UWB, bool HK>
-AGF_DEV void radio_deliver(VState<P, UWB, HK>& s, const LogicParams& k, uint32_t type, uint32_t flags, const float f[4]) {
+template<typename P, bool PARITY, bool UWB, bool HK>
+AGF_DEV void radio_deliver(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, uint32_t type, uint32_t flags, const float f[4]) {
   s.bits |= B_RADIO_NEW;
   s.bits = bset(s.bits, B_RTYPE_SHIFT, B_RTYPE_MASK, type);
   s.bits = bset(s.bits, B_RFLAGS_SHIFT, B_RFLAGS_MASK, flags);
@@ -900,11 +1183,12 @@ AGF_DEV uint32_t sat_add(uint32_t a, uint32_t d) { return a > 0xF0000000u ? a : 
 // one tick: [radio delivery] -> Quadcopter_T::Run -> UWBNetwork::Run -> clock advance
 // ---------------------------------------------------------------------------------------------
 template<typename P, bool PARITY, bool UWB, bool HK>
-AGF_DEV void tick(VState<P, UWB, HK>& s, const StepShared<P>& p, const PlantPV<P>& pv, Timing& ts,
+AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PlantPV<P>& pv, Timing& ts,
                   uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
   const TickPlan plan = timing_plan(ts, p.tc);
   if (plan.run_plant) {
     const P dt = P(double(plan.plant_dt_us) * 1e-6);
+    const P inv_dt = PARITY ? P(0) : P(1) / dt;
     // ---- motors (Motor.cpp:39-84).  Axes are (0,0,+-1) and thrust is (0,0,f): the products with
     // the exact-zero components are dropped, the rest keeps the reference's order.
     P Fz = P(0), Tx = P(0), Ty = P(0), Tz = P(0);
@@ -924,8 +1208,13 @@ AGF_DEV void tick(VState<P, UWB, HK>& s, const StepShared<P>& p, const PlantPV<P
       s.ms[m] = sp;
       const P fz = (pv.kF * sp) * rabs_(sp);
       const P aero = (((-pv.kTau) * sp) * rabs_(sp)) * sgn;
-      const P angAcc = (sp - old) / dt;
-      const P tz = (aero + P(0)) - ((angAcc * p.motor_J) * sgn);
+      P tz;
+      if (PARITY) {
+        const P angAcc = (sp - old) / dt;
+        tz = (aero + P(0)) - ((angAcc * p.motor_J) * sgn);
+      } else {
+        tz = aero - (((sp - old) * inv_dt) * p.motor_J) * sgn;
+      }
       const P tx = p.motor_pos[m][1] * fz;   // (r x T).x = ry*fz - rz*0
       const P ty = P(0) - p.motor_pos[m][0] * fz;  // (r x T).y = rz*0 - rx*fz
       Fz = Fz + fz; Tx = Tx + tx; Ty = Ty + ty; Tz = Tz + tz;
@@ -952,7 +1241,7 @@ AGF_DEV void tick(VState<P, UWB, HK>& s, const StepShared<P>& p, const PlantPV<P
       F = F + V3<P>(p.drag[0] * (-vb.x), p.drag[1] * (-vb.y), p.drag[2] * (-vb.z));
     }
     V3<P> acc(P(0), P(0), P(-9.81));
-    acc = acc + (qrot(att, F) + extF) / pv.mass;
+    acc = acc + vdiv<PARITY>(qrot(att, F) + extF, pv.mass);
     const V3<P> pos(s.pos[0], s.pos[1], s.pos[2]), vel(s.vel[0], s.vel[1], s.vel[2]);
     V3<P> npos = (pos + vel * dt) + ((P(0.5) * acc) * dt) * dt;
     V3<P> nvel = vel + acc * dt;
@@ -989,8 +1278,8 @@ AGF_DEV void tick(VState<P, UWB, HK>& s, const StepShared<P>& p, const PlantPV<P
           a = a + V3<float>(b[3], b[4], b[5]) * p.bias_sigma_acc;
         }
       }
-      logic_run<PARITY>(s, p, g, a, float(plan.kf_dt_us) * 1e-6f);
-      if (UWB) {  // radio exchange :191-199
+      logic_run<PARITY>(s, sc, p, g, a, float(plan.kf_dt_us) * 1e-6f);
+      if constexpr (UWB) {  // radio exchange :191-199
         s.rpos[0] = s.pos[0]; s.rpos[1] = s.pos[1]; s.rpos[2] = s.pos[2];
         if (s.bits & B_RADIO_MEAS_NEW) {  // SetUWBMeasurement (QuadcopterLogic.hpp:61-69)
           s.bits &= ~B_RADIO_MEAS_NEW;
@@ -1006,7 +1295,7 @@ AGF_DEV void tick(VState<P, UWB, HK>& s, const StepShared<P>& p, const PlantPV<P
   // ---- UWBNetwork::Run (UWBNetwork.cpp:22-89), private network: this vehicle + the anchors.
   // When it runs, and whether it starts or completes a transaction, depends on the clock only
   // (TickPlan); which anchor answers and the measured range are per vehicle.
-  if (UWB) {
+  if constexpr (UWB) {
     if (plan.net_start) {  // :32-41 responder = the requester's next ranging target
       const uint32_t nxt = (s.uwbw >> W_NEXT_TARGET) & 0xFFu;
       s.uwbw = (s.uwbw & ~(0xFFu << W_NET_RESP)) | (nxt << W_NET_RESP);
@@ -1060,12 +1349,40 @@ AGF_DEV void plant_params_load(PlantPV<P>& pv, const StepLaunch<P>& L, size_t i)
   }
 }
 
+// Occupancy targets (blocks of AGF_BLOCK_THREADS per SM) of the fast variants; the parity variants
+// take whatever registers they need.  Tuned with -Xptxas -v and ncu, see DESIGN.md.
+#ifndef AGF_MINB_F32_UWB
+#define AGF_MINB_F32_UWB 4
+#endif
+#ifndef AGF_MINB_F32_RATES
+#define AGF_MINB_F32_RATES 4
+#endif
+#ifndef AGF_MINB_F64_UWB
+#define AGF_MINB_F64_UWB 2
+#endif
+#ifndef AGF_MINB_F64_RATES
+#define AGF_MINB_F64_RATES 3
+#endif
+template<typename P, bool PARITY, bool UWB>
+constexpr int step_min_blocks() {
+  return PARITY ? 1 : (sizeof(P) == 4 ? (UWB ? AGF_MINB_F32_UWB : AGF_MINB_F32_RATES) : (UWB ? AGF_MINB_F64_UWB : AGF_MINB_F64_RATES));
+}
+template<bool PARITY, bool UWB>
+constexpr size_t step_smem_bytes(int block) {
+  return PARITY ? 0 : size_t(block) * (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) * sizeof(float4);
+}
+
 template<typename P, bool PARITY, bool UWB, bool HK>
-__global__ void __launch_bounds__(AGF_BLOCK_THREADS) step_kernel(const __grid_constant__ StepLaunch<P> L) {
+__global__ void __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
+step_kernel(const __grid_constant__ StepLaunch<P> L) {
+  extern __shared__ float4 agf_scratch[];
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= L.n) return;
-  VState<P, UWB, HK> s;
-  state_load(s, L.st, L.n, i);
+  Scratch sc;
+  sc.q = agf_scratch + threadIdx.x;
+  sc.stride = int(blockDim.x);
+  VState<P, PARITY, UWB, HK> s;
+  state_load(s, L.st, L.n, i, sc);
   PlantPV<P> pv;
   plant_params_load(pv, L, i);
   Timing ts = L.ts;
@@ -1086,7 +1403,7 @@ __global__ void __launch_bounds__(AGF_BLOCK_THREADS) step_kernel(const __grid_co
       }
       si++;
     }
-    tick<P, PARITY, UWB, HK>(s, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
+    tick<P, PARITY, UWB, HK>(s, sc, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
     if (L.log && ((abs_tick + 1) % L.log_stride) == 0) {
       const uint64_t rec = (abs_tick + 1) / L.log_stride - 1;
       P* base = L.log + (size_t(rec % L.log_capacity) * AGF_LOG_FIELDS) * L.n + i;
@@ -1096,7 +1413,7 @@ __global__ void __launch_bounds__(AGF_BLOCK_THREADS) step_kernel(const __grid_co
       for (int k = 0; k < 4; k++) { base[size_t(6 + k) * L.n] = s.att[k]; base[size_t(13 + k) * L.n] = s.ms[k]; }
     }
   }
-  state_store(s, L.st, L.n, i);
+  state_store(s, L.st, L.n, i, sc, L.sh.logic.mix_kf);
 }
 
 }  // namespace agf

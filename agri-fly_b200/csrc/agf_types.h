@@ -86,6 +86,8 @@ struct LogicParams {  // what QuadcopterLogic::Initialise derives from Quadcopte
   float batt_voltage, batt_warning, batt_critical;
   float onboard_period;
   float mon_cmd_coef, mon_loop_coef;  // LowPassFilterFirstOrder coefficients (expf on the host)
+  // reciprocals used by the fast-arithmetic variants only
+  float inv_mix_d, inv_mix_kt, inv_mix_kf, inv_tc_w_xy, inv_tc_w_z, k3_att, k12_att;
   int valid;
 };
 
@@ -95,7 +97,25 @@ struct TimingConsts {
   double comm_period;     // UWBNetwork::_commPeriod
   int net_enabled;
   int n_anchors;
+  // The reference compares stopwatch readings as doubles, `us * 1e-6 > period` etc.  Those
+  // predicates are monotone in the integer microsecond reading, so the host evaluates them once
+  // (timing_thresholds) and the kernels compare integers: same decisions, no FP64 per tick.
+  uint32_t logic_min_age_us;  // smallest reading with  double(us)*1e-6 >  logic_period  (Quadcopter_T.cpp:159)
+  uint32_t net_min_age_us;    // smallest reading with !(double(us)*1e-6 <  comm_period)  (UWBNetwork.cpp:28)
+  uint32_t plant_min_age_us;  // smallest reading with !(double(us)*1e-6 <  1e-6)         (Quadcopter_T.cpp:88)
 };
+
+inline uint32_t first_true_us(double guess_us, bool (*pred)(double, double), double arg) {
+  int64_t a = int64_t(guess_us) - 4;
+  if (a < 0) a = 0;
+  while (!pred(double(uint64_t(a)) * double(1e-6), arg)) a++;
+  return uint32_t(a);
+}
+inline void timing_thresholds(TimingConsts& tc) {
+  tc.logic_min_age_us = first_true_us(tc.logic_period * 1e6, [](double t, double p) { return t > p; }, tc.logic_period);
+  tc.net_min_age_us = tc.net_enabled ? first_true_us(tc.comm_period * 1e6, [](double t, double p) { return !(t < p); }, tc.comm_period) : 0xFFFFFFFFu;
+  tc.plant_min_age_us = first_true_us(1.0, [](double t, double p) { return !(t < p); }, 1e-6);
+}
 
 // Stopwatch readings that are identical for every vehicle of a batch (they depend on the clock
 // only): Quadcopter_T::_integrationTimer, ::_timerOnboardLogic, KalmanFilter6DOF::_estimateTimer,
@@ -116,12 +136,12 @@ AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc) {
   p.plant_dt_us = ts.integ_age;
   p.kf_dt_us = ts.kf_age;
   // Quadcopter_T.cpp:87-90: dt = GetSeconds<double>(); if (dt < 1e-6) return;
-  p.run_plant = !(double(ts.integ_age) * double(1e-6) < 1e-6);
+  p.run_plant = ts.integ_age >= tc.plant_min_age_us;
   // Quadcopter_T.cpp:159: if (_timerOnboardLogic.GetSeconds<double>() > _onboardLogicPeriod)
-  p.run_logic = p.run_plant && (double(ts.logic_age) * double(1e-6) > tc.logic_period);
+  p.run_logic = p.run_plant && ts.logic_age >= tc.logic_min_age_us;
   p.has_target = ts.has_target || (p.run_logic && tc.n_anchors > 0);
   // UWBNetwork.cpp:28: if (_timeSinceLastRange.GetSeconds<double>() < _commPeriod) return;
-  p.run_net = tc.net_enabled && !(double(ts.net_age) * double(1e-6) < tc.comm_period);
+  p.run_net = tc.net_enabled && ts.net_age >= tc.net_min_age_us;
   p.net_start = p.net_complete = p.net_reset = false;
   if (p.run_net) {
     if (!ts.net_active) {

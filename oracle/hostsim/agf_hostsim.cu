@@ -47,9 +47,12 @@ struct orc_vehicle {
 template<bool UWB>
 static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entry* sched, uint32_t nsched,
                      const uint8_t* slot_raw, double* traj) {
-  VState<double, UWB, true> s;
+  VState<double, true, UWB, true> s;
   StateArrays<double> a = v->arrays();
-  state_load(s, a, 1, 0);
+  Scratch sc;
+  sc.q = nullptr;
+  sc.stride = 0;
+  state_load(s, a, 1, 0, sc);
   v->sh.ext_force = v->ext_f.empty() ? nullptr : v->ext_f.data();
   v->sh.ext_torque = v->ext_t.empty() ? nullptr : v->ext_t.data();
   uint32_t si = 0;
@@ -67,7 +70,7 @@ static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_
       radio_deliver(s, v->sh.logic, type, flags, f);
       si++;
     }
-    tick<double, true, UWB, true>(s, v->sh, v->pv, v->ts, dt_us, v->tick, 0, 0, 1);
+    tick<double, true, UWB, true>(s, sc, v->sh, v->pv, v->ts, dt_us, v->tick, 0, 0, 1);
     if (traj) {
       double* r = traj + size_t(k) * ORC_NTRAJ;
       for (int c = 0; c < 3; c++) { r[c] = s.pos[c]; r[3 + c] = s.vel[c]; r[10 + c] = s.w[c]; r[21 + c] = s.kpos[c]; r[24 + c] = s.kvel[c]; r[31 + c] = s.kw[c]; }
@@ -82,7 +85,7 @@ static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_
     v->tick++;
     v->now_us += dt_us;
   }
-  state_store(s, a, 1, 0);
+  state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
 }
 
 extern "C" {
@@ -132,11 +135,11 @@ void orc_set_radio(orc_vehicle* v, const uint8_t raw[23]) {
   memcpy(e.raw, raw, 23);
   // deliver through a zero-tick run: load, deliver, store
   if (v->uwb) {
-    VState<double, true, true> s; StateArrays<double> a = v->arrays(); state_load(s, a, 1, 0);
-    uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0);
+    VState<double, true, true, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr, 0}; state_load(s, a, 1, 0, sc);
+    uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   } else {
-    VState<double, false, true> s; StateArrays<double> a = v->arrays(); state_load(s, a, 1, 0);
-    uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0);
+    VState<double, true, false, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr, 0}; state_load(s, a, 1, 0, sc);
+    uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   }
 }
 void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entry* sched, uint32_t nsched,
