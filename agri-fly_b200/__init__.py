@@ -17,7 +17,7 @@ from . import _abi as abi
 from . import scenarios  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libagrifly_b200.so")
+LIB_PATH = os.environ.get("AGF_LIB_PATH") or os.path.join(HERE, "libagrifly_b200.so")  # override: tuning variants only
 _lib = None
 
 
@@ -167,6 +167,10 @@ class Batch:
     # stepping
     def run(self, nticks, dt_us=2000):
         _check(self.L.agf_batch_run(self.h, dt_us, nticks))
+
+    def advance_clock(self, dt_us):
+        """ManualTimer::AdvanceMicroSeconds for the batch's clock; pair with run(1, dt_us=0) == Run()."""
+        _check(self.L.agf_batch_advance_clock(self.h, dt_us))
 
     def sync(self):
         _check(self.L.agf_batch_sync(self.h))

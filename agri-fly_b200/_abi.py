@@ -100,6 +100,7 @@ PROTOTYPES = {
     "agf_batch_size": (C.c_size_t, [C.c_void_p]),
     "agf_batch_stream": (C.c_void_p, [C.c_void_p]),
     "agf_batch_run": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "agf_batch_advance_clock": (C.c_int, [C.c_void_p, C.c_uint32]),
     "agf_batch_sync": (C.c_int, [C.c_void_p]),
     "agf_batch_time_us": (C.c_uint64, [C.c_void_p]),
     "agf_batch_ticks": (C.c_uint64, [C.c_void_p]),

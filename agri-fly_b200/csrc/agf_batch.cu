@@ -158,6 +158,22 @@ __global__ void radio_now_kernel(float* sf, uint32_t* su, size_t n, size_t first
   }
 }
 
+// Clock advance without a Run(): the per-vehicle stopwatches (radio / UWB timeouts, monitors) age by dt
+__global__ void advance_clock_kernel(uint4* su, size_t n, uint32_t dt_us) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto sat = [dt_us](uint32_t a) { return a > 0xF0000000u ? a : a + dt_us; };
+  uint4 a = su[size_t(SU_AGE_RADIO / 4) * n + i];  // {uwb_count, age_radio, age_uwb, uwbw}
+  a.y = sat(a.y);
+  a.z = sat(a.z);
+  su[size_t(SU_AGE_RADIO / 4) * n + i] = a;
+  uint4 h = su[size_t(SU_AGE_EST_RESET / 4) * n + i];  // {age_est_reset, pc_count, age_mon_cmd, age_mon_loop}
+  h.x = sat(h.x);
+  h.z = sat(h.z);
+  h.w = sat(h.w);
+  su[size_t(SU_AGE_EST_RESET / 4) * n + i] = h;
+}
+
 // TelemetryPacket.hpp:39-63: MapToOnesRange + EncodeOnesRange (round-to-nearest ops, never contracted)
 __device__ inline uint16_t tel_encode(float x, float a, float b) {
   const float t = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, a), __fsub_rn(b, a)), 2.0f), 1.0f);
@@ -283,6 +299,7 @@ __global__ void stats_kernel(const P* sp, const float* sf, const uint32_t* su, s
 struct Batch {
   virtual ~Batch() {}
   virtual int run(uint32_t dt_us, uint32_t nticks) = 0;
+  virtual int advance_clock(uint32_t dt_us) = 0;
   virtual int get_field(int field, void* dst, size_t first, size_t count) = 0;
   virtual int set_field(int field, const void* src, size_t first, size_t count) = 0;
   virtual int set_radio(const uint8_t* raw, size_t first, size_t count, int broadcast) = 0;
@@ -346,6 +363,8 @@ struct BatchImpl : Batch {
   P* d_ext_force = nullptr;
   P* d_ext_torque = nullptr;
   uint32_t* d_tel_counter = nullptr;
+  uint32_t* d_flags = nullptr;  // balanced-schedule hand-over flags, one per 32 vehicles (smallest block)
+  uint32_t epoch = 0;
   SchedEntryDev* d_sched = nullptr;
   std::vector<SchedEntryDev> sched;
   float4* d_slot_f[AGF_MAX_CMD_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
@@ -369,7 +388,7 @@ struct BatchImpl : Batch {
   ~BatchImpl() override {
     cudaSetDevice(opts.device);
     cudaFree(st.sp); cudaFree(st.sf); cudaFree(st.su); cudaFree(st.sc);
-    cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter);
+    cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter); cudaFree(d_flags);
     cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target);
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
     for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -443,6 +462,8 @@ struct BatchImpl : Batch {
     if (uwb) AGF_CUDA(cudaMalloc(&st.sc, sizeof(float4) * (NC_PAD / 4) * n));
     AGF_CUDA(cudaMalloc(&d_tel_counter, sizeof(uint32_t) * n));
     AGF_CUDA(cudaMemsetAsync(d_tel_counter, 0, sizeof(uint32_t) * n, stream));
+    AGF_CUDA(cudaMalloc(&d_flags, sizeof(uint32_t) * ((n + 31) / 32)));
+    AGF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * ((n + 31) / 32), stream));
     if (per_vehicle) AGF_CUDA(cudaMalloc(&d_pv, sizeof(PV) * (NPV_PAD / VP) * n));
     return init_state();
   }
@@ -493,6 +514,7 @@ struct BatchImpl : Batch {
         h[sidx(PV_KF, n, i, VP)] = P(c.prop_thrust_from_speed_sqr);
         h[sidx(PV_KTAU, n, i, VP)] = P(c.prop_torque_from_speed_sqr);
         h[sidx(PV_MOTOR_C, n, i, VP)] = P(motor_c_host(tau[i], dt_us));
+        h[sidx(PV_INV_MASS, n, i, VP)] = P(1.0 / c.mass);
       }
       AGF_CUDA(cudaMemcpyAsync(d_pv, h.data(), h.size() * sizeof(P), cudaMemcpyHostToDevice, stream));
       AGF_CUDA(cudaStreamSynchronize(stream));
@@ -529,6 +551,8 @@ struct BatchImpl : Batch {
     L.log_stride = log_stride ? log_stride : 1;
     L.log_capacity = log_cap ? log_cap : 1;
     L.first_global_index = opts.first_global_index;
+    L.flags = d_flags;
+    L.epoch = ++epoch;
 
     if (events_used == events.size()) {
       cudaEvent_t a, b;
@@ -556,8 +580,23 @@ struct BatchImpl : Batch {
 
   cudaError_t do_launch(const StepLaunch<P>& L, int block);
 
+  // BaseTimer advancing between two Run() calls (ManualTimer::AdvanceMicroSeconds, ManualTimer.hpp:29)
+  int advance_clock(uint32_t dt_us) override {
+    if (!dt_us) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    advance_clock_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(st.su, n, dt_us);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    ts.integ_age += dt_us;
+    ts.logic_age += dt_us;
+    ts.kf_age += dt_us;
+    ts.net_age += dt_us;
+    now_us += dt_us;
+    return AGF_OK;
+  }
+
   int run(uint32_t dt_us, uint32_t nticks) override {
-    if (dt_us == 0) return fail(AGF_EINVAL, "dt_us must be > 0");
+    if (dt_us == 0 && nticks > 1) return fail(AGF_EINVAL, "dt_us == 0 (Run() without a clock advance) takes nticks == 1");
     AGF_CUDA(cudaSetDevice(opts.device));
     while (nticks) {
       // the plant step of the first tick integrates over the time since the previous Run(); the motor lag
@@ -840,11 +879,11 @@ struct BatchImpl : Batch {
 template<>
 cudaError_t BatchImpl<double>::do_launch(const StepLaunch<double>& L, int block) {
   if (parity) return launch_step_parity(L, uwb, block, stream);
-  return launch_step_fast_f64(L, uwb, hk, block, stream);
+  return uwb ? launch_step_fast_f64_uwb(L, hk, stream) : launch_step_fast_f64_rates(L, hk, stream);
 }
 template<>
 cudaError_t BatchImpl<float>::do_launch(const StepLaunch<float>& L, int block) {
-  return launch_step_fast_f32(L, uwb, hk, block, stream);
+  return uwb ? launch_step_fast_f32_uwb(L, hk, stream) : launch_step_fast_f32_rates(L, hk, stream);
 }
 
 }  // namespace agf
@@ -935,6 +974,7 @@ int agf_batch_destroy(agf_batch* b) {
 size_t agf_batch_size(const agf_batch* b) { return b ? B(b)->n : 0; }
 void* agf_batch_stream(const agf_batch* b) { return b ? (void*)B(b)->stream : nullptr; }
 int agf_batch_run(agf_batch* b, uint32_t dt_us, uint32_t nticks) { return b ? B(b)->run(dt_us, nticks) : fail(AGF_EINVAL, "null handle"); }
+int agf_batch_advance_clock(agf_batch* b, uint32_t dt_us) { return b ? B(b)->advance_clock(dt_us) : fail(AGF_EINVAL, "null handle"); }
 int agf_batch_sync(agf_batch* b) { return b ? B(b)->sync() : fail(AGF_EINVAL, "null handle"); }
 uint64_t agf_batch_time_us(const agf_batch* b) { return b ? B(b)->now_us : 0; }
 uint64_t agf_batch_ticks(const agf_batch* b) { return b ? B(b)->ticks : 0; }
@@ -1049,9 +1089,13 @@ const char* agf_build_info(void) {
     if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
       agf::kernel_attrs_parity(buf + o, sizeof(buf) - o);
       o = int(strlen(buf));
-      agf::kernel_attrs_fast_f64(buf + o, sizeof(buf) - o);
+      agf::kernel_attrs_fast_f64_uwb(buf + o, sizeof(buf) - o);
       o = int(strlen(buf));
-      agf::kernel_attrs_fast_f32(buf + o, sizeof(buf) - o);
+      agf::kernel_attrs_fast_f64_rates(buf + o, sizeof(buf) - o);
+      o = int(strlen(buf));
+      agf::kernel_attrs_fast_f32_uwb(buf + o, sizeof(buf) - o);
+      o = int(strlen(buf));
+      agf::kernel_attrs_fast_f32_rates(buf + o, sizeof(buf) - o);
     } else {
       cudaGetLastError();
       snprintf(buf + o, sizeof(buf) - o, "no CUDA device visible");

@@ -127,6 +127,7 @@ inline void fill_plant(const agf_vehicle_cfg& c, PlantPV<P>& pv) {
   pv.kF = P(c.prop_thrust_from_speed_sqr);
   pv.kTau = P(c.prop_torque_from_speed_sqr);
   pv.motor_c = P(0);
+  pv.inv_mass = P(1.0 / c.mass);
 }
 
 // everything of StepShared that does not depend on device pointers, anchors or noise settings

@@ -1,0 +1,77 @@
+// agf_kernels_fast.cu -- step kernels with FMA contraction and CUDA fast paths.
+// Compiled four times (build.py): -DAGF_FAST_F64=0|1 (plant precision) x -DAGF_FAST_UWB=0|1 (EKF + ranging),
+// each object holding the {housekeeping} x {per-vehicle parameters} instantiations of one kernel family.
+#include <stdio.h>
+
+#include "agf_launch.h"
+#include "agf_step.cuh"
+
+#ifndef AGF_FAST_F64
+#error "define AGF_FAST_F64 to 0 or 1"
+#endif
+#ifndef AGF_FAST_UWB
+#error "define AGF_FAST_UWB to 0 or 1"
+#endif
+
+namespace agf {
+
+#if AGF_FAST_F64
+typedef double FastP;
+#define AGF_FAST_NAME(a, b) a##f64##b
+#else
+typedef float FastP;
+#define AGF_FAST_NAME(a, b) a##f32##b
+#endif
+#if AGF_FAST_UWB
+#define AGF_FAST_FN(stem) AGF_FAST_NAME(stem, _uwb)
+static constexpr bool kUwb = true;
+#else
+#define AGF_FAST_FN(stem) AGF_FAST_NAME(stem, _rates)
+static constexpr bool kUwb = false;
+#endif
+
+template<bool HK, bool PV>
+static cudaError_t go(const StepLaunch<FastP>& L, cudaStream_t stream) {
+  auto kernel = step_kernel<FastP, false, kUwb, HK, PV>;
+  static bool carveout_set = false;
+  if (!carveout_set) {  // the scratch of the resident blocks needs most of the SM's shared memory
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
+  return launch_step_kernel<FastP>(kernel, L, AGF_BLOCK_THREADS, step_smem_bytes<false, kUwb>(AGF_BLOCK_THREADS), stream);
+}
+
+// launch_step_fast_{f32,f64}_{uwb,rates}
+cudaError_t AGF_FAST_FN(launch_step_fast_)(const StepLaunch<FastP>& L, bool hk, cudaStream_t stream) {
+  const bool pv = L.pv != nullptr;
+  if (hk) return pv ? go<true, true>(L, stream) : go<true, false>(L, stream);
+  return pv ? go<false, true>(L, stream) : go<false, false>(L, stream);
+}
+
+template<typename K>
+static int attr_line(char* buf, size_t n, const char* name, K kernel) {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess) {
+    cudaGetLastError();
+    return snprintf(buf, n, "%s: n/a; ", name);
+  }
+  return snprintf(buf, n, "%s: %d regs, %zu B local; ", name, a.numRegs, a.localSizeBytes);
+}
+
+#define AGF_STR2(x) #x
+#define AGF_STR(x) AGF_STR2(x)
+void AGF_FAST_FN(kernel_attrs_fast_)(char* buf, size_t n) {
+  const char* fam = AGF_STR(AGF_FAST_FN(step_fast_));
+  char nm[96];
+  int o = 0;
+  snprintf(nm, sizeof nm, "%s", fam);
+  o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, false>);
+  snprintf(nm, sizeof nm, "%s+hk", fam);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, true, false>);
+  snprintf(nm, sizeof nm, "%s+pv", fam);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, true>);
+  snprintf(nm, sizeof nm, "%s+hk+pv", fam);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, true, true>);
+}
+
+}  // namespace agf

@@ -8,13 +8,8 @@
 namespace agf {
 
 cudaError_t launch_step_parity(const StepLaunch<double>& L, bool uwb, int block, cudaStream_t stream) {
-  const unsigned grid = unsigned((L.n + block - 1) / block);
-  if (uwb) {
-    step_kernel<double, true, true, true><<<grid, block, 0, stream>>>(L);
-  } else {
-    step_kernel<double, true, false, true><<<grid, block, 0, stream>>>(L);
-  }
-  return cudaGetLastError();
+  if (uwb) return launch_step_kernel<double>(step_kernel<double, true, true, true, false>, L, block, 0, stream);
+  return launch_step_kernel<double>(step_kernel<double, true, false, true, false>, L, block, 0, stream);
 }
 
 template<typename K>
@@ -29,8 +24,8 @@ static int attr_line(char* buf, size_t n, const char* name, K kernel) {
 }
 
 void kernel_attrs_parity(char* buf, size_t n) {
-  int o = attr_line(buf, n, "step<f64,parity,uwb>", step_kernel<double, true, true, true>);
-  if (o > 0 && size_t(o) < n) attr_line(buf + o, n - o, "step<f64,parity,nouwb>", step_kernel<double, true, false, true>);
+  int o = attr_line(buf, n, "step<f64,parity,uwb>", step_kernel<double, true, true, true, false>);
+  if (o > 0 && size_t(o) < n) attr_line(buf + o, n - o, "step<f64,parity,nouwb>", step_kernel<double, true, false, true, false>);
 }
 
 }  // namespace agf

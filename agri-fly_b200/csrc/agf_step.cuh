@@ -379,9 +379,33 @@ AGF_DEV uint32_t bset(uint32_t w, uint32_t shift, uint32_t mask, uint32_t v) {
 // pin ~70 registers for the whole tick: the six IMU low-pass states and the packed EKF covariance.
 struct Scratch {
   float4* q;   // already offset by the thread index
-  int stride;  // threads per block
 };
+// threads per block of the variants that use the scratch: a compile-time stride turns every scratch address
+// into base register + immediate and lets the compiler tell the quads apart (no false LDS/STS dependencies)
+enum { SQ_STRIDE = AGF_BLOCK_THREADS };
 enum { SQ_LPF = 0, SQ_COV = 6, SQ_QUADS_NOUWB = 6, SQ_QUADS_UWB = 18 };
+// Scratch accesses are volatile 128-bit shared-memory instructions: with the compile-time stride the compiler
+// could otherwise forward a tick's stores to the next tick's loads, i.e. keep the whole scratch in registers
+// across the loop -- the opposite of what the scratch is for (measured: 3x the local-memory spill traffic).
+AGF_DEV float4 sq_load(const Scratch& sc, int quad) {
+#if defined(__CUDA_ARCH__)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(uint32_t(__cvta_generic_to_shared(sc.q)) + uint32_t(quad * SQ_STRIDE * sizeof(float4))));
+  return v;
+#else
+  return sc.q[quad * SQ_STRIDE];
+#endif
+}
+AGF_DEV void sq_store(const Scratch& sc, int quad, const float4& v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(uint32_t(__cvta_generic_to_shared(sc.q)) + uint32_t(quad * SQ_STRIDE * sizeof(float4))),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+#else
+  sc.q[quad * SQ_STRIDE] = v;
+#endif
+}
 // packed upper triangle of a symmetric 9x9
 AGF_DEV constexpr int SI(int i, int j) {
   return i <= j ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
@@ -389,21 +413,31 @@ AGF_DEV constexpr int SI(int i, int j) {
 AGF_DEV void cov_load(const Scratch& sc, float* P) {
 #pragma unroll
   for (int q = 0; q < 12; q++) {
-    const float4 v = sc.q[(SQ_COV + q) * sc.stride];
+    const float4 v = sq_load(sc, SQ_COV + q);
     P[4 * q] = v.x; P[4 * q + 1] = v.y; P[4 * q + 2] = v.z; P[4 * q + 3] = v.w;
   }
 }
 AGF_DEV void cov_store(const Scratch& sc, const float* P) {
 #pragma unroll
-  for (int q = 0; q < 12; q++) sc.q[(SQ_COV + q) * sc.stride] = make_float4(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3]);
+  for (int q = 0; q < 12; q++) sq_store(sc, SQ_COV + q, make_float4(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3]));
 }
 AGF_DEV float lpf2_scratch(const Lpf2Coef& c, const Scratch& sc, int quad, float in) {
-  float4 st = sc.q[(SQ_LPF + quad) * sc.stride];  // {xm0, xm1, ym0, ym1}
+  const float4 st = sq_load(sc, SQ_LPF + quad);  // {xm0, xm1, ym0, ym1}
   float out = c.b2 * in;
   out = out + (c.b0 * st.x + c.b1 * st.y);
   out = out + ((-c.a1) * st.z - c.a2 * st.w);
-  sc.q[(SQ_LPF + quad) * sc.stride] = make_float4(st.y, in, st.w, out);
+  sq_store(sc, SQ_LPF + quad, make_float4(st.y, in, st.w, out));
   return out;
+}
+
+// State is read once per work item and may have been written by another CTA of the same launch (balanced
+// schedule below): load through L2 only (ld.global.cg), never from a possibly stale L1 line.
+template<typename T> AGF_DEV T ldcg_(const T* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
 }
 
 // --- flat (de)serialisation order; the host get/set kernels use the same tables (agf_types.h) ---
@@ -414,7 +448,7 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
   P rp[NP_PAD];
 #pragma unroll
   for (int q = 0; q < NP_PAD / VP; q++) {
-    PV v = a.sp[size_t(q) * n + i];
+    PV v = ldcg_(&a.sp[size_t(q) * n + i]);
     VecOf<P>::unpack(v, &rp[q * VP]);
   }
 #pragma unroll
@@ -429,7 +463,7 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
 #pragma unroll
   for (int q = 0; q < NF_PAD / 4; q++) {
     if (!HK && q >= NF_CORE / 4) break;
-    float4 v = a.sf[size_t(q) * n + i];
+    float4 v = ldcg_(&a.sf[size_t(q) * n + i]);
     rf[4 * q] = v.x; rf[4 * q + 1] = v.y; rf[4 * q + 2] = v.z; rf[4 * q + 3] = v.w;
   }
 #pragma unroll
@@ -444,8 +478,8 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
   } else {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      sc.q[(SQ_LPF + c) * sc.stride] = make_float4(rf[SF_GYRO_LP + 4 * c], rf[SF_GYRO_LP + 4 * c + 1], rf[SF_GYRO_LP + 4 * c + 2], rf[SF_GYRO_LP + 4 * c + 3]);
-      sc.q[(SQ_LPF + 3 + c) * sc.stride] = make_float4(rf[SF_ACC_LP + 4 * c], rf[SF_ACC_LP + 4 * c + 1], rf[SF_ACC_LP + 4 * c + 2], rf[SF_ACC_LP + 4 * c + 3]);
+      sq_store(sc, SQ_LPF + c, make_float4(rf[SF_GYRO_LP + 4 * c], rf[SF_GYRO_LP + 4 * c + 1], rf[SF_GYRO_LP + 4 * c + 2], rf[SF_GYRO_LP + 4 * c + 3]));
+      sq_store(sc, SQ_LPF + 3 + c, make_float4(rf[SF_ACC_LP + 4 * c], rf[SF_ACC_LP + 4 * c + 1], rf[SF_ACC_LP + 4 * c + 2], rf[SF_ACC_LP + 4 * c + 3]));
     }
   }
 #pragma unroll
@@ -461,7 +495,7 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
 #pragma unroll
   for (int q = 0; q < NU_PAD / 4; q++) {
     if (!HK && q >= NU_CORE / 4) break;
-    uint4 v = a.su[size_t(q) * n + i];
+    uint4 v = ldcg_(&a.su[size_t(q) * n + i]);
     ru[4 * q] = v.x; ru[4 * q + 1] = v.y; ru[4 * q + 2] = v.z; ru[4 * q + 3] = v.w;
   }
   s.bits = ru[SU_BITS]; s.cnt = ru[SU_CNT]; s.cycle = ru[SU_CYCLE]; s.kfcnt = ru[SU_KFCNT];
@@ -472,7 +506,7 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
     float full[NC_PAD];
 #pragma unroll
     for (int q = 0; q < NC_PAD / 4; q++) {
-      float4 v = a.sc[size_t(q) * n + i];
+      float4 v = ldcg_(&a.sc[size_t(q) * n + i]);
       full[4 * q + 0] = v.x; full[4 * q + 1] = v.y; full[4 * q + 2] = v.z; full[4 * q + 3] = v.w;
     }
     if constexpr (PARITY) {
@@ -527,7 +561,7 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
   } else {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const float4 g = sc.q[(SQ_LPF + c) * sc.stride], a4 = sc.q[(SQ_LPF + 3 + c) * sc.stride];
+      const float4 g = sq_load(sc, SQ_LPF + c), a4 = sq_load(sc, SQ_LPF + 3 + c);
       rf[SF_GYRO_LP + 4 * c] = g.x; rf[SF_GYRO_LP + 4 * c + 1] = g.y; rf[SF_GYRO_LP + 4 * c + 2] = g.z; rf[SF_GYRO_LP + 4 * c + 3] = g.w;
       rf[SF_ACC_LP + 4 * c] = a4.x; rf[SF_ACC_LP + 4 * c + 1] = a4.y; rf[SF_ACC_LP + 4 * c + 2] = a4.z; rf[SF_ACC_LP + 4 * c + 3] = a4.w;
     }
@@ -1182,8 +1216,19 @@ AGF_DEV uint32_t sat_add(uint32_t a, uint32_t d) { return a > 0xF0000000u ? a : 
 // ---------------------------------------------------------------------------------------------
 // one tick: [radio delivery] -> Quadcopter_T::Run -> UWBNetwork::Run -> clock advance
 // ---------------------------------------------------------------------------------------------
-template<typename P, bool PARITY, bool UWB, bool HK>
-AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PlantPV<P>& pv, Timing& ts,
+// inertia products for the two plant-parameter carriers: full 3x3 (shared parameters, read straight from the
+// kernel-parameter constant bank) and diagonal (per-vehicle sweep, registers)
+template<typename P> AGF_DEV V3<P> inertia_mul(const PlantPV<P>& pv, const V3<P>& w) { return matvec(pv.I, w); }
+template<typename P> AGF_DEV V3<P> inertia_inv_mul(const PlantPV<P>& pv, const V3<P>& x) { return matvec(pv.Iinv, x); }
+template<typename P> AGF_DEV V3<P> inertia_mul(const PlantPVDiag<P>& pv, const V3<P>& w) {
+  return V3<P>(pv.Id[0] * w.x, pv.Id[1] * w.y, pv.Id[2] * w.z);
+}
+template<typename P> AGF_DEV V3<P> inertia_inv_mul(const PlantPVDiag<P>& pv, const V3<P>& x) {
+  return V3<P>(pv.Iinvd[0] * x.x, pv.Iinvd[1] * x.y, pv.Iinvd[2] * x.z);
+}
+
+template<typename P, bool PARITY, bool UWB, bool HK, typename PVT>
+AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PVT& pv, Timing& ts,
                   uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
   const TickPlan plan = timing_plan(ts, p.tc);
   if (plan.run_plant) {
@@ -1229,19 +1274,23 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       T = T + qrot(qinv(att), extT);
     }
     // angular momentum: I*w + sum of rotor momenta (Quadcopter_T.cpp:113-117)
-    V3<P> L = matvec(pv.I, w);
+    V3<P> L = inertia_mul(pv, w);
 #pragma unroll
     for (int m = 0; m < 4; m++) {
       const P sgn = (m & 1) ? P(-1) : P(1);
       L.z = L.z + (s.ms[m] * p.motor_J) * sgn;
     }
-    const V3<P> angAcc = matvec(pv.Iinv, T - cross(w, L));
+    const V3<P> angAcc = inertia_inv_mul(pv, T - cross(w, L));
     if (p.has_drag) {  // :123-128
       const V3<P> vb = qrot(qinv(att), V3<P>(s.vel[0], s.vel[1], s.vel[2]));
       F = F + V3<P>(p.drag[0] * (-vb.x), p.drag[1] * (-vb.y), p.drag[2] * (-vb.z));
     }
     V3<P> acc(P(0), P(0), P(-9.81));
-    acc = acc + vdiv<PARITY>(qrot(att, F) + extF, pv.mass);
+    if (PARITY) {
+      acc = acc + vdiv<true>(qrot(att, F) + extF, pv.mass);
+    } else {
+      acc = acc + (qrot(att, F) + extF) * pv.inv_mass;
+    }
     const V3<P> pos(s.pos[0], s.pos[1], s.pos[2]), vel(s.vel[0], s.vel[1], s.vel[2]);
     V3<P> npos = (pos + vel * dt) + ((P(0.5) * acc) * dt) * dt;
     V3<P> nvel = vel + acc * dt;
@@ -1329,8 +1378,17 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
 
 
 // ---------------------------------------------------------------------------------------------
-// K1/K2/K3: the step kernel.  One vehicle per thread; nticks ticks per launch with the state in
+// K1/K2/K3: the step kernel.  One vehicle per thread; many ticks per launch with the state in
 // registers; optional trajectory log [record][field][vehicle] (every store a coalesced line).
+//
+// Balanced schedule.  Every vehicle-tick costs the same, so a launch is nblocks x nticks equal units of
+// work ("block-ticks").  A plain grid of nblocks CTAs runs them in ceil(nblocks / resident CTAs) waves and
+// the last wave is partly empty (131072 vehicles: 1024 blocks over 592 resident CTAs = 2 waves for 1.73
+// waves of work).  Instead the launch is one wave of G co-resident CTAs and CTA j owns the contiguous range
+// [j*T/G, (j+1)*T/G) of the block-major sequence of T = nblocks*nticks block-ticks.  A range boundary that
+// falls inside block b splits b's ticks between CTA j (ticks [0,t)) and CTA j+1 (ticks [t,nticks)): CTA j
+// runs that head part FIRST, stores the state and publishes flags[b] = epoch; CTA j+1 runs its tail part
+// LAST, after acquiring the flag.  Every CTA therefore finishes at the same time and nobody waits in practice.
 // ---------------------------------------------------------------------------------------------
 template<typename P>
 AGF_DEV void plant_params_load(PlantPV<P>& pv, const StepLaunch<P>& L, size_t i) {
@@ -1341,6 +1399,7 @@ AGF_DEV void plant_params_load(PlantPV<P>& pv, const StepLaunch<P>& L, size_t i)
 #pragma unroll
     for (int q = 0; q < NPV_PAD / VP; q++) VecOf<P>::unpack(L.pv[size_t(q) * L.n + i], &r[q * VP]);
     pv.mass = r[PV_MASS];
+    pv.inv_mass = r[PV_INV_MASS];
 #pragma unroll
     for (int k = 0; k < 9; k++) { pv.I[k] = P(0); pv.Iinv[k] = P(0); }
     pv.I[0] = r[PV_IXX]; pv.I[4] = r[PV_IYY]; pv.I[8] = r[PV_IZZ];
@@ -1348,11 +1407,23 @@ AGF_DEV void plant_params_load(PlantPV<P>& pv, const StepLaunch<P>& L, size_t i)
     pv.kF = r[PV_KF]; pv.kTau = r[PV_KTAU]; pv.motor_c = r[PV_MOTOR_C];
   }
 }
+template<typename P>
+AGF_DEV void plant_params_load(PlantPVDiag<P>& pv, const StepLaunch<P>& L, size_t i) {
+  constexpr int VP = VecOf<P>::lanes;
+  P r[NPV_PAD];
+#pragma unroll
+  for (int q = 0; q < NPV_PAD / VP; q++) VecOf<P>::unpack(L.pv[size_t(q) * L.n + i], &r[q * VP]);
+  pv.mass = r[PV_MASS];
+  pv.inv_mass = r[PV_INV_MASS];
+  pv.Id[0] = r[PV_IXX]; pv.Id[1] = r[PV_IYY]; pv.Id[2] = r[PV_IZZ];
+  pv.Iinvd[0] = r[PV_IIXX]; pv.Iinvd[1] = r[PV_IIYY]; pv.Iinvd[2] = r[PV_IIZZ];
+  pv.kF = r[PV_KF]; pv.kTau = r[PV_KTAU]; pv.motor_c = r[PV_MOTOR_C];
+}
 
 // Occupancy targets (blocks of AGF_BLOCK_THREADS per SM) of the fast variants; the parity variants
 // take whatever registers they need.  Tuned with -Xptxas -v and ncu, see DESIGN.md.
 #ifndef AGF_MINB_F32_UWB
-#define AGF_MINB_F32_UWB 4
+#define AGF_MINB_F32_UWB 3
 #endif
 #ifndef AGF_MINB_F32_RATES
 #define AGF_MINB_F32_RATES 4
@@ -1372,26 +1443,29 @@ constexpr size_t step_smem_bytes(int block) {
   return PARITY ? 0 : size_t(block) * (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) * sizeof(float4);
 }
 
-template<typename P, bool PARITY, bool UWB, bool HK>
-__global__ void __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
-step_kernel(const __grid_constant__ StepLaunch<P> L) {
-  extern __shared__ float4 agf_scratch[];
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= L.n) return;
-  Scratch sc;
-  sc.q = agf_scratch + threadIdx.x;
-  sc.stride = int(blockDim.x);
+// the ticks [t0, t1) of vehicle i; pv is the constant-bank struct or a register copy
+template<typename P, bool PARITY, bool UWB, bool HK, typename PVT>
+AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc, size_t i, uint32_t t0, uint32_t t1) {
   VState<P, PARITY, UWB, HK> s;
   state_load(s, L.st, L.n, i, sc);
-  PlantPV<P> pv;
-  plant_params_load(pv, L, i);
+  // clock-only stopwatches at tick t0: the same integer recurrence for every vehicle
   Timing ts = L.ts;
+  for (uint32_t t = 0; t < t0; t++) {
+    const TickPlan pl = timing_plan(ts, L.sh.tc);
+    timing_advance(ts, L.sh.tc, pl, L.dt_us);
+  }
+  // next scheduled radio delivery, as a tick offset into this launch (0xFFFFFFFF: none left)
   uint32_t si = L.sched_begin;
+  while (si < L.sched_end && L.sched[si].tick < L.tick0 + t0) si++;
+  uint32_t next_cmd = si < L.sched_end ? uint32_t(L.sched[si].tick - L.tick0) : 0xFFFFFFFFu;
+  // ticks until the next log record
+  uint32_t log_in = 0;
+  if (L.log) log_in = L.log_stride - uint32_t((L.tick0 + t0) % L.log_stride);
   const uint64_t gidx = L.first_global_index + i;
-  for (uint32_t t = 0; t < L.nticks; t++) {
+  for (uint32_t t = t0; t < t1; t++) {
     const uint64_t abs_tick = L.tick0 + t;
     // radio delivery before Run() (main.cpp:737-739 of the previous loop iteration)
-    if (si < L.sched_end && L.sched[si].tick == abs_tick) {
+    if (t == next_cmd) {
       const SchedEntryDev& e = L.sched[si];
       if (e.slot < 0) {
         radio_deliver(s, L.sh.logic, e.type, e.flags, e.f);
@@ -1402,9 +1476,11 @@ step_kernel(const __grid_constant__ StepLaunch<P> L) {
         radio_deliver(s, L.sh.logic, tf & 0xFFu, (tf >> 8) & 0xFFu, ff);
       }
       si++;
+      next_cmd = si < L.sched_end ? uint32_t(L.sched[si].tick - L.tick0) : 0xFFFFFFFFu;
     }
     tick<P, PARITY, UWB, HK>(s, sc, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
-    if (L.log && ((abs_tick + 1) % L.log_stride) == 0) {
+    if (L.log && --log_in == 0) {
+      log_in = L.log_stride;
       const uint64_t rec = (abs_tick + 1) / L.log_stride - 1;
       P* base = L.log + (size_t(rec % L.log_capacity) * AGF_LOG_FIELDS) * L.n + i;
 #pragma unroll
@@ -1414,6 +1490,114 @@ step_kernel(const __grid_constant__ StepLaunch<P> L) {
     }
   }
   state_store(s, L.st, L.n, i, sc, L.sh.logic.mix_kf);
+}
+
+// one work item: ticks [t0, t1) of vehicle block b
+template<typename P, bool PARITY, bool UWB, bool HK, bool PV>
+AGF_DEV void step_item(const StepLaunch<P>& L, const Scratch& sc, uint32_t b, uint32_t t0, uint32_t t1) {
+  const size_t i = size_t(b) * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  if constexpr (PARITY) {  // generic carrier, shared or per-vehicle decided at run time
+    PlantPV<P> pv;
+    plant_params_load(pv, L, i);
+    step_ticks<P, PARITY, UWB, HK>(L, pv, sc, i, t0, t1);
+  } else if constexpr (PV) {
+    PlantPVDiag<P> pv;
+    plant_params_load(pv, L, i);
+    step_ticks<P, PARITY, UWB, HK>(L, pv, sc, i, t0, t1);
+  } else {
+    step_ticks<P, PARITY, UWB, HK>(L, L.pv_shared, sc, i, t0, t1);
+  }
+}
+
+AGF_DEV void flag_publish(uint32_t* flag, uint32_t epoch) {
+#if defined(__CUDA_ARCH__)
+  __threadfence();   // this thread's state stores are visible device-wide ...
+  __syncthreads();   // ... for every thread of the CTA, before one thread raises the flag
+  if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+#endif
+}
+AGF_DEV void flag_wait(const uint32_t* flag, uint32_t epoch) {
+#if defined(__CUDA_ARCH__)
+  if (threadIdx.x == 0) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v != epoch) __nanosleep(200);
+    } while (v != epoch);
+  }
+  __syncthreads();
+#endif
+}
+
+template<typename P, bool PARITY, bool UWB, bool HK, bool PV>
+__global__ void __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
+step_kernel(const __grid_constant__ StepLaunch<P> L) {
+  extern __shared__ float4 agf_scratch[];
+  Scratch sc;
+  sc.q = agf_scratch + threadIdx.x;
+  // work items of this CTA, in order: [head part of block b_hi] [whole blocks] [tail part of block b_lo];
+  // a single call site keeps one copy of the step in the kernel image
+  uint32_t b_lo = blockIdx.x, t_lo = 0, b_hi = blockIdx.x + 1, t_hi = 0;
+  if (L.balanced) {
+    const uint64_t total = uint64_t(L.nblocks) * L.nticks;
+    const uint64_t lo = (uint64_t(blockIdx.x) * total) / gridDim.x, hi = (uint64_t(blockIdx.x + 1) * total) / gridDim.x;
+    b_lo = uint32_t(lo / L.nticks); t_lo = uint32_t(lo % L.nticks);
+    b_hi = uint32_t(hi / L.nticks); t_hi = uint32_t(hi % L.nticks);
+  }
+  const uint32_t first_whole = t_lo ? b_lo + 1 : b_lo;
+  const uint32_t n_head = t_hi ? 1u : 0u, n_whole = b_hi - first_whole, n_items = n_head + n_whole + (t_lo ? 1u : 0u);
+  for (uint32_t k = 0; k < n_items; k++) {
+    uint32_t b, t0 = 0, t1 = L.nticks;
+    const bool head = k < n_head, tail = k >= n_head + n_whole;
+    if (head) {  // first, then publish
+      b = b_hi;
+      t1 = t_hi;
+    } else if (tail) {  // last, after its head part was stored by the neighbouring CTA
+      b = b_lo;
+      t0 = t_lo;
+      flag_wait(L.flags + b_lo, L.epoch);
+    } else {
+      b = first_whole + (k - n_head);
+    }
+    step_item<P, PARITY, UWB, HK, PV>(L, sc, b, t0, t1);
+    if (head) flag_publish(L.flags + b_hi, L.epoch);
+  }
+}
+
+// Host side of the schedule: one wave of co-resident CTAs when that is fewer than the vehicle blocks.
+// (CTAs are dispatched in index order and a CTA only ever waits, at the end of its work, for what its
+// lower-indexed neighbour does first, so the wait cannot deadlock even if the wave is not fully resident.)
+template<typename P, typename K>
+static cudaError_t launch_step_kernel(K kernel, StepLaunch<P> L, int block, size_t smem, cudaStream_t stream) {
+  struct Cached { const void* fn; int block; size_t smem; int dev; int resident; };
+  static Cached cache[16];
+  static int ncached = 0;
+  L.nblocks = uint32_t((L.n + block - 1) / block);
+  L.balanced = 0;
+  unsigned grid = L.nblocks;
+  if (L.flags && L.nticks > 1) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int resident = -1;
+    for (int k = 0; k < ncached; k++)
+      if (cache[k].fn == (const void*)kernel && cache[k].block == block && cache[k].smem == smem && cache[k].dev == dev) resident = cache[k].resident;
+    if (resident < 0) {
+      int sms = 0, per_sm = 0;
+      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+      if (e != cudaSuccess) return e;
+      resident = sms * per_sm;
+      if (ncached < 16) cache[ncached++] = Cached{(const void*)kernel, block, smem, dev, resident};
+    }
+    if (resident > 0 && L.nblocks > unsigned(resident)) {
+      L.balanced = 1;
+      grid = unsigned(resident);
+    }
+  }
+  kernel<<<grid, block, smem, stream>>>(L);
+  return cudaGetLastError();
 }
 
 }  // namespace agf

@@ -199,14 +199,24 @@ struct PlantPV {
   P I[9], Iinv[9];
   P kF, kTau;
   P motor_c;  // exp(-dt/tau) of Motor.cpp:53-57 for the dt of this launch, evaluated on the host
+  P inv_mass; // 1/mass, used by the fast-arithmetic variants only
+};
+
+// the same for a per-vehicle parameter sweep: diagonal inertia, everything in registers
+template<typename P>
+struct PlantPVDiag {
+  P mass, inv_mass;
+  P Id[3], Iinvd[3];
+  P kF, kTau;
+  P motor_c;
 };
 
 #if defined(__CUDACC__)
 // per-vehicle plant parameters in HBM: 3 quads of P-lanes... stored as plain component arrays
 // grouped in 16-byte quads like the state: {mass, ixx, iyy, izz}, {iinv_xx, iinv_yy, iinv_zz, kF},
-// {kTau, motor_c, 0, 0}  -> NPV_PAD scalars
+// {kTau, motor_c, 1/mass, 0}  -> NPV_PAD scalars
 enum { PV_MASS = 0, PV_IXX = 1, PV_IYY = 2, PV_IZZ = 3, PV_IIXX = 4, PV_IIYY = 5, PV_IIZZ = 6, PV_KF = 7,
-       PV_KTAU = 8, PV_MOTOR_C = 9, NPV_PAD = 12 };
+       PV_KTAU = 8, PV_MOTOR_C = 9, PV_INV_MASS = 10, NPV_PAD = 12 };
 
 struct SchedEntryDev {
   uint64_t tick;
@@ -237,6 +247,14 @@ struct StepLaunch {
   P* log;  // [capacity][AGF_LOG_FIELDS][N] or null
   uint32_t log_stride, log_capacity;
   uint64_t first_global_index;
+  // Work distribution (agf_step.cuh "balanced schedule"): the population is cut into nblocks vehicle blocks of
+  // blockDim.x vehicles.  balanced == 0: CTA b steps block b for all nticks.  balanced == 1: the grid is one
+  // wave of co-resident CTAs and the nblocks x nticks block-ticks are dealt out evenly, a block's ticks being
+  // split between two neighbouring CTAs where a boundary falls inside it; flags[b] == epoch publishes that the
+  // first part of block b has been stored.
+  uint32_t nblocks, balanced;
+  uint32_t* flags;
+  uint32_t epoch;
 };
 #endif
 

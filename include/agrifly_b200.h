@@ -221,6 +221,11 @@ void* agf_batch_stream(const agf_batch* b);
  * -> clock += dt_us, for every vehicle: the loop body of
  * Simulator/Rappids_Simulator/main.cpp:391-392,737-739.  Asynchronous on the handle's stream. */
 int agf_batch_run(agf_batch* b, uint32_t dt_us, uint32_t nticks);
+/* The two halves of a tick for callers that own the clock, as the reference's apps do:
+ * agf_batch_run(b, 0, 1) is exactly `Run()` at the current clock reading (a second call without an advance
+ * in between returns early like Quadcopter_T.cpp:88-90), and agf_batch_advance_clock is
+ * ManualTimer::AdvanceMicroSeconds (ManualTimer.hpp:29) for every stopwatch slaved to the batch's clock. */
+int agf_batch_advance_clock(agf_batch* b, uint32_t dt_us);
 int agf_batch_sync(agf_batch* b);
 /* simulation clock (ManualTimer::GetMicroSeconds, ManualTimer.hpp:38) and ticks run so far */
 uint64_t agf_batch_time_us(const agf_batch* b);

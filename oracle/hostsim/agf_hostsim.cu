@@ -51,7 +51,7 @@ static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_
   StateArrays<double> a = v->arrays();
   Scratch sc;
   sc.q = nullptr;
-  sc.stride = 0;
+
   state_load(s, a, 1, 0, sc);
   v->sh.ext_force = v->ext_f.empty() ? nullptr : v->ext_f.data();
   v->sh.ext_torque = v->ext_t.empty() ? nullptr : v->ext_t.data();
@@ -135,10 +135,10 @@ void orc_set_radio(orc_vehicle* v, const uint8_t raw[23]) {
   memcpy(e.raw, raw, 23);
   // deliver through a zero-tick run: load, deliver, store
   if (v->uwb) {
-    VState<double, true, true, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr, 0}; state_load(s, a, 1, 0, sc);
+    VState<double, true, true, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr}; state_load(s, a, 1, 0, sc);
     uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   } else {
-    VState<double, true, false, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr, 0}; state_load(s, a, 1, 0, sc);
+    VState<double, true, false, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr}; state_load(s, a, 1, 0, sc);
     uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   }
 }
