@@ -40,6 +40,15 @@
 namespace agf {
 
 #define AGF_DEV __host__ __device__ __forceinline__
+// Rarely taken paths (estimator resets, start-up alignment, the external-acceleration controller, optional noise
+// sources) are real calls: the per-tick loop then spans ~half the bytes, which matters because it does not fit
+// the SM's instruction caches (profiles/: "no_instruction" was the largest single stall reason).
+#define AGF_COLD __host__ __device__ __noinline__
+#if defined(__CUDA_ARCH__)
+#define AGF_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define AGF_UNLIKELY(x) (x)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // libm policy
@@ -293,28 +302,41 @@ AGF_DEV uint4 philox4x32(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-AGF_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  const float u1 = (float(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
-  const float u2 = float(b >> 8) * (1.0f / 16777216.0f);           // [0, 1)
+// Box-Muller from two 21-bit uniforms: u1 in (0,1] (tails reach 5.4 sigma), angle = 2 pi u2.  The uniforms are
+// assembled in the mantissa of a float in [1,2) -- no integer-to-float conversion (XU pipe) needed.
+AGF_DEV void box_muller21(uint32_t f1, uint32_t f2, float& n0, float& n1) {
 #if defined(__CUDA_ARCH__)
-  const float r = ::sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.28318530718f * u2, &s, &c);
+  const float a = __uint_as_float(0x3f800000u | (f1 << 2));  // 1 + u, u = f1 / 2^21
+  const float b = __uint_as_float(0x3f800000u | (f2 << 2));
+  const float u1 = 2.0f - a;                                 // (0, 1]
+  const float r = ::sqrtf(-1.38629436f * __log2f(u1));       // sqrt(-2 ln u1)
+  float sn, cs;
+  __sincosf(6.28318530718f * (b - 1.0f), &sn, &cs);
 #else
+  const float u1 = 1.0f - float(f1) * (1.0f / 2097152.0f);
   const float r = ::sqrtf(-2.0f * ::logf(u1));
-  const float s = ::sinf(6.28318530718f * u2), c = ::cosf(6.28318530718f * u2);
+  const float ang = 6.28318530718f * (float(f2) * (1.0f / 2097152.0f));
+  const float sn = ::sinf(ang), cs = ::cosf(ang);
 #endif
-  n0 = r * c;
-  n1 = r * s;
+  n0 = r * cs;
+  n1 = r * sn;
 }
-// 6 standard normals for (vehicle, cycle, stream)
+// 6 standard normals for (vehicle, cycle, stream): ONE Philox4x32-10 block, its 128 bits cut into six 21-bit fields
 AGF_DEV void normals6(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream, float* n) {
   const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
-  const uint4 a = philox4x32<10>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u), key);
-  const uint4 b = philox4x32<10>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream * 2u + 1u), key);
-  box_muller(a.x, a.y, n[0], n[1]);
-  box_muller(a.z, a.w, n[2], n[3]);
-  box_muller(b.x, b.y, n[4], n[5]);
+  const uint4 r = philox4x32<10>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream), key);
+  const uint32_t m = 0x1FFFFFu;
+  box_muller21(r.x & m, ((r.x >> 21) | (r.y << 11)) & m, n[0], n[1]);
+  box_muller21((r.y >> 10) & m, r.z & m, n[2], n[3]);
+  box_muller21(((r.z >> 21) | (r.w << 11)) & m, (r.w >> 10) & m, n[4], n[5]);
+}
+struct Normals6 {
+  float n[6];
+};
+static AGF_COLD Normals6 normals6_cold(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream) {
+  Normals6 o;
+  normals6(seed, vehicle, cycle, stream, o.n);
+  return o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -623,8 +645,30 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
 // ---------------------------------------------------------------------------------------------
 #define AGF_COV(i, j) s.cov[9 * (i) + (j)]
 
-template<typename P, bool PARITY, bool UWB, bool HK>
-AGF_DEV void kf_reset(VState<P, PARITY, UWB, HK>& s, const Scratch& sc) {  // KalmanFilter6DOF.cpp:33-68
+// The estimator members the rarely taken paths touch, packed so they can cross a real call (fast variants)
+struct KfCore {
+  float kpos[3], kvel[3], kw[3], kcorr[3], katt[4];
+  uint32_t bits, kfcnt, cnt;
+};
+template<typename ST> AGF_DEV void kf_core_get(KfCore& c, const ST& s) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { c.kpos[k] = s.kpos[k]; c.kvel[k] = s.kvel[k]; c.kw[k] = s.kw[k]; c.kcorr[k] = s.kcorr[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) c.katt[k] = s.katt[k];
+  c.bits = s.bits; c.kfcnt = s.kfcnt; c.cnt = s.cnt;
+}
+template<typename ST> AGF_DEV void kf_core_put(ST& s, const KfCore& c) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.kpos[k] = c.kpos[k]; s.kvel[k] = c.kvel[k]; s.kw[k] = c.kw[k]; s.kcorr[k] = c.kcorr[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) s.katt[k] = c.katt[k];
+  s.bits = c.bits; s.kfcnt = c.kfcnt; s.cnt = c.cnt;
+}
+
+// ST is the register-resident VState, or a KfCore in the out-of-line copies of the fast variants (whose
+// covariance lives in the shared-memory scratch, not in ST)
+template<bool PARITY, bool UWB, typename ST>
+AGF_DEV void kf_reset(ST& s, const Scratch& sc) {  // KalmanFilter6DOF.cpp:33-68
   s.kfcnt = (s.kfcnt & 0xFFFF0000u) | ((s.kfcnt + 1u) & 0xFFFFu);
   s.bits &= ~(B_IMU_INIT | B_UWB_INIT);
   s.bits |= B_KF_RESET_SEEN;
@@ -674,10 +718,12 @@ AGF_DEV void gravity_axis_angle(const Q4<float>& att, const V3<float>& acc, V3<f
   ang = acos_guarded<PARITY>(cosErr);
 }
 
-template<bool PARITY, typename P, bool UWB, bool HK>
-AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const V3<float>& gyro, const V3<float>& acc, float dt) {
+// The two start-up branches of Predict: first call = reset + gravity alignment (:71-108); until the first UWB
+// range (always, without UWB) = complementary filter (:114-147).
+template<bool PARITY, bool UWB, typename ST>
+AGF_DEV void kf_predict_startup(ST& s, const Scratch& sc, const V3<float>& gyro, const V3<float>& acc, float dt) {
   if (!(s.bits & B_IMU_INIT)) {  // :71-108
-    kf_reset(s, sc);
+    kf_reset<PARITY, UWB>(s, sc);
     s.bits |= B_IMU_INIT;
     Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
     V3<float> ax;
@@ -688,17 +734,46 @@ AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const 
     return;
   }
   Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
-  if (!UWB || !(s.bits & B_UWB_INIT)) {  // :114-147 complementary filter
-    s.kw[0] = gyro.x; s.kw[1] = gyro.y; s.kw[2] = gyro.z;
-    att = q_apply_rotvec<PARITY>(att, gyro * dt);
-    V3<float> ax;
-    float ang;
-    gravity_axis_angle<PARITY>(att, acc, ax, ang);
-    const float corr = (dt / 4.0f) * ang;
-    att = qmul(att, q_from_axis_angle<PARITY>(ax, corr));
-    s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
-    return;
+  s.kw[0] = gyro.x; s.kw[1] = gyro.y; s.kw[2] = gyro.z;
+  att = q_apply_rotvec<PARITY>(att, gyro * dt);
+  V3<float> ax;
+  float ang;
+  gravity_axis_angle<PARITY>(att, acc, ax, ang);
+  const float corr = (dt / 4.0f) * ang;
+  att = qmul(att, q_from_axis_angle<PARITY>(ax, corr));
+  s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
+}
+static AGF_COLD void kf_predict_startup_cold(KfCore* c, Scratch sc, V3<float> gyro, V3<float> acc, float dt) {
+  kf_predict_startup<false, true>(*c, sc, gyro, acc, dt);
+}
+// a rejected range: counters, reset after 5 in a row (:272-284)
+template<bool PARITY, bool UWB, typename ST>
+AGF_DEV void kf_range_rejected(ST& s, const Scratch& sc) {
+  const uint32_t rej = (s.kfcnt >> 16) + 1u;
+  s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
+  const uint32_t seq = (s.cnt & 0xFFu) + 1u;
+  s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
+  if (seq >= 5u) kf_reset<PARITY, UWB>(s, sc);
+}
+static AGF_COLD void kf_range_rejected_cold(KfCore* c, Scratch sc) { kf_range_rejected<false, true>(*c, sc); }
+
+template<bool PARITY, typename P, bool UWB, bool HK>
+AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const V3<float>& gyro, const V3<float>& acc, float dt) {
+  if constexpr (!PARITY && UWB) {  // start-up is rare once ranging runs: out of line
+    if (AGF_UNLIKELY((s.bits & (B_IMU_INIT | B_UWB_INIT)) != (B_IMU_INIT | B_UWB_INIT))) {
+      KfCore c;
+      kf_core_get(c, s);
+      kf_predict_startup_cold(&c, sc, gyro, acc, dt);
+      kf_core_put(s, c);
+      return;
+    }
+  } else {
+    if (!UWB || (s.bits & (B_IMU_INIT | B_UWB_INIT)) != (B_IMU_INIT | B_UWB_INIT)) {
+      kf_predict_startup<PARITY, UWB>(s, sc, gyro, acc, dt);
+      return;
+    }
   }
+  Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
   if constexpr (UWB) {  // :149-241
     const V3<float> p0(s.kpos[0], s.kpos[1], s.kpos[2]), v0(s.kvel[0], s.kvel[1], s.kvel[2]);
     float Rm[9];
@@ -837,12 +912,11 @@ AGF_DEV void kf_update_range(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, c
     for (int i = 0; i < 9; i++) PHt[i] = PS(i, 0) * H.x + PS(i, 1) * H.y + PS(i, 2) * H.z;
     const float innovCov = (H.x * PHt[0] + H.y * PHt[1] + H.z * PHt[2]) + 0.14f * 0.14f;
     const float inv = fdiv<false>(1.0f, innovCov);
-    if (innov * innov * inv > 3.0f * 3.0f) {
-      const uint32_t rej = (s.kfcnt >> 16) + 1u;
-      s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
-      const uint32_t seq = (s.cnt & 0xFFu) + 1u;
-      s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
-      if (seq >= 5u) kf_reset(s, sc);
+    if (AGF_UNLIKELY(innov * innov * inv > 3.0f * 3.0f)) {
+      KfCore c;
+      kf_core_get(c, s);
+      kf_range_rejected_cold(&c, sc);
+      kf_core_put(s, c);
       return;
     }
     s.cnt &= ~0xFFu;
@@ -872,11 +946,7 @@ AGF_DEV void kf_update_range(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, c
   for (int i = 0; i < 9; i++) L[i] = PHt[i] * inv;
   const float d2 = innov * innov / innovCov;
   if (d2 > 3.0f * 3.0f) {
-    uint32_t rej = (s.kfcnt >> 16) + 1u;
-    s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
-    uint32_t seq = (s.cnt & 0xFFu) + 1u;
-    s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
-    if (seq >= 5u) kf_reset(s, sc);
+    kf_range_rejected<PARITY, UWB>(s, sc);
     return;
   }
   s.cnt &= ~0xFFu;
@@ -1014,6 +1084,29 @@ AGF_DEV Q4<float> att_from_thrust_dir(const V3<float>& dir) {
   return out;
 }
 
+// RunControllerExternalAccelerationControl up to the desired body rates (QuadcopterLogic.cpp:459-517):
+// returns (desW.x, desW.y, desW.z, thrust); thrust < 0 stands for "motors off" (desired z acceleration below -g/2)
+template<bool PARITY>
+AGF_DEV float4 ctl_accel_mode(const LogicParams& k, const float4& estAtt4, const float4& radio) {
+  const Q4<float> estAtt(estAtt4.x, estAtt4.y, estAtt4.z, estAtt4.w);
+  const V3<float> desAcc(radio.x, radio.y, radio.z);
+  if (desAcc.z < -9.81f / 2) return make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+  const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
+  const float thrust = norm(proper);
+  const V3<float> dir = vdiv<PARITY>(proper, thrust);
+  const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
+  // ToEulerYPR (Rotation.hpp:163-169); yaw is computed by the reference but unused
+  const Q4<float>& q = estAtt;
+  const float pch = -Mf<PARITY>::asin(2.0f * q.x * q.z - 2.0f * q.w * q.y);
+  const float rll = Mf<PARITY>::atan2(2.0f * q.y * q.z + 2.0f * q.w * q.x, q.z * q.z - q.y * q.y - q.x * q.x + q.w * q.w);
+  const Q4<float> noYaw = q_from_euler_ypr<PARITY>(0.0f, pch, rll);
+  const V3<float> desW = ctl_att<PARITY>(k, desAtt, noYaw);
+  return make_float4(desW.x, desW.y, radio.w, thrust);
+}
+static AGF_COLD float4 ctl_accel_mode_cold(const LogicParams* k, float4 estAtt, float4 radio) {
+  return ctl_accel_mode<false>(*k, estAtt, radio);
+}
+
 // ---------------------------------------------------------------------------------------------
 // QuadcopterLogic::Run (QuadcopterLogic.cpp:164-219) with its intake setters
 // ---------------------------------------------------------------------------------------------
@@ -1114,12 +1207,60 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
   }
   s.bits = bset(s.bits, B_FS_SHIFT, B_FS_MASK, fs);
 
-  // --- controllers :194-217 ---
+  // --- controllers :194-217 ---  Each flight mode produces (total thrust [m/s^2], desired body rates); the
+  // rate controller and mixer that all three modes end in (:451-455, :519-524, :547-551) are written once.
   const V3<float> estW(s.kw[0], s.kw[1], s.kw[2]);
+  bool powered = false;
+  float thrust = 0.0f;
+  V3<float> desW(0.0f, 0.0f, 0.0f);
   if (fs == AGF_FS_EXTERNAL_RATES_CONTROL) {  // :528-588
-    const V3<float> tq = ctl_torques<PARITY>(k, V3<float>(s.radio_f[1], s.radio_f[2], s.radio_f[3]), estW);
-    ctl_mix(s, k, s.radio_f[0] * k.mass, tq);
-    if constexpr (HK) {
+    desW = V3<float>(s.radio_f[1], s.radio_f[2], s.radio_f[3]);
+    thrust = s.radio_f[0];
+    powered = true;
+  } else if (fs == AGF_FS_FULLY_AUTONOMOUS) {  // :393-457
+    const V3<float> estPos(s.kpos[0], s.kpos[1], s.kpos[2]), estVel(s.kvel[0], s.kvel[1], s.kvel[2]);
+    const Q4<float> estAtt(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
+    const V3<float> desPos(s.radio_f[0], s.radio_f[1], s.radio_f[2]);
+    // GetDesAcceleration (QuadcopterPositionController.hpp:22-27), desVel = desAcc = 0
+    const V3<float> zero(0, 0, 0);
+    const V3<float> dv = zero - estVel;
+    const V3<float> desAcc = (((desPos - estPos) * k.nat_freq) * k.nat_freq +
+                              ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * k.nat_freq) * k.damping)) + zero;
+    const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
+    const float nProper = norm(proper);
+    const V3<float> dir = vdiv<PARITY>(proper, nProper);
+    const float corr = qrot_e3_z(estAtt);
+    const float corrSat = corr < 1.00f ? 1.00f : corr;
+    thrust = fdiv<PARITY>(nProper, corrSat);
+    const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
+    desW = ctl_att<PARITY>(k, desAtt, estAtt);
+    powered = true;
+  } else if (fs == AGF_FS_EXTERNAL_ACCELERATION_CONTROL) {  // :459-526
+    float4 r;
+    if constexpr (PARITY) {
+      r = ctl_accel_mode<true>(k, make_float4(s.katt[0], s.katt[1], s.katt[2], s.katt[3]),
+                               make_float4(s.radio_f[0], s.radio_f[1], s.radio_f[2], s.radio_f[3]));
+    } else {
+      r = ctl_accel_mode_cold(&k, make_float4(s.katt[0], s.katt[1], s.katt[2], s.katt[3]),
+                              make_float4(s.radio_f[0], s.radio_f[1], s.radio_f[2], s.radio_f[3]));
+    }
+    if (r.w >= 0.0f) {  // thrust is a norm: negative marks "motors off" (:466-470)
+      desW = V3<float>(r.x, r.y, r.z);
+      thrust = r.w;
+      powered = true;
+    }
+  }
+  if (powered) {
+    ctl_mix(s, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      s.cmd[i] = 0;
+      if constexpr (PARITY || HK) s.dforce[i] = 0;
+    }
+  }
+  if constexpr (HK) {  // propeller calibration, rates mode only (:553-587)
+    if (fs == AGF_FS_EXTERNAL_RATES_CONTROL) {
       if (rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) {
         if (!(s.bits & B_PC_RUNNING)) {
           s.bits |= B_PC_RUNNING;
@@ -1144,53 +1285,6 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
           }
         }
       }
-    }
-  } else if (fs == AGF_FS_FULLY_AUTONOMOUS) {  // :393-457
-    const V3<float> estPos(s.kpos[0], s.kpos[1], s.kpos[2]), estVel(s.kvel[0], s.kvel[1], s.kvel[2]);
-    const Q4<float> estAtt(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
-    const V3<float> desPos(s.radio_f[0], s.radio_f[1], s.radio_f[2]);
-    // GetDesAcceleration (QuadcopterPositionController.hpp:22-27), desVel = desAcc = 0
-    const V3<float> zero(0, 0, 0);
-    const V3<float> dv = zero - estVel;
-    const V3<float> desAcc = (((desPos - estPos) * k.nat_freq) * k.nat_freq +
-                              ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * k.nat_freq) * k.damping)) + zero;
-    const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
-    const float nProper = norm(proper);
-    const V3<float> dir = vdiv<PARITY>(proper, nProper);
-    const float corr = qrot_e3_z(estAtt);
-    const float corrSat = corr < 1.00f ? 1.00f : corr;
-    const float thrust = fdiv<PARITY>(nProper, corrSat);
-    const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
-    const V3<float> desW = ctl_att<PARITY>(k, desAtt, estAtt);
-    ctl_mix(s, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
-  } else if (fs == AGF_FS_EXTERNAL_ACCELERATION_CONTROL) {  // :459-526
-    const Q4<float> estAtt(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
-    const V3<float> desAcc(s.radio_f[0], s.radio_f[1], s.radio_f[2]);
-    if (desAcc.z < -9.81f / 2) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        s.cmd[i] = 0;
-        if constexpr (PARITY || HK) s.dforce[i] = 0;
-      }
-    } else {
-      const V3<float> proper = desAcc + V3<float>(0, 0, 9.81f);
-      const float thrust = norm(proper);
-      const V3<float> dir = vdiv<PARITY>(proper, thrust);
-      const Q4<float> desAtt = att_from_thrust_dir<PARITY>(dir);
-      // ToEulerYPR (Rotation.hpp:163-169); yaw is computed by the reference but unused
-      const Q4<float>& q = estAtt;
-      const float pch = -Mf<PARITY>::asin(2.0f * q.x * q.z - 2.0f * q.w * q.y);
-      const float rll = Mf<PARITY>::atan2(2.0f * q.y * q.z + 2.0f * q.w * q.x, q.z * q.z - q.y * q.y - q.x * q.x + q.w * q.w);
-      const Q4<float> noYaw = q_from_euler_ypr<PARITY>(0.0f, pch, rll);
-      V3<float> desW = ctl_att<PARITY>(k, desAtt, noYaw);
-      desW.z = s.radio_f[3];
-      ctl_mix(s, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      s.cmd[i] = 0;
-      if constexpr (PARITY || HK) s.dforce[i] = 0;
     }
   }
 }
@@ -1288,8 +1382,12 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     V3<P> acc(P(0), P(0), P(-9.81));
     if (PARITY) {
       acc = acc + vdiv<true>(qrot(att, F) + extF, pv.mass);
-    } else {
+    } else if (p.has_drag) {
       acc = acc + (qrot(att, F) + extF) * pv.inv_mass;
+    } else {  // F = (0, 0, Fz): only the third column of the rotation matrix is needed
+      const V3<P> c3(2 * att.x * att.z + 2 * att.w * att.y, 2 * att.y * att.z - 2 * att.w * att.x,
+                     att.w * att.w - att.x * att.x - att.y * att.y + att.z * att.z);
+      acc = acc + (c3 * F.z + extF) * pv.inv_mass;
     }
     const V3<P> pos(s.pos[0], s.pos[1], s.pos[2]), vel(s.vel[0], s.vel[1], s.vel[2]);
     V3<P> npos = (pos + vel * dt) + ((P(0.5) * acc) * dt) * dt;
@@ -1320,11 +1418,10 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
         normals6(p.seed, gidx, s.cycle, 0u, nrm);
         g = g + V3<float>(nrm[0], nrm[1], nrm[2]) * p.sigma_gyro;
         a = a + V3<float>(nrm[3], nrm[4], nrm[5]) * p.sigma_acc;
-        if (p.bias_on) {
-          float b[6];
-          normals6(p.seed, gidx, 0xFFFFFFFFu, 1u, b);
-          g = g + V3<float>(b[0], b[1], b[2]) * p.bias_sigma_gyro;
-          a = a + V3<float>(b[3], b[4], b[5]) * p.bias_sigma_acc;
+        if (AGF_UNLIKELY(p.bias_on)) {  // constant per vehicle: counter (vehicle, 0xFFFFFFFF, 1)
+          const Normals6 b = normals6_cold(p.seed, gidx, 0xFFFFFFFFu, 1u);
+          g = g + V3<float>(b.n[0], b.n[1], b.n[2]) * p.bias_sigma_gyro;
+          a = a + V3<float>(b.n[3], b.n[4], b.n[5]) * p.bias_sigma_acc;
         }
       }
       logic_run<PARITY>(s, sc, p, g, a, float(plan.kf_dt_us) * 1e-6f);
@@ -1354,10 +1451,9 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       const V3<P> d = V3<P>(s.rpos[0], s.rpos[1], s.rpos[2]) -
                       V3<P>(P(p.anchors[resp].x), P(p.anchors[resp].y), P(p.anchors[resp].z));
       P r = norm(d);
-      if (p.uwb_noise_on) {
-        float nrm[6];
-        normals6(p.seed, gidx, uint32_t(abs_tick), 2u, nrm);
-        r = r + P(nrm[0]) * P(p.uwb_sigma);
+      if (AGF_UNLIKELY(p.uwb_noise_on)) {
+        const Normals6 nrm = normals6_cold(p.seed, gidx, uint32_t(abs_tick), 2u);
+        r = r + P(nrm.n[0]) * P(p.uwb_sigma);
       } else {
         r = r + P(0);
       }
