@@ -130,6 +130,13 @@ template<bool PARITY> AGF_DEV float fdiv(float a, float b) {
   return a / b;
 }
 template<bool PARITY> AGF_DEV double fdiv(double a, double b) { return a / b; }
+AGF_DEV float rsqrtf_(float x) {  // 1/sqrt(x)
+#if defined(__CUDA_ARCH__)
+  return ::rsqrtf(x);
+#else
+  return 1.0f / ::sqrtf(x);
+#endif
+}
 AGF_DEV float rsqrt_(float x) { return ::sqrtf(x); }
 AGF_DEV double rsqrt_(double x) { return ::sqrt(x); }
 AGF_DEV float rabs_(float x) { return ::fabsf(x); }
@@ -230,11 +237,71 @@ AGF_DEV bool q_from_rotvec(const V3<R>& rv, Q4<R>& out) {
   out = q_from_axis_angle<PARITY>(vdiv<PARITY>(rv, theta), theta);
   return true;
 }
+// Fast variants: FromRotationVector as two even polynomials of the half angle h, q = (cos h, rv * sin(h)/(2h)),
+// evaluated in z = h^2 = |rv|^2/4 -- no square root, no division, no range test for sin and cos separately.
+// |h| <= 0.5 covers every per-tick rotation (|w| < 500 rad/s at 2 ms); larger angles take the general routine.
+template<typename R> struct RotvecPoly;
+template<> struct RotvecPoly<float> {
+  static AGF_DEV float cosp(float z) {  // cos(h), error < 3e-10 for z <= 0.25
+    float p = ::fmaf(z, 2.48015873e-5f, -1.38888889e-3f);
+    p = ::fmaf(z, p, 4.16666667e-2f);
+    p = ::fmaf(z, p, -0.5f);
+    return ::fmaf(z, p, 1.0f);
+  }
+  static AGF_DEV float half_sinc(float z) {  // sin(h)/(2h)
+    float p = ::fmaf(z, 1.37786596e-6f, -9.92063492e-5f);
+    p = ::fmaf(z, p, 4.16666667e-3f);
+    p = ::fmaf(z, p, -8.33333333e-2f);
+    return ::fmaf(z, p, 0.5f);
+  }
+};
+template<> struct RotvecPoly<double> {
+  static AGF_DEV double cosp(double z) {
+    double p = ::fma(z, 4.7794773323873853e-14, -1.1470745597729725e-11);
+    p = ::fma(z, p, 2.0876756987868099e-9);
+    p = ::fma(z, p, -2.7557319223985888e-7);
+    p = ::fma(z, p, 2.4801587301587302e-5);
+    p = ::fma(z, p, -1.3888888888888889e-3);
+    p = ::fma(z, p, 4.1666666666666664e-2);
+    p = ::fma(z, p, -0.5);
+    return ::fma(z, p, 1.0);
+  }
+  static AGF_DEV double half_sinc(double z) {
+    double p = ::fma(z, 1.4056851100590741e-15, -3.8238541122497209e-13);
+    p = ::fma(z, p, 8.0295219184108065e-11);
+    p = ::fma(z, p, -1.2526054192720860e-8);
+    p = ::fma(z, p, 1.3778659611992946e-6);
+    p = ::fma(z, p, -9.9206349206349206e-5);
+    p = ::fma(z, p, 4.1666666666666666e-3);
+    p = ::fma(z, p, -8.3333333333333329e-2);
+    return ::fma(z, p, 0.5);
+  }
+};
+template<typename R>
+static AGF_COLD Q4<R> q_from_rotvec_general(V3<R> rv) {  // angles beyond the polynomial's range
+  Q4<R> d(R(1), R(0), R(0), R(0));
+  q_from_rotvec<false>(rv, d);
+  return d;
+}
 template<bool PARITY, typename R>
 AGF_DEV Q4<R> q_apply_rotvec(const Q4<R>& a, const V3<R>& rv) {  // a * FromRotationVector(rv)
-  Q4<R> d;
-  if (!q_from_rotvec<PARITY>(rv, d)) return a;  // a * Identity == a exactly
-  return qmul(a, d);
+  if constexpr (PARITY) {
+    Q4<R> d;
+    if (!q_from_rotvec<PARITY>(rv, d)) return a;  // a * Identity == a exactly
+    return qmul(a, d);
+  } else {
+    const R z = R(0.25) * dot(rv, rv);
+    Q4<R> d;
+    if (AGF_UNLIKELY(z > R(0.25))) {
+      d = q_from_rotvec_general<R>(rv);
+    } else {
+      // below MIN_ANGLE the reference returns the identity (Rotation.hpp:84-88): theta^2 < MIN_ANGLE^2 <=> z < MIN_ANGLE^2/4
+      const bool tiny = z < R(5.8761074e-12);
+      const R k = tiny ? R(0) : RotvecPoly<R>::half_sinc(z);
+      d = Q4<R>(tiny ? R(1) : RotvecPoly<R>::cosp(z), k * rv.x, k * rv.y, k * rv.z);
+    }
+    return qmul(a, d);
+  }
 }
 // FromEulerYPR (Rotation.hpp:99-110)
 template<bool PARITY>
@@ -1016,12 +1083,16 @@ AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q
     c = e3b.z;
   }
   float redAn;
-  if (c >= 1.0f) {
-    redAn = 0;
-  } else if (c <= -1.0f) {
-    redAn = 3.14159274f;
+  if constexpr (PARITY) {
+    if (c >= 1.0f) {
+      redAn = 0;
+    } else if (c <= -1.0f) {
+      redAn = 3.14159274f;
+    } else {
+      redAn = Mf<PARITY>::acos(c);
+    }
   } else {
-    redAn = Mf<PARITY>::acos(c);
+    redAn = Mf<PARITY>::acos(::fminf(::fmaxf(c, -1.0f), 1.0f));  // acosf(+-1) = 0 / pi exactly
   }
   const float n = norm(redAx);
   if (n < 1e-12f) {
@@ -1052,10 +1123,14 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float 
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    if (f[i] < k.min_thrust) {
-      f[i] = k.min_thrust;
-    } else if (f[i] > k.max_thrust) {
-      f[i] = k.max_thrust;
+    if constexpr (PARITY) {
+      if (f[i] < k.min_thrust) {
+        f[i] = k.min_thrust;
+      } else if (f[i] > k.max_thrust) {
+        f[i] = k.max_thrust;
+      }
+    } else {
+      f[i] = f[i] < k.min_thrust ? k.min_thrust : (f[i] > k.max_thrust ? k.max_thrust : f[i]);
     }
     if constexpr (PARITY || HK) s.dforce[i] = f[i];
     float corr = 1.0f;
@@ -1063,7 +1138,7 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float 
     if (PARITY || HK) {
       s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(fdiv<PARITY>(f[i], corr * k.mix_kf));
     } else {
-      s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(f[i] * k.inv_mix_kf);
+      s.cmd[i] = ::sqrtf(::fmaxf(f[i], 0.0f) * k.inv_mix_kf);  // sqrt(0) = 0: no branch for f <= 0
     }
   }
 }
@@ -1071,17 +1146,29 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float 
 // thrust direction -> attitude (QuadcopterLogic.cpp:423-445)
 template<bool PARITY>
 AGF_DEV Q4<float> att_from_thrust_dir(const V3<float>& dir) {
-  const V3<float> e3(0, 0, 1);
-  const float cosAngle = dot(dir, e3);
-  const float angle = acos_guarded<PARITY>(cosAngle);
-  const V3<float> rotAx = cross(e3, dir);
-  const float n = norm(rotAx);
-  Q4<float> out(1, 0, 0, 0);
-  if (!(n < 1e-6f)) {
-    Q4<float> d;
-    if (q_from_rotvec<PARITY>(rotAx * fdiv<PARITY>(angle, n), d)) out = d;
+  if constexpr (PARITY) {
+    const V3<float> e3(0, 0, 1);
+    const float cosAngle = dot(dir, e3);
+    const float angle = acos_guarded<PARITY>(cosAngle);
+    const V3<float> rotAx = cross(e3, dir);
+    const float n = norm(rotAx);
+    Q4<float> out(1, 0, 0, 0);
+    if (!(n < 1e-6f)) {
+      Q4<float> d;
+      if (q_from_rotvec<PARITY>(rotAx * fdiv<PARITY>(angle, n), d)) out = d;
+    }
+    return out;
+  } else {
+    // Same rotation in closed form: axis = e3 x dir = (-dy, dx, 0)/sin(a), cos(a) = dz, so with c = cos(a/2) =
+    // sqrt((1 + dz)/2):  q = (c, -dy/(2c), dx/(2c), 0).  No acos, no sin/cos; identity where the reference's
+    // guards (|e3 x dir| < 1e-6, angle < MIN_ANGLE) return it.
+    const float n2 = dir.x * dir.x + dir.y * dir.y;
+    const float c2 = 0.5f * (1.0f + dir.z);
+    const bool ident = (n2 < 1e-12f) || !(c2 > 0.0f);
+    const float ic = rsqrtf_(ident ? 1.0f : c2);
+    const float k = 0.5f * ic;
+    return ident ? Q4<float>(1, 0, 0, 0) : Q4<float>(c2 * ic, -dir.y * k, dir.x * k, 0.0f);
   }
-  return out;
 }
 
 // RunControllerExternalAccelerationControl up to the desired body rates (QuadcopterLogic.cpp:459-517):
@@ -1188,7 +1275,7 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
   s.bits &= ~B_KF_RESET_SEEN;
   // --- CheckPanicReasons :344-391 ---
   {
-    const bool running = s.cmd[0] > 0 || s.cmd[1] > 0 || s.cmd[2] > 0 || s.cmd[3] > 0;
+    const bool running = (s.cmd[0] > 0) | (s.cmd[1] > 0) | (s.cmd[2] > 0) | (s.cmd[3] > 0);
     uint32_t unsafe = 0;
     if (running) {
       const bool nochk = (rflags & AGF_RADIO_FLAG_DISABLE_ONBOARD_SAFETY) != 0;
@@ -1339,10 +1426,14 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       if (cmd < 0) cmd = 0;
       const P old = s.ms[m];
       P sp = c * old + (1 - c) * cmd;
-      if (sp > p.motor_max) {
-        sp = p.motor_max;
-      } else if (sp < p.motor_min) {
-        sp = p.motor_min;
+      if constexpr (PARITY) {
+        if (sp > p.motor_max) {
+          sp = p.motor_max;
+        } else if (sp < p.motor_min) {
+          sp = p.motor_min;
+        }
+      } else {
+        sp = sp > p.motor_max ? p.motor_max : (sp < p.motor_min ? p.motor_min : sp);
       }
       s.ms[m] = sp;
       const P fz = (pv.kF * sp) * rabs_(sp);

@@ -12,8 +12,8 @@ done
 unset AGF_LIB_PATH
 for m in "fp32 rates" "fp64 uwb" "fp64 rates"; do echo "== base $m" >> gpurun_out/variants.log; timeout 120 python profiles/prof_step.py $m 131072 500 3 >> gpurun_out/variants.log 2>&1; done
 timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; echo "bench rc=$?" >> gpurun_out/bench_b.err
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_b.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/launches_b.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 1 -c 1 -o gpurun_out/prof_f32_uwb_b python profiles/prof_step.py fp32 uwb 131072 100 2 > gpurun_out/prof_full_b.log 2>&1
+AGF_NO_WARM=1 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_b.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/launches_b.log 2>&1
+AGF_NO_WARM=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 1 -c 1 -o gpurun_out/prof_f32_uwb_b python profiles/prof_step.py fp32 uwb 131072 100 2 > gpurun_out/prof_full_b.log 2>&1
 for w in "parity fp64 uwb" "parity fp64 rates" "fast fp32 uwb" "fast fp32 rates" "fast fp64 uwb"; do
   timeout 200 ncu --metrics $OPS --clock-control none -k regex:step_kernel -s 1 -c 1 --csv --log-file "gpurun_out/flops_${w// /_}.csv" python profiles/flop_count.py $w 4096 300 > "gpurun_out/flops_${w// /_}.log" 2>&1
 done
