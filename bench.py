@@ -18,10 +18,12 @@ value   = vehicle-steps/s over all GPUs, state resident in HBM, timed with CUDA 
 e2e     = same metric through the public C ABI with HOST buffers: every step copies the population's 6-DOF
           state in from pinned host memory (agf_batch_set_field), runs the ticks, and copies positions and the
           statistics vector back (agf_batch_get_field / agf_batch_reduce_stats).
-roofline: the step is ALU-bound (nothing is a contraction; state stays in registers): achieved = vehicle-steps/s x
-          algorithmic FLOP per vehicle-step (2900 full mode) against the FP32 pipe peak
-          148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json).  The HBM-bound logging configuration (C4)
-          is reported under "roofline_logging" against the measured copy bandwidth.
+roofline: the step is ALU-bound (nothing is a contraction; state stays in registers): achieved = vehicle-steps/s of
+          the step kernel alone x algorithmic FLOP per vehicle-step (2489 full mode, counted with hardware counters on
+          the literal restatement of the reference's algorithm; SURVEY.md 8d's hand count 2900 and the 1378 FLOP the
+          fast kernel really executes are reported beside it) against the FP32 pipe peak 148 SM x 128 lanes x 2 x
+          sm_max_mhz (MEASURED_PEAKS.json).  The HBM-bound logging configuration (C4) is reported under
+          "roofline_logging" against the measured copy bandwidth.
 """
 import argparse
 import json
@@ -35,16 +37,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_FULL = 2900.0   # algorithmic FLOP per vehicle-step, full onboard mode
-FLOP_RATES = 1180.0  # rates mode
+# Algorithmic FLOP per vehicle-step (+,-,x = 1, FMA = 2), three ways (DESIGN.md "Work per vehicle-step"):
+#   *_INSTR  counted with hardware counters (ncu smsp__sass_thread_inst_executed_op_{f,d}{add,mul,fma}) on the parity
+#            kernel, i.e. the reference's algorithm restated literally minus its structural zeros, in flight, noise on
+#            (profiles/r1/flops_parity_*.csv).  This is the figure the roofline uses.
+#   *_SURVEY the hand count of SURVEY.md 8d (2900 "sparsity-aware" full mode / 1180 rates mode)
+#   *_EXEC   what the fast FP32 kernel actually executes per step (symmetric packed EKF, closed forms)
+FLOP_FULL_INSTR, FLOP_FULL_SURVEY, FLOP_FULL_EXEC = 2489.0, 2900.0, 1378.0
+FLOP_RATES_INSTR, FLOP_RATES_SURVEY, FLOP_RATES_EXEC = 1264.0, 1180.0, 699.0
+FLOP_FULL, FLOP_RATES = FLOP_FULL_INSTR, FLOP_RATES_INSTR
 LOG_BYTES_FP32 = 68.0
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--vehicles-per-gpu", type=int, default=131072)
     ap.add_argument("--ticks-per-step", type=int, default=500)
@@ -68,51 +77,94 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event reasons sampled through NVML every 10 ms DURING the timed region (a thread of this
+    process; nvidia-smi -lms buffers its output and loses short regions)."""
 
     def __init__(self, index):
         self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.rows = []
+        self.stop_flag = False
+        self.th = None
+        self.h = None
+        self.nv = None
 
     def start(self):
+        import threading
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            self.h = None
+            if uuid:
+                for cand in ("GPU-" + uuid, ("GPU-" + uuid).encode()):
+                    try:
+                        self.h = nv.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        continue
+            if self.h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+                self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = nv
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+
+        def loop():
+            nv = self.nv
+            while not self.stop_flag:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    self.rows.append((sm, mx, pw, rs))
+                except Exception:
+                    pass
+                time.sleep(0.01)
+
+        self.th = threading.Thread(target=loop, daemon=True)
+        self.th.start()
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        if self.p is None:
+        if self.nv is None or self.th is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
-        os.unlink(self.f.name)
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        nv, rows = self.nv, self.rows
         if not rows:
             return out
-        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if r[2].strip().replace(".", "").isdigit()]
-        pw = [float(r[3]) for r in rows if r[3].strip().replace(".", "").isdigit()]
-        # under load = upper half of the power samples
-        if sm:
-            k = sorted(range(len(sm)), key=lambda i: pw[i] if i < len(pw) else 0)[len(sm) // 2:]
-            out["sm_mhz"] = statistics.median([sm[i] for i in k])
-        out["sm_max_mhz"] = max(mx) if mx else None
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for j, nm in enumerate(names):
-            if any("Active" in r[5 + j] and "Not" not in r[5 + j] for r in rows):
+        out["sm_mhz"] = statistics.median([r[0] for r in rows])
+        out["sm_min_mhz"] = min(r[0] for r in rows)
+        out["sm_max_mhz"] = max(r[1] for r in rows)
+        out["power_w_max"] = max(r[2] for r in rows)
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        for nm, bit in names:
+            if any(r[3] & bit for r in rows):
                 out["reasons"].append(nm)
         out["samples"] = len(rows)
-        out["power_w_max"] = max(pw) if pw else None
         return out
+
+
+def traffic_per_launch(args, n, ticks):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch of the bench configuration, from the
+    committed ncu capture (profiles/r1/traffic.json); None when the configuration was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "traffic.json")) as f:
+            t = json.load(f)
+        key = "%s_uwb_%d_%d" % (args.precision, n, ticks)
+        return t.get(key)
+    except Exception:
+        return None
 
 
 def workload(agf, n, first, precision, ticks_total, seed=7, device=0, stream=None, hk=False, uwb=True, noise=True):
@@ -303,10 +355,18 @@ def main():
                  steps=ke, note="per GPU bytes; state set from pinned host memory, positions + statistics read back"),
         gpu_launches=int(launches),
         roofline=dict(bound="fp32_alu" if args.precision == "fp32" else "fp64_alu", achieved=achieved, peak=peak, unit="TFLOP/s",
-                      frac=achieved / peak, traffic=None,
-                      note="ALU-bound kernel (no contraction, state in registers): algorithmic %.0f FLOP per vehicle-step x "
-                           "vehicle-steps/s of the step kernel alone (CUDA events inside the library on the launching stream, "
-                           "%d launches, %.3f ms each) / FP32 pipe peak 148x128x2x%.0f MHz (%s sm_max_mhz)"
+                      frac=achieved / peak, traffic=traffic_per_launch(args, n, S),
+                      flop_per_vehicle_step=dict(used=flop, instrumented_literal=FLOP_FULL_INSTR, survey_hand_count=FLOP_FULL_SURVEY,
+                                                 executed_by_fast_kernel=FLOP_FULL_EXEC),
+                      frac_survey_count=kernel_steps_per_s * FLOP_FULL_SURVEY / 1e12 / peak,
+                      frac_executed=kernel_steps_per_s * FLOP_FULL_EXEC / 1e12 / peak,
+                      kernel_vehicle_steps_per_s=kernel_steps_per_s,
+                      note="ALU-bound kernel (no contraction, state in registers; HBM is touched at launch boundaries only: "
+                           "traffic = DRAM bytes of one launch from profiles/, a few %% of what the HBM could move in that time). "
+                           "achieved = %.0f FLOP per vehicle-step (hardware-counted on the literal restatement of the reference's "
+                           "algorithm) x vehicle-steps/s of the step kernel alone (CUDA events inside the library on the launching "
+                           "stream, %d launches, %.3f ms each); peak = FP32 pipe 148 SM x 128 lanes x 2 x %.0f MHz (%s sm_max_mhz); "
+                           "frac_executed counts only the FLOP the fast kernel really issues"
                            % (flop, kl, kms / max(kl, 1), pk["sm_max_mhz"], pk["source"])),
         wall_ms=t_wall * 1e3, stats=sharding.summarize_stats(final_stats),
     )
