@@ -21,6 +21,15 @@ LIB_PATH = os.environ.get("AGF_LIB_PATH") or os.path.join(HERE, "libagrifly_b200
 _lib = None
 
 
+def offboard_cfg(quad_type=5, **edits):
+    """agf_offboard_cfg_default(quad_type) with field edits (period_us=..., delay_us=..., yaw_angle=...)."""
+    c = abi.OffboardCfg()
+    _check(lib().agf_offboard_cfg_default(int(quad_type), C.byref(c)))
+    for k, v in edits.items():
+        setattr(c, k, v)
+    return c
+
+
 class AgfError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("agrifly_b200 error %d: %s" % (code, msg))
@@ -257,6 +266,20 @@ class Batch:
         t = None if torque is None else np.ascontiguousarray(np.broadcast_to(torque, (count, 3)), dtype=np.float64)
         _check(self.L.agf_batch_set_external_wrench(self.h, None if f is None else f.ctypes.data,
                                                     None if t is None else t.ctypes.data, first, count))
+
+    def set_offboard_loop(self, cfg, targets, offsets=None):
+        """In-kernel offboard rates loop (agrifly_b200.h).  cfg: abi.OffboardCfg (offboard_cfg()) or None to switch it
+        off; targets: [(time_us, (x, y, z)), ...]; offsets: [n][3] per-vehicle shift of the targets or None."""
+        if cfg is None:
+            _check(self.L.agf_batch_set_offboard_loop(self.h, None, None, 0, None))
+            return
+        tarr = (abi.OffboardTarget * max(1, len(targets)))()
+        for i, (t, p) in enumerate(targets):
+            tarr[i].time_us = int(t)
+            tarr[i].pos[:] = [float(x) for x in p]
+        off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64).reshape(self.n, 3)
+        _check(self.L.agf_batch_set_offboard_loop(self.h, C.byref(cfg), tarr, len(targets),
+                                                  None if off is None else off.ctypes.data))
 
     def add_anchor(self, id_, pos):
         _check(self.L.agf_batch_add_uwb_anchor(self.h, id_, _f3(pos)))

@@ -81,6 +81,21 @@ class CmdEntry(C.Structure):
                 ("pad_", C.c_uint8)]
 
 
+OFFBOARD_QUEUE = 4
+
+
+class OffboardCfg(C.Structure):
+    _fields_ = [("period_us", C.c_uint32), ("delay_us", C.c_uint32),
+                ("pos_control_nat_freq", C.c_float), ("pos_control_damping", C.c_float),
+                ("att_control_time_const_xy", C.c_float), ("att_control_time_const_z", C.c_float),
+                ("min_vertical_proper_acc", C.c_double), ("max_proper_acc", C.c_double), ("min_proper_acc", C.c_double),
+                ("yaw_angle", C.c_double), ("radio_flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class OffboardTarget(C.Structure):
+    _fields_ = [("time_us", C.c_uint64), ("pos", C.c_double * 3)]
+
+
 # every symbol include/agrifly_b200.h declares: name -> (restype, argtypes)
 _P = C.POINTER
 PROTOTYPES = {
@@ -110,6 +125,8 @@ PROTOTYPES = {
     "agf_batch_set_radio_cmd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "agf_batch_set_cmd_schedule": (C.c_int, [C.c_void_p, _P(CmdEntry), C.c_size_t]),
     "agf_batch_set_cmd_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "agf_offboard_cfg_default": (C.c_int, [C.c_int, _P(OffboardCfg)]),
+    "agf_batch_set_offboard_loop": (C.c_int, [C.c_void_p, _P(OffboardCfg), _P(OffboardTarget), C.c_size_t, C.c_void_p]),
     "agf_batch_get_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_set_external_wrench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_add_uwb_anchor": (C.c_int, [C.c_void_p, C.c_uint8, _P(C.c_float)]),

@@ -312,6 +312,7 @@ struct Batch {
   virtual int read_log(uint64_t rec, double* dst, size_t first, size_t count) = 0;
   virtual int log_ptr(void** p, size_t* es) = 0;
   virtual int stats(const double* target, double* dev_out) = 0;
+  virtual int set_offboard(const agf_offboard_cfg* cfg, const agf_offboard_target* targets, size_t n_targets, const double* offsets) = 0;
 
   size_t n = 0;
   agf_batch_opts opts;
@@ -358,7 +359,7 @@ struct BatchImpl : Batch {
   typedef typename VecOf<P>::type PV;
   static constexpr int VP = VecOf<P>::lanes;
 
-  StateArrays<P> st{nullptr, nullptr, nullptr, nullptr};
+  StateArrays<P> st{nullptr, nullptr, nullptr, nullptr, nullptr};
   PV* d_pv = nullptr;
   P* d_ext_force = nullptr;
   P* d_ext_torque = nullptr;
@@ -375,6 +376,8 @@ struct BatchImpl : Batch {
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
   double* d_target = nullptr;
+  agf_offboard_target* d_off_targets = nullptr;
+  double* d_off_offsets = nullptr;
 
   StepShared<P> sh;
   PlantPV<P> pv_shared;
@@ -389,7 +392,7 @@ struct BatchImpl : Batch {
     cudaSetDevice(opts.device);
     cudaFree(st.sp); cudaFree(st.sf); cudaFree(st.su); cudaFree(st.sc);
     cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter); cudaFree(d_flags);
-    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target);
+    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(st.sq);
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
     for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -537,6 +540,7 @@ struct BatchImpl : Batch {
     L.tick0 = ticks;
     L.nticks = nticks;
     L.dt_us = dt_us;
+    ts.now_us = now_us;
     L.ts = ts;
     L.sched = d_sched;
     // entries of this launch: [begin, end) with tick in [ticks, ticks + nticks)
@@ -569,7 +573,7 @@ struct BatchImpl : Batch {
     launches++;
     // carry the clock-only stopwatches across the launch with the same function the device uses
     for (uint32_t t = 0; t < nticks; t++) {
-      const TickPlan p = timing_plan(ts, sh.tc);
+      const TickPlan p = timing_plan(ts, sh.tc, dt_us);
       timing_advance(ts, sh.tc, p, dt_us);
     }
     if (d_log) log_records = (ticks + nticks) / log_stride - log_base_tick / log_stride;
@@ -592,6 +596,23 @@ struct BatchImpl : Batch {
     ts.kf_age += dt_us;
     ts.net_age += dt_us;
     now_us += dt_us;
+    ts.now_us = now_us;
+    if (sh.tc.off_enabled) {  // the offboard main loop acts after the clock advance (main.cpp:392,471-673)
+      for (uint32_t q = 0; q < AGF_OFFQ; q++) ts.off_wait[q] = ts.off_wait[q] > dt_us ? ts.off_wait[q] - dt_us : 0;
+      ts.off_age += dt_us;
+      if (ts.off_age >= sh.tc.off_min_age_us) {
+        ts.off_age -= sh.tc.off_adj_us;
+        if (now_us >= sh.tc.off_first_target_us) {
+          if (ts.off_count >= AGF_OFFQ) return fail(AGF_EUNSUPPORTED, "offboard loop: command queue full (Run() not called between clock advances)");
+          const uint32_t slot = (ts.off_head + ts.off_count) % AGF_OFFQ;
+          cudaError_t e = launch_offboard_generate(st, n, sh.off, now_us, slot, stream);
+          if (e != cudaSuccess) return fail(AGF_ECUDA, "offboard command kernel launch", e);
+          launches++;
+          ts.off_wait[slot] = sh.tc.off_delay_us;
+          ts.off_count++;
+        }
+      }
+    }
     return AGF_OK;
   }
 
@@ -612,6 +633,57 @@ struct BatchImpl : Batch {
       rc = launch(dt_us, chunk);
       if (rc) return rc;
       nticks -= chunk;
+    }
+    return AGF_OK;
+  }
+
+  // ---- offboard loop -------------------------------------------------------------------------
+  int set_offboard(const agf_offboard_cfg* cfg, const agf_offboard_target* targets, size_t n_targets, const double* offsets) override {
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    if (!cfg) {
+      sh.tc.off_enabled = 0;
+      ts.off_age = ts.off_head = ts.off_count = 0;
+      memset(ts.off_wait, 0, sizeof(ts.off_wait));
+      return AGF_OK;
+    }
+    if (!targets || !n_targets) return fail(AGF_EINVAL, "offboard loop needs at least one target");
+    for (size_t k = 1; k < n_targets; k++)
+      if (targets[k].time_us <= targets[k - 1].time_us) return fail(AGF_EINVAL, "offboard targets must be strictly increasing in time");
+    OffboardParams off;
+    memset(&off, 0, sizeof(off));
+    TimingConsts tc = sh.tc;
+    const char* why = fill_offboard(*cfg, off, tc);
+    if (why) return fail(AGF_EINVAL, why);
+    cudaFree(d_off_targets);
+    d_off_targets = nullptr;
+    AGF_CUDA(cudaMalloc(&d_off_targets, n_targets * sizeof(agf_offboard_target)));
+    AGF_CUDA(cudaMemcpyAsync(d_off_targets, targets, n_targets * sizeof(agf_offboard_target), cudaMemcpyHostToDevice, stream));
+    cudaFree(d_off_offsets);
+    d_off_offsets = nullptr;
+    if (offsets) {
+      std::vector<double> soa(3 * n);
+      for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) soa[size_t(k) * n + i] = offsets[3 * i + k];
+      AGF_CUDA(cudaMalloc(&d_off_offsets, soa.size() * sizeof(double)));
+      AGF_CUDA(cudaMemcpyAsync(d_off_offsets, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+      AGF_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (!st.sq) {
+      AGF_CUDA(cudaMalloc(&st.sq, sizeof(float4) * AGF_OFFQ * n));
+      AGF_CUDA(cudaMemsetAsync(st.sq, 0, sizeof(float4) * AGF_OFFQ * n, stream));
+    }
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    const bool was_on = sh.tc.off_enabled != 0;
+    off.targets = d_off_targets;
+    off.n_targets = uint32_t(n_targets);
+    off.offsets = d_off_offsets;
+    sh.off = off;
+    sh.tc = tc;
+    sh.tc.off_first_target_us = targets[0].time_us;
+    if (!was_on) {  // the loop's Timer and queue are created now (Timer::Timer resets to the current clock reading)
+      ts.off_age = ts.off_head = ts.off_count = 0;
+      memset(ts.off_wait, 0, sizeof(ts.off_wait));
     }
     return AGF_OK;
   }
@@ -1000,6 +1072,28 @@ int agf_batch_set_cmd_schedule(agf_batch* b, const agf_cmd_entry* e, size_t n) {
 int agf_batch_set_cmd_slot(agf_batch* b, int slot, const uint8_t* raw) {
   if (!b) return fail(AGF_EINVAL, "null handle");
   return B(b)->set_slot(slot, raw);
+}
+int agf_offboard_cfg_default(int quad_type, agf_offboard_cfg* out) {
+  if (!out) return fail(AGF_EINVAL, "null output");
+  agf_logic_consts lc;
+  const int rc = agf_logic_consts_from_type(quad_type, &lc);
+  if (rc) return rc;
+  memset(out, 0, sizeof(*out));
+  out->period_us = 10000;  // main.cpp:175
+  out->delay_us = 30000;   // main.cpp:178
+  out->pos_control_nat_freq = lc.pos_control_nat_freq;  // main.cpp:227-229
+  out->pos_control_damping = lc.pos_control_damping;
+  out->att_control_time_const_xy = lc.att_control_time_const_xy;
+  out->att_control_time_const_z = lc.att_control_time_const_z;
+  out->min_vertical_proper_acc = 0.5 * 9.81;  // QuadcopterController.cpp:6-8
+  out->max_proper_acc = 20;
+  out->min_proper_acc = -1;
+  out->yaw_angle = 0;
+  return AGF_OK;
+}
+int agf_batch_set_offboard_loop(agf_batch* b, const agf_offboard_cfg* cfg, const agf_offboard_target* targets, size_t n_targets,
+                                const double* per_vehicle_offset) {
+  return b ? B(b)->set_offboard(cfg, targets, n_targets, per_vehicle_offset) : fail(AGF_EINVAL, "null handle");
 }
 int agf_batch_get_telemetry(agf_batch* b, uint8_t* p1, uint8_t* p2, size_t first, size_t count) {
   if (!b) return fail(AGF_EINVAL, "null handle");

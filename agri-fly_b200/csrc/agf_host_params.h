@@ -130,6 +130,29 @@ inline void fill_plant(const agf_vehicle_cfg& c, PlantPV<P>& pv) {
   pv.inv_mass = P(1.0 / c.mass);
 }
 
+// offboard loop parameters (agf_offboard_cfg -> OffboardParams + the clock-only thresholds); returns 0 or a reason
+inline const char* fill_offboard(const agf_offboard_cfg& c, OffboardParams& off, TimingConsts& tc) {
+  if (c.period_us == 0) return "offboard loop period must be > 0";
+  if ((uint64_t(c.delay_us) + c.period_us - 1) / c.period_us + 1 > uint64_t(AGF_OFFQ))
+    return "offboard loop: ceil(delay_us / period_us) + 1 commands in flight exceed AGF_OFFBOARD_QUEUE";
+  if (!(c.att_control_time_const_xy > 0) || !(c.att_control_time_const_z > 0)) return "offboard loop: attitude time constants must be > 0";
+  off.nat_freq = c.pos_control_nat_freq;
+  off.damping = c.pos_control_damping;
+  off.tc_att_xy = c.att_control_time_const_xy;
+  off.tc_att_z = c.att_control_time_const_z;
+  off.k3_att = 1.0f / c.att_control_time_const_z;
+  off.k12_att = 1.0f / c.att_control_time_const_xy;
+  off.max_proper = c.max_proper_acc;
+  off.min_vert = c.min_vertical_proper_acc;
+  off.min_proper = c.min_proper_acc;
+  off.yaw = float(c.yaw_angle);
+  off.flags = c.radio_flags & 0xFFu;
+  tc.off_enabled = 1;
+  timing_thresholds_offboard(tc, double(c.period_us) * 1e-6);
+  tc.off_delay_us = c.delay_us;
+  return nullptr;
+}
+
 // everything of StepShared that does not depend on device pointers, anchors or noise settings
 template<typename P>
 inline void build_shared(const agf_vehicle_cfg& c0, double onboard_logic_period, double uwb_comm_period, StepShared<P>& sh) {

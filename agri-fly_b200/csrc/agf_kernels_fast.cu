@@ -38,7 +38,7 @@ static cudaError_t go(const StepLaunch<FastP>& L, cudaStream_t stream) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     carveout_set = true;
   }
-  return launch_step_kernel<FastP>(kernel, L, AGF_BLOCK_THREADS, step_smem_bytes<false, kUwb>(AGF_BLOCK_THREADS), stream);
+  return launch_step_kernel<FastP>(kernel, L, AGF_BLOCK_THREADS, step_smem_bytes<false, kUwb>(AGF_BLOCK_THREADS, L.st.sq != nullptr), stream);
 }
 
 // launch_step_fast_{f32,f64}_{uwb,rates}

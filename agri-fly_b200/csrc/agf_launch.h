@@ -20,6 +20,13 @@ cudaError_t launch_step_fast_f64_rates(const StepLaunch<double>& L, bool hk, cud
 cudaError_t launch_step_fast_f32_uwb(const StepLaunch<float>& L, bool hk, cudaStream_t stream);
 cudaError_t launch_step_fast_f32_rates(const StepLaunch<float>& L, bool hk, cudaStream_t stream);
 
+// Offboard-loop command generation as a kernel of its own, for callers that step with the split Run()/advance form
+// (agf_batch_advance_clock): one command per vehicle from the stored state into queue slot `slot`.
+cudaError_t launch_offboard_generate(const StateArrays<double>& st, size_t n, const OffboardParams& off, uint64_t t_gen_us,
+                                     uint32_t slot, cudaStream_t stream);
+cudaError_t launch_offboard_generate(const StateArrays<float>& st, size_t n, const OffboardParams& off, uint64_t t_gen_us,
+                                     uint32_t slot, cudaStream_t stream);
+
 // registers per thread / local memory of each instantiation, for agf_build_info()
 void kernel_attrs_parity(char* buf, size_t n);
 void kernel_attrs_fast_f64_uwb(char* buf, size_t n);

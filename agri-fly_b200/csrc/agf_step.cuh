@@ -139,6 +139,10 @@ AGF_DEV float rsqrtf_(float x) {  // 1/sqrt(x)
 }
 AGF_DEV float rsqrt_(float x) { return ::sqrtf(x); }
 AGF_DEV double rsqrt_(double x) { return ::sqrt(x); }
+AGF_DEV float pmin_(float a, float b) { return ::fminf(a, b); }
+AGF_DEV double pmin_(double a, double b) { return ::fmin(a, b); }
+AGF_DEV float pmax_(float a, float b) { return ::fmaxf(a, b); }
+AGF_DEV double pmax_(double a, double b) { return ::fmax(a, b); }
 AGF_DEV float rabs_(float x) { return ::fabsf(x); }
 AGF_DEV double rabs_(double x) { return ::fabs(x); }
 
@@ -440,6 +444,8 @@ struct VState {
   float cov[(UWB && PARITY) ? 81 : 1];
   // radio true position latched at the last logic run (UWBRadio::_uwbTruePosition)
   P rpos[UWB ? 3 : 1];
+  // offboard-loop command queue payloads (parity variant; the fast variants keep them in the scratch)
+  float offq[PARITY ? 4 * AGF_OFFQ : 1];
 };
 
 // bit layout of VState::bits
@@ -472,7 +478,7 @@ struct Scratch {
 // threads per block of the variants that use the scratch: a compile-time stride turns every scratch address
 // into base register + immediate and lets the compiler tell the quads apart (no false LDS/STS dependencies)
 enum { SQ_STRIDE = AGF_BLOCK_THREADS };
-enum { SQ_LPF = 0, SQ_COV = 6, SQ_QUADS_NOUWB = 6, SQ_QUADS_UWB = 18 };
+enum { SQ_LPF = 0, SQ_COV = 6, SQ_QUADS_NOUWB = 6, SQ_QUADS_UWB = 18 };  // + AGF_OFFQ quads (offboard queue) behind, when the loop is on
 // Scratch accesses are volatile 128-bit shared-memory instructions: with the compile-time stride the compiler
 // could otherwise forward a tick's stores to the next tick's loads, i.e. keep the whole scratch in registers
 // across the loop -- the opposite of what the scratch is for (measured: 3x the local-memory spill traffic).
@@ -591,6 +597,17 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
   s.uwb_count = ru[SU_UWB_COUNT]; s.age_radio = ru[SU_AGE_RADIO]; s.age_uwb = ru[SU_AGE_UWB];
   s.uwbw = ru[SU_UWBW];
   if (HK) { s.age_est_reset = ru[SU_AGE_EST_RESET]; s.pc_count = ru[SU_PC_COUNT]; s.age_mon_cmd = ru[SU_AGE_MON_CMD]; s.age_mon_loop = ru[SU_AGE_MON_LOOP]; }
+  if (a.sq) {
+#pragma unroll
+    for (int q = 0; q < AGF_OFFQ; q++) {
+      const float4 v = ldcg_(&a.sq[size_t(q) * n + i]);
+      if constexpr (PARITY) {
+        s.offq[4 * q] = v.x; s.offq[4 * q + 1] = v.y; s.offq[4 * q + 2] = v.z; s.offq[4 * q + 3] = v.w;
+      } else {
+        sq_store(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + q, v);
+      }
+    }
+  }
   if constexpr (UWB) {
     float full[NC_PAD];
 #pragma unroll
@@ -685,6 +702,16 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
 #pragma unroll
     for (int q = 0; q < NU_CORE / 4; q++)
       a.su[size_t(q) * n + i] = make_uint4(ru[4 * q], ru[4 * q + 1], ru[4 * q + 2], ru[4 * q + 3]);
+  }
+  if (a.sq) {
+#pragma unroll
+    for (int q = 0; q < AGF_OFFQ; q++) {
+      if constexpr (PARITY) {
+        a.sq[size_t(q) * n + i] = make_float4(s.offq[4 * q], s.offq[4 * q + 1], s.offq[4 * q + 2], s.offq[4 * q + 3]);
+      } else {
+        a.sq[size_t(q) * n + i] = sq_load(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + q);
+      }
+    }
   }
   if constexpr (UWB) {
     float full[NC_PAD];
@@ -1067,7 +1094,7 @@ AGF_DEV V3<float> ctl_torques(const LogicParams& k, const V3<float>& des, const 
 
 // QuadcopterAttitudeController::GetDesiredAngularVelocity (:35-68)
 template<bool PARITY>
-AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q4<float>& estAtt) {
+AGF_DEV V3<float> ctl_att_core(float tc_att_xy, float tc_att_z, float k3_fast, float k12_fast, const Q4<float>& desAtt, const Q4<float>& estAtt) {
   const Q4<float> err = qmul(qinv(desAtt), estAtt);
   const V3<float> rotVec = q_to_rotvec<PARITY>(err);
   V3<float> e3b, redAx;
@@ -1100,8 +1127,13 @@ AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q
   } else {
     redAx = vdiv<PARITY>(redAx, n);
   }
-  const float k3 = PARITY ? 1.0f / k.tc_att_z : k.k3_att, k12 = PARITY ? 1.0f / k.tc_att_xy : k.k12_att;
+  const float k3 = PARITY ? 1.0f / tc_att_z : k3_fast, k12 = PARITY ? 1.0f / tc_att_xy : k12_fast;
   return (-k3) * rotVec - ((k12 - k3) * redAn) * redAx;
+}
+
+template<bool PARITY>
+AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q4<float>& estAtt) {
+  return ctl_att_core<PARITY>(k.tc_att_xy, k.tc_att_z, k.k3_att, k.k12_att, desAtt, estAtt);
 }
 
 // QuadcopterMixer::GetMotorForces + PropellerSpeedsFromThrust (:63-99)
@@ -1130,7 +1162,7 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float 
         f[i] = k.max_thrust;
       }
     } else {
-      f[i] = f[i] < k.min_thrust ? k.min_thrust : (f[i] > k.max_thrust ? k.max_thrust : f[i]);
+      f[i] = ::fminf(::fmaxf(f[i], k.min_thrust), k.max_thrust);
     }
     if constexpr (PARITY || HK) s.dforce[i] = f[i];
     float corr = 1.0f;
@@ -1169,6 +1201,77 @@ AGF_DEV Q4<float> att_from_thrust_dir(const V3<float>& dir) {
     const float k = 0.5f * ic;
     return ident ? Q4<float>(1, 0, 0, 0) : Q4<float>(c2 * ic, -dir.y * k, dir.x * k, 0.0f);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Offboard loop: Offboard::QuadcopterController::Run (Offboard/QuadcopterController.cpp:11-74),
+// then RadioMessageDecoded::CreateRatesCommand + the decode on the vehicle side (RadioTypes.hpp:73-116,158-171,
+// 210-219).  Returns the four floats the onboard logic will read: thrust [m/s^2], body rates [rad/s].
+// ---------------------------------------------------------------------------------------------
+AGF_DEV float radio_quantise(float v, float limit) {
+  int out;
+  if ((v > -limit) && (v < limit)) {
+    out = int(v * 32768 / limit + 0.5f) + 32768;
+  } else if (v > -limit) {
+    out = 65536 - 1;
+  } else {
+    out = 0;  // min value, and NaN
+  }
+  out &= 0xFFFF;  // two bytes on the wire
+  return limit * (out - 32768) / float(32768);
+}
+template<bool PARITY, typename P>
+AGF_DEV float4 offboard_command(const OffboardParams& c, const V3<P>& curPos, const V3<P>& curVel, const Q4<P>& curAtt,
+                                const double des[3]) {
+  const V3<float> e3(0, 0, 1);
+  const V3<float> estPos = V3<float>(float(curPos.x), float(curPos.y), float(curPos.z));
+  const V3<float> estVel = V3<float>(float(curVel.x), float(curVel.y), float(curVel.z));
+  const V3<float> desPos = V3<float>(float(des[0]), float(des[1]), float(des[2]));
+  const Q4<float> attf = Q4<float>(float(curAtt.w), float(curAtt.x), float(curAtt.y), float(curAtt.z));
+  // GetDesAcceleration (QuadcopterPositionController.hpp:22-27), desVel = desAcc = 0
+  const V3<float> zero(0, 0, 0);
+  const V3<float> dv = zero - estVel;
+  const V3<float> cmdAcc = (((desPos - estPos) * c.nat_freq) * c.nat_freq + ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * c.nat_freq) * c.damping)) + zero;
+  V3<float> cmdProperAcc = cmdAcc + V3<float>(0, 0, 9.81f);
+  {
+    const float n0 = norm(cmdProperAcc);
+    if (double(n0) > c.max_proper) cmdProperAcc = cmdProperAcc * float(c.max_proper / double(norm(cmdProperAcc)));
+  }
+  if (double(cmdProperAcc.z) < c.min_vert) cmdProperAcc.z = float(c.min_vert);
+  const float normCmdProperAcc = norm(cmdProperAcc);
+  const V3<float> cmdThrustDir = vdiv<PARITY>(cmdProperAcc, normCmdProperAcc);
+  double outCmdThrust = double(normCmdProperAcc * dot(qrot(attf, V3<float>(0, 0, 1)), cmdThrustDir));
+  if (outCmdThrust < c.min_proper) outCmdThrust = c.min_proper;
+  const float cosAngle = dot(cmdThrustDir, e3);
+  float angle;
+  if (cosAngle >= (1 - 1e-12f)) {
+    angle = 0;
+  } else if (cosAngle <= -(1 - 1e-12f)) {
+    angle = 3.14159274f;
+  } else {
+    angle = Mf<PARITY>::acos(cosAngle);
+  }
+  const V3<float> rotAx = cross(e3, cmdThrustDir);
+  const float n = norm(rotAx);
+  Q4<float> cmdAtt(1, 0, 0, 0);
+  if (!(n < 1e-6f)) {
+    Q4<float> d;
+    if (q_from_rotvec<PARITY>(rotAx * fdiv<PARITY>(angle, n), d)) cmdAtt = d;
+  }
+  Q4<float> yawq(1, 0, 0, 0);
+  {
+    Q4<float> d;
+    if (q_from_rotvec<PARITY>(V3<float>(0, 0, c.yaw), d)) yawq = d;
+  }
+  const Q4<float> cmdAttYawed = qmul(cmdAtt, yawq);
+  const V3<float> w = ctl_att_core<PARITY>(c.tc_att_xy, c.tc_att_z, c.k3_att, c.k12_att, cmdAttYawed, attf);
+  return make_float4(radio_quantise(float(outCmdThrust), 35.0f), radio_quantise(w.x, 35.0f), radio_quantise(w.y, 35.0f),
+                     radio_quantise(w.z, 35.0f));
+}
+template<typename P>
+static AGF_COLD float4 offboard_command_cold(const OffboardParams* c, V3<P> curPos, V3<P> curVel, Q4<P> curAtt, double dx, double dy, double dz) {
+  const double des[3] = {dx, dy, dz};
+  return offboard_command<false, P>(*c, curPos, curVel, curAtt, des);
 }
 
 // RunControllerExternalAccelerationControl up to the desired body rates (QuadcopterLogic.cpp:459-517):
@@ -1411,7 +1514,18 @@ template<typename P> AGF_DEV V3<P> inertia_inv_mul(const PlantPVDiag<P>& pv, con
 template<typename P, bool PARITY, bool UWB, bool HK, typename PVT>
 AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PVT& pv, Timing& ts,
                   uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
-  const TickPlan plan = timing_plan(ts, p.tc);
+  const TickPlan plan = timing_plan(ts, p.tc, dt_us);
+  if (plan.off_deliver) {  // CommunicationsDelay::GetMessage -> SetCommandRadioMsg (main.cpp:737-739)
+    float4 c;
+    if constexpr (PARITY) {
+      c = make_float4(s.offq[4 * plan.off_deliver_slot], s.offq[4 * plan.off_deliver_slot + 1], s.offq[4 * plan.off_deliver_slot + 2],
+                      s.offq[4 * plan.off_deliver_slot + 3]);
+    } else {
+      c = sq_load(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_deliver_slot));
+    }
+    const float cf[4] = {c.x, c.y, c.z, c.w};
+    radio_deliver(s, p.logic, AGF_RADIO_EXTERNAL_RATES_CMD, p.off.flags, cf);
+  }
   if (plan.run_plant) {
     const P dt = P(double(plan.plant_dt_us) * 1e-6);
     const P inv_dt = PARITY ? P(0) : P(1) / dt;
@@ -1433,7 +1547,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
           sp = p.motor_min;
         }
       } else {
-        sp = sp > p.motor_max ? p.motor_max : (sp < p.motor_min ? p.motor_min : sp);
+        sp = pmin_(pmax_(sp, p.motor_min), p.motor_max);
       }
       s.ms[m] = sp;
       const P fz = (pv.kF * sp) * rabs_(sp);
@@ -1553,6 +1667,28 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       s.bits |= B_RADIO_MEAS_NEW;
     }
   }
+  if (plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance; estimate = truth
+    const uint64_t t_gen = ts.now_us + dt_us;
+    uint32_t ti = 0;
+    for (uint32_t j = 1; j < p.off.n_targets; j++)
+      if (p.off.targets[j].time_us <= t_gen) ti = j;
+    double des[3] = {p.off.targets[ti].pos[0], p.off.targets[ti].pos[1], p.off.targets[ti].pos[2]};
+    if (p.off.offsets) {
+      des[0] = des[0] + p.off.offsets[i];
+      des[1] = des[1] + p.off.offsets[n + i];
+      des[2] = des[2] + p.off.offsets[2 * n + i];
+    }
+    const V3<P> cp(s.pos[0], s.pos[1], s.pos[2]), cv(s.vel[0], s.vel[1], s.vel[2]);
+    const Q4<P> ca(s.att[0], s.att[1], s.att[2], s.att[3]);
+    if constexpr (PARITY) {
+      const float4 c = offboard_command<true, P>(p.off, cp, cv, ca, des);
+      s.offq[4 * plan.off_gen_slot] = c.x; s.offq[4 * plan.off_gen_slot + 1] = c.y;
+      s.offq[4 * plan.off_gen_slot + 2] = c.z; s.offq[4 * plan.off_gen_slot + 3] = c.w;
+    } else {
+      const float4 c = offboard_command_cold<P>(&p.off, cp, cv, ca, des[0], des[1], des[2]);
+      sq_store(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_gen_slot), c);
+    }
+  }
   timing_advance(ts, p.tc, plan, dt_us);
   s.age_radio = sat_add(s.age_radio, dt_us);
   s.age_uwb = sat_add(s.age_uwb, dt_us);
@@ -1626,8 +1762,8 @@ constexpr int step_min_blocks() {
   return PARITY ? 1 : (sizeof(P) == 4 ? (UWB ? AGF_MINB_F32_UWB : AGF_MINB_F32_RATES) : (UWB ? AGF_MINB_F64_UWB : AGF_MINB_F64_RATES));
 }
 template<bool PARITY, bool UWB>
-constexpr size_t step_smem_bytes(int block) {
-  return PARITY ? 0 : size_t(block) * (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) * sizeof(float4);
+constexpr size_t step_smem_bytes(int block, bool offboard) {
+  return PARITY ? 0 : size_t(block) * ((UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + (offboard ? AGF_OFFQ : 0)) * sizeof(float4);
 }
 
 // the ticks [t0, t1) of vehicle i; pv is the constant-bank struct or a register copy
@@ -1638,7 +1774,7 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
   // clock-only stopwatches at tick t0: the same integer recurrence for every vehicle
   Timing ts = L.ts;
   for (uint32_t t = 0; t < t0; t++) {
-    const TickPlan pl = timing_plan(ts, L.sh.tc);
+    const TickPlan pl = timing_plan(ts, L.sh.tc, L.dt_us);
     timing_advance(ts, L.sh.tc, pl, L.dt_us);
   }
   // next scheduled radio delivery, as a tick offset into this launch (0xFFFFFFFF: none left)

@@ -45,6 +45,7 @@ enum {  // uint32 words
   NU_PAD = 12
 };
 enum { NC_PAD = 84 };
+enum { AGF_OFFQ = AGF_OFFBOARD_QUEUE };  // offboard-loop commands in flight per vehicle
 
 template<typename P> struct VecOf;
 #if defined(__CUDACC__)
@@ -67,6 +68,7 @@ struct StateArrays {
   float4* sf;
   uint4* su;
   float4* sc;  // null unless the batch ranges against UWB anchors
+  float4* sq;  // offboard-loop command queue [AGF_OFFQ][N], null unless the loop is on
 };
 #endif
 
@@ -103,6 +105,12 @@ struct TimingConsts {
   uint32_t logic_min_age_us;  // smallest reading with  double(us)*1e-6 >  logic_period  (Quadcopter_T.cpp:159)
   uint32_t net_min_age_us;    // smallest reading with !(double(us)*1e-6 <  comm_period)  (UWBNetwork.cpp:28)
   uint32_t plant_min_age_us;  // smallest reading with !(double(us)*1e-6 <  1e-6)         (Quadcopter_T.cpp:88)
+  // offboard loop (Simulator/Rappids_Simulator/main.cpp:471-476, CommunicationsDelay.hpp:18-39): clock-only as well
+  int off_enabled;
+  uint32_t off_min_age_us;    // smallest reading with  double(us)*1e-6 >  period               (main.cpp:471)
+  uint32_t off_adj_us;        // uint64_t(period * 1e6) of Timer::AdjustTimeBySeconds            (main.cpp:476)
+  uint32_t off_delay_us;      // CommunicationsDelay::_delayTime_us
+  uint64_t off_first_target_us;  // no command is generated before the first target applies
 };
 
 inline uint32_t first_true_us(double guess_us, bool (*pred)(double, double), double arg) {
@@ -116,6 +124,10 @@ inline void timing_thresholds(TimingConsts& tc) {
   tc.net_min_age_us = tc.net_enabled ? first_true_us(tc.comm_period * 1e6, [](double t, double p) { return !(t < p); }, tc.comm_period) : 0xFFFFFFFFu;
   tc.plant_min_age_us = first_true_us(1.0, [](double t, double p) { return !(t < p); }, 1e-6);
 }
+inline void timing_thresholds_offboard(TimingConsts& tc, double period) {
+  tc.off_min_age_us = first_true_us(period * 1e6, [](double t, double p) { return t > p; }, period);
+  tc.off_adj_us = uint32_t(uint64_t((-period) * double(-1e6)));  // Timer.hpp:31-33
+}
 
 // Stopwatch readings that are identical for every vehicle of a batch (they depend on the clock
 // only): Quadcopter_T::_integrationTimer, ::_timerOnboardLogic, KalmanFilter6DOF::_estimateTimer,
@@ -124,14 +136,21 @@ inline void timing_thresholds(TimingConsts& tc) {
 struct Timing {
   uint32_t integ_age, logic_age, kf_age, net_age;
   uint32_t net_active, has_target;
+  // offboard loop: main-loop stopwatch and the delay queue's control state (payloads are per vehicle)
+  uint32_t off_age, off_head, off_count;
+  uint32_t off_wait[AGF_OFFQ];  // microseconds until each queued command is due (0: deliverable)
+  uint64_t now_us;              // simulation clock (ManualTimer::GetMicroSeconds)
 };
 
 struct TickPlan {
   uint32_t plant_dt_us, kf_dt_us;
   bool run_plant, run_logic, run_net, net_start, net_complete, net_reset, has_target;
+  bool off_deliver, off_generate;
+  uint32_t off_deliver_slot, off_gen_slot;
 };
 
-AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc) {
+// dt_us: the clock advance that follows this tick's Run() (the offboard loop acts after the advance)
+AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc, uint32_t dt_us) {
   TickPlan p;
   p.plant_dt_us = ts.integ_age;
   p.kf_dt_us = ts.kf_age;
@@ -151,6 +170,12 @@ AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc) {
       p.net_complete = true;
     }
   }
+  // offboard loop.  Delivery (main.cpp:737-739 of the previous iteration): the oldest queued command, once due.
+  p.off_deliver = tc.off_enabled && ts.off_count > 0 && ts.off_wait[ts.off_head % AGF_OFFQ] == 0;
+  p.off_deliver_slot = ts.off_head % AGF_OFFQ;
+  // Generation (main.cpp:471): after Run() and the clock advance, when the stopwatch exceeds the period
+  p.off_generate = tc.off_enabled && (ts.off_age + dt_us >= tc.off_min_age_us) && (ts.now_us + dt_us >= tc.off_first_target_us);
+  p.off_gen_slot = (ts.off_head + ts.off_count) % AGF_OFFQ;  // the delivered one (if any) frees the head, not the tail
   return p;
 }
 
@@ -168,6 +193,22 @@ AGF_HDI void timing_advance(Timing& ts, const TimingConsts& tc, const TickPlan& 
   ts.logic_age += dt_us;
   ts.kf_age += dt_us;
   ts.net_age += dt_us;
+  ts.now_us += dt_us;
+  if (tc.off_enabled) {
+    if (p.off_deliver) {
+      ts.off_head = (ts.off_head + 1) % AGF_OFFQ;
+      ts.off_count--;
+    }
+    for (uint32_t q = 0; q < AGF_OFFQ; q++) ts.off_wait[q] = ts.off_wait[q] > dt_us ? ts.off_wait[q] - dt_us : 0;
+    ts.off_age += dt_us;
+    if (ts.off_age >= tc.off_min_age_us) {  // stopwatch restarts whether or not a target applies yet (main.cpp:476)
+      ts.off_age -= tc.off_adj_us;
+      if (p.off_generate) {
+        ts.off_wait[p.off_gen_slot] = tc.off_delay_us;
+        ts.off_count++;
+      }
+    }
+  }
 }
 
 struct AnchorDev {
@@ -175,9 +216,22 @@ struct AnchorDev {
   uint32_t id;
 };
 
+// Offboard::QuadcopterController + radio link of the in-kernel offboard loop (agrifly_b200.h "offboard rates loop")
+struct OffboardParams {
+  float nat_freq, damping, tc_att_xy, tc_att_z;
+  float k3_att, k12_att;   // reciprocals, fast variants
+  double max_proper, min_vert, min_proper;
+  float yaw;
+  uint32_t flags;
+  uint32_t n_targets;
+  const agf_offboard_target* targets;  // device, sorted by time
+  const double* offsets;               // device [3][N] or null
+};
+
 template<typename P>
 struct StepShared {
   LogicParams logic;
+  OffboardParams off;
   TimingConsts tc;
   P motor_min, motor_max, motor_J;
   P motor_pos[4][3];

@@ -140,3 +140,14 @@ def monte_carlo_initial_states(n, seed=1234, yaw_max=np.pi):
     out[:, 1] = py
     out[:, 6:10] = q
     return out
+
+
+def offboard_scenario(nticks=4000):
+    """the closed loop Rappids_Simulator flies (main.cpp:471-739, CTRL_OFFBOARD_RATES) with a
+    truth-fed estimate: offboard position controller at 100 Hz -> 16-bit rates commands -> 30 ms uplink delay ->
+    onboard rate controller.  Take-off to a hover set-point, then a step to a second set-point.  No UWB, the
+    onboard estimator runs its complementary attitude filter only."""
+    targets = [(0, (0.0, 0.0, 2.0)), (3000000, (1.0, -0.5, 2.5)), (6000000, (1.0, -0.5, 1.0))]
+    return dict(name="offboard", quad_type=5, vehicle_id=1, motor_time_const=0.015, motor_inertia=0.0,
+                pos=(0.0, 0.0, 0.0), att=(1.0, 0.0, 0.0, 0.0), anchors=[], uwb_comm_period=0.0, sched=[],
+                targets=targets, nticks=nticks)

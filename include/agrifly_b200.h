@@ -282,6 +282,41 @@ int agf_batch_set_cmd_schedule(agf_batch* b, const agf_cmd_entry* entries, size_
 #define AGF_MAX_CMD_SLOTS 4
 int agf_batch_set_cmd_slot(agf_batch* b, int slot, const uint8_t* raw /* [n_vehicles][23] */);
 
+/* ---- offboard rates loop inside the kernel ---------------------------------
+ * The control loop Rappids_Simulator wraps around Run() (Simulator/Rappids_Simulator/main.cpp:471-739,
+ * controllerType == CTRL_OFFBOARD_RATES), executed per vehicle on the device so that populations fly the
+ * reference's own demo without a host round trip per command:
+ *   every `period_us` of simulation time (stopwatch with strict '>', main.cpp:471-476), right after Run() and
+ *   the clock advance: state estimate -> Offboard::QuadcopterController::Run (QuadcopterController.cpp:11-74)
+ *   -> RadioMessageDecoded::CreateRatesCommand (16-bit quantisation, RadioTypes.hpp:73-100,158-171) ->
+ *   CommunicationsDelay queue (`delay_us`, CommunicationsDelay.hpp:18-39) -> SetCommandRadioMsg before the
+ *   first Run() at or after the due time (main.cpp:737-739).
+ * The state estimate is the true state at command generation (a MocapStateEstimator-equivalent predictor is a
+ * later row); the desired position is piecewise constant in time (`targets`, sorted by time_us; the entry
+ * with the largest time_us <= the simulation clock at command generation applies; before the first entry no
+ * command is generated), optionally shifted per vehicle by `per_vehicle_offset`. */
+#define AGF_OFFBOARD_QUEUE 4 /* commands in flight: ceil(delay_us / period_us) + 1 must not exceed this */
+typedef struct agf_offboard_cfg {
+  uint32_t period_us; /* periodOffboardMainLoop, main.cpp:175: 10000 */
+  uint32_t delay_us;  /* timeDelayOffboardControlLoopTrue, main.cpp:178,282-283: 30000 */
+  /* QuadcopterController::SetParameters (main.cpp:227-229) from the airframe table */
+  float pos_control_nat_freq, pos_control_damping, att_control_time_const_xy, att_control_time_const_z;
+  /* QuadcopterController::QuadcopterController (QuadcopterController.cpp:5-9): 0.5*9.81, 20, -1 */
+  double min_vertical_proper_acc, max_proper_acc, min_proper_acc;
+  double yaw_angle; /* desiredYawAngle [rad] (main.cpp:244,627) */
+  uint32_t radio_flags;
+  uint32_t reserved;
+} agf_offboard_cfg;
+typedef struct agf_offboard_target {
+  uint64_t time_us;
+  double pos[3];
+} agf_offboard_target;
+/* period/delay of Rappids_Simulator, controller parameters of the airframe `quad_type` */
+int agf_offboard_cfg_default(int quad_type, agf_offboard_cfg* out);
+/* cfg == NULL switches the loop off.  per_vehicle_offset: [n_vehicles][3] doubles or NULL. */
+int agf_batch_set_offboard_loop(agf_batch* b, const agf_offboard_cfg* cfg, const agf_offboard_target* targets,
+                                size_t n_targets, const double* per_vehicle_offset);
+
 /* SimulationObject6DOF::GetTelemetryDataPackets (SimulationObject6DOF.hpp:67;
  * QuadcopterLogic.cpp:621-679), including its side effects (packet counter++, warnings cleared).
  * p1, p2: [count][30]. */

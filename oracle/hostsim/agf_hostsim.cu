@@ -31,7 +31,7 @@ struct orc_vehicle {
   Timing ts;
   bool uwb;
   std::vector<double> hp, ext_f, ext_t;
-  std::vector<float> hf, hc;
+  std::vector<float> hf, hc, hq;
   std::vector<uint32_t> hu;
   uint64_t tick, now_us;
   StateArrays<double> arrays() {
@@ -40,6 +40,7 @@ struct orc_vehicle {
     a.sf = (float4*)hf.data();
     a.su = (uint4*)hu.data();
     a.sc = uwb ? (float4*)hc.data() : nullptr;
+    a.sq = hq.empty() ? nullptr : (float4*)hq.data();
     return a;
   }
 };
@@ -146,6 +147,22 @@ void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entr
              const uint8_t* slot_raw, double* traj) {
   if (v->uwb) run_impl<true>(v, dt_us, nticks, sched, nsched, slot_raw, traj);
   else run_impl<false>(v, dt_us, nticks, sched, nsched, slot_raw, traj);
+}
+
+// the device step's own offboard loop (tick(): plan.off_deliver / plan.off_generate), compiled for the host
+void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                      const agf_offboard_target* targets, uint32_t n_targets, const double* offset, double* traj) {
+  if (v->hq.empty()) {
+    v->hq.assign(4 * AGF_OFFQ, 0.0f);
+    const char* why = fill_offboard(*cfg, v->sh.off, v->sh.tc);
+    if (why) { fprintf(stderr, "hostsim: %s\n", why); abort(); }
+  }
+  v->sh.off.targets = targets;
+  v->sh.off.n_targets = n_targets;
+  v->sh.off.offsets = offset;  // [3][1]
+  v->sh.tc.off_first_target_us = n_targets ? targets[0].time_us : ~0ull;
+  v->ts.now_us = v->now_us;
+  orc_run(v, dt_us, nticks, nullptr, 0, nullptr, traj);
 }
 
 void orc_get_full(orc_vehicle* v, orc_full_state* o) {

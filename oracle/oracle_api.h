@@ -77,6 +77,13 @@ void orc_set_radio(orc_vehicle* v, const uint8_t raw[AGF_RADIO_PACKET_SIZE]);
 void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entry* sched,
              uint32_t nsched, const uint8_t* slot_raw /* [AGF_MAX_CMD_SLOTS][23] or NULL */,
              double* traj /* [nticks][ORC_NTRAJ] or NULL */);
+/* The same ticks with the offboard rates loop of Simulator/Rappids_Simulator/main.cpp:471-739 around Run()
+ * (semantics: include/agrifly_b200.h "offboard rates loop"): truth-fed QuadcopterController::Run ->
+ * CreateRatesCommand -> CommunicationsDelay -> SetCommandRadioMsg.  The loop's stopwatch and queue live in the
+ * vehicle object, so consecutive calls continue seamlessly.  offset: this vehicle's [3] shift or NULL. */
+void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                      const agf_offboard_target* targets, uint32_t n_targets, const double* offset,
+                      double* traj /* [nticks][ORC_NTRAJ] or NULL */);
 void orc_get_full(orc_vehicle* v, orc_full_state* out);
 void orc_get_telemetry(orc_vehicle* v, uint8_t p1[AGF_TELEMETRY_PACKET_SIZE],
                        uint8_t p2[AGF_TELEMETRY_PACKET_SIZE]);

@@ -109,6 +109,9 @@ class Oracle:
         L.orc_add_anchor.restype = C.c_int
         L.orc_set_radio.argtypes = [vp, C.c_char_p]
         L.orc_run.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.CmdEntry), C.c_uint32, C.c_void_p, C.c_void_p]
+        if True:
+            L.orc_run_offboard.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardTarget), C.c_uint32,
+                                           C.c_void_p, C.c_void_p]
         L.orc_get_full.argtypes = [vp, P(FullState)]
         L.orc_time_us.restype = C.c_uint64
         L.orc_time_us.argtypes = [vp]
@@ -196,6 +199,18 @@ class OracleVehicle:
             sr = np.ascontiguousarray(slot_raw, dtype=np.uint8)
         self.L.orc_run(self.h, dt_us, nticks, sch, len(sched), None if sr is None else sr.ctypes.data,
                        None if traj is None else traj.ctypes.data)
+        return traj
+
+    def run_offboard(self, nticks, cfg, targets, offset=None, dt_us=2000, record=True):
+        """targets: list of (time_us, (x, y, z)); cfg: abi.OffboardCfg"""
+        tarr = (abi.OffboardTarget * max(1, len(targets)))()
+        for i, (t, p) in enumerate(targets):
+            tarr[i].time_us = int(t)
+            tarr[i].pos[:] = [float(x) for x in p]
+        traj = np.zeros((nticks, NTRAJ)) if record else None
+        off = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64)
+        self.L.orc_run_offboard(self.h, dt_us, nticks, C.byref(cfg), tarr, len(targets),
+                                None if off is None else off.ctypes.data, None if traj is None else traj.ctypes.data)
         return traj
 
     def full(self):

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <limits>
 #include <thread>
+#include <deque>
 #include <vector>
 
 #include "../oracle_api.h"
@@ -1277,12 +1278,84 @@ struct Quadcopter {
 // =============================================================================================
 // C interface (oracle/oracle_api.h)
 // =============================================================================================
+namespace port {
+// RadioMessageDecoded::encodeToRadioByte (RadioTypes.hpp:73-100): 16-bit field as the two bytes it is sent in
+inline uint16_t radio_encode_field(float valIn, float limit) {
+  int out;
+  if ((valIn > -limit) && (valIn < limit)) {
+    out = int(valIn * 32768 / limit + 0.5f) + 32768;
+  } else if (valIn > -limit) {
+    out = 65536 - 1;
+  } else {
+    out = 0;  // min value, and NaN
+  }
+  return uint16_t(((out >> 8) % 256) << 8 | (out % 256));
+}
+// Offboard::QuadcopterController::Run (QuadcopterController.cpp:11-74) followed by CreateRatesCommand +
+// RadioMessageDecoded(raw) (RadioTypes.hpp:158-171,210-219): returns the four floats the vehicle will decode
+struct OffboardCmd {
+  float f[4];
+};
+inline OffboardCmd offboard_rates_command(const agf_offboard_cfg& c, const V3d& curPos, const V3d& curVel, const Rotd& curAtt,
+                                          const V3d& desPos) {
+  PositionController posCtrl;
+  posCtrl.natFreq = c.pos_control_nat_freq;
+  posCtrl.damping = c.pos_control_damping;
+  AttitudeController attCtr;
+  attCtr.tc_xy = c.att_control_time_const_xy;
+  attCtr.tc_z = c.att_control_time_const_z;
+  const V3f e3(0, 0, 1);
+  const V3f cmdAcc = posCtrl.des_acceleration(V3f(curPos), V3f(curVel), V3f(desPos));
+  V3f cmdProperAcc = cmdAcc + V3f(0, 0, 9.81f);
+  if (cmdProperAcc.norm() > c.max_proper_acc) {  // float norm compared (and divided) in double, product back in float
+    cmdProperAcc = cmdProperAcc * float(c.max_proper_acc / cmdProperAcc.norm());
+  }
+  if (cmdProperAcc.z < c.min_vertical_proper_acc) cmdProperAcc.z = float(c.min_vertical_proper_acc);
+  const float normCmdProperAcc = cmdProperAcc.norm();
+  const V3f cmdThrustDir = cmdProperAcc / normCmdProperAcc;
+  const Rotf attf(float(curAtt.v[0]), float(curAtt.v[1]), float(curAtt.v[2]), float(curAtt.v[3]));
+  double outCmdThrust = normCmdProperAcc * attf.rotate(V3f(0, 0, 1)).dot(cmdThrustDir);
+  if (outCmdThrust < c.min_proper_acc) outCmdThrust = c.min_proper_acc;
+  Rotf cmdAtt;
+  const float cosAngle = cmdThrustDir.dot(e3);
+  float angle;
+  if (cosAngle >= (1 - 1e-12f)) {
+    angle = 0;
+  } else if (cosAngle <= -(1 - 1e-12f)) {
+    angle = float(M_PI);
+  } else {
+    angle = m_acos(cosAngle);
+  }
+  V3f rotAx = e3.cross(cmdThrustDir);
+  const float n = rotAx.norm();
+  if (n < 1e-6f) {
+    cmdAtt = Rotf::identity();
+  } else {
+    cmdAtt = Rotf::from_rotation_vector(rotAx * (angle / n));
+  }
+  Rotf cmdAttYawed = cmdAtt * Rotf::from_rotation_vector(V3f(0, 0, float(c.yaw_angle)));
+  const V3d outCmdAngVel(attCtr.desired_angular_velocity(cmdAttYawed, attf));
+  const float tx[4] = {float(outCmdThrust), float(outCmdAngVel.x), float(outCmdAngVel.y), float(outCmdAngVel.z)};
+  OffboardCmd o;
+  for (int i = 0; i < 4; i++) {
+    const float limit = 35;  // MAX_VAL_CMD_THRUST == MAX_VAL_CMD_ANG_RATES == 35
+    const int q = radio_encode_field(tx[i], limit);
+    o.f[i] = limit * (q - 32768) / float(32768);
+  }
+  return o;
+}
+}  // namespace port
+
 struct orc_vehicle {
   port::Clock clock;
   port::Quadcopter* quad;
   port::Network* net;
   std::vector<port::Radio*> anchors;
   uint64_t tick;
+  // offboard loop (orc_run_offboard)
+  port::Timer* offTimer = nullptr;
+  struct Queued { uint64_t due; port::OffboardCmd cmd; };
+  std::deque<Queued> offQueue;
 };
 
 static void record(orc_vehicle* v, double* r) {
@@ -1330,6 +1403,7 @@ void orc_destroy(orc_vehicle* v) {
   for (auto* a : v->anchors) delete a;
   delete v->net;
   delete v->quad;
+  delete v->offTimer;
   delete v;
 }
 
@@ -1377,6 +1451,41 @@ void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entr
     if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
     v->clock.now_us += dt_us;
     v->tick++;
+  }
+}
+
+void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                      const agf_offboard_target* targets, uint32_t n_targets, const double* offset, double* traj) {
+  if (!v->offTimer) v->offTimer = new port::Timer(&v->clock);
+  const double period = double(cfg->period_us) * 1e-6;
+  for (uint32_t k = 0; k < nticks; k++) {
+    if (!v->offQueue.empty() && v->clock.now_us >= v->offQueue.front().due) {  // CommunicationsDelay.hpp:27-35, main.cpp:737-739
+      port::RadioMsg m;
+      m.type = AGF_RADIO_EXTERNAL_RATES_CMD;
+      m.flags = uint8_t(cfg->radio_flags);
+      for (int i = 0; i < 4; i++) m.f[i] = v->offQueue.front().cmd.f[i];
+      for (int i = 4; i < 10; i++) m.f[i] = 35.0f * (0 - 32768) / float(32768);  // zero-filled packet bytes decode to -limit; never read
+      v->quad->logic.set_radio(m);
+      v->offQueue.pop_front();
+    }
+    v->quad->run();
+    if (v->net) v->net->run();
+    if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
+    v->clock.now_us += dt_us;
+    v->tick++;
+    if (v->offTimer->seconds_d() > period) {  // main.cpp:471
+      v->offTimer->adjust_by_seconds(-period);  // main.cpp:476
+      int ti = -1;
+      for (uint32_t j = 0; j < n_targets; j++)
+        if (targets[j].time_us <= v->clock.now_us) ti = int(j);
+      if (ti < 0) continue;
+      port::V3d des(targets[ti].pos[0], targets[ti].pos[1], targets[ti].pos[2]);
+      if (offset) des = des + port::V3d(offset[0], offset[1], offset[2]);
+      orc_vehicle::Queued q;
+      q.due = v->clock.now_us + cfg->delay_us;
+      q.cmd = port::offboard_rates_command(*cfg, v->quad->pos, v->quad->vel, v->quad->att, des);
+      v->offQueue.push_back(q);
+    }
   }
 }
 

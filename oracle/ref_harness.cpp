@@ -36,6 +36,8 @@
 #include "Common/Time/ManualTimer.hpp"
 #include "Components/Simulation/Quadcopter_T.hpp"
 #include "Components/Simulation/UWBNetwork.hpp"
+#include "Components/Simulation/CommunicationsDelay.hpp"
+#include "Components/Offboard/QuadcopterController.hpp"
 #undef private
 #undef protected
 
@@ -51,6 +53,9 @@ struct orc_vehicle {
   std::unique_ptr<Simulation::UWBNetwork> net;
   std::vector<std::shared_ptr<Simulation::UWBRadio>> anchors;
   uint64_t tick;
+  // offboard loop (orc_run_offboard): created on first use
+  std::unique_ptr<Timer> offTimer;
+  std::unique_ptr<Simulation::CommunicationsDelay<RadioTypes::RadioMessageDecoded::RawMessage>> offChannel;
 };
 
 template<typename LPF>
@@ -164,6 +169,53 @@ void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entr
     if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
     v->timer.AdvanceMicroSeconds(dt_us);
     v->tick++;
+  }
+}
+
+// Loop body of Simulator/Rappids_Simulator/main.cpp:391-392,471-476,625-627,666-673,737-739 with the reference's own
+// Timer, QuadcopterController, RadioTypes and CommunicationsDelay; estimate = truth.
+void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                      const agf_offboard_target* targets, uint32_t n_targets, const double* offset, double* traj) {
+  if (!v->offTimer) {
+    v->offTimer.reset(new Timer(&v->timer));
+    v->offChannel.reset(new Simulation::CommunicationsDelay<RadioTypes::RadioMessageDecoded::RawMessage>(
+        &v->timer, double(cfg->delay_us) * 1e-6));
+    v->offChannel->_delayTime_us = cfg->delay_us;  // exact integer microseconds
+  }
+  Offboard::QuadcopterController ctrl;
+  ctrl.SetParameters(cfg->pos_control_nat_freq, cfg->pos_control_damping, cfg->att_control_time_const_xy,
+                     cfg->att_control_time_const_z);
+  ctrl._minVerticalProperAcceleration = cfg->min_vertical_proper_acc;
+  ctrl._maxProperAcc = cfg->max_proper_acc;
+  ctrl._minProperAcc = cfg->min_proper_acc;
+  const double period = double(cfg->period_us) * 1e-6;
+  for (uint32_t k = 0; k < nticks; k++) {
+    // main.cpp:737-739 of the previous iteration == before this Run()
+    if (v->offChannel->HaveNewMessage()) v->quad->SetCommandRadioMsg(v->offChannel->GetMessage());
+    v->quad->Run();
+    if (v->net) v->net->Run();
+    if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
+    v->timer.AdvanceMicroSeconds(dt_us);
+    v->tick++;
+    if (v->offTimer->GetSeconds<double>() > period) {  // main.cpp:471
+      v->offTimer->AdjustTimeBySeconds(-period);       // main.cpp:476
+      const uint64_t now = v->timer.GetMicroSeconds();
+      int ti = -1;
+      for (uint32_t j = 0; j < n_targets; j++)
+        if (targets[j].time_us <= now) ti = int(j);
+      if (ti < 0) continue;
+      Vec3d des(targets[ti].pos[0], targets[ti].pos[1], targets[ti].pos[2]);
+      if (offset) des = des + Vec3d(offset[0], offset[1], offset[2]);
+      Vec3d cmdAngVel;
+      double cmdThrust;
+      ctrl.Run(v->quad->GetPosition(), v->quad->GetVelocity(), v->quad->GetAttitude(), des, Vec3d(0, 0, 0),
+               Vec3d(0, 0, 0), cfg->yaw_angle, cmdAngVel, cmdThrust);  // main.cpp:625-627
+      RadioTypes::RadioMessageDecoded::RawMessage rawMsg;
+      memset(rawMsg.raw, 0, sizeof(rawMsg.raw));
+      RadioTypes::RadioMessageDecoded::CreateRatesCommand(uint8_t(cfg->radio_flags), float(cmdThrust), Vec3f(cmdAngVel),
+                                                          rawMsg.raw);  // main.cpp:666-669
+      v->offChannel->AddMessage(rawMsg);                                 // main.cpp:673
+    }
   }
 }
 

@@ -50,3 +50,25 @@ def rel_err(a, b, floor=1.0):
 def bit_equal(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def run_oracle_offboard(O, agf, sc, nticks=None, chunks=None, offset=None, cfg=None, ocfg=None, **kw):
+    """Offboard-loop scenario on an oracle; `chunks` splits the run into several calls."""
+    v = O.vehicle(cfg if cfg is not None else cfg_for(agf, sc), uwb_comm_period=sc["uwb_comm_period"], **kw)
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    oc = ocfg if ocfg is not None else agf.offboard_cfg(sc["quad_type"])
+    n = nticks or sc["nticks"]
+    parts = []
+    for c in (chunks or [n]):
+        parts.append(v.run_offboard(c, oc, sc["targets"], offset=offset))
+    return np.vstack(parts), v
+
+
+def make_batch_offboard(agf, sc, n=1, offsets=None, cfg=None, ocfg=None, **kw):
+    b = agf.Batch(cfg if cfg is not None else cfg_for(agf, sc), n, uwb_comm_period=sc["uwb_comm_period"], **kw)
+    s13 = np.zeros((n, 13))
+    s13[:, 0:3] = sc["pos"]
+    s13[:, 6:10] = sc["att"]
+    b.set_state13(s13)
+    b.set_offboard_loop(ocfg if ocfg is not None else agf.offboard_cfg(sc["quad_type"]), sc["targets"], offsets)
+    return b

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import agrifly_b200 as agf  # noqa: E402
 import orc  # noqa: E402
 from agrifly_b200 import scenarios as scen  # noqa: E402
-from common import run_oracle  # noqa: E402
+from common import run_oracle, run_oracle_offboard  # noqa: E402
 
 
 def sample_ticks(n):
@@ -45,6 +45,15 @@ def main():
             p1, p2 = v.telemetry()
             out[key + "/tel1"] = p1
             out[key + "/tel2"] = p2
+        # offboard loop (Rappids_Simulator's closed loop, truth-fed): reference QuadcopterController + CommunicationsDelay
+        sc = scen.offboard_scenario()
+        tr, v = run_oracle_offboard(O, agf, sc)
+        idx = sample_ticks(len(tr))
+        key = "%s/%s" % (flavour, sc["name"])
+        out[key + "/ticks"] = idx
+        out[key + "/traj"] = tr[idx]
+        for k, val in v.full().items():
+            out[key + "/full/" + k] = np.asarray(val)
     # codec known-answer vectors from the reference's own RadioTypes / TelemetryPacket code
     O = orc.Oracle("ref-glibc")
     rng = np.random.default_rng(7)

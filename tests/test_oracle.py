@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from common import bit_equal, run_oracle
+from common import bit_equal, run_oracle, run_oracle_offboard
 from conftest import ROOT, oracle_or_skip
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
@@ -47,6 +47,42 @@ def test_port_matches_live_reference(agf, orc_mod, math, name):
     sc = scenario(agf, name)
     a, _ = run_oracle(R, agf, sc)
     b, _ = run_oracle(P, agf, sc)
+    assert bit_equal(a, b)
+
+
+@pytest.mark.parametrize("math", ["glibc", "shared"])
+def test_offboard_loop_port_matches_reference(agf, orc_mod, math):
+    """SURVEY 8f N1: the offboard rates loop (reference QuadcopterController::Run + CreateRatesCommand +
+    CommunicationsDelay around Run(), truth-fed) restated in the port: golden vectors, and the live reference."""
+    sc = agf.scenarios.offboard_scenario()
+    P = oracle_or_skip(orc_mod, "port-" + math)
+    tr, v = run_oracle_offboard(P, agf, sc, chunks=[1777, 2223])  # the loop's stopwatch and queue persist across calls
+    key = "ref-%s/offboard" % math
+    assert bit_equal(tr[GOLD[key + "/ticks"]], GOLD[key + "/traj"])
+    full = v.full()
+    for k, val in full.items():
+        if k not in FULL_SKIP:
+            assert bit_equal(np.asarray(val), GOLD[key + "/full/" + k]), k
+    # the loop really flies the vehicle: set-points reached, no panic
+    assert np.linalg.norm(tr[2999, 0:3] - np.array([1.0, -0.5, 2.5])) < 0.05 and tr[-1, 35] == 0
+    if orc_mod.available("ref-" + math):
+        R = orc_mod.Oracle("ref-" + math)
+        a, _ = run_oracle_offboard(R, agf, sc)
+        assert bit_equal(a, tr)
+
+
+def test_offboard_loop_device_step_on_host_matches_port(agf, orc_mod, port_shared):
+    """The product's own offboard loop (agf_step.cuh tick(): clock-driven delivery/generation, per-vehicle command
+    queue) compiled for the host equals the port bit for bit, also when the run is cut into launches."""
+    if not orc_mod.available("hostsim-shared"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "hostsim"], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("hostsim not buildable here: " + r.stderr[-300:])
+    H = orc_mod.Oracle("hostsim-shared")
+    sc = agf.scenarios.offboard_scenario(nticks=2500)
+    off = (0.3, -0.2, 0.1)
+    a, _ = run_oracle_offboard(port_shared, agf, sc, offset=off)
+    b, _ = run_oracle_offboard(H, agf, sc, chunks=[1, 1, 13, 985, 1500], offset=off)
     assert bit_equal(a, b)
 
 

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from common import bit_equal, cfg_for, make_batch, rel_err, run_oracle
+from common import bit_equal, cfg_for, make_batch, make_batch_offboard, rel_err, run_oracle, run_oracle_offboard
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
@@ -136,6 +136,62 @@ def test_balanced_schedule_fast_variant_with_noise(agf):
     # vehicles at both ends of the big population (blocks that were split sit all over the index range)
     assert bit_equal(out[0][0][:2000], out[1][0])
     assert bit_equal(out[0][1][:2000], out[1][1])
+
+
+def test_offboard_loop_parity(agf, port_shared):
+    """Rappids_Simulator's closed loop (offboard position controller -> 16-bit rates commands -> 30 ms
+    uplink delay -> onboard rate controller; estimate = truth) inside the kernel, per vehicle with its own set-point
+    offset.  Parity variant == oracle bit for bit for every vehicle, across launch boundaries."""
+    sc = agf.scenarios.offboard_scenario(nticks=3500)
+    n = 5
+    offs = np.array([[0, 0, 0], [0.3, -0.2, 0.1], [-1.0, 0.5, 0.4], [2.0, 2.0, -0.5], [0.01, 0.02, 0.03]], float)
+    b = make_batch_offboard(agf, sc, n=n, offsets=offs)
+    for c in (1, 2, 997, 1000, 1500):
+        b.run(c)
+    got = b.record()
+    for i in range(n):
+        ref, _ = run_oracle_offboard(port_shared, agf, sc, offset=offs[i])
+        assert bit_equal(got[i], ref[-1]), (i, got[i][0:3], ref[-1][0:3])
+    # the population flew: everybody near its own set-point, rates mode, no panic
+    tgt = np.array(sc["targets"][2][1]) + offs  # 1 s after the last set-point change: still descending
+    assert np.all(np.linalg.norm(got[:, 0:2] - tgt[:, 0:2], axis=1) < 0.05) and np.all(np.abs(got[:, 2] - tgt[:, 2]) < 0.6)
+    assert np.all(got[:, 34] == agf.abi.FS_EXTERNAL_RATES_CONTROL) and np.all(got[:, 35] == 0)
+    b.close()
+
+
+def test_offboard_loop_fast_variants_and_object_api(agf, port_glibc):
+    """Fast FP64/FP32 kernels fly the same loop within the stated tolerance (position 1e-3 / 5e-3 relative, whole plant state
+    incl. body rates and motor speeds 1e-2: closed loop through float controllers and a 16-bit quantiser whose
+    rounding boundaries amplify last-bit differences into one-LSB command differences), also when a big
+    population takes the balanced schedule; and the split Run()/advance path (object facade) equals the fused path."""
+    sc = agf.scenarios.offboard_scenario(nticks=3000)
+    ref, _ = run_oracle_offboard(port_glibc, agf, sc)
+    for prec in (agf.abi.PREC_FP64, agf.abi.PREC_FP32):
+        b = make_batch_offboard(agf, sc, n=3, precision=prec, math=agf.abi.MATH_FAST)
+        b.run(sc["nticks"])
+        got = b.record()[0]
+        e, ep = rel_err(got[0:17], ref[-1, 0:17]), rel_err(got[0:3], ref[-1, 0:3])
+        print("offboard fast prec=%d: rel err position %.3e, plant state %.3e" % (prec, ep, e))
+        assert ep < (1e-3 if prec == agf.abi.PREC_FP64 else 5e-3) and e < 1e-2
+        b.close()
+    n = 148 * 4 * 128 + 777
+    b = make_batch_offboard(agf, sc, n=n, precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST, telemetry_warnings=False)
+    b.run(1501)
+    b.run(1499)
+    big = b.record()
+    b.close()
+    assert bit_equal(big, np.tile(big[0], (n, 1)))
+    assert rel_err(big[0, 0:3], ref[-1, 0:3]) < 5e-3
+    # Run() / advance split == fused ticks (parity arithmetic, bit for bit)
+    b1 = make_batch_offboard(agf, sc, n=2)
+    b1.run(600)
+    b2 = make_batch_offboard(agf, sc, n=2)
+    for _ in range(600):
+        b2.run(1, dt_us=0)
+        b2.advance_clock(2000)
+    assert bit_equal(b1.record(), b2.record())
+    b1.close()
+    b2.close()
 
 
 def test_monte_carlo_population_parity(agf, port_shared):
