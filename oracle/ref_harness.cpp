@@ -304,6 +304,9 @@ double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t
   std::vector<orc_vehicle*> vs(n);
   for (uint32_t i = 0; i < n; i++) {
     vs[i] = orc_create(&cfgs[n_cfgs == 1 ? 0 : i], opts);
+    // The reference default-seeds every vehicle's IMU noise engine identically (Quadcopter_T.hpp:122, seed 1); a
+    // Monte-Carlo population needs independent streams: vehicle i is seeded i + 1 (vehicle 0 = the reference default).
+    vs[i]->quad->_generator.seed(i + 1);
     if (init13) {
       const double* s = init13 + 13 * size_t(i);
       orc_set_state(vs[i], s, s + 3, s + 6, s + 10);

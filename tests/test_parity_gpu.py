@@ -225,6 +225,55 @@ def test_monte_carlo_population_parity(agf, port_shared):
     b.close()
 
 
+def test_monte_carlo_hover_with_noise_matches_reference_population(agf, orc_mod):
+    """BASELINE config 2 (b): hover with IMU noise on.  Noise realisations differ by construction (Philox on the GPU,
+    the reference's std::default_random_engine + normal_distribution on the CPU), so the comparison is between
+    POPULATIONS: the same randomized initial states and set-points flown by the CUDA path and by the unmodified
+    reference (oracle/_ref, vehicle i seeded i + 1) must give the same tracking-error and estimator-error
+    distributions (means within 10 %, two-sample Kolmogorov-Smirnov not rejecting at 1e-3)."""
+    from scipy import stats as sps
+    if not orc_mod.available("ref-glibc"):
+        pytest.skip("oracle/_ref was not built (needs the reference tree at build time)")
+    R = orc_mod.Oracle("ref-glibc")
+    n, nt = 768, 2500
+    s = agf.scenarios
+    sc = s.full_scenario(agf.codec, nticks=nt)
+    init = s.monte_carlo_initial_states(n, seed=4321, yaw_max=np.pi / 3)
+    idle = agf.codec.encode_idle(0)
+    slot = np.array([np.frombuffer(agf.codec.encode_position(0, (p[0], p[1], 1.5)), np.uint8) for p in init])
+    sched = [(d, idle, -1) if sl == -2 else (d, None, 0) for d, _, sl in s.hover_slot_schedule(nt)]
+    cfg = cfg_for(agf, sc)
+    anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
+    slots = np.zeros((4, n, 23), np.uint8)
+    slots[0] = slot
+    ref, _ = R.run_population(cfg, n, init13=init, anchors=anchors, nticks=nt, sched=sched, slot_raw=slots,
+                              threads=os.cpu_count() or 1, uwb_comm_period=sc["uwb_comm_period"], sigma_acc=0.2, sigma_gyro=0.1)
+    out = {}
+    for name, kw in (("fp64-parity", {}), ("fp32-fast", dict(precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST))):
+        b = agf.Batch(cfg, n, uwb_comm_period=sc["uwb_comm_period"], sigma_acc=0.2, sigma_gyro=0.1, seed=5, **kw)
+        for i, p in sc["anchors"]:
+            b.add_anchor(i, p)
+        b.set_state13(init)
+        b.set_slot(0, slot)
+        b.set_schedule(sched)
+        b.run(nt)
+        out[name] = b.record()
+        b.close()
+    tgt = np.column_stack([init[:, 0], init[:, 1], np.full(n, 1.5)])
+    e_ref = np.linalg.norm(ref[:, 0:3] - tgt, axis=1)
+    est_ref = np.linalg.norm(ref[:, 21:24] - ref[:, 0:3], axis=1)
+    assert np.all(ref[:, 35] == 0)
+    for name, got in out.items():
+        assert np.all(got[:, 35] == 0), name
+        e = np.linalg.norm(got[:, 0:3] - tgt, axis=1)
+        est = np.linalg.norm(got[:, 21:24] - got[:, 0:3], axis=1)
+        ks_e, ks_est = sps.ks_2samp(e, e_ref), sps.ks_2samp(est, est_ref)
+        print("%s: mean tracking error %.4f (reference %.4f), mean estimator error %.4f (reference %.4f), KS p %.3f / %.3f"
+              % (name, e.mean(), e_ref.mean(), est.mean(), est_ref.mean(), ks_e.pvalue, ks_est.pvalue))
+        assert abs(e.mean() / e_ref.mean() - 1) < 0.10 and abs(est.mean() / est_ref.mean() - 1) < 0.10
+        assert ks_e.pvalue > 1e-3 and ks_est.pvalue > 1e-3
+
+
 def test_per_vehicle_parameter_sweep_parity(agf, port_shared):
     """BASELINE config 4's parameter sweep (mass, inertia, motor constants per vehicle), FP64 parity."""
     n = 24
