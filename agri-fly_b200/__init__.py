@@ -321,5 +321,142 @@ class Batch:
         return ms.value, nl.value
 
 
+RESULT_DTYPE = np.dtype([("found", "<i4"), ("best_index", "<i4"), ("n_generated", "<i4"), ("n_cost_checks", "<i4"),
+                         ("n_collision_checks", "<i4"), ("n_velocity_checks", "<i4"), ("n_collision_free", "<i4"),
+                         ("n_pyramids", "<i4"), ("best_cost", "<f8"), ("best_coeffs", "<f8", (6, 3)), ("best_tf", "<f8")])
+assert RESULT_DTYPE.itemsize == C.sizeof(abi.RappidsResult)
+
+
+def rappids_cfg(width=320, height=240, **edits):
+    """agf_rappids_cfg_default(width, height) with field edits (cost_kind=..., cost_vec=(..), math=..., ...)."""
+    c = abi.RappidsCfg()
+    _check(lib().agf_rappids_cfg_default(int(width), int(height), C.byref(c)))
+    for k, v in edits.items():
+        if k == "cost_vec":
+            c.cost_vec[:] = [float(x) for x in v]
+        else:
+            setattr(c, k, v)
+    return c
+
+
+class Rappids:
+    """Batched RAPPIDS planner handle (include/agrifly_b200_rappids.h): one planner call per vehicle."""
+
+    def __init__(self, cfg, n, max_candidates):
+        self.n, self.kcap, self.cfg = int(n), int(max_candidates), cfg
+        self.W, self.H = cfg.width, cfg.height
+        self._h = C.c_void_p()
+        _check(lib().agf_rappids_create(C.byref(cfg), self.n, self.kcap, C.byref(self._h)))
+        self.k = 0
+
+    def close(self):
+        if self._h:
+            lib().agf_rappids_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _cnt(self, first, count):
+        return self.n - first if count is None else count
+
+    def set_images(self, images, first=0):
+        images = np.ascontiguousarray(images, dtype=np.uint16)
+        assert images.shape[1:] == (self.H, self.W), images.shape
+        _check(lib().agf_rappids_set_images(self._h, images.ctypes.data, first, images.shape[0]))
+
+    def render_scenes(self, row_bg, boxes, first=0):
+        row_bg = np.ascontiguousarray(row_bg, dtype=np.uint16)
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32)
+        assert row_bg.shape[1] == self.H and boxes.shape[1:] == (abi.RAPPIDS_MAX_BOXES, 5)
+        _check(lib().agf_rappids_render_scenes(self._h, row_bg.ctypes.data, boxes.ctypes.data, first, row_bg.shape[0]))
+
+    def get_images(self, first=0, count=None):
+        count = self._cnt(first, count)
+        out = np.zeros((count, self.H, self.W), dtype=np.uint16)
+        _check(lib().agf_rappids_get_images(self._h, out.ctypes.data, first, count))
+        return out
+
+    def set_states(self, vel0, acc0, grav, first=0):
+        v, a, g = (np.ascontiguousarray(x, dtype=np.float64) for x in (vel0, acc0, grav))
+        assert v.shape == a.shape == g.shape and v.shape[1] == 3
+        _check(lib().agf_rappids_set_states(self._h, v.ctypes.data, a.ctypes.data, g.ctypes.data, first, v.shape[0]))
+
+    def set_goals(self, goals, first=0):
+        g = np.ascontiguousarray(goals, dtype=np.float64)
+        _check(lib().agf_rappids_set_goals(self._h, g.ctypes.data, first, g.shape[0]))
+
+    def set_candidates(self, cands, first=0):
+        c = np.ascontiguousarray(cands, dtype=np.float64)
+        assert c.ndim == 3 and c.shape[2] == 4
+        _check(lib().agf_rappids_set_candidates(self._h, c.ctypes.data, c.shape[1], first, c.shape[0]))
+        self.k = c.shape[1]
+
+    def sample_candidates(self, k, seed, first_global_index=0):
+        _check(lib().agf_rappids_sample_candidates(self._h, int(k), int(seed), int(first_global_index)))
+        self.k = int(k)
+
+    def get_candidates(self, first=0, count=None):
+        count = self._cnt(first, count)
+        out = np.zeros((count, self.k, 4))
+        _check(lib().agf_rappids_get_candidates(self._h, out.ctypes.data, first, count))
+        return out
+
+    def plan(self):
+        _check(lib().agf_rappids_plan(self._h))
+
+    def sync(self):
+        _check(lib().agf_rappids_sync(self._h))
+
+    def results(self, first=0, count=None):
+        count = self._cnt(first, count)
+        out = np.zeros(count, dtype=RESULT_DTYPE)
+        _check(lib().agf_rappids_get_results(self._h, out.ctypes.data, first, count))
+        return out
+
+    def candidate_flags(self, first=0, count=None):
+        count = self._cnt(first, count)
+        out = np.zeros((count, self.k), dtype=np.uint8)
+        _check(lib().agf_rappids_get_candidate_flags(self._h, out.ctypes.data, first, count))
+        return out
+
+    def pyramids(self, first=0, count=None):
+        count = self._cnt(first, count)
+        out = np.zeros((count, abi.RAPPIDS_MAX_PYRAMIDS, abi.RAPPIDS_PYRAMID_DOUBLES))
+        _check(lib().agf_rappids_get_pyramids(self._h, out.ctypes.data, first, count))
+        return out
+
+    def stats(self):
+        out = np.zeros(8)
+        _check(lib().agf_rappids_reduce_stats(self._h, out.ctypes.data))
+        return dict(zip(("found", "generated", "cost_checks", "input_feasible", "velocity_admissible",
+                         "collision_free", "pyramids", "sum_best_cost"), out.tolist()))
+
+    def stats_device(self, dev_ptr):
+        _check(lib().agf_rappids_reduce_stats_device(self._h, C.c_void_p(dev_ptr)))
+
+    @property
+    def stream(self):
+        return lib().agf_rappids_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().agf_rappids_launch_count(self._h))
+
+    def plan_kernel_time(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().agf_rappids_plan_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
 def build_info():
     return lib().agf_build_info().decode()

@@ -96,9 +96,59 @@ class OffboardTarget(C.Structure):
     _fields_ = [("time_us", C.c_uint64), ("pos", C.c_double * 3)]
 
 
-# every symbol include/agrifly_b200.h declares: name -> (restype, argtypes)
+# ---- include/agrifly_b200_rappids.h ------------------------------------------------------------
+RAPPIDS_MAX_PYRAMIDS = 32
+RAPPIDS_PYRAMID_DOUBLES = 17
+RAPPIDS_MAX_BOXES = 4
+RAPPIDS_COST_DIRECTION, RAPPIDS_COST_GOAL = 0, 1
+RAPPIDS_LOW_COST, RAPPIDS_DYNAMICS_FEASIBLE, RAPPIDS_VELOCITY_ADMISSIBLE, RAPPIDS_COLLISION_FREE = 1, 2, 4, 8
+
+
+class RappidsCfg(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("depth_scale", C.c_double),
+                ("focal_length", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("true_radius", C.c_double), ("planning_radius", C.c_double), ("min_checking_dist", C.c_double),
+                ("min_thrust", C.c_double), ("max_thrust", C.c_double), ("max_angvel", C.c_double),
+                ("min_section_time", C.c_double), ("max_velocity", C.c_double),
+                ("max_pyramids", C.c_int32), ("cost_kind", C.c_int32), ("cost_vec", C.c_double * 3),
+                ("sample_min_x", C.c_double), ("sample_max_x", C.c_double), ("sample_min_y", C.c_double),
+                ("sample_max_y", C.c_double), ("sample_min_depth", C.c_double), ("sample_max_depth", C.c_double),
+                ("sample_min_time", C.c_double), ("sample_max_time", C.c_double),
+                ("math", C.c_int32), ("device", C.c_int32)]
+
+
+class RappidsResult(C.Structure):
+    _fields_ = [("found", C.c_int32), ("best_index", C.c_int32), ("n_generated", C.c_int32),
+                ("n_cost_checks", C.c_int32), ("n_collision_checks", C.c_int32), ("n_velocity_checks", C.c_int32),
+                ("n_collision_free", C.c_int32), ("n_pyramids", C.c_int32), ("best_cost", C.c_double),
+                ("best_coeffs", C.c_double * 18), ("best_tf", C.c_double)]
+
+
+# every symbol include/agrifly_b200.h and include/agrifly_b200_rappids.h declare: name -> (restype, argtypes)
 _P = C.POINTER
 PROTOTYPES = {
+    "agf_rappids_cfg_default": (C.c_int, [C.c_int32, C.c_int32, _P(RappidsCfg)]),
+    "agf_rappids_create": (C.c_int, [_P(RappidsCfg), C.c_size_t, C.c_int32, _P(C.c_void_p)]),
+    "agf_rappids_destroy": (C.c_int, [C.c_void_p]),
+    "agf_rappids_size": (C.c_size_t, [C.c_void_p]),
+    "agf_rappids_stream": (C.c_void_p, [C.c_void_p]),
+    "agf_rappids_set_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_render_scenes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_get_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_set_states": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_set_goals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_set_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t, C.c_size_t]),
+    "agf_rappids_sample_candidates": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64]),
+    "agf_rappids_get_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_plan": (C.c_int, [C.c_void_p]),
+    "agf_rappids_sync": (C.c_int, [C.c_void_p]),
+    "agf_rappids_get_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_get_candidate_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_get_pyramids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "agf_rappids_reduce_stats_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "agf_rappids_plan_kernel_time": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_uint64)]),
+    "agf_rappids_launch_count": (C.c_uint64, [C.c_void_p]),
     "agf_quad_type_from_id": (C.c_int, [C.c_uint]),
     "agf_logic_consts_from_type": (C.c_int, [C.c_int, _P(LogicConsts)]),
     "agf_vehicle_cfg_from_type": (C.c_int, [C.c_int, C.c_int, _P(VehicleCfg)]),

@@ -29,9 +29,14 @@ UNITS = [
     ("agf_kernels_fast.cu", "agf_kernels_fast_f64_uwb", FAST + ["-DAGF_FAST_F64=1", "-DAGF_FAST_UWB=1"]),
     ("agf_kernels_fast.cu", "agf_kernels_fast_f64_rates", FAST + ["-DAGF_FAST_F64=1", "-DAGF_FAST_UWB=0"]),
     ("agf_batch.cu", "agf_batch", ["-fmad=false"]),
+    # the batched RAPPIDS planner (include/agrifly_b200_rappids.h): parity and throughput variants of the kernel
+    ("agf_rappids_plan.cu", "agf_rappids_plan_parity", ["-fmad=false", "-DAGF_RAPPIDS_PARITY=1"]),
+    ("agf_rappids_plan.cu", "agf_rappids_plan_fast", ["-DAGF_RAPPIDS_PARITY=0"]),
+    ("agf_rappids.cu", "agf_rappids", ["-fmad=false"]),
     ("agf_config.cpp", "agf_config", []),
 ]
-HEADERS = ["agf_step.cuh", "agf_types.h", "agf_math.h", "agf_launch.h", "agf_host_params.h", os.path.join(ROOT, "include", "agrifly_b200.h")]
+HEADERS = ["agf_step.cuh", "agf_types.h", "agf_math.h", "agf_launch.h", "agf_host_params.h", "agf_rappids_plan.cuh",
+           os.path.join(ROOT, "include", "agrifly_b200.h"), os.path.join(ROOT, "include", "agrifly_b200_rappids.h")]
 
 
 def _digest(paths, flags):

@@ -36,6 +36,8 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   g_last_error = buf;
   return code;
 }
+// error reporting for the other translation units of the library (agf_rappids.cu)
+int fail_from(int code, const char* what, int cuda_error) { return fail(code, what, (cudaError_t)cuda_error); }
 #define AGF_CUDA(call)                                      \
   do {                                                      \
     cudaError_t e_ = (call);                                \

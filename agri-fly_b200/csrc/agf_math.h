@@ -299,3 +299,46 @@ AGF_HD float agf_cosf(float x) { return (float)agf_cos((double)x); }
 AGF_HD float agf_asinf(float x) { return (float)agf_asin((double)x); }
 AGF_HD float agf_acosf(float x) { return (float)agf_acos((double)x); }
 AGF_HD float agf_atan2f(float y, float x) { return (float)agf_atan2((double)y, (double)x); }
+
+// ---------------------------------------------------------------------------
+// cube root of a non-negative number: the planner's cubic solver calls
+// pow(|r| + sqrt(r^2 - q^3), 1./3) (Common/Common/Math/RootFinder.hpp:80).
+// Exponent split by bit manipulation (exact), Newton iterations y <- (2y + m/y^2)/3
+// on m in [1, 8) from a secant start (relative error 0.11 -> 1e-2 -> 1.5e-4 -> 2e-8 -> <1e-15).
+// ---------------------------------------------------------------------------
+AGF_HD long long agf_d2bits(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(x);
+#else
+  long long b;
+  __builtin_memcpy(&b, &x, sizeof(b));
+  return b;
+#endif
+}
+AGF_HD double agf_bits2d(long long b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(b);
+#else
+  double x;
+  __builtin_memcpy(&x, &b, sizeof(x));
+  return x;
+#endif
+}
+AGF_HD double agf_cbrt_pos(double x) {
+  if (!(x > 0.0) || x > 1.7976931348623157e308) return x;  // 0, NaN and +inf pass through
+  int eadj = 0;
+  if (x < 2.2250738585072014e-308) {  // subnormal: scale by 2^54 (exact)
+    x = AGF_DMUL(x, 18014398509481984.0);
+    eadj = -18;
+  }
+  long long b = agf_d2bits(x);
+  int e = (int)((b >> 52) & 0x7ff) - 1023;
+  int k = e >= 0 ? e / 3 : -((2 - e) / 3);  // floor(e / 3)
+  int r = e - 3 * k;                         // 0, 1, 2
+  double m = agf_bits2d((b & 0x000fffffffffffffLL) | ((long long)(1023 + r) << 52));  // [1, 8)
+  double y = AGF_DADD(1.0, AGF_DDIV(AGF_DSUB(m, 1.0), 7.0));
+#pragma unroll 1
+  for (int it = 0; it < 6; it++)
+    y = AGF_DDIV(AGF_DADD(AGF_DMUL(2.0, y), AGF_DDIV(m, AGF_DMUL(y, y))), 3.0);
+  return AGF_DMUL(y, agf_bits2d((long long)(1023 + k + eadj) << 52));
+}

@@ -1,0 +1,602 @@
+// agf_rappids.cu -- host side of the batched RAPPIDS planner behind include/agrifly_b200_rappids.h:
+// the handle, device buffers (depth images [n][H][W] + transposed copies [n][W][H], states, candidate lists,
+// results), the small kernels around the planner (scene rasteriser, image transpose, Philox candidate sampler,
+// population statistics) and the C ABI.  The planner kernel itself is agf_rappids_plan.cuh.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "agf_rappids_plan.cuh"
+#include "agrifly_b200_rappids.h"
+
+namespace agf {
+int fail_from(int code, const char* what, int cuda_error);  // agf_batch.cu (sets agf_last_error_string)
+}
+namespace agfr {
+cudaError_t launch_plan_parity(const PlanParams& P, int grid, cudaStream_t stream);
+cudaError_t launch_plan_fast(const PlanParams& P, int grid, cudaStream_t stream);
+cudaError_t plan_blocks_per_sm_parity(int* blocks, int* regs);
+cudaError_t plan_blocks_per_sm_fast(int* blocks, int* regs);
+}  // namespace agfr
+
+namespace {
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) { return agf::fail_from(code, what, (int)e); }
+#define AGFR_CUDA(call)                                         \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if (e_ != cudaSuccess) return fail(AGF_ECUDA, #call, e_);   \
+  } while (0)
+
+static_assert(sizeof(agf_rappids_result) == sizeof(agfr::ResultRec), "result record layout");
+static_assert(AGF_RAPPIDS_MAX_PYRAMIDS == agfr::kMaxPyr, "pyramid capacity");
+
+// pixel = min(row value, boxes covering it); written row-major (T == false) or transposed (T == true), the
+// thread index running along the contiguous dimension of the destination in both cases
+template<bool T>
+__global__ void render_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ row_bg,
+                              const int32_t* __restrict__ boxes, int W, int H, size_t count) {
+  const size_t npix = (size_t)W * H;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count * npix;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = idx / npix;
+    const int r = (int)(idx - v * npix);
+    const int x = T ? r / H : r % W;
+    const int y = T ? r % H : r / W;
+    unsigned val = row_bg[v * H + y];
+    const int32_t* b = boxes + v * AGF_RAPPIDS_MAX_BOXES * 5;
+#pragma unroll
+    for (int k = 0; k < AGF_RAPPIDS_MAX_BOXES; k++) {
+      const int x0 = b[5 * k], x1 = b[5 * k + 1], y0 = b[5 * k + 2], y1 = b[5 * k + 3], bv = b[5 * k + 4];
+      if (bv > 0 && x >= x0 && x < x1 && y >= y0 && y < y1) val = min(val, (unsigned)bv);
+    }
+    dst[idx] = (uint16_t)val;
+  }
+}
+
+// [count][H][W] -> [count][W][H] through 32x32 shared-memory tiles (both sides coalesced)
+__global__ void transpose_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ src, int W, int H) {
+  __shared__ uint16_t tile[32][34];
+  const size_t v = blockIdx.z;
+  const uint16_t* s = src + v * (size_t)W * H;
+  uint16_t* d = dst + v * (size_t)W * H;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = bx + threadIdx.x, y = by + j;
+    if (x < W && y < H) tile[j][threadIdx.x] = s[(size_t)y * W + x];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int y = by + threadIdx.x, x = bx + j;
+    if (x < W && y < H) d[(size_t)x * H + y] = tile[threadIdx.x][j];
+  }
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+struct SampleBox {
+  double x0, x1, y0, y1, d0, d1, t0, t1, cx, cy, f;
+};
+// RandomTrajectoryGenerator::GetNextCandidateTrajectory (DepthImagePlanner.hpp:383-393) with counter-based draws:
+// one Philox block per (vehicle, candidate) -> pixel x, pixel y, depth, duration
+__global__ void sample_kernel(double* __restrict__ cands, size_t n, int k, int kcap, uint64_t seed, uint64_t first,
+                              const SampleBox B) {
+  const size_t total = n * (size_t)k;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = idx / k;
+    const int i = (int)(idx - v * k);
+    const uint64_t gv = first + v;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)gv, (uint32_t)(gv >> 32), (uint32_t)i, 0x52415050u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const double s = 1.0 / 4294967296.0;
+    const double px = B.x0 + (B.x1 - B.x0) * (((double)r.x + 0.5) * s);
+    const double py = B.y0 + (B.y1 - B.y0) * (((double)r.y + 0.5) * s);
+    const double dp = B.d0 + (B.d1 - B.d0) * (((double)r.z + 0.5) * s);
+    const double T = B.t0 + (B.t1 - B.t0) * (((double)r.w + 0.5) * s);
+    double4 c;
+    c.x = dp * ((px - B.cx) / B.f);
+    c.y = dp * ((py - B.cy) / B.f);
+    c.z = dp * 1;
+    c.w = T;
+    *reinterpret_cast<double4*>(cands + (v * kcap + i) * 4) = c;
+  }
+}
+
+// K4-style reduction of the per-vehicle results: warp shuffles, one atomic per warp and statistic
+__global__ void stats_kernel(const agf_rappids_result* __restrict__ res, size_t n, double* __restrict__ out) {
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+    const agf_rappids_result& r = res[v];
+    a[0] += r.found;
+    a[1] += r.n_generated;
+    a[2] += r.n_cost_checks;
+    a[3] += r.n_collision_checks;
+    a[4] += r.n_velocity_checks;
+    a[5] += r.n_collision_free;
+    a[6] += r.n_pyramids;
+    if (r.found) a[7] += r.best_cost;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + k, a[k]);
+  }
+}
+
+struct Handle {
+  agf_rappids_cfg cfg;
+  size_t n = 0;
+  int kcap = 0, k = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint16_t *img = nullptr, *imgT = nullptr;
+  double *state = nullptr, *cands = nullptr, *pyr = nullptr, *stats = nullptr;
+  uint8_t* flags = nullptr;
+  agf_rappids_result* results = nullptr;
+  int* next = nullptr;
+  void* stage = nullptr;  // device staging for scene descriptions
+  size_t stage_bytes = 0;
+  int grid = 0, regs = 0, blocks_per_sm = 0;
+  uint64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  size_t events_used = 0;
+
+  ~Handle() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& e : events) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    cudaFree(img);
+    cudaFree(imgT);
+    cudaFree(state);
+    cudaFree(cands);
+    cudaFree(pyr);
+    cudaFree(stats);
+    cudaFree(flags);
+    cudaFree(results);
+    cudaFree(next);
+    cudaFree(stage);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  size_t npix() const { return (size_t)cfg.width * cfg.height; }
+  int range(size_t first, size_t count) const {
+    if (first > n || count > n - first) return fail(AGF_ERANGE, "vehicle range outside the handle");
+    return AGF_OK;
+  }
+  int ensure_stage(size_t bytes) {
+    if (bytes <= stage_bytes) return AGF_OK;
+    cudaFree(stage);
+    stage = nullptr;
+    stage_bytes = 0;
+    AGFR_CUDA(cudaMalloc(&stage, bytes));
+    stage_bytes = bytes;
+    return AGF_OK;
+  }
+  int retranspose(size_t first, size_t count) {
+    const int W = cfg.width, H = cfg.height;
+    size_t done = 0;
+    while (done < count) {  // gridDim.z <= 65535
+      const size_t c = count - done < 32768 ? count - done : 32768;
+      dim3 g((W + 31) / 32, (H + 31) / 32, (unsigned)c), b(32, 8);
+      transpose_kernel<<<g, b, 0, stream>>>(imgT + (first + done) * npix(), img + (first + done) * npix(), W, H);
+      done += c;
+    }
+    AGFR_CUDA(cudaGetLastError());
+    return AGF_OK;
+  }
+};
+
+Handle* H_(agf_rappids* p) { return reinterpret_cast<Handle*>(p); }
+const Handle* H_(const agf_rappids* p) { return reinterpret_cast<const Handle*>(p); }
+
+}  // namespace
+
+extern "C" {
+
+int agf_rappids_cfg_default(int32_t width, int32_t height, agf_rappids_cfg* c) {
+  if (!c || width <= 0 || height <= 0) return fail(AGF_EINVAL, "bad arguments");
+  memset(c, 0, sizeof(*c));
+  c->width = width;
+  c->height = height;
+  c->depth_scale = 10.0 / 256.0;       // Simulator/Rappids_Simulator/main.cpp:121-122
+  c->focal_length = width / 2.0;       // :360
+  c->cx = width / 2.0;                 // :485-486
+  c->cy = height / 2.0;
+  c->true_radius = 0.116;              // :167-169
+  c->planning_radius = 0.174;
+  c->min_checking_dist = 0.5;
+  c->min_thrust = 5;                   // DepthImagePlanner.cpp:44-52
+  c->max_thrust = 30;
+  c->max_angvel = 20;
+  c->min_section_time = 0.02;
+  c->max_velocity = 5;
+  c->max_pyramids = AGF_RAPPIDS_MAX_PYRAMIDS;
+  c->cost_kind = AGF_RAPPIDS_COST_DIRECTION;
+  c->cost_vec[0] = 0;
+  c->cost_vec[1] = 0;
+  c->cost_vec[2] = 1;
+  c->sample_min_x = 0.1 * width;       // DepthImagePlanner.hpp:334-352
+  c->sample_max_x = 0.9 * width;
+  c->sample_min_y = 0.1 * height;
+  c->sample_max_y = 0.9 * height;
+  c->sample_min_depth = 1.5;
+  c->sample_max_depth = 3.0;
+  c->sample_min_time = 2.0;
+  c->sample_max_time = 3.0;
+  c->math = AGF_MATH_FAST;
+  c->device = -1;
+  return AGF_OK;
+}
+
+int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candidates, agf_rappids** out) {
+  if (!out) return fail(AGF_EINVAL, "out is null");
+  *out = nullptr;
+  if (!cfg) return fail(AGF_EINVAL, "cfg is null");
+  if (n == 0 || n > (size_t)1 << 30) return fail(AGF_EINVAL, "n_vehicles out of range");
+  if (max_candidates <= 0) return fail(AGF_EINVAL, "max_candidates must be > 0");
+  if (cfg->width < 8 || cfg->height < 8 || cfg->width > 4096 || cfg->height > 4096)
+    return fail(AGF_EINVAL, "image size out of range");
+  if (!(cfg->depth_scale > 0) || !(cfg->focal_length > 0) || !(cfg->min_checking_dist > 0) ||
+      !(cfg->true_radius > 0) || !(cfg->planning_radius > 0))
+    return fail(AGF_EINVAL, "camera / vehicle geometry must be positive");
+  if (!(cfg->min_section_time > 0)) return fail(AGF_EINVAL, "min_section_time must be > 0");
+  if (cfg->cost_kind != AGF_RAPPIDS_COST_DIRECTION && cfg->cost_kind != AGF_RAPPIDS_COST_GOAL)
+    return fail(AGF_EINVAL, "bad cost_kind");
+  if (cfg->math != AGF_MATH_PARITY && cfg->math != AGF_MATH_FAST) return fail(AGF_EINVAL, "bad math");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(AGF_ENODEVICE, "no CUDA device available: agrifly_b200 has no CPU execution path");
+  }
+  int dev = cfg->device;
+  if (dev < 0) AGFR_CUDA(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(AGF_EINVAL, "device ordinal out of range");
+  AGFR_CUDA(cudaSetDevice(dev));
+  Handle* h = new (std::nothrow) Handle();
+  if (!h) return fail(AGF_ENOMEM, "host allocation");
+  h->cfg = *cfg;
+  h->cfg.device = dev;
+  if (h->cfg.max_pyramids <= 0 || h->cfg.max_pyramids > AGF_RAPPIDS_MAX_PYRAMIDS)
+    h->cfg.max_pyramids = AGF_RAPPIDS_MAX_PYRAMIDS;
+  h->n = n;
+  h->kcap = max_candidates;
+  h->device = dev;
+  const size_t npix = h->npix();
+#define AGFR_ALLOC(ptr, bytes)                                  \
+  do {                                                          \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));       \
+    if (e_ != cudaSuccess) {                                    \
+      delete h;                                                 \
+      return fail(AGF_ENOMEM, "cudaMalloc " #ptr, e_);          \
+    }                                                           \
+  } while (0)
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(AGF_ECUDA, "cudaStreamCreate", e);
+  }
+  AGFR_ALLOC(h->img, n * npix * sizeof(uint16_t));
+  AGFR_ALLOC(h->imgT, n * npix * sizeof(uint16_t));
+  AGFR_ALLOC(h->state, n * 12 * sizeof(double));
+  AGFR_ALLOC(h->cands, n * (size_t)h->kcap * 4 * sizeof(double));
+  AGFR_ALLOC(h->flags, n * (size_t)h->kcap);
+  AGFR_ALLOC(h->results, n * sizeof(agf_rappids_result));
+  AGFR_ALLOC(h->pyr, n * (size_t)AGF_RAPPIDS_MAX_PYRAMIDS * AGF_RAPPIDS_PYRAMID_DOUBLES * sizeof(double));
+  AGFR_ALLOC(h->stats, 8 * sizeof(double));
+  AGFR_ALLOC(h->next, sizeof(int));
+#undef AGFR_ALLOC
+  // images start empty (everything at the far plane would be 65535; zero = "ignored" pixels), states zero with
+  // the shared cost vector
+  cudaMemsetAsync(h->img, 0, n * npix * sizeof(uint16_t), h->stream);
+  cudaMemsetAsync(h->imgT, 0, n * npix * sizeof(uint16_t), h->stream);
+  cudaMemsetAsync(h->results, 0, n * sizeof(agf_rappids_result), h->stream);
+  cudaMemsetAsync(h->flags, 0, n * (size_t)h->kcap, h->stream);
+  {
+    std::vector<double> st(n * 12, 0.0);
+    for (size_t v = 0; v < n; v++) {
+      st[v * 12 + 7] = 9.81;  // level camera: gravity along +y
+      for (int a = 0; a < 3; a++) st[v * 12 + 9 + a] = cfg->cost_vec[a];
+    }
+    e = cudaMemcpyAsync(h->state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+      delete h;
+      return fail(AGF_ECUDA, "state upload", e);
+    }
+  }
+  int nsm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  e = (h->cfg.math == AGF_MATH_PARITY) ? agfr::plan_blocks_per_sm_parity(&h->blocks_per_sm, &h->regs)
+                                       : agfr::plan_blocks_per_sm_fast(&h->blocks_per_sm, &h->regs);
+  if (e != cudaSuccess || h->blocks_per_sm < 1) {
+    delete h;
+    return fail(AGF_ECUDA, "planner kernel occupancy query", e);
+  }
+  // one resident wave of CTAs; warps fetch vehicles from a counter until the population is done
+  h->grid = nsm * h->blocks_per_sm;
+  const size_t need = (n + agfr::kWarps - 1) / agfr::kWarps;
+  if ((size_t)h->grid > need) h->grid = (int)need;
+  *out = reinterpret_cast<agf_rappids*>(h);
+  return AGF_OK;
+}
+
+int agf_rappids_destroy(agf_rappids* p) {
+  if (p) delete H_(p);
+  return AGF_OK;
+}
+size_t agf_rappids_size(const agf_rappids* p) { return p ? H_(p)->n : 0; }
+void* agf_rappids_stream(const agf_rappids* p) { return p ? (void*)H_(p)->stream : nullptr; }
+uint64_t agf_rappids_launch_count(const agf_rappids* p) { return p ? H_(p)->launches : 0; }
+
+int agf_rappids_set_images(agf_rappids* p, const uint16_t* images, size_t first, size_t count) {
+  if (!p || !images) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaMemcpyAsync(h->img + first * h->npix(), images, count * h->npix() * sizeof(uint16_t),
+                            cudaMemcpyHostToDevice, h->stream));
+  if (int rc = h->retranspose(first, count)) return rc;
+  h->launches += 1;
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
+  return AGF_OK;
+}
+
+int agf_rappids_render_scenes(agf_rappids* p, const uint16_t* row_bg, const int32_t* boxes, size_t first, size_t count) {
+  if (!p || !row_bg || !boxes) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const int W = h->cfg.width, Hh = h->cfg.height;
+  const size_t bg_bytes = count * Hh * sizeof(uint16_t), box_bytes = count * AGF_RAPPIDS_MAX_BOXES * 5 * sizeof(int32_t);
+  const size_t box_off = (bg_bytes + 15) & ~(size_t)15;
+  if (int rc = h->ensure_stage(box_off + box_bytes)) return rc;
+  uint16_t* d_bg = reinterpret_cast<uint16_t*>(h->stage);
+  int32_t* d_box = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(h->stage) + box_off);
+  AGFR_CUDA(cudaMemcpyAsync(d_bg, row_bg, bg_bytes, cudaMemcpyHostToDevice, h->stream));
+  AGFR_CUDA(cudaMemcpyAsync(d_box, boxes, box_bytes, cudaMemcpyHostToDevice, h->stream));
+  const size_t total = count * h->npix();
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  render_kernel<false><<<grid, 256, 0, h->stream>>>(h->img + first * h->npix(), d_bg, d_box, W, Hh, count);
+  render_kernel<true><<<grid, 256, 0, h->stream>>>(h->imgT + first * h->npix(), d_bg, d_box, W, Hh, count);
+  AGFR_CUDA(cudaGetLastError());
+  h->launches += 2;
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_get_images(agf_rappids* p, uint16_t* images, size_t first, size_t count) {
+  if (!p || !images) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaMemcpyAsync(images, h->img + first * h->npix(), count * h->npix() * sizeof(uint16_t),
+                            cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_set_states(agf_rappids* p, const double* vel0, const double* acc0, const double* grav, size_t first,
+                           size_t count) {
+  if (!p || !vel0 || !acc0 || !grav) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const size_t pitch = 12 * sizeof(double), w = 3 * sizeof(double);
+  char* base = reinterpret_cast<char*>(h->state + first * 12);
+  AGFR_CUDA(cudaMemcpy2DAsync(base, pitch, vel0, w, w, count, cudaMemcpyHostToDevice, h->stream));
+  AGFR_CUDA(cudaMemcpy2DAsync(base + w, pitch, acc0, w, w, count, cudaMemcpyHostToDevice, h->stream));
+  AGFR_CUDA(cudaMemcpy2DAsync(base + 2 * w, pitch, grav, w, w, count, cudaMemcpyHostToDevice, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_set_goals(agf_rappids* p, const double* goals, size_t first, size_t count) {
+  if (!p || !goals) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const size_t pitch = 12 * sizeof(double), w = 3 * sizeof(double);
+  char* base = reinterpret_cast<char*>(h->state + first * 12);
+  AGFR_CUDA(cudaMemcpy2DAsync(base + 3 * w, pitch, goals, w, w, count, cudaMemcpyHostToDevice, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_set_candidates(agf_rappids* p, const double* candidates, int32_t k, size_t first, size_t count) {
+  if (!p || !candidates) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (k <= 0 || k > h->kcap) return fail(AGF_EINVAL, "k outside (0, max_candidates]");
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const size_t w = (size_t)k * 4 * sizeof(double);
+  AGFR_CUDA(cudaMemcpy2DAsync(h->cands + first * h->kcap * 4, (size_t)h->kcap * 4 * sizeof(double), candidates, w, w,
+                              count, cudaMemcpyHostToDevice, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  h->k = k;
+  return AGF_OK;
+}
+
+int agf_rappids_sample_candidates(agf_rappids* p, int32_t k, uint64_t seed, uint64_t first_global_index) {
+  if (!p) return fail(AGF_EINVAL, "null handle");
+  Handle* h = H_(p);
+  if (k <= 0 || k > h->kcap) return fail(AGF_EINVAL, "k outside (0, max_candidates]");
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const agf_rappids_cfg& c = h->cfg;
+  SampleBox B{c.sample_min_x, c.sample_max_x, c.sample_min_y, c.sample_max_y, c.sample_min_depth, c.sample_max_depth,
+              c.sample_min_time, c.sample_max_time, c.cx, c.cy, c.focal_length};
+  const size_t total = h->n * (size_t)k;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  sample_kernel<<<grid, 256, 0, h->stream>>>(h->cands, h->n, k, h->kcap, seed, first_global_index, B);
+  AGFR_CUDA(cudaGetLastError());
+  h->launches += 1;
+  h->k = k;
+  return AGF_OK;
+}
+
+int agf_rappids_get_candidates(agf_rappids* p, double* candidates, size_t first, size_t count) {
+  if (!p || !candidates) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (h->k <= 0) return fail(AGF_EINVAL, "no candidates set");
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const size_t w = (size_t)h->k * 4 * sizeof(double);
+  AGFR_CUDA(cudaMemcpy2DAsync(candidates, w, h->cands + first * h->kcap * 4, (size_t)h->kcap * 4 * sizeof(double), w,
+                              count, cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_plan(agf_rappids* p) {
+  if (!p) return fail(AGF_EINVAL, "null handle");
+  Handle* h = H_(p);
+  if (h->k <= 0) return fail(AGF_EINVAL, "no candidates: call agf_rappids_set_candidates or agf_rappids_sample_candidates");
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const agf_rappids_cfg& c = h->cfg;
+  agfr::PlanParams P;
+  P.img = h->img;
+  P.imgT = h->imgT;
+  P.state = h->state;
+  P.cands = h->cands;
+  P.flags = h->flags;
+  P.results = h->results;
+  P.pyramids = h->pyr;
+  P.next = h->next;
+  P.n = (int)h->n;
+  P.k = h->k;
+  P.kcap = h->kcap;
+  P.W = c.width;
+  P.H = c.height;
+  P.scale = c.depth_scale;
+  P.f = c.focal_length;
+  P.cx = c.cx;
+  P.cy = c.cy;
+  P.rPlan = c.planning_radius;
+  P.minDist = c.min_checking_dist;
+  P.fminA = c.min_thrust;
+  P.fmaxA = c.max_thrust;
+  P.wmaxA = c.max_angvel;
+  P.minSec = c.min_section_time;
+  P.vmax = c.max_velocity;
+  P.maxPyr = c.max_pyramids;
+  P.costKind = c.cost_kind;
+  // the integer constants of InflatePyramid, evaluated in double on the host exactly as the reference does
+  // (DepthImagePlanner.cpp:460,506,608)
+  P.edgeOff = (int)(c.focal_length * c.true_radius / c.min_checking_dist);
+  P.ignore = (int)(uint16_t)(c.true_radius / c.depth_scale);
+  P.num = (int)(c.focal_length * c.planning_radius / c.depth_scale);
+  if (h->events_used == h->events.size()) {
+    cudaEvent_t a, b;
+    AGFR_CUDA(cudaEventCreate(&a));
+    AGFR_CUDA(cudaEventCreate(&b));
+    h->events.emplace_back(a, b);
+  }
+  AGFR_CUDA(cudaMemsetAsync(h->next, 0, sizeof(int), h->stream));
+  auto& ev = h->events[h->events_used++];
+  AGFR_CUDA(cudaEventRecord(ev.first, h->stream));
+  cudaError_t e = (c.math == AGF_MATH_PARITY) ? agfr::launch_plan_parity(P, h->grid, h->stream)
+                                              : agfr::launch_plan_fast(P, h->grid, h->stream);
+  if (e != cudaSuccess) return fail(AGF_ECUDA, "planner kernel launch", e);
+  AGFR_CUDA(cudaEventRecord(ev.second, h->stream));
+  h->launches += 1;
+  return AGF_OK;
+}
+
+int agf_rappids_sync(agf_rappids* p) {
+  if (!p) return fail(AGF_EINVAL, "null handle");
+  AGFR_CUDA(cudaSetDevice(H_(p)->device));
+  AGFR_CUDA(cudaStreamSynchronize(H_(p)->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_get_results(agf_rappids* p, agf_rappids_result* out, size_t first, size_t count) {
+  if (!p || !out) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaMemcpyAsync(out, h->results + first, count * sizeof(agf_rappids_result), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_get_candidate_flags(agf_rappids* p, uint8_t* flags, size_t first, size_t count) {
+  if (!p || !flags) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (h->k <= 0) return fail(AGF_EINVAL, "no candidates set");
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaMemcpy2DAsync(flags, (size_t)h->k, h->flags + first * h->kcap, (size_t)h->kcap, (size_t)h->k, count,
+                              cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_get_pyramids(agf_rappids* p, double* pyramids, size_t first, size_t count) {
+  if (!p || !pyramids) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const size_t rec = (size_t)AGF_RAPPIDS_MAX_PYRAMIDS * AGF_RAPPIDS_PYRAMID_DOUBLES;
+  AGFR_CUDA(cudaMemcpyAsync(pyramids, h->pyr + first * rec, count * rec * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_reduce_stats_device(agf_rappids* p, double* dev_out) {
+  if (!p || !dev_out) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaMemsetAsync(dev_out, 0, 8 * sizeof(double), h->stream));
+  const int grid = (int)((h->n + 255) / 256 < 148 * 4 ? (h->n + 255) / 256 : 148 * 4);
+  stats_kernel<<<grid, 256, 0, h->stream>>>(h->results, h->n, dev_out);
+  AGFR_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return AGF_OK;
+}
+
+int agf_rappids_reduce_stats(agf_rappids* p, double* host_out) {
+  if (!p || !host_out) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = agf_rappids_reduce_stats_device(p, h->stats)) return rc;
+  AGFR_CUDA(cudaMemcpyAsync(host_out, h->stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_plan_kernel_time(agf_rappids* p, double* ms, uint64_t* launches) {
+  if (!p || !ms || !launches) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  double total = 0;
+  for (size_t i = 0; i < h->events_used; i++) {
+    float t = 0;
+    AGFR_CUDA(cudaEventElapsedTime(&t, h->events[i].first, h->events[i].second));
+    total += t;
+  }
+  *launches = h->events_used;
+  *ms = h->events_used ? total / (double)h->events_used : 0.0;
+  h->events_used = 0;
+  return AGF_OK;
+}
+
+}  // extern "C"

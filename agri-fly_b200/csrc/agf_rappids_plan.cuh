@@ -1,0 +1,936 @@
+// agf_rappids_plan.cuh -- K6: the batched RAPPIDS planner kernel (C5 / N3).
+//
+// One warp plans for one vehicle: FindLowestCostTrajectory (Components/Components/DepthImagePlanner/
+// DepthImagePlanner.cpp:91-214) on that vehicle's depth image, with the reference's sequential semantics kept
+// exactly (candidates in order, cost pruning against the best collision-free candidate so far, pyramids
+// generated on demand and reused) and the 32 lanes used where the algorithm is data parallel:
+//   * 32 candidates at a time: motion primitive (TrajectoryGenerator/SingleAxisTrajectory.cpp:59-103), cost,
+//     and -- speculatively, for the lanes that beat the best cost at the start of the batch -- the recursive
+//     input-feasibility test (RapidTrajectoryGenerator.cpp:75-160) and the velocity test (:163-205);
+//   * the survivors are collision checked one after the other in candidate order (DepthImagePlanner.cpp:216-301)
+//     with the whole warp on each: the four lateral faces of a pyramid on four lanes (:382-454), the pyramid
+//     list searched with one ballot (:356-380), the pixel scans of InflatePyramid (:456-970) 32 pixels per step
+//     in the reference's scan order -- a ballot finds the first pixel that changes the state, the update is
+//     applied warp-uniformly and the lanes behind it are re-evaluated, so the result is the sequential one.
+// Row walks read the image [H][W]; column walks read a transposed copy [W][H] so that both are coalesced.
+//
+// Compiled twice (agf_rappids_plan.cu): PARITY (-fmad=false, agf_math.h: bit-comparable with the oracle) and
+// FAST (FMA contraction, CUDA libm).  No tensor cores: nothing here is a contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "agf_math.h"
+
+namespace agfr {
+
+#define AGFR_DEV __device__ __forceinline__
+#define AGFR_FULL 0xffffffffu
+
+constexpr int kBlock = 128;           // 4 warps = 4 vehicles per CTA
+constexpr int kWarps = kBlock / 32;
+constexpr int kMaxPyr = 32;
+constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
+
+struct PlanParams {
+  // images
+  const uint16_t* img;    // [n][H][W]
+  const uint16_t* imgT;   // [n][W][H]
+  const double* state;    // [n][12]: vel0, acc0, grav, cost vector
+  const double* cands;    // [n][kcap][4]
+  uint8_t* flags;         // [n][kcap]
+  void* results;          // agf_rappids_result [n]
+  double* pyramids;       // [n][kMaxPyr][17]
+  int* next;              // work counter
+  int n, k, kcap;
+  int W, H;
+  double scale, f, cx, cy, rPlan, minDist;
+  double fminA, fmaxA, wmaxA, minSec, vmax;
+  int maxPyr, costKind;
+  int edgeOff, num;       // int(f * rTrue / minDist), int(f * rPlan / scale)   (DepthImagePlanner.cpp:460,608)
+  int ignore;             // uint16(rTrue / scale)                               (:506)
+};
+
+struct ResultRec {  // == agf_rappids_result
+  int32_t found, best_index, n_generated, n_cost_checks, n_collision_checks, n_velocity_checks, n_collision_free,
+      n_pyramids;
+  double best_cost;
+  double best_coeffs[18];
+  double best_tf;
+};
+
+template<bool PARITY>
+struct Mth {
+  static AGFR_DEV double cos(double x) { return PARITY ? agf_cos(x) : ::cos(x); }
+  static AGFR_DEV double acos(double x) { return PARITY ? agf_acos(x) : ::acos(x); }
+  static AGFR_DEV double cbrt(double x) { return PARITY ? agf_cbrt_pos(x) : ::cbrt(x); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// closed-form roots (Common/Common/Math/RootFinder.hpp:60-174; float 2*pi and float eps as there)
+// ---------------------------------------------------------------------------------------------
+template<bool PARITY>
+__device__ __noinline__ unsigned cubic(double a, double b, double c, double* x) {
+  const float piF = 3.141592653589793238463;
+  const float twoPiF = 2 * piF;
+  const float epsF = 1e-12;
+  const double a2 = a * a;
+  double q = (a2 - 3 * b) / 9;
+  const double r = (a * (2 * a2 - 9 * b) + 27 * c) / 54;
+  const double r2 = r * r;
+  const double q3 = q * q * q;
+  if (r2 < q3) {
+    double t = r / sqrt(q3);
+    if (t < -1) t = -1;
+    if (t > 1) t = 1;
+    t = Mth<PARITY>::acos(t);
+    a /= 3;
+    q = -2 * sqrt(q);
+    x[0] = q * Mth<PARITY>::cos(t / 3) - a;
+    x[1] = q * Mth<PARITY>::cos((t + double(twoPiF)) / 3.0) - a;
+    x[2] = q * Mth<PARITY>::cos((t - double(twoPiF)) / 3.0) - a;
+    return 3;
+  }
+  double A = -Mth<PARITY>::cbrt(fabs(r) + sqrt(r2 - q3));
+  if (r < 0) A = -A;
+  const double B = (fabs(A) < double(epsF) ? 0 : q / A);
+  a /= 3;
+  x[0] = (A + B) - a;
+  x[1] = -0.5 * (A + B) - a;
+  x[2] = 0.5 * sqrt(3.0) * (A - B);
+  if (fabs(x[2]) < double(epsF)) {
+    x[2] = x[1];
+    return 2;
+  }
+  return 1;
+}
+
+template<bool PARITY>
+__device__ __noinline__ unsigned quartic(double a, double b, double c, double d, double* root) {
+  const float epsF = 1e-12;
+  const double a3 = -b;
+  const double b3 = a * c - 4.0 * d;
+  const double c3 = -a * a * d - c * c + 4.0 * b * d;
+  int n = 0;
+  double x3[3];
+  const unsigned nz = cubic<PARITY>(a3, b3, c3, x3);
+  double q1, q2, p1, p2, D, sqD, y;
+  y = x3[0];
+  if (nz != 1) {
+    if (fabs(x3[1]) > fabs(y)) y = x3[1];
+    if (fabs(x3[2]) > fabs(y)) y = x3[2];
+  }
+  D = y * y - 4 * d;
+  if (fabs(D) < double(epsF)) {
+    q1 = q2 = y * 0.5;
+    D = a * a - 4.0 * (b - y);
+    if (fabs(D) < double(epsF)) {
+      p1 = p2 = a * 0.5;
+    } else {
+      sqD = sqrt(D);
+      p1 = (a + sqD) * 0.5;
+      p2 = (a - sqD) * 0.5;
+    }
+  } else {
+    sqD = sqrt(D);
+    q1 = (y + sqD) * 0.5;
+    q2 = (y - sqD) * 0.5;
+    p1 = (a * q1 - c) / (q1 - q2);
+    p2 = (c - a * q2) / (q1 - q2);
+  }
+  D = p1 * p1 - 4 * q1;
+  if (!(D < 0.0)) {
+    sqD = sqrt(D);
+    root[n++] = (-p1 + sqD) * 0.5;
+    root[n++] = (-p1 - sqD) * 0.5;
+  }
+  D = p2 * p2 - 4 * q2;
+  if (!(D < 0.0)) {
+    sqD = sqrt(D);
+    root[n++] = (-p2 + sqD) * 0.5;
+    root[n++] = (-p2 - sqD) * 0.5;
+  }
+  return n;
+}
+
+// roots of c0 t^4 + .. + c4 (or the cubic when the leading coefficient vanishes): the dispatch used at
+// DepthImagePlanner.cpp:318-325,412-419
+template<bool PARITY>
+AGFR_DEV unsigned poly_roots(const double* c, double* roots) {
+  if (fabs(c[0]) > 1e-6) return quartic<PARITY>(c[1] / c[0], c[2] / c[0], c[3] / c[0], c[4] / c[0], roots);
+  return cubic<PARITY>(c[2] / c[1], c[3] / c[1], c[4] / c[1], roots);
+}
+
+// ---------------------------------------------------------------------------------------------
+// motion primitive of one candidate (one lane): rest-to-rest-goal quintic per axis
+// ---------------------------------------------------------------------------------------------
+struct Axis {
+  double v0, a0;        // initial velocity / acceleration (initial position is the focal point, 0)
+  double al, be, ga;    // alpha, beta, gamma
+  double pk0, pk1;      // acceleration extremum times (SingleAxisTrajectory.cpp:120-141)
+  AGFR_DEV double jerk(double t) const { return ga + be * t + (1 / 2.0) * al * t * t; }
+  AGFR_DEV double acc(double t) const { return a0 + ga * t + (1 / 2.0) * be * t * t + (1 / 6.0) * al * t * t * t; }
+  AGFR_DEV double vel(double t) const {
+    return v0 + a0 * t + (1 / 2.0) * ga * t * t + (1 / 6.0) * be * t * t * t + (1 / 24.0) * al * t * t * t * t;
+  }
+  AGFR_DEV double pos(double t) const {
+    return 0.0 + v0 * t + (1 / 2.0) * a0 * t * t + (1 / 6.0) * ga * t * t * t + (1 / 24.0) * be * t * t * t * t +
+           (1 / 120.0) * al * t * t * t * t * t;
+  }
+  // fully defined end state (pf, 0, 0) at Tf (SingleAxisTrajectory.cpp:59-78)
+  AGFR_DEV void generate(double pf, double Tf) {
+    const double da = 0.0 - a0;
+    const double dv = 0.0 - v0 - a0 * Tf;
+    const double dp = pf - 0.0 - v0 * Tf - 0.5 * a0 * Tf * Tf;
+    const double T2 = Tf * Tf, T3 = T2 * Tf, T4 = T3 * Tf, T5 = T4 * Tf;
+    al = (60 * T2 * da - 360 * Tf * dv + 720 * dp) / T5;
+    be = (-24 * T3 * da + 168 * T2 * dv - 360 * Tf * dp) / T5;
+    ga = (3 * T4 * da - 24 * T3 * dv + 60 * T2 * dp) / T5;
+    if (al != 0.0) {
+      const double det = be * be - 2 * ga * al;
+      if (det < 0) {
+        pk0 = 0;
+        pk1 = 0;
+      } else {
+        pk0 = (-be + sqrt(det)) / al;
+        pk1 = (-be - sqrt(det)) / al;
+      }
+    } else {
+      pk0 = (be != 0.0) ? -ga / be : 0;
+      pk1 = 0;
+    }
+  }
+  AGFR_DEV void minmax_acc(double& lo, double& hi, double t1, double t2) const {
+    const double e1 = acc(t1), e2 = acc(t2);
+    lo = e2 < e1 ? e2 : e1;
+    hi = e1 < e2 ? e2 : e1;
+    if (pk0 > t1 && pk0 < t2) {
+      const double e = acc(pk0);
+      lo = e < lo ? e : lo;
+      hi = hi < e ? e : hi;
+    }
+    if (pk1 > t1 && pk1 < t2) {
+      const double e = acc(pk1);
+      lo = e < lo ? e : lo;
+      hi = hi < e ? e : hi;
+    }
+  }
+  AGFR_DEV double max_jerk_sq(double t1, double t2) const {
+    const double j1 = jerk(t1), j2 = jerk(t2);
+    const double s1 = j1 * j1, s2 = j2 * j2;
+    double m = s1 < s2 ? s2 : s1;
+    if (al != 0.0) {
+      const double tm = -be / al;
+      if (tm > t1 && tm < t2) {
+        const double j = jerk(tm);
+        const double s = j * j;
+        m = s < m ? m : s;
+      }
+    }
+    return m;
+  }
+};
+
+enum { IN_FEASIBLE = 0, IN_INDETERMINABLE = 1, IN_THRUST_HIGH = 2, IN_THRUST_LOW = 3, IN_SPLIT = -1 };
+
+struct Prim {
+  Axis ax[3];
+  double g[3];
+  double tf;
+  AGFR_DEV double thrust(double t) const {
+    const double x = ax[0].acc(t) - g[0], y = ax[1].acc(t) - g[1], z = ax[2].acc(t) - g[2];
+    return sqrt(x * x + y * y + z * z);
+  }
+  // one section of RapidTrajectoryGenerator::CheckInputFeasibilitySection (RapidTrajectoryGenerator.cpp:75-150)
+  AGFR_DEV int section(const PlanParams& P, double t1, double t2) const {
+    if (t2 - t1 < P.minSec) return IN_INDETERMINABLE;
+    const double f1 = thrust(t1), f2 = thrust(t2);
+    if ((f1 < f2 ? f2 : f1) > P.fmaxA) return IN_THRUST_HIGH;
+    if ((f2 < f1 ? f2 : f1) < P.fminA) return IN_THRUST_LOW;
+    double fminSqr = 0, fmaxSqr = 0, jmaxSqr = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      double amin, amax;
+      ax[i].minmax_acc(amin, amax, t1, t2);
+      const double v1 = amin - g[i];
+      const double v2 = amax - g[i];
+      const double s1 = v1 * v1, s2 = v2 * v2;
+      if ((s1 < s2 ? s2 : s1) > P.fmaxA * P.fmaxA) return IN_THRUST_HIGH;
+      const double f1a = fabs(v1), f2a = fabs(v2);
+      if (v1 * v2 < 0) {
+        fminSqr += 0;
+      } else {
+        const double m = f2a < f1a ? f2a : f1a;
+        fminSqr += m * m;
+      }
+      const double M = f1a < f2a ? f2a : f1a;
+      fmaxSqr += M * M;
+      jmaxSqr += ax[i].max_jerk_sq(t1, t2);
+    }
+    const double fmin = sqrt(fminSqr);
+    const double fmax = sqrt(fmaxSqr);
+    double wBound;
+    if (fminSqr > 1e-6)
+      wBound = sqrt(jmaxSqr / fminSqr);
+    else
+      wBound = DBL_MAX;
+    if (fmax < P.fminA) return IN_THRUST_LOW;
+    if (fmin > P.fmaxA) return IN_THRUST_HIGH;
+    if (fmin < P.fminA || fmax > P.fmaxA || wBound > P.wmaxA) return IN_SPLIT;
+    return IN_FEASIBLE;
+  }
+  // the recursion (:133-147) is a depth-first walk over halved sections that stops at the first section that is
+  // not feasible; the right halves still to visit are kept on a small stack
+  __device__ __noinline__ int input_feasibility(const PlanParams& P) const {
+    constexpr int kStack = 24;
+    double hi[kStack];
+    int sp = 0;
+    double t1 = 0, t2 = tf;
+    for (;;) {
+      const int r = section(P, t1, t2);
+      if (r == IN_SPLIT) {
+        if (sp >= kStack) return IN_INDETERMINABLE;
+        hi[sp++] = t2;            // right half [th, t2] later
+        t2 = (t1 + t2) / 2;       // left half first
+        continue;
+      }
+      if (r != IN_FEASIBLE) return r;
+      if (sp == 0) return IN_FEASIBLE;
+      t1 = t2;                    // the right sibling starts where this section ended (same value th)
+      t2 = hi[--sp];
+    }
+  }
+  // RapidTrajectoryGenerator::CheckVelocityFeasibility (:163-205): 0 feasible, 1 infeasible
+  template<bool PARITY>
+  __device__ __noinline__ int velocity_feasibility(double vmax) const {
+#pragma unroll 1
+    for (int dim = 0; dim < 3; dim++) {
+      const double c0 = ax[dim].al / 6.0, c1 = ax[dim].be / 2.0, c2 = ax[dim].ga / 1.0, c3 = ax[dim].a0;
+      double roots[5];
+      unsigned n;
+      if (fabs(c0) > 1e-6)
+        n = cubic<PARITY>(c1 / c0, c2 / c0, c3 / c0, roots);
+      else
+        return 1;
+      roots[n] = 0;
+      roots[n + 1] = tf;
+      for (unsigned i = 0; i < n + 2; i++) {
+        const double r = roots[i];
+        if (r < 0) continue;
+        if (r > tf) continue;
+        if (fabs(ax[0].vel(r)) >= vmax || fabs(ax[1].vel(r)) >= vmax || fabs(ax[2].vel(r)) >= vmax) return 1;
+      }
+    }
+    return 0;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp-uniform pieces of the collision test
+// ---------------------------------------------------------------------------------------------
+struct Poly {
+  double c[6][3];  // GetTrajectory(): t^5 first (RapidTrajectoryGenerator.hpp:232-241)
+  AGFR_DEV double axis(int i, double t) const {
+    return c[0][i] * t * t * t * t * t + c[1][i] * t * t * t * t + c[2][i] * t * t * t + c[3][i] * t * t + c[4][i] * t +
+           c[5][i];
+  }
+};
+struct Section {
+  double t0, t1;
+  bool inc;
+};
+
+struct WarpCtx {
+  const uint16_t* img;
+  const uint16_t* imgT;
+  double* pdepth;  // shared: [kMaxPyr] base-plane depths, ascending
+  int4* pedge;     // shared: [kMaxPyr] (right, top, left, bottom)
+  int npyr;
+  int lane;
+};
+
+AGFR_DEV unsigned ld16(const uint16_t* p) { return (unsigned)__ldg(p); }
+AGFR_DEV unsigned lanes_after(int src) { return 0xfffffffeu << src; }
+
+// DepthImagePlanner::InflatePyramid (DepthImagePlanner.cpp:456-970), warp cooperative.
+// The eight shrink regions share one scan routine; REGION selects geometry, trigger and update.
+struct Shrink {
+  int rS, lS, tS, bS;
+};
+enum { R_RIGHT = 0, R_LEFT, R_TOP, R_BOTTOM, R_TR, R_BR, R_TL, R_BL };
+
+template<int REGION>
+AGFR_DEV bool shrink_trigger(const Shrink& s, int num, int x, int y, int p) {
+  switch (REGION) {
+    case R_RIGHT: return num > (x - s.rS) * p;
+    case R_LEFT: return (s.lS - x) * p < num;
+    case R_TOP: return (s.tS - y) * p < num;
+    case R_BOTTOM: return num > (y - s.bS) * p;
+    case R_TR: return num > (x - s.rS) * p && (s.tS - y) * p < num;
+    case R_BR: return num > (x - s.rS) * p && num > (y - s.bS) * p;
+    case R_TL: return (s.lS - x) * p < num && (s.tS - y) * p < num;
+    default: return (s.lS - x) * p < num && num > (y - s.bS) * p;
+  }
+}
+// applies the update of one triggering pixel; false = "the pyramid cannot contain the sample point"
+template<int REGION>
+AGFR_DEV bool shrink_apply(Shrink& s, int num, int x, int y, int p, int x0, int y0) {
+  const int q = num / p;
+  const int rT = x - q, lT = x + q, tT = y + q, bT = y - q;
+  if (REGION == R_RIGHT || REGION == R_LEFT) {
+    const bool blocked = (REGION == R_RIGHT) ? (x0 > rT - kBuf) : (x0 < lT + kBuf);
+    if (!blocked) {
+      if (REGION == R_RIGHT) s.rS = rT; else s.lS = lT;
+      return true;
+    }
+    const bool noTop = y0 < tT + kBuf, noBot = y0 > bT - kBuf;
+    if (noTop && noBot) return false;
+    if (noTop) {
+      s.bS = bT;
+    } else if (noBot) {
+      s.tS = tT;
+    } else {
+      const int u = tT - s.tS, d = s.bS - bT;
+      if (d > u) {
+        s.tS = tT;
+      } else if (REGION == R_RIGHT) {
+        s.rS = bT;  // sic: the reference assigns the right edge here (DepthImagePlanner.cpp:648)
+      } else {
+        s.bS = bT;
+      }
+    }
+    return true;
+  }
+  if (REGION == R_TOP || REGION == R_BOTTOM) {
+    const bool blocked = (REGION == R_TOP) ? (y0 < tT + kBuf) : (y0 > bT - kBuf);
+    if (!blocked) {
+      if (REGION == R_TOP) s.tS = tT; else s.bS = bT;
+      return true;
+    }
+    const bool noRight = x0 > rT - kBuf, noLeft = x0 < lT + kBuf;
+    if (noRight && noLeft) return false;
+    if (noRight) {
+      s.lS = lT;
+    } else if (noLeft) {
+      s.rS = rT;
+    } else {
+      const int r = s.rS - rT, l = lT - s.lS;
+      if (r > l) s.lS = lT; else s.rS = rT;
+    }
+    return true;
+  }
+  // corners: one horizontal (right/left) and one vertical (top/bottom) edge compete
+  const bool isRight = (REGION == R_TR || REGION == R_BR), isTop = (REGION == R_TR || REGION == R_TL);
+  const bool noH = isRight ? (x0 > rT - kBuf) : (x0 < lT + kBuf);
+  const bool noV = isTop ? (y0 < tT + kBuf) : (y0 > bT - kBuf);
+  if (noH && noV) return false;
+  bool shrinkV;
+  if (noH) {
+    shrinkV = true;
+  } else if (noV) {
+    shrinkV = false;
+  } else {
+    const int hLoss = (isRight ? (s.rS - rT) : (lT - s.lS)) * (s.bS - s.tS);
+    const int vLoss = (isTop ? (tT - s.tS) : (s.bS - bT)) * (s.rS - s.lS);
+    shrinkV = hLoss > vLoss;
+  }
+  if (shrinkV) {
+    if (isTop) s.tS = tT; else s.bS = bT;
+  } else {
+    if (isRight) s.rS = rT; else s.lS = lT;
+  }
+  return true;
+}
+
+// scans one region in the reference's order.  outer: o = o0, o0+dO, .. (nOuter values); inner: i = i0 + dI*k, k < cnt
+template<int REGION>
+AGFR_DEV bool shrink_region(const PlanParams& P, const WarpCtx& w, Shrink& s, int maxDepth, int x0, int y0, int o0,
+                            int dO, int nOuter, int i0, int dI, int cnt) {
+  constexpr bool colWalk = (REGION == R_RIGHT || REGION == R_LEFT);  // outer x, inner y
+  for (int oc = 0; oc < nOuter; oc++) {
+    const int o = o0 + dO * oc;
+    const uint16_t* line = colWalk ? (w.imgT + (size_t)o * P.H) : (w.img + (size_t)o * P.W);
+    for (int base = 0; base < cnt; base += 32) {
+      const int k = base + w.lane;
+      const bool valid = k < cnt;
+      const int i = i0 + dI * k;
+      const int p = valid ? (int)ld16(line + i) : 0;
+      const bool pre = valid && p > P.ignore && p < maxDepth;
+      unsigned todo = __ballot_sync(AGFR_FULL, pre);
+      const int x = colWalk ? o : i, y = colWalk ? i : o;
+      while (todo) {
+        const bool trig = ((todo >> w.lane) & 1u) && shrink_trigger<REGION>(s, P.num, x, y, p);
+        const unsigned tm = __ballot_sync(AGFR_FULL, trig);
+        if (!tm) break;
+        const int src = __ffs(tm) - 1;
+        const int sx = __shfl_sync(AGFR_FULL, x, src), sy = __shfl_sync(AGFR_FULL, y, src),
+                  sp = __shfl_sync(AGFR_FULL, p, src);
+        if (!shrink_apply<REGION>(s, P.num, sx, sy, sp, x0, y0)) return false;
+        todo &= lanes_after(src);
+      }
+    }
+  }
+  return true;
+}
+
+// one line of the spiral expansion (DepthImagePlanner.cpp:521-597): returns true when a pixel nearer than the
+// pyramid's minimum depth blocks the side; folds the depths seen before it into maxDepth
+AGFR_DEV bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* line, int a, int b, int minPyr,
+                          int& maxDepth) {
+  unsigned mn = 65535u;
+  bool blocked = false;
+  for (int v0 = a; v0 <= b; v0 += 32) {
+    const int v = v0 + w.lane;
+    const bool valid = v <= b;
+    const int p = valid ? (int)ld16(line + v) : 0;
+    const bool sees = valid && p > P.ignore;
+    const bool blk = sees && p < minPyr;
+    const unsigned bm = __ballot_sync(AGFR_FULL, blk);
+    const unsigned before = bm ? ((1u << (__ffs(bm) - 1)) - 1u) : AGFR_FULL;
+    if (sees && !blk && ((before >> w.lane) & 1u)) mn = min(mn, (unsigned)p);
+    if (bm) {
+      blocked = true;
+      break;
+    }
+  }
+  mn = __reduce_min_sync(AGFR_FULL, mn);
+  if ((int)mn < maxDepth) maxDepth = (int)mn;
+  return blocked;
+}
+
+static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& w, int x0, int y0, double minimumDepth,
+                                     double& outDepth, int4& outEdge) {
+  const int W = P.W, H = P.H, edgeOff = P.edgeOff;
+  if (x0 <= edgeOff + kBuf + 1 || x0 > W - edgeOff - kBuf - 1 || y0 <= edgeOff + kBuf + 1 ||
+      y0 > H - edgeOff - kBuf - 1)
+    return false;
+  // uint16_t((minimumDepth + rPlan) / scale): x86 converts through int32 and keeps the low 16 bits
+  const int minPyr = (int)(uint16_t)(int)((minimumDepth + P.rPlan) / P.scale);
+  const double rD = P.f * P.rPlan / (P.scale * minPyr);
+  // double -> int: out-of-range is INT_MIN on x86 (cvttsd2si), saturating here; both fail the size test below
+  const int initR = (minPyr == 0) ? INT_MIN : (int)rD;
+  if (initR == INT_MIN || initR > (1 << 20)) return false;
+  if (2 * initR >= (W < H ? W : H) - 2 * edgeOff) return false;
+
+  int left, top, right, bottom;
+  if (y0 - initR < edgeOff) {
+    top = edgeOff;
+    bottom = top + 2 * initR;
+  } else {
+    bottom = min(H - edgeOff - 1, y0 + initR);
+    top = bottom - 2 * initR;
+  }
+  if (x0 - initR < edgeOff) {
+    left = edgeOff;
+    right = left + 2 * initR;
+  } else {
+    right = min(W - edgeOff - 1, x0 + initR);
+    left = right - 2 * initR;
+  }
+  // the initial rectangle must be free (:509-517; order independent)
+  {
+    bool bad = false;
+    for (int y = top; y < bottom; y++)
+      for (int xb = left; xb < right; xb += 32) {
+        const int x = xb + w.lane;
+        if (x < right) {
+          const int p = (int)ld16(w.img + (size_t)y * W + x);
+          bad |= (p <= minPyr && p > P.ignore);
+        }
+      }
+    if (__any_sync(AGFR_FULL, bad)) return false;
+  }
+  // spiral expansion (:519-599)
+  int maxDepth = 65535;
+  bool rf = true, tf = true, lf = true, bf = true;
+  while (rf || tf || lf || bf) {
+    if (rf) {
+      if (right < W - edgeOff - 1) {
+        if (expand_line(P, w, w.imgT + (size_t)(right + 1) * H, top, bottom, minPyr, maxDepth)) {
+          rf = false;
+          right--;
+        }
+        right++;
+      } else {
+        rf = false;
+      }
+    }
+    if (tf) {
+      if (top > edgeOff) {
+        if (expand_line(P, w, w.img + (size_t)(top - 1) * W, left, right, minPyr, maxDepth)) {
+          tf = false;
+          top++;
+        }
+        top--;
+      } else {
+        tf = false;
+      }
+    }
+    if (lf) {
+      if (left > edgeOff) {
+        if (expand_line(P, w, w.imgT + (size_t)(left - 1) * H, top, bottom, minPyr, maxDepth)) {
+          lf = false;
+          left++;
+        }
+        left--;
+      } else {
+        lf = false;
+      }
+    }
+    if (bf) {
+      if (bottom < H - edgeOff - 1) {
+        if (expand_line(P, w, w.img + (size_t)(bottom + 1) * W, left, right, minPyr, maxDepth)) {
+          bf = false;
+          bottom--;
+        }
+        bottom++;
+      } else {
+        bf = false;
+      }
+    }
+  }
+  // shrink by the projected vehicle radius (:601-939)
+  Shrink s;
+  s.rS = W - 1 - edgeOff;
+  s.lS = edgeOff;
+  s.tS = edgeOff;
+  s.bS = H - 1 - edgeOff;
+  const int rows = bottom - top + 1, cols = right - left + 1;
+  if (!shrink_region<R_RIGHT>(P, w, s, maxDepth, x0, y0, right, 1, W - right, top, 1, rows)) return false;
+  if (!shrink_region<R_LEFT>(P, w, s, maxDepth, x0, y0, left, -1, left + 1, top, 1, rows)) return false;
+  if (s.lS + kBuf > s.rS - kBuf) return false;
+  if (!shrink_region<R_TOP>(P, w, s, maxDepth, x0, y0, top, -1, top + 1, left, 1, cols)) return false;
+  if (!shrink_region<R_BOTTOM>(P, w, s, maxDepth, x0, y0, bottom, 1, H - bottom, left, 1, cols)) return false;
+  if (s.tS + kBuf > s.bS - kBuf) return false;
+  if (!shrink_region<R_TR>(P, w, s, maxDepth, x0, y0, top, -1, top + 1, right, 1, W - right)) return false;
+  if (!shrink_region<R_BR>(P, w, s, maxDepth, x0, y0, bottom, 1, H - bottom, right, 1, W - right)) return false;
+  if (!shrink_region<R_TL>(P, w, s, maxDepth, x0, y0, top, -1, top + 1, left, -1, left + 1)) return false;
+  if (!shrink_region<R_BL>(P, w, s, maxDepth, x0, y0, bottom, 1, H - bottom, left, -1, left + 1)) return false;
+  outDepth = maxDepth * P.scale - P.rPlan;
+  outEdge = make_int4(s.rS, s.tS, s.lS, s.bS);
+  return true;
+}
+
+// corner `k` of a pyramid (top right, top left, bottom left, bottom right; DepthImagePlanner.cpp:945-957)
+AGFR_DEV void pyr_corner(const PlanParams& P, double depth, const int4& e, int k, double* c) {
+  const int ex = (k == 0 || k == 3) ? e.x : e.z;  // right : left
+  const int ey = (k < 2) ? e.y : e.w;             // top : bottom
+  c[0] = depth * (((double)ex - P.cx) / P.f);
+  c[1] = depth * (((double)ey - P.cy) / P.f);
+  c[2] = depth * 1;
+}
+// unit normal of lateral face `f` (Pyramid.hpp:55-58; the norm is truncated to float, Vec3.hpp:126-129)
+AGFR_DEV void pyr_normal(const PlanParams& P, double depth, const int4& e, int f, double* n) {
+  double a[3], b[3];
+  pyr_corner(P, depth, e, f, a);
+  pyr_corner(P, depth, e, (f + 1) & 3, b);
+  const double x = a[1] * b[2] - a[2] * b[1];
+  const double y = a[2] * b[0] - a[0] * b[2];
+  const double z = a[0] * b[1] - a[1] * b[0];
+  const float nrm = (float)sqrt(x * x + y * y + z * z);
+  n[0] = x / nrm;
+  n[1] = y / nrm;
+  n[2] = z / nrm;
+}
+
+AGFR_DEV Section make_section(const Poly& Q, double t0, double t1) {
+  Section s;
+  s.t0 = t0;
+  s.t1 = t1;
+  s.inc = Q.axis(2, t0) < Q.axis(2, t1);
+  return s;
+}
+AGFR_DEV double deepest(const Poly& Q, const Section& s) { return Q.axis(2, s.inc ? s.t1 : s.t0); }
+
+// DepthImagePlanner::IsCollisionFree (DepthImagePlanner.cpp:216-301) for one candidate; all lanes hold the same Q
+template<bool PARITY>
+__device__ __noinline__ bool collision_free(const PlanParams& P, WarpCtx& w, const Poly& Q, double tEnd) {
+  // sections of monotonic depth (:303-354)
+  Section st[8];
+  int ns = 0;
+  {
+    double d[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) d[i] = (5 - i) * Q.c[i][2];
+    double roots[6];
+    roots[0] = 0.0;
+    roots[1] = tEnd;
+    const unsigned n = poly_roots<PARITY>(d, roots + 2);
+    const int m = (int)n + 2;
+    for (int i = 1; i < m; i++) {  // ascending
+      const double kx = roots[i];
+      int j = i - 1;
+      while (j >= 0 && kx < roots[j]) {
+        roots[j + 1] = roots[j];
+        j--;
+      }
+      roots[j + 1] = kx;
+    }
+    for (unsigned i = 0; i < n + 1; i++) {
+      if (roots[i] < 0.0) continue;
+      if (fabs(roots[i] - roots[i + 1]) < 1e-6) continue;
+      if (roots[i] >= tEnd) break;
+      if (roots[i + 1] <= tEnd)
+        st[ns++] = make_section(Q, roots[i], roots[i + 1]);
+      else
+        break;
+    }
+    // std::sort by deepest point == stable insertion sort at this size (ties are the rule: neighbours share a turning point)
+    for (int i = 1; i < ns; i++) {
+      const Section kx = st[i];
+      const double kd = deepest(Q, kx);
+      int j = i - 1;
+      while (j >= 0 && kd < deepest(Q, st[j])) {
+        st[j + 1] = st[j];
+        j--;
+      }
+      st[j + 1] = kx;
+    }
+  }
+  while (ns > 0) {
+    const Section s = st[--ns];
+    const double ts = s.inc ? s.t0 : s.t1, te = s.inc ? s.t1 : s.t0;
+    const double startZ = Q.axis(2, ts);
+    const double ex = Q.axis(0, te), ey = Q.axis(1, te), ez = Q.axis(2, te);
+    if (startZ < P.minDist && ez < P.minDist) continue;
+    const double px = ex * P.f / ez + P.cx;
+    const double py = ey * P.f / ez + P.cy;
+    // FindContainingPyramid (:356-380): first pyramid in depth order, not shallower than the point, that contains it
+    double pdepth;
+    int4 pedge;
+    {
+      bool ok = false;
+      if (w.lane < w.npyr) {
+        const double d = w.pdepth[w.lane];
+        const int4 e = w.pedge[w.lane];
+        ok = !(d < ez) && (e.z + kBuf < px) && (px < e.x - kBuf) && (e.y + kBuf < py) && (py < e.w - kBuf);
+      }
+      const unsigned hit = __ballot_sync(AGFR_FULL, ok);
+      if (hit) {
+        const int idx = __ffs(hit) - 1;
+        pdepth = w.pdepth[idx];
+        pedge = w.pedge[idx];
+      } else {
+        if (w.npyr >= P.maxPyr) return false;
+        // (int) of a double: the values reaching here are finite and small (the end point is deeper than minDist)
+        if (!inflate(P, w, (int)px, (int)py, ez, pdepth, pedge)) return false;
+        // insert in depth order (std::lower_bound on the new depth, :267-269)
+        bool less = false;
+        double d = 0;
+        int4 e = make_int4(0, 0, 0, 0);
+        if (w.lane < w.npyr) {
+          d = w.pdepth[w.lane];
+          e = w.pedge[w.lane];
+          less = d < pdepth;
+        }
+        const int pos = __popc(__ballot_sync(AGFR_FULL, less));
+        __syncwarp();
+        if (w.lane < w.npyr && w.lane >= pos) {
+          w.pdepth[w.lane + 1] = d;
+          w.pedge[w.lane + 1] = e;
+        }
+        if (w.lane == 0) {
+          w.pdepth[pos] = pdepth;
+          w.pedge[pos] = pedge;
+        }
+        w.npyr++;
+        __syncwarp();
+      }
+    }
+    // FindDeepestCollisionTime (:382-454): lateral face (lane & 3); the deepest crossing over the four faces is
+    // the latest (increasing depth) or the earliest (decreasing depth) one inside the section
+    double nrm[3];
+    pyr_normal(P, pdepth, pedge, w.lane & 3, nrm);
+    double c[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dim = 0; dim < 3; dim++)
+#pragma unroll
+      for (int k = 0; k < 5; k++) c[k] += nrm[dim] * Q.c[k][dim];
+    double roots[4];
+    const unsigned n = poly_roots<PARITY>(c, roots);
+    double tc = s.inc ? s.t0 : s.t1;
+    bool hit = false;
+    for (unsigned i = 0; i < n; i++) {
+      const double r = roots[i];
+      if (s.inc) {
+        if (!(r > s.t1) && r > s.t0 && r > tc) {
+          tc = r;
+          hit = true;
+        }
+      } else {
+        if (!(r < s.t0) && r < s.t1 && r < tc) {
+          tc = r;
+          hit = true;
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+      const double o = __shfl_xor_sync(AGFR_FULL, tc, off);
+      tc = s.inc ? (o > tc ? o : tc) : (o < tc ? o : tc);
+    }
+    hit = __any_sync(AGFR_FULL, hit);
+    if (hit) {
+      if (s.inc)
+        st[ns++] = make_section(Q, s.t0, tc);
+      else
+        st[ns++] = make_section(Q, tc, s.t1);
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel: one warp per vehicle, vehicles handed out through a counter
+// ---------------------------------------------------------------------------------------------
+template<bool PARITY>
+__global__ void __launch_bounds__(kBlock) rappids_plan_kernel(const __grid_constant__ PlanParams P) {
+  __shared__ double s_depth[kWarps][kMaxPyr + 1];
+  __shared__ int4 s_edge[kWarps][kMaxPyr + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  WarpCtx w;
+  w.lane = lane;
+  w.pdepth = s_depth[wid];
+  w.pedge = s_edge[wid];
+  for (;;) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(P.next, 1);
+    v = __shfl_sync(AGFR_FULL, v, 0);
+    if (v >= P.n) break;
+    w.img = P.img + (size_t)v * P.W * P.H;
+    w.imgT = P.imgT + (size_t)v * P.W * P.H;
+    w.npyr = 0;
+    const double* st = P.state + (size_t)v * 12;
+    Prim pr;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      pr.ax[a].v0 = __ldg(st + a);
+      pr.ax[a].a0 = __ldg(st + 3 + a);
+      pr.g[a] = __ldg(st + 6 + a);
+    }
+    const double cv0 = __ldg(st + 9), cv1 = __ldg(st + 10), cv2 = __ldg(st + 11);
+    const double sg = sqrt((cv0 - 0) * (cv0 - 0) + (cv1 - 0) * (cv1 - 0) + (cv2 - 0) * (cv2 - 0));
+
+    double best = DBL_MAX;
+    int found = 0, bestIdx = -1, nCost = 0, nColl = 0, nVel = 0, nFree = 0;
+    Poly bestQ;
+    double bestT = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+      for (int a = 0; a < 3; a++) bestQ.c[k][a] = 0;
+
+    for (int i0 = 0; i0 < P.k; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < P.k;
+      double goal[3] = {0, 0, 1}, T = 1;
+      if (valid) {
+        const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + i) * 4);
+        goal[0] = c4.x;
+        goal[1] = c4.y;
+        goal[2] = c4.z;
+        T = c4.w;
+      }
+      pr.tf = T;
+#pragma unroll
+      for (int a = 0; a < 3; a++) pr.ax[a].generate(goal[a], T);
+      const double pe0 = pr.ax[0].pos(T), pe1 = pr.ax[1].pos(T), pe2 = pr.ax[2].pos(T);
+      double cost;
+      if (P.costKind == 0) {
+        cost = -(cv0 * pe0 + cv1 * pe1 + cv2 * pe2) / T;
+      } else {
+        const double dx = cv0 - pe0, dy = cv1 - pe1, dz = cv2 - pe2;
+        cost = -(sg - sqrt(dx * dx + dy * dy + dz * dz)) / T;
+      }
+      // speculative feasibility for the lanes that beat the best cost so far (it can only get lower)
+      const bool low0 = valid && cost < best;
+      int inRes = -2, velRes = -2;
+      if (low0) {
+        inRes = pr.input_feasibility(P);
+        if (inRes == IN_FEASIBLE) velRes = pr.template velocity_feasibility<PARITY>(P.vmax);
+      }
+      unsigned pend = __ballot_sync(AGFR_FULL, low0);
+      unsigned flag = 0;
+      while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const double csrc = __shfl_sync(AGFR_FULL, cost, src);
+        if (!(csrc < best)) continue;
+        unsigned f = 1;  // LowCost
+        nCost++;
+        const int ir = __shfl_sync(AGFR_FULL, inRes, src), vr = __shfl_sync(AGFR_FULL, velRes, src);
+        if (ir == IN_FEASIBLE) {
+          f |= 2;
+          nColl++;
+          if (vr == 0) {
+            f |= 4;
+            nVel++;
+            Poly Q;
+            const double Ts = __shfl_sync(AGFR_FULL, T, src);
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+              const double al = __shfl_sync(AGFR_FULL, pr.ax[a].al, src), be = __shfl_sync(AGFR_FULL, pr.ax[a].be, src),
+                           ga = __shfl_sync(AGFR_FULL, pr.ax[a].ga, src);
+              Axis ax = pr.ax[a];  // v0, a0 are the vehicle's
+              ax.al = al;
+              ax.be = be;
+              ax.ga = ga;
+              Q.c[0][a] = al / 120;
+              Q.c[1][a] = be / 24;
+              Q.c[2][a] = ga / 6;
+              Q.c[3][a] = ax.acc(0.0) / 2;
+              Q.c[4][a] = ax.vel(0.0);
+              Q.c[5][a] = ax.pos(0.0);
+            }
+            if (collision_free<PARITY>(P, w, Q, Ts)) {
+              f |= 8;
+              found = 1;
+              best = csrc;
+              nFree++;
+              bestIdx = i0 + src;
+              bestQ = Q;
+              bestT = Ts;
+            }
+          }
+        }
+        if (lane == src) flag = f;
+      }
+      if (valid) P.flags[(size_t)v * P.kcap + i] = (uint8_t)flag;
+    }
+    // results
+    ResultRec* out = reinterpret_cast<ResultRec*>(P.results) + v;
+    if (lane == 0) {
+      out->found = found;
+      out->best_index = bestIdx;
+      out->n_generated = P.k;
+      out->n_cost_checks = nCost;
+      out->n_collision_checks = nColl;
+      out->n_velocity_checks = nVel;
+      out->n_collision_free = nFree;
+      out->n_pyramids = w.npyr;
+      out->best_cost = best;
+      out->best_tf = bestT;
+    }
+    if (lane < 18) out->best_coeffs[lane] = bestQ.c[lane / 3][lane % 3];
+    {
+      double* rec = P.pyramids + ((size_t)v * kMaxPyr + lane) * 17;
+      if (lane < w.npyr) {
+        const double d = w.pdepth[lane];
+        const int4 e = w.pedge[lane];
+        rec[0] = d;
+        rec[1] = e.x;
+        rec[2] = e.y;
+        rec[3] = e.z;
+        rec[4] = e.w;
+        for (int f = 0; f < 4; f++) pyr_normal(P, d, e, f, rec + 5 + 3 * f);
+      } else {
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        for (int q = 0; q < 17; q++) rec[q] = nanv;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace agfr

@@ -151,3 +151,82 @@ def offboard_scenario(nticks=4000):
     return dict(name="offboard", quad_type=5, vehicle_id=1, motor_time_const=0.015, motor_inertia=0.0,
                 pos=(0.0, 0.0, 0.0), att=(1.0, 0.0, 0.0, 0.0), anchors=[], uwb_comm_period=0.0, sched=[],
                 targets=targets, nticks=nticks)
+
+
+# ---------------------------------------------------------------------------------------------
+# RAPPIDS planner workloads: synthetic depth scenes + planner initial states
+# ---------------------------------------------------------------------------------------------
+RAPPIDS_DEPTH_SCALE = 10.0 / 256.0   # Simulator/Rappids_Simulator/main.cpp:121-122
+RAPPIDS_MAX_BOXES = 4
+
+
+def rappids_population(n, seed=2024, width=320, height=240, camera_height=1.5, first=0, speed_max=2.0,
+                       acc_max=0.5, box_depth=(1.5, 4.0), n_boxes=(1, 3)):
+    """Scene descriptions and initial states of vehicles first .. first+n-1 of a population (independent of the
+    sharding: every vehicle draws from its own Philox stream).
+
+    Scene: background at 8 m, a floor band below the horizon (camera `camera_height` above a flat floor),
+    1-3 axis-aligned boxes at 1.5-4 m.  Returned as integer data so that host (numpy) and device rasterisers
+    produce identical images:
+      row_bg  [n, height] uint16   background/floor pixel value of every image row
+      boxes   [n, RAPPIDS_MAX_BOXES, 5] int32  (x0, x1, y0, y1, value), x1/y1 exclusive, value 0 = unused
+    State in the camera frame (x right, y down, z forward; Rappids_Simulator main.cpp:491-497):
+      vel0 forward 0-2 m/s with a small lateral part, acc0 small, grav = 9.81 m/s^2 along +y tilted by up to 5 deg.
+    """
+    f = width / 2.0
+    row_bg = np.zeros((n, height), dtype=np.uint16)
+    boxes = np.zeros((n, RAPPIDS_MAX_BOXES, 5), dtype=np.int32)
+    vel0 = np.zeros((n, 3))
+    acc0 = np.zeros((n, 3))
+    grav = np.zeros((n, 3))
+    ys = np.arange(height)
+    for i in range(n):
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, first + i]))
+        h = camera_height * rng.uniform(0.8, 1.2)
+        with np.errstate(divide="ignore"):
+            floor = np.where(ys > height / 2.0, h * f / np.maximum(ys - height / 2.0, 1e-9), np.inf)
+        depth = np.minimum(8.0, floor)
+        row_bg[i] = np.floor(depth / RAPPIDS_DEPTH_SCALE).astype(np.uint16)
+        nb = int(rng.integers(n_boxes[0], n_boxes[1] + 1))
+        for b in range(nb):
+            d = rng.uniform(box_depth[0], box_depth[1])
+            w = int(rng.integers(width // 16, width // 4))
+            hh = int(rng.integers(height // 8, height // 2))
+            x0 = int(rng.integers(0, width - w))
+            y0 = int(rng.integers(0, height - hh))
+            boxes[i, b] = (x0, x0 + w, y0, y0 + hh, int(d / RAPPIDS_DEPTH_SCALE))
+        vel0[i] = (rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), rng.uniform(0.0, speed_max))
+        acc0[i] = rng.uniform(-acc_max, acc_max, size=3)
+        tilt = np.deg2rad(rng.uniform(-5.0, 5.0, size=2))
+        grav[i] = 9.81 * np.array([np.sin(tilt[0]), np.cos(tilt[0]) * np.cos(tilt[1]), np.sin(tilt[1])])
+    return dict(row_bg=row_bg, boxes=boxes, vel0=vel0, acc0=acc0, grav=grav, width=width, height=height)
+
+
+def rappids_render(row_bg, boxes, width):
+    """Host rasteriser of a scene description: pixel = min(row background, values of the boxes covering it)."""
+    n, height = row_bg.shape
+    img = np.repeat(row_bg[:, :, None], width, axis=2).astype(np.uint16)
+    for i in range(n):
+        for x0, x1, y0, y1, v in boxes[i]:
+            if v > 0:
+                img[i, y0:y1, x0:x1] = np.minimum(img[i, y0:y1, x0:x1], np.uint16(v))
+    return img
+
+
+def rappids_candidates(n, k, seed=77, width=320, height=240, first=0):
+    """[n, k, 4] candidate end points (camera frame) + durations drawn like the reference's
+    RandomTrajectoryGenerator (DepthImagePlanner.hpp:334-352: pixel in the central 80 % of the image, depth
+    1.5-3 m, duration 2-3 s), from numpy's Philox (the population generator; the parity tests also use the
+    reference's own std::mt19937 draws)."""
+    out = np.zeros((n, k, 4))
+    f = width / 2.0
+    for i in range(n):
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 1, first + i]))
+        px = rng.uniform(0.1 * width, 0.9 * width, size=k)
+        py = rng.uniform(0.1 * height, 0.9 * height, size=k)
+        d = rng.uniform(1.5, 3.0, size=k)
+        out[i, :, 0] = d * ((px - width / 2.0) / f)
+        out[i, :, 1] = d * ((py - height / 2.0) / f)
+        out[i, :, 2] = d * 1
+        out[i, :, 3] = rng.uniform(2.0, 3.0, size=k)
+    return out
