@@ -13,9 +13,12 @@ GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
 
 
 def header_functions():
-    src = open(os.path.join(ROOT, "include", "agrifly_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(agf_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in ("agrifly_b200.h", "agrifly_b200_rappids.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(agf_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol(agf):
