@@ -30,6 +30,34 @@ def offboard_cfg(quad_type=5, **edits):
     return c
 
 
+def offboard_ref(kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=0):
+    r = abi.OffboardRef(kind=int(kind), traj_id=int(traj_id), start_us=int(start_us), stop_us=int(stop_us),
+                        desired_yaw=float(desired_yaw))
+    r.desired_pos[:] = [float(x) for x in desired_pos]
+    return r
+
+
+def primitive_record(pf, T, p0=(0, 0, 0), v0=(0, 0, 0), a0=(0, 0, 0), grav=(0.0, 0.0, -9.81), att=(1.0, 0.0, 0.0, 0.0),
+                     offset=(0.0, 0.0, 0.0)):
+    """AGF_OFFTRAJ_DOUBLES record of the minimum-jerk primitive from (p0, v0, a0) to rest at pf in T seconds
+    (fully defined end state: SingleAxisTrajectory.cpp:59-103 with position, velocity and acceleration goals)."""
+    rec = np.zeros(abi.OFFTRAJ_DOUBLES)
+    for a in range(3):
+        dp = pf[a] - p0[a] - v0[a] * T - 0.5 * a0[a] * T * T
+        dv = 0.0 - v0[a] - a0[a] * T
+        da = 0.0 - a0[a]
+        T2, T3, T4, T5 = T * T, T ** 3, T ** 4, T ** 5
+        alpha = (60 * T2 * da - 360 * T * dv + 720 * dp) / T5
+        beta = (-24 * T3 * da + 168 * T2 * dv - 360 * T * dp) / T5
+        gamma = (3 * T4 * da - 24 * T3 * dv + 60 * T2 * dp) / T5
+        rec[6 * a:6 * a + 6] = [p0[a], v0[a], a0[a], alpha, beta, gamma]
+    rec[18:21] = grav
+    rec[21] = T
+    rec[22:26] = att
+    rec[26:29] = offset
+    return rec
+
+
 class AgfError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("agrifly_b200 error %d: %s" % (code, msg))
@@ -280,6 +308,25 @@ class Batch:
         off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64).reshape(self.n, 3)
         _check(self.L.agf_batch_set_offboard_loop(self.h, C.byref(cfg), tarr, len(targets),
                                                   None if off is None else off.ctypes.data))
+
+    def set_offboard_reference(self, kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=0):
+        """Reference generator of the offboard loop (agrifly_b200.h): abi.OFFREF_STAGES (flight stages of the ROS
+        rates-control node) or abi.OFFREF_TRAJECTORY (tracking of per-vehicle motion primitives); None: targets."""
+        if kind is None:
+            _check(self.L.agf_batch_set_offboard_reference(self.h, None))
+            return
+        _check(self.L.agf_batch_set_offboard_reference(self.h, C.byref(offboard_ref(kind, start_us, stop_us, desired_pos,
+                                                                                   desired_yaw, traj_id))))
+
+    def set_offboard_trajectories(self, traj, first=0):
+        t = np.ascontiguousarray(traj, dtype=np.float64).reshape(-1, abi.OFFTRAJ_DOUBLES)
+        _check(self.L.agf_batch_set_offboard_trajectories(self.h, t.ctypes.data, first, len(t)))
+
+    def offboard_state(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty((count, abi.OFFSTATE_DOUBLES))
+        _check(self.L.agf_batch_get_offboard_state(self.h, out.ctypes.data, first, count))
+        return out
 
     def add_anchor(self, id_, pos):
         _check(self.L.agf_batch_add_uwb_anchor(self.h, id_, _f3(pos)))

@@ -96,6 +96,16 @@ class OffboardTarget(C.Structure):
     _fields_ = [("time_us", C.c_uint64), ("pos", C.c_double * 3)]
 
 
+OFFREF_TARGETS, OFFREF_STAGES, OFFREF_TRAJECTORY = 0, 1, 2
+STAGE_WAIT_FOR_START, STAGE_SPOOL_UP, STAGE_TAKEOFF, STAGE_FLIGHT, STAGE_LANDING, STAGE_COMPLETE = range(6)
+OFFTRAJ_DOUBLES, OFFSTATE_DOUBLES = 29, 16
+
+
+class OffboardRef(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("traj_id", C.c_int32), ("start_us", C.c_uint64), ("stop_us", C.c_uint64),
+                ("desired_pos", C.c_double * 3), ("desired_yaw", C.c_double)]
+
+
 # ---- include/agrifly_b200_rappids.h ------------------------------------------------------------
 RAPPIDS_MAX_PYRAMIDS = 32
 RAPPIDS_PYRAMID_DOUBLES = 17
@@ -177,6 +187,9 @@ PROTOTYPES = {
     "agf_batch_set_cmd_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "agf_offboard_cfg_default": (C.c_int, [C.c_int, _P(OffboardCfg)]),
     "agf_batch_set_offboard_loop": (C.c_int, [C.c_void_p, _P(OffboardCfg), _P(OffboardTarget), C.c_size_t, C.c_void_p]),
+    "agf_batch_set_offboard_reference": (C.c_int, [C.c_void_p, _P(OffboardRef)]),
+    "agf_batch_set_offboard_trajectories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_batch_get_offboard_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_get_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_set_external_wrench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_add_uwb_anchor": (C.c_int, [C.c_void_p, C.c_uint8, _P(C.c_float)]),

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <limits>
 #include <mutex>
 #include <new>
 #include <string>
@@ -315,6 +316,9 @@ struct Batch {
   virtual int log_ptr(void** p, size_t* es) = 0;
   virtual int stats(const double* target, double* dev_out) = 0;
   virtual int set_offboard(const agf_offboard_cfg* cfg, const agf_offboard_target* targets, size_t n_targets, const double* offsets) = 0;
+  virtual int set_offboard_ref(const agf_offboard_ref* ref) = 0;
+  virtual int set_offboard_traj(const double* traj, size_t first, size_t count) = 0;
+  virtual int get_offboard_state(double* out, size_t first, size_t count) = 0;
 
   size_t n = 0;
   agf_batch_opts opts;
@@ -380,6 +384,9 @@ struct BatchImpl : Batch {
   double* d_target = nullptr;
   agf_offboard_target* d_off_targets = nullptr;
   double* d_off_offsets = nullptr;
+  uint64_t first_target_us = 0;
+  double* d_off_state = nullptr;  // [AGF_OFFSTATE_DOUBLES][n]
+  double* d_off_traj = nullptr;   // [AGF_OFFTRAJ_DOUBLES][n]
 
   StepShared<P> sh;
   PlantPV<P> pv_shared;
@@ -394,7 +401,7 @@ struct BatchImpl : Batch {
     cudaSetDevice(opts.device);
     cudaFree(st.sp); cudaFree(st.sf); cudaFree(st.su); cudaFree(st.sc);
     cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter); cudaFree(d_flags);
-    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(st.sq);
+    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(d_off_state); cudaFree(d_off_traj); cudaFree(st.sq);
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
     for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -680,12 +687,85 @@ struct BatchImpl : Batch {
     off.targets = d_off_targets;
     off.n_targets = uint32_t(n_targets);
     off.offsets = d_off_offsets;
+    // the reference generator survives a change of the loop parameters
+    off.ref_kind = sh.off.ref_kind; off.traj_id = sh.off.traj_id;
+    off.start_us = sh.off.start_us; off.stop_us = sh.off.stop_us;
+    for (int k = 0; k < 3; k++) off.desired[k] = sh.off.desired[k];
+    off.desired_yaw = sh.off.desired_yaw;
+    off.state = d_off_state;
+    off.traj = d_off_traj;
     sh.off = off;
     sh.tc = tc;
-    sh.tc.off_first_target_us = targets[0].time_us;
+    sh.tc.off_first_target_us = off.ref_kind == AGF_OFFREF_TARGETS ? targets[0].time_us : 0;
+    first_target_us = targets[0].time_us;
     if (!was_on) {  // the loop's Timer and queue are created now (Timer::Timer resets to the current clock reading)
       ts.off_age = ts.off_head = ts.off_count = 0;
       memset(ts.off_wait, 0, sizeof(ts.off_wait));
+    }
+    return AGF_OK;
+  }
+
+  int set_offboard_ref(const agf_offboard_ref* ref) override {
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    if (!sh.tc.off_enabled) return fail(AGF_EINVAL, "set the offboard loop (agf_batch_set_offboard_loop) before its reference generator");
+    if (!ref || ref->kind == AGF_OFFREF_TARGETS) {
+      sh.off.ref_kind = AGF_OFFREF_TARGETS;
+      sh.tc.off_first_target_us = first_target_us;
+      return AGF_OK;
+    }
+    if (ref->kind != AGF_OFFREF_STAGES && ref->kind != AGF_OFFREF_TRAJECTORY) return fail(AGF_EINVAL, "unknown reference generator");
+    if (ref->kind == AGF_OFFREF_STAGES && (ref->traj_id < 0 || ref->traj_id > 5)) return fail(AGF_EINVAL, "traj_id must be 0..5");
+    if (ref->kind == AGF_OFFREF_TRAJECTORY && !d_off_traj) return fail(AGF_EINVAL, "set the trajectories (agf_batch_set_offboard_trajectories) first");
+    if (ref->kind == AGF_OFFREF_STAGES) {  // a fresh state machine (ExampleVehicleStateMachine.cpp:10-19; Vec3d members are NaN)
+      std::vector<double> h(size_t(AGF_OFFSTATE_DOUBLES) * n, std::numeric_limits<double>::quiet_NaN());
+      for (size_t i = 0; i < n; i++) {
+        h[0 * n + i] = AGF_STAGE_WAIT_FOR_START;
+        h[1 * n + i] = AGF_STAGE_COMPLETE;
+        h[2 * n + i] = double(now_us);
+        h[15 * n + i] = 0.0;
+      }
+      if (!d_off_state) AGF_CUDA(cudaMalloc(&d_off_state, h.size() * sizeof(double)));
+      AGF_CUDA(cudaMemcpy(d_off_state, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    sh.off.ref_kind = ref->kind;
+    sh.off.traj_id = ref->traj_id;
+    sh.off.start_us = ref->start_us;
+    sh.off.stop_us = ref->stop_us;
+    for (int k = 0; k < 3; k++) sh.off.desired[k] = ref->desired_pos[k];
+    sh.off.desired_yaw = ref->desired_yaw;
+    sh.off.state = d_off_state;
+    sh.off.traj = d_off_traj;
+    sh.tc.off_first_target_us = 0;
+    return AGF_OK;
+  }
+  int set_offboard_traj(const double* traj, size_t first, size_t count) override {
+    if (!traj) return fail(AGF_EINVAL, "null trajectory array");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    if (!d_off_traj) {
+      AGF_CUDA(cudaMalloc(&d_off_traj, size_t(AGF_OFFTRAJ_DOUBLES) * n * sizeof(double)));
+      AGF_CUDA(cudaMemset(d_off_traj, 0, size_t(AGF_OFFTRAJ_DOUBLES) * n * sizeof(double)));
+      sh.off.traj = d_off_traj;
+    }
+    std::vector<double> col(count);
+    for (int k = 0; k < AGF_OFFTRAJ_DOUBLES; k++) {  // AoS in, [field][vehicle] on the device
+      for (size_t i = 0; i < count; i++) col[i] = traj[i * AGF_OFFTRAJ_DOUBLES + k];
+      AGF_CUDA(cudaMemcpy(d_off_traj + size_t(k) * n + first, col.data(), count * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return AGF_OK;
+  }
+  int get_offboard_state(double* out, size_t first, size_t count) override {
+    if (!out) return fail(AGF_EINVAL, "null output");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!d_off_state) return fail(AGF_EINVAL, "no stage reference generator is set");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    std::vector<double> col(count);
+    for (int k = 0; k < AGF_OFFSTATE_DOUBLES; k++) {
+      AGF_CUDA(cudaMemcpy(col.data(), d_off_state + size_t(k) * n + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < count; i++) out[i * AGF_OFFSTATE_DOUBLES + k] = col[i];
     }
     return AGF_OK;
   }
@@ -1092,6 +1172,15 @@ int agf_offboard_cfg_default(int quad_type, agf_offboard_cfg* out) {
   out->min_proper_acc = -1;
   out->yaw_angle = 0;
   return AGF_OK;
+}
+int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref) {
+  return b ? B(b)->set_offboard_ref(ref) : fail(AGF_EINVAL, "null handle");
+}
+int agf_batch_set_offboard_trajectories(agf_batch* b, const double* traj, size_t first, size_t count) {
+  return b ? B(b)->set_offboard_traj(traj, first, count) : fail(AGF_EINVAL, "null handle");
+}
+int agf_batch_get_offboard_state(agf_batch* b, double* out, size_t first, size_t count) {
+  return b ? B(b)->get_offboard_state(out, first, count) : fail(AGF_EINVAL, "null handle");
 }
 int agf_batch_set_offboard_loop(agf_batch* b, const agf_offboard_cfg* cfg, const agf_offboard_target* targets, size_t n_targets,
                                 const double* per_vehicle_offset) {

@@ -21,18 +21,9 @@ __global__ void offboard_generate_kernel(StateArrays<P> st, size_t n, OffboardPa
   P r[12];
 #pragma unroll
   for (int q = 0; q < 12 / VP; q++) VecOf<P>::unpack(st.sp[size_t(q) * n + i], &r[q * VP]);  // pos3 vel3 att4 (+2)
-  uint32_t ti = 0;
-  for (uint32_t j = 1; j < off.n_targets; j++)
-    if (off.targets[j].time_us <= t_gen_us) ti = j;
-  double des[3] = {off.targets[ti].pos[0], off.targets[ti].pos[1], off.targets[ti].pos[2]};
-  if (off.offsets) {
-    des[0] = des[0] + off.offsets[i];
-    des[1] = des[1] + off.offsets[n + i];
-    des[2] = des[2] + off.offsets[2 * n + i];
-  }
   const V3<P> cp(r[SP_POS], r[SP_POS + 1], r[SP_POS + 2]), cv(r[SP_VEL], r[SP_VEL + 1], r[SP_VEL + 2]);
   const Q4<P> ca(r[SP_ATT], r[SP_ATT + 1], r[SP_ATT + 2], r[SP_ATT + 3]);
-  st.sq[size_t(slot) * n + i] = offboard_command<true, P>(off, cp, cv, ca, des);
+  st.sq[size_t(slot) * n + i] = offboard_generate<true, P>(off, i, n, t_gen_us, cp, cv, ca);
 }
 cudaError_t launch_offboard_generate(const StateArrays<double>& st, size_t n, const OffboardParams& off, uint64_t t_gen_us,
                                      uint32_t slot, cudaStream_t stream) {

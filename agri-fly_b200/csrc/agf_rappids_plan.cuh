@@ -31,6 +31,17 @@ namespace agfr {
 constexpr int kBlock = 128;           // 4 warps = 4 vehicles per CTA
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxPyr = 32;
+// CTAs per SM the register allocation aims at (tuning: profiles/r1_rappids2.sh; 5 measured best for the fast variant)
+#ifndef AGFR_MIN_BLOCKS
+#if defined(AGF_RAPPIDS_PARITY) && AGF_RAPPIDS_PARITY
+#define AGFR_MIN_BLOCKS 3
+#else
+#define AGFR_MIN_BLOCKS 5
+#endif
+#endif
+#ifndef AGFR_AHEAD
+#define AGFR_AHEAD 6       // image lines prefetched ahead of a region scan
+#endif
 constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
 
 struct PlanParams {
@@ -360,8 +371,7 @@ struct Shrink {
 };
 enum { R_RIGHT = 0, R_LEFT, R_TOP, R_BOTTOM, R_TR, R_BR, R_TL, R_BL };
 
-template<int REGION>
-AGFR_DEV bool shrink_trigger(const Shrink& s, int num, int x, int y, int p) {
+AGFR_DEV bool shrink_trigger(const int REGION, const Shrink& s, int num, int x, int y, int p) {
   switch (REGION) {
     case R_RIGHT: return num > (x - s.rS) * p;
     case R_LEFT: return (s.lS - x) * p < num;
@@ -374,8 +384,7 @@ AGFR_DEV bool shrink_trigger(const Shrink& s, int num, int x, int y, int p) {
   }
 }
 // applies the update of one triggering pixel; false = "the pyramid cannot contain the sample point"
-template<int REGION>
-AGFR_DEV bool shrink_apply(Shrink& s, int num, int x, int y, int p, int x0, int y0) {
+AGFR_DEV bool shrink_apply(const int REGION, Shrink& s, int num, int x, int y, int p, int x0, int y0) {
   const int q = num / p;
   const int rT = x - q, lT = x + q, tT = y + q, bT = y - q;
   if (REGION == R_RIGHT || REGION == R_LEFT) {
@@ -443,32 +452,94 @@ AGFR_DEV bool shrink_apply(Shrink& s, int num, int x, int y, int p, int x0, int 
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 256-pixel chunks.  The scans below are waits on dependent 64-byte loads when taken 32 pixels per step (ncu, round 1:
+// 64 % of the stall samples on the two pixel loads), so a line is first read 8 pixels per lane (one aligned 128-bit
+// load, 512 B per warp step) and tested for "can any pixel of this chunk matter at all"; only chunks that can are
+// replayed 32 pixels per step in the reference's scan order (L1 hits).  Skipping a chunk in which no pixel passes
+// the order-independent part of the test is exact.
+// ---------------------------------------------------------------------------------------------
+AGFR_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// lb: 16-byte aligned pointer at or below `line`, mis = line - lb (elements); chunk c covers lb[256 c .. 256 c + 255]
+AGFR_DEV bool chunk_load(const uint16_t* lb, int c, int lane, int jlo, int jhi, uint4& v, int& j0) {
+  j0 = c * 256 + lane * 8;
+  const bool in = (j0 + 7 >= jlo) && (j0 <= jhi);
+  v = in ? __ldg(reinterpret_cast<const uint4*>(lb + j0)) : make_uint4(0, 0, 0, 0);
+  return in;
+}
+// per-halfword masks (0xFFFF where true) of `ignore < p` and `p < bound` for the two pixels of a word
+AGFR_DEV unsigned pix_between(unsigned w, unsigned ign2, unsigned bnd2) { return __vcmpgtu2(w, ign2) & __vcmpltu2(w, bnd2); }
+// mask of the halfwords of word q (pixels j0 + 2q, j0 + 2q + 1) that lie inside [jlo, jhi]
+AGFR_DEV unsigned pix_inside(int j0, int q, int jlo, int jhi) {
+  const int a = j0 + 2 * q, b = a + 1;
+  return ((a >= jlo && a <= jhi) ? 0x0000FFFFu : 0u) | ((b >= jlo && b <= jhi) ? 0xFFFF0000u : 0u);
+}
+
+// the 32-pixels-per-step scan of inner indices i0 + dI*k, k < cnt, of one line (reference order)
+AGFR_DEV bool shrink_span(const int REGION, const PlanParams& P, const WarpCtx& w, Shrink& s, int maxDepth, int x0, int y0,
+                          int o, const uint16_t* line, int i0, int dI, int cnt) {
+  const bool colWalk = (REGION == R_RIGHT || REGION == R_LEFT);  // outer x, inner y
+  for (int base = 0; base < cnt; base += 32) {
+    const int k = base + w.lane;
+    const bool valid = k < cnt;
+    const int i = i0 + dI * k;
+    const int p = valid ? (int)ld16(line + i) : 0;
+    const bool pre = valid && p > P.ignore && p < maxDepth;
+    unsigned todo = __ballot_sync(AGFR_FULL, pre);
+    const int x = colWalk ? o : i, y = colWalk ? i : o;
+    while (todo) {
+      const bool trig = ((todo >> w.lane) & 1u) && shrink_trigger(REGION, s, P.num, x, y, p);
+      const unsigned tm = __ballot_sync(AGFR_FULL, trig);
+      if (!tm) break;
+      const int src = __ffs(tm) - 1;
+      const int sx = __shfl_sync(AGFR_FULL, x, src), sy = __shfl_sync(AGFR_FULL, y, src),
+                sp = __shfl_sync(AGFR_FULL, p, src);
+      if (!shrink_apply(REGION, s, P.num, sx, sy, sp, x0, y0)) return false;
+      todo &= lanes_after(src);
+    }
+  }
+  return true;
+}
+
 // scans one region in the reference's order.  outer: o = o0, o0+dO, .. (nOuter values); inner: i = i0 + dI*k, k < cnt
-template<int REGION>
-AGFR_DEV bool shrink_region(const PlanParams& P, const WarpCtx& w, Shrink& s, int maxDepth, int x0, int y0, int o0,
-                            int dO, int nOuter, int i0, int dI, int cnt) {
-  constexpr bool colWalk = (REGION == R_RIGHT || REGION == R_LEFT);  // outer x, inner y
+// One copy of this code for the eight regions (REGION is a run-time argument): inlined eight times the scan outgrew
+// the instruction cache (ncu, round 1: 74 % of the stall samples were instruction fetches).
+static __device__ __noinline__ bool shrink_region(const int REGION, const PlanParams& P, const WarpCtx& w, Shrink& s,
+                                                  int maxDepth, int x0, int y0, int o0, int dO, int nOuter, int i0, int dI,
+                                                  int cnt) {
+  const bool colWalk = (REGION == R_RIGHT || REGION == R_LEFT);  // outer x, inner y
+  if (cnt <= 0) return true;
+  const int pitch = colWalk ? P.H : P.W;
+  const int lo = dI > 0 ? i0 : i0 - (cnt - 1), hi = dI > 0 ? i0 + (cnt - 1) : i0;
+  const unsigned ign2 = (unsigned)min(max(P.ignore, 0), 65535) * 0x10001u, bnd2 = (unsigned)min(maxDepth, 65535) * 0x10001u;
+  constexpr int kAhead = AGFR_AHEAD;  // lines prefetched ahead of the scan
+  const uint16_t* plane = colWalk ? w.imgT : w.img;
   for (int oc = 0; oc < nOuter; oc++) {
     const int o = o0 + dO * oc;
-    const uint16_t* line = colWalk ? (w.imgT + (size_t)o * P.H) : (w.img + (size_t)o * P.W);
-    for (int base = 0; base < cnt; base += 32) {
-      const int k = base + w.lane;
-      const bool valid = k < cnt;
-      const int i = i0 + dI * k;
-      const int p = valid ? (int)ld16(line + i) : 0;
-      const bool pre = valid && p > P.ignore && p < maxDepth;
-      unsigned todo = __ballot_sync(AGFR_FULL, pre);
-      const int x = colWalk ? o : i, y = colWalk ? i : o;
-      while (todo) {
-        const bool trig = ((todo >> w.lane) & 1u) && shrink_trigger<REGION>(s, P.num, x, y, p);
-        const unsigned tm = __ballot_sync(AGFR_FULL, trig);
-        if (!tm) break;
-        const int src = __ffs(tm) - 1;
-        const int sx = __shfl_sync(AGFR_FULL, x, src), sy = __shfl_sync(AGFR_FULL, y, src),
-                  sp = __shfl_sync(AGFR_FULL, p, src);
-        if (!shrink_apply<REGION>(s, P.num, sx, sy, sp, x0, y0)) return false;
-        todo &= lanes_after(src);
-      }
+    const uint16_t* line = plane + (size_t)o * pitch;
+    if (lo + w.lane * 64 <= hi) {  // one 128-byte line per lane
+      if (oc == 0)
+        for (int d = 1; d < kAhead && d < nOuter; d++) prefetch_l1(plane + (size_t)(o + dO * d) * pitch + lo + w.lane * 64);
+      if (oc + kAhead < nOuter) prefetch_l1(plane + (size_t)(o + dO * kAhead) * pitch + lo + w.lane * 64);
+    }
+    const int mis = (int)(((uintptr_t)line & 15u) >> 1);
+    const uint16_t* lb = line - mis;
+    const int jlo = lo + mis, jhi = hi + mis;
+    const int c0 = jlo >> 8, c1 = jhi >> 8;
+    for (int cc = 0; cc <= c1 - c0; cc++) {
+      const int c = dI > 0 ? c0 + cc : c1 - cc;
+      uint4 v;
+      int j0;
+      chunk_load(lb, c, w.lane, jlo, jhi, v, j0);
+      unsigned m = pix_between(v.x, ign2, bnd2) | pix_between(v.y, ign2, bnd2) | pix_between(v.z, ign2, bnd2) |
+                   pix_between(v.w, ign2, bnd2);
+      if (m != 0u && !(j0 >= jlo && j0 + 7 <= jhi))  // a segment that straddles an end of the range: mask pixel by pixel
+        m = (pix_between(v.x, ign2, bnd2) & pix_inside(j0, 0, jlo, jhi)) | (pix_between(v.y, ign2, bnd2) & pix_inside(j0, 1, jlo, jhi)) |
+            (pix_between(v.z, ign2, bnd2) & pix_inside(j0, 2, jlo, jhi)) | (pix_between(v.w, ign2, bnd2) & pix_inside(j0, 3, jlo, jhi));
+      if (!__any_sync(AGFR_FULL, m != 0u)) continue;
+      // replay this chunk's part of the range in scan order
+      const int a = max(lo, c * 256 - mis), b = min(hi, c * 256 + 255 - mis);
+      if (!shrink_span(REGION, P, w, s, maxDepth, x0, y0, o, line, dI > 0 ? a : b, dI, b - a + 1)) return false;
     }
   }
   return true;
@@ -476,22 +547,54 @@ AGFR_DEV bool shrink_region(const PlanParams& P, const WarpCtx& w, Shrink& s, in
 
 // one line of the spiral expansion (DepthImagePlanner.cpp:521-597): returns true when a pixel nearer than the
 // pyramid's minimum depth blocks the side; folds the depths seen before it into maxDepth
-AGFR_DEV bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* line, int a, int b, int minPyr,
-                          int& maxDepth) {
+// `plane` + idx * pitch is the line; the lines idx + step .. are the ones the next rounds of the spiral will ask for
+static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* plane, int pitch, int nLines, int idx,
+                          int step, int a, int b, int minPyr, int& maxDepth) {
+  const uint16_t* line = plane + (size_t)idx * pitch;
+  {
+    const int nx = idx + 3 * step;  // three rounds ahead
+    if (nx >= 0 && nx < nLines && a + w.lane * 64 <= b) prefetch_l1(plane + (size_t)nx * pitch + a + w.lane * 64);
+  }
   unsigned mn = 65535u;
   bool blocked = false;
-  for (int v0 = a; v0 <= b; v0 += 32) {
-    const int v = v0 + w.lane;
-    const bool valid = v <= b;
-    const int p = valid ? (int)ld16(line + v) : 0;
-    const bool sees = valid && p > P.ignore;
-    const bool blk = sees && p < minPyr;
-    const unsigned bm = __ballot_sync(AGFR_FULL, blk);
-    const unsigned before = bm ? ((1u << (__ffs(bm) - 1)) - 1u) : AGFR_FULL;
-    if (sees && !blk && ((before >> w.lane) & 1u)) mn = min(mn, (unsigned)p);
-    if (bm) {
-      blocked = true;
-      break;
+  const unsigned ign2 = (unsigned)min(max(P.ignore, 0), 65535) * 0x10001u,
+                 blk2 = (unsigned)min(max(minPyr, 0), 65535) * 0x10001u;
+  const int mis = (int)(((uintptr_t)line & 15u) >> 1);
+  const uint16_t* lb = line - mis;
+  const int jlo = a + mis, jhi = b + mis;
+  for (int c = jlo >> 8; c <= (jhi >> 8) && !blocked; c++) {
+    uint4 v;
+    int j0;
+    chunk_load(lb, c, w.lane, jlo, jhi, v, j0);
+    const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+    unsigned anyblk = 0, lmin = 0xFFFFFFFFu;
+    const bool whole = j0 >= jlo && j0 + 7 <= jhi;  // lanes outside the range hold zeros, which are never seen
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      unsigned sees = __vcmpgtu2(wd[q], ign2);
+      if (!whole) sees &= pix_inside(j0, q, jlo, jhi);
+      anyblk |= sees & __vcmpltu2(wd[q], blk2);
+      lmin = __vminu2(lmin, wd[q] | ~sees);  // pixels that are not seen count as 65535
+    }
+    if (!__any_sync(AGFR_FULL, anyblk != 0u)) {
+      mn = min(mn, min(lmin & 0xFFFFu, lmin >> 16));
+      continue;
+    }
+    // a blocking pixel in this chunk: 32 pixels per step, the depths before the first blocking pixel count
+    const int ca = max(a, c * 256 - mis), cb = min(b, c * 256 + 255 - mis);
+    for (int v0 = ca; v0 <= cb; v0 += 32) {
+      const int vv = v0 + w.lane;
+      const bool valid = vv <= cb;
+      const int p = valid ? (int)ld16(line + vv) : 0;
+      const bool sees = valid && p > P.ignore;
+      const bool blk = sees && p < minPyr;
+      const unsigned bm = __ballot_sync(AGFR_FULL, blk);
+      const unsigned before = bm ? ((1u << (__ffs(bm) - 1)) - 1u) : AGFR_FULL;
+      if (sees && !blk && ((before >> w.lane) & 1u)) mn = min(mn, (unsigned)p);
+      if (bm) {
+        blocked = true;
+        break;
+      }
     }
   }
   mn = __reduce_min_sync(AGFR_FULL, mn);
@@ -547,7 +650,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
   while (rf || tf || lf || bf) {
     if (rf) {
       if (right < W - edgeOff - 1) {
-        if (expand_line(P, w, w.imgT + (size_t)(right + 1) * H, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, H, W, right + 1, 1, top, bottom, minPyr, maxDepth)) {
           rf = false;
           right--;
         }
@@ -558,7 +661,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (tf) {
       if (top > edgeOff) {
-        if (expand_line(P, w, w.img + (size_t)(top - 1) * W, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, W, H, top - 1, -1, left, right, minPyr, maxDepth)) {
           tf = false;
           top++;
         }
@@ -569,7 +672,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (lf) {
       if (left > edgeOff) {
-        if (expand_line(P, w, w.imgT + (size_t)(left - 1) * H, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, H, W, left - 1, -1, top, bottom, minPyr, maxDepth)) {
           lf = false;
           left++;
         }
@@ -580,7 +683,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (bf) {
       if (bottom < H - edgeOff - 1) {
-        if (expand_line(P, w, w.img + (size_t)(bottom + 1) * W, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, W, H, bottom + 1, 1, left, right, minPyr, maxDepth)) {
           bf = false;
           bottom--;
         }
@@ -597,16 +700,33 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
   s.tS = edgeOff;
   s.bS = H - 1 - edgeOff;
   const int rows = bottom - top + 1, cols = right - left + 1;
-  if (!shrink_region<R_RIGHT>(P, w, s, maxDepth, x0, y0, right, 1, W - right, top, 1, rows)) return false;
-  if (!shrink_region<R_LEFT>(P, w, s, maxDepth, x0, y0, left, -1, left + 1, top, 1, rows)) return false;
-  if (s.lS + kBuf > s.rS - kBuf) return false;
-  if (!shrink_region<R_TOP>(P, w, s, maxDepth, x0, y0, top, -1, top + 1, left, 1, cols)) return false;
-  if (!shrink_region<R_BOTTOM>(P, w, s, maxDepth, x0, y0, bottom, 1, H - bottom, left, 1, cols)) return false;
-  if (s.tS + kBuf > s.bS - kBuf) return false;
-  if (!shrink_region<R_TR>(P, w, s, maxDepth, x0, y0, top, -1, top + 1, right, 1, W - right)) return false;
-  if (!shrink_region<R_BR>(P, w, s, maxDepth, x0, y0, bottom, 1, H - bottom, right, 1, W - right)) return false;
-  if (!shrink_region<R_TL>(P, w, s, maxDepth, x0, y0, top, -1, top + 1, left, -1, left + 1)) return false;
-  if (!shrink_region<R_BL>(P, w, s, maxDepth, x0, y0, bottom, 1, H - bottom, left, -1, left + 1)) return false;
+  // the eight regions in the reference's order, through ONE out-of-line scan routine (the loop is kept rolled so that
+  // the compiler does not clone the routine per region)
+#pragma unroll 1
+  for (int r = R_RIGHT; r <= R_BL; r++) {
+    int o0, dO, nOuter, i0, dI, cnt;
+    if (r == R_RIGHT || r == R_LEFT) {  // columns outwards, rows top..bottom
+      o0 = (r == R_RIGHT) ? right : left;
+      dO = (r == R_RIGHT) ? 1 : -1;
+      nOuter = (r == R_RIGHT) ? W - right : left + 1;
+      i0 = top; dI = 1; cnt = rows;
+    } else {                            // rows outwards; columns left..right, or from a corner outwards
+      const bool up = (r == R_TOP || r == R_TR || r == R_TL);
+      o0 = up ? top : bottom;
+      dO = up ? -1 : 1;
+      nOuter = up ? top + 1 : H - bottom;
+      if (r == R_TOP || r == R_BOTTOM) {
+        i0 = left; dI = 1; cnt = cols;
+      } else if (r == R_TR || r == R_BR) {
+        i0 = right; dI = 1; cnt = W - right;
+      } else {
+        i0 = left; dI = -1; cnt = left + 1;
+      }
+    }
+    if (!shrink_region(r, P, w, s, maxDepth, x0, y0, o0, dO, nOuter, i0, dI, cnt)) return false;
+    if (r == R_LEFT && s.lS + kBuf > s.rS - kBuf) return false;
+    if (r == R_BOTTOM && s.tS + kBuf > s.bS - kBuf) return false;
+  }
   outDepth = maxDepth * P.scale - P.rPlan;
   outEdge = make_int4(s.rS, s.tS, s.lS, s.bS);
   return true;
@@ -785,7 +905,7 @@ __device__ __noinline__ bool collision_free(const PlanParams& P, WarpCtx& w, con
 // the kernel: one warp per vehicle, vehicles handed out through a counter
 // ---------------------------------------------------------------------------------------------
 template<bool PARITY>
-__global__ void __launch_bounds__(kBlock) rappids_plan_kernel(const __grid_constant__ PlanParams P) {
+__global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(const __grid_constant__ PlanParams P) {
   __shared__ double s_depth[kWarps][kMaxPyr + 1];
   __shared__ int4 s_edge[kWarps][kMaxPyr + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -64,6 +64,7 @@ struct Mf<true> {
   static AGF_DEV float atan2(float y, float x) { return agf_atan2f(y, x); }
   static AGF_DEV double sin(double x) { return agf_sin(x); }
   static AGF_DEV double cos(double x) { return agf_cos(x); }
+  static AGF_DEV double acos(double x) { return agf_acos(x); }
 };
 // Fast variants: the step only ever takes sin/cos of HALF rotation angles per tick (|x| << 1), so a
 // short odd/even polynomial (error < 1e-9 relative for |x| <= 0.5) serves the hot path and the
@@ -121,6 +122,7 @@ struct Mf<false> {
   static AGF_DEV float asin(float x) { return ::asinf(x); }
   static AGF_DEV float acos(float x) { return ::acosf(x); }
   static AGF_DEV float atan2(float y, float x) { return ::atan2f(y, x); }
+  static AGF_DEV double acos(double x) { return ::acos(x); }
 };
 // division: IEEE in the parity variant, reciprocal-multiply in the fast ones
 template<bool PARITY> AGF_DEV float fdiv(float a, float b) {
@@ -1220,18 +1222,53 @@ AGF_DEV float radio_quantise(float v, float limit) {
   out &= 0xFFFF;  // two bytes on the wire
   return limit * (out - 32768) / float(32768);
 }
+// attitude whose z axis is `dir` (shortest rotation from e3), then yawed: QuadcopterController.cpp:46-71 / :107-127
+template<bool PARITY>
+AGF_DEV Q4<float> offboard_att_from_dir(const V3<float>& dir, float yaw) {
+  const V3<float> e3(0, 0, 1);
+  const float cosAngle = dot(dir, e3);
+  float angle;
+  if (cosAngle >= (1 - 1e-12f)) {
+    angle = 0;
+  } else if (cosAngle <= -(1 - 1e-12f)) {
+    angle = 3.14159274f;
+  } else {
+    angle = Mf<PARITY>::acos(cosAngle);
+  }
+  const V3<float> rotAx = cross(e3, dir);
+  const float n = norm(rotAx);
+  Q4<float> att(1, 0, 0, 0);
+  if (!(n < 1e-6f)) {
+    Q4<float> d;
+    if (q_from_rotvec<PARITY>(rotAx * fdiv<PARITY>(angle, n), d)) att = d;
+  }
+  Q4<float> yawq(1, 0, 0, 0);
+  {
+    Q4<float> d;
+    if (q_from_rotvec<PARITY>(V3<float>(0, 0, yaw), d)) yawq = d;
+  }
+  return qmul(att, yawq);
+}
+AGF_DEV V3<float> v3f(const double v[3]) { return V3<float>(float(v[0]), float(v[1]), float(v[2])); }
+// GetDesAcceleration (QuadcopterPositionController.hpp:22-27)
+AGF_DEV V3<float> offboard_des_acc(const OffboardParams& c, const V3<float>& estPos, const V3<float>& estVel, const V3<float>& desPos,
+                                   const V3<float>& desVel, const V3<float>& desAcc) {
+  const V3<float> dv = desVel - estVel;
+  return (((desPos - estPos) * c.nat_freq) * c.nat_freq + ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * c.nat_freq) * c.damping)) + desAcc;
+}
+AGF_DEV float4 offboard_rates_packet(double thrust, const V3<float>& w) {
+  return make_float4(radio_quantise(float(thrust), 35.0f), radio_quantise(w.x, 35.0f), radio_quantise(w.y, 35.0f),
+                     radio_quantise(w.z, 35.0f));
+}
+// QuadcopterController::Run (Offboard/QuadcopterController.cpp:11-74)
 template<bool PARITY, typename P>
 AGF_DEV float4 offboard_command(const OffboardParams& c, const V3<P>& curPos, const V3<P>& curVel, const Q4<P>& curAtt,
-                                const double des[3]) {
+                                const double des[3], const double desVel[3], const double desAcc[3], double yaw) {
   const V3<float> e3(0, 0, 1);
   const V3<float> estPos = V3<float>(float(curPos.x), float(curPos.y), float(curPos.z));
   const V3<float> estVel = V3<float>(float(curVel.x), float(curVel.y), float(curVel.z));
-  const V3<float> desPos = V3<float>(float(des[0]), float(des[1]), float(des[2]));
   const Q4<float> attf = Q4<float>(float(curAtt.w), float(curAtt.x), float(curAtt.y), float(curAtt.z));
-  // GetDesAcceleration (QuadcopterPositionController.hpp:22-27), desVel = desAcc = 0
-  const V3<float> zero(0, 0, 0);
-  const V3<float> dv = zero - estVel;
-  const V3<float> cmdAcc = (((desPos - estPos) * c.nat_freq) * c.nat_freq + ((V3<float>(2 * dv.x, 2 * dv.y, 2 * dv.z) * c.nat_freq) * c.damping)) + zero;
+  const V3<float> cmdAcc = offboard_des_acc(c, estPos, estVel, v3f(des), v3f(desVel), v3f(desAcc));
   V3<float> cmdProperAcc = cmdAcc + V3<float>(0, 0, 9.81f);
   {
     const float n0 = norm(cmdProperAcc);
@@ -1242,36 +1279,247 @@ AGF_DEV float4 offboard_command(const OffboardParams& c, const V3<P>& curPos, co
   const V3<float> cmdThrustDir = vdiv<PARITY>(cmdProperAcc, normCmdProperAcc);
   double outCmdThrust = double(normCmdProperAcc * dot(qrot(attf, V3<float>(0, 0, 1)), cmdThrustDir));
   if (outCmdThrust < c.min_proper) outCmdThrust = c.min_proper;
-  const float cosAngle = dot(cmdThrustDir, e3);
-  float angle;
-  if (cosAngle >= (1 - 1e-12f)) {
-    angle = 0;
-  } else if (cosAngle <= -(1 - 1e-12f)) {
-    angle = 3.14159274f;
-  } else {
-    angle = Mf<PARITY>::acos(cosAngle);
-  }
-  const V3<float> rotAx = cross(e3, cmdThrustDir);
-  const float n = norm(rotAx);
-  Q4<float> cmdAtt(1, 0, 0, 0);
-  if (!(n < 1e-6f)) {
-    Q4<float> d;
-    if (q_from_rotvec<PARITY>(rotAx * fdiv<PARITY>(angle, n), d)) cmdAtt = d;
-  }
-  Q4<float> yawq(1, 0, 0, 0);
-  {
-    Q4<float> d;
-    if (q_from_rotvec<PARITY>(V3<float>(0, 0, c.yaw), d)) yawq = d;
-  }
-  const Q4<float> cmdAttYawed = qmul(cmdAtt, yawq);
+  const Q4<float> cmdAttYawed = offboard_att_from_dir<PARITY>(cmdThrustDir, float(yaw));
   const V3<float> w = ctl_att_core<PARITY>(c.tc_att_xy, c.tc_att_z, c.k3_att, c.k12_att, cmdAttYawed, attf);
-  return make_float4(radio_quantise(float(outCmdThrust), 35.0f), radio_quantise(w.x, 35.0f), radio_quantise(w.y, 35.0f),
-                     radio_quantise(w.z, 35.0f));
+  return offboard_rates_packet(outCmdThrust, w);
+}
+// QuadcopterController::RunTracking (Offboard/QuadcopterController.cpp:76-131)
+template<bool PARITY, typename P>
+AGF_DEV float4 offboard_tracking(const OffboardParams& c, const V3<P>& curPos, const V3<P>& curVel, const Q4<P>& curAtt,
+                                 const double refPos[3], const double refVel[3], const double refAcc[3], double yaw,
+                                 double refThrust, const double refAngVel[3]) {
+  const V3<float> estPos = V3<float>(float(curPos.x), float(curPos.y), float(curPos.z));
+  const V3<float> estVel = V3<float>(float(curVel.x), float(curVel.y), float(curVel.z));
+  const Q4<float> attf = Q4<float>(float(curAtt.w), float(curAtt.x), float(curAtt.y), float(curAtt.z));
+  const V3<float> accErr = offboard_des_acc(c, estPos, estVel, v3f(refPos), v3f(refVel), V3<float>(0.0f, 0.0f, 0.0f));
+  // double = double + float
+  const double outCmdThrust = refThrust + double(dot(accErr, qrot(attf, V3<float>(0, 0, 1))));
+  // (refAcc + accErr + Vec3f(0,0,9.81f)): Vec3d + Vec3f converts the right operand to Vec3d; GetNorm2() in double,
+  // stored to float; the division is Vec3d / double(float)
+  const V3<double> sum = (V3<double>(refAcc[0], refAcc[1], refAcc[2]) + V3<double>(double(accErr.x), double(accErr.y), double(accErr.z))) +
+                         V3<double>(0.0, 0.0, double(9.81f));
+  const float normRefProperAcc = float(norm(sum));
+  const V3<double> dird = sum / double(normRefProperAcc);
+  const V3<float> refThrustDir(float(dird.x), float(dird.y), float(dird.z));
+  const Q4<float> refAttYawed = offboard_att_from_dir<PARITY>(refThrustDir, float(yaw));
+  const V3<float> angVelErr = ctl_att_core<PARITY>(c.tc_att_xy, c.tc_att_z, c.k3_att, c.k12_att, refAttYawed, attf);
+  // outCmdAngVel = refAngVel + Vec3d(Vec3f(...)); CreateRatesCommand takes Vec3f(cmdAngVel)
+  const V3<float> w(float(refAngVel[0] + double(angVelErr.x)), float(refAngVel[1] + double(angVelErr.y)),
+                    float(refAngVel[2] + double(angVelErr.z)));
+  return offboard_rates_packet(outCmdThrust, w);
+}
+
+// ---- reference generators (agrifly_b200.h "offboard loop: reference generators") --------------
+// queue payload markers: x = +inf "no command this round" (wait stage), x = NaN "idle command"
+AGF_DEV float4 offboard_no_command() { return make_float4(1.0f / 0.0f, 0.0f, 0.0f, 0.0f); }
+AGF_DEV float4 offboard_idle_command() { return make_float4(0.0f / 0.0f, 0.0f, 0.0f, 0.0f); }
+// SingleAxisTrajectory::GetPosition / GetVelocity / GetAcceleration (SingleAxisTrajectory.hpp:57-63); q: p0 v0 a0 alpha beta gamma
+AGF_DEV double sat_pos(const double* q, double t) {
+  return q[0] + q[1] * t + (1 / 2.0) * q[2] * t * t + (1 / 6.0) * q[5] * t * t * t + (1 / 24.0) * q[4] * t * t * t * t +
+         (1 / 120.0) * q[3] * t * t * t * t * t;
+}
+AGF_DEV double sat_vel(const double* q, double t) {
+  return q[1] + q[2] * t + (1 / 2.0) * q[5] * t * t + (1 / 6.0) * q[4] * t * t * t + (1 / 24.0) * q[3] * t * t * t * t;
+}
+AGF_DEV double sat_acc(const double* q, double t) { return q[2] + q[5] * t + (1 / 2.0) * q[4] * t * t + (1 / 6.0) * q[3] * t * t * t; }
+// (GetAcceleration(t) - _grav): thrust vector of the primitive (RapidTrajectoryGenerator.hpp:187-194)
+AGF_DEV V3<double> rtg_thrust_vec(const double* tr, double t) {
+  return V3<double>(sat_acc(tr, t) - tr[18], sat_acc(tr + 6, t) - tr[19], sat_acc(tr + 12, t) - tr[20]);
+}
+AGF_DEV V3<double> unit_vector_d(const V3<double>& v) {  // Vec3.hpp:126-129: the norm is stored in a float
+  const float n = float(norm(v));
+  return v / double(n);
+}
+// RapidTrajectoryGenerator::GetOmega (RapidTrajectoryGenerator.cpp:264-286)
+template<bool PARITY>
+AGF_DEV V3<double> rtg_omega(const double* tr, double t, double timeStep) {
+  const V3<double> n0 = unit_vector_d(rtg_thrust_vec(tr, t));
+  const V3<double> n1 = unit_vector_d(rtg_thrust_vec(tr, t + timeStep));
+  const V3<double> crossProd = cross(n0, n1);
+  if (norm(crossProd) <= 1e-6) return V3<double>(0, 0, 0);
+  const V3<double> n = unit_vector_d(crossProd);
+  const double d = dot(n0, n1);
+  if (d > 1.0 || d < -1.0 || d != d) return V3<double>(0, 0, 0);  // errno set by acos (domain error)
+  const double angle = Mf<PARITY>::acos(d) / timeStep;
+  return angle * n;
+}
+
+// One round of the offboard main loop for vehicle i at clock reading t_gen: desired state from the configured
+// generator, then the controller; returns the queue payload.
+template<bool PARITY, typename P>
+AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, uint64_t t_gen, const V3<P>& cp, const V3<P>& cv,
+                                 const Q4<P>& ca) {
+  const double zero3[3] = {0.0, 0.0, 0.0};
+  double des[3];
+  if (c.ref_kind == AGF_OFFREF_TARGETS) {
+    uint32_t ti = 0;
+    for (uint32_t j = 1; j < c.n_targets; j++)
+      if (c.targets[j].time_us <= t_gen) ti = j;
+    des[0] = c.targets[ti].pos[0]; des[1] = c.targets[ti].pos[1]; des[2] = c.targets[ti].pos[2];
+  } else {
+    des[0] = c.desired[0]; des[1] = c.desired[1]; des[2] = c.desired[2];
+  }
+  if (c.offsets) {
+    des[0] = des[0] + c.offsets[i];
+    des[1] = des[1] + c.offsets[n + i];
+    des[2] = des[2] + c.offsets[2 * n + i];
+  }
+  if (c.ref_kind == AGF_OFFREF_TARGETS) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, double(c.yaw));
+  if (c.ref_kind == AGF_OFFREF_TRAJECTORY) {
+    if (!(t_gen > c.start_us)) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, c.desired_yaw);
+    double tr[AGF_OFFTRAJ_DOUBLES];
+    for (int k = 0; k < AGF_OFFTRAJ_DOUBLES; k++) tr[k] = c.traj[size_t(k) * n + i];
+    double traj_t = double(t_gen - c.start_us) * 1e-6;
+    const double tEnd = tr[21];
+    double tp[3], tv[3], ta[3];
+    if (traj_t < tEnd) {
+      traj_t += 0.04;
+      for (int a = 0; a < 3; a++) {
+        tp[a] = sat_pos(tr + 6 * a, traj_t); tv[a] = sat_vel(tr + 6 * a, traj_t); ta[a] = sat_acc(tr + 6 * a, traj_t);
+      }
+    } else {
+      for (int a = 0; a < 3; a++) {
+        tp[a] = sat_pos(tr + 6 * a, tEnd); tv[a] = 0; ta[a] = 0;
+      }
+    }
+    if (tp[2] < 0) {
+      tp[2] = 0;
+      if (tv[2] < 0) tv[2] = 0;
+      if (ta[2] < 0) ta[2] = 0;
+    }
+    const Q4<double> trajAtt(tr[22], tr[23], tr[24], tr[25]);
+    const V3<double> rp = qrot(trajAtt, V3<double>(tp[0], tp[1], tp[2])) + V3<double>(tr[26], tr[27], tr[28]);
+    const V3<double> rv = qrot(trajAtt, V3<double>(tv[0], tv[1], tv[2]));
+    const V3<double> ra = qrot(trajAtt, V3<double>(ta[0], ta[1], ta[2]));
+    const double refThrust = norm(rtg_thrust_vec(tr, traj_t));
+    const Q4<double> cad(double(ca.w), double(ca.x), double(ca.y), double(ca.z));
+    const V3<double> rw = qrot(qmul(qinv(cad), trajAtt), rtg_omega<PARITY>(tr, traj_t, 0.02));
+    const double refPos[3] = {rp.x, rp.y, rp.z}, refVel[3] = {rv.x, rv.y, rv.z}, refAcc[3] = {ra.x, ra.y, ra.z},
+                 refW[3] = {rw.x, rw.y, rw.z};
+    return offboard_tracking<PARITY, P>(c, cp, cv, ca, refPos, refVel, refAcc, c.desired_yaw, refThrust, refW);
+  }
+  // AGF_OFFREF_STAGES: ExampleVehicleStateMachine::Run (ExampleVehicleStateMachine.cpp:93-370)
+  double* st = c.state + i;  // field k at st[k * n]
+  const bool shouldStart = t_gen >= c.start_us, shouldStop = t_gen >= c.stop_us;
+  int stage = int(st[0]);
+  const bool stageChange = stage != int(st[n]);
+  st[n] = double(stage);
+  if (stageChange) st[2 * n] = double(t_gen);
+  const double ts = double(t_gen - uint64_t(st[2 * n])) * 1e-6;  // _stageTimer->GetSeconds<double>()
+  const int stage_in = stage;
+  float4 out;
+  double cmdYaw = st[15 * n];
+  switch (stage) {
+    case AGF_STAGE_WAIT_FOR_START:
+      if (shouldStart) stage = AGF_STAGE_SPOOL_UP;
+      out = offboard_no_command();
+      break;
+    case AGF_STAGE_SPOOL_UP:
+      out = offboard_rates_packet(9.81 * 0.25, V3<float>(0.0f, 0.0f, 0.0f));
+      if (ts > 0.5) stage = AGF_STAGE_TAKEOFF;
+      break;
+    case AGF_STAGE_TAKEOFF: {
+      if (stageChange) {
+        st[3 * n] = double(cp.x); st[4 * n] = double(cp.y); st[5 * n] = double(cp.z);
+      }
+      double frac = ts / 2.0;
+      if (frac >= 1.0) {
+        stage = AGF_STAGE_FLIGHT;
+        frac = 1.0;
+      }
+      double cmdPos[3];
+      for (int a = 0; a < 3; a++) cmdPos[a] = (1 - frac) * st[(3 + a) * n] + frac * des[a];
+      out = offboard_command<PARITY, P>(c, cp, cv, ca, cmdPos, zero3, zero3, cmdYaw);
+    } break;
+    case AGF_STAGE_FLIGHT: {
+      double cmdPos[3] = {0, 0, 0}, cmdVel[3] = {0, 0, 0}, cmdAcc[3] = {0, 0, 0};
+      const double t = ts;
+      const double frac = (t / 2.0 < 1.0) ? t / 2.0 : 1.0;  // min(t / getIntoActionTime, 1.0)
+      switch (c.traj_id) {
+        case 0:
+          cmdPos[0] = des[0]; cmdPos[1] = des[1]; cmdPos[2] = des[2];
+          cmdYaw = 0;
+          break;
+        case 1: {
+          const double radius = 1.0, angSpeed = 0.5;
+          const double cs = Mf<PARITY>::cos(angSpeed * t), sn = Mf<PARITY>::sin(angSpeed * t);
+          cmdPos[0] = 0.0 + radius * cs; cmdPos[1] = -2.0 + radius * sn; cmdPos[2] = des[2] + radius * 0;
+          cmdVel[0] = (radius * angSpeed) * -sn; cmdVel[1] = (radius * angSpeed) * cs; cmdVel[2] = (radius * angSpeed) * 0;
+          cmdAcc[0] = (radius * (angSpeed * angSpeed)) * -cs; cmdAcc[1] = (radius * (angSpeed * angSpeed)) * -sn;
+          cmdAcc[2] = (radius * (angSpeed * angSpeed)) * 0;
+          cmdYaw = c.desired_yaw + angSpeed * t;
+        } break;
+        case 2: {
+          const double amplitude = 1.0, angFreq = 2.0;
+          const double cs = Mf<PARITY>::cos(angFreq * t), sn = Mf<PARITY>::sin(angFreq * t);
+          cmdPos[0] = des[0] + amplitude * 0; cmdPos[1] = des[1] + amplitude * sn; cmdPos[2] = des[2] + amplitude * 0;
+          cmdVel[0] = (amplitude * angFreq) * 0; cmdVel[1] = (amplitude * angFreq) * cs; cmdVel[2] = (amplitude * angFreq) * 0;
+          cmdAcc[0] = (amplitude * (angFreq * angFreq)) * 0; cmdAcc[1] = (amplitude * (angFreq * angFreq)) * -sn;
+          cmdAcc[2] = (amplitude * (angFreq * angFreq)) * 0;
+          cmdYaw = c.desired_yaw;
+        } break;
+        case 3: {
+          const double radius = 0.5, angSpeed = 1;
+          const double cs = Mf<PARITY>::cos(angSpeed * t), sn = Mf<PARITY>::sin(angSpeed * t);
+          cmdPos[0] = 0.0 + radius * cs; cmdPos[1] = 0.0 + radius * sn; cmdPos[2] = des[2] + radius * 0;
+          cmdVel[0] = (radius * angSpeed) * -sn; cmdVel[1] = (radius * angSpeed) * cs; cmdVel[2] = (radius * angSpeed) * 0;
+          cmdAcc[0] = (radius * (angSpeed * angSpeed)) * -cs; cmdAcc[1] = (radius * (angSpeed * angSpeed)) * -sn;
+          cmdAcc[2] = (radius * (angSpeed * angSpeed)) * 0;
+          cmdYaw = 0;
+        } break;
+        case 4: {
+          const double radius = 0.5, angSpeed = 0.5;
+          const double cs = Mf<PARITY>::cos(angSpeed * t), sn = Mf<PARITY>::sin(angSpeed * t);
+          const double c4 = Mf<PARITY>::cos(angSpeed * t * 4), s4 = Mf<PARITY>::sin(angSpeed * t * 4);
+          cmdPos[0] = 0.0 + radius * cs; cmdPos[1] = 0.0 + radius * sn; cmdPos[2] = des[2] + radius * c4;
+          cmdVel[0] = (radius * angSpeed) * -sn; cmdVel[1] = (radius * angSpeed) * cs; cmdVel[2] = (radius * angSpeed) * -s4;
+          cmdAcc[0] = (radius * (angSpeed * angSpeed)) * -cs; cmdAcc[1] = (radius * (angSpeed * angSpeed)) * -sn;
+          cmdAcc[2] = (radius * (angSpeed * angSpeed)) * -c4;
+          cmdYaw = angSpeed * t;
+        } break;
+        default:
+          cmdPos[0] = des[0]; cmdPos[1] = des[1]; cmdPos[2] = des[2];
+          cmdYaw = 0.2 * t;
+          break;
+      }
+      double lp[3], lv[3], la[3];
+      for (int a = 0; a < 3; a++) {
+        lp[a] = (1 - frac) * des[a] + frac * cmdPos[a];
+        lv[a] = frac * cmdVel[a];
+        la[a] = frac * cmdAcc[a];
+        st[(6 + a) * n] = lp[a]; st[(9 + a) * n] = lv[a]; st[(12 + a) * n] = la[a];
+      }
+      out = offboard_command<PARITY, P>(c, cp, cv, ca, lp, lv, la, cmdYaw);
+      if (shouldStop) stage = AGF_STAGE_LANDING;
+    } break;
+    case AGF_STAGE_LANDING: {
+      const double LANDING_SPEED = 0.5;
+      const double frac = (ts / 2.0 < 1.0) ? ts / 2.0 : 1.0;
+      double lp[3], lv[3], la[3], cmdPos[3], dp[3], dv[3], da[3];
+      const double land[3] = {0.0, 0.0, -LANDING_SPEED};
+      for (int a = 0; a < 3; a++) {
+        lp[a] = st[(6 + a) * n]; lv[a] = st[(9 + a) * n]; la[a] = st[(12 + a) * n];
+        cmdPos[a] = lp[a] + ts * land[a];
+      }
+      if (cmdPos[2] < 0) stage = AGF_STAGE_COMPLETE;
+      for (int a = 0; a < 3; a++) {
+        dp[a] = (1 - frac) * lp[a] + frac * cmdPos[a];
+        dv[a] = (1 - frac) * lv[a] + frac * land[a];
+        da[a] = (1 - frac) * la[a] + frac * 0.0;
+      }
+      out = offboard_command<PARITY, P>(c, cp, cv, ca, dp, dv, da, cmdYaw);
+    } break;
+    default:
+      out = offboard_idle_command();
+      break;
+  }
+  if (stage != stage_in) st[0] = double(stage);
+  st[15 * n] = cmdYaw;
+  return out;
 }
 template<typename P>
-static AGF_COLD float4 offboard_command_cold(const OffboardParams* c, V3<P> curPos, V3<P> curVel, Q4<P> curAtt, double dx, double dy, double dz) {
-  const double des[3] = {dx, dy, dz};
-  return offboard_command<false, P>(*c, curPos, curVel, curAtt, des);
+static AGF_COLD float4 offboard_generate_cold(const OffboardParams* c, size_t i, size_t n, uint64_t t_gen, V3<P> cp, V3<P> cv, Q4<P> ca) {
+  return offboard_generate<false, P>(*c, i, n, t_gen, cp, cv, ca);
 }
 
 // RunControllerExternalAccelerationControl up to the desired body rates (QuadcopterLogic.cpp:459-517):
@@ -1523,8 +1771,13 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     } else {
       c = sq_load(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_deliver_slot));
     }
-    const float cf[4] = {c.x, c.y, c.z, c.w};
-    radio_deliver(s, p.logic, AGF_RADIO_EXTERNAL_RATES_CMD, p.off.flags, cf);
+    if (c.x != c.x) {  // idle command (CreateIdleCommand): type and flags only
+      const float cf[4] = {s.radio_f[0], s.radio_f[1], s.radio_f[2], s.radio_f[3]};
+      radio_deliver(s, p.logic, AGF_RADIO_IDLE_CMD, p.off.flags, cf);
+    } else if (c.x <= 3.0e38f) {  // +inf: nothing was sent that round
+      const float cf[4] = {c.x, c.y, c.z, c.w};
+      radio_deliver(s, p.logic, AGF_RADIO_EXTERNAL_RATES_CMD, p.off.flags, cf);
+    }
   }
   if (plan.run_plant) {
     const P dt = P(double(plan.plant_dt_us) * 1e-6);
@@ -1669,23 +1922,14 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
   }
   if (plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance; estimate = truth
     const uint64_t t_gen = ts.now_us + dt_us;
-    uint32_t ti = 0;
-    for (uint32_t j = 1; j < p.off.n_targets; j++)
-      if (p.off.targets[j].time_us <= t_gen) ti = j;
-    double des[3] = {p.off.targets[ti].pos[0], p.off.targets[ti].pos[1], p.off.targets[ti].pos[2]};
-    if (p.off.offsets) {
-      des[0] = des[0] + p.off.offsets[i];
-      des[1] = des[1] + p.off.offsets[n + i];
-      des[2] = des[2] + p.off.offsets[2 * n + i];
-    }
     const V3<P> cp(s.pos[0], s.pos[1], s.pos[2]), cv(s.vel[0], s.vel[1], s.vel[2]);
     const Q4<P> ca(s.att[0], s.att[1], s.att[2], s.att[3]);
     if constexpr (PARITY) {
-      const float4 c = offboard_command<true, P>(p.off, cp, cv, ca, des);
+      const float4 c = offboard_generate<true, P>(p.off, i, n, t_gen, cp, cv, ca);
       s.offq[4 * plan.off_gen_slot] = c.x; s.offq[4 * plan.off_gen_slot + 1] = c.y;
       s.offq[4 * plan.off_gen_slot + 2] = c.z; s.offq[4 * plan.off_gen_slot + 3] = c.w;
     } else {
-      const float4 c = offboard_command_cold<P>(&p.off, cp, cv, ca, des[0], des[1], des[2]);
+      const float4 c = offboard_generate_cold<P>(&p.off, i, n, t_gen, cp, cv, ca);
       sq_store(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_gen_slot), c);
     }
   }

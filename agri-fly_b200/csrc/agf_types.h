@@ -226,6 +226,12 @@ struct OffboardParams {
   uint32_t n_targets;
   const agf_offboard_target* targets;  // device, sorted by time
   const double* offsets;               // device [3][N] or null
+  // reference generator (agf_offboard_ref)
+  int ref_kind, traj_id;
+  uint64_t start_us, stop_us;
+  double desired[3], desired_yaw;
+  double* state;       // device [AGF_OFFSTATE_DOUBLES][N]: stage machine state per vehicle
+  const double* traj;  // device [AGF_OFFTRAJ_DOUBLES][N]: motion primitive per vehicle
 };
 
 template<typename P>

@@ -153,6 +153,29 @@ def offboard_scenario(nticks=4000):
                 targets=targets, nticks=nticks)
 
 
+def stages_scenario(traj_id=3, nticks=7000):
+    """the flight stages of the ROS rates-control node (ExampleVehicleStateMachine.cpp:93-370) as the
+    reference generator of the offboard loop: start signal at 0.5 s -> spool-up 0.5 s -> 2 s take-off ramp -> flight
+    trajectory `traj_id` -> stop signal at 9 s -> landing -> idle."""
+    sc = offboard_scenario(nticks)
+    sc.update(name="stages%d" % traj_id, pos=(0.2, -0.1, 0.0),
+              ref=dict(kind=1, start_us=500000, stop_us=9000000, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.3, traj_id=traj_id),
+              primitive=None)
+    return sc
+
+
+def tracking_scenario(nticks=3400):
+    """Rappids_Simulator's tracking of a planned motion primitive (main.cpp:560-634): hover at 2 m with
+    QuadcopterController::Run until 4 s, then RunTracking along a 2.5 s rest-to-rest quintic given in a frame yawed by
+    0.4 rad (trajAtt) and anchored at the hover point (trajOffset)."""
+    import numpy as np
+    sc = offboard_scenario(nticks)
+    sc.update(name="tracking", pos=(0.2, -0.1, 0.0),
+              ref=dict(kind=2, start_us=4000000, stop_us=0, desired_pos=(0.2, -0.1, 2.0), desired_yaw=0.1, traj_id=0),
+              primitive=dict(pf=(1.5, 0.5, 0.3), T=2.5, offset=(0.2, -0.1, 2.0), att=(float(np.cos(0.2)), 0.0, 0.0, float(np.sin(0.2)))))
+    return sc
+
+
 # ---------------------------------------------------------------------------------------------
 # RAPPIDS planner workloads (SURVEY section 8d, C5): synthetic depth scenes + planner initial states
 # ---------------------------------------------------------------------------------------------

@@ -317,6 +317,54 @@ int agf_offboard_cfg_default(int quad_type, agf_offboard_cfg* out);
 int agf_batch_set_offboard_loop(agf_batch* b, const agf_offboard_cfg* cfg, const agf_offboard_target* targets,
                                 size_t n_targets, const double* per_vehicle_offset);
 
+/* ---- offboard loop: reference generators, tracking controller ---------
+ * What the desired position / velocity / acceleration handed to the offboard controller is, per vehicle and on the
+ * device.  The default (AGF_OFFREF_TARGETS) is the piecewise-constant table of agf_batch_set_offboard_loop.
+ *
+ * AGF_OFFREF_STAGES -- the flight stages of the ROS rates-control node, ExampleVehicleStateMachine::Run
+ *   (AIFS_ROS/hiperlab_rostools/src/QuadMocapRatesControl/ExampleVehicleStateMachine.cpp:93-370), evaluated once per
+ *   offboard period: wait for start -> spool-up (rates command 0.25 g, 0.5 s, :122-153) -> take-off (2 s ramp from
+ *   the position at stage entry to desired_pos, :162-189) -> flight (trajectory `traj_id` 0..5 of :211-287, blended
+ *   in over 2 s, :289-294) -> landing after the stop signal (0.5 m/s, :300-323) -> complete (idle command,
+ *   :326-343).  The start / stop signals (joystick buttons in the node) are the clock reaching start_us / stop_us.
+ *   Safety net, battery check and ROS publishing are not part of the path; in the wait stage no command is sent.
+ * AGF_OFFREF_TRAJECTORY -- Rappids_Simulator's tracking of a planned motion primitive (Simulator/Rappids_Simulator/
+ *   main.cpp:560-618): until start_us the vehicle holds desired_pos with QuadcopterController::Run (:623-627); from
+ *   then on it follows its own quintic (agf_batch_set_offboard_trajectories) with QuadcopterController::RunTracking
+ *   (QuadcopterController.cpp:76-131; main.cpp:629-634): reference position / velocity / acceleration rotated by
+ *   trajAtt and shifted by trajOffset, thrust and angular-velocity feed-forward from the primitive
+ *   (RapidTrajectoryGenerator::GetThrust / GetOmega(t, 0.02), RapidTrajectoryGenerator.cpp:264-286), with the loop's
+ *   own quirks kept: the sample time runs 0.04 s ahead of the tracking stopwatch while t < end (:562-563), and
+ *   the z clamps behind the camera (:580-591). */
+enum { AGF_OFFREF_TARGETS = 0, AGF_OFFREF_STAGES = 1, AGF_OFFREF_TRAJECTORY = 2 };
+enum { AGF_STAGE_WAIT_FOR_START = 0, AGF_STAGE_SPOOL_UP = 1, AGF_STAGE_TAKEOFF = 2, AGF_STAGE_FLIGHT = 3,
+       AGF_STAGE_LANDING = 4, AGF_STAGE_COMPLETE = 5 }; /* ExampleVehicleStateMachine.hpp FlightStage */
+typedef struct agf_offboard_ref {
+  int32_t kind;          /* AGF_OFFREF_* */
+  int32_t traj_id;       /* STAGES: trajID of the flight stage (ExampleVehicleStateMachine.cpp:213), 0..5 */
+  uint64_t start_us;     /* STAGES: start signal; TRAJECTORY: start of tracking (startFlightTime, main.cpp:141) */
+  uint64_t stop_us;      /* STAGES: stop signal (UINT64_MAX: never) */
+  double desired_pos[3]; /* _desiredPosition (QuadMocapRatesControl/main.cpp:82: (0,0,1)) / hover point (main.cpp:505) */
+  double desired_yaw;    /* _desiredYawAngle [rad]; TRAJECTORY: desYawAngleDeg * pi / 180 (main.cpp:244) */
+} agf_offboard_ref;
+/* Needs agf_batch_set_offboard_loop first (period, delay, controller gains; its targets are ignored for the other
+ * kinds, its per-vehicle offsets shift desired_pos).  ref == NULL: back to AGF_OFFREF_TARGETS. */
+int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref);
+/* One motion primitive per vehicle, [count][AGF_OFFTRAJ_DOUBLES]:
+ *   [0..17]  per axis a = 0..2 at [6a..6a+5]: p0, v0, a0, alpha, beta, gamma of SingleAxisTrajectory
+ *            (TrajectoryGenerator/SingleAxisTrajectory.hpp; position = p0 + v0 t + a0 t^2/2 + gamma t^3/6 + beta t^4/24
+ *            + alpha t^5/120)
+ *   [18..20] gravity in the trajectory frame (RapidTrajectoryGenerator constructor, main.cpp:495-497)
+ *   [21]     end time tf
+ *   [22..25] trajAtt quaternion w, x, y, z: world = trajAtt * trajectory frame (main.cpp:519)
+ *   [26..28] trajOffset, world frame (main.cpp:522) */
+#define AGF_OFFTRAJ_DOUBLES 29
+int agf_batch_set_offboard_trajectories(agf_batch* b, const double* traj, size_t first, size_t count);
+/* Per-vehicle state of the reference generator, [count][AGF_OFFSTATE_DOUBLES]: stage, last stage, stage start
+ * [us], position at take-off [3], last commanded position / velocity / acceleration [3 each], commanded yaw. */
+#define AGF_OFFSTATE_DOUBLES 16
+int agf_batch_get_offboard_state(agf_batch* b, double* out, size_t first, size_t count);
+
 /* SimulationObject6DOF::GetTelemetryDataPackets (SimulationObject6DOF.hpp:67;
  * QuadcopterLogic.cpp:621-679), including its side effects (packet counter++, warnings cleared).
  * p1, p2: [count][30]. */

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <limits>
 #include <vector>
 
 #include "../oracle_api.h"
@@ -34,6 +35,7 @@ struct orc_vehicle {
   std::vector<float> hf, hc, hq;
   std::vector<uint32_t> hu;
   uint64_t tick, now_us;
+  std::vector<double> offstate, offtraj;  // reference generators of the offboard loop (n = 1)
   StateArrays<double> arrays() {
     StateArrays<double> a;
     a.sp = (double2*)hp.data();
@@ -163,6 +165,42 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
   v->sh.tc.off_first_target_us = n_targets ? targets[0].time_us : ~0ull;
   v->ts.now_us = v->now_us;
   orc_run(v, dt_us, nticks, nullptr, 0, nullptr, traj);
+}
+
+void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                          const agf_offboard_ref* ref, const double* offset, const double* tr, double* traj) {
+  if (v->hq.empty()) {
+    v->hq.assign(4 * AGF_OFFQ, 0.0f);
+    const char* why = fill_offboard(*cfg, v->sh.off, v->sh.tc);
+    if (why) { fprintf(stderr, "hostsim: %s\n", why); abort(); }
+  }
+  if (v->offstate.empty()) {  // what agf_batch_set_offboard_reference writes
+    v->offstate.assign(AGF_OFFSTATE_DOUBLES, std::numeric_limits<double>::quiet_NaN());
+    v->offstate[0] = AGF_STAGE_WAIT_FOR_START;
+    v->offstate[1] = AGF_STAGE_COMPLETE;
+    v->offstate[2] = double(v->now_us);
+    v->offstate[15] = 0.0;
+  }
+  if (tr) v->offtraj.assign(tr, tr + AGF_OFFTRAJ_DOUBLES);
+  OffboardParams& o = v->sh.off;
+  o.targets = nullptr;
+  o.n_targets = 0;
+  o.offsets = offset;
+  o.ref_kind = ref->kind;
+  o.traj_id = ref->traj_id;
+  o.start_us = ref->start_us;
+  o.stop_us = ref->stop_us;
+  for (int k = 0; k < 3; k++) o.desired[k] = ref->desired_pos[k];
+  o.desired_yaw = ref->desired_yaw;
+  o.state = v->offstate.data();
+  o.traj = v->offtraj.empty() ? nullptr : v->offtraj.data();
+  v->sh.tc.off_first_target_us = 0;
+  v->ts.now_us = v->now_us;
+  orc_run(v, dt_us, nticks, nullptr, 0, nullptr, traj);
+}
+
+void orc_get_offboard_state(orc_vehicle* v, double* out) {
+  for (int k = 0; k < AGF_OFFSTATE_DOUBLES; k++) out[k] = v->offstate.empty() ? 0.0 : v->offstate[k];
 }
 
 void orc_get_full(orc_vehicle* v, orc_full_state* o) {

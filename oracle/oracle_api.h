@@ -84,6 +84,12 @@ void orc_run(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_cmd_entr
 void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
                       const agf_offboard_target* targets, uint32_t n_targets, const double* offset,
                       double* traj /* [nticks][ORC_NTRAJ] or NULL */);
+/* The same loop with a reference generator (agf_offboard_ref: flight stages of the ROS rates-control node, or
+ * Rappids_Simulator's tracking of a motion primitive `tr` [AGF_OFFTRAJ_DOUBLES] with RunTracking). */
+void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                          const agf_offboard_ref* ref, const double* offset, const double* tr,
+                          double* traj /* [nticks][ORC_NTRAJ] or NULL */);
+void orc_get_offboard_state(orc_vehicle* v, double* out /* [AGF_OFFSTATE_DOUBLES] */);
 void orc_get_full(orc_vehicle* v, orc_full_state* out);
 void orc_get_telemetry(orc_vehicle* v, uint8_t p1[AGF_TELEMETRY_PACKET_SIZE],
                        uint8_t p2[AGF_TELEMETRY_PACKET_SIZE]);

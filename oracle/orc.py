@@ -112,6 +112,10 @@ class Oracle:
         if True:
             L.orc_run_offboard.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardTarget), C.c_uint32,
                                            C.c_void_p, C.c_void_p]
+        if hasattr(L, "orc_run_offboard_ref"):
+            L.orc_run_offboard_ref.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardRef), C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+            L.orc_get_offboard_state.argtypes = [vp, C.c_void_p]
         L.orc_get_full.argtypes = [vp, P(FullState)]
         L.orc_time_us.restype = C.c_uint64
         L.orc_time_us.argtypes = [vp]
@@ -212,6 +216,20 @@ class OracleVehicle:
         self.L.orc_run_offboard(self.h, dt_us, nticks, C.byref(cfg), tarr, len(targets),
                                 None if off is None else off.ctypes.data, None if traj is None else traj.ctypes.data)
         return traj
+
+    def run_offboard_ref(self, nticks, cfg, ref, offset=None, trajectory=None, dt_us=2000, record=True):
+        """cfg: abi.OffboardCfg, ref: abi.OffboardRef, trajectory: [29] doubles (AGF_OFFREF_TRAJECTORY)"""
+        traj = np.zeros((nticks, NTRAJ)) if record else None
+        off = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64)
+        tr = None if trajectory is None else np.ascontiguousarray(trajectory, dtype=np.float64)
+        self.L.orc_run_offboard_ref(self.h, dt_us, nticks, C.byref(cfg), C.byref(ref), None if off is None else off.ctypes.data,
+                                    None if tr is None else tr.ctypes.data, None if traj is None else traj.ctypes.data)
+        return traj
+
+    def offboard_state(self):
+        o = np.zeros(abi.OFFSTATE_DOUBLES)
+        self.L.orc_get_offboard_state(self.h, o.ctypes.data)
+        return o
 
     def full(self):
         fs = FullState()

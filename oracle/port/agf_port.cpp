@@ -340,8 +340,7 @@ inline uint16_t encode_ones(float t) {
 // ---------------------------------------------------------------------------------------------
 struct PositionController {
   float natFreq, damping;
-  V3f des_acceleration(V3f estPos, V3f estVel, V3f desPos) const {  // QuadcopterPositionController.hpp:22-27
-    V3f desVel(0, 0, 0), desAcc(0, 0, 0);
+  V3f des_acceleration(V3f estPos, V3f estVel, V3f desPos, V3f desVel = V3f(0, 0, 0), V3f desAcc = V3f(0, 0, 0)) const {  // QuadcopterPositionController.hpp:22-27
     return (desPos - estPos) * natFreq * natFreq + muli(desVel - estVel, 2) * natFreq * damping + desAcc;
   }
 };
@@ -1296,8 +1295,62 @@ inline uint16_t radio_encode_field(float valIn, float limit) {
 struct OffboardCmd {
   float f[4];
 };
+inline OffboardCmd quantise_rates(double thrust, const V3d& w) {
+  const float tx[4] = {float(thrust), float(w.x), float(w.y), float(w.z)};
+  OffboardCmd o;
+  for (int i = 0; i < 4; i++) {
+    const float limit = 35;  // MAX_VAL_CMD_THRUST == MAX_VAL_CMD_ANG_RATES == 35
+    const int q = radio_encode_field(tx[i], limit);
+    o.f[i] = limit * (q - 32768) / float(32768);
+  }
+  return o;
+}
+// shortest rotation taking e3 to `dir`, then the yaw rotation (QuadcopterController.cpp:46-71, 107-127)
+inline Rotf att_from_thrust_dir_yawed(const V3f& dir, double yaw) {
+  const V3f e3(0, 0, 1);
+  Rotf att;
+  const float cosAngle = dir.dot(e3);
+  float angle;
+  if (cosAngle >= (1 - 1e-12f)) {
+    angle = 0;
+  } else if (cosAngle <= -(1 - 1e-12f)) {
+    angle = float(M_PI);
+  } else {
+    angle = m_acos(cosAngle);
+  }
+  V3f rotAx = e3.cross(dir);
+  const float n = rotAx.norm();
+  if (n < 1e-6f) {
+    att = Rotf::identity();
+  } else {
+    att = Rotf::from_rotation_vector(rotAx * (angle / n));
+  }
+  return att * Rotf::from_rotation_vector(V3f(0, 0, float(yaw)));
+}
+// QuadcopterController::RunTracking (QuadcopterController.cpp:76-131) + CreateRatesCommand
+inline OffboardCmd offboard_tracking_command(const agf_offboard_cfg& c, const V3d& curPos, const V3d& curVel, const Rotd& curAtt,
+                                             const V3d& refPos, const V3d& refVel, const V3d& refAcc, double yaw, double refThrust,
+                                             const V3d& refAngVel) {
+  PositionController posCtrl;
+  posCtrl.natFreq = c.pos_control_nat_freq;
+  posCtrl.damping = c.pos_control_damping;
+  AttitudeController attCtr;
+  attCtr.tc_xy = c.att_control_time_const_xy;
+  attCtr.tc_z = c.att_control_time_const_z;
+  const Rotf attf(float(curAtt.v[0]), float(curAtt.v[1]), float(curAtt.v[2]), float(curAtt.v[3]));
+  const V3f accErr = posCtrl.des_acceleration(V3f(curPos), V3f(curVel), V3f(refPos), V3f(refVel), V3f(0.0f, 0.0f, 0.0f));
+  const double outCmdThrust = refThrust + accErr.dot(attf.rotate(V3f(0, 0, 1)));
+  const V3d sum = refAcc + V3d(accErr) + V3d(V3f(0, 0, 9.81f));  // mixed Vec3d/Vec3f sum is carried in double
+  const float normRefProperAcc = float(sum.norm());
+  const V3f refThrustDir(sum / double(normRefProperAcc));
+  const Rotf refAttYawed = att_from_thrust_dir_yawed(refThrustDir, yaw);
+  const V3f angVelErr = attCtr.desired_angular_velocity(refAttYawed, attf);
+  return quantise_rates(outCmdThrust, refAngVel + V3d(angVelErr));
+}
 inline OffboardCmd offboard_rates_command(const agf_offboard_cfg& c, const V3d& curPos, const V3d& curVel, const Rotd& curAtt,
-                                          const V3d& desPos) {
+                                          const V3d& desPos, const V3d& desVel = V3d(0, 0, 0), const V3d& desAcc = V3d(0, 0, 0),
+                                          double yawOverride = std::numeric_limits<double>::quiet_NaN()) {
+  const double yawAngle = (yawOverride == yawOverride) ? yawOverride : c.yaw_angle;
   PositionController posCtrl;
   posCtrl.natFreq = c.pos_control_nat_freq;
   posCtrl.damping = c.pos_control_damping;
@@ -1305,7 +1358,7 @@ inline OffboardCmd offboard_rates_command(const agf_offboard_cfg& c, const V3d& 
   attCtr.tc_xy = c.att_control_time_const_xy;
   attCtr.tc_z = c.att_control_time_const_z;
   const V3f e3(0, 0, 1);
-  const V3f cmdAcc = posCtrl.des_acceleration(V3f(curPos), V3f(curVel), V3f(desPos));
+  const V3f cmdAcc = posCtrl.des_acceleration(V3f(curPos), V3f(curVel), V3f(desPos), V3f(desVel), V3f(desAcc));
   V3f cmdProperAcc = cmdAcc + V3f(0, 0, 9.81f);
   if (cmdProperAcc.norm() > c.max_proper_acc) {  // float norm compared (and divided) in double, product back in float
     cmdProperAcc = cmdProperAcc * float(c.max_proper_acc / cmdProperAcc.norm());
@@ -1333,7 +1386,7 @@ inline OffboardCmd offboard_rates_command(const agf_offboard_cfg& c, const V3d& 
   } else {
     cmdAtt = Rotf::from_rotation_vector(rotAx * (angle / n));
   }
-  Rotf cmdAttYawed = cmdAtt * Rotf::from_rotation_vector(V3f(0, 0, float(c.yaw_angle)));
+  Rotf cmdAttYawed = cmdAtt * Rotf::from_rotation_vector(V3f(0, 0, float(yawAngle)));
   const V3d outCmdAngVel(attCtr.desired_angular_velocity(cmdAttYawed, attf));
   const float tx[4] = {float(outCmdThrust), float(outCmdAngVel.x), float(outCmdAngVel.y), float(outCmdAngVel.z)};
   OffboardCmd o;
@@ -1354,8 +1407,13 @@ struct orc_vehicle {
   uint64_t tick;
   // offboard loop (orc_run_offboard)
   port::Timer* offTimer = nullptr;
-  struct Queued { uint64_t due; port::OffboardCmd cmd; };
+  struct Queued { uint64_t due; port::OffboardCmd cmd; int type; };
   std::deque<Queued> offQueue;
+  // reference generators (orc_run_offboard_ref): ExampleVehicleStateMachine members
+  int stage = AGF_STAGE_WAIT_FOR_START, lastStage = AGF_STAGE_COMPLETE;
+  uint64_t stageStart = 0;
+  port::V3d initPosition, lastPos, lastVel, lastAcc;
+  double cmdYawAngle = 0;
 };
 
 static void record(orc_vehicle* v, double* r) {
@@ -1461,7 +1519,7 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
   for (uint32_t k = 0; k < nticks; k++) {
     if (!v->offQueue.empty() && v->clock.now_us >= v->offQueue.front().due) {  // CommunicationsDelay.hpp:27-35, main.cpp:737-739
       port::RadioMsg m;
-      m.type = AGF_RADIO_EXTERNAL_RATES_CMD;
+      m.type = uint8_t(v->offQueue.front().type);
       m.flags = uint8_t(cfg->radio_flags);
       for (int i = 0; i < 4; i++) m.f[i] = v->offQueue.front().cmd.f[i];
       for (int i = 4; i < 10; i++) m.f[i] = 35.0f * (0 - 32768) / float(32768);  // zero-filled packet bytes decode to -limit; never read
@@ -1483,10 +1541,205 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
       if (offset) des = des + port::V3d(offset[0], offset[1], offset[2]);
       orc_vehicle::Queued q;
       q.due = v->clock.now_us + cfg->delay_us;
+      q.type = AGF_RADIO_EXTERNAL_RATES_CMD;
       q.cmd = port::offboard_rates_command(*cfg, v->quad->pos, v->quad->vel, v->quad->att, des);
       v->offQueue.push_back(q);
     }
   }
+}
+
+namespace port {
+// SingleAxisTrajectory.hpp:57-63; q: p0 v0 a0 alpha beta gamma
+inline double sat_pos(const double* q, double t) {
+  return q[0] + q[1] * t + (1 / 2.0) * q[2] * t * t + (1 / 6.0) * q[5] * t * t * t + (1 / 24.0) * q[4] * t * t * t * t +
+         (1 / 120.0) * q[3] * t * t * t * t * t;
+}
+inline double sat_vel(const double* q, double t) {
+  return q[1] + q[2] * t + (1 / 2.0) * q[5] * t * t + (1 / 6.0) * q[4] * t * t * t + (1 / 24.0) * q[3] * t * t * t * t;
+}
+inline double sat_acc(const double* q, double t) { return q[2] + q[5] * t + (1 / 2.0) * q[4] * t * t + (1 / 6.0) * q[3] * t * t * t; }
+inline V3d prim_at(const double* tr, double t, double (*f)(const double*, double)) { return V3d(f(tr, t), f(tr + 6, t), f(tr + 12, t)); }
+inline V3d prim_thrust_vec(const double* tr, double t) { return prim_at(tr, t, sat_acc) - V3d(tr[18], tr[19], tr[20]); }
+// RapidTrajectoryGenerator::GetOmega (RapidTrajectoryGenerator.cpp:264-286)
+inline V3d prim_omega(const double* tr, double t, double timeStep) {
+  const V3d n0 = prim_thrust_vec(tr, t).unit();
+  const V3d n1 = prim_thrust_vec(tr, t + timeStep).unit();
+  const V3d crossProd = n0.cross(n1);
+  if (crossProd.norm() <= 1e-6) return V3d(0, 0, 0);
+  const V3d n = crossProd.unit();
+  const double d = n0.dot(n1);
+  if (d > 1.0 || d < -1.0 || d != d) return V3d(0, 0, 0);  // errno after acos
+  const double angle = m_acos(d) / timeStep;
+  return angle * n;
+}
+}  // namespace port
+
+void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                          const agf_offboard_ref* ref, const double* offset, const double* tr, double* traj) {
+  using port::V3d;
+  if (!v->offTimer) v->offTimer = new port::Timer(&v->clock);
+  const double period = double(cfg->period_us) * 1e-6;
+  V3d desired(ref->desired_pos[0], ref->desired_pos[1], ref->desired_pos[2]);
+  if (offset) desired = desired + V3d(offset[0], offset[1], offset[2]);
+  const V3d zero(0, 0, 0);
+  for (uint32_t k = 0; k < nticks; k++) {
+    if (!v->offQueue.empty() && v->clock.now_us >= v->offQueue.front().due) {
+      port::RadioMsg m;
+      m.type = uint8_t(v->offQueue.front().type);
+      m.flags = uint8_t(cfg->radio_flags);
+      for (int i = 0; i < 4; i++) m.f[i] = v->offQueue.front().cmd.f[i];
+      for (int i = 4; i < 10; i++) m.f[i] = 35.0f * (0 - 32768) / float(32768);
+      v->quad->logic.set_radio(m);
+      v->offQueue.pop_front();
+    }
+    v->quad->run();
+    if (v->net) v->net->run();
+    if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
+    v->clock.now_us += dt_us;
+    v->tick++;
+    if (!(v->offTimer->seconds_d() > period)) continue;
+    v->offTimer->adjust_by_seconds(-period);
+    const uint64_t now = v->clock.now_us;
+    const V3d estPos = v->quad->pos, estVel = v->quad->vel;
+    const port::Rotd estAtt = v->quad->att;
+    orc_vehicle::Queued q;
+    q.due = now + cfg->delay_us;
+    q.type = AGF_RADIO_EXTERNAL_RATES_CMD;
+    bool send = true;
+    if (ref->kind == AGF_OFFREF_TRAJECTORY) {
+      if (!(now > ref->start_us)) {
+        q.cmd = port::offboard_rates_command(*cfg, estPos, estVel, estAtt, desired, zero, zero, ref->desired_yaw);
+      } else {
+        double traj_t = double(now - ref->start_us) * 1e-6;
+        const double tEnd = tr[21];
+        V3d tp, tv, ta;
+        if (traj_t < tEnd) {
+          traj_t += 0.04;
+          tp = port::prim_at(tr, traj_t, port::sat_pos);
+          tv = port::prim_at(tr, traj_t, port::sat_vel);
+          ta = port::prim_at(tr, traj_t, port::sat_acc);
+        } else {
+          tp = port::prim_at(tr, tEnd, port::sat_pos);
+          tv = zero;
+          ta = zero;
+        }
+        if (tp.z < 0) {
+          tp.z = 0;
+          if (tv.z < 0) tv.z = 0;
+          if (ta.z < 0) ta.z = 0;
+        }
+        const port::Rotd trajAtt(tr[22], tr[23], tr[24], tr[25]);
+        const V3d refPos = trajAtt.rotate(tp) + V3d(tr[26], tr[27], tr[28]);
+        const V3d refVel = trajAtt.rotate(tv), refAcc = trajAtt.rotate(ta);
+        const double refThrust = port::prim_thrust_vec(tr, traj_t).norm();
+        const V3d refAngVel = (estAtt.inverse() * trajAtt).rotate(port::prim_omega(tr, traj_t, 0.02));
+        q.cmd = port::offboard_tracking_command(*cfg, estPos, estVel, estAtt, refPos, refVel, refAcc, ref->desired_yaw, refThrust,
+                                                refAngVel);
+      }
+    } else {
+      const bool shouldStart = now >= ref->start_us, shouldStop = now >= ref->stop_us;
+      const bool stageChange = v->stage != v->lastStage;
+      v->lastStage = v->stage;
+      if (stageChange) v->stageStart = now;
+      const double ts = double(now - v->stageStart) * 1e-6;
+      switch (v->stage) {
+        case AGF_STAGE_WAIT_FOR_START:
+          if (shouldStart) v->stage = AGF_STAGE_SPOOL_UP;
+          send = false;
+          break;
+        case AGF_STAGE_SPOOL_UP:
+          q.cmd = port::quantise_rates(9.81 * 0.25, zero);
+          if (ts > 0.5) v->stage = AGF_STAGE_TAKEOFF;
+          break;
+        case AGF_STAGE_TAKEOFF: {
+          if (stageChange) v->initPosition = estPos;
+          double frac = ts / 2.0;
+          if (frac >= 1.0) {
+            v->stage = AGF_STAGE_FLIGHT;
+            frac = 1.0;
+          }
+          const V3d cmdPos = (1 - frac) * v->initPosition + frac * desired;
+          q.cmd = port::offboard_rates_command(*cfg, estPos, estVel, estAtt, cmdPos, zero, zero, v->cmdYawAngle);
+        } break;
+        case AGF_STAGE_FLIGHT: {
+          V3d cmdPos(0, 0, 0), cmdVel(0, 0, 0), cmdAcc(0, 0, 0);
+          const double t = ts;
+          const double frac = std::min(t / 2.0, 1.0);
+          const double yaw0 = ref->desired_yaw;
+          switch (ref->traj_id) {
+            case 0:
+              cmdPos = desired;
+              v->cmdYawAngle = 0;
+              break;
+            case 1: {
+              const double radius = 1.0, angSpeed = 0.5;
+              cmdPos = V3d(0.0, -2.0, desired.z) + radius * V3d(port::m_cos(angSpeed * t), port::m_sin(angSpeed * t), 0);
+              cmdVel = (radius * angSpeed) * V3d(-port::m_sin(angSpeed * t), port::m_cos(angSpeed * t), 0);
+              cmdAcc = (radius * (angSpeed * angSpeed)) * V3d(-port::m_cos(angSpeed * t), -port::m_sin(angSpeed * t), 0);
+              v->cmdYawAngle = yaw0 + angSpeed * t;
+            } break;
+            case 2: {
+              const double amplitude = 1.0, angFreq = 2.0;
+              cmdPos = desired + amplitude * V3d(0, port::m_sin(angFreq * t), 0);
+              cmdVel = (amplitude * angFreq) * V3d(0, port::m_cos(angFreq * t), 0);
+              cmdAcc = (amplitude * (angFreq * angFreq)) * V3d(0, -port::m_sin(angFreq * t), 0);
+              v->cmdYawAngle = yaw0;
+            } break;
+            case 3: {
+              const double radius = 0.5, angSpeed = 1;
+              cmdPos = V3d(0.0, 0.0, desired.z) + radius * V3d(port::m_cos(angSpeed * t), port::m_sin(angSpeed * t), 0);
+              cmdVel = (radius * angSpeed) * V3d(-port::m_sin(angSpeed * t), port::m_cos(angSpeed * t), 0);
+              cmdAcc = (radius * (angSpeed * angSpeed)) * V3d(-port::m_cos(angSpeed * t), -port::m_sin(angSpeed * t), 0);
+              v->cmdYawAngle = 0;
+            } break;
+            case 4: {
+              const double radius = 0.5, angSpeed = 0.5;
+              cmdPos = V3d(0.0, 0.0, desired.z) +
+                       radius * V3d(port::m_cos(angSpeed * t), port::m_sin(angSpeed * t), port::m_cos(angSpeed * t * 4));
+              cmdVel = (radius * angSpeed) * V3d(-port::m_sin(angSpeed * t), port::m_cos(angSpeed * t), -port::m_sin(angSpeed * t * 4));
+              cmdAcc = (radius * (angSpeed * angSpeed)) *
+                       V3d(-port::m_cos(angSpeed * t), -port::m_sin(angSpeed * t), -port::m_cos(angSpeed * t * 4));
+              v->cmdYawAngle = angSpeed * t;
+            } break;
+            default:
+              cmdPos = desired;
+              v->cmdYawAngle = 0.2 * t;
+              break;
+          }
+          v->lastPos = (1 - frac) * desired + frac * cmdPos;
+          v->lastVel = frac * cmdVel;
+          v->lastAcc = frac * cmdAcc;
+          q.cmd = port::offboard_rates_command(*cfg, estPos, estVel, estAtt, v->lastPos, v->lastVel, v->lastAcc, v->cmdYawAngle);
+          if (shouldStop) v->stage = AGF_STAGE_LANDING;
+        } break;
+        case AGF_STAGE_LANDING: {
+          const double frac = std::min(ts / 2.0, 1.0);
+          const V3d land(0, 0, -0.5);
+          const V3d cmdPos = v->lastPos + ts * land;
+          if (cmdPos.z < 0) v->stage = AGF_STAGE_COMPLETE;
+          q.cmd = port::offboard_rates_command(*cfg, estPos, estVel, estAtt, (1 - frac) * v->lastPos + frac * cmdPos,
+                                               (1 - frac) * v->lastVel + frac * land, (1 - frac) * v->lastAcc + frac * zero,
+                                               v->cmdYawAngle);
+        } break;
+        default:
+          q.type = AGF_RADIO_IDLE_CMD;
+          for (int i = 0; i < 4; i++) q.cmd.f[i] = 35.0f * (0 - 32768) / float(32768);  // zero bytes decode to -limit; never read
+          break;
+      }
+    }
+    if (send) v->offQueue.push_back(q);
+  }
+}
+
+void orc_get_offboard_state(orc_vehicle* v, double* o) {
+  o[0] = v->stage;
+  o[1] = v->lastStage;
+  o[2] = double(v->stageStart);
+  const port::V3d* q[4] = {&v->initPosition, &v->lastPos, &v->lastVel, &v->lastAcc};
+  for (int i = 0; i < 4; i++) {
+    o[3 + 3 * i] = q[i]->x; o[4 + 3 * i] = q[i]->y; o[5 + 3 * i] = q[i]->z;
+  }
+  o[15] = v->cmdYawAngle;
 }
 
 static void dump3(const port::LPF2<port::V3f>& f, float out[4][3]) {

@@ -38,6 +38,7 @@
 #include "Components/Simulation/UWBNetwork.hpp"
 #include "Components/Simulation/CommunicationsDelay.hpp"
 #include "Components/Offboard/QuadcopterController.hpp"
+#include "Components/TrajectoryGenerator/RapidTrajectoryGenerator.hpp"
 #undef private
 #undef protected
 
@@ -56,6 +57,11 @@ struct orc_vehicle {
   // offboard loop (orc_run_offboard): created on first use
   std::unique_ptr<Timer> offTimer;
   std::unique_ptr<Simulation::CommunicationsDelay<RadioTypes::RadioMessageDecoded::RawMessage>> offChannel;
+  // reference generators of the offboard loop (orc_run_offboard_ref)
+  int stage = AGF_STAGE_WAIT_FOR_START, lastStage = AGF_STAGE_COMPLETE;  // ExampleVehicleStateMachine.cpp:10-11
+  std::unique_ptr<Timer> stageTimer;
+  Vec3d initPosition, lastPos, lastVel, lastAcc;  // NaN until set (Vec3.hpp:35), as the node's members
+  double cmdYawAngle = 0;                         // ExampleVehicleStateMachine.cpp:19
 };
 
 template<typename LPF>
@@ -217,6 +223,219 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
       v->offChannel->AddMessage(rawMsg);                                 // main.cpp:673
     }
   }
+}
+
+// The same loop with the desired state coming from a reference generator (include/agrifly_b200.h "offboard loop:
+// reference generators"): the stage logic of ExampleVehicleStateMachine::Run restated line by line around the
+// reference's own Timer / QuadcopterController / RadioTypes (the node itself needs ROS), and Rappids_Simulator's
+// trajectory tracking (main.cpp:560-634) around the reference's RapidTrajectoryGenerator and RunTracking.
+void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg,
+                          const agf_offboard_ref* ref, const double* offset, const double* tr /* [AGF_OFFTRAJ_DOUBLES] */,
+                          double* traj) {
+  if (!v->offTimer) {
+    v->offTimer.reset(new Timer(&v->timer));
+    v->offChannel.reset(new Simulation::CommunicationsDelay<RadioTypes::RadioMessageDecoded::RawMessage>(
+        &v->timer, double(cfg->delay_us) * 1e-6));
+    v->offChannel->_delayTime_us = cfg->delay_us;
+  }
+  if (!v->stageTimer) v->stageTimer.reset(new Timer(&v->timer));
+  Offboard::QuadcopterController ctrl;
+  ctrl.SetParameters(cfg->pos_control_nat_freq, cfg->pos_control_damping, cfg->att_control_time_const_xy,
+                     cfg->att_control_time_const_z);
+  ctrl._minVerticalProperAcceleration = cfg->min_vertical_proper_acc;
+  ctrl._maxProperAcc = cfg->max_proper_acc;
+  ctrl._minProperAcc = cfg->min_proper_acc;
+  const double period = double(cfg->period_us) * 1e-6;
+  Vec3d _desiredPosition(ref->desired_pos[0], ref->desired_pos[1], ref->desired_pos[2]);
+  if (offset) _desiredPosition = _desiredPosition + Vec3d(offset[0], offset[1], offset[2]);
+  const double _desiredYawAngle = ref->desired_yaw;
+  std::unique_ptr<RapidQuadrocopterTrajectoryGenerator::RapidTrajectoryGenerator> _traj;
+  Rotationd trajAtt = Rotationd::Identity();
+  Vec3d trajOffset(0, 0, 0);
+  double trajEndTime = 0;
+  if (ref->kind == AGF_OFFREF_TRAJECTORY) {
+    _traj.reset(new RapidQuadrocopterTrajectoryGenerator::RapidTrajectoryGenerator(
+        Vec3d(tr[0], tr[6], tr[12]), Vec3d(tr[1], tr[7], tr[13]), Vec3d(tr[2], tr[8], tr[14]), Vec3d(tr[18], tr[19], tr[20])));
+    for (int a = 0; a < 3; a++) {
+      _traj->_axis[a]._a = tr[6 * a + 3];
+      _traj->_axis[a]._b = tr[6 * a + 4];
+      _traj->_axis[a]._g = tr[6 * a + 5];
+    }
+    trajEndTime = tr[21];
+    trajAtt = Rotationd(tr[22], tr[23], tr[24], tr[25]);
+    trajOffset = Vec3d(tr[26], tr[27], tr[28]);
+  }
+  for (uint32_t k = 0; k < nticks; k++) {
+    if (v->offChannel->HaveNewMessage()) v->quad->SetCommandRadioMsg(v->offChannel->GetMessage());
+    v->quad->Run();
+    if (v->net) v->net->Run();
+    if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
+    v->timer.AdvanceMicroSeconds(dt_us);
+    v->tick++;
+    if (!(v->offTimer->GetSeconds<double>() > period)) continue;  // main.cpp:471
+    v->offTimer->AdjustTimeBySeconds(-period);                     // main.cpp:476
+    const uint64_t now = v->timer.GetMicroSeconds();
+    // estimate = truth
+    const Vec3d estPos = v->quad->GetPosition(), estVel = v->quad->GetVelocity();
+    const Rotationd estAtt = v->quad->GetAttitude();
+    RadioTypes::RadioMessageDecoded::RawMessage rawMsg;
+    memset(rawMsg.raw, 0, sizeof(rawMsg.raw));
+    bool send = true;
+    Vec3d cmdAngVel;
+    double cmdThrust;
+    if (ref->kind == AGF_OFFREF_TRAJECTORY) {
+      if (!(now > ref->start_us)) {  // main.cpp:623-627 (t < startFlightTime; the clocks are integer microseconds)
+        ctrl.Run(estPos, estVel, estAtt, _desiredPosition, Vec3d(0, 0, 0), Vec3d(0, 0, 0), _desiredYawAngle, cmdAngVel,
+                 cmdThrust);
+      } else {
+        double traj_t = double(now - ref->start_us) * 1e-6;  // trackTrajTime.GetSeconds<double>() (main.cpp:560)
+        Vec3d trajPos, trajVel, trajAcc;
+        if (traj_t < trajEndTime) {  // main.cpp:562-571
+          traj_t += 0.04;
+          trajPos = _traj->GetPosition(traj_t);
+          trajVel = _traj->GetVelocity(traj_t);
+          trajAcc = _traj->GetAcceleration(traj_t);
+        } else {
+          trajPos = _traj->GetPosition(trajEndTime);
+          trajVel = Vec3d(0, 0, 0);
+          trajAcc = Vec3d(0, 0, 0);
+        }
+        if (trajPos.z < 0) {  // main.cpp:580-591
+          trajPos.z = 0;
+          if (trajVel.z < 0) trajVel.z = 0;
+          if (trajAcc.z < 0) trajAcc.z = 0;
+        }
+        Vec3d refPos = trajAtt * trajPos + trajOffset;  // main.cpp:593-600
+        Vec3d refVel = trajAtt * trajVel;
+        Vec3d refAcc = trajAtt * trajAcc;
+        double refThrust = _traj->GetThrust(traj_t);
+        Vec3d refAngVel = estAtt.Inverse() * trajAtt * _traj->GetOmega(traj_t, 0.02);
+        Rotationf cmdAtt;
+        ctrl.RunTracking(estPos, estVel, estAtt, refPos, refVel, refAcc, _desiredYawAngle, refThrust, refAngVel,
+                         cmdAngVel, cmdThrust, cmdAtt);  // main.cpp:629-634
+      }
+      RadioTypes::RadioMessageDecoded::CreateRatesCommand(uint8_t(cfg->radio_flags), float(cmdThrust), Vec3f(cmdAngVel),
+                                                          rawMsg.raw);
+    } else {  // AGF_OFFREF_STAGES: ExampleVehicleStateMachine::Run(shouldStart, shouldStop)
+      const bool shouldStart = now >= ref->start_us, shouldStop = now >= ref->stop_us;
+      bool stageChange = v->stage != v->lastStage;  // :96-100
+      v->lastStage = v->stage;
+      if (stageChange) v->stageTimer->Reset();
+      auto runController = [&](Vec3d desPos, Vec3d desVel, Vec3d desAcc) {  // RunControllerAndUpdateEstimator :407-432
+        ctrl.Run(estPos, estVel, estAtt, desPos, desVel, desAcc, v->cmdYawAngle, cmdAngVel, cmdThrust);
+        RadioTypes::RadioMessageDecoded::CreateRatesCommand(uint8_t(cfg->radio_flags), float(cmdThrust), Vec3f(cmdAngVel),
+                                                            rawMsg.raw);
+      };
+      switch (v->stage) {
+        case AGF_STAGE_WAIT_FOR_START:  // :113-120
+          if (shouldStart) v->stage = AGF_STAGE_SPOOL_UP;
+          send = false;
+          break;
+        case AGF_STAGE_SPOOL_UP: {  // :122-160
+          double const motorSpoolUpTime = 0.5;
+          double const spoolUpThrustByWeight = 0.25;
+          cmdThrust = 9.81 * spoolUpThrustByWeight;
+          cmdAngVel = Vec3d(0, 0, 0);
+          RadioTypes::RadioMessageDecoded::CreateRatesCommand(uint8_t(cfg->radio_flags), float(cmdThrust), Vec3f(cmdAngVel),
+                                                              rawMsg.raw);
+          if (v->stageTimer->GetSeconds<double>() > motorSpoolUpTime) v->stage = AGF_STAGE_TAKEOFF;
+        } break;
+        case AGF_STAGE_TAKEOFF: {  // :162-189
+          if (stageChange) v->initPosition = estPos;
+          double const takeOffTime = 2.0;
+          double frac = v->stageTimer->GetSeconds<double>() / takeOffTime;
+          if (frac >= 1.0) {
+            v->stage = AGF_STAGE_FLIGHT;
+            frac = 1.0;
+          }
+          Vec3d cmdPos = (1 - frac) * v->initPosition + frac * _desiredPosition;
+          runController(cmdPos, Vec3d(0, 0, 0), Vec3d(0, 0, 0));
+        } break;
+        case AGF_STAGE_FLIGHT: {  // :191-298
+          Vec3d cmdPos(0, 0, 0), cmdVel(0, 0, 0), cmdAcc(0, 0, 0);
+          double t = v->stageTimer->GetSeconds<double>();
+          double const getIntoActionTime = 2.0;
+          double frac = std::min(t / getIntoActionTime, 1.0);
+          switch (ref->traj_id) {
+            case 0:
+              cmdPos = _desiredPosition;
+              cmdVel = Vec3d(0, 0, 0);
+              cmdAcc = Vec3d(0, 0, 0);
+              v->cmdYawAngle = 0;
+              break;
+            case 1: {
+              Vec3d circleCenter(0.0, -2.0, _desiredPosition.z);
+              double radius = 1.0;
+              double angSpeed = 0.5;
+              cmdPos = circleCenter + radius * Vec3d(cos(angSpeed * t), sin(angSpeed * t), 0);
+              cmdVel = radius * angSpeed * Vec3d(-sin(angSpeed * t), cos(angSpeed * t), 0);
+              cmdAcc = radius * pow(angSpeed, 2) * Vec3d(-cos(angSpeed * t), -sin(angSpeed * t), 0);
+              v->cmdYawAngle = _desiredYawAngle + angSpeed * t;
+            } break;
+            case 2: {
+              double amplitude = 1.0;
+              double angFreq = 2.0;
+              cmdPos = _desiredPosition + amplitude * Vec3d(0, sin(angFreq * t), 0);
+              cmdVel = amplitude * angFreq * Vec3d(0, cos(angFreq * t), 0);
+              cmdAcc = amplitude * pow(angFreq, 2) * Vec3d(0, -sin(angFreq * t), 0);
+              v->cmdYawAngle = _desiredYawAngle;
+            } break;
+            case 3: {
+              Vec3d circleCenter(0.0, 0.0, _desiredPosition.z);
+              double radius = 0.5;
+              double angSpeed = 1;
+              cmdPos = circleCenter + radius * Vec3d(cos(angSpeed * t), sin(angSpeed * t), 0);
+              cmdVel = radius * angSpeed * Vec3d(-sin(angSpeed * t), cos(angSpeed * t), 0);
+              cmdAcc = radius * pow(angSpeed, 2) * Vec3d(-cos(angSpeed * t), -sin(angSpeed * t), 0);
+              v->cmdYawAngle = 0;
+            } break;
+            case 4: {
+              Vec3d circleCenter(0.0, 0.0, _desiredPosition.z);
+              double radius = 0.5;
+              double angSpeed = 0.5;
+              cmdPos = circleCenter + radius * Vec3d(cos(angSpeed * t), sin(angSpeed * t), cos(angSpeed * t * 4));
+              cmdVel = radius * angSpeed * Vec3d(-sin(angSpeed * t), cos(angSpeed * t), -sin(angSpeed * t * 4));
+              cmdAcc = radius * pow(angSpeed, 2) * Vec3d(-cos(angSpeed * t), -sin(angSpeed * t), -cos(angSpeed * t * 4));
+              v->cmdYawAngle = angSpeed * t;
+            } break;
+            case 5:
+              cmdPos = _desiredPosition;
+              v->cmdYawAngle = 0.2 * t;
+              break;
+          }
+          v->lastPos = (1 - frac) * _desiredPosition + frac * cmdPos;
+          v->lastVel = frac * cmdVel;
+          v->lastAcc = frac * cmdAcc;
+          runController(v->lastPos, v->lastVel, v->lastAcc);
+          if (shouldStop) v->stage = AGF_STAGE_LANDING;
+        } break;
+        case AGF_STAGE_LANDING: {  // :300-324
+          double const LANDING_SPEED = 0.5;
+          double const getIntoActionTime = 2.0;
+          double frac = std::min(v->stageTimer->GetSeconds<double>() / getIntoActionTime, 1.0);
+          Vec3d cmdPos = v->lastPos + v->stageTimer->GetSeconds<double>() * Vec3d(0, 0, -LANDING_SPEED);
+          if (cmdPos.z < 0) v->stage = AGF_STAGE_COMPLETE;
+          runController((1 - frac) * v->lastPos + frac * cmdPos, (1 - frac) * v->lastVel + frac * Vec3d(0, 0, -LANDING_SPEED),
+                        (1 - frac) * v->lastAcc + frac * Vec3d(0, 0, 0));
+        } break;
+        default:  // AGF_STAGE_COMPLETE :326-343
+          RadioTypes::RadioMessageDecoded::CreateIdleCommand(uint8_t(cfg->radio_flags), rawMsg.raw);
+          break;
+      }
+    }
+    if (send) v->offChannel->AddMessage(rawMsg);
+  }
+}
+
+void orc_get_offboard_state(orc_vehicle* v, double* o) {
+  o[0] = v->stage;
+  o[1] = v->lastStage;
+  o[2] = v->stageTimer ? double(v->stageTimer->_lastResetTime_usec) : 0.0;
+  const Vec3d* q[4] = {&v->initPosition, &v->lastPos, &v->lastVel, &v->lastAcc};
+  for (int i = 0; i < 4; i++) {
+    o[3 + 3 * i] = q[i]->x; o[4 + 3 * i] = q[i]->y; o[5 + 3 * i] = q[i]->z;
+  }
+  o[15] = v->cmdYawAngle;
 }
 
 void orc_get_full(orc_vehicle* v, orc_full_state* o) {

@@ -72,3 +72,24 @@ def make_batch_offboard(agf, sc, n=1, offsets=None, cfg=None, ocfg=None, **kw):
     b.set_state13(s13)
     b.set_offboard_loop(ocfg if ocfg is not None else agf.offboard_cfg(sc["quad_type"]), sc["targets"], offsets)
     return b
+
+
+def run_oracle_offboard_ref(O, agf, sc, chunks=None, offset=None, nticks=None):
+    """Offboard loop with a reference generator (flight stages / primitive tracking) on an oracle."""
+    v = O.vehicle(cfg_for(agf, sc), uwb_comm_period=sc["uwb_comm_period"])
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    oc = agf.offboard_cfg(sc["quad_type"])
+    ref = agf.offboard_ref(**sc["ref"])
+    rec = None if sc["primitive"] is None else agf.primitive_record(**sc["primitive"])
+    n = nticks or sc["nticks"]
+    parts = [v.run_offboard_ref(c, oc, ref, offset=offset, trajectory=rec) for c in (chunks or [n])]
+    return np.vstack(parts), v
+
+
+def make_batch_offboard_ref(agf, sc, n=1, offsets=None, primitives=None, **kw):
+    b = make_batch_offboard(agf, dict(sc, targets=[(0, (0.0, 0.0, 0.0))]), n=n, offsets=offsets, **kw)
+    if sc["primitive"] is not None or primitives is not None:
+        recs = primitives if primitives is not None else np.tile(agf.primitive_record(**sc["primitive"]), (n, 1))
+        b.set_offboard_trajectories(recs)
+    b.set_offboard_reference(**sc["ref"])
+    return b

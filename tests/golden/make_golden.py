@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import agrifly_b200 as agf  # noqa: E402
 import orc  # noqa: E402
 from agrifly_b200 import scenarios as scen  # noqa: E402
-from common import run_oracle, run_oracle_offboard  # noqa: E402
+from common import run_oracle, run_oracle_offboard, run_oracle_offboard_ref  # noqa: E402
 
 
 def sample_ticks(n):
@@ -54,6 +54,14 @@ def main():
         out[key + "/traj"] = tr[idx]
         for k, val in v.full().items():
             out[key + "/full/" + k] = np.asarray(val)
+        # reference generators of the offboard loop: flight stages (ROS rates-control node) and primitive tracking
+        for sc in [scen.stages_scenario(t) for t in range(6)] + [scen.tracking_scenario()]:
+            tr, v = run_oracle_offboard_ref(O, agf, sc)
+            idx = sample_ticks(len(tr))
+            key = "%s/%s" % (flavour, sc["name"])
+            out[key + "/ticks"] = idx
+            out[key + "/traj"] = tr[idx]
+            out[key + "/offstate"] = v.offboard_state()
     # codec known-answer vectors from the reference's own RadioTypes / TelemetryPacket code
     O = orc.Oracle("ref-glibc")
     rng = np.random.default_rng(7)

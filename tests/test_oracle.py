@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from common import bit_equal, run_oracle, run_oracle_offboard
+from common import bit_equal, run_oracle, run_oracle_offboard, run_oracle_offboard_ref
 from conftest import ROOT, oracle_or_skip
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
@@ -84,6 +84,57 @@ def test_offboard_loop_device_step_on_host_matches_port(agf, orc_mod, port_share
     a, _ = run_oracle_offboard(port_shared, agf, sc, offset=off)
     b, _ = run_oracle_offboard(H, agf, sc, chunks=[1, 1, 13, 985, 1500], offset=off)
     assert bit_equal(a, b)
+
+
+REF_SCENARIOS = ["stages0", "stages1", "stages2", "stages3", "stages4", "stages5", "tracking"]
+
+
+def ref_scenario(agf, name):
+    return agf.scenarios.tracking_scenario() if name == "tracking" else agf.scenarios.stages_scenario(int(name[-1]))
+
+
+@pytest.mark.parametrize("math", ["glibc", "shared"])
+@pytest.mark.parametrize("name", REF_SCENARIOS)
+def test_offboard_reference_generators_port_matches_reference(agf, orc_mod, math, name):
+    """flight stages of the ROS rates-control node (spool-up, take-off ramp, the six flight
+    trajectories, landing, idle) and Rappids_Simulator's primitive tracking (RunTracking + GetThrust/GetOmega
+    feed-forward) restated in the port: golden vectors from the reference, and the live reference where present."""
+    sc = ref_scenario(agf, name)
+    P = oracle_or_skip(orc_mod, "port-" + math)
+    tr, v = run_oracle_offboard_ref(P, agf, sc, chunks=[1234, sc["nticks"] - 1234])
+    key = "ref-%s/%s" % (math, name)
+    assert bit_equal(tr[GOLD[key + "/ticks"]], GOLD[key + "/traj"])
+    assert bit_equal(v.offboard_state(), GOLD[key + "/offstate"])
+    assert tr[-1, 35] == 0  # no panic
+    if name == "tracking":  # the primitive ends 1.5 m ahead in a frame yawed by 0.4 rad, 0.3 m up
+        end = np.array([0.2, -0.1, 2.0]) + np.array([1.5 * np.cos(0.4) - 0.5 * np.sin(0.4), 1.5 * np.sin(0.4) + 0.5 * np.cos(0.4), 0.3])
+        assert np.linalg.norm(tr[-1, 0:3] - end) < 0.1
+    else:  # took off, flew at 1 m, landed, idles
+        assert abs(tr[2500, 2] - 1.0) < (0.55 if name == "stages4" else 0.05)  # trajectory 4 oscillates in height
+        assert tr[-1, 2] < 0.02 and v.offboard_state()[0] == agf.abi.STAGE_COMPLETE
+    if orc_mod.available("ref-" + math):
+        a, _ = run_oracle_offboard_ref(orc_mod.Oracle("ref-" + math), agf, sc)
+        assert bit_equal(a, tr)
+
+
+def test_offboard_reference_generators_device_code_on_host(agf, orc_mod, port_shared):
+    """The product's device code for the generators and the tracking controller (agf_step.cuh offboard_generate),
+    compiled for the host, equals the port bit for bit, also across launch boundaries and with a set-point offset."""
+    if not orc_mod.available("hostsim-shared"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "hostsim"], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("hostsim not buildable here: " + r.stderr[-300:])
+    H = orc_mod.Oracle("hostsim-shared")
+    if not hasattr(H.L, "orc_run_offboard_ref"):
+        pytest.skip("stale hostsim build")
+    for name in ("stages1", "stages4", "tracking"):
+        sc = ref_scenario(agf, name)
+        off = (0.3, -0.2, 0.1)
+        a, va = run_oracle_offboard_ref(port_shared, agf, sc, offset=off)
+        b, vb = run_oracle_offboard_ref(H, agf, sc, chunks=[1, 1, 13, 985, sc["nticks"] - 1000], offset=off)
+        assert bit_equal(a, b), name
+        if name != "tracking":
+            assert bit_equal(va.offboard_state(), vb.offboard_state())
 
 
 def test_reference_golden_still_reproducible(agf, orc_mod):

@@ -12,7 +12,8 @@ import os
 import numpy as np
 import pytest
 
-from common import bit_equal, cfg_for, make_batch, make_batch_offboard, rel_err, run_oracle, run_oracle_offboard
+from common import (bit_equal, cfg_for, make_batch, make_batch_offboard, make_batch_offboard_ref, rel_err, run_oracle,
+                    run_oracle_offboard, run_oracle_offboard_ref)
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
@@ -192,6 +193,77 @@ def test_offboard_loop_fast_variants_and_object_api(agf, port_glibc):
     assert bit_equal(b1.record(), b2.record())
     b1.close()
     b2.close()
+
+
+@pytest.mark.parametrize("name", ["stages1", "stages3", "stages4", "tracking"])
+def test_offboard_reference_generators_parity(agf, port_shared, name):
+    """the flight-stage state machine of the ROS rates-control node and Rappids_Simulator's primitive
+    tracking (RunTracking with thrust / angular-velocity feed-forward) evaluated per vehicle inside the kernel.
+    Parity variant == oracle bit for bit for every vehicle (own set-point offset / own primitive), across launch
+    boundaries, including the per-vehicle stage state; the split Run()/advance path equals the fused one."""
+    s = agf.scenarios
+    sc = s.tracking_scenario() if name == "tracking" else s.stages_scenario(int(name[-1]))
+    n = 4
+    offs = np.array([[0, 0, 0], [0.3, -0.2, 0.1], [-1.0, 0.5, 0.4], [0.01, 0.02, 0.03]], float)
+    prims = None
+    if name == "tracking":
+        prims = np.array([agf.primitive_record(pf=(1.5 - 0.2 * i, 0.5, 0.3 + 0.1 * i), T=2.5 + 0.25 * i, offset=(0.2, -0.1, 2.0),
+                                               att=(np.cos(0.2 + 0.1 * i), 0.0, 0.0, np.sin(0.2 + 0.1 * i))) for i in range(n)])
+        offs = None
+    b = make_batch_offboard_ref(agf, sc, n=n, offsets=offs, primitives=prims)
+    left = sc["nticks"]
+    for c in (1, 2, 997, 1000):
+        b.run(c)
+        left -= c
+    b.run(left)
+    got = b.record()
+    for i in range(n):
+        sci = dict(sc)
+        if prims is not None:
+            sci["primitive"] = None
+            v = port_shared.vehicle(cfg_for(agf, sc), uwb_comm_period=0.0)
+            v.set_state(pos=sc["pos"], att=sc["att"])
+            ref = v.run_offboard_ref(sc["nticks"], agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), trajectory=prims[i])
+        else:
+            ref, v = run_oracle_offboard_ref(port_shared, agf, sc, offset=offs[i])
+            assert bit_equal(b.offboard_state(i, 1)[0], v.offboard_state()), i
+        assert bit_equal(got[i], ref[-1]), (name, i, got[i][0:3], ref[-1][0:3])
+    assert np.all(got[:, 35] == 0)
+    b.close()
+    b1 = make_batch_offboard_ref(agf, sc, n=2, primitives=None if prims is None else prims[:2])
+    b1.run(2600)
+    b2 = make_batch_offboard_ref(agf, sc, n=2, primitives=None if prims is None else prims[:2])
+    for _ in range(2600):
+        b2.run(1, dt_us=0)
+        b2.advance_clock(2000)
+    assert bit_equal(b1.record(), b2.record())
+    b1.close()
+    b2.close()
+
+
+def test_offboard_reference_generators_fast_variants(agf, port_glibc):
+    """Fast FP64 / FP32 kernels fly the stages and the tracked primitive within the offboard loop's stated tolerance
+    (position 1e-3 / 5e-3 relative to the oracle with glibc libm), also for a population on the balanced schedule."""
+    s = agf.scenarios
+    for sc, nt in ((s.stages_scenario(3), 4000), (s.tracking_scenario(), 3400)):
+        ref, _ = run_oracle_offboard_ref(port_glibc, agf, sc, nticks=nt)
+        for prec in (agf.abi.PREC_FP64, agf.abi.PREC_FP32):
+            b = make_batch_offboard_ref(agf, sc, n=3, precision=prec, math=agf.abi.MATH_FAST)
+            b.run(nt)
+            got = b.record()[0]
+            ep = rel_err(got[0:3], ref[-1, 0:3])
+            print("%s fast prec=%d: rel err position %.3e" % (sc["name"], prec, ep))
+            assert ep < (1e-3 if prec == agf.abi.PREC_FP64 else 5e-3)
+            b.close()
+    sc = s.stages_scenario(1)
+    n = 148 * 4 * 128 + 333
+    b = make_batch_offboard_ref(agf, sc, n=n, precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST, telemetry_warnings=False)
+    b.run(2001)
+    b.run(1999)
+    big = b.record()
+    st = b.offboard_state()
+    b.close()
+    assert bit_equal(big, np.tile(big[0], (n, 1))) and np.all(st[:, 0] == agf.abi.STAGE_FLIGHT)
 
 
 def test_monte_carlo_population_parity(agf, port_shared):
