@@ -342,3 +342,35 @@ AGF_HD double agf_cbrt_pos(double x) {
     y = AGF_DDIV(AGF_DADD(AGF_DMUL(2.0, y), AGF_DDIV(m, AGF_DMUL(y, y))), 3.0);
   return AGF_DMUL(y, agf_bits2d((long long)(1023 + k + eadj) << 52));
 }
+
+// ---------------------------------------------------------------------------
+// exp(x): the offboard state estimator's discrete angular-velocity lag exp(-dt / tau)
+// (Components/Offboard/MocapStateEstimator.cpp:96,164) has a data-dependent argument, so it needs
+// the same routine on both sides.  x = k ln2 + r with |r| <= ln2 / 2 (two-part ln2, the products with
+// k are exact), exp(r) = 1 + 2 r / (2 - c(r)) - r ... in the rational form R(r^2), result scaled by 2^k.
+// ---------------------------------------------------------------------------
+AGF_HD double agf_exp(double x) {
+  if (x != x) return x;
+  if (x > 709.0) return 1.0e308 * 10.0;  // overflow (+inf)
+  if (x < -745.0) return 0.0;
+  const double ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10;
+  const double invln2 = 1.44269504088896338700e+00;
+  const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  const double fk = AGF_DSUB(AGF_DADD(AGF_DMUL(x, invln2), magic), magic);
+  const int k = (int)fk;
+  const double hi = AGF_DSUB(x, AGF_DMUL(fk, ln2hi));
+  const double lo = AGF_DMUL(fk, ln2lo);
+  const double r = AGF_DSUB(hi, lo);
+  const double t = AGF_DMUL(r, r);
+  double c = AGF_DADD(P4, AGF_DMUL(t, P5));
+  c = AGF_DADD(P3, AGF_DMUL(t, c));
+  c = AGF_DADD(P2, AGF_DMUL(t, c));
+  c = AGF_DADD(P1, AGF_DMUL(t, c));
+  c = AGF_DSUB(r, AGF_DMUL(t, c));
+  const double y = AGF_DSUB(1.0, AGF_DSUB(AGF_DSUB(lo, AGF_DDIV(AGF_DMUL(r, c), AGF_DSUB(2.0, c))), hi));
+  if (k >= -1021 && k <= 1023) return AGF_DMUL(y, agf_bits2d((long long)(1023 + k) << 52));
+  // result near the subnormal range: two exact power-of-two factors
+  return AGF_DMUL(AGF_DMUL(y, agf_bits2d((long long)(1023 + k + 1000) << 52)), agf_bits2d((long long)(1023 - 1000) << 52));
+}
