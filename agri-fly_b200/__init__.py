@@ -37,6 +37,15 @@ def offboard_ref(kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0
     return r
 
 
+def offboard_estimator(**edits):
+    """agf_offboard_estimator_default() (MocapStateEstimator as Rappids_Simulator sets it up) with field edits."""
+    e = abi.OffboardEstimator()
+    _check(lib().agf_offboard_estimator_default(C.byref(e)))
+    for k, v in edits.items():
+        setattr(e, k, v)
+    return e
+
+
 def primitive_record(pf, T, p0=(0, 0, 0), v0=(0, 0, 0), a0=(0, 0, 0), grav=(0.0, 0.0, -9.81), att=(1.0, 0.0, 0.0, 0.0),
                      offset=(0.0, 0.0, 0.0)):
     """AGF_OFFTRAJ_DOUBLES record of the minimum-jerk primitive from (p0, v0, a0) to rest at pf in T seconds
@@ -317,6 +326,16 @@ class Batch:
             return
         _check(self.L.agf_batch_set_offboard_reference(self.h, C.byref(offboard_ref(kind, start_us, stop_us, desired_pos,
                                                                                    desired_yaw, traj_id))))
+
+    def set_offboard_estimator(self, est):
+        """est: abi.OffboardEstimator (offboard_estimator()) or None for the true state"""
+        _check(self.L.agf_batch_set_offboard_estimator(self.h, None if est is None else C.byref(est)))
+
+    def offboard_estimate(self, horizon=0.0, first=0, count=None):
+        count = self.n - first if count is None else count
+        e, c = np.empty((count, 13)), np.empty((count, 4))
+        _check(self.L.agf_batch_get_offboard_estimate(self.h, float(horizon), e.ctypes.data, c.ctypes.data, first, count))
+        return e, c
 
     def set_offboard_trajectories(self, traj, first=0):
         t = np.ascontiguousarray(traj, dtype=np.float64).reshape(-1, abi.OFFTRAJ_DOUBLES)

@@ -101,6 +101,16 @@ STAGE_WAIT_FOR_START, STAGE_SPOOL_UP, STAGE_TAKEOFF, STAGE_FLIGHT, STAGE_LANDING
 OFFTRAJ_DOUBLES, OFFSTATE_DOUBLES = 29, 16
 
 
+OFFEST_TRUTH, OFFEST_MOCAP = 0, 1
+
+
+class OffboardEstimator(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("mocap_period_us", C.c_uint32), ("prediction_delay", C.c_double),
+                ("meas_reject_dist", C.c_double), ("angvel_time_const", C.c_double),
+                ("meas_noise_pos", C.c_double), ("meas_noise_att", C.c_double),
+                ("proc_noise_pos", C.c_double), ("proc_noise_att", C.c_double)]
+
+
 class OffboardRef(C.Structure):
     _fields_ = [("kind", C.c_int32), ("traj_id", C.c_int32), ("start_us", C.c_uint64), ("stop_us", C.c_uint64),
                 ("desired_pos", C.c_double * 3), ("desired_yaw", C.c_double)]
@@ -190,6 +200,9 @@ PROTOTYPES = {
     "agf_batch_set_offboard_reference": (C.c_int, [C.c_void_p, _P(OffboardRef)]),
     "agf_batch_set_offboard_trajectories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_get_offboard_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_offboard_estimator_default": (C.c_int, [_P(OffboardEstimator)]),
+    "agf_batch_set_offboard_estimator": (C.c_int, [C.c_void_p, _P(OffboardEstimator)]),
+    "agf_batch_get_offboard_estimate": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_get_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_set_external_wrench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_add_uwb_anchor": (C.c_int, [C.c_void_p, C.c_uint8, _P(C.c_float)]),

@@ -319,6 +319,8 @@ struct Batch {
   virtual int set_offboard_ref(const agf_offboard_ref* ref) = 0;
   virtual int set_offboard_traj(const double* traj, size_t first, size_t count) = 0;
   virtual int get_offboard_state(double* out, size_t first, size_t count) = 0;
+  virtual int set_offboard_estimator(const agf_offboard_estimator* e) = 0;
+  virtual int get_offboard_estimate(double horizon, double* est13, double* counters4, size_t first, size_t count) = 0;
 
   size_t n = 0;
   agf_batch_opts opts;
@@ -385,6 +387,7 @@ struct BatchImpl : Batch {
   agf_offboard_target* d_off_targets = nullptr;
   double* d_off_offsets = nullptr;
   uint64_t first_target_us = 0;
+  double* d_off_est = nullptr;  // [E_FIELDS][n] estimator state
   double* d_off_state = nullptr;  // [AGF_OFFSTATE_DOUBLES][n]
   double* d_off_traj = nullptr;   // [AGF_OFFTRAJ_DOUBLES][n]
 
@@ -401,7 +404,7 @@ struct BatchImpl : Batch {
     cudaSetDevice(opts.device);
     cudaFree(st.sp); cudaFree(st.sf); cudaFree(st.su); cudaFree(st.sc);
     cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter); cudaFree(d_flags);
-    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(d_off_state); cudaFree(d_off_traj); cudaFree(st.sq);
+    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(d_off_state); cudaFree(d_off_traj); cudaFree(d_off_est); cudaFree(st.sq);
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
     for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -606,6 +609,15 @@ struct BatchImpl : Batch {
     ts.net_age += dt_us;
     now_us += dt_us;
     ts.now_us = now_us;
+    if (sh.tc.off_enabled && sh.tc.mocap_enabled) {  // simulated mocap packet (main.cpp:451-457), before the main loop
+      ts.mocap_age += dt_us;
+      if (ts.mocap_age >= sh.tc.mocap_min_age_us) {
+        ts.mocap_age -= sh.tc.mocap_adj_us;
+        cudaError_t e = launch_offboard_mocap(st, n, sh.off.est, now_us, stream);
+        if (e != cudaSuccess) return fail(AGF_ECUDA, "mocap update kernel launch", e);
+        launches++;
+      }
+    }
     if (sh.tc.off_enabled) {  // the offboard main loop acts after the clock advance (main.cpp:392,471-673)
       for (uint32_t q = 0; q < AGF_OFFQ; q++) ts.off_wait[q] = ts.off_wait[q] > dt_us ? ts.off_wait[q] - dt_us : 0;
       ts.off_age += dt_us;
@@ -652,6 +664,8 @@ struct BatchImpl : Batch {
     AGF_CUDA(cudaStreamSynchronize(stream));
     if (!cfg) {
       sh.tc.off_enabled = 0;
+      sh.tc.mocap_enabled = 0;
+      sh.off.est.kind = AGF_OFFEST_TRUTH;
       ts.off_age = ts.off_head = ts.off_count = 0;
       memset(ts.off_wait, 0, sizeof(ts.off_wait));
       return AGF_OK;
@@ -694,6 +708,10 @@ struct BatchImpl : Batch {
     off.desired_yaw = sh.off.desired_yaw;
     off.state = d_off_state;
     off.traj = d_off_traj;
+    off.est = sh.off.est;
+    tc.mocap_enabled = sh.tc.mocap_enabled;
+    tc.mocap_min_age_us = sh.tc.mocap_min_age_us;
+    tc.mocap_adj_us = sh.tc.mocap_adj_us;
     sh.off = off;
     sh.tc = tc;
     sh.tc.off_first_target_us = off.ref_kind == AGF_OFFREF_TARGETS ? targets[0].time_us : 0;
@@ -737,6 +755,69 @@ struct BatchImpl : Batch {
     sh.off.state = d_off_state;
     sh.off.traj = d_off_traj;
     sh.tc.off_first_target_us = 0;
+    return AGF_OK;
+  }
+  int set_offboard_estimator(const agf_offboard_estimator* e) override {
+    AGF_CUDA(cudaSetDevice(opts.device));
+    AGF_CUDA(cudaStreamSynchronize(stream));
+    if (!sh.tc.off_enabled) return fail(AGF_EINVAL, "set the offboard loop (agf_batch_set_offboard_loop) before its estimator");
+    if (!e || e->kind == AGF_OFFEST_TRUTH) {
+      sh.off.est.kind = AGF_OFFEST_TRUTH;
+      sh.tc.mocap_enabled = 0;
+      return AGF_OK;
+    }
+    if (e->kind != AGF_OFFEST_MOCAP) return fail(AGF_EINVAL, "unknown estimator kind");
+    if (!(e->mocap_period_us > 0) || !(e->angvel_time_const > 0) || !(e->prediction_delay >= 0))
+      return fail(AGF_EINVAL, "estimator: mocap period and angular-velocity time constant must be positive");
+    // MocapStateEstimator::MocapStateEstimator -> Reset() (MocapStateEstimator.cpp:9-50) for every vehicle
+    std::vector<double> h(size_t(E_FIELDS) * n, 0.0);
+    for (size_t i = 0; i < n; i++) {
+      h[(E_ATT + 0) * n + i] = 1.0;
+      h[(E_VP + 0) * n + i] = 25.0; h[(E_VP + 3) * n + i] = 25.0;
+      h[(E_VA + 0) * n + i] = 1.0; h[(E_VA + 3) * n + i] = 400.0;
+      h[E_LASTGOOD * n + i] = double(now_us);
+    }
+    if (!d_off_est) AGF_CUDA(cudaMalloc(&d_off_est, h.size() * sizeof(double)));
+    AGF_CUDA(cudaMemcpy(d_off_est, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    EstParams& p = sh.off.est;
+    p.kind = AGF_OFFEST_MOCAP;
+    p.t0_us = now_us;
+    p.delay = e->prediction_delay;
+    p.reject = e->meas_reject_dist;
+    p.tc_angvel = e->angvel_time_const;
+    p.meas_pos = e->meas_noise_pos; p.meas_att = e->meas_noise_att;
+    p.proc_pos = e->proc_noise_pos; p.proc_att = e->proc_noise_att;
+    p.state = d_off_est;
+    sh.tc.mocap_enabled = 1;
+    timing_thresholds_mocap(sh.tc, double(e->mocap_period_us) * 1e-6);
+    ts.mocap_age = 0;  // timerMocap is created now (main.cpp:286)
+    return AGF_OK;
+  }
+  int get_offboard_estimate(double horizon, double* est13, double* counters4, size_t first, size_t count) override {
+    if (!est13) return fail(AGF_EINVAL, "null output");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (sh.off.est.kind != AGF_OFFEST_MOCAP || !d_off_est) return fail(AGF_EINVAL, "no offboard estimator is set");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    double* d_out = nullptr;
+    AGF_CUDA(cudaMalloc(&d_out, 13 * count * sizeof(double)));
+    cudaError_t e = launch_offboard_estimate(sh.off.est, n, first, count, now_us, horizon, d_out, stream);
+    launches++;
+    std::vector<double> h(13 * count);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(AGF_ECUDA, "estimator read-out", e);
+    for (size_t k = 0; k < count; k++)
+      for (int f = 0; f < 13; f++) est13[k * 13 + f] = h[size_t(f) * count + k];
+    if (counters4) {
+      const int fields[4] = {E_INIT, E_NREJ, E_NREJC, E_NPIPE};
+      std::vector<double> col(count);
+      for (int f = 0; f < 4; f++) {
+        AGF_CUDA(cudaMemcpy(col.data(), d_off_est + size_t(fields[f]) * n + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < count; k++) counters4[k * 4 + f] = col[k];
+      }
+    }
     return AGF_OK;
   }
   int set_offboard_traj(const double* traj, size_t first, size_t count) override {
@@ -1172,6 +1253,26 @@ int agf_offboard_cfg_default(int quad_type, agf_offboard_cfg* out) {
   out->min_proper_acc = -1;
   out->yaw_angle = 0;
   return AGF_OK;
+}
+int agf_offboard_estimator_default(agf_offboard_estimator* o) {
+  if (!o) return fail(AGF_EINVAL, "null output");
+  memset(o, 0, sizeof(*o));
+  o->kind = AGF_OFFEST_MOCAP;
+  o->mocap_period_us = 5000;          // 1/200 s, Simulator/Rappids_Simulator/main.cpp:174
+  o->prediction_delay = 0.03;         // main.cpp:179
+  o->meas_reject_dist = 6.0;          // MocapStateEstimator.cpp:20-32
+  o->angvel_time_const = 0.04;
+  o->meas_noise_pos = 0.02;
+  o->meas_noise_att = 5 * M_PI / 180;
+  o->proc_noise_pos = 1.0 * 9.81;
+  o->proc_noise_att = 200;
+  return AGF_OK;
+}
+int agf_batch_set_offboard_estimator(agf_batch* b, const agf_offboard_estimator* est) {
+  return b ? B(b)->set_offboard_estimator(est) : fail(AGF_EINVAL, "null handle");
+}
+int agf_batch_get_offboard_estimate(agf_batch* b, double horizon, double* est13, double* counters4, size_t first, size_t count) {
+  return b ? B(b)->get_offboard_estimate(horizon, est13, counters4, first, count) : fail(AGF_EINVAL, "null handle");
 }
 int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref) {
   return b ? B(b)->set_offboard_ref(ref) : fail(AGF_EINVAL, "null handle");

@@ -25,6 +25,40 @@ __global__ void offboard_generate_kernel(StateArrays<P> st, size_t n, OffboardPa
   const Q4<P> ca(r[SP_ATT], r[SP_ATT + 1], r[SP_ATT + 2], r[SP_ATT + 3]);
   st.sq[size_t(slot) * n + i] = offboard_generate<true, P>(off, i, n, t_gen_us, cp, cv, ca);
 }
+// simulated mocap packet of the offboard estimator for the split Run()/advance stepping: same code as tick()'s
+template<typename P>
+__global__ void offboard_mocap_kernel(StateArrays<P> st, size_t n, EstParams ep, uint64_t now_us) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int VP = VecOf<P>::lanes;
+  P r[12];
+#pragma unroll
+  for (int q = 0; q < 12 / VP; q++) VecOf<P>::unpack(st.sp[size_t(q) * n + i], &r[q * VP]);
+  mocap_update<true>(ep, i, n, now_us, V3<double>(double(r[SP_POS]), double(r[SP_POS + 1]), double(r[SP_POS + 2])),
+                     Q4<double>(double(r[SP_ATT]), double(r[SP_ATT + 1]), double(r[SP_ATT + 2]), double(r[SP_ATT + 3])));
+}
+cudaError_t launch_offboard_mocap(const StateArrays<double>& st, size_t n, const EstParams& ep, uint64_t now_us, cudaStream_t stream) {
+  offboard_mocap_kernel<double><<<unsigned((n + 127) / 128), 128, 0, stream>>>(st, n, ep, now_us);
+  return cudaGetLastError();
+}
+cudaError_t launch_offboard_mocap(const StateArrays<float>& st, size_t n, const EstParams& ep, uint64_t now_us, cudaStream_t stream) {
+  offboard_mocap_kernel<float><<<unsigned((n + 127) / 128), 128, 0, stream>>>(st, n, ep, now_us);
+  return cudaGetLastError();
+}
+// MocapStateEstimator::GetPrediction(horizon) for vehicles first .. first+count-1 -> out [13][count]
+__global__ void offboard_estimate_kernel(EstParams ep, size_t n, size_t first, size_t count, uint64_t now_us, double horizon, double* out) {
+  const size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  EstCore e;
+  mocap_predict<true>(ep, first + k, n, now_us, horizon, e);
+  const double v[13] = {e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z, e.att.w, e.att.x, e.att.y, e.att.z, e.w.x, e.w.y, e.w.z};
+  for (int f = 0; f < 13; f++) out[size_t(f) * count + k] = v[f];
+}
+cudaError_t launch_offboard_estimate(const EstParams& ep, size_t n, size_t first, size_t count, uint64_t now_us, double horizon,
+                                     double* out, cudaStream_t stream) {
+  offboard_estimate_kernel<<<unsigned((count + 127) / 128), 128, 0, stream>>>(ep, n, first, count, now_us, horizon, out);
+  return cudaGetLastError();
+}
 cudaError_t launch_offboard_generate(const StateArrays<double>& st, size_t n, const OffboardParams& off, uint64_t t_gen_us,
                                      uint32_t slot, cudaStream_t stream) {
   offboard_generate_kernel<double><<<unsigned((n + 127) / 128), 128, 0, stream>>>(st, n, off, t_gen_us, slot);

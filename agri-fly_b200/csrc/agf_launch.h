@@ -27,6 +27,12 @@ cudaError_t launch_offboard_generate(const StateArrays<double>& st, size_t n, co
 cudaError_t launch_offboard_generate(const StateArrays<float>& st, size_t n, const OffboardParams& off, uint64_t t_gen_us,
                                      uint32_t slot, cudaStream_t stream);
 
+// the offboard estimator's mocap packet and read-out as kernels of their own (split stepping, agf_batch_get_offboard_estimate)
+cudaError_t launch_offboard_mocap(const StateArrays<double>& st, size_t n, const EstParams& ep, uint64_t now_us, cudaStream_t stream);
+cudaError_t launch_offboard_mocap(const StateArrays<float>& st, size_t n, const EstParams& ep, uint64_t now_us, cudaStream_t stream);
+cudaError_t launch_offboard_estimate(const EstParams& ep, size_t n, size_t first, size_t count, uint64_t now_us, double horizon,
+                                     double* out, cudaStream_t stream);
+
 // registers per thread / local memory of each instantiation, for agf_build_info()
 void kernel_attrs_parity(char* buf, size_t n);
 void kernel_attrs_fast_f64_uwb(char* buf, size_t n);

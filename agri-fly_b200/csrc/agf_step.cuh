@@ -65,6 +65,8 @@ struct Mf<true> {
   static AGF_DEV double sin(double x) { return agf_sin(x); }
   static AGF_DEV double cos(double x) { return agf_cos(x); }
   static AGF_DEV double acos(double x) { return agf_acos(x); }
+  static AGF_DEV double asin(double x) { return agf_asin(x); }
+  static AGF_DEV double exp(double x) { return agf_exp(x); }
 };
 // Fast variants: the step only ever takes sin/cos of HALF rotation angles per tick (|x| << 1), so a
 // short odd/even polynomial (error < 1e-9 relative for |x| <= 0.5) serves the hot path and the
@@ -123,6 +125,8 @@ struct Mf<false> {
   static AGF_DEV float acos(float x) { return ::acosf(x); }
   static AGF_DEV float atan2(float y, float x) { return ::atan2f(y, x); }
   static AGF_DEV double acos(double x) { return ::acos(x); }
+  static AGF_DEV double asin(double x) { return ::asin(x); }
+  static AGF_DEV double exp(double x) { return ::exp(x); }
 };
 // division: IEEE in the parity variant, reciprocal-multiply in the fast ones
 template<bool PARITY> AGF_DEV float fdiv(float a, float b) {
@@ -1263,7 +1267,8 @@ AGF_DEV float4 offboard_rates_packet(double thrust, const V3<float>& w) {
 // QuadcopterController::Run (Offboard/QuadcopterController.cpp:11-74)
 template<bool PARITY, typename P>
 AGF_DEV float4 offboard_command(const OffboardParams& c, const V3<P>& curPos, const V3<P>& curVel, const Q4<P>& curAtt,
-                                const double des[3], const double desVel[3], const double desAcc[3], double yaw) {
+                                const double des[3], const double desVel[3], const double desAcc[3], double yaw, double& thrustOut,
+                                V3<double>& wOut) {
   const V3<float> e3(0, 0, 1);
   const V3<float> estPos = V3<float>(float(curPos.x), float(curPos.y), float(curPos.z));
   const V3<float> estVel = V3<float>(float(curVel.x), float(curVel.y), float(curVel.z));
@@ -1281,13 +1286,15 @@ AGF_DEV float4 offboard_command(const OffboardParams& c, const V3<P>& curPos, co
   if (outCmdThrust < c.min_proper) outCmdThrust = c.min_proper;
   const Q4<float> cmdAttYawed = offboard_att_from_dir<PARITY>(cmdThrustDir, float(yaw));
   const V3<float> w = ctl_att_core<PARITY>(c.tc_att_xy, c.tc_att_z, c.k3_att, c.k12_att, cmdAttYawed, attf);
+  thrustOut = outCmdThrust;
+  wOut = V3<double>(double(w.x), double(w.y), double(w.z));
   return offboard_rates_packet(outCmdThrust, w);
 }
 // QuadcopterController::RunTracking (Offboard/QuadcopterController.cpp:76-131)
 template<bool PARITY, typename P>
 AGF_DEV float4 offboard_tracking(const OffboardParams& c, const V3<P>& curPos, const V3<P>& curVel, const Q4<P>& curAtt,
                                  const double refPos[3], const double refVel[3], const double refAcc[3], double yaw,
-                                 double refThrust, const double refAngVel[3]) {
+                                 double refThrust, const double refAngVel[3], double& thrustOut, V3<double>& wOut) {
   const V3<float> estPos = V3<float>(float(curPos.x), float(curPos.y), float(curPos.z));
   const V3<float> estVel = V3<float>(float(curVel.x), float(curVel.y), float(curVel.z));
   const Q4<float> attf = Q4<float>(float(curAtt.w), float(curAtt.x), float(curAtt.y), float(curAtt.z));
@@ -1304,8 +1311,9 @@ AGF_DEV float4 offboard_tracking(const OffboardParams& c, const V3<P>& curPos, c
   const Q4<float> refAttYawed = offboard_att_from_dir<PARITY>(refThrustDir, float(yaw));
   const V3<float> angVelErr = ctl_att_core<PARITY>(c.tc_att_xy, c.tc_att_z, c.k3_att, c.k12_att, refAttYawed, attf);
   // outCmdAngVel = refAngVel + Vec3d(Vec3f(...)); CreateRatesCommand takes Vec3f(cmdAngVel)
-  const V3<float> w(float(refAngVel[0] + double(angVelErr.x)), float(refAngVel[1] + double(angVelErr.y)),
-                    float(refAngVel[2] + double(angVelErr.z)));
+  wOut = V3<double>(refAngVel[0] + double(angVelErr.x), refAngVel[1] + double(angVelErr.y), refAngVel[2] + double(angVelErr.z));
+  thrustOut = outCmdThrust;
+  const V3<float> w(float(wOut.x), float(wOut.y), float(wOut.z));
   return offboard_rates_packet(outCmdThrust, w);
 }
 
@@ -1344,12 +1352,275 @@ AGF_DEV V3<double> rtg_omega(const double* tr, double t, double timeStep) {
   return angle * n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Offboard::MocapStateEstimator + PredictionPipe per vehicle (agrifly_b200.h "offboard loop: state estimator";
+// Components/Offboard/MocapStateEstimator.cpp, PredictionPipe.hpp).  State [field][N] doubles in HBM, touched on
+// mocap packets (every 2-3 ticks) and at command generation only; everything here is double as in the reference.
+// ---------------------------------------------------------------------------------------------
+struct EstCore {
+  V3<double> pos, vel, w;
+  Q4<double> att;
+};
+AGF_DEV void est_load(const double* st, size_t n, EstCore& e) {
+  e.pos = V3<double>(st[(E_POS + 0) * n], st[(E_POS + 1) * n], st[(E_POS + 2) * n]);
+  e.vel = V3<double>(st[(E_VEL + 0) * n], st[(E_VEL + 1) * n], st[(E_VEL + 2) * n]);
+  e.w = V3<double>(st[(E_W + 0) * n], st[(E_W + 1) * n], st[(E_W + 2) * n]);
+  e.att = Q4<double>(st[(E_ATT + 0) * n], st[(E_ATT + 1) * n], st[(E_ATT + 2) * n], st[(E_ATT + 3) * n]);
+}
+AGF_DEV void est_store(double* st, size_t n, const EstCore& e) {
+  st[(E_POS + 0) * n] = e.pos.x; st[(E_POS + 1) * n] = e.pos.y; st[(E_POS + 2) * n] = e.pos.z;
+  st[(E_VEL + 0) * n] = e.vel.x; st[(E_VEL + 1) * n] = e.vel.y; st[(E_VEL + 2) * n] = e.vel.z;
+  st[(E_W + 0) * n] = e.w.x; st[(E_W + 1) * n] = e.w.y; st[(E_W + 2) * n] = e.w.z;
+  st[(E_ATT + 0) * n] = e.att.w; st[(E_ATT + 1) * n] = e.att.x; st[(E_ATT + 2) * n] = e.att.y; st[(E_ATT + 3) * n] = e.att.z;
+}
+struct EstMsg {
+  V3<double> acc, w;
+  bool ballistic;
+};
+// PredictionPipe::GetActiveMessage (PredictionPipe.hpp:32-53) + the "no messages" default of its callers
+AGF_DEV void est_fetch(const double* st, size_t n, double t, EstMsg& m, double& timeRemaining) {
+  const int cnt = int(st[E_NPIPE * n]);
+  double tLast = 1e10;
+  for (int k = cnt - 1; k >= 0; k--) {
+    const double* q = st + size_t(E_PIPE + E_MSG * k) * n;
+    const double ta = q[0];
+    if ((t + 1e-6) >= ta) {
+      m.acc = V3<double>(q[1 * n], q[2 * n], q[3 * n]);
+      m.w = V3<double>(q[4 * n], q[5 * n], q[6 * n]);
+      m.ballistic = q[7 * n] != 0.0;
+      timeRemaining = tLast - ta;
+      return;
+    }
+    tLast = ta;
+  }
+  m.acc = V3<double>(0, 0, 0);
+  m.w = V3<double>(0, 0, 0);
+  m.ballistic = true;
+  timeRemaining = 1e10;
+}
+template<bool PARITY>
+AGF_DEV Q4<double> est_rotvec_q(const V3<double>& rv) {  // Rotationd::FromRotationVector
+  Q4<double> d;
+  return q_from_rotvec<PARITY>(rv, d) ? d : Q4<double>(1, 0, 0, 0);
+}
+template<bool PARITY>
+AGF_DEV V3<double> est_q_to_rotvec(const Q4<double>& q) {  // Rotation.hpp:144-161
+  const V3<double> nv = q.w > 0 ? V3<double>(q.x, q.y, q.z) : V3<double>(-q.x, -q.y, -q.z);
+  const double nn = norm(nv);
+  const double angle = Mf<PARITY>::asin(nn) * 2;
+  if (angle < 4.84813681e-6) return V3<double>(0, 0, 0);
+  return nv * (angle / nn);
+}
+// MocapStateEstimator::GetPrediction (MocapStateEstimator.cpp:61-118)
+template<bool PARITY>
+AGF_DEV void mocap_predict(const EstParams& ep, size_t i, size_t n, uint64_t now_us, double dt, EstCore& o) {
+  const double* st = ep.state + i;
+  const double tEnd = dt + double(now_us - ep.t0_us) * 1e-6;
+  const double tStart = double(uint64_t(st[E_TEST * n])) * 1e-6;
+  EstCore m;
+  est_load(st, n, m);
+  o = m;
+  double t = tStart;
+  while ((t + 1e-6) < tEnd) {
+    EstMsg cmd;
+    double predictionTime;
+    est_fetch(st, n, t, cmd, predictionTime);
+    double dtInt = tEnd - t;
+    if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
+    const V3<double> newPos = (o.pos + m.vel * dtInt) + ((cmd.acc * dtInt) * dtInt) / 2.0;  // sic: _vel (:90)
+    const V3<double> newVel = o.vel + cmd.acc * dtInt;
+    const Q4<double> newAtt = qmul(o.att, est_rotvec_q<PARITY>(m.w * dtInt));  // sic: _angVel (:92)
+    double discrete = Mf<PARITY>::exp(-dtInt / ep.tc_angvel);
+    if (cmd.ballistic) discrete = 1;
+    const V3<double> newW = discrete * o.w + (1 - discrete) * cmd.w;
+    o.pos = newPos; o.vel = newVel; o.att = newAtt; o.w = newW;
+    t += dtInt;
+  }
+}
+AGF_DEV void est_reset_variance(double* vp, double* va) {  // :52-60
+  vp[0] = 25.0; vp[3] = 25.0; vp[1] = vp[2] = 0.0;
+  va[0] = 1.0; va[3] = 400; va[1] = va[2] = 0.0;
+}
+// C = A * B for 2x2 row-major, coefficient-wise, sequential in k (the oracle's Eigen contract)
+AGF_DEV void est_mm2(const double* a, const double* b, double* c) {
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      double acc = a[2 * r] * b[q];
+      acc += a[2 * r + 1] * b[2 + q];
+      c[2 * r + q] = acc;
+    }
+}
+AGF_DEV void est_propagate_var(double* v, double dtInt, double proc) {  // A V A^T + Q (:171-186)
+  const double A[4] = {1, dtInt, 0, 1}, At[4] = {1, 0, dtInt, 1};
+  double t1[4], t2[4];
+  est_mm2(A, v, t1);
+  est_mm2(t1, At, t2);
+  v[0] = t2[0] + dtInt * dtInt * dtInt * dtInt * proc / 4;
+  v[1] = t2[1] + 0.0;
+  v[2] = t2[2] + 0.0;
+  v[3] = t2[3] + dtInt * dtInt * proc;
+}
+// MocapStateEstimator::UpdateWithMeasurement (:120-265)
+template<bool PARITY>
+AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_us, const V3<double>& measPos, const Q4<double>& measAtt) {
+  double* st = ep.state + i;
+  EstCore e;
+  double vp[4], va[4];
+  if (st[E_INIT * n] == 0.0) {
+    e.pos = measPos;
+    e.vel = V3<double>(0, 0, 0);
+    e.att = measAtt;
+    e.w = V3<double>(0, 0, 0);
+    est_store(st, n, e);
+    est_reset_variance(vp, va);
+    for (int k = 0; k < 4; k++) {
+      st[(E_VP + k) * n] = vp[k];
+      st[(E_VA + k) * n] = va[k];
+    }
+    st[E_INIT * n] = 1.0;
+    st[E_LASTGOOD * n] = double(now_us);
+    return;
+  }
+  est_load(st, n, e);
+  for (int k = 0; k < 4; k++) {
+    vp[k] = st[(E_VP + k) * n];
+    va[k] = st[(E_VA + k) * n];
+  }
+  uint64_t est_us = uint64_t(st[E_TEST * n]);
+  const double t0 = double(est_us) * 1e-6;
+  const double tEnd = double(now_us - ep.t0_us) * 1e-6;
+  if (tEnd > t0) {
+    for (;;) {
+      const double tNow = double(est_us) * 1e-6;
+      if ((tNow + 1e-6) >= tEnd) break;
+      EstMsg p;
+      double predictionTime;
+      est_fetch(st, n, tNow, p, predictionTime);
+      double dtInt = tEnd - tNow;
+      if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
+      const EstCore c = e;
+      e.pos = c.pos + c.vel * dtInt;
+      e.vel = c.vel + p.acc * dtInt;
+      e.att = qmul(c.att, est_rotvec_q<PARITY>(c.w * dtInt));
+      double discrete = Mf<PARITY>::exp(-dtInt / ep.tc_angvel);
+      if (p.ballistic) discrete = 1;
+      e.w = discrete * c.w + (1 - discrete) * p.w;
+      est_us += uint64_t(0.5 + dtInt * 1e6);
+      est_propagate_var(vp, dtInt, ep.proc_pos);
+      est_propagate_var(va, dtInt, ep.proc_att);
+    }
+  }
+  double innovP = vp[0] + ep.meas_pos * ep.meas_pos;
+  double innovA = va[0] + ep.meas_att * ep.meas_att;
+  const double distP = norm(measPos - e.pos) / ::sqrt(3 * innovP);
+  const Q4<double> dq = qmul(qinv(measAtt), e.att);
+  const double distA = (Mf<PARITY>::acos(::fabs(dq.w)) * 2.0) / ::sqrt(innovA);  // Rotation::GetAngle
+  const bool reject = (distP > ep.reject) || (distA > ep.reject);
+  double nrej = st[E_NREJ * n], nrejc = st[E_NREJC * n];
+  if (reject && nrejc < 10.0) {
+    nrej += 1.0;
+    nrejc += 1.0;
+  } else {
+    if (nrejc >= 10.0) {  // forced acceptance: Reset() (:37-50), then the update against the zeroed state
+      e.pos = V3<double>(0, 0, 0);
+      e.vel = V3<double>(0, 0, 0);
+      e.att = Q4<double>(1, 0, 0, 0);
+      e.w = V3<double>(0, 0, 0);
+      est_reset_variance(vp, va);
+      est_us = now_us - ep.t0_us;
+      st[E_INIT * n] = 0.0;
+      innovP = vp[0] + ep.meas_pos * ep.meas_pos;
+      innovA = va[0] + ep.meas_att * ep.meas_att;
+    }
+    nrejc = 0.0;
+    st[E_LASTGOOD * n] = double(now_us);
+    const double sP = 1 / innovP, sA = 1 / innovA;
+    double gP[2], gA[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {  // V * H^T * (1 / S), H = [1 0]
+      double a = vp[2 * r] * 1.0;
+      a += vp[2 * r + 1] * 0.0;
+      gP[r] = a * sP;
+      double b = va[2 * r] * 1.0;
+      b += va[2 * r + 1] * 0.0;
+      gA[r] = b * sA;
+    }
+    const V3<double> errP = measPos - e.pos;
+    e.pos = e.pos + gP[0] * errP;
+    e.vel = e.vel + gP[1] * errP;
+    const V3<double> errA = est_q_to_rotvec<PARITY>(qmul(qinv(e.att), measAtt));
+    e.att = qmul(e.att, est_rotvec_q<PARITY>(gA[0] * errA));
+    e.w = e.w + gA[1] * errA;
+    const double Ip[4] = {1.0 - gP[0] * 1.0, 0.0 - gP[0] * 0.0, 0.0 - gP[1] * 1.0, 1.0 - gP[1] * 0.0};
+    const double Ia[4] = {1.0 - gA[0] * 1.0, 0.0 - gA[0] * 0.0, 0.0 - gA[1] * 1.0, 1.0 - gA[1] * 0.0};
+    double np_[4], na_[4];
+    est_mm2(Ip, vp, np_);
+    est_mm2(Ia, va, na_);
+    for (int k = 0; k < 4; k++) {
+      vp[k] = np_[k];
+      va[k] = na_[k];
+    }
+  }
+  {  // symmetry (:257-261)
+    const double p01 = (vp[1] + vp[2]) * 0.5, p10 = (vp[2] + vp[1]) * 0.5, a01 = (va[1] + va[2]) * 0.5, a10 = (va[2] + va[1]) * 0.5;
+    vp[0] = (vp[0] + vp[0]) * 0.5; vp[3] = (vp[3] + vp[3]) * 0.5; vp[1] = p01; vp[2] = p10;
+    va[0] = (va[0] + va[0]) * 0.5; va[3] = (va[3] + va[3]) * 0.5; va[1] = a01; va[2] = a10;
+  }
+  est_store(st, n, e);
+  for (int k = 0; k < 4; k++) {
+    st[(E_VP + k) * n] = vp[k];
+    st[(E_VA + k) * n] = va[k];
+  }
+  st[E_TEST * n] = double(est_us);
+  st[E_NREJ * n] = nrej;
+  st[E_NREJC * n] = nrejc;
+  {  // PredictionPipe::ClearExpiredMessages(estimate time) (PredictionPipe.hpp:55-68)
+    const double cur = double(est_us) * 1e-6;
+    int cnt = int(st[E_NPIPE * n]);
+    const int N = cnt;
+    for (int it = 0; it < N; it++) {
+      if (cnt < 2) break;
+      if (st[size_t(E_PIPE + E_MSG) * n] <= cur) {  // _messages[1].timeActive
+        for (int k = 0; k + 1 < cnt; k++)
+          for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = st[size_t(E_PIPE + E_MSG * (k + 1) + f) * n];
+        cnt--;
+      }
+    }
+    st[E_NPIPE * n] = double(cnt);
+  }
+}
+// MocapStateEstimator::SetPredictedValues -> PredictionPipe::AddMessage (hpp:74-80, PredictionPipe.hpp:25-30)
+AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, size_t n, uint64_t now_us, const V3<double>& w, const V3<double>& acc) {
+  double* st = ep.state + i;
+  int cnt = int(st[E_NPIPE * n]);
+  if (cnt >= AGF_OFFEST_PIPE) {  // cannot happen while measurements arrive; keep the newest messages
+    for (int k = 0; k + 1 < cnt; k++)
+      for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = st[size_t(E_PIPE + E_MSG * (k + 1) + f) * n];
+    cnt--;
+  }
+  double* q = st + size_t(E_PIPE + E_MSG * cnt) * n;
+  q[0] = double(now_us - ep.t0_us) * 1e-6 + ep.delay;
+  q[1 * n] = acc.x; q[2 * n] = acc.y; q[3 * n] = acc.z;
+  q[4 * n] = w.x; q[5 * n] = w.y; q[6 * n] = w.z;
+  q[7 * n] = 0.0;
+  st[E_NPIPE * n] = double(cnt + 1);
+}
+template<typename P>
+static AGF_COLD void mocap_update_cold(const EstParams* ep, size_t i, size_t n, uint64_t now_us, V3<P> p, Q4<P> a) {
+  mocap_update<false>(*ep, i, n, now_us, V3<double>(double(p.x), double(p.y), double(p.z)),
+                      Q4<double>(double(a.w), double(a.x), double(a.y), double(a.z)));
+}
+
 // One round of the offboard main loop for vehicle i at clock reading t_gen: desired state from the configured
 // generator, then the controller; returns the queue payload.
-template<bool PARITY, typename P>
-AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, uint64_t t_gen, const V3<P>& cp, const V3<P>& cv,
-                                 const Q4<P>& ca) {
+template<bool PARITY>
+AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t n, uint64_t t_gen, const V3<double>& cp,
+                                      const V3<double>& cv, const Q4<double>& ca, int& predicted, double& thrustOut, V3<double>& wOut) {
+  typedef double P;
   const double zero3[3] = {0.0, 0.0, 0.0};
+  predicted = 2;  // 0: no SetPredictedValues, 1: SetPredictedValues(0, 0), 2: from the command
   double des[3];
   if (c.ref_kind == AGF_OFFREF_TARGETS) {
     uint32_t ti = 0;
@@ -1364,9 +1635,9 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
     des[1] = des[1] + c.offsets[n + i];
     des[2] = des[2] + c.offsets[2 * n + i];
   }
-  if (c.ref_kind == AGF_OFFREF_TARGETS) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, double(c.yaw));
+  if (c.ref_kind == AGF_OFFREF_TARGETS) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, double(c.yaw), thrustOut, wOut);
   if (c.ref_kind == AGF_OFFREF_TRAJECTORY) {
-    if (!(t_gen > c.start_us)) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, c.desired_yaw);
+    if (!(t_gen > c.start_us)) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, c.desired_yaw, thrustOut, wOut);
     double tr[AGF_OFFTRAJ_DOUBLES];
     for (int k = 0; k < AGF_OFFTRAJ_DOUBLES; k++) tr[k] = c.traj[size_t(k) * n + i];
     double traj_t = double(t_gen - c.start_us) * 1e-6;
@@ -1396,7 +1667,7 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
     const V3<double> rw = qrot(qmul(qinv(cad), trajAtt), rtg_omega<PARITY>(tr, traj_t, 0.02));
     const double refPos[3] = {rp.x, rp.y, rp.z}, refVel[3] = {rv.x, rv.y, rv.z}, refAcc[3] = {ra.x, ra.y, ra.z},
                  refW[3] = {rw.x, rw.y, rw.z};
-    return offboard_tracking<PARITY, P>(c, cp, cv, ca, refPos, refVel, refAcc, c.desired_yaw, refThrust, refW);
+    return offboard_tracking<PARITY, P>(c, cp, cv, ca, refPos, refVel, refAcc, c.desired_yaw, refThrust, refW, thrustOut, wOut);
   }
   // AGF_OFFREF_STAGES: ExampleVehicleStateMachine::Run (ExampleVehicleStateMachine.cpp:93-370)
   double* st = c.state + i;  // field k at st[k * n]
@@ -1413,9 +1684,11 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
     case AGF_STAGE_WAIT_FOR_START:
       if (shouldStart) stage = AGF_STAGE_SPOOL_UP;
       out = offboard_no_command();
+      predicted = 0;
       break;
     case AGF_STAGE_SPOOL_UP:
       out = offboard_rates_packet(9.81 * 0.25, V3<float>(0.0f, 0.0f, 0.0f));
+      predicted = 1;
       if (ts > 0.5) stage = AGF_STAGE_TAKEOFF;
       break;
     case AGF_STAGE_TAKEOFF: {
@@ -1429,7 +1702,7 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
       }
       double cmdPos[3];
       for (int a = 0; a < 3; a++) cmdPos[a] = (1 - frac) * st[(3 + a) * n] + frac * des[a];
-      out = offboard_command<PARITY, P>(c, cp, cv, ca, cmdPos, zero3, zero3, cmdYaw);
+      out = offboard_command<PARITY, P>(c, cp, cv, ca, cmdPos, zero3, zero3, cmdYaw, thrustOut, wOut);
     } break;
     case AGF_STAGE_FLIGHT: {
       double cmdPos[3] = {0, 0, 0}, cmdVel[3] = {0, 0, 0}, cmdAcc[3] = {0, 0, 0};
@@ -1489,7 +1762,7 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
         la[a] = frac * cmdAcc[a];
         st[(6 + a) * n] = lp[a]; st[(9 + a) * n] = lv[a]; st[(12 + a) * n] = la[a];
       }
-      out = offboard_command<PARITY, P>(c, cp, cv, ca, lp, lv, la, cmdYaw);
+      out = offboard_command<PARITY, P>(c, cp, cv, ca, lp, lv, la, cmdYaw, thrustOut, wOut);
       if (shouldStop) stage = AGF_STAGE_LANDING;
     } break;
     case AGF_STAGE_LANDING: {
@@ -1507,14 +1780,38 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
         dv[a] = (1 - frac) * lv[a] + frac * land[a];
         da[a] = (1 - frac) * la[a] + frac * 0.0;
       }
-      out = offboard_command<PARITY, P>(c, cp, cv, ca, dp, dv, da, cmdYaw);
+      out = offboard_command<PARITY, P>(c, cp, cv, ca, dp, dv, da, cmdYaw, thrustOut, wOut);
     } break;
     default:
       out = offboard_idle_command();
+      predicted = 1;
       break;
   }
   if (stage != stage_in) st[0] = double(stage);
   st[15 * n] = cmdYaw;
+  return out;
+}
+// the estimate the controller sees (true state or MocapStateEstimator::GetPrediction), the command, and what the
+// estimator is told about it (main.cpp:468-469,652-654)
+template<bool PARITY, typename P>
+AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, uint64_t t_gen, const V3<P>& cp, const V3<P>& cv,
+                                 const Q4<P>& ca) {
+  EstCore e;
+  if (c.est.kind == AGF_OFFEST_MOCAP) {
+    mocap_predict<PARITY>(c.est, i, n, t_gen, c.est.delay, e);
+  } else {
+    e.pos = V3<double>(double(cp.x), double(cp.y), double(cp.z));
+    e.vel = V3<double>(double(cv.x), double(cv.y), double(cv.z));
+    e.att = Q4<double>(double(ca.w), double(ca.x), double(ca.y), double(ca.z));
+  }
+  int predicted;
+  double thrust = 0.0;
+  V3<double> w(0, 0, 0);
+  const float4 out = offboard_generate_core<PARITY>(c, i, n, t_gen, e.pos, e.vel, e.att, predicted, thrust, w);
+  if (c.est.kind == AGF_OFFEST_MOCAP) {
+    if (predicted == 1) mocap_set_predicted(c.est, i, n, t_gen, V3<double>(0, 0, 0), V3<double>(0, 0, 0));
+    if (predicted == 2) mocap_set_predicted(c.est, i, n, t_gen, w, qrot(e.att, V3<double>(0, 0, 1)) * thrust - V3<double>(0, 0, 9.81));
+  }
   return out;
 }
 template<typename P>
@@ -1920,7 +2217,17 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       s.bits |= B_RADIO_MEAS_NEW;
     }
   }
-  if (plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance; estimate = truth
+  if (plan.mocap_update) {  // simulated mocap packet (main.cpp:451-457): the true pose after this tick's Run()
+    const V3<P> mp(s.pos[0], s.pos[1], s.pos[2]);
+    const Q4<P> ma(s.att[0], s.att[1], s.att[2], s.att[3]);
+    if constexpr (PARITY) {
+      mocap_update<true>(p.off.est, i, n, ts.now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
+                         Q4<double>(double(ma.w), double(ma.x), double(ma.y), double(ma.z)));
+    } else {
+      mocap_update_cold<P>(&p.off.est, i, n, ts.now_us + dt_us, mp, ma);
+    }
+  }
+  if (plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance
     const uint64_t t_gen = ts.now_us + dt_us;
     const V3<P> cp(s.pos[0], s.pos[1], s.pos[2]), cv(s.vel[0], s.vel[1], s.vel[2]);
     const Q4<P> ca(s.att[0], s.att[1], s.att[2], s.att[3]);

@@ -111,6 +111,9 @@ struct TimingConsts {
   uint32_t off_adj_us;        // uint64_t(period * 1e6) of Timer::AdjustTimeBySeconds            (main.cpp:476)
   uint32_t off_delay_us;      // CommunicationsDelay::_delayTime_us
   uint64_t off_first_target_us;  // no command is generated before the first target applies
+  // simulated mocap packets for the offboard estimator (main.cpp:451-457): clock-only
+  int mocap_enabled;
+  uint32_t mocap_min_age_us, mocap_adj_us;
 };
 
 inline uint32_t first_true_us(double guess_us, bool (*pred)(double, double), double arg) {
@@ -123,6 +126,10 @@ inline void timing_thresholds(TimingConsts& tc) {
   tc.logic_min_age_us = first_true_us(tc.logic_period * 1e6, [](double t, double p) { return t > p; }, tc.logic_period);
   tc.net_min_age_us = tc.net_enabled ? first_true_us(tc.comm_period * 1e6, [](double t, double p) { return !(t < p); }, tc.comm_period) : 0xFFFFFFFFu;
   tc.plant_min_age_us = first_true_us(1.0, [](double t, double p) { return !(t < p); }, 1e-6);
+}
+inline void timing_thresholds_mocap(TimingConsts& tc, double period) {
+  tc.mocap_min_age_us = first_true_us(period * 1e6, [](double t, double p) { return t > p; }, period);
+  tc.mocap_adj_us = uint32_t(uint64_t((-period) * double(-1e6)));
 }
 inline void timing_thresholds_offboard(TimingConsts& tc, double period) {
   tc.off_min_age_us = first_true_us(period * 1e6, [](double t, double p) { return t > p; }, period);
@@ -139,13 +146,14 @@ struct Timing {
   // offboard loop: main-loop stopwatch and the delay queue's control state (payloads are per vehicle)
   uint32_t off_age, off_head, off_count;
   uint32_t off_wait[AGF_OFFQ];  // microseconds until each queued command is due (0: deliverable)
+  uint32_t mocap_age;           // timerMocap
   uint64_t now_us;              // simulation clock (ManualTimer::GetMicroSeconds)
 };
 
 struct TickPlan {
   uint32_t plant_dt_us, kf_dt_us;
   bool run_plant, run_logic, run_net, net_start, net_complete, net_reset, has_target;
-  bool off_deliver, off_generate;
+  bool off_deliver, off_generate, mocap_update;
   uint32_t off_deliver_slot, off_gen_slot;
 };
 
@@ -176,6 +184,8 @@ AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc, uint32_t 
   // Generation (main.cpp:471): after Run() and the clock advance, when the stopwatch exceeds the period
   p.off_generate = tc.off_enabled && (ts.off_age + dt_us >= tc.off_min_age_us) && (ts.now_us + dt_us >= tc.off_first_target_us);
   p.off_gen_slot = (ts.off_head + ts.off_count) % AGF_OFFQ;  // the delivered one (if any) frees the head, not the tail
+  // mocap packet (main.cpp:451): after Run() and the clock advance, before the offboard main loop
+  p.mocap_update = tc.mocap_enabled && (ts.mocap_age + dt_us >= tc.mocap_min_age_us);
   return p;
 }
 
@@ -194,6 +204,10 @@ AGF_HDI void timing_advance(Timing& ts, const TimingConsts& tc, const TickPlan& 
   ts.kf_age += dt_us;
   ts.net_age += dt_us;
   ts.now_us += dt_us;
+  if (tc.mocap_enabled) {
+    ts.mocap_age += dt_us;
+    if (ts.mocap_age >= tc.mocap_min_age_us) ts.mocap_age -= tc.mocap_adj_us;
+  }
   if (tc.off_enabled) {
     if (p.off_deliver) {
       ts.off_head = (ts.off_head + 1) % AGF_OFFQ;
@@ -216,6 +230,18 @@ struct AnchorDev {
   uint32_t id;
 };
 
+// Offboard::MocapStateEstimator of the in-kernel offboard loop (agrifly_b200.h "offboard loop: state estimator")
+// state fields [field][N]: position, velocity, angular velocity, attitude, 2x2 variances (row-major), estimate time
+// [us], time of the last accepted measurement, initialised flag, rejection counters, prediction pipe (count, then
+// AGF_OFFEST_PIPE messages of time-active, acceleration, angular velocity, ballistic flag)
+enum { E_POS = 0, E_VEL = 3, E_W = 6, E_ATT = 9, E_VP = 13, E_VA = 17, E_TEST = 21, E_LASTGOOD = 22, E_INIT = 23, E_NREJ = 24,
+       E_NREJC = 25, E_NPIPE = 26, E_PIPE = 27, E_MSG = 8, E_FIELDS = E_PIPE + E_MSG * AGF_OFFEST_PIPE };
+struct EstParams {
+  int kind;
+  uint64_t t0_us;  // clock reading at construction: origin of the estimator's and its pipe's Timer
+  double delay, reject, tc_angvel, meas_pos, meas_att, proc_pos, proc_att;
+  double* state;   // device [E_FIELDS][N]
+};
 // Offboard::QuadcopterController + radio link of the in-kernel offboard loop (agrifly_b200.h "offboard rates loop")
 struct OffboardParams {
   float nat_freq, damping, tc_att_xy, tc_att_z;
@@ -232,6 +258,7 @@ struct OffboardParams {
   double desired[3], desired_yaw;
   double* state;       // device [AGF_OFFSTATE_DOUBLES][N]: stage machine state per vehicle
   const double* traj;  // device [AGF_OFFTRAJ_DOUBLES][N]: motion primitive per vehicle
+  EstParams est;
 };
 
 template<typename P>

@@ -365,6 +365,35 @@ int agf_batch_set_offboard_trajectories(agf_batch* b, const double* traj, size_t
 #define AGF_OFFSTATE_DOUBLES 16
 int agf_batch_get_offboard_state(agf_batch* b, double* out, size_t first, size_t count);
 
+/* ---- offboard loop: state estimator ------------------------------------------
+ * Where the offboard controller's state estimate comes from.  AGF_OFFEST_TRUTH: the true state at command
+ * generation.  AGF_OFFEST_MOCAP: Offboard::MocapStateEstimator (Components/Offboard/MocapStateEstimator.cpp) as
+ * Rappids_Simulator runs it (Simulator/Rappids_Simulator/main.cpp:221-225,451-457,468-469,652-654), per vehicle on
+ * the device: every `mocap_period_us` (stopwatch, strict '>') UpdateWithMeasurement(true position, true attitude)
+ * -- prediction through the queued commands (PredictionPipe.hpp), per-axis position/velocity and attitude/rate
+ * Kalman filters with 2x2 covariances, 6-sigma measurement rejection, forced reset after 10 rejections -- and, at
+ * command generation, GetPrediction(prediction_delay) (:61-118, incl. its use of the un-predicted velocity and
+ * angular velocity for the position and attitude increments); after each command SetPredictedValues(cmdAngVel,
+ * att * e3 * cmdThrust - g) queues it with the pipe's delay. */
+enum { AGF_OFFEST_TRUTH = 0, AGF_OFFEST_MOCAP = 1 };
+#define AGF_OFFEST_PIPE 8 /* prediction messages kept per vehicle (steady state: delay / period + 2) */
+typedef struct agf_offboard_estimator {
+  int32_t kind;             /* AGF_OFFEST_* */
+  uint32_t mocap_period_us; /* periodMocapSystem, main.cpp:174: 5000 */
+  double prediction_delay;  /* timeDelayOffboardControlLoopEstimate, main.cpp:179,223-224,469: 0.03 s */
+  /* MocapStateEstimator::MocapStateEstimator (MocapStateEstimator.cpp:20-32) */
+  double meas_reject_dist, angvel_time_const;
+  double meas_noise_pos, meas_noise_att, proc_noise_pos, proc_noise_att;
+} agf_offboard_estimator;
+int agf_offboard_estimator_default(agf_offboard_estimator* out);
+/* Needs agf_batch_set_offboard_loop first; est == NULL or kind TRUTH: back to the true state.  The estimator objects
+ * are constructed (Reset()) at the current clock reading. */
+int agf_batch_set_offboard_estimator(agf_batch* b, const agf_offboard_estimator* est);
+/* MocapStateEstimator::GetPrediction(horizon) now, [count][13]: position, velocity, attitude (w,x,y,z), angular
+ * velocity; plus the counters [count][4] (may be NULL): initialised, measurements rejected, rejected consecutively,
+ * messages in the prediction pipe. */
+int agf_batch_get_offboard_estimate(agf_batch* b, double horizon, double* est13, double* counters4, size_t first, size_t count);
+
 /* SimulationObject6DOF::GetTelemetryDataPackets (SimulationObject6DOF.hpp:67;
  * QuadcopterLogic.cpp:621-679), including its side effects (packet counter++, warnings cleared).
  * p1, p2: [count][30]. */

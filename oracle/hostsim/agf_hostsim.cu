@@ -36,6 +36,7 @@ struct orc_vehicle {
   std::vector<uint32_t> hu;
   uint64_t tick, now_us;
   std::vector<double> offstate, offtraj;  // reference generators of the offboard loop (n = 1)
+  std::vector<double> offest;             // offboard estimator state
   StateArrays<double> arrays() {
     StateArrays<double> a;
     a.sp = (double2*)hp.data();
@@ -197,6 +198,42 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
   v->sh.tc.off_first_target_us = 0;
   v->ts.now_us = v->now_us;
   orc_run(v, dt_us, nticks, nullptr, 0, nullptr, traj);
+}
+
+// what agf_batch_set_offboard_estimator does (the offboard loop's parameters are filled at the first run call)
+void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e) {
+  EstParams& p = v->sh.off.est;
+  if (!e || e->kind != AGF_OFFEST_MOCAP) {
+    p.kind = AGF_OFFEST_TRUTH;
+    v->sh.tc.mocap_enabled = 0;
+    return;
+  }
+  v->offest.assign(E_FIELDS, 0.0);
+  v->offest[E_ATT] = 1.0;
+  v->offest[E_VP] = 25.0; v->offest[E_VP + 3] = 25.0;
+  v->offest[E_VA] = 1.0; v->offest[E_VA + 3] = 400.0;
+  v->offest[E_LASTGOOD] = double(v->now_us);
+  p.kind = AGF_OFFEST_MOCAP;
+  p.t0_us = v->now_us;
+  p.delay = e->prediction_delay;
+  p.reject = e->meas_reject_dist;
+  p.tc_angvel = e->angvel_time_const;
+  p.meas_pos = e->meas_noise_pos; p.meas_att = e->meas_noise_att;
+  p.proc_pos = e->proc_noise_pos; p.proc_att = e->proc_noise_att;
+  p.state = v->offest.data();
+  v->sh.tc.mocap_enabled = 1;
+  timing_thresholds_mocap(v->sh.tc, double(e->mocap_period_us) * 1e-6);
+  v->ts.mocap_age = 0;
+}
+
+void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* o, double* c4) {
+  EstCore e;
+  mocap_predict<true>(v->sh.off.est, 0, 1, v->now_us, horizon, e);
+  const double x[13] = {e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z, e.att.w, e.att.x, e.att.y, e.att.z, e.w.x, e.w.y, e.w.z};
+  for (int k = 0; k < 13; k++) o[k] = x[k];
+  if (c4) {
+    c4[0] = v->offest[E_INIT]; c4[1] = v->offest[E_NREJ]; c4[2] = v->offest[E_NREJC]; c4[3] = v->offest[E_NPIPE];
+  }
 }
 
 void orc_get_offboard_state(orc_vehicle* v, double* out) {

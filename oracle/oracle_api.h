@@ -90,6 +90,9 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
                           const agf_offboard_ref* ref, const double* offset, const double* tr,
                           double* traj /* [nticks][ORC_NTRAJ] or NULL */);
 void orc_get_offboard_state(orc_vehicle* v, double* out /* [AGF_OFFSTATE_DOUBLES] */);
+/* Offboard::MocapStateEstimator in the loop (agf_offboard_estimator); NULL: back to the true state */
+void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* est);
+void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* est13, double* counters4 /* or NULL */);
 void orc_get_full(orc_vehicle* v, orc_full_state* out);
 void orc_get_telemetry(orc_vehicle* v, uint8_t p1[AGF_TELEMETRY_PACKET_SIZE],
                        uint8_t p2[AGF_TELEMETRY_PACKET_SIZE]);

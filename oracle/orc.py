@@ -116,6 +116,9 @@ class Oracle:
             L.orc_run_offboard_ref.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardRef), C.c_void_p,
                                                C.c_void_p, C.c_void_p]
             L.orc_get_offboard_state.argtypes = [vp, C.c_void_p]
+        if hasattr(L, "orc_set_offboard_estimator"):
+            L.orc_set_offboard_estimator.argtypes = [vp, P(abi.OffboardEstimator)]
+            L.orc_get_offboard_estimate.argtypes = [vp, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_get_full.argtypes = [vp, P(FullState)]
         L.orc_time_us.restype = C.c_uint64
         L.orc_time_us.argtypes = [vp]
@@ -225,6 +228,15 @@ class OracleVehicle:
         self.L.orc_run_offboard_ref(self.h, dt_us, nticks, C.byref(cfg), C.byref(ref), None if off is None else off.ctypes.data,
                                     None if tr is None else tr.ctypes.data, None if traj is None else traj.ctypes.data)
         return traj
+
+    def set_offboard_estimator(self, est):
+        """est: abi.OffboardEstimator or None (true state)"""
+        self.L.orc_set_offboard_estimator(self.h, None if est is None else C.byref(est))
+
+    def offboard_estimate(self, horizon=0.0):
+        e, c = np.zeros(13), np.zeros(4)
+        self.L.orc_get_offboard_estimate(self.h, horizon, e.ctypes.data, c.ctypes.data)
+        return e, c
 
     def offboard_state(self):
         o = np.zeros(abi.OFFSTATE_DOUBLES)

@@ -49,6 +49,7 @@ inline double m_cos(double x) { return agf_cos(x); }
 inline double m_asin(double x) { return agf_asin(x); }
 inline double m_acos(double x) { return agf_acos(x); }
 inline double m_atan2(double y, double x) { return agf_atan2(y, x); }
+inline double m_exp(double x) { return agf_exp(x); }  // the offboard estimator's exp only; the plant's motor lag keeps glibc
 #else
 inline float m_sin(float x) { return sinf(x); }
 inline float m_cos(float x) { return cosf(x); }
@@ -60,6 +61,7 @@ inline double m_cos(double x) { return cos(x); }
 inline double m_asin(double x) { return asin(x); }
 inline double m_acos(double x) { return acos(x); }
 inline double m_atan2(double y, double x) { return atan2(y, x); }
+inline double m_exp(double x) { return exp(x); }
 #endif
 inline float m_sqrt(float x) { return sqrtf(x); }
 inline double m_sqrt(double x) { return sqrt(x); }
@@ -1294,10 +1296,14 @@ inline uint16_t radio_encode_field(float valIn, float limit) {
 // RadioMessageDecoded(raw) (RadioTypes.hpp:158-171,210-219): returns the four floats the vehicle will decode
 struct OffboardCmd {
   float f[4];
+  double thrust;  // before quantisation: what SetPredictedValues is told (main.cpp:652-654)
+  V3d angVel;
 };
 inline OffboardCmd quantise_rates(double thrust, const V3d& w) {
   const float tx[4] = {float(thrust), float(w.x), float(w.y), float(w.z)};
   OffboardCmd o;
+  o.thrust = thrust;
+  o.angVel = w;
   for (int i = 0; i < 4; i++) {
     const float limit = 35;  // MAX_VAL_CMD_THRUST == MAX_VAL_CMD_ANG_RATES == 35
     const int q = radio_encode_field(tx[i], limit);
@@ -1388,15 +1394,241 @@ inline OffboardCmd offboard_rates_command(const agf_offboard_cfg& c, const V3d& 
   }
   Rotf cmdAttYawed = cmdAtt * Rotf::from_rotation_vector(V3f(0, 0, float(yawAngle)));
   const V3d outCmdAngVel(attCtr.desired_angular_velocity(cmdAttYawed, attf));
-  const float tx[4] = {float(outCmdThrust), float(outCmdAngVel.x), float(outCmdAngVel.y), float(outCmdAngVel.z)};
-  OffboardCmd o;
-  for (int i = 0; i < 4; i++) {
-    const float limit = 35;  // MAX_VAL_CMD_THRUST == MAX_VAL_CMD_ANG_RATES == 35
-    const int q = radio_encode_field(tx[i], limit);
-    o.f[i] = limit * (q - 32768) / float(32768);
-  }
-  return o;
+  return quantise_rates(outCmdThrust, outCmdAngVel);
 }
+}  // namespace port
+
+namespace port {
+// ---------------------------------------------------------------------------------------------
+// Offboard::MocapStateEstimator (Components/Offboard/MocapStateEstimator.cpp) and its PredictionPipe
+// (Components/Offboard/PredictionPipe.hpp).  2x2 products follow the oracle's Eigen contract: coefficient-wise,
+// sequential in k from the k = 0 product, left to right.
+// ---------------------------------------------------------------------------------------------
+struct M22 {
+  double d[2][2];
+};
+inline M22 mm2(const M22& a, const M22& b) {
+  M22 c;
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++) {
+      double acc = a.d[i][0] * b.d[0][j];
+      acc += a.d[i][1] * b.d[1][j];
+      c.d[i][j] = acc;
+    }
+  return c;
+}
+inline M22 add2(const M22& a, const M22& b) {
+  M22 c;
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++) c.d[i][j] = a.d[i][j] + b.d[i][j];
+  return c;
+}
+inline M22 tr2(const M22& a) {
+  M22 c;
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++) c.d[j][i] = a.d[i][j];
+  return c;
+}
+struct MocapEstimator {
+  static constexpr double SMALL_TIME = 1e-6;
+  static constexpr unsigned MAX_NUM_CONSECUTIVE_REJECTION = 10;
+  struct Msg {
+    double timeActive;
+    V3d acc, angVel;
+    bool ballistic;
+  };
+  Timer timer, lastGood, pipeTimer;
+  uint64_t estTime_us;  // ManualTimer _estimateTimer
+  bool initialized;
+  V3d pos, vel, angVel;
+  Rotd att;
+  M22 varPos, varAtt;
+  unsigned numRej, numRejCons;
+  double tcAngVel, rejectDist, nMeasPos, nMeasAtt, nProcPos, nProcAtt, pipeDelay;
+  std::deque<Msg> pipe;
+
+  MocapEstimator(const Clock* c, const agf_offboard_estimator& e)
+      : timer(c), lastGood(c), pipeTimer(c), estTime_us(0), initialized(false), numRej(0), numRejCons(0) {
+    rejectDist = e.meas_reject_dist;
+    tcAngVel = e.angvel_time_const;
+    nMeasPos = e.meas_noise_pos;
+    nMeasAtt = e.meas_noise_att;
+    nProcPos = e.proc_noise_pos;
+    nProcAtt = e.proc_noise_att;
+    pipeDelay = e.prediction_delay;
+    reset();
+  }
+  double est_seconds() const { return double(estTime_us * double(1e-6)); }
+  void reset_variance() {  // :52-60
+    varPos.d[0][0] = 25.0; varPos.d[1][1] = 25.0; varPos.d[0][1] = varPos.d[1][0] = 0.0;
+    varAtt.d[0][0] = 1.0; varAtt.d[1][1] = 400; varAtt.d[0][1] = varAtt.d[1][0] = 0.0;
+  }
+  void reset() {  // :37-50
+    initialized = false;
+    pos = V3d(0, 0, 0);
+    vel = V3d(0, 0, 0);
+    att = Rotd::identity();
+    angVel = V3d(0, 0, 0);
+    reset_variance();
+    estTime_us = timer.micros();
+    lastGood.reset();
+  }
+  void set_predicted(const V3d& w, const V3d& a, bool ballistic = false) {  // hpp:74-80, PredictionPipe.hpp:25-30
+    Msg m;
+    m.timeActive = pipeTimer.seconds_d() + pipeDelay;
+    m.acc = a;
+    m.angVel = w;
+    m.ballistic = ballistic;
+    pipe.push_back(m);
+  }
+  bool active_message(double t, Msg& out, double& timeRemaining) const {  // PredictionPipe.hpp:32-53
+    if (pipe.empty()) return false;
+    double tLastMsg = 1e10;
+    for (size_t k = pipe.size(); k-- > 0;) {
+      if ((t + SMALL_TIME) >= pipe[k].timeActive) {
+        out = pipe[k];
+        timeRemaining = tLastMsg - pipe[k].timeActive;
+        return true;
+      }
+      tLastMsg = pipe[k].timeActive;
+    }
+    return false;
+  }
+  void clear_expired(double currentTime) {  // PredictionPipe.hpp:55-68
+    const int N = int(pipe.size());
+    for (int i = 0; i < N; i++) {
+      if (pipe.size() < 2) return;
+      if (pipe[1].timeActive <= currentTime) pipe.pop_front();
+    }
+  }
+  static void fetch(const MocapEstimator& e, double t, Msg& cmd, double& predictionTime) {
+    predictionTime = 0;
+    if (!e.active_message(t, cmd, predictionTime)) {
+      cmd.acc = V3d(0, 0, 0);
+      cmd.angVel = V3d(0, 0, 0);
+      cmd.ballistic = true;
+      predictionTime = 1e10;
+    }
+  }
+  void prediction(double dt, V3d& oPos, V3d& oVel, Rotd& oAtt, V3d& oAngVel) const {  // GetPrediction :61-118
+    const double tEnd = dt + timer.seconds_d();
+    const double tStart = est_seconds();
+    oPos = pos; oVel = vel; oAtt = att; oAngVel = angVel;
+    double t = tStart;
+    while ((t + SMALL_TIME) < tEnd) {
+      Msg cmd;
+      double predictionTime;
+      fetch(*this, t, cmd, predictionTime);
+      double dtInt = tEnd - t;
+      if (dtInt > (predictionTime + SMALL_TIME)) dtInt = predictionTime;
+      const V3d newPos = oPos + vel * dtInt + cmd.acc * dtInt * dtInt / 2.0;  // sic: _vel, not est.vel (:90)
+      const V3d newVel = oVel + cmd.acc * dtInt;
+      const Rotd newAtt = oAtt * Rotd::from_rotation_vector(angVel * dtInt);  // sic: _angVel (:92)
+      double discrete = m_exp(-dtInt / tcAngVel);
+      if (cmd.ballistic) discrete = 1;
+      const V3d newAngVel = discrete * oAngVel + (1 - discrete) * cmd.angVel;
+      oPos = newPos; oVel = newVel; oAtt = newAtt; oAngVel = newAngVel;
+      t += dtInt;
+    }
+  }
+  void update(const V3d& measPos, const Rotd& measAtt) {  // UpdateWithMeasurement :120-265
+    if (!initialized) {
+      initialized = true;
+      pos = measPos;
+      vel = V3d(0, 0, 0);
+      att = measAtt;
+      angVel = V3d(0, 0, 0);
+      lastGood.reset();
+      reset_variance();
+      return;
+    }
+    const double t0 = est_seconds();
+    const double tEnd = timer.seconds_d();
+    if (tEnd > t0) {
+      for (;;) {
+        const double tNow = est_seconds();
+        if ((tNow + SMALL_TIME) >= tEnd) break;
+        Msg p;
+        double predictionTime;
+        fetch(*this, est_seconds(), p, predictionTime);
+        double dtInt = tEnd - est_seconds();
+        if (dtInt > (predictionTime + SMALL_TIME)) dtInt = predictionTime;
+        const V3d pos0(pos), vel0(vel), angVel0(angVel);
+        const Rotd att0(att);
+        pos = pos0 + vel0 * dtInt;
+        vel = vel0 + p.acc * dtInt;
+        att = att0 * Rotd::from_rotation_vector(angVel0 * dtInt);
+        double discrete = m_exp(-dtInt / tcAngVel);
+        if (p.ballistic) discrete = 1;
+        angVel = discrete * angVel0 + (1 - discrete) * p.angVel;
+        estTime_us += uint64_t(0.5 + dtInt * 1e6);
+        M22 A, Qp, Qa;
+        A.d[0][0] = 1; A.d[0][1] = dtInt; A.d[1][0] = 0; A.d[1][1] = 1;
+        Qp.d[0][0] = dtInt * dtInt * dtInt * dtInt * nProcPos / 4; Qp.d[0][1] = 0; Qp.d[1][0] = 0; Qp.d[1][1] = dtInt * dtInt * nProcPos;
+        Qa.d[0][0] = dtInt * dtInt * dtInt * dtInt * nProcAtt / 4; Qa.d[0][1] = 0; Qa.d[1][0] = 0; Qa.d[1][1] = dtInt * dtInt * nProcAtt;
+        const M22 newPosVar = add2(mm2(mm2(A, varPos), tr2(A)), Qp);
+        const M22 newAttVar = add2(mm2(mm2(A, varAtt), tr2(A)), Qa);
+        varPos = newPosVar;
+        varAtt = newAttVar;
+      }
+    }
+    double innovationCovPos = varPos.d[0][0] + nMeasPos * nMeasPos;
+    double innovationCovAtt = varAtt.d[0][0] + nMeasAtt * nMeasAtt;
+    const double distMeasPos = (measPos - pos).norm() / m_sqrt(3 * innovationCovPos);
+    const Rotd dq = measAtt.inverse() * att;
+    const double distMeasAtt = (m_acos(fabs(dq.v[0])) * 2.0) / m_sqrt(innovationCovAtt);  // Rotation::GetAngle :138-142
+    bool shouldRejectMeas = false;
+    if ((distMeasPos > rejectDist) || (distMeasAtt > rejectDist)) shouldRejectMeas = true;
+    if (shouldRejectMeas && numRejCons < MAX_NUM_CONSECUTIVE_REJECTION) {
+      numRej++;
+      numRejCons++;
+    } else {
+      if (numRejCons >= MAX_NUM_CONSECUTIVE_REJECTION) {
+        reset();
+        innovationCovPos = varPos.d[0][0] + nMeasPos * nMeasPos;
+        innovationCovAtt = varAtt.d[0][0] + nMeasAtt * nMeasAtt;
+      }
+      numRejCons = 0;
+      lastGood.reset();
+      // gain = V * H^T * (1 / S), H = [1 0]
+      const double sP = 1 / innovationCovPos, sA = 1 / innovationCovAtt;
+      double gP[2], gA[2];
+      for (int i = 0; i < 2; i++) {
+        double a = varPos.d[i][0] * 1.0;
+        a += varPos.d[i][1] * 0.0;
+        gP[i] = a * sP;
+        double b = varAtt.d[i][0] * 1.0;
+        b += varAtt.d[i][1] * 0.0;
+        gA[i] = b * sA;
+      }
+      const V3d measErrPos = measPos - pos;
+      pos = pos + gP[0] * measErrPos;
+      vel = vel + gP[1] * measErrPos;
+      const V3d measErrAtt = (att.inverse() * measAtt).to_rotation_vector();
+      att = att * Rotd::from_rotation_vector(gA[0] * measErrAtt);
+      angVel = angVel + gA[1] * measErrAtt;
+      M22 Ip, Ia;
+      for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) {
+          const double h = (j == 0) ? 1.0 : 0.0, id = (i == j) ? 1.0 : 0.0;
+          Ip.d[i][j] = id - gP[i] * h;
+          Ia.d[i][j] = id - gA[i] * h;
+        }
+      const M22 newPosVar = mm2(Ip, varPos), newAttVar = mm2(Ia, varAtt);
+      varPos = newPosVar;
+      varAtt = newAttVar;
+    }
+    M22 sp, sa;
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) {
+        sp.d[i][j] = (varPos.d[i][j] + varPos.d[j][i]) * 0.5;
+        sa.d[i][j] = (varAtt.d[i][j] + varAtt.d[j][i]) * 0.5;
+      }
+    varPos = sp;
+    varAtt = sa;
+    clear_expired(est_seconds());
+  }
+};
 }  // namespace port
 
 struct orc_vehicle {
@@ -1409,6 +1641,28 @@ struct orc_vehicle {
   port::Timer* offTimer = nullptr;
   struct Queued { uint64_t due; port::OffboardCmd cmd; int type; };
   std::deque<Queued> offQueue;
+  // offboard state estimator (orc_set_offboard_estimator)
+  port::MocapEstimator* est = nullptr;
+  port::Timer* timerMocap = nullptr;
+  double periodMocap = 0, delayEst = 0;
+  void mocap_step() {  // main.cpp:451-457
+    if (!est) return;
+    if (timerMocap->seconds_d() > periodMocap) {
+      timerMocap->adjust_by_seconds(-periodMocap);
+      est->update(quad->pos, quad->att);
+    }
+  }
+  void estimate(port::V3d& p, port::V3d& vl, port::Rotd& a) {
+    port::V3d w;
+    if (est) {
+      est->prediction(delayEst, p, vl, a, w);
+    } else {
+      p = quad->pos; vl = quad->vel; a = quad->att;
+    }
+  }
+  void set_predicted(const port::V3d& w, double thrust, const port::Rotd& a) {  // main.cpp:652-654
+    if (est) est->set_predicted(w, a.rotate(port::V3d(0, 0, 1)) * thrust - port::V3d(0, 0, 9.81));
+  }
   // reference generators (orc_run_offboard_ref): ExampleVehicleStateMachine members
   int stage = AGF_STAGE_WAIT_FOR_START, lastStage = AGF_STAGE_COMPLETE;
   uint64_t stageStart = 0;
@@ -1531,6 +1785,7 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
     if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
     v->clock.now_us += dt_us;
     v->tick++;
+    v->mocap_step();
     if (v->offTimer->seconds_d() > period) {  // main.cpp:471
       v->offTimer->adjust_by_seconds(-period);  // main.cpp:476
       int ti = -1;
@@ -1542,7 +1797,11 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
       orc_vehicle::Queued q;
       q.due = v->clock.now_us + cfg->delay_us;
       q.type = AGF_RADIO_EXTERNAL_RATES_CMD;
-      q.cmd = port::offboard_rates_command(*cfg, v->quad->pos, v->quad->vel, v->quad->att, des);
+      port::V3d ePos, eVel;
+      port::Rotd eAtt;
+      v->estimate(ePos, eVel, eAtt);
+      q.cmd = port::offboard_rates_command(*cfg, ePos, eVel, eAtt, des);
+      v->set_predicted(q.cmd.angVel, q.cmd.thrust, eAtt);
       v->offQueue.push_back(q);
     }
   }
@@ -1597,11 +1856,14 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
     if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
     v->clock.now_us += dt_us;
     v->tick++;
+    v->mocap_step();
     if (!(v->offTimer->seconds_d() > period)) continue;
     v->offTimer->adjust_by_seconds(-period);
     const uint64_t now = v->clock.now_us;
-    const V3d estPos = v->quad->pos, estVel = v->quad->vel;
-    const port::Rotd estAtt = v->quad->att;
+    V3d estPos, estVel;
+    port::Rotd estAtt;
+    v->estimate(estPos, estVel, estAtt);
+    int predicted = 2;  // 0: nothing, 1: SetPredictedValues(0, 0), 2: from the command
     orc_vehicle::Queued q;
     q.due = now + cfg->delay_us;
     q.type = AGF_RADIO_EXTERNAL_RATES_CMD;
@@ -1646,8 +1908,10 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
         case AGF_STAGE_WAIT_FOR_START:
           if (shouldStart) v->stage = AGF_STAGE_SPOOL_UP;
           send = false;
+          predicted = 0;
           break;
         case AGF_STAGE_SPOOL_UP:
+          predicted = 1;
           q.cmd = port::quantise_rates(9.81 * 0.25, zero);
           if (ts > 0.5) v->stage = AGF_STAGE_TAKEOFF;
           break;
@@ -1722,12 +1986,47 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
                                                v->cmdYawAngle);
         } break;
         default:
+          predicted = 1;
           q.type = AGF_RADIO_IDLE_CMD;
           for (int i = 0; i < 4; i++) q.cmd.f[i] = 35.0f * (0 - 32768) / float(32768);  // zero bytes decode to -limit; never read
           break;
       }
     }
+    if (v->est && predicted == 1) v->est->set_predicted(zero, zero);
+    if (predicted == 2) v->set_predicted(q.cmd.angVel, q.cmd.thrust, estAtt);
     if (send) v->offQueue.push_back(q);
+  }
+}
+
+void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e) {
+  delete v->est;
+  delete v->timerMocap;
+  v->est = nullptr;
+  v->timerMocap = nullptr;
+  if (!e || e->kind != AGF_OFFEST_MOCAP) return;
+  v->est = new port::MocapEstimator(&v->clock, *e);
+  v->timerMocap = new port::Timer(&v->clock);
+  v->periodMocap = double(e->mocap_period_us) * 1e-6;
+  v->delayEst = e->prediction_delay;
+}
+
+void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* o13, double* c4) {
+  port::V3d p, vl, w;
+  port::Rotd a;
+  if (v->est) {
+    v->est->prediction(horizon, p, vl, a, w);
+  } else {
+    p = v->quad->pos; vl = v->quad->vel; a = v->quad->att; w = v->quad->angVel;
+  }
+  o13[0] = p.x; o13[1] = p.y; o13[2] = p.z;
+  o13[3] = vl.x; o13[4] = vl.y; o13[5] = vl.z;
+  for (int i = 0; i < 4; i++) o13[6 + i] = a.v[i];
+  o13[10] = w.x; o13[11] = w.y; o13[12] = w.z;
+  if (c4) {
+    c4[0] = v->est ? double(v->est->initialized) : 0.0;
+    c4[1] = v->est ? double(v->est->numRej) : 0.0;
+    c4[2] = v->est ? double(v->est->numRejCons) : 0.0;
+    c4[3] = v->est ? double(v->est->pipe.size()) : 0.0;
   }
 }
 

@@ -38,6 +38,7 @@
 #include "Components/Simulation/UWBNetwork.hpp"
 #include "Components/Simulation/CommunicationsDelay.hpp"
 #include "Components/Offboard/QuadcopterController.hpp"
+#include "Components/Offboard/MocapStateEstimator.hpp"
 #include "Components/TrajectoryGenerator/RapidTrajectoryGenerator.hpp"
 #undef private
 #undef protected
@@ -57,6 +58,27 @@ struct orc_vehicle {
   // offboard loop (orc_run_offboard): created on first use
   std::unique_ptr<Timer> offTimer;
   std::unique_ptr<Simulation::CommunicationsDelay<RadioTypes::RadioMessageDecoded::RawMessage>> offChannel;
+  // offboard state estimator (orc_set_offboard_estimator): main.cpp:221-225,286
+  std::unique_ptr<Offboard::MocapStateEstimator> est;
+  std::unique_ptr<Timer> timerMocap;
+  double periodMocap = 0, delayEst = 0;
+  // after Run() + clock advance: simulated mocap packet (main.cpp:451-457)
+  void mocapStep() {
+    if (!est) return;
+    if (timerMocap->GetSeconds<double>() > periodMocap) {
+      timerMocap->AdjustTimeBySeconds(-periodMocap);
+      est->UpdateWithMeasurement(quad->GetPosition(), quad->GetAttitude());
+    }
+  }
+  Offboard::EstimatedState estimate() {  // main.cpp:468-469
+    if (est) return est->GetPrediction(delayEst);
+    Offboard::EstimatedState e;
+    e.pos = quad->GetPosition();
+    e.vel = quad->GetVelocity();
+    e.att = quad->GetAttitude();
+    e.angVel = quad->GetAngularVelocity();
+    return e;
+  }
   // reference generators of the offboard loop (orc_run_offboard_ref)
   int stage = AGF_STAGE_WAIT_FOR_START, lastStage = AGF_STAGE_COMPLETE;  // ExampleVehicleStateMachine.cpp:10-11
   std::unique_ptr<Timer> stageTimer;
@@ -203,6 +225,7 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
     if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
     v->timer.AdvanceMicroSeconds(dt_us);
     v->tick++;
+    v->mocapStep();
     if (v->offTimer->GetSeconds<double>() > period) {  // main.cpp:471
       v->offTimer->AdjustTimeBySeconds(-period);       // main.cpp:476
       const uint64_t now = v->timer.GetMicroSeconds();
@@ -214,12 +237,15 @@ void orc_run_offboard(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf
       if (offset) des = des + Vec3d(offset[0], offset[1], offset[2]);
       Vec3d cmdAngVel;
       double cmdThrust;
-      ctrl.Run(v->quad->GetPosition(), v->quad->GetVelocity(), v->quad->GetAttitude(), des, Vec3d(0, 0, 0),
+      const Offboard::EstimatedState estState = v->estimate();
+      ctrl.Run(estState.pos, estState.vel, estState.att, des, Vec3d(0, 0, 0),
                Vec3d(0, 0, 0), cfg->yaw_angle, cmdAngVel, cmdThrust);  // main.cpp:625-627
       RadioTypes::RadioMessageDecoded::RawMessage rawMsg;
       memset(rawMsg.raw, 0, sizeof(rawMsg.raw));
       RadioTypes::RadioMessageDecoded::CreateRatesCommand(uint8_t(cfg->radio_flags), float(cmdThrust), Vec3f(cmdAngVel),
                                                           rawMsg.raw);  // main.cpp:666-669
+      if (v->est)  // main.cpp:652-654
+        v->est->SetPredictedValues(cmdAngVel, (estState.att * Vec3d(0, 0, 1) * cmdThrust - Vec3d(0, 0, 9.81)));
       v->offChannel->AddMessage(rawMsg);                                 // main.cpp:673
     }
   }
@@ -272,12 +298,15 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
     if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
     v->timer.AdvanceMicroSeconds(dt_us);
     v->tick++;
+    v->mocapStep();
     if (!(v->offTimer->GetSeconds<double>() > period)) continue;  // main.cpp:471
     v->offTimer->AdjustTimeBySeconds(-period);                     // main.cpp:476
     const uint64_t now = v->timer.GetMicroSeconds();
-    // estimate = truth
-    const Vec3d estPos = v->quad->GetPosition(), estVel = v->quad->GetVelocity();
-    const Rotationd estAtt = v->quad->GetAttitude();
+    const Offboard::EstimatedState estState = v->estimate();
+    const Vec3d estPos = estState.pos, estVel = estState.vel;
+    const Rotationd estAtt = estState.att;
+    // 0: nothing, 1: SetPredictedValues(0, 0), 2: SetPredictedValues(cmdAngVel, att * e3 * cmdThrust - g)
+    int predicted = 2;
     RadioTypes::RadioMessageDecoded::RawMessage rawMsg;
     memset(rawMsg.raw, 0, sizeof(rawMsg.raw));
     bool send = true;
@@ -330,10 +359,12 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
         case AGF_STAGE_WAIT_FOR_START:  // :113-120
           if (shouldStart) v->stage = AGF_STAGE_SPOOL_UP;
           send = false;
+          predicted = 0;
           break;
         case AGF_STAGE_SPOOL_UP: {  // :122-160
           double const motorSpoolUpTime = 0.5;
           double const spoolUpThrustByWeight = 0.25;
+          predicted = 1;  // :134
           cmdThrust = 9.81 * spoolUpThrustByWeight;
           cmdAngVel = Vec3d(0, 0, 0);
           RadioTypes::RadioMessageDecoded::CreateRatesCommand(uint8_t(cfg->radio_flags), float(cmdThrust), Vec3f(cmdAngVel),
@@ -419,11 +450,44 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
                         (1 - frac) * v->lastAcc + frac * Vec3d(0, 0, 0));
         } break;
         default:  // AGF_STAGE_COMPLETE :326-343
+          predicted = 1;  // :332
           RadioTypes::RadioMessageDecoded::CreateIdleCommand(uint8_t(cfg->radio_flags), rawMsg.raw);
           break;
       }
     }
+    if (v->est && predicted == 1) v->est->SetPredictedValues(Vec3d(0, 0, 0), Vec3d(0, 0, 0));
+    if (v->est && predicted == 2)
+      v->est->SetPredictedValues(cmdAngVel, (estState.att * Vec3d(0, 0, 1) * cmdThrust - Vec3d(0, 0, 9.81)));
     if (send) v->offChannel->AddMessage(rawMsg);
+  }
+}
+
+void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e) {
+  if (!e || e->kind != AGF_OFFEST_MOCAP) {
+    v->est.reset();
+    v->timerMocap.reset();
+    return;
+  }
+  v->est.reset(new Offboard::MocapStateEstimator(&v->timer, 1, e->prediction_delay));  // main.cpp:221-224
+  v->est->SetStatistics(e->meas_noise_pos, e->meas_noise_att, e->proc_noise_pos, e->proc_noise_att);
+  v->est->SetAngularVelocityTimeConstant(e->angvel_time_const);
+  v->est->_measRejectDist = e->meas_reject_dist;
+  v->timerMocap.reset(new Timer(&v->timer));  // main.cpp:286
+  v->periodMocap = double(e->mocap_period_us) * 1e-6;
+  v->delayEst = e->prediction_delay;
+}
+
+void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* o13, double* c4) {
+  Offboard::EstimatedState e = v->est ? v->est->GetPrediction(horizon) : v->estimate();
+  o13[0] = e.pos.x; o13[1] = e.pos.y; o13[2] = e.pos.z;
+  o13[3] = e.vel.x; o13[4] = e.vel.y; o13[5] = e.vel.z;
+  for (int i = 0; i < 4; i++) o13[6 + i] = e.att[i];
+  o13[10] = e.angVel.x; o13[11] = e.angVel.y; o13[12] = e.angVel.z;
+  if (c4) {
+    c4[0] = v->est ? double(v->est->_initialized) : 0.0;
+    c4[1] = v->est ? double(v->est->_numMeasRejected) : 0.0;
+    c4[2] = v->est ? double(v->est->_numMeasRejectedConsecutively) : 0.0;
+    c4[3] = v->est ? double(v->est->_predictionPipe._messages.size()) : 0.0;
   }
 }
 

@@ -93,3 +93,41 @@ def make_batch_offboard_ref(agf, sc, n=1, offsets=None, primitives=None, **kw):
         b.set_offboard_trajectories(recs)
     b.set_offboard_reference(**sc["ref"])
     return b
+
+
+def run_oracle_estimator(O, agf, sc, chunks=None, jump_at=None, est=None):
+    """Offboard loop fed by the MocapStateEstimator on an oracle.  sc: offboard / stages / tracking scenario.
+    jump_at: tick at which the vehicle is teleported by (3, 0.5, 0) m, so that measurements are rejected until the forced
+    reset.  Returns (trajectory, [estimate(0), estimate(0.03), counters])."""
+    v = O.vehicle(cfg_for(agf, sc), uwb_comm_period=sc["uwb_comm_period"])
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    v.set_offboard_estimator(est if est is not None else agf.offboard_estimator())
+    oc = agf.offboard_cfg(sc["quad_type"])
+    if "ref" in sc:
+        ref = agf.offboard_ref(**sc["ref"])
+        rec = None if sc["primitive"] is None else agf.primitive_record(**sc["primitive"])
+        step = lambda c: v.run_offboard_ref(c, oc, ref, trajectory=rec)
+    else:
+        step = lambda c: v.run_offboard(c, oc, sc["targets"])
+    parts = []
+    n = sc["nticks"]
+    if jump_at is not None:
+        parts.append(step(jump_at))
+        a = parts[0][-1]
+        v.set_state(pos=a[0:3] + np.array([3.0, 0.5, 0.0]), vel=a[3:6], att=a[6:10], ang_vel=a[10:13])
+        n -= jump_at
+    for c in (chunks or [n]):
+        parts.append(step(c))
+    e0, c4 = v.offboard_estimate(0.0)
+    e1, _ = v.offboard_estimate(0.03)
+    return np.vstack(parts), np.concatenate([e0, e1, c4])
+
+
+def make_batch_estimator(agf, sc, n=1, est=None, **kw):
+    """Batch flying `sc` (offboard / stages / tracking scenario) with the MocapStateEstimator in the loop."""
+    if "ref" in sc:
+        b = make_batch_offboard_ref(agf, sc, n=n, **kw)
+    else:
+        b = make_batch_offboard(agf, sc, n=n, **kw)
+    b.set_offboard_estimator(est if est is not None else agf.offboard_estimator())
+    return b

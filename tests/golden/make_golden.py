@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import agrifly_b200 as agf  # noqa: E402
 import orc  # noqa: E402
 from agrifly_b200 import scenarios as scen  # noqa: E402
-from common import run_oracle, run_oracle_offboard, run_oracle_offboard_ref  # noqa: E402
+from common import run_oracle, run_oracle_estimator, run_oracle_offboard, run_oracle_offboard_ref  # noqa: E402
 
 
 def sample_ticks(n):
@@ -62,6 +62,15 @@ def main():
             out[key + "/ticks"] = idx
             out[key + "/traj"] = tr[idx]
             out[key + "/offstate"] = v.offboard_state()
+        # the offboard loop fed by the reference's MocapStateEstimator (+ measurement rejection and forced reset)
+        for sc, jump in ((scen.offboard_scenario(), None), (scen.stages_scenario(1), None), (scen.tracking_scenario(), None),
+                         (scen.offboard_scenario(2000), 1000)):
+            tr, est = run_oracle_estimator(O, agf, sc, jump_at=jump)
+            idx = sample_ticks(len(tr))
+            key = "%s/est/%s%s" % (flavour, sc["name"], "" if jump is None else "-jump")
+            out[key + "/ticks"] = idx
+            out[key + "/traj"] = tr[idx]
+            out[key + "/estimate"] = est
     # codec known-answer vectors from the reference's own RadioTypes / TelemetryPacket code
     O = orc.Oracle("ref-glibc")
     rng = np.random.default_rng(7)

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from common import bit_equal, run_oracle, run_oracle_offboard, run_oracle_offboard_ref
+from common import bit_equal, run_oracle, run_oracle_estimator, run_oracle_offboard, run_oracle_offboard_ref
 from conftest import ROOT, oracle_or_skip
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
@@ -135,6 +135,53 @@ def test_offboard_reference_generators_device_code_on_host(agf, orc_mod, port_sh
         assert bit_equal(a, b), name
         if name != "tracking":
             assert bit_equal(va.offboard_state(), vb.offboard_state())
+
+
+EST_CASES = [("offboard", None), ("stages1", None), ("tracking", None), ("offboard", 1000)]
+
+
+def est_scenario(agf, name, jump):
+    if name == "offboard":
+        return agf.scenarios.offboard_scenario(2000 if jump else 4000)
+    return ref_scenario(agf, name)
+
+
+@pytest.mark.parametrize("math", ["glibc", "shared"])
+@pytest.mark.parametrize("name,jump", EST_CASES)
+def test_offboard_estimator_port_matches_reference(agf, orc_mod, math, name, jump):
+    """SURVEY 8f N1: Offboard::MocapStateEstimator in the loop (200 Hz pose measurements, prediction through the queued
+    commands, GetPrediction(30 ms) feeding the controller, SetPredictedValues after each command), restated in the
+    port: golden vectors from the reference incl. the estimates and counters, and the live reference where present.
+    The jump case teleports the vehicle: ten measurements are rejected, then the estimator resets and re-initialises."""
+    sc = est_scenario(agf, name, jump)
+    P = oracle_or_skip(orc_mod, "port-" + math)
+    tr, est = run_oracle_estimator(P, agf, sc, jump_at=jump, chunks=None if jump else [777, sc["nticks"] - 777])
+    key = "ref-%s/est/%s%s" % (math, sc["name"], "" if jump is None else "-jump")
+    assert bit_equal(tr[GOLD[key + "/ticks"]], GOLD[key + "/traj"])
+    assert bit_equal(est, GOLD[key + "/estimate"])
+    assert tr[-1, 35] == 0 and est[26] == 1 and est[27] == (10 if jump else 0)
+    # the estimate is the state: prediction over the loop latency within centimetres of the truth
+    assert np.linalg.norm(est[0:3] - tr[-1, 0:3]) < 0.02
+    if orc_mod.available("ref-" + math):
+        a, ea = run_oracle_estimator(orc_mod.Oracle("ref-" + math), agf, sc, jump_at=jump)
+        assert bit_equal(a, tr) and bit_equal(ea, est)
+
+
+def test_offboard_estimator_device_code_on_host(agf, orc_mod, port_shared):
+    """The product's device code of the estimator (agf_step.cuh mocap_update / mocap_predict / mocap_set_predicted),
+    compiled for the host, equals the port bit for bit, across launch boundaries and through the reset path."""
+    if not orc_mod.available("hostsim-shared"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "hostsim"], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("hostsim not buildable here: " + r.stderr[-300:])
+    H = orc_mod.Oracle("hostsim-shared")
+    if not hasattr(H.L, "orc_set_offboard_estimator"):
+        pytest.skip("stale hostsim build")
+    for name, jump in EST_CASES:
+        sc = est_scenario(agf, name, jump)
+        a, ea = run_oracle_estimator(port_shared, agf, sc, jump_at=jump)
+        b, eb = run_oracle_estimator(H, agf, sc, jump_at=jump, chunks=None if jump else [1, 13, 985, sc["nticks"] - 999])
+        assert bit_equal(a, b) and bit_equal(ea, eb), (name, jump)
 
 
 def test_reference_golden_still_reproducible(agf, orc_mod):

@@ -12,8 +12,8 @@ import os
 import numpy as np
 import pytest
 
-from common import (bit_equal, cfg_for, make_batch, make_batch_offboard, make_batch_offboard_ref, rel_err, run_oracle,
-                    run_oracle_offboard, run_oracle_offboard_ref)
+from common import (bit_equal, cfg_for, make_batch, make_batch_estimator, make_batch_offboard, make_batch_offboard_ref, rel_err,
+                    run_oracle, run_oracle_estimator, run_oracle_offboard, run_oracle_offboard_ref)
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
@@ -264,6 +264,69 @@ def test_offboard_reference_generators_fast_variants(agf, port_glibc):
     st = b.offboard_state()
     b.close()
     assert bit_equal(big, np.tile(big[0], (n, 1))) and np.all(st[:, 0] == agf.abi.STAGE_FLIGHT)
+
+
+@pytest.mark.parametrize("name,jump", [("offboard", None), ("stages1", None), ("tracking", None), ("offboard", 1000)])
+def test_offboard_estimator_parity(agf, port_shared, name, jump):
+    """SURVEY 8f N1: Offboard::MocapStateEstimator per vehicle inside the kernel (mocap packets every 5 ms of simulation
+    time, prediction through the queued commands, GetPrediction feeding the offboard controller).  Parity variant ==
+    oracle bit for bit: trajectory, estimates at two horizons and counters, across launch boundaries; the jump case
+    goes through ten rejected measurements and the forced reset."""
+    s = agf.scenarios
+    sc = s.offboard_scenario(2000 if jump else 3000) if name == "offboard" else (
+        s.tracking_scenario() if name == "tracking" else s.stages_scenario(int(name[-1]), nticks=5500))
+    ref, eref = run_oracle_estimator(port_shared, agf, sc, jump_at=jump)
+    b = make_batch_estimator(agf, sc, n=3)
+    left = sc["nticks"]
+    if jump:
+        b.run(jump)
+        left -= jump
+        b.set("position", b.get("position") + np.array([3.0, 0.5, 0.0]))
+    for c in (1, 2, 497):
+        b.run(c)
+        left -= c
+    b.run(left)
+    got = b.record()
+    e0, c4 = b.offboard_estimate(0.0)
+    e1, _ = b.offboard_estimate(0.03)
+    for i in range(3):
+        assert bit_equal(got[i], ref[-1]), (name, i, got[i][0:3], ref[-1][0:3])
+        assert bit_equal(np.concatenate([e0[i], e1[i], c4[i]]), eref), (name, i)
+    b.close()
+    # split Run()/advance stepping == fused ticks
+    b1 = make_batch_estimator(agf, sc, n=2)
+    b1.run(700)
+    b2 = make_batch_estimator(agf, sc, n=2)
+    for _ in range(700):
+        b2.run(1, dt_us=0)
+        b2.advance_clock(2000)
+    assert bit_equal(b1.record(), b2.record()) and bit_equal(b1.offboard_estimate(0.03)[0], b2.offboard_estimate(0.03)[0])
+    b1.close()
+    b2.close()
+
+
+def test_offboard_estimator_fast_variants(agf, port_glibc):
+    """Fast FP64 / FP32 kernels with the estimator in the loop: position within the offboard loop's stated tolerance of the
+    oracle (1e-3 / 5e-3 relative), estimate within 2 cm of the truth, for a population on the balanced schedule too."""
+    sc = agf.scenarios.offboard_scenario(3000)
+    ref, _ = run_oracle_estimator(port_glibc, agf, sc)
+    for prec in (agf.abi.PREC_FP64, agf.abi.PREC_FP32):
+        b = make_batch_estimator(agf, sc, n=3, precision=prec, math=agf.abi.MATH_FAST)
+        b.run(sc["nticks"])
+        got = b.record()[0]
+        ep = rel_err(got[0:3], ref[-1, 0:3])
+        e0, c4 = b.offboard_estimate(0.0)
+        print("estimator fast prec=%d: rel err position %.3e, |estimate - truth| %.3e" % (prec, ep, np.linalg.norm(e0[0, 0:3] - got[0:3])))
+        assert ep < (1e-3 if prec == agf.abi.PREC_FP64 else 5e-3)
+        assert np.linalg.norm(e0[0, 0:3] - got[0:3]) < 0.02 and c4[0, 0] == 1 and c4[0, 1] == 0
+        b.close()
+    n = 148 * 4 * 128 + 99
+    b = make_batch_estimator(agf, sc, n=n, precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST, telemetry_warnings=False)
+    b.run(1001)
+    b.run(999)
+    big = b.record()
+    b.close()
+    assert bit_equal(big, np.tile(big[0], (n, 1)))
 
 
 def test_monte_carlo_population_parity(agf, port_shared):
