@@ -37,6 +37,26 @@ def offboard_ref(kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0
     return r
 
 
+def csv_header():
+    """Header line of Rappids_Simulator's simulation.csv (agf_csv_header)."""
+    buf = C.create_string_buffer(1024)
+    lib().agf_csv_header(buf, len(buf))
+    return buf.value.decode()
+
+
+def csv_row(t, pos, vel, att, ang_vel, motor_forces, est_pos, est_vel, est_att, est_ang_vel, des_pos, des_vel, panic_reason,
+            last_radio_cmd):
+    """One row of simulation.csv (agf_csv_format_row) from the values Rappids_Simulator logs."""
+    r = abi.CsvRecord(t=float(t), panic_reason=int(panic_reason))
+    for name, val in (("pos", pos), ("vel", vel), ("att", att), ("ang_vel", ang_vel), ("motor_forces", motor_forces),
+                      ("est_pos", est_pos), ("est_vel", est_vel), ("est_att", est_att), ("est_ang_vel", est_ang_vel),
+                      ("des_pos", des_pos), ("des_vel", des_vel), ("last_radio_cmd", last_radio_cmd)):
+        getattr(r, name)[:] = [float(x) for x in val]
+    buf = C.create_string_buffer(2048)
+    lib().agf_csv_format_row(C.byref(r), buf, len(buf))
+    return buf.value.decode(), r
+
+
 def offboard_estimator(**edits):
     """agf_offboard_estimator_default() (MocapStateEstimator as Rappids_Simulator sets it up) with field edits."""
     e = abi.OffboardEstimator()

@@ -101,6 +101,14 @@ STAGE_WAIT_FOR_START, STAGE_SPOOL_UP, STAGE_TAKEOFF, STAGE_FLIGHT, STAGE_LANDING
 OFFTRAJ_DOUBLES, OFFSTATE_DOUBLES = 29, 16
 
 
+class CsvRecord(C.Structure):
+    _fields_ = [("t", C.c_double), ("pos", C.c_double * 3), ("vel", C.c_double * 3), ("att", C.c_double * 4),
+                ("ang_vel", C.c_double * 3), ("motor_forces", C.c_float * 4), ("est_pos", C.c_float * 3),
+                ("est_vel", C.c_float * 3), ("est_att", C.c_float * 4), ("est_ang_vel", C.c_float * 3),
+                ("des_pos", C.c_double * 3), ("des_vel", C.c_double * 3), ("panic_reason", C.c_int32),
+                ("last_radio_cmd", C.c_float * 4)]
+
+
 OFFEST_TRUTH, OFFEST_MOCAP = 0, 1
 
 
@@ -200,6 +208,8 @@ PROTOTYPES = {
     "agf_batch_set_offboard_reference": (C.c_int, [C.c_void_p, _P(OffboardRef)]),
     "agf_batch_set_offboard_trajectories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_get_offboard_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_csv_header": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "agf_csv_format_row": (C.c_size_t, [_P(CsvRecord), C.c_char_p, C.c_size_t]),
     "agf_offboard_estimator_default": (C.c_int, [_P(OffboardEstimator)]),
     "agf_batch_set_offboard_estimator": (C.c_int, [C.c_void_p, _P(OffboardEstimator)]),
     "agf_batch_get_offboard_estimate": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),

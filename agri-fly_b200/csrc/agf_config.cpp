@@ -10,6 +10,7 @@
 // All table arithmetic is float, in the reference's order, with the platform powf/sqrtf
 // (run once on the host, never on the device).
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "agrifly_b200.h"
@@ -340,6 +341,76 @@ void agf_telemetry_decode(const uint8_t* packet, agf_telemetry* o) {
     memcpy(&o->panic_reason, &d[12], 1);
     memcpy(&o->warnings, &d[13], 1);
   }
+}
+
+// ---- simulation.csv (Simulator/Rappids_Simulator/main.cpp:266-270,676-733) -------------------------------
+size_t agf_csv_header(char* buf, size_t cap) {
+  static const char h[] =
+      "t,posx,posy,posz,velx,vely,velz,attY,attP,attR,angvelx,angvely,angvelz,m1,m2,m3,m4,"
+      "estposx,estposy,estposz,estvelx,estvely,estvelz,esty,estp,estr,estangx,estangy,estangz,"
+      "desposx,desposy,desposz,desvelx,desvely,desvelz,panic,r1,r2,r3,r4\n";
+  if (buf && cap) {
+    strncpy(buf, h, cap - 1);
+    buf[cap - 1] = 0;
+  }
+  return sizeof(h) - 1;
+}
+
+namespace {
+struct CsvOut {
+  char* buf;
+  size_t cap, len;
+  void num(double v) {  // operator<<(double) of a default-constructed stream == "%g" (precision 6)
+    char tmp[40];
+    const int k = snprintf(tmp, sizeof(tmp), "%g,", v);
+    for (int i = 0; i < k; i++, len++)
+      if (buf && len + 1 < cap) buf[len] = tmp[i];
+  }
+  void integer(int v) {
+    char tmp[24];
+    const int k = snprintf(tmp, sizeof(tmp), "%d,", v);
+    for (int i = 0; i < k; i++, len++)
+      if (buf && len + 1 < cap) buf[len] = tmp[i];
+  }
+};
+}  // namespace
+
+size_t agf_csv_format_row(const agf_csv_record* r, char* buf, size_t cap) {
+  CsvOut o{buf, cap, 0};
+  o.num(r->t);
+  for (int i = 0; i < 3; i++) o.num(r->pos[i]);
+  for (int i = 0; i < 3; i++) o.num(r->vel[i]);
+  {  // Rotationd::ToEulerYPR (Rotation.hpp:163-169)
+    const double* v = r->att;
+    const double y = atan2(2.0 * v[1] * v[2] + 2.0 * v[0] * v[3], v[1] * v[1] + v[0] * v[0] - v[3] * v[3] - v[2] * v[2]);
+    const double p = -asin(2.0 * v[1] * v[3] - 2.0 * v[0] * v[2]);
+    const double rr = atan2(2.0 * v[2] * v[3] + 2.0 * v[0] * v[1], v[3] * v[3] - v[2] * v[2] - v[1] * v[1] + v[0] * v[0]);
+    o.num(y);
+    o.num(p);
+    o.num(rr);
+  }
+  for (int i = 0; i < 3; i++) o.num(r->ang_vel[i]);
+  for (int i = 0; i < 4; i++) o.num(double(r->motor_forces[i]));
+  for (int i = 0; i < 3; i++) o.num(double(r->est_pos[i]));
+  for (int i = 0; i < 3; i++) o.num(double(r->est_vel[i]));
+  {  // Rotationf::ToEulerYPR
+    const float* v = r->est_att;
+    const float y = atan2f(2.0f * v[1] * v[2] + 2.0f * v[0] * v[3], v[1] * v[1] + v[0] * v[0] - v[3] * v[3] - v[2] * v[2]);
+    const float p = -asinf(2.0f * v[1] * v[3] - 2.0f * v[0] * v[2]);
+    const float rr = atan2f(2.0f * v[2] * v[3] + 2.0f * v[0] * v[1], v[3] * v[3] - v[2] * v[2] - v[1] * v[1] + v[0] * v[0]);
+    o.num(double(y));
+    o.num(double(p));
+    o.num(double(rr));
+  }
+  for (int i = 0; i < 3; i++) o.num(double(r->est_ang_vel[i]));
+  for (int i = 0; i < 3; i++) o.num(r->des_pos[i]);
+  for (int i = 0; i < 3; i++) o.num(r->des_vel[i]);
+  o.integer(r->panic_reason);
+  for (int i = 0; i < 4; i++) o.num(double(r->last_radio_cmd[i]));
+  if (buf && o.len + 1 < cap) buf[o.len] = '\n';
+  o.len++;
+  if (buf && cap) buf[o.len < cap ? o.len : cap - 1] = 0;
+  return o.len;
 }
 
 }  // extern "C"

@@ -30,9 +30,9 @@ static constexpr bool kUwb = true;
 static constexpr bool kUwb = false;
 #endif
 
-template<bool HK, bool PV>
+template<bool HK, bool PV, bool OFFB>
 static cudaError_t go(const StepLaunch<FastP>& L, cudaStream_t stream) {
-  auto kernel = step_kernel<FastP, false, kUwb, HK, PV>;
+  auto kernel = step_kernel<FastP, false, kUwb, HK, PV, OFFB>;
   static bool carveout_set = false;
   if (!carveout_set) {  // the scratch of the resident blocks needs most of the SM's shared memory
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -44,8 +44,12 @@ static cudaError_t go(const StepLaunch<FastP>& L, cudaStream_t stream) {
 // launch_step_fast_{f32,f64}_{uwb,rates}
 cudaError_t AGF_FAST_FN(launch_step_fast_)(const StepLaunch<FastP>& L, bool hk, cudaStream_t stream) {
   const bool pv = L.pv != nullptr;
-  if (hk) return pv ? go<true, true>(L, stream) : go<true, false>(L, stream);
-  return pv ? go<false, true>(L, stream) : go<false, false>(L, stream);
+  if (L.sh.tc.off_enabled) {  // kernels with the in-kernel offboard loop compiled in
+    if (hk) return pv ? go<true, true, true>(L, stream) : go<true, false, true>(L, stream);
+    return pv ? go<false, true, true>(L, stream) : go<false, false, true>(L, stream);
+  }
+  if (hk) return pv ? go<true, true, false>(L, stream) : go<true, false, false>(L, stream);
+  return pv ? go<false, true, false>(L, stream) : go<false, false, false>(L, stream);
 }
 
 template<typename K>
@@ -65,13 +69,15 @@ void AGF_FAST_FN(kernel_attrs_fast_)(char* buf, size_t n) {
   char nm[96];
   int o = 0;
   snprintf(nm, sizeof nm, "%s", fam);
-  o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, false>);
+  o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, false, false>);
   snprintf(nm, sizeof nm, "%s+hk", fam);
-  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, true, false>);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, true, false, false>);
   snprintf(nm, sizeof nm, "%s+pv", fam);
-  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, true>);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, true, false>);
+  snprintf(nm, sizeof nm, "%s+offboard", fam);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, false, false, true>);
   snprintf(nm, sizeof nm, "%s+hk+pv", fam);
-  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, true, true>);
+  if (size_t(o) < n) o += attr_line(buf + o, n - o, nm, step_kernel<FastP, false, kUwb, true, true, false>);
 }
 
 }  // namespace agf

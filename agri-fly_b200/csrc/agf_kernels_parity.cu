@@ -8,8 +8,8 @@
 namespace agf {
 
 cudaError_t launch_step_parity(const StepLaunch<double>& L, bool uwb, int block, cudaStream_t stream) {
-  if (uwb) return launch_step_kernel<double>(step_kernel<double, true, true, true, false>, L, block, 0, stream);
-  return launch_step_kernel<double>(step_kernel<double, true, false, true, false>, L, block, 0, stream);
+  if (uwb) return launch_step_kernel<double>(step_kernel<double, true, true, true, false, true>, L, block, 0, stream);
+  return launch_step_kernel<double>(step_kernel<double, true, false, true, false, true>, L, block, 0, stream);
 }
 
 // offboard main loop outside the step kernel (split Run()/advance stepping): same arithmetic as tick()'s
@@ -82,8 +82,8 @@ static int attr_line(char* buf, size_t n, const char* name, K kernel) {
 }
 
 void kernel_attrs_parity(char* buf, size_t n) {
-  int o = attr_line(buf, n, "step<f64,parity,uwb>", step_kernel<double, true, true, true, false>);
-  if (o > 0 && size_t(o) < n) attr_line(buf + o, n - o, "step<f64,parity,nouwb>", step_kernel<double, true, false, true, false>);
+  int o = attr_line(buf, n, "step<f64,parity,uwb>", step_kernel<double, true, true, true, false, true>);
+  if (o > 0 && size_t(o) < n) attr_line(buf + o, n - o, "step<f64,parity,nouwb>", step_kernel<double, true, false, true, false, true>);
 }
 
 }  // namespace agf

@@ -2056,11 +2056,14 @@ template<typename P> AGF_DEV V3<P> inertia_inv_mul(const PlantPVDiag<P>& pv, con
   return V3<P>(pv.Iinvd[0] * x.x, pv.Iinvd[1] * x.y, pv.Iinvd[2] * x.z);
 }
 
-template<typename P, bool PARITY, bool UWB, bool HK, typename PVT>
+// OFFB: the in-kernel offboard loop (command delivery, mocap packets, command generation) is compiled in.  It is a
+// template axis because its call sites cost the hot loop registers even when never taken (spills in every fast
+// variant, round 1: FP32 full mode 1.77e10 -> 1.26e10 vehicle-steps/s with the sites merely present).
+template<typename P, bool PARITY, bool UWB, bool HK, bool OFFB, typename PVT>
 AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PVT& pv, Timing& ts,
                   uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
   const TickPlan plan = timing_plan(ts, p.tc, dt_us);
-  if (plan.off_deliver) {  // CommunicationsDelay::GetMessage -> SetCommandRadioMsg (main.cpp:737-739)
+  if (OFFB && plan.off_deliver) {  // CommunicationsDelay::GetMessage -> SetCommandRadioMsg (main.cpp:737-739)
     float4 c;
     if constexpr (PARITY) {
       c = make_float4(s.offq[4 * plan.off_deliver_slot], s.offq[4 * plan.off_deliver_slot + 1], s.offq[4 * plan.off_deliver_slot + 2],
@@ -2217,7 +2220,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       s.bits |= B_RADIO_MEAS_NEW;
     }
   }
-  if (plan.mocap_update) {  // simulated mocap packet (main.cpp:451-457): the true pose after this tick's Run()
+  if (OFFB && plan.mocap_update) {  // simulated mocap packet (main.cpp:451-457): the true pose after this tick's Run()
     const V3<P> mp(s.pos[0], s.pos[1], s.pos[2]);
     const Q4<P> ma(s.att[0], s.att[1], s.att[2], s.att[3]);
     if constexpr (PARITY) {
@@ -2227,7 +2230,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       mocap_update_cold<P>(&p.off.est, i, n, ts.now_us + dt_us, mp, ma);
     }
   }
-  if (plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance
+  if (OFFB && plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance
     const uint64_t t_gen = ts.now_us + dt_us;
     const V3<P> cp(s.pos[0], s.pos[1], s.pos[2]), cv(s.vel[0], s.vel[1], s.vel[2]);
     const Q4<P> ca(s.att[0], s.att[1], s.att[2], s.att[3]);
@@ -2318,7 +2321,7 @@ constexpr size_t step_smem_bytes(int block, bool offboard) {
 }
 
 // the ticks [t0, t1) of vehicle i; pv is the constant-bank struct or a register copy
-template<typename P, bool PARITY, bool UWB, bool HK, typename PVT>
+template<typename P, bool PARITY, bool UWB, bool HK, bool OFFB, typename PVT>
 AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc, size_t i, uint32_t t0, uint32_t t1) {
   VState<P, PARITY, UWB, HK> s;
   state_load(s, L.st, L.n, i, sc);
@@ -2352,7 +2355,7 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
       si++;
       next_cmd = si < L.sched_end ? uint32_t(L.sched[si].tick - L.tick0) : 0xFFFFFFFFu;
     }
-    tick<P, PARITY, UWB, HK>(s, sc, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
+    tick<P, PARITY, UWB, HK, OFFB>(s, sc, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
     if (L.log && --log_in == 0) {
       log_in = L.log_stride;
       const uint64_t rec = (abs_tick + 1) / L.log_stride - 1;
@@ -2367,20 +2370,20 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
 }
 
 // one work item: ticks [t0, t1) of vehicle block b
-template<typename P, bool PARITY, bool UWB, bool HK, bool PV>
+template<typename P, bool PARITY, bool UWB, bool HK, bool PV, bool OFFB>
 AGF_DEV void step_item(const StepLaunch<P>& L, const Scratch& sc, uint32_t b, uint32_t t0, uint32_t t1) {
   const size_t i = size_t(b) * blockDim.x + threadIdx.x;
   if (i >= L.n) return;
   if constexpr (PARITY) {  // generic carrier, shared or per-vehicle decided at run time
     PlantPV<P> pv;
     plant_params_load(pv, L, i);
-    step_ticks<P, PARITY, UWB, HK>(L, pv, sc, i, t0, t1);
+    step_ticks<P, PARITY, UWB, HK, OFFB>(L, pv, sc, i, t0, t1);
   } else if constexpr (PV) {
     PlantPVDiag<P> pv;
     plant_params_load(pv, L, i);
-    step_ticks<P, PARITY, UWB, HK>(L, pv, sc, i, t0, t1);
+    step_ticks<P, PARITY, UWB, HK, OFFB>(L, pv, sc, i, t0, t1);
   } else {
-    step_ticks<P, PARITY, UWB, HK>(L, L.pv_shared, sc, i, t0, t1);
+    step_ticks<P, PARITY, UWB, HK, OFFB>(L, L.pv_shared, sc, i, t0, t1);
   }
 }
 
@@ -2404,7 +2407,7 @@ AGF_DEV void flag_wait(const uint32_t* flag, uint32_t epoch) {
 #endif
 }
 
-template<typename P, bool PARITY, bool UWB, bool HK, bool PV>
+template<typename P, bool PARITY, bool UWB, bool HK, bool PV, bool OFFB>
 __global__ void __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
 step_kernel(const __grid_constant__ StepLaunch<P> L) {
   extern __shared__ float4 agf_scratch[];
@@ -2434,7 +2437,7 @@ step_kernel(const __grid_constant__ StepLaunch<P> L) {
     } else {
       b = first_whole + (k - n_head);
     }
-    step_item<P, PARITY, UWB, HK, PV>(L, sc, b, t0, t1);
+    step_item<P, PARITY, UWB, HK, PV, OFFB>(L, sc, b, t0, t1);
     if (head) flag_publish(L.flags + b_hi, L.epoch);
   }
 }

@@ -179,6 +179,25 @@ typedef struct agf_telemetry { /* TelemetryPacket::TelemetryPacket :100-119 */
 /* DecodeTelemetryPacket :169-207; fills only the fields the packet type carries */
 void agf_telemetry_decode(const uint8_t packet[AGF_TELEMETRY_PACKET_SIZE], agf_telemetry* out);
 
+/* ---- log format: Rappids_Simulator's Logs/rappids_simulator/simulation.csv -------------
+ * Header line (Simulator/Rappids_Simulator/main.cpp:266-270) and one row per offboard main-loop round (:676-733):
+ * time, true position / velocity / attitude as Euler yaw-pitch-roll (Rotation.hpp:163-169) / angular velocity,
+ * the four motor forces of the decoded telemetry packet, estimated position / velocity / Euler angles / angular
+ * velocity (floats, :696-716), desired position and velocity, panic reason, last radio command.  Every value is
+ * followed by a comma, numbers are written as the reference's ofstream writes them (6 significant digits). */
+typedef struct agf_csv_record {
+  double t;
+  double pos[3], vel[3], att[4], ang_vel[3];
+  float motor_forces[4];
+  float est_pos[3], est_vel[3], est_att[4], est_ang_vel[3];
+  double des_pos[3], des_vel[3];
+  int32_t panic_reason;
+  float last_radio_cmd[4];
+} agf_csv_record;
+/* Both return the length of the text (without the terminating NUL) and write at most cap bytes incl. the NUL. */
+size_t agf_csv_header(char* buf, size_t cap);
+size_t agf_csv_format_row(const agf_csv_record* r, char* buf, size_t cap);
+
 /* ---- the batched handle -------------------------------------------------- */
 typedef struct agf_batch agf_batch;
 

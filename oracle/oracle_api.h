@@ -93,6 +93,8 @@ void orc_get_offboard_state(orc_vehicle* v, double* out /* [AGF_OFFSTATE_DOUBLES
 /* Offboard::MocapStateEstimator in the loop (agf_offboard_estimator); NULL: back to the true state */
 void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* est);
 void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* est13, double* counters4 /* or NULL */);
+/* simulation.csv row through the reference's own stream operators and Euler conversion (ref flavours only) */
+size_t orc_csv_row(const agf_csv_record* r, char* buf, size_t cap);
 void orc_get_full(orc_vehicle* v, orc_full_state* out);
 void orc_get_telemetry(orc_vehicle* v, uint8_t p1[AGF_TELEMETRY_PACKET_SIZE],
                        uint8_t p2[AGF_TELEMETRY_PACKET_SIZE]);

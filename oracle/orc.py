@@ -116,6 +116,9 @@ class Oracle:
             L.orc_run_offboard_ref.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardRef), C.c_void_p,
                                                C.c_void_p, C.c_void_p]
             L.orc_get_offboard_state.argtypes = [vp, C.c_void_p]
+        if hasattr(L, "orc_csv_row"):
+            L.orc_csv_row.restype = C.c_size_t
+            L.orc_csv_row.argtypes = [P(abi.CsvRecord), C.c_char_p, C.c_size_t]
         if hasattr(L, "orc_set_offboard_estimator"):
             L.orc_set_offboard_estimator.argtypes = [vp, P(abi.OffboardEstimator)]
             L.orc_get_offboard_estimate.argtypes = [vp, C.c_double, C.c_void_p, C.c_void_p]

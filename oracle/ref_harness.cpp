@@ -27,6 +27,8 @@
 #include <queue>
 #include <random>
 #include <thread>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include <Eigen/Dense>
@@ -92,6 +94,13 @@ static void dump_lpf3(const LPF& f, float out[4][3]) {
   for (int i = 0; i < 4; i++) {
     out[i][0] = s[i]->x; out[i][1] = s[i]->y; out[i][2] = s[i]->z;
   }
+}
+
+template<typename Real>
+static std::string toCSV(const Vec3<Real> v) {
+  std::stringstream ss;
+  ss << v.x << "," << v.y << "," << v.z << ",";
+  return ss.str();
 }
 
 extern "C" {
@@ -500,6 +509,36 @@ void orc_get_offboard_state(orc_vehicle* v, double* o) {
     o[3 + 3 * i] = q[i]->x; o[4 + 3 * i] = q[i]->y; o[5 + 3 * i] = q[i]->z;
   }
   o[15] = v->cmdYawAngle;
+}
+
+// One row of Rappids_Simulator's simulation.csv written with the reference's own types and stream operators
+// (main.cpp:55-59 toCSV, :676-733), from the same record the product formats.
+size_t orc_csv_row(const agf_csv_record* r, char* buf, size_t cap) {
+  std::ostringstream logfile;
+  logfile << r->t << ",";
+  logfile << toCSV(Vec3d(r->pos[0], r->pos[1], r->pos[2]));
+  logfile << toCSV(Vec3d(r->vel[0], r->vel[1], r->vel[2]));
+  logfile << toCSV(Rotationd(r->att[0], r->att[1], r->att[2], r->att[3]).ToEulerYPR());
+  logfile << toCSV(Vec3d(r->ang_vel[0], r->ang_vel[1], r->ang_vel[2]));
+  for (int i = 0; i < 4; i++) logfile << r->motor_forces[i] << ",";
+  Vec3f pos(r->est_pos[0], r->est_pos[1], r->est_pos[2]), vel(r->est_vel[0], r->est_vel[1], r->est_vel[2]);
+  Rotationf att(r->est_att[0], r->est_att[1], r->est_att[2], r->est_att[3]);
+  Vec3f angVel(r->est_ang_vel[0], r->est_ang_vel[1], r->est_ang_vel[2]);
+  logfile << toCSV(pos);
+  logfile << toCSV(vel);
+  logfile << toCSV(att.ToEulerYPR());
+  logfile << toCSV(angVel);
+  logfile << toCSV(Vec3d(r->des_pos[0], r->des_pos[1], r->des_pos[2]));
+  logfile << toCSV(Vec3d(r->des_vel[0], r->des_vel[1], r->des_vel[2]));
+  logfile << int(r->panic_reason) << ",";
+  for (int i = 0; i < 4; i++) logfile << double(r->last_radio_cmd[i]) << ",";
+  logfile << "\n";
+  const std::string s = logfile.str();
+  if (buf && cap) {
+    strncpy(buf, s.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+  }
+  return s.size();
 }
 
 void orc_get_full(orc_vehicle* v, orc_full_state* o) {

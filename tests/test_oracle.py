@@ -184,6 +184,46 @@ def test_offboard_estimator_device_code_on_host(agf, orc_mod, port_shared):
         assert bit_equal(a, b) and bit_equal(ea, eb), (name, jump)
 
 
+def test_simulation_csv_rows_match_reference_stream_output(agf, orc_mod):
+    """rows of Rappids_Simulator's simulation.csv.  The product's formatter against the reference's own
+    stream operators, Rotation::ToEulerYPR and Vec3 types (oracle/_ref harness), character for character, on records
+    taken from a flight with the estimator in the loop and on awkward values; the header against main.cpp:266-270."""
+    import ctypes as C
+    hdr = agf.csv_header()
+    assert hdr.startswith("t,posx,posy,posz,velx,vely,velz,attY,attP,attR,angvelx") and hdr.endswith("panic,r1,r2,r3,r4\n")
+    assert hdr.count(",") == 39
+    R = oracle_or_skip(orc_mod, "ref-glibc")
+    sc = agf.scenarios.offboard_scenario(1500)
+    v = R.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"]), uwb_comm_period=0.0)
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    v.set_offboard_estimator(agf.offboard_estimator())
+    rng = np.random.default_rng(5)
+    rows = 0
+    for k in range(60):
+        tr = v.run_offboard(25, agf.offboard_cfg(sc["quad_type"]), sc["targets"])[-1]
+        e, _ = v.offboard_estimate(0.0)
+        p1, p2 = v.telemetry()
+        t1, t2 = agf.abi.Telemetry(), agf.abi.Telemetry()
+        agf.lib().agf_telemetry_decode(p1.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(t1))
+        agf.lib().agf_telemetry_decode(p2.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(t2))
+        text, rec = agf.csv_row(0.05 * (k + 1), tr[0:3], tr[3:6], tr[6:10], tr[10:13], list(t1.motor_forces), e[0:3], e[3:6], e[6:10],
+                                e[10:13], (1.0, -0.5, 2.5), (0, 0, 0), t2.panic_reason, rng.normal(size=4) * 10)
+        buf = C.create_string_buffer(2048)
+        R.L.orc_csv_row(C.byref(rec), buf, len(buf))
+        assert text == buf.value.decode(), (text, buf.value.decode())
+        assert text.count(",") == 40 and text.endswith(",\n")
+        rows += 1
+    for vals in ([0.0] * 3, [1e-7, -1e-7, 123456789.0], [1e21, -1e-21, 0.1], [float("nan"), float("inf"), -float("inf")],
+                 [100000.0, 1000000.0, 999999.5]):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        text, rec = agf.csv_row(vals[0], vals, vals[::-1], q, vals, vals + [0.5], vals, vals, q, vals, vals, vals, 3, vals + [1.5])
+        buf = C.create_string_buffer(2048)
+        R.L.orc_csv_row(C.byref(rec), buf, len(buf))
+        assert text == buf.value.decode(), (text, buf.value.decode())
+    assert rows == 60
+
+
 def test_reference_golden_still_reproducible(agf, orc_mod):
     """The committed vectors are what the reference build in this container produces today."""
     R = oracle_or_skip(orc_mod, "ref-glibc")
