@@ -2407,8 +2407,14 @@ AGF_DEV void flag_wait(const uint32_t* flag, uint32_t epoch) {
 #endif
 }
 
+// AGF_MAXNREG (tuning builds only): cap the registers per thread directly instead of through a blocks-per-SM target
+#ifdef AGF_MAXNREG
+#define AGF_STEP_BOUNDS __maxnreg__(AGF_MAXNREG)
+#else
+#define AGF_STEP_BOUNDS __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
+#endif
 template<typename P, bool PARITY, bool UWB, bool HK, bool PV, bool OFFB>
-__global__ void __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
+__global__ void AGF_STEP_BOUNDS
 step_kernel(const __grid_constant__ StepLaunch<P> L) {
   extern __shared__ float4 agf_scratch[];
   Scratch sc;

@@ -412,6 +412,64 @@ def main():
                                             traffic=None, vehicle_steps_per_s=sps,
                                             note="rates mode, %d vehicles, 17 floats logged per vehicle-step (68 B), ring of 32 records" % nl)
             bl.close()
+            # the in-kernel offboard loop: Rappids_Simulator's closed loop with the mocap estimator, FP32
+            try:
+                bo = agf.Batch(agf.vehicle_cfg(vehicle_id=1, motor_time_const=0.015), n, precision=agf.abi.PREC_FP32,
+                               math=agf.abi.MATH_FAST, device=local, stream=stream.cuda_stream, telemetry_warnings=False)
+                bo.set_offboard_loop(agf.offboard_cfg(5), [(0, (0.0, 0.0, 2.0)), (3000000, (1.0, -0.5, 2.5))])
+                bo.set_offboard_estimator(agf.offboard_estimator())
+                bo.run(S)
+                bo.sync()
+                bo.step_kernel_time()
+                bo.run(S)
+                bo.run(S)
+                k4, l4 = bo.step_kernel_time()
+                extras["fp32_offboard_loop_mocap"] = dict(vehicle_steps_per_s=n * S * l4 / (k4 * 1e-3), vehicles=n,
+                                                          note="rates mode + offboard position controller at 100 Hz + MocapStateEstimator at 200 Hz, in the kernel")
+                bo.close()
+            except Exception as ex:  # a secondary number must not take the headline down
+                extras["fp32_offboard_loop_mocap"] = dict(error=str(ex))
+        # C5: batched RAPPIDS planner (K6), HBM-latency-bound pixel scans
+        try:
+            nr, kr = 65536, 512  # BASELINE config 5: 64K vehicles
+            pop = agf.scenarios.rappids_population(nr, seed=2024)
+            with agf.Rappids(agf.rappids_cfg(math=agf.abi.MATH_FAST), nr, kr) as pl:
+                pl.render_scenes(pop["row_bg"], pop["boxes"])
+                pl.set_states(pop["vel0"], pop["acc0"], pop["grav"])
+                pl.sample_candidates(kr, seed=7)
+                pl.plan()
+                pl.sync()
+                pl.plan_kernel_time()
+                for _ in range(3):
+                    pl.plan()
+                pl.sync()
+                pms, pcnt = pl.plan_kernel_time()
+                st = pl.stats()
+                bytes_per_plan = 1.06e6  # DRAM bytes per plan of this workload (ncu, profiles/r1/rappids_plan_fast_summary*.txt)
+                gbs = nr * bytes_per_plan / (pms * 1e-3) / 1e9
+                extras["rappids_c5"] = dict(plans_per_s=nr / (pms * 1e-3), candidates_per_s=nr * kr / (pms * 1e-3), vehicles=nr,
+                                            candidates=kr, ms_per_launch=pms, found_fraction=st["found"] / nr,
+                                            roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=gbs / pk["hbm_gbs"],
+                                                          note="pixel scans of InflatePyramid: %.2f MB read per plan (ncu); latency-bound" % (bytes_per_plan / 1e6)))
+                # the reference planner on the host cores, same images / states / candidates (bounded sample)
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import orc_rappids
+                fl = "ref-glibc" if orc_rappids.available("ref-glibc") else "port-glibc"
+                ns = min(nr, 128 * (os.cpu_count() or 1))
+                imgs = pl.get_images(0, ns)
+                cands = pl.get_candidates(0, ns)
+                P = orc_rappids.Planner(fl)
+                reps, t0 = 0, time.time()
+                while reps < 40 and time.time() - t0 < 2.0:
+                    P.plan_many(orc_rappids.default_cfg(), imgs, pop["vel0"][:ns], pop["acc0"][:ns], pop["grav"][:ns], cands,
+                                threads=os.cpu_count() or 1, want_results=False)
+                    reps += 1
+                dt = time.time() - t0
+                extras["rappids_c5"]["cpu_baseline"] = dict(value=ns * reps / dt, unit="plans/s", cores=os.cpu_count() or 1,
+                                                            kind="reference" if fl.startswith("ref") else "port",
+                                                            sample="%d x %d plans x %d candidates, %.2f s" % (reps, ns, kr, dt))
+        except Exception as ex:
+            extras["rappids_c5"] = dict(error=str(ex))
         line["extra"] = extras
         cb, _ = cpu_baseline(args, seconds=args.cpu_seconds)
         line["cpu_baseline"] = cb

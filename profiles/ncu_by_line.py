@@ -19,7 +19,7 @@ def function_spans(src_path):
     lines = open(src_path).read().split("\n")
     owner = [None] * (len(lines) + 2)
     cur, depth, pending = None, 0, None
-    sig = re.compile(r"^\s*(?:static\s+)?(?:AGF_DEV|__global__|__device__|AGF_HDI|static AGF_DEV)[^;(]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(")
+    sig = re.compile(r"^\s*(?:static\s+)?(?:AGF_DEV|AGFR_DEV|AGF_COLD|static AGF_COLD|__global__|__device__(?:\s+__noinline__)?|AGF_HDI|static AGF_DEV|static __device__ __noinline__)[^;(]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(")
     for i, ln in enumerate(lines, 1):
         if depth == 0:
             m = sig.match(ln)
