@@ -78,6 +78,25 @@ __global__ void transpose_kernel(uint16_t* __restrict__ dst, const uint16_t* __r
   }
 }
 
+// Minimum of every group of 32 consecutive pixels of every line of `plane` ([lines][pitch]); pixels <= ignore count as
+// 65535 (they are never "seen" by the planner, DepthImagePlanner.cpp:506).  One thread per (line, group).
+__global__ void groupmin_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ plane, int pitch, int G, size_t lines,
+                                int ignore) {
+  const size_t total = lines * (size_t)G;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t line = idx / G;
+    const int g = (int)(idx - line * G);
+    const uint16_t* src = plane + line * pitch + (size_t)g * 32;
+    const int cnt = min(32, pitch - g * 32);
+    unsigned m = 65535u;
+    for (int k = 0; k < cnt; k++) {
+      const unsigned p = src[k];
+      if ((int)p > ignore) m = min(m, p);
+    }
+    out[idx] = (uint16_t)m;
+  }
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -147,6 +166,20 @@ struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint16_t *img = nullptr, *imgT = nullptr;
+  uint16_t *gminR = nullptr, *gminC = nullptr;  // group minima of the rows / columns (agf_rappids_plan.cuh)
+  int GW() const { return (cfg.width + 31) / 32; }
+  int GH() const { return (cfg.height + 31) / 32; }
+  int ignore_value() const { return (int)(uint16_t)(cfg.true_radius / cfg.depth_scale); }
+  int rebuild_groupmin(size_t first, size_t count) {  // after the images of these vehicles changed
+    const int W = cfg.width, H = cfg.height;
+    const size_t tr = count * (size_t)H * GW(), tc = count * (size_t)W * GH();
+    const int gr = (int)((tr + 255) / 256 < 148 * 16 ? (tr + 255) / 256 : 148 * 16);
+    const int gc = (int)((tc + 255) / 256 < 148 * 16 ? (tc + 255) / 256 : 148 * 16);
+    groupmin_kernel<<<gr, 256, 0, stream>>>(gminR + first * (size_t)H * GW(), img + first * npix(), W, GW(), count * (size_t)H, ignore_value());
+    groupmin_kernel<<<gc, 256, 0, stream>>>(gminC + first * (size_t)W * GH(), imgT + first * npix(), H, GH(), count * (size_t)W, ignore_value());
+    launches += 2;
+    return cudaGetLastError() == cudaSuccess ? AGF_OK : AGF_ECUDA;
+  }
   double *state = nullptr, *cands = nullptr, *pyr = nullptr, *stats = nullptr;
   uint8_t* flags = nullptr;
   agf_rappids_result* results = nullptr;
@@ -167,6 +200,8 @@ struct Handle {
     }
     cudaFree(img);
     cudaFree(imgT);
+    cudaFree(gminR);
+    cudaFree(gminC);
     cudaFree(state);
     cudaFree(cands);
     cudaFree(pyr);
@@ -297,6 +332,8 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   }
   AGFR_ALLOC(h->img, n * npix * sizeof(uint16_t));
   AGFR_ALLOC(h->imgT, n * npix * sizeof(uint16_t));
+  AGFR_ALLOC(h->gminR, n * (size_t)cfg->height * ((cfg->width + 31) / 32) * sizeof(uint16_t));
+  AGFR_ALLOC(h->gminC, n * (size_t)cfg->width * ((cfg->height + 31) / 32) * sizeof(uint16_t));
   AGFR_ALLOC(h->state, n * 12 * sizeof(double));
   AGFR_ALLOC(h->cands, n * (size_t)h->kcap * 4 * sizeof(double));
   AGFR_ALLOC(h->flags, n * (size_t)h->kcap);
@@ -309,6 +346,8 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   // the shared cost vector
   cudaMemsetAsync(h->img, 0, n * npix * sizeof(uint16_t), h->stream);
   cudaMemsetAsync(h->imgT, 0, n * npix * sizeof(uint16_t), h->stream);
+  cudaMemsetAsync(h->gminR, 0xFF, n * (size_t)cfg->height * ((cfg->width + 31) / 32) * sizeof(uint16_t), h->stream);  // nothing seen
+  cudaMemsetAsync(h->gminC, 0xFF, n * (size_t)cfg->width * ((cfg->height + 31) / 32) * sizeof(uint16_t), h->stream);
   cudaMemsetAsync(h->results, 0, n * sizeof(agf_rappids_result), h->stream);
   cudaMemsetAsync(h->flags, 0, n * (size_t)h->kcap, h->stream);
   {
@@ -357,6 +396,7 @@ int agf_rappids_set_images(agf_rappids* p, const uint16_t* images, size_t first,
                             cudaMemcpyHostToDevice, h->stream));
   if (int rc = h->retranspose(first, count)) return rc;
   h->launches += 1;
+  if (int rc = h->rebuild_groupmin(first, count)) return fail(rc, "group-minimum kernel launch");
   AGFR_CUDA(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
   return AGF_OK;
 }
@@ -380,6 +420,7 @@ int agf_rappids_render_scenes(agf_rappids* p, const uint16_t* row_bg, const int3
   render_kernel<true><<<grid, 256, 0, h->stream>>>(h->imgT + first * h->npix(), d_bg, d_box, W, Hh, count);
   AGFR_CUDA(cudaGetLastError());
   h->launches += 2;
+  if (int rc = h->rebuild_groupmin(first, count)) return fail(rc, "group-minimum kernel launch");
   AGFR_CUDA(cudaStreamSynchronize(h->stream));
   return AGF_OK;
 }
@@ -475,6 +516,10 @@ int agf_rappids_plan(agf_rappids* p) {
   agfr::PlanParams P;
   P.img = h->img;
   P.imgT = h->imgT;
+  P.gminR = h->gminR;
+  P.gminC = h->gminC;
+  P.GW = h->GW();
+  P.GH = h->GH();
   P.state = h->state;
   P.cands = h->cands;
   P.flags = h->flags;

@@ -39,15 +39,14 @@ constexpr int kMaxPyr = 32;
 #define AGFR_MIN_BLOCKS 5
 #endif
 #endif
-#ifndef AGFR_AHEAD
-#define AGFR_AHEAD 6       // image lines prefetched ahead of a region scan
-#endif
 constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
 
 struct PlanParams {
   // images
   const uint16_t* img;    // [n][H][W]
   const uint16_t* imgT;   // [n][W][H]
+  const uint16_t* gminR;  // [n][H][GW] minimum of each group of 32 pixels of a row (pixels <= ignore count as 65535)
+  const uint16_t* gminC;  // [n][W][GH] the same per column
   const double* state;    // [n][12]: vel0, acc0, grav, cost vector
   const double* cands;    // [n][kcap][4]
   uint8_t* flags;         // [n][kcap]
@@ -55,7 +54,7 @@ struct PlanParams {
   double* pyramids;       // [n][kMaxPyr][17]
   int* next;              // work counter
   int n, k, kcap;
-  int W, H;
+  int W, H, GW, GH;       // GW = ceil(W / 32), GH = ceil(H / 32)
   double scale, f, cx, cy, rPlan, minDist;
   double fminA, fmaxA, wmaxA, minSec, vmax;
   int maxPyr, costKind;
@@ -355,6 +354,8 @@ struct Section {
 struct WarpCtx {
   const uint16_t* img;
   const uint16_t* imgT;
+  const uint16_t* gminR;
+  const uint16_t* gminC;
   double* pdepth;  // shared: [kMaxPyr] base-plane depths, ascending
   int4* pedge;     // shared: [kMaxPyr] (right, top, left, bottom)
   int npyr;
@@ -453,26 +454,41 @@ AGFR_DEV bool shrink_apply(const int REGION, Shrink& s, int num, int x, int y, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// 256-pixel chunks.  The scans below are waits on dependent 64-byte loads when taken 32 pixels per step (ncu, round 1:
-// 64 % of the stall samples on the two pixel loads), so a line is first read 8 pixels per lane (one aligned 128-bit
-// load, 512 B per warp step) and tested for "can any pixel of this chunk matter at all"; only chunks that can are
-// replayed 32 pixels per step in the reference's scan order (L1 hits).  Skipping a chunk in which no pixel passes
-// the order-independent part of the test is exact.
+// Group minima.  The scans below are waits on dependent pixel loads when every pixel is fetched (ncu, round 1: 64 % of
+// the stall samples on the two pixel loads, 1.06 MB of DRAM reads per plan), and most of what they fetch cannot
+// matter: a pixel only changes the state if it is nearer than the pyramid's depth.  gminR[y][g] / gminC[x][g] hold, for
+// every image row / column, the minimum of each group of 32 pixels (pixels <= `ignore` count as 65535).  A scan first
+// reads the minima of the groups its range touches (20 bytes per 320-pixel line, L1/L2 resident: 10 KB per image) and
+// only groups whose minimum is below the bound are replayed 32 pixels per step in the reference's scan order.
+// Skipping a group in which no pixel passes the order-independent part of the test is exact -- also for a group the
+// range covers only partly, because its minimum bounds the sub-range's minimum from below.
 // ---------------------------------------------------------------------------------------------
-AGFR_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// lb: 16-byte aligned pointer at or below `line`, mis = line - lb (elements); chunk c covers lb[256 c .. 256 c + 255]
-AGFR_DEV bool chunk_load(const uint16_t* lb, int c, int lane, int jlo, int jhi, uint4& v, int& j0) {
-  j0 = c * 256 + lane * 8;
-  const bool in = (j0 + 7 >= jlo) && (j0 <= jhi);
-  v = in ? __ldg(reinterpret_cast<const uint4*>(lb + j0)) : make_uint4(0, 0, 0, 0);
-  return in;
-}
-// per-halfword masks (0xFFFF where true) of `ignore < p` and `p < bound` for the two pixels of a word
-AGFR_DEV unsigned pix_between(unsigned w, unsigned ign2, unsigned bnd2) { return __vcmpgtu2(w, ign2) & __vcmpltu2(w, bnd2); }
-// mask of the halfwords of word q (pixels j0 + 2q, j0 + 2q + 1) that lie inside [jlo, jhi]
-AGFR_DEV unsigned pix_inside(int j0, int q, int jlo, int jhi) {
-  const int a = j0 + 2 * q, b = a + 1;
-  return ((a >= jlo && a <= jhi) ? 0x0000FFFFu : 0u) | ((b >= jlo && b <= jhi) ? 0xFFFF0000u : 0u);
+// Can any pixel of a group trigger an update (shrink_trigger) at all?  o: the line (x for column walks, y for row
+// walks), [ia, ib]: the inner indices of the group's part of the range, gm: the group minimum (<= every seen pixel of
+// it).  Each trigger has the form  f * p < num  with a factor f that does not depend on p; if the smallest factor of
+// the group is >= 0 then f * p >= fmin * gm for all its pixels, so  fmin * gm >= num  rules every pixel out -- exactly,
+// in integers.  The bounds only ever move inwards, which only makes factors larger, so testing with the current
+// bounds is safe.
+AGFR_DEV bool group_may_trigger(const int REGION, const Shrink& s, int num, int o, int ia, int ib, int gm) {
+  const bool colWalk = (REGION == R_RIGHT || REGION == R_LEFT);
+  bool may = true;
+  if (REGION == R_RIGHT || REGION == R_TR || REGION == R_BR) {  // num > (x - rS) * p
+    const int f = (colWalk ? o : ia) - s.rS;
+    if (f >= 0 && f * gm >= num) may = false;
+  }
+  if (REGION == R_LEFT || REGION == R_TL || REGION == R_BL) {  // (lS - x) * p < num
+    const int f = s.lS - (colWalk ? o : ib);
+    if (f >= 0 && f * gm >= num) may = false;
+  }
+  if (REGION == R_TOP || REGION == R_TR || REGION == R_TL) {  // (tS - y) * p < num
+    const int f = s.tS - o;
+    if (f >= 0 && f * gm >= num) may = false;
+  }
+  if (REGION == R_BOTTOM || REGION == R_BR || REGION == R_BL) {  // num > (y - bS) * p
+    const int f = o - s.bS;
+    if (f >= 0 && f * gm >= num) may = false;
+  }
+  return may;
 }
 
 // the 32-pixels-per-step scan of inner indices i0 + dI*k, k < cnt, of one line (reference order)
@@ -509,81 +525,60 @@ static __device__ __noinline__ bool shrink_region(const int REGION, const PlanPa
                                                   int cnt) {
   const bool colWalk = (REGION == R_RIGHT || REGION == R_LEFT);  // outer x, inner y
   if (cnt <= 0) return true;
-  const int pitch = colWalk ? P.H : P.W;
+  const int pitch = colWalk ? P.H : P.W, G = colWalk ? P.GH : P.GW;
   const int lo = dI > 0 ? i0 : i0 - (cnt - 1), hi = dI > 0 ? i0 + (cnt - 1) : i0;
-  const unsigned ign2 = (unsigned)min(max(P.ignore, 0), 65535) * 0x10001u, bnd2 = (unsigned)min(maxDepth, 65535) * 0x10001u;
-  constexpr int kAhead = AGFR_AHEAD;  // lines prefetched ahead of the scan
   const uint16_t* plane = colWalk ? w.imgT : w.img;
+  const uint16_t* gplane = colWalk ? w.gminC : w.gminR;
+  const int g0 = lo >> 5, g1 = hi >> 5;
   for (int oc = 0; oc < nOuter; oc++) {
     const int o = o0 + dO * oc;
-    const uint16_t* line = plane + (size_t)o * pitch;
-    if (lo + w.lane * 64 <= hi) {  // one 128-byte line per lane
-      if (oc == 0)
-        for (int d = 1; d < kAhead && d < nOuter; d++) prefetch_l1(plane + (size_t)(o + dO * d) * pitch + lo + w.lane * 64);
-      if (oc + kAhead < nOuter) prefetch_l1(plane + (size_t)(o + dO * kAhead) * pitch + lo + w.lane * 64);
-    }
-    const int mis = (int)(((uintptr_t)line & 15u) >> 1);
-    const uint16_t* lb = line - mis;
-    const int jlo = lo + mis, jhi = hi + mis;
-    const int c0 = jlo >> 8, c1 = jhi >> 8;
-    for (int cc = 0; cc <= c1 - c0; cc++) {
-      const int c = dI > 0 ? c0 + cc : c1 - cc;
-      uint4 v;
-      int j0;
-      chunk_load(lb, c, w.lane, jlo, jhi, v, j0);
-      unsigned m = pix_between(v.x, ign2, bnd2) | pix_between(v.y, ign2, bnd2) | pix_between(v.z, ign2, bnd2) |
-                   pix_between(v.w, ign2, bnd2);
-      if (m != 0u && !(j0 >= jlo && j0 + 7 <= jhi))  // a segment that straddles an end of the range: mask pixel by pixel
-        m = (pix_between(v.x, ign2, bnd2) & pix_inside(j0, 0, jlo, jhi)) | (pix_between(v.y, ign2, bnd2) & pix_inside(j0, 1, jlo, jhi)) |
-            (pix_between(v.z, ign2, bnd2) & pix_inside(j0, 2, jlo, jhi)) | (pix_between(v.w, ign2, bnd2) & pix_inside(j0, 3, jlo, jhi));
-      if (!__any_sync(AGFR_FULL, m != 0u)) continue;
-      // replay this chunk's part of the range in scan order
-      const int a = max(lo, c * 256 - mis), b = min(hi, c * 256 + 255 - mis);
-      if (!shrink_span(REGION, P, w, s, maxDepth, x0, y0, o, line, dI > 0 ? a : b, dI, b - a + 1)) return false;
+    const uint16_t* gl = gplane + (size_t)o * G;
+    for (int gb = 0; gb <= g1 - g0; gb += 32) {  // 32 groups (1024 pixels) per step, in scan order
+      const int k = gb + w.lane;
+      const int g = dI > 0 ? g0 + k : g1 - k;
+      const bool in = k <= g1 - g0;
+      const unsigned gm = in ? ld16(gl + g) : 65535u;
+      unsigned need = __ballot_sync(AGFR_FULL, in && (int)gm < maxDepth &&
+                                                   group_may_trigger(REGION, s, P.num, o, max(lo, g << 5), min(hi, (g << 5) + 31), (int)gm));
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int gs = dI > 0 ? g0 + gb + src : g1 - gb - src;
+        const int a = max(lo, gs << 5), b = min(hi, (gs << 5) + 31);
+        if (!shrink_span(REGION, P, w, s, maxDepth, x0, y0, o, plane + (size_t)o * pitch, dI > 0 ? a : b, dI, b - a + 1))
+          return false;
+      }
     }
   }
   return true;
 }
 
 // one line of the spiral expansion (DepthImagePlanner.cpp:521-597): returns true when a pixel nearer than the
-// pyramid's minimum depth blocks the side; folds the depths seen before it into maxDepth
-// `plane` + idx * pitch is the line; the lines idx + step .. are the ones the next rounds of the spiral will ask for
-static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* plane, int pitch, int nLines, int idx,
-                          int step, int a, int b, int minPyr, int& maxDepth) {
+// pyramid's minimum depth blocks the side; folds the depths seen before it into maxDepth.
+// `plane` + idx * pitch is the pixel line, `gplane` + idx * G its group minima.
+static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* plane, const uint16_t* gplane,
+                                                int pitch, int G, int idx, int a, int b, int minPyr, int& maxDepth) {
   const uint16_t* line = plane + (size_t)idx * pitch;
-  {
-    const int nx = idx + 3 * step;  // three rounds ahead
-    if (nx >= 0 && nx < nLines && a + w.lane * 64 <= b) prefetch_l1(plane + (size_t)nx * pitch + a + w.lane * 64);
-  }
+  const uint16_t* gl = gplane + (size_t)idx * G;
   unsigned mn = 65535u;
   bool blocked = false;
-  const unsigned ign2 = (unsigned)min(max(P.ignore, 0), 65535) * 0x10001u,
-                 blk2 = (unsigned)min(max(minPyr, 0), 65535) * 0x10001u;
-  const int mis = (int)(((uintptr_t)line & 15u) >> 1);
-  const uint16_t* lb = line - mis;
-  const int jlo = a + mis, jhi = b + mis;
-  for (int c = jlo >> 8; c <= (jhi >> 8) && !blocked; c++) {
-    uint4 v;
-    int j0;
-    chunk_load(lb, c, w.lane, jlo, jhi, v, j0);
-    const unsigned wd[4] = {v.x, v.y, v.z, v.w};
-    unsigned anyblk = 0, lmin = 0xFFFFFFFFu;
-    const bool whole = j0 >= jlo && j0 + 7 <= jhi;  // lanes outside the range hold zeros, which are never seen
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      unsigned sees = __vcmpgtu2(wd[q], ign2);
-      if (!whole) sees &= pix_inside(j0, q, jlo, jhi);
-      anyblk |= sees & __vcmpltu2(wd[q], blk2);
-      lmin = __vminu2(lmin, wd[q] | ~sees);  // pixels that are not seen count as 65535
-    }
-    if (!__any_sync(AGFR_FULL, anyblk != 0u)) {
-      mn = min(mn, min(lmin & 0xFFFFu, lmin >> 16));
-      continue;
-    }
-    // a blocking pixel in this chunk: 32 pixels per step, the depths before the first blocking pixel count
-    const int ca = max(a, c * 256 - mis), cb = min(b, c * 256 + 255 - mis);
-    for (int v0 = ca; v0 <= cb; v0 += 32) {
-      const int vv = v0 + w.lane;
+  const int g0 = a >> 5, g1 = b >> 5;
+  for (int gb = g0; gb <= g1 && !blocked; gb += 32) {
+    const int g = gb + w.lane;
+    const bool in = g <= g1;
+    const unsigned gm = in ? ld16(gl + g) : 65535u;
+    const bool full = in && (g << 5) >= a && (g << 5) + 31 <= b;
+    // a group is looked at pixel by pixel if it may hold a blocking pixel, or if it is covered partly and may lower maxDepth
+    // (the minimum of the covered part is >= the group minimum, so gm >= maxDepth means it cannot)
+    const bool cand = in && (int)gm < minPyr;
+    unsigned scan = __ballot_sync(AGFR_FULL, cand || (in && !full && (int)gm < maxDepth));
+    int blockLane = 32;
+    while (scan) {
+      const int src = __ffs(scan) - 1;
+      scan &= scan - 1;
+      const int gs = gb + src;
+      const int ca = max(a, gs << 5), cb = min(b, (gs << 5) + 31);
+      const int vv = ca + w.lane;
       const bool valid = vv <= cb;
       const int p = valid ? (int)ld16(line + vv) : 0;
       const bool sees = valid && p > P.ignore;
@@ -593,9 +588,12 @@ static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpC
       if (sees && !blk && ((before >> w.lane) & 1u)) mn = min(mn, (unsigned)p);
       if (bm) {
         blocked = true;
+        blockLane = src;
         break;
       }
     }
+    // whole groups without a blocking pixel, before the blocking group: their minimum is the minimum of their seen pixels
+    if (full && !cand && w.lane < blockLane) mn = min(mn, gm);
   }
   mn = __reduce_min_sync(AGFR_FULL, mn);
   if ((int)mn < maxDepth) maxDepth = (int)mn;
@@ -650,7 +648,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
   while (rf || tf || lf || bf) {
     if (rf) {
       if (right < W - edgeOff - 1) {
-        if (expand_line(P, w, w.imgT, H, W, right + 1, 1, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, right + 1, top, bottom, minPyr, maxDepth)) {
           rf = false;
           right--;
         }
@@ -661,7 +659,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (tf) {
       if (top > edgeOff) {
-        if (expand_line(P, w, w.img, W, H, top - 1, -1, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, w.gminR, W, P.GW, top - 1, left, right, minPyr, maxDepth)) {
           tf = false;
           top++;
         }
@@ -672,7 +670,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (lf) {
       if (left > edgeOff) {
-        if (expand_line(P, w, w.imgT, H, W, left - 1, -1, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, left - 1, top, bottom, minPyr, maxDepth)) {
           lf = false;
           left++;
         }
@@ -683,7 +681,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (bf) {
       if (bottom < H - edgeOff - 1) {
-        if (expand_line(P, w, w.img, W, H, bottom + 1, 1, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, w.gminR, W, P.GW, bottom + 1, left, right, minPyr, maxDepth)) {
           bf = false;
           bottom--;
         }
@@ -920,6 +918,8 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
     if (v >= P.n) break;
     w.img = P.img + (size_t)v * P.W * P.H;
     w.imgT = P.imgT + (size_t)v * P.W * P.H;
+    w.gminR = P.gminR + (size_t)v * P.H * P.GW;
+    w.gminC = P.gminC + (size_t)v * P.W * P.GH;
     w.npyr = 0;
     const double* st = P.state + (size_t)v * 12;
     Prim pr;

@@ -445,12 +445,12 @@ def main():
                 pl.sync()
                 pms, pcnt = pl.plan_kernel_time()
                 st = pl.stats()
-                bytes_per_plan = 1.06e6  # DRAM bytes per plan of this workload (ncu, profiles/r1/rappids_plan_fast_summary*.txt)
+                bytes_per_plan = 1.06e6  # algorithmic: bytes of the pixels the reference scans per plan of this workload (ncu DRAM reads of the all-pixels build, profiles/r1/rappids_plan_fast_summary_v0.txt)
                 gbs = nr * bytes_per_plan / (pms * 1e-3) / 1e9
                 extras["rappids_c5"] = dict(plans_per_s=nr / (pms * 1e-3), candidates_per_s=nr * kr / (pms * 1e-3), vehicles=nr,
                                             candidates=kr, ms_per_launch=pms, found_fraction=st["found"] / nr,
                                             roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=gbs / pk["hbm_gbs"],
-                                                          note="pixel scans of InflatePyramid: %.2f MB read per plan (ncu); latency-bound" % (bytes_per_plan / 1e6)))
+                                                          note="pixel scans of InflatePyramid: %.2f MB of pixels per plan in the reference algorithm; latency-bound" % (bytes_per_plan / 1e6)))
                 # the reference planner on the host cores, same images / states / candidates (bounded sample)
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import orc_rappids
