@@ -509,6 +509,14 @@ class Rappids:
         _check(lib().agf_rappids_get_results(self._h, out.ctypes.data, first, count))
         return out
 
+    def tracking_primitives(self, first=0, count=None):
+        """[count][29] records for Batch.set_offboard_trajectories (trajAtt identity, trajOffset zero: fill in columns
+        22:26 and 26:29)."""
+        count = self._cnt(first, count)
+        out = np.zeros((count, abi.OFFTRAJ_DOUBLES))
+        _check(lib().agf_rappids_get_tracking_primitives(self._h, out.ctypes.data, first, count))
+        return out
+
     def candidate_flags(self, first=0, count=None):
         count = self._cnt(first, count)
         out = np.zeros((count, self.k), dtype=np.uint8)

@@ -172,6 +172,7 @@ PROTOTYPES = {
     "agf_rappids_sync": (C.c_int, [C.c_void_p]),
     "agf_rappids_get_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_rappids_get_candidate_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_get_tracking_primitives": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_rappids_get_pyramids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_rappids_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "agf_rappids_reduce_stats_device": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -180,7 +180,7 @@ struct Handle {
     launches += 2;
     return cudaGetLastError() == cudaSuccess ? AGF_OK : AGF_ECUDA;
   }
-  double *state = nullptr, *cands = nullptr, *pyr = nullptr, *stats = nullptr;
+  double *state = nullptr, *cands = nullptr, *pyr = nullptr, *stats = nullptr, *prims = nullptr;
   uint8_t* flags = nullptr;
   agf_rappids_result* results = nullptr;
   int* next = nullptr;
@@ -201,6 +201,7 @@ struct Handle {
     cudaFree(img);
     cudaFree(imgT);
     cudaFree(gminR);
+    cudaFree(prims);
     cudaFree(gminC);
     cudaFree(state);
     cudaFree(cands);
@@ -340,6 +341,7 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   AGFR_ALLOC(h->results, n * sizeof(agf_rappids_result));
   AGFR_ALLOC(h->pyr, n * (size_t)AGF_RAPPIDS_MAX_PYRAMIDS * AGF_RAPPIDS_PYRAMID_DOUBLES * sizeof(double));
   AGFR_ALLOC(h->stats, 8 * sizeof(double));
+  AGFR_ALLOC(h->prims, n * 9 * sizeof(double));
   AGFR_ALLOC(h->next, sizeof(int));
 #undef AGFR_ALLOC
   // images start empty (everything at the far plane would be 65535; zero = "ignored" pixels), states zero with
@@ -525,6 +527,7 @@ int agf_rappids_plan(agf_rappids* p) {
   P.flags = h->flags;
   P.results = h->results;
   P.pyramids = h->pyr;
+  P.prims = h->prims;
   P.next = h->next;
   P.n = (int)h->n;
   P.k = h->k;
@@ -580,6 +583,36 @@ int agf_rappids_get_results(agf_rappids* p, agf_rappids_result* out, size_t firs
   AGFR_CUDA(cudaSetDevice(h->device));
   AGFR_CUDA(cudaMemcpyAsync(out, h->results + first, count * sizeof(agf_rappids_result), cudaMemcpyDeviceToHost, h->stream));
   AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  return AGF_OK;
+}
+
+int agf_rappids_get_tracking_primitives(agf_rappids* p, double* records, size_t first, size_t count) {
+  if (!p || !records) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  if (!count) return AGF_OK;
+  AGFR_CUDA(cudaSetDevice(h->device));
+  std::vector<double> abg(count * 9), st(count * 12);
+  std::vector<agf_rappids_result> res(count);
+  AGFR_CUDA(cudaMemcpyAsync(abg.data(), h->prims + first * 9, abg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaMemcpyAsync(st.data(), h->state + first * 12, st.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaMemcpyAsync(res.data(), h->results + first, count * sizeof(agf_rappids_result), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < count; i++) {
+    double* r = records + i * AGF_OFFTRAJ_DOUBLES;
+    for (int a = 0; a < 3; a++) {
+      r[6 * a + 0] = 0.0;                // trajectories start at the focal point
+      r[6 * a + 1] = st[i * 12 + a];      // vel0
+      r[6 * a + 2] = st[i * 12 + 3 + a];  // acc0
+      r[6 * a + 3] = abg[i * 9 + 3 * a];
+      r[6 * a + 4] = abg[i * 9 + 3 * a + 1];
+      r[6 * a + 5] = abg[i * 9 + 3 * a + 2];
+      r[18 + a] = st[i * 12 + 6 + a];     // gravity in the trajectory frame
+      r[26 + a] = 0.0;
+    }
+    r[21] = res[i].found ? res[i].best_tf : 0.0;
+    r[22] = 1.0; r[23] = r[24] = r[25] = 0.0;
+  }
   return AGF_OK;
 }
 

@@ -52,6 +52,7 @@ struct PlanParams {
   uint8_t* flags;         // [n][kcap]
   void* results;          // agf_rappids_result [n]
   double* pyramids;       // [n][kMaxPyr][17]
+  double* prims;          // [n][9]: alpha, beta, gamma of the returned primitive per axis (SingleAxisTrajectory state), or null
   int* next;              // work counter
   int n, k, kcap;
   int W, H, GW, GH;       // GW = ceil(W / 32), GH = ceil(H / 32)
@@ -1033,6 +1034,23 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
       out->best_tf = bestT;
     }
     if (lane < 18) out->best_coeffs[lane] = bestQ.c[lane / 3][lane % 3];
+    if (P.prims) {  // the returned primitive in the generator's own variables: regenerated (same code, same inputs) rather than
+                    // carried through the candidate loop in registers
+      double abg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      if (found) {
+        const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + bestIdx) * 4);
+        const double goal[3] = {c4.x, c4.y, c4.z};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          pr.ax[a].generate(goal[a], c4.w);
+          abg[3 * a] = pr.ax[a].al;
+          abg[3 * a + 1] = pr.ax[a].be;
+          abg[3 * a + 2] = pr.ax[a].ga;
+        }
+      }
+      if (lane == 0)
+        for (int q = 0; q < 9; q++) P.prims[(size_t)v * 9 + q] = abg[q];
+    }
     {
       double* rec = P.pyramids + ((size_t)v * kMaxPyr + lane) * 17;
       if (lane < w.npyr) {

@@ -115,6 +115,12 @@ int agf_rappids_plan(agf_rappids* p);
 int agf_rappids_sync(agf_rappids* p);
 
 int agf_rappids_get_results(agf_rappids* p, agf_rappids_result* out, size_t first, size_t count);
+/* The returned trajectories as records for the in-kernel tracking loop, [count][AGF_OFFTRAJ_DOUBLES] (agrifly_b200.h,
+ * agf_batch_set_offboard_trajectories): the primitive in SingleAxisTrajectory's own variables (p0 = 0, v0, a0 of the
+ * vehicle, alpha / beta / gamma of the best candidate -- the object Rappids_Simulator copies into `_traj`, main.cpp:524-526),
+ * gravity in the trajectory frame and the end time; trajAtt is written as identity and trajOffset as zero, to be filled in
+ * by the caller (estState.att * depthCamAtt and estState.pos, main.cpp:519-522).  Vehicles without a trajectory get tf = 0. */
+int agf_rappids_get_tracking_primitives(agf_rappids* p, double* records, size_t first, size_t count);
 /* TrajectoryTestResult of every candidate, [count][k] bytes (the `trajectories` vector of the reference call). */
 int agf_rappids_get_candidate_flags(agf_rappids* p, uint8_t* flags, size_t first, size_t count);
 /* GetPyramids(): [count][AGF_RAPPIDS_MAX_PYRAMIDS][AGF_RAPPIDS_PYRAMID_DOUBLES], depth order, unused records NaN. */

@@ -245,3 +245,56 @@ def test_full_size_population_properties(agf):
         e = P.plan(R.default_cfg(max_pyramids=32), img, pop["vel0"][i], pop["acc0"][i], pop["grav"][i], candidates=cand)
         same += int(np.array_equal(flags[i], e["results"]) and res[i]["best_index"] == e["best_index"])
     assert same >= 46, same
+
+
+def test_planned_primitives_fly_in_the_tracking_loop(agf):
+    """N3 -> N1: depth image -> planner -> the returned primitive in SingleAxisTrajectory's own variables
+    (agf_rappids_get_tracking_primitives) -> RunTracking inside the step kernel.  The records reproduce the planner's
+    polynomial exactly (alpha / 120 == t^5 coefficient, ...), and a population flying its planned primitives matches the
+    oracle flying the same records bit for bit."""
+    import orc
+    from common import cfg_for, make_batch_offboard_ref
+    if not orc.available("port-shared"):
+        pytest.skip("oracle port not built")
+    n, k = 24, 256
+    pop = agf.scenarios.rappids_population(n, seed=77)
+    with agf.Rappids(agf.rappids_cfg(math=agf.abi.MATH_PARITY), n, k) as pl:
+        pl.render_scenes(pop["row_bg"], pop["boxes"])
+        pl.set_states(pop["vel0"], pop["acc0"], pop["grav"])
+        pl.sample_candidates(k, seed=3)
+        pl.plan()
+        pl.sync()
+        res = pl.results()
+        rec = pl.tracking_primitives()
+    assert rec.shape == (n, agf.abi.OFFTRAJ_DOUBLES) and np.sum(res["found"]) >= n // 2
+    for i in range(n):
+        if not res[i]["found"]:
+            assert rec[i, 21] == 0.0
+            continue
+        c = res[i]["best_coeffs"].reshape(6, 3)
+        for a in range(3):
+            p0, v0, a0, al, be, ga = rec[i, 6 * a:6 * a + 6]
+            assert (al / 120, be / 24, ga / 6, a0 / 2, v0, p0) == tuple(c[:, a]), (i, a)
+        assert rec[i, 21] == res[i]["best_tf"] and bit_equal(rec[i, 18:21], pop["grav"][i])
+    # fly them: camera frame (x right, y down, z forward) -> world (x forward, y left, z up), hover point 2 m up
+    s = np.sqrt(0.5)
+    cam_to_world = np.array([0.5, -0.5, 0.5, -0.5])  # body x = camera z, body y = -camera x, body z = -camera y
+    fly = [i for i in range(n) if res[i]["found"]][:6]
+    recs = rec[fly].copy()
+    recs[:, 22:26] = cam_to_world
+    recs[:, 26:29] = (0.0, 0.0, 2.0)
+    sc = agf.scenarios.tracking_scenario(nticks=2600)
+    sc["ref"] = dict(sc["ref"], desired_pos=(0.0, 0.0, 2.0), start_us=3000000)
+    sc["pos"] = (0.0, 0.0, 0.0)
+    b = make_batch_offboard_ref(agf, sc, n=len(fly), primitives=recs)
+    b.run(1300)
+    b.run(1300)
+    got = b.record()
+    b.close()
+    O = orc.Oracle("port-shared")
+    for j in range(len(fly)):
+        v = O.vehicle(cfg_for(agf, sc), uwb_comm_period=0.0)
+        v.set_state(pos=sc["pos"], att=sc["att"])
+        ref = v.run_offboard_ref(2600, agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), trajectory=recs[j])
+        assert bit_equal(got[j], ref[-1]), (j, got[j][0:3], ref[-1][0:3])
+        assert ref[-1, 35] == 0 and np.linalg.norm(ref[-1, 0:3] - np.array([0.0, 0.0, 2.0])) > 0.3  # it went somewhere
