@@ -329,10 +329,11 @@ def test_offboard_estimator_fast_variants(agf, port_glibc):
     assert bit_equal(big, np.tile(big[0], (n, 1)))
 
 
-def test_monte_carlo_population_parity(agf, port_shared):
-    """BASELINE config 2 at a size the oracle finishes in seconds: randomized initial states, per-vehicle
-    hover set-points (command slot), full onboard mode, noise-free, FP64 parity -> bit-identical."""
-    n, nt = 192, 2500
+@pytest.mark.parametrize("n,nt", [(192, 2500), (4096, 5000)])
+def test_monte_carlo_population_parity(agf, port_shared, n, nt):
+    """BASELINE config 2 -- at a small size and at its FULL size (4 096 vehicles, 10 s at 500 Hz; the oracle needs a few
+    seconds on all host cores): randomized initial states, per-vehicle hover set-points (command slot), full onboard
+    mode, noise-free, FP64 parity -> bit-identical for every vehicle."""
     s = agf.scenarios
     sc = s.full_scenario(agf.codec, nticks=nt)
     init = s.monte_carlo_initial_states(n, seed=1234)
