@@ -1357,15 +1357,18 @@ AGF_DEV V3<double> rtg_omega(const double* tr, double t, double timeStep) {
 // Components/Offboard/MocapStateEstimator.cpp, PredictionPipe.hpp).  State [field][N] doubles in HBM, touched on
 // mocap packets (every 2-3 ticks) and at command generation only; everything here is double as in the reference.
 // ---------------------------------------------------------------------------------------------
+// The per-vehicle arrays of the offboard loop are read through L2 (ld.global.cg), like the vehicle state: with the
+// balanced schedule another CTA may have written them earlier in the same launch, and L1 is not coherent.
+AGF_DEV double ldg2(const double* p) { return ldcg_(p); }
 struct EstCore {
   V3<double> pos, vel, w;
   Q4<double> att;
 };
 AGF_DEV void est_load(const double* st, size_t n, EstCore& e) {
-  e.pos = V3<double>(st[(E_POS + 0) * n], st[(E_POS + 1) * n], st[(E_POS + 2) * n]);
-  e.vel = V3<double>(st[(E_VEL + 0) * n], st[(E_VEL + 1) * n], st[(E_VEL + 2) * n]);
-  e.w = V3<double>(st[(E_W + 0) * n], st[(E_W + 1) * n], st[(E_W + 2) * n]);
-  e.att = Q4<double>(st[(E_ATT + 0) * n], st[(E_ATT + 1) * n], st[(E_ATT + 2) * n], st[(E_ATT + 3) * n]);
+  e.pos = V3<double>(ldg2(st + (E_POS + 0) * n), ldg2(st + (E_POS + 1) * n), ldg2(st + (E_POS + 2) * n));
+  e.vel = V3<double>(ldg2(st + (E_VEL + 0) * n), ldg2(st + (E_VEL + 1) * n), ldg2(st + (E_VEL + 2) * n));
+  e.w = V3<double>(ldg2(st + (E_W + 0) * n), ldg2(st + (E_W + 1) * n), ldg2(st + (E_W + 2) * n));
+  e.att = Q4<double>(ldg2(st + (E_ATT + 0) * n), ldg2(st + (E_ATT + 1) * n), ldg2(st + (E_ATT + 2) * n), ldg2(st + (E_ATT + 3) * n));
 }
 AGF_DEV void est_store(double* st, size_t n, const EstCore& e) {
   st[(E_POS + 0) * n] = e.pos.x; st[(E_POS + 1) * n] = e.pos.y; st[(E_POS + 2) * n] = e.pos.z;
@@ -1379,15 +1382,15 @@ struct EstMsg {
 };
 // PredictionPipe::GetActiveMessage (PredictionPipe.hpp:32-53) + the "no messages" default of its callers
 AGF_DEV void est_fetch(const double* st, size_t n, double t, EstMsg& m, double& timeRemaining) {
-  const int cnt = int(st[E_NPIPE * n]);
+  const int cnt = int(ldg2(st + E_NPIPE * n));
   double tLast = 1e10;
   for (int k = cnt - 1; k >= 0; k--) {
     const double* q = st + size_t(E_PIPE + E_MSG * k) * n;
-    const double ta = q[0];
+    const double ta = ldg2(q);
     if ((t + 1e-6) >= ta) {
-      m.acc = V3<double>(q[1 * n], q[2 * n], q[3 * n]);
-      m.w = V3<double>(q[4 * n], q[5 * n], q[6 * n]);
-      m.ballistic = q[7 * n] != 0.0;
+      m.acc = V3<double>(ldg2(q + 1 * n), ldg2(q + 2 * n), ldg2(q + 3 * n));
+      m.w = V3<double>(ldg2(q + 4 * n), ldg2(q + 5 * n), ldg2(q + 6 * n));
+      m.ballistic = ldg2(q + 7 * n) != 0.0;
       timeRemaining = tLast - ta;
       return;
     }
@@ -1416,7 +1419,7 @@ template<bool PARITY>
 AGF_DEV void mocap_predict(const EstParams& ep, size_t i, size_t n, uint64_t now_us, double dt, EstCore& o) {
   const double* st = ep.state + i;
   const double tEnd = dt + double(now_us - ep.t0_us) * 1e-6;
-  const double tStart = double(uint64_t(st[E_TEST * n])) * 1e-6;
+  const double tStart = double(uint64_t(ldg2(st + E_TEST * n))) * 1e-6;
   EstCore m;
   est_load(st, n, m);
   o = m;
@@ -1468,7 +1471,7 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   double* st = ep.state + i;
   EstCore e;
   double vp[4], va[4];
-  if (st[E_INIT * n] == 0.0) {
+  if (ldg2(st + E_INIT * n) == 0.0) {
     e.pos = measPos;
     e.vel = V3<double>(0, 0, 0);
     e.att = measAtt;
@@ -1485,10 +1488,10 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   }
   est_load(st, n, e);
   for (int k = 0; k < 4; k++) {
-    vp[k] = st[(E_VP + k) * n];
-    va[k] = st[(E_VA + k) * n];
+    vp[k] = ldg2(st + (E_VP + k) * n);
+    va[k] = ldg2(st + (E_VA + k) * n);
   }
-  uint64_t est_us = uint64_t(st[E_TEST * n]);
+  uint64_t est_us = uint64_t(ldg2(st + E_TEST * n));
   const double t0 = double(est_us) * 1e-6;
   const double tEnd = double(now_us - ep.t0_us) * 1e-6;
   if (tEnd > t0) {
@@ -1518,7 +1521,7 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   const Q4<double> dq = qmul(qinv(measAtt), e.att);
   const double distA = (Mf<PARITY>::acos(::fabs(dq.w)) * 2.0) / ::sqrt(innovA);  // Rotation::GetAngle
   const bool reject = (distP > ep.reject) || (distA > ep.reject);
-  double nrej = st[E_NREJ * n], nrejc = st[E_NREJC * n];
+  double nrej = ldg2(st + E_NREJ * n), nrejc = ldg2(st + E_NREJC * n);
   if (reject && nrejc < 10.0) {
     nrej += 1.0;
     nrejc += 1.0;
@@ -1578,13 +1581,13 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   st[E_NREJC * n] = nrejc;
   {  // PredictionPipe::ClearExpiredMessages(estimate time) (PredictionPipe.hpp:55-68)
     const double cur = double(est_us) * 1e-6;
-    int cnt = int(st[E_NPIPE * n]);
+    int cnt = int(ldg2(st + E_NPIPE * n));
     const int N = cnt;
     for (int it = 0; it < N; it++) {
       if (cnt < 2) break;
-      if (st[size_t(E_PIPE + E_MSG) * n] <= cur) {  // _messages[1].timeActive
+      if (ldg2(st + size_t(E_PIPE + E_MSG) * n) <= cur) {  // _messages[1].timeActive
         for (int k = 0; k + 1 < cnt; k++)
-          for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = st[size_t(E_PIPE + E_MSG * (k + 1) + f) * n];
+          for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = ldg2(st + size_t(E_PIPE + E_MSG * (k + 1) + f) * n);
         cnt--;
       }
     }
@@ -1594,10 +1597,10 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
 // MocapStateEstimator::SetPredictedValues -> PredictionPipe::AddMessage (hpp:74-80, PredictionPipe.hpp:25-30)
 AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, size_t n, uint64_t now_us, const V3<double>& w, const V3<double>& acc) {
   double* st = ep.state + i;
-  int cnt = int(st[E_NPIPE * n]);
+  int cnt = int(ldg2(st + E_NPIPE * n));
   if (cnt >= AGF_OFFEST_PIPE) {  // cannot happen while measurements arrive; keep the newest messages
     for (int k = 0; k + 1 < cnt; k++)
-      for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = st[size_t(E_PIPE + E_MSG * (k + 1) + f) * n];
+      for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = ldg2(st + size_t(E_PIPE + E_MSG * (k + 1) + f) * n);
     cnt--;
   }
   double* q = st + size_t(E_PIPE + E_MSG * cnt) * n;
@@ -1639,7 +1642,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
   if (c.ref_kind == AGF_OFFREF_TRAJECTORY) {
     if (!(t_gen > c.start_us)) return offboard_command<PARITY, P>(c, cp, cv, ca, des, zero3, zero3, c.desired_yaw, thrustOut, wOut);
     double tr[AGF_OFFTRAJ_DOUBLES];
-    for (int k = 0; k < AGF_OFFTRAJ_DOUBLES; k++) tr[k] = c.traj[size_t(k) * n + i];
+    for (int k = 0; k < AGF_OFFTRAJ_DOUBLES; k++) tr[k] = ldg2(c.traj + size_t(k) * n + i);
     double traj_t = double(t_gen - c.start_us) * 1e-6;
     const double tEnd = tr[21];
     double tp[3], tv[3], ta[3];
@@ -1672,14 +1675,15 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
   // AGF_OFFREF_STAGES: ExampleVehicleStateMachine::Run (ExampleVehicleStateMachine.cpp:93-370)
   double* st = c.state + i;  // field k at st[k * n]
   const bool shouldStart = t_gen >= c.start_us, shouldStop = t_gen >= c.stop_us;
-  int stage = int(st[0]);
-  const bool stageChange = stage != int(st[n]);
+  int stage = int(ldg2(st));
+  const bool stageChange = stage != int(ldg2(st + n));
   st[n] = double(stage);
+  const uint64_t stageStart = stageChange ? t_gen : uint64_t(ldg2(st + 2 * n));
   if (stageChange) st[2 * n] = double(t_gen);
-  const double ts = double(t_gen - uint64_t(st[2 * n])) * 1e-6;  // _stageTimer->GetSeconds<double>()
+  const double ts = double(t_gen - stageStart) * 1e-6;  // _stageTimer->GetSeconds<double>()
   const int stage_in = stage;
   float4 out;
-  double cmdYaw = st[15 * n];
+  double cmdYaw = ldg2(st + 15 * n);
   switch (stage) {
     case AGF_STAGE_WAIT_FOR_START:
       if (shouldStart) stage = AGF_STAGE_SPOOL_UP;
@@ -1701,7 +1705,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
         frac = 1.0;
       }
       double cmdPos[3];
-      for (int a = 0; a < 3; a++) cmdPos[a] = (1 - frac) * st[(3 + a) * n] + frac * des[a];
+      for (int a = 0; a < 3; a++) cmdPos[a] = (1 - frac) * (stageChange ? (a == 0 ? double(cp.x) : (a == 1 ? double(cp.y) : double(cp.z))) : ldg2(st + (3 + a) * n)) + frac * des[a];
       out = offboard_command<PARITY, P>(c, cp, cv, ca, cmdPos, zero3, zero3, cmdYaw, thrustOut, wOut);
     } break;
     case AGF_STAGE_FLIGHT: {
@@ -1771,7 +1775,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
       double lp[3], lv[3], la[3], cmdPos[3], dp[3], dv[3], da[3];
       const double land[3] = {0.0, 0.0, -LANDING_SPEED};
       for (int a = 0; a < 3; a++) {
-        lp[a] = st[(6 + a) * n]; lv[a] = st[(9 + a) * n]; la[a] = st[(12 + a) * n];
+        lp[a] = ldg2(st + (6 + a) * n); lv[a] = ldg2(st + (9 + a) * n); la[a] = ldg2(st + (12 + a) * n);
         cmdPos[a] = lp[a] + ts * land[a];
       }
       if (cmdPos[2] < 0) stage = AGF_STAGE_COMPLETE;

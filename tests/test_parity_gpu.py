@@ -354,7 +354,8 @@ def test_monte_carlo_population_parity(agf, port_shared, n, nt):
     b.set_schedule(sched)
     b.run(nt)
     got = b.record()
-    assert rel_err(got[:, 0:17], ref[:, 0:17]) <= 1e-9
+    fin = np.isfinite(ref[:, 0:17]).all(axis=1)  # a vehicle that diverges does so on the oracle and on the GPU alike (NaN == NaN below)
+    assert fin.mean() > 0.75 and rel_err(got[fin, 0:17], ref[fin, 0:17]) <= 1e-9
     assert bit_equal(got, ref)
     # vehicles hover at their own set-points (a few with |yaw| near 180 deg do not, on the oracle as on the GPU)
     assert np.median(np.abs(got[:, 2] - 1.5)) < 0.02 and np.mean(got[:, 35] == 0) > 0.75
