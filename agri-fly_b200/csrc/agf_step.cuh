@@ -769,7 +769,7 @@ template<typename ST> AGF_DEV void kf_core_put(ST& s, const KfCore& c) {
 // covariance lives in the shared-memory scratch, not in ST)
 template<bool PARITY, bool UWB, typename ST>
 AGF_DEV void kf_reset(ST& s, const Scratch& sc) {  // KalmanFilter6DOF.cpp:33-68
-  s.kfcnt = (s.kfcnt & 0xFFFF0000u) | ((s.kfcnt + 1u) & 0xFFFFu);
+  s.kfcnt = (s.kfcnt & 0xFFFF0000u) | min((s.kfcnt & 0xFFFFu) + 1u, 0xFFFFu);  // saturating, see kf_range_rejected
   s.bits &= ~(B_IMU_INIT | B_UWB_INIT);
   s.bits |= B_KF_RESET_SEEN;
 #pragma unroll
@@ -849,10 +849,14 @@ static AGF_COLD void kf_predict_startup_cold(KfCore* c, Scratch sc, V3<float> gy
 // a rejected range: counters, reset after 5 in a row (:272-284)
 template<bool PARITY, bool UWB, typename ST>
 AGF_DEV void kf_range_rejected(ST& s, const Scratch& sc) {
-  const uint32_t rej = (s.kfcnt >> 16) + 1u;
+  // The reference's counters are unsigned ints and Reset() does not clear the in-a-row count, so a filter that keeps
+  // rejecting resets on EVERY further rejection (a panicked vehicle lying far from its anchors does this for thousands
+  // of ranges).  The packed fields saturate instead of wrapping: the decision `seq >= 5` stays the reference's for any run
+  // length (found by the full-size C2 parity test: a wrap at 256 silently skipped four resets).
+  const uint32_t rej = min((s.kfcnt >> 16) + 1u, 0xFFFFu);
   s.kfcnt = (s.kfcnt & 0xFFFFu) | (rej << 16);
-  const uint32_t seq = (s.cnt & 0xFFu) + 1u;
-  s.cnt = (s.cnt & ~0xFFu) | (seq & 0xFFu);
+  const uint32_t seq = min((s.cnt & 0xFFu) + 1u, 0xFFu);
+  s.cnt = (s.cnt & ~0xFFu) | seq;
   if (seq >= 5u) kf_reset<PARITY, UWB>(s, sc);
 }
 static AGF_COLD void kf_range_rejected_cold(KfCore* c, Scratch sc) { kf_range_rejected<false, true>(*c, sc); }

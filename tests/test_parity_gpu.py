@@ -354,9 +354,13 @@ def test_monte_carlo_population_parity(agf, port_shared, n, nt):
     b.set_schedule(sched)
     b.run(nt)
     got = b.record()
-    fin = np.isfinite(ref[:, 0:17]).all(axis=1)  # a vehicle that diverges does so on the oracle and on the GPU alike (NaN == NaN below)
-    assert fin.mean() > 0.75 and rel_err(got[fin, 0:17], ref[fin, 0:17]) <= 1e-9
-    assert bit_equal(got, ref)
+    # A vehicle whose estimator produces NaN (2 of the 4 096: they fly off by > 100 m) does so at the same tick on the oracle
+    # and on the GPU, plant state identical; from then on only its rejection COUNTERS may differ, because the reference
+    # multiplies NaN covariances by the structural zeros of H and f, which the restatement drops.
+    fin = np.isfinite(ref[:, 0:34]).all(axis=1)
+    assert fin.mean() > 0.99 and rel_err(got[fin, 0:17], ref[fin, 0:17]) <= 1e-9
+    assert bit_equal(got[fin], ref[fin])
+    assert bit_equal(got[~fin][:, 0:34], ref[~fin][:, 0:34])
     # vehicles hover at their own set-points (a few with |yaw| near 180 deg do not, on the oracle as on the GPU)
     assert np.median(np.abs(got[:, 2] - 1.5)) < 0.02 and np.mean(got[:, 35] == 0) > 0.75
     b.close()
