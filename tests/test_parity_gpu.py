@@ -642,6 +642,35 @@ def test_full_size_population_properties(agf):
     b.close()
 
 
+def test_full_size_waypoint_population_spot_check_against_oracle(agf, port_shared):
+    """BASELINE config 3's per-GPU shard at full size and full length (131 072 vehicles, 4-waypoint square, 10 s at 500 Hz) in
+    the parity arithmetic, noise-free: 64 vehicles picked at random are bit-identical to the oracle flying the same
+    initial states and command schedule ("parity spot-check: 64 random vehicles vs oracle in noise-free replay")."""
+    n, nt, k = 131072, 5000, 64
+    s = agf.scenarios
+    sc = s.full_scenario(agf.codec, nticks=nt)
+    cfg = cfg_for(agf, sc)
+    init = s.monte_carlo_initial_states(n, seed=1234, yaw_max=np.pi / 3)
+    sched = s.waypoint_square_schedule(agf.codec, nticks=nt)
+    b = agf.Batch(cfg, n, uwb_comm_period=sc["uwb_comm_period"])
+    for i, p in sc["anchors"]:
+        b.add_anchor(i, p)
+    b.set_state13(init)
+    b.set_schedule(sched)
+    b.run(2500)
+    b.run(2500)
+    got = b.record()
+    b.close()
+    pick = np.sort(np.random.default_rng(11).choice(n, k, replace=False))
+    anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
+    ref, _ = port_shared.run_population(cfg, k, init13=init[pick], anchors=anchors, nticks=nt, sched=sched,
+                                        threads=os.cpu_count() or 1, uwb_comm_period=sc["uwb_comm_period"])
+    assert bit_equal(got[pick], ref)
+    assert np.all(got[:, 35] == 0) and np.all(np.isfinite(got))
+    err = np.linalg.norm(got[:, 0:3] - np.array([1.0, -1.0, 1.5]), axis=1)  # fourth waypoint of the square
+    assert np.median(err) < 0.3
+
+
 def test_trajectory_log_ring(agf):
     n = 300
     b = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST)
