@@ -57,6 +57,37 @@ def csv_row(t, pos, vel, att, ang_vel, motor_forces, est_pos, est_vel, est_att, 
     return buf.value.decode(), r
 
 
+def sweep_cfgs(base, n, seed=5):
+    """BASELINE config 4's parameter sweep as an [n][sizeof(agf_vehicle_cfg)] byte array for Batch(): mass x U(0.8, 1.2),
+    I_xx = I_yy and I_zz x U(0.7, 1.3), kF x U(0.9, 1.1), k_tau x U(0.8, 1.2), motor time constant U(0, 0.05) s
+    (SURVEY.md 8d).  cfg_at(arr, i) gives vehicle i's configuration back as a struct."""
+    V = abi.VehicleCfg
+    raw = np.tile(np.frombuffer(bytes(base), np.uint8), (n, 1))
+    rng = np.random.default_rng(seed)
+
+    def col(field, k=0):
+        off = getattr(V, field).offset + 8 * k
+        return raw[:, off:off + 8].view(np.float64)[:, 0]
+
+    def put(field, values, k=0):
+        off = getattr(V, field).offset + 8 * k
+        raw[:, off:off + 8] = np.ascontiguousarray(values, dtype=np.float64).view(np.uint8).reshape(n, 8)
+
+    put("mass", col("mass") * rng.uniform(0.8, 1.2, n))
+    ixx = col("inertia", 0) * rng.uniform(0.7, 1.3, n)
+    put("inertia", ixx, 0)
+    put("inertia", ixx, 4)
+    put("inertia", col("inertia", 8) * rng.uniform(0.7, 1.3, n), 8)
+    put("prop_thrust_from_speed_sqr", col("prop_thrust_from_speed_sqr") * rng.uniform(0.9, 1.1, n))
+    put("prop_torque_from_speed_sqr", col("prop_torque_from_speed_sqr") * rng.uniform(0.8, 1.2, n))
+    put("motor_time_const", rng.uniform(0.0, 0.05, n))
+    return raw
+
+
+def cfg_at(arr, i):
+    return abi.VehicleCfg.from_buffer_copy(arr[i].tobytes())
+
+
 def offboard_estimator(**edits):
     """agf_offboard_estimator_default() (MocapStateEstimator as Rappids_Simulator sets it up) with field edits."""
     e = abi.OffboardEstimator()
@@ -207,6 +238,9 @@ class Batch:
         o.telemetry_warnings = 1 if telemetry_warnings else 0
         if isinstance(cfgs, abi.VehicleCfg):
             arr, ncfg = (abi.VehicleCfg * 1)(cfgs), 1
+        elif isinstance(cfgs, np.ndarray):  # [n][sizeof(agf_vehicle_cfg)] bytes: big sweeps built with numpy (sweep_cfgs())
+            assert cfgs.dtype == np.uint8 and cfgs.ndim == 2 and cfgs.shape[1] == C.sizeof(abi.VehicleCfg) and cfgs.flags.c_contiguous
+            arr, ncfg = cfgs.ctypes.data_as(C.POINTER(abi.VehicleCfg)), cfgs.shape[0]
         else:
             arr, ncfg = (abi.VehicleCfg * len(cfgs))(*cfgs), len(cfgs)
         h = C.c_void_p()
