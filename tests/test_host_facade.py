@@ -64,3 +64,48 @@ def test_object_api_loop_matches_oracle(agf, port_shared):
     for row in rows:
         k = int(row[0])
         assert bit_equal(row[1:18], ref[k, 0:17]), (k, row[1:18] - ref[k, 0:17])
+
+
+FLEET = os.path.join(ROOT, "examples", "rappids_fleet.cpp")
+FLEET_BIN = os.path.join(ROOT, "examples", "rappids_fleet")
+
+
+def build_fleet():
+    lib_dir = os.path.join(ROOT, "agri-fly_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", INC[0], FLEET, "-L" + lib_dir, "-lagrifly_b200",
+                        "-Wl,-rpath," + lib_dir, "-o", FLEET_BIN], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return FLEET_BIN
+
+
+def test_fleet_example_compiles_against_the_c_abi_only(agf):
+    build_fleet()
+    assert os.path.exists(FLEET_BIN)
+
+
+@pytest.mark.gpu
+def test_fleet_example_writes_the_reference_csv(agf, orc_mod):
+    """examples/rappids_fleet.cpp: a fleet flying the ROS node's flight stages with the mocap estimator, the whole offboard
+    loop inside the kernel, vehicle 0 written as Rappids_Simulator's simulation.csv.  The rows equal what the oracle
+    (reference controller + estimator in the same loop) gives for the same scenario, to the 6 digits the file carries."""
+    from common import cfg_for
+    build_fleet()
+    r = subprocess.run([FLEET_BIN, "513", "6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] + "\n" == agf.csv_header() and len(lines) == 601
+    rows = np.array([[float(x) for x in ln.rstrip(",").split(",")] for ln in lines[1:]])
+    assert rows.shape == (600, 40)
+    if not orc_mod.available("port-shared"):
+        pytest.skip("oracle port not built")
+    O = orc_mod.Oracle("port-shared")
+    sc = agf.scenarios.stages_scenario(3, nticks=3000)
+    v = O.vehicle(cfg_for(agf, sc), uwb_comm_period=0.0)
+    v.set_offboard_estimator(agf.offboard_estimator())
+    ref = agf.offboard_ref(kind=1, start_us=500000, stop_us=3000000, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=3)
+    tr = v.run_offboard_ref(3000, agf.offboard_cfg(sc["quad_type"]), ref)
+    want = tr[4::5]  # state after ticks 5, 10, ...
+    np.testing.assert_allclose(rows[:, 1:7], want[:, 0:6], rtol=2e-5, atol=1e-9)     # position, velocity: 6 significant digits
+    np.testing.assert_allclose(rows[:, 10:13], want[:, 10:13], rtol=2e-5, atol=1e-9)  # angular velocity
+    assert rows[:, 3].max() > 0.9 and rows[-1, 3] < 0.05 and np.all(rows[:, 35] == 0)   # took off, landed, no panic
+    assert np.max(np.abs(rows[:, 17:20] - rows[:, 1:4])) < 0.05                          # estimate follows the truth
