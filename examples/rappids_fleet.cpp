@@ -6,7 +6,7 @@
 // every 10 ms and writes the reference's simulation.csv (main.cpp:266-270,676-733) to stdout.
 //
 //   g++ -std=c++14 -Iinclude examples/rappids_fleet.cpp -Lagri-fly_b200 -lagrifly_b200 -o rappids_fleet
-//   ./rappids_fleet [vehicles] [seconds] > simulation.csv
+//   ./rappids_fleet [vehicles] [seconds] [imu noise 1|0] > simulation.csv
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,7 +27,8 @@ int main(int argc, char** argv) {
   check(agf_vehicle_cfg_from_type(agf_quad_type_from_id(1), 1, &cfg), "agf_vehicle_cfg_from_type");  // main.cpp:147-150
   cfg.motor_time_const = 0.015;
   agf_batch_opts o;
-  agf_batch_opts_default(&o);
+  agf_batch_opts_default(&o);  // the reference's IMU noise (Quadcopter_T.cpp:5-6) is on by default
+  if (argc > 3 && atoi(argv[3]) == 0) o.sigma_acc = o.sigma_gyro = 0.0;
   agf_batch* b = nullptr;
   check(agf_batch_create(&cfg, 1, n, &o, &b), "agf_batch_create");
 
