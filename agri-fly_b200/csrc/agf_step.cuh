@@ -2319,9 +2319,15 @@ AGF_DEV void plant_params_load(PlantPVDiag<P>& pv, const StepLaunch<P>& L, size_
 #ifndef AGF_MINB_F64_RATES
 #define AGF_MINB_F64_RATES 3
 #endif
-template<typename P, bool PARITY, bool UWB>
+// the kernels with the offboard loop compiled in keep more state live across its out-of-line calls: one block per SM fewer
+#ifndef AGF_OFFB_MINB_DELTA
+#define AGF_OFFB_MINB_DELTA 1
+#endif
+template<typename P, bool PARITY, bool UWB, bool OFFB = false>
 constexpr int step_min_blocks() {
-  return PARITY ? 1 : (sizeof(P) == 4 ? (UWB ? AGF_MINB_F32_UWB : AGF_MINB_F32_RATES) : (UWB ? AGF_MINB_F64_UWB : AGF_MINB_F64_RATES));
+  return PARITY ? 1
+                : (sizeof(P) == 4 ? (UWB ? AGF_MINB_F32_UWB : AGF_MINB_F32_RATES) : (UWB ? AGF_MINB_F64_UWB : AGF_MINB_F64_RATES)) -
+                      ((OFFB && !(sizeof(P) == 8 && UWB)) ? AGF_OFFB_MINB_DELTA : 0);
 }
 template<bool PARITY, bool UWB>
 constexpr size_t step_smem_bytes(int block, bool offboard) {
@@ -2419,7 +2425,7 @@ AGF_DEV void flag_wait(const uint32_t* flag, uint32_t epoch) {
 #ifdef AGF_MAXNREG
 #define AGF_STEP_BOUNDS __maxnreg__(AGF_MAXNREG)
 #else
-#define AGF_STEP_BOUNDS __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB>())
+#define AGF_STEP_BOUNDS __launch_bounds__(AGF_BLOCK_THREADS, step_min_blocks<P, PARITY, UWB, OFFB>())
 #endif
 template<typename P, bool PARITY, bool UWB, bool HK, bool PV, bool OFFB>
 __global__ void AGF_STEP_BOUNDS

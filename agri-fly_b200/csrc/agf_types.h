@@ -150,6 +150,18 @@ struct Timing {
   uint64_t now_us;              // simulation clock (ManualTimer::GetMicroSeconds)
 };
 
+// off_wait[] by a run-time slot without dynamic register-array indexing (which would put the whole struct in local memory)
+AGF_HDI uint32_t off_wait_get(const Timing& ts, uint32_t slot) {
+  uint32_t v = ts.off_wait[0];
+#pragma unroll
+  for (uint32_t q = 1; q < AGF_OFFQ; q++) v = (slot == q) ? ts.off_wait[q] : v;
+  return v;
+}
+AGF_HDI void off_wait_set(Timing& ts, uint32_t slot, uint32_t value) {
+#pragma unroll
+  for (uint32_t q = 0; q < AGF_OFFQ; q++) ts.off_wait[q] = (slot == q) ? value : ts.off_wait[q];
+}
+
 struct TickPlan {
   uint32_t plant_dt_us, kf_dt_us;
   bool run_plant, run_logic, run_net, net_start, net_complete, net_reset, has_target;
@@ -179,7 +191,7 @@ AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc, uint32_t 
     }
   }
   // offboard loop.  Delivery (main.cpp:737-739 of the previous iteration): the oldest queued command, once due.
-  p.off_deliver = tc.off_enabled && ts.off_count > 0 && ts.off_wait[ts.off_head % AGF_OFFQ] == 0;
+  p.off_deliver = tc.off_enabled && ts.off_count > 0 && off_wait_get(ts, ts.off_head % AGF_OFFQ) == 0;
   p.off_deliver_slot = ts.off_head % AGF_OFFQ;
   // Generation (main.cpp:471): after Run() and the clock advance, when the stopwatch exceeds the period
   p.off_generate = tc.off_enabled && (ts.off_age + dt_us >= tc.off_min_age_us) && (ts.now_us + dt_us >= tc.off_first_target_us);
@@ -218,7 +230,7 @@ AGF_HDI void timing_advance(Timing& ts, const TimingConsts& tc, const TickPlan& 
     if (ts.off_age >= tc.off_min_age_us) {  // stopwatch restarts whether or not a target applies yet (main.cpp:476)
       ts.off_age -= tc.off_adj_us;
       if (p.off_generate) {
-        ts.off_wait[p.off_gen_slot] = tc.off_delay_us;
+        off_wait_set(ts, p.off_gen_slot, tc.off_delay_us);
         ts.off_count++;
       }
     }
