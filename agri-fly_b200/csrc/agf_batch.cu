@@ -387,6 +387,9 @@ struct BatchImpl : Batch {
   agf_offboard_target* d_off_targets = nullptr;
   double* d_off_offsets = nullptr;
   uint64_t first_target_us = 0;
+  std::vector<PackedPlan> h_plans;
+  PackedPlan* d_plans = nullptr;
+  uint32_t plans_cap = 0;
   double* d_off_est = nullptr;  // [E_FIELDS][n] estimator state
   double* d_off_state = nullptr;  // [AGF_OFFSTATE_DOUBLES][n]
   double* d_off_traj = nullptr;   // [AGF_OFFTRAJ_DOUBLES][n]
@@ -404,7 +407,7 @@ struct BatchImpl : Batch {
     cudaSetDevice(opts.device);
     cudaFree(st.sp); cudaFree(st.sf); cudaFree(st.su); cudaFree(st.sc);
     cudaFree(d_pv); cudaFree(d_ext_force); cudaFree(d_ext_torque); cudaFree(d_tel_counter); cudaFree(d_flags);
-    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(d_off_state); cudaFree(d_off_traj); cudaFree(d_off_est); cudaFree(st.sq);
+    cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(d_off_state); cudaFree(d_off_traj); cudaFree(d_off_est); cudaFree(d_plans); cudaFree(st.sq);
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
     for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -553,7 +556,27 @@ struct BatchImpl : Batch {
     L.nticks = nticks;
     L.dt_us = dt_us;
     ts.now_us = now_us;
-    L.ts = ts;
+    // the launch's tick plans: the clock-only stopwatches evolved here, once, with the function the whole design shares
+    {
+      h_plans.resize(nticks);
+      Timing tt = ts;
+      for (uint32_t t = 0; t < nticks; t++) {
+        const TickPlan p = timing_plan(tt, sh.tc, dt_us);
+        h_plans[t] = pack_plan(p);
+        timing_advance(tt, sh.tc, p, dt_us);
+      }
+      if (nticks > plans_cap) {
+        cudaFree(d_plans);
+        d_plans = nullptr;
+        plans_cap = 0;
+        AGF_CUDA(cudaMalloc(&d_plans, size_t(nticks) * sizeof(PackedPlan)));
+        plans_cap = nticks;
+      }
+      // pageable source: the runtime stages it before returning, so h_plans may be reused by the next launch
+      AGF_CUDA(cudaMemcpyAsync(d_plans, h_plans.data(), size_t(nticks) * sizeof(PackedPlan), cudaMemcpyHostToDevice, stream));
+      L.plans = reinterpret_cast<const uint4*>(d_plans);
+      L.now0_us = now_us;
+    }
     L.sched = d_sched;
     // entries of this launch: [begin, end) with tick in [ticks, ticks + nticks)
     auto lo = std::lower_bound(sched.begin(), sched.end(), ticks, [](const SchedEntryDev& e, uint64_t t) { return e.tick < t; });

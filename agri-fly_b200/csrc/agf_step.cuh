@@ -533,6 +533,13 @@ AGF_DEV float lpf2_scratch(const Lpf2Coef& c, const Scratch& sc, int quad, float
 
 // State is read once per work item and may have been written by another CTA of the same launch (balanced
 // schedule below): load through L2 only (ld.global.cg), never from a possibly stale L1 line.
+template<typename T> AGF_DEV T ldro_(const T* p) {  // read-only for the whole launch: L1-cached, one line serves every warp of the SM
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 template<typename T> AGF_DEV T ldcg_(const T* p) {
 #if defined(__CUDA_ARCH__)
   return __ldcg(p);
@@ -2068,9 +2075,8 @@ template<typename P> AGF_DEV V3<P> inertia_inv_mul(const PlantPVDiag<P>& pv, con
 // template axis because its call sites cost the hot loop registers even when never taken (spills in every fast
 // variant, round 1: FP32 full mode 1.77e10 -> 1.26e10 vehicle-steps/s with the sites merely present).
 template<typename P, bool PARITY, bool UWB, bool HK, bool OFFB, typename PVT>
-AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PVT& pv, Timing& ts,
-                  uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
-  const TickPlan plan = timing_plan(ts, p.tc, dt_us);
+AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepShared<P>& p, const PVT& pv, const TickPlan& plan,
+                  uint64_t now_us, uint32_t dt_us, uint64_t abs_tick, uint64_t gidx, size_t i, size_t n) {
   if (OFFB && plan.off_deliver) {  // CommunicationsDelay::GetMessage -> SetCommandRadioMsg (main.cpp:737-739)
     float4 c;
     if constexpr (PARITY) {
@@ -2232,14 +2238,14 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     const V3<P> mp(s.pos[0], s.pos[1], s.pos[2]);
     const Q4<P> ma(s.att[0], s.att[1], s.att[2], s.att[3]);
     if constexpr (PARITY) {
-      mocap_update<true>(p.off.est, i, n, ts.now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
+      mocap_update<true>(p.off.est, i, n, now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
                          Q4<double>(double(ma.w), double(ma.x), double(ma.y), double(ma.z)));
     } else {
-      mocap_update_cold<P>(&p.off.est, i, n, ts.now_us + dt_us, mp, ma);
+      mocap_update_cold<P>(&p.off.est, i, n, now_us + dt_us, mp, ma);
     }
   }
   if (OFFB && plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance
-    const uint64_t t_gen = ts.now_us + dt_us;
+    const uint64_t t_gen = now_us + dt_us;
     const V3<P> cp(s.pos[0], s.pos[1], s.pos[2]), cv(s.vel[0], s.vel[1], s.vel[2]);
     const Q4<P> ca(s.att[0], s.att[1], s.att[2], s.att[3]);
     if constexpr (PARITY) {
@@ -2251,7 +2257,6 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       sq_store(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_gen_slot), c);
     }
   }
-  timing_advance(ts, p.tc, plan, dt_us);
   s.age_radio = sat_add(s.age_radio, dt_us);
   s.age_uwb = sat_add(s.age_uwb, dt_us);
   if (HK) {
@@ -2339,12 +2344,10 @@ template<typename P, bool PARITY, bool UWB, bool HK, bool OFFB, typename PVT>
 AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc, size_t i, uint32_t t0, uint32_t t1) {
   VState<P, PARITY, UWB, HK> s;
   state_load(s, L.st, L.n, i, sc);
-  // clock-only stopwatches at tick t0: the same integer recurrence for every vehicle
-  Timing ts = L.ts;
-  for (uint32_t t = 0; t < t0; t++) {
-    const TickPlan pl = timing_plan(ts, L.sh.tc, L.dt_us);
-    timing_advance(ts, L.sh.tc, pl, L.dt_us);
-  }
+  // what each tick does (plant step, logic, ranging, offboard loop) depends on the clock only: the host evaluated the
+  // stopwatch recurrence (agf_types.h timing_plan / timing_advance) for every tick of the launch; one 16-byte word per tick,
+  // the same address for the whole grid, the next one requested a tick ahead
+  uint4 pp = ldro_(L.plans + t0);
   // next scheduled radio delivery, as a tick offset into this launch (0xFFFFFFFF: none left)
   uint32_t si = L.sched_begin;
   while (si < L.sched_end && L.sched[si].tick < L.tick0 + t0) si++;
@@ -2369,7 +2372,9 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
       si++;
       next_cmd = si < L.sched_end ? uint32_t(L.sched[si].tick - L.tick0) : 0xFFFFFFFFu;
     }
-    tick<P, PARITY, UWB, HK, OFFB>(s, sc, L.sh, pv, ts, L.dt_us, abs_tick, gidx, i, L.n);
+    const TickPlan plan = unpack_plan(pp.x, pp.y, pp.z);
+    if (t + 1 < t1) pp = ldro_(L.plans + t + 1);
+    tick<P, PARITY, UWB, HK, OFFB>(s, sc, L.sh, pv, plan, L.now0_us + uint64_t(t) * L.dt_us, L.dt_us, abs_tick, gidx, i, L.n);
     if (L.log && --log_in == 0) {
       log_in = L.log_stride;
       const uint64_t rec = (abs_tick + 1) / L.log_stride - 1;

@@ -237,6 +237,42 @@ AGF_HDI void timing_advance(Timing& ts, const TimingConsts& tc, const TickPlan& 
   }
 }
 
+// A launch's tick plans, evaluated ONCE on the host (they depend on the clock only) and read by the kernel as one
+// 16-byte word per tick instead of evolving the stopwatch recurrence in every thread: that state cost the hot loop
+// ~10 registers and, in the kernels with the offboard loop, was spilled and re-read every tick (ncu, round 1: 30 % of
+// the stall samples of the offboard kernels were local-memory loads of it).
+enum { PP_RUN_PLANT = 1u, PP_RUN_LOGIC = 2u, PP_NET_START = 4u, PP_NET_COMPLETE = 8u, PP_OFF_DELIVER = 16u, PP_OFF_GENERATE = 32u,
+       PP_MOCAP = 64u, PP_DSLOT_SHIFT = 8, PP_GSLOT_SHIFT = 12 };
+struct PackedPlan {
+  uint32_t flags, plant_dt_us, kf_dt_us, pad;
+};
+inline PackedPlan pack_plan(const TickPlan& p) {
+  PackedPlan q;
+  q.flags = (p.run_plant ? PP_RUN_PLANT : 0u) | (p.run_logic ? PP_RUN_LOGIC : 0u) | (p.net_start ? PP_NET_START : 0u) |
+            (p.net_complete ? PP_NET_COMPLETE : 0u) | (p.off_deliver ? PP_OFF_DELIVER : 0u) | (p.off_generate ? PP_OFF_GENERATE : 0u) |
+            (p.mocap_update ? PP_MOCAP : 0u) | (p.off_deliver_slot << PP_DSLOT_SHIFT) | (p.off_gen_slot << PP_GSLOT_SHIFT);
+  q.plant_dt_us = p.plant_dt_us;
+  q.kf_dt_us = p.kf_dt_us;
+  q.pad = 0;
+  return q;
+}
+AGF_HDI TickPlan unpack_plan(uint32_t flags, uint32_t plant_dt_us, uint32_t kf_dt_us) {
+  TickPlan p;
+  p.plant_dt_us = plant_dt_us;
+  p.kf_dt_us = kf_dt_us;
+  p.run_plant = (flags & PP_RUN_PLANT) != 0;
+  p.run_logic = (flags & PP_RUN_LOGIC) != 0;
+  p.net_start = (flags & PP_NET_START) != 0;
+  p.net_complete = (flags & PP_NET_COMPLETE) != 0;
+  p.off_deliver = (flags & PP_OFF_DELIVER) != 0;
+  p.off_generate = (flags & PP_OFF_GENERATE) != 0;
+  p.mocap_update = (flags & PP_MOCAP) != 0;
+  p.off_deliver_slot = (flags >> PP_DSLOT_SHIFT) & 0xFu;
+  p.off_gen_slot = (flags >> PP_GSLOT_SHIFT) & 0xFu;
+  p.run_net = p.net_reset = p.has_target = false;  // host-side bookkeeping only
+  return p;
+}
+
 struct AnchorDev {
   float x, y, z;
   uint32_t id;
@@ -339,7 +375,8 @@ struct StepLaunch {
   size_t n;
   uint64_t tick0;
   uint32_t nticks, dt_us;
-  Timing ts;
+  const uint4* plans;  // [nticks] PackedPlan of every tick of this launch
+  uint64_t now0_us;    // simulation clock at the first tick
   const SchedEntryDev* sched;
   uint32_t sched_begin, sched_end;
   SlotArrays slots[AGF_MAX_CMD_SLOTS];

@@ -74,7 +74,11 @@ static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_
       radio_deliver(s, v->sh.logic, type, flags, f);
       si++;
     }
-    tick<double, true, UWB, true, true>(s, sc, v->sh, v->pv, v->ts, dt_us, v->tick, 0, 0, 1);
+    {
+      const TickPlan plan = timing_plan(v->ts, v->sh.tc, dt_us);
+      tick<double, true, UWB, true, true>(s, sc, v->sh, v->pv, plan, v->ts.now_us, dt_us, v->tick, 0, 0, 1);
+      timing_advance(v->ts, v->sh.tc, plan, dt_us);
+    }
     if (traj) {
       double* r = traj + size_t(k) * ORC_NTRAJ;
       for (int c = 0; c < 3; c++) { r[c] = s.pos[c]; r[3 + c] = s.vel[c]; r[10 + c] = s.w[c]; r[21 + c] = s.kpos[c]; r[24 + c] = s.kvel[c]; r[31 + c] = s.kw[c]; }
