@@ -2319,12 +2319,13 @@ AGF_DEV void plant_params_load(PlantPVDiag<P>& pv, const StepLaunch<P>& L, size_
 #define AGF_MINB_F32_RATES 4
 #endif
 #ifndef AGF_MINB_F64_UWB
-#define AGF_MINB_F64_UWB 2
+#define AGF_MINB_F64_UWB 3
 #endif
 #ifndef AGF_MINB_F64_RATES
-#define AGF_MINB_F64_RATES 3
+#define AGF_MINB_F64_RATES 4
 #endif
-// the kernels with the offboard loop compiled in keep more state live across its out-of-line calls: one block per SM fewer
+// blocks per SM fewer for the kernels with the offboard loop compiled in (measured after the tick-plan table: truth-fed loop
+// 2.13e10 with one fewer vs 1.85e10 with the same number; with the mocap estimator 7.7e9 vs 8.0e9 -- profiles/r1/)
 #ifndef AGF_OFFB_MINB_DELTA
 #define AGF_OFFB_MINB_DELTA 1
 #endif
@@ -2332,7 +2333,7 @@ template<typename P, bool PARITY, bool UWB, bool OFFB = false>
 constexpr int step_min_blocks() {
   return PARITY ? 1
                 : (sizeof(P) == 4 ? (UWB ? AGF_MINB_F32_UWB : AGF_MINB_F32_RATES) : (UWB ? AGF_MINB_F64_UWB : AGF_MINB_F64_RATES)) -
-                      ((OFFB && !(sizeof(P) == 8 && UWB)) ? AGF_OFFB_MINB_DELTA : 0);
+                      (OFFB ? AGF_OFFB_MINB_DELTA : 0);
 }
 template<bool PARITY, bool UWB>
 constexpr size_t step_smem_bytes(int block, bool offboard) {
