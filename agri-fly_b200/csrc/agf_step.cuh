@@ -2473,7 +2473,7 @@ step_kernel(const __grid_constant__ StepLaunch<P> L) {
 // lower-indexed neighbour does first, so the wait cannot deadlock even if the wave is not fully resident.)
 template<typename P, typename K>
 static cudaError_t launch_step_kernel(K kernel, StepLaunch<P> L, int block, size_t smem, cudaStream_t stream) {
-  struct Cached { const void* fn; int block; size_t smem; int dev; int resident; };
+  struct Cached { const void* fn; int block; size_t smem; int dev; int resident; int sms; };
   static Cached cache[16];
   static int ncached = 0;
   L.nblocks = uint32_t((L.n + block - 1) / block);
@@ -2483,20 +2483,28 @@ static cudaError_t launch_step_kernel(K kernel, StepLaunch<P> L, int block, size
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int resident = -1;
+    int resident = -1, sms = 0;
     for (int k = 0; k < ncached; k++)
-      if (cache[k].fn == (const void*)kernel && cache[k].block == block && cache[k].smem == smem && cache[k].dev == dev) resident = cache[k].resident;
+      if (cache[k].fn == (const void*)kernel && cache[k].block == block && cache[k].smem == smem && cache[k].dev == dev) {
+        resident = cache[k].resident;
+        sms = cache[k].sms;
+      }
     if (resident < 0) {
-      int sms = 0, per_sm = 0;
+      int per_sm = 0;
       e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
       if (e != cudaSuccess) return e;
       resident = sms * per_sm;
-      if (ncached < 16) cache[ncached++] = Cached{(const void*)kernel, block, smem, dev, resident};
+      if (ncached < 16) cache[ncached++] = Cached{(const void*)kernel, block, smem, dev, resident, sms};
     }
     if (resident > 0 && L.nblocks > unsigned(resident)) {
       L.balanced = 1;
       grid = unsigned(resident);
+    } else if (sms > 0 && L.nblocks > unsigned(sms) && L.nblocks % unsigned(sms) != 0) {
+      // fewer blocks than fit, but not a multiple of the SM count: the same number of CTAs on every SM, the block-ticks
+      // dealt out evenly, instead of some SMs carrying one block more than the others for the whole launch
+      L.balanced = 1;
+      grid = (L.nblocks / unsigned(sms)) * unsigned(sms);
     }
   }
   kernel<<<grid, block, smem, stream>>>(L);
