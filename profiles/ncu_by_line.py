@@ -19,7 +19,7 @@ def function_spans(src_path):
     lines = open(src_path).read().split("\n")
     owner = [None] * (len(lines) + 2)
     cur, depth, pending = None, 0, None
-    sig = re.compile(r"^\s*(?:static\s+)?(?:AGF_DEV|AGFR_DEV|AGF_COLD|static AGF_COLD|__global__|__device__(?:\s+__noinline__)?|AGF_HDI|static AGF_DEV|static __device__ __noinline__)[^;(]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(")
+    sig = re.compile(r"^\s*(?:static\s+)?(?:template<[^>]*>\s*)?(?:AGF_DEV|AGFR_DEV|AGF_COLD|static AGF_COLD|__global__|__device__(?:\s+__noinline__)?|AGF_HDI|static AGF_DEV|static __device__ __noinline__)[^;(]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(")
     for i, ln in enumerate(lines, 1):
         if depth == 0:
             m = sig.match(ln)
@@ -95,12 +95,15 @@ def main():
                 per_line_stall[key][h] += int(r[i])
     print("kernel %s: %d warp-instructions executed, %d stall samples" % (kern, tot_ex, tot_smp))
     # per function
-    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "agri-fly_b200", "csrc", "agf_step.cuh")
-    owner, _ = function_spans(src)
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "agri-fly_b200", "csrc")
+    owners = {}
+    for name in ("agf_step.cuh", "agf_rappids_plan.cuh", "agf_types.h", "agf_math.h"):
+        owners[name] = function_spans(os.path.join(csrc, name))[0]
     per_fn = defaultdict(lambda: [0, 0])
     per_fn_stall = defaultdict(lambda: defaultdict(int))
     for (f, l), (ex, smp) in per_line.items():
-        fn = owner[l] if f == "agf_step.cuh" and l < len(owner) and owner[l] else f + ":other"
+        owner = owners.get(f)
+        fn = owner[l] if owner is not None and l < len(owner) and owner[l] else f + ":other"
         per_fn[fn][0] += ex
         per_fn[fn][1] += smp
         for h, v in per_line_stall[(f, l)].items():
