@@ -301,11 +301,9 @@ class Batch:
         _check(self.L.agf_batch_set_field(self.h, fid, v.ctypes.data, first, len(v)))
 
     def set_state13(self, s13, first=0):
-        s13 = np.asarray(s13, dtype=np.float64).reshape(-1, 13)
-        self.set("position", s13[:, 0:3], first)
-        self.set("velocity", s13[:, 3:6], first)
-        self.set("attitude", s13[:, 6:10], first)
-        self.set("angular_velocity", s13[:, 10:13], first)
+        """position 3, velocity 3, attitude 4, angular velocity 3 per vehicle: one call, one copy (agf_batch_set_state)"""
+        s13 = np.ascontiguousarray(s13, dtype=np.float64).reshape(-1, 13)
+        _check(self.L.agf_batch_set_state(self.h, s13.ctypes.data, first, len(s13)))
 
     def record(self):
         """[n][40] in the oracle's trajectory-record column order (oracle/oracle_api.h)."""

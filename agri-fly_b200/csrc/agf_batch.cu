@@ -134,6 +134,18 @@ __global__ void field_set_kernel(FieldCtx<P> c, int field, int ncomp, size_t fir
   }
 }
 
+// the whole 6-DOF state of a vehicle range in one pass: in = [count][13] doubles, position 3, velocity 3, attitude 4, angular velocity 3
+template<typename P>
+__global__ void state13_set_kernel(FieldCtx<P> c, size_t first, size_t count, const double* __restrict__ in) {
+  constexpr int VP = VecOf<P>::lanes;
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count * 13) return;
+  const size_t i = first + t / 13;
+  const int comp = int(t % 13);
+  const int slot = comp < 3 ? SP_POS + comp : (comp < 6 ? SP_VEL + comp - 3 : (comp < 10 ? SP_ATT + comp - 6 : SP_W + comp - 10));
+  c.sp[sidx(slot, c.n, i, VP)] = P(in[t]);
+}
+
 // SetCommandRadioMsg now (QuadcopterLogic.hpp:110-116), outside the step kernel
 struct RadioNow {
   uint32_t type, flags;
@@ -305,6 +317,7 @@ struct Batch {
   virtual int advance_clock(uint32_t dt_us) = 0;
   virtual int get_field(int field, void* dst, size_t first, size_t count) = 0;
   virtual int set_field(int field, const void* src, size_t first, size_t count) = 0;
+  virtual int set_state13(const double* src, size_t first, size_t count) = 0;
   virtual int set_radio(const uint8_t* raw, size_t first, size_t count, int broadcast) = 0;
   virtual int set_schedule(const agf_cmd_entry* e, size_t n) = 0;
   virtual int set_slot(int slot, const uint8_t* raw) = 0;
@@ -931,6 +944,23 @@ struct BatchImpl : Batch {
     return AGF_OK;
   }
 
+  int set_state13(const double* src, size_t first, size_t count) override {
+    if (!src) return fail(AGF_EINVAL, "null state array");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    const size_t bytes = count * 13 * sizeof(double);
+    int rc = ensure_stage(bytes);
+    if (rc) return rc;
+    AGF_CUDA(cudaMemcpyAsync(d_stage, src, bytes, cudaMemcpyHostToDevice, stream));
+    const size_t total = count * 13;
+    state13_set_kernel<P><<<unsigned((total + 255) / 256), 256, 0, stream>>>(ctx(), first, count, reinterpret_cast<const double*>(d_stage));
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its buffer
+    return AGF_OK;
+  }
+
   // ---- radio -----------------------------------------------------------------------------------
   static RadioNow decode_now(const uint8_t* raw) {
     RadioNow m;
@@ -1296,6 +1326,9 @@ int agf_batch_set_offboard_estimator(agf_batch* b, const agf_offboard_estimator*
 }
 int agf_batch_get_offboard_estimate(agf_batch* b, double horizon, double* est13, double* counters4, size_t first, size_t count) {
   return b ? B(b)->get_offboard_estimate(horizon, est13, counters4, first, count) : fail(AGF_EINVAL, "null handle");
+}
+int agf_batch_set_state(agf_batch* b, const double* state13, size_t first, size_t count) {
+  return b ? B(b)->set_state13(state13, first, count) : fail(AGF_EINVAL, "null handle");
 }
 int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref) {
   return b ? B(b)->set_offboard_ref(ref) : fail(AGF_EINVAL, "null handle");

@@ -16,7 +16,7 @@ N > 1).  Vehicles shard by contiguous index range; there is no communication ins
 value   = vehicle-steps/s over all GPUs, state resident in HBM, timed with CUDA events on the launching stream,
           max over ranks.
 e2e     = same metric through the public C ABI with HOST buffers: every step copies the population's 6-DOF
-          state in from pinned host memory (agf_batch_set_field), runs the ticks, and copies positions and the
+          state in from pinned host memory (agf_batch_set_state), runs the ticks, and copies positions and the
           statistics vector back (agf_batch_get_field / agf_batch_reduce_stats).
 roofline: the step is ALU-bound (nothing is a contraction; state stays in registers): achieved = vehicle-steps/s of
           the step kernel alone x algorithmic FLOP per vehicle-step (2489 full mode, counted with hardware counters on
@@ -309,16 +309,12 @@ def main():
         final_stats = stats.cpu().numpy().copy()
 
         # ---- e2e: public API with host buffers -------------------------------------------------
-        pins = {name: torch.from_numpy(np.ascontiguousarray(init[:, sl])).pin_memory()
-                for name, sl in (("position", slice(0, 3)), ("velocity", slice(3, 6)), ("attitude", slice(6, 10)),
-                                 ("angular_velocity", slice(10, 13)))}
-        h_in = {k: v.numpy() for k, v in pins.items()}
+        pin13 = torch.from_numpy(np.ascontiguousarray(init[:, 0:13])).pin_memory()  # the population's 6-DOF state, pinned host memory
         pos_out = torch.empty((n, 3), dtype=torch.float64).pin_memory()
         ke = max(2, min(K, 5))
 
         def e2e_step():
-            for name, arr in h_in.items():
-                b.set(name, arr)  # H2D from pinned host memory through agf_batch_set_field
+            agf._check(b.L.agf_batch_set_state(b.h, pin13.data_ptr(), 0, n))  # H2D from pinned host memory, one copy
             b.run(S)
             agf._check(b.L.agf_batch_get_field(b.h, 0, pos_out.data_ptr(), 0, n))  # D2H positions
             return b.stats()  # D2H statistics vector
