@@ -771,8 +771,8 @@ struct BatchImpl : Batch {
     if (ref->kind != AGF_OFFREF_STAGES && ref->kind != AGF_OFFREF_TRAJECTORY) return fail(AGF_EINVAL, "unknown reference generator");
     if (ref->kind == AGF_OFFREF_STAGES && (ref->traj_id < 0 || ref->traj_id > 5)) return fail(AGF_EINVAL, "traj_id must be 0..5");
     if (ref->kind == AGF_OFFREF_TRAJECTORY && !d_off_traj) return fail(AGF_EINVAL, "set the trajectories (agf_batch_set_offboard_trajectories) first");
-    if (ref->kind == AGF_OFFREF_STAGES) {  // a fresh state machine (ExampleVehicleStateMachine.cpp:10-19; Vec3d members are NaN)
-      std::vector<double> h(size_t(AGF_OFFSTATE_DOUBLES) * n, std::numeric_limits<double>::quiet_NaN());
+    if (ref->kind == AGF_OFFREF_STAGES) {  // a fresh state machine (ExampleVehicleStateMachine::ExampleVehicleStateMachine, .cpp:5-26)
+      std::vector<double> h(size_t(AGF_OFFSTATE_DOUBLES) * n, 0.0);
       for (size_t i = 0; i < n; i++) {
         h[0 * n + i] = AGF_STAGE_WAIT_FOR_START;
         h[1 * n + i] = AGF_STAGE_COMPLETE;

@@ -78,8 +78,8 @@ int main(int argc, char** argv) {
     for (int a = 0; a < 4; a++) r.est_att[a] = float(e[6 + a]);
     check(agf_batch_get_offboard_state(b, st, 0, 1), "agf_batch_get_offboard_state");
     for (int a = 0; a < 3; a++) {  // desired position / velocity as last commanded by the stage machine
-      r.des_pos[a] = st[6 + a] == st[6 + a] ? st[6 + a] : ref.desired_pos[a];
-      r.des_vel[a] = st[9 + a] == st[9 + a] ? st[9 + a] : 0.0;
+      r.des_pos[a] = st[6 + a];
+      r.des_vel[a] = st[9 + a];
     }
     agf_csv_format_row(&r, line, sizeof line);
     fputs(line, stdout);

@@ -180,7 +180,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
     if (why) { fprintf(stderr, "hostsim: %s\n", why); abort(); }
   }
   if (v->offstate.empty()) {  // what agf_batch_set_offboard_reference writes
-    v->offstate.assign(AGF_OFFSTATE_DOUBLES, std::numeric_limits<double>::quiet_NaN());
+    v->offstate.assign(AGF_OFFSTATE_DOUBLES, 0.0);
     v->offstate[0] = AGF_STAGE_WAIT_FOR_START;
     v->offstate[1] = AGF_STAGE_COMPLETE;
     v->offstate[2] = double(v->now_us);

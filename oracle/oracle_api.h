@@ -90,6 +90,11 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
                           const agf_offboard_ref* ref, const double* offset, const double* tr,
                           double* traj /* [nticks][ORC_NTRAJ] or NULL */);
 void orc_get_offboard_state(orc_vehicle* v, double* out /* [AGF_OFFSTATE_DOUBLES] */);
+/* ref flavours only: the unmodified ExampleVehicleStateMachine of the ROS rates-control node in the same loop (pins the
+ * restated stage logic); traj_id must be the value compiled into the node (ExampleVehicleStateMachine.cpp:213: 3) */
+void orc_run_stages_node(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg, const agf_offboard_ref* ref,
+                         const agf_offboard_estimator* est, int traj_id_check, double* traj);
+void orc_get_stages_node_state(orc_vehicle* v, double* out /* [AGF_OFFSTATE_DOUBLES] */);
 /* Offboard::MocapStateEstimator in the loop (agf_offboard_estimator); NULL: back to the true state */
 void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* est);
 void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* est13, double* counters4 /* or NULL */);

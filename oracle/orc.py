@@ -116,6 +116,10 @@ class Oracle:
             L.orc_run_offboard_ref.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardRef), C.c_void_p,
                                                C.c_void_p, C.c_void_p]
             L.orc_get_offboard_state.argtypes = [vp, C.c_void_p]
+        if hasattr(L, "orc_run_stages_node"):
+            L.orc_run_stages_node.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardRef),
+                                              P(abi.OffboardEstimator), C.c_int, C.c_void_p]
+            L.orc_get_stages_node_state.argtypes = [vp, C.c_void_p]
         if hasattr(L, "orc_csv_row"):
             L.orc_csv_row.restype = C.c_size_t
             L.orc_csv_row.argtypes = [P(abi.CsvRecord), C.c_char_p, C.c_size_t]
@@ -231,6 +235,17 @@ class OracleVehicle:
         self.L.orc_run_offboard_ref(self.h, dt_us, nticks, C.byref(cfg), C.byref(ref), None if off is None else off.ctypes.data,
                                     None if tr is None else tr.ctypes.data, None if traj is None else traj.ctypes.data)
         return traj
+
+    def run_stages_node(self, nticks, cfg, ref, est, dt_us=2000):
+        """the unmodified ExampleVehicleStateMachine in the loop (ref flavours only)"""
+        traj = np.zeros((nticks, NTRAJ))
+        self.L.orc_run_stages_node(self.h, dt_us, nticks, C.byref(cfg), C.byref(ref), C.byref(est), 3, traj.ctypes.data)
+        return traj
+
+    def stages_node_state(self):
+        o = np.zeros(abi.OFFSTATE_DOUBLES)
+        self.L.orc_get_stages_node_state(self.h, o.ctypes.data)
+        return o
 
     def set_offboard_estimator(self, est):
         """est: abi.OffboardEstimator or None (true state)"""

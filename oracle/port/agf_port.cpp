@@ -1666,7 +1666,7 @@ struct orc_vehicle {
   // reference generators (orc_run_offboard_ref): ExampleVehicleStateMachine members
   int stage = AGF_STAGE_WAIT_FOR_START, lastStage = AGF_STAGE_COMPLETE;
   uint64_t stageStart = 0;
-  port::V3d initPosition, lastPos, lastVel, lastAcc;
+  port::V3d initPosition = port::V3d(0, 0, 0), lastPos = port::V3d(0, 0, 0), lastVel = port::V3d(0, 0, 0), lastAcc = port::V3d(0, 0, 0);  // ExampleVehicleStateMachine.cpp:16-25
   double cmdYawAngle = 0;
 };
 

@@ -42,6 +42,7 @@
 #include "Components/Offboard/QuadcopterController.hpp"
 #include "Components/Offboard/MocapStateEstimator.hpp"
 #include "Components/TrajectoryGenerator/RapidTrajectoryGenerator.hpp"
+#include "ExampleVehicleStateMachine.hpp"  // AIFS_ROS/hiperlab_rostools/src/QuadMocapRatesControl, against oracle/shim/ros
 #undef private
 #undef protected
 
@@ -81,10 +82,13 @@ struct orc_vehicle {
     e.angVel = quad->GetAngularVelocity();
     return e;
   }
+  // the ROS rates-control node's own state machine object (orc_run_stages_node)
+  std::unique_ptr<Offboard::ExampleVehicleStateMachine> node;
+  std::unique_ptr<Timer> nodeTimerMocap;
   // reference generators of the offboard loop (orc_run_offboard_ref)
   int stage = AGF_STAGE_WAIT_FOR_START, lastStage = AGF_STAGE_COMPLETE;  // ExampleVehicleStateMachine.cpp:10-11
   std::unique_ptr<Timer> stageTimer;
-  Vec3d initPosition, lastPos, lastVel, lastAcc;  // NaN until set (Vec3.hpp:35), as the node's members
+  Vec3d initPosition = Vec3d(0, 0, 0), lastPos = Vec3d(0, 0, 0), lastVel = Vec3d(0, 0, 0), lastAcc = Vec3d(0, 0, 0);  // ExampleVehicleStateMachine.cpp:16-25
   double cmdYawAngle = 0;                         // ExampleVehicleStateMachine.cpp:19
 };
 
@@ -469,6 +473,87 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
       v->est->SetPredictedValues(cmdAngVel, (estState.att * Vec3d(0, 0, 1) * cmdThrust - Vec3d(0, 0, 9.81)));
     if (send) v->offChannel->AddMessage(rawMsg);
   }
+}
+
+// The UNMODIFIED flight-stage state machine of the ROS rates-control node (ExampleVehicleStateMachine.cpp) in the loop: its
+// own MocapStateEstimator fed through CallbackEstimator at the mocap rate, Run(shouldStart, shouldStop) at the offboard
+// period, the radio_command it publishes taken from the roscpp shim and sent through the delay queue.  This pins the
+// restatement of the stage logic in orc_run_offboard_ref / the port / the device code.  A message whose type byte is 0 (the
+// default-constructed message the node publishes while it waits for the start signal) is not transmitted.
+void orc_run_stages_node(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_offboard_cfg* cfg, const agf_offboard_ref* ref,
+                         const agf_offboard_estimator* e, int traj_id_check, double* traj) {
+  using hiperlab_rostools::radio_command;
+  (void)traj_id_check;
+  if (!v->offTimer) {
+    v->offTimer.reset(new Timer(&v->timer));
+    v->offChannel.reset(new Simulation::CommunicationsDelay<RadioTypes::RadioMessageDecoded::RawMessage>(
+        &v->timer, double(cfg->delay_us) * 1e-6));
+    v->offChannel->_delayTime_us = cfg->delay_us;
+  }
+  if (!v->node) {
+    std::cout.setstate(std::ios_base::failbit);  // the node narrates its stages on stdout
+    v->node.reset(new Offboard::ExampleVehicleStateMachine());
+    ros::NodeHandle n;
+    v->node->Initialize(1, "oracle", n, &v->timer, e->prediction_delay);  // id 1: the airframe of the tests (GetVehicleTypeFromID)
+    std::cout.clear();
+    v->node->_ctrl->SetParameters(cfg->pos_control_nat_freq, cfg->pos_control_damping, cfg->att_control_time_const_xy,
+                                  cfg->att_control_time_const_z);
+    v->node->_ctrl->_minVerticalProperAcceleration = cfg->min_vertical_proper_acc;
+    v->node->_ctrl->_maxProperAcc = cfg->max_proper_acc;
+    v->node->_ctrl->_minProperAcc = cfg->min_proper_acc;
+    v->node->_est->SetStatistics(e->meas_noise_pos, e->meas_noise_att, e->proc_noise_pos, e->proc_noise_att);
+    v->node->_est->SetAngularVelocityTimeConstant(e->angvel_time_const);
+    v->node->_est->_measRejectDist = e->meas_reject_dist;
+    v->node->SetDesiredPosition(Vec3d(ref->desired_pos[0], ref->desired_pos[1], ref->desired_pos[2]));
+    v->node->SetDesiredYaw(ref->desired_yaw);
+    v->nodeTimerMocap.reset(new Timer(&v->timer));
+  }
+  const double period = double(cfg->period_us) * 1e-6, periodMocap = double(e->mocap_period_us) * 1e-6;
+  std::cout.setstate(std::ios_base::failbit);
+  for (uint32_t k = 0; k < nticks; k++) {
+    if (v->offChannel->HaveNewMessage()) v->quad->SetCommandRadioMsg(v->offChannel->GetMessage());
+    v->quad->Run();
+    if (v->net) v->net->Run();
+    if (traj) record(v, traj + size_t(k) * ORC_NTRAJ);
+    v->timer.AdvanceMicroSeconds(dt_us);
+    v->tick++;
+    if (v->nodeTimerMocap->GetSeconds<double>() > periodMocap) {  // the mocap node's packet
+      v->nodeTimerMocap->AdjustTimeBySeconds(-periodMocap);
+      hiperlab_rostools::mocap_output m;
+      const Vec3d p = v->quad->GetPosition();
+      const Rotationd a = v->quad->GetAttitude();
+      m.vehicleID = 1;
+      m.posx = p.x; m.posy = p.y; m.posz = p.z;
+      m.attq0 = a[0]; m.attq1 = a[1]; m.attq2 = a[2]; m.attq3 = a[3];
+      v->node->CallbackEstimator(m);
+    }
+    if (!(v->offTimer->GetSeconds<double>() > period)) continue;
+    v->offTimer->AdjustTimeBySeconds(-period);
+    const uint64_t now = v->timer.GetMicroSeconds();
+    ros::LastPublished<radio_command>::fresh() = false;
+    v->node->Run(now >= ref->start_us, now >= ref->stop_us);
+    if (!ros::LastPublished<radio_command>::fresh()) continue;
+    const radio_command& c = ros::LastPublished<radio_command>::get();
+    if (c.raw[0] == 0) continue;  // RadioTypes::invalid: the wait stage's default-constructed message
+    RadioTypes::RadioMessageDecoded::RawMessage rawMsg;
+    memcpy(rawMsg.raw, c.raw, sizeof(rawMsg.raw));
+    v->offChannel->AddMessage(rawMsg);
+  }
+  std::cout.clear();
+}
+
+void orc_get_stages_node_state(orc_vehicle* v, double* o) {
+  for (int i = 0; i < AGF_OFFSTATE_DOUBLES; i++) o[i] = 0.0;
+  if (!v->node) return;
+  Offboard::ExampleVehicleStateMachine& m = *v->node;
+  o[0] = int(m._flightStage);
+  o[1] = int(m._lastFlightStage);
+  o[2] = double(m._stageTimer->_lastResetTime_usec);
+  const Vec3d* q[4] = {&m._initPosition, &m._lastPos, &m._lastVel, &m._lastAcc};
+  for (int i = 0; i < 4; i++) {
+    o[3 + 3 * i] = q[i]->x; o[4 + 3 * i] = q[i]->y; o[5 + 3 * i] = q[i]->z;
+  }
+  o[15] = m._cmdYawAngle;
 }
 
 void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e) {

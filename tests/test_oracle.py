@@ -167,6 +167,34 @@ def test_offboard_estimator_port_matches_reference(agf, orc_mod, math, name, jum
         assert bit_equal(a, tr) and bit_equal(ea, est)
 
 
+@pytest.mark.parametrize("math", ["glibc", "shared"])
+def test_stage_logic_is_pinned_by_the_unmodified_ros_state_machine(agf, orc_mod, math):
+    """AIFS_ROS/hiperlab_rostools/src/QuadMocapRatesControl/ExampleVehicleStateMachine.cpp compiles UNMODIFIED
+    into oracle/_ref against a roscpp / message shim; driven in the same loop (its own MocapStateEstimator, Run() at 100 Hz,
+    the radio_command it publishes through the delay queue) it flies wait -> spool-up -> take-off -> circle -> landing ->
+    idle.  The restated stage logic (port; and through it the device code) reproduces that trajectory and the machine's
+    final state bit for bit: golden vectors from the node, and the live node where the reference build exists."""
+    sc = agf.scenarios.stages_scenario(3)
+    P = oracle_or_skip(orc_mod, "port-" + math)
+    v = P.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"],
+                                  motor_inertia=sc["motor_inertia"]), uwb_comm_period=0.0)
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    v.set_offboard_estimator(agf.offboard_estimator())
+    tr = v.run_offboard_ref(sc["nticks"], agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]))
+    key = "ref-%s/node/%s" % (math, sc["name"])
+    assert bit_equal(tr[GOLD[key + "/ticks"]], GOLD[key + "/traj"])
+    assert bit_equal(v.offboard_state(), GOLD[key + "/offstate"])
+    assert v.offboard_state()[0] == agf.abi.STAGE_COMPLETE and tr[-1, 35] == 0 and abs(tr[2500, 2] - 1.0) < 0.05
+    if orc_mod.available("ref-" + math):
+        R = orc_mod.Oracle("ref-" + math)
+        if hasattr(R.L, "orc_run_stages_node"):
+            n = R.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"],
+                                          motor_inertia=sc["motor_inertia"]), uwb_comm_period=0.0)
+            n.set_state(pos=sc["pos"], att=sc["att"])
+            tn = n.run_stages_node(sc["nticks"], agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), agf.offboard_estimator())
+            assert bit_equal(tn, tr) and bit_equal(n.stages_node_state(), v.offboard_state())
+
+
 def test_offboard_estimator_device_code_on_host(agf, orc_mod, port_shared):
     """The product's device code of the estimator (agf_step.cuh mocap_update / mocap_predict / mocap_set_predicted),
     compiled for the host, equals the port bit for bit, across launch boundaries and through the reset path."""
