@@ -305,6 +305,25 @@ def test_offboard_estimator_parity(agf, port_shared, name, jump):
     b2.close()
 
 
+def test_flight_stages_on_the_gpu_match_the_unmodified_ros_state_machine(agf):
+    """the in-kernel stage machine + mocap estimator against golden vectors recorded from the UNMODIFIED
+    ExampleVehicleStateMachine.cpp of the ROS rates-control node (oracle/_ref with the roscpp shim): the sampled
+    trajectory of the 14 s flight and the machine's final state, bit for bit, for every vehicle of the batch."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    sc = agf.scenarios.stages_scenario(3)
+    key = "ref-shared/node/%s" % sc["name"]
+    ticks, want = gold[key + "/ticks"], gold[key + "/traj"]
+    b = make_batch_estimator(agf, sc, n=5)
+    done = 0
+    for t, w in zip(ticks[-21:], want[-21:]):  # the last sampled ticks (every 25th, then the final 20)
+        b.run(int(t) + 1 - done)
+        done = int(t) + 1
+        got = b.record()
+        assert bit_equal(got, np.tile(w, (5, 1))), (t, got[0][0:3], w[0:3])
+    assert bit_equal(b.offboard_state(), np.tile(gold[key + "/offstate"], (5, 1)))
+    b.close()
+
+
 def test_offboard_estimator_fast_variants(agf, port_glibc):
     """Fast FP64 / FP32 kernels with the estimator in the loop: position within the offboard loop's stated tolerance of the
     oracle (1e-3 / 5e-3 relative), estimate within 2 cm of the truth, for a population on the balanced schedule too."""
