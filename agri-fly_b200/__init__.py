@@ -30,10 +30,12 @@ def offboard_cfg(quad_type=5, **edits):
     return c
 
 
-def offboard_ref(kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=0):
+def offboard_ref(kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=0, safety_net=False):
     r = abi.OffboardRef(kind=int(kind), traj_id=int(traj_id), start_us=int(start_us), stop_us=int(stop_us),
                         desired_yaw=float(desired_yaw))
     r.desired_pos[:] = [float(x) for x in desired_pos]
+    if safety_net:
+        lib().agf_offboard_ref_safety_default(C.byref(r))  # Offboard::SafetyNet's lab-space box, 1 m, 0.5 s
     return r
 
 
@@ -370,14 +372,15 @@ class Batch:
         _check(self.L.agf_batch_set_offboard_loop(self.h, C.byref(cfg), tarr, len(targets),
                                                   None if off is None else off.ctypes.data))
 
-    def set_offboard_reference(self, kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=0):
+    def set_offboard_reference(self, kind, start_us=0, stop_us=2**64 - 1, desired_pos=(0.0, 0.0, 1.0), desired_yaw=0.0, traj_id=0,
+                               safety_net=False):
         """Reference generator of the offboard loop (agrifly_b200.h): abi.OFFREF_STAGES (flight stages of the ROS
         rates-control node) or abi.OFFREF_TRAJECTORY (tracking of per-vehicle motion primitives); None: targets."""
         if kind is None:
             _check(self.L.agf_batch_set_offboard_reference(self.h, None))
             return
         _check(self.L.agf_batch_set_offboard_reference(self.h, C.byref(offboard_ref(kind, start_us, stop_us, desired_pos,
-                                                                                   desired_yaw, traj_id))))
+                                                                                   desired_yaw, traj_id, safety_net))))
 
     def set_offboard_estimator(self, est):
         """est: abi.OffboardEstimator (offboard_estimator()) or None for the true state"""

@@ -97,7 +97,7 @@ class OffboardTarget(C.Structure):
 
 
 OFFREF_TARGETS, OFFREF_STAGES, OFFREF_TRAJECTORY = 0, 1, 2
-STAGE_WAIT_FOR_START, STAGE_SPOOL_UP, STAGE_TAKEOFF, STAGE_FLIGHT, STAGE_LANDING, STAGE_COMPLETE = range(6)
+STAGE_WAIT_FOR_START, STAGE_SPOOL_UP, STAGE_TAKEOFF, STAGE_FLIGHT, STAGE_LANDING, STAGE_COMPLETE, STAGE_EMERGENCY = range(7)
 OFFTRAJ_DOUBLES, OFFSTATE_DOUBLES = 29, 16
 
 
@@ -121,7 +121,9 @@ class OffboardEstimator(C.Structure):
 
 class OffboardRef(C.Structure):
     _fields_ = [("kind", C.c_int32), ("traj_id", C.c_int32), ("start_us", C.c_uint64), ("stop_us", C.c_uint64),
-                ("desired_pos", C.c_double * 3), ("desired_yaw", C.c_double)]
+                ("desired_pos", C.c_double * 3), ("desired_yaw", C.c_double), ("safety_net", C.c_int32), ("reserved", C.c_int32),
+                ("safe_min", C.c_double * 3), ("safe_max", C.c_double * 3), ("min_normal_height", C.c_double),
+                ("not_seen_timeout", C.c_double)]
 
 
 # ---- include/agrifly_b200_rappids.h ------------------------------------------------------------
@@ -206,6 +208,7 @@ PROTOTYPES = {
     "agf_batch_set_cmd_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "agf_offboard_cfg_default": (C.c_int, [C.c_int, _P(OffboardCfg)]),
     "agf_batch_set_offboard_loop": (C.c_int, [C.c_void_p, _P(OffboardCfg), _P(OffboardTarget), C.c_size_t, C.c_void_p]),
+    "agf_offboard_ref_safety_default": (None, [_P(OffboardRef)]),
     "agf_batch_set_offboard_reference": (C.c_int, [C.c_void_p, _P(OffboardRef)]),
     "agf_batch_set_offboard_trajectories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_get_offboard_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),

@@ -742,6 +742,10 @@ struct BatchImpl : Batch {
     off.start_us = sh.off.start_us; off.stop_us = sh.off.stop_us;
     for (int k = 0; k < 3; k++) off.desired[k] = sh.off.desired[k];
     off.desired_yaw = sh.off.desired_yaw;
+    off.safety_net = sh.off.safety_net;
+    for (int k = 0; k < 3; k++) { off.safe_min[k] = sh.off.safe_min[k]; off.safe_max[k] = sh.off.safe_max[k]; }
+    off.min_normal_height = sh.off.min_normal_height;
+    off.not_seen_timeout = sh.off.not_seen_timeout;
     off.state = d_off_state;
     off.traj = d_off_traj;
     off.est = sh.off.est;
@@ -788,6 +792,10 @@ struct BatchImpl : Batch {
     sh.off.stop_us = ref->stop_us;
     for (int k = 0; k < 3; k++) sh.off.desired[k] = ref->desired_pos[k];
     sh.off.desired_yaw = ref->desired_yaw;
+    sh.off.safety_net = ref->kind == AGF_OFFREF_STAGES ? ref->safety_net : 0;
+    for (int k = 0; k < 3; k++) { sh.off.safe_min[k] = ref->safe_min[k]; sh.off.safe_max[k] = ref->safe_max[k]; }
+    sh.off.min_normal_height = ref->min_normal_height;
+    sh.off.not_seen_timeout = ref->not_seen_timeout;
     sh.off.state = d_off_state;
     sh.off.traj = d_off_traj;
     sh.tc.off_first_target_us = 0;
@@ -1329,6 +1337,14 @@ int agf_batch_get_offboard_estimate(agf_batch* b, double horizon, double* est13,
 }
 int agf_batch_set_state(agf_batch* b, const double* state13, size_t first, size_t count) {
   return b ? B(b)->set_state13(state13, first, count) : fail(AGF_EINVAL, "null handle");
+}
+void agf_offboard_ref_safety_default(agf_offboard_ref* r) {  // SafetyNet::SafetyNet (SafetyNet.hpp:52-58)
+  if (!r) return;
+  r->safety_net = 1;
+  r->safe_min[0] = -2.4; r->safe_min[1] = -3.1; r->safe_min[2] = -0.5;
+  r->safe_max[0] = +1.8; r->safe_max[1] = +3.1; r->safe_max[2] = 4.5;
+  r->min_normal_height = 1.0;
+  r->not_seen_timeout = 0.5;
 }
 int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref) {
   return b ? B(b)->set_offboard_ref(ref) : fail(AGF_EINVAL, "null handle");

@@ -1332,6 +1332,7 @@ AGF_DEV float4 offboard_tracking(const OffboardParams& c, const V3<P>& curPos, c
 // queue payload markers: x = +inf "no command this round" (wait stage), x = NaN "idle command"
 AGF_DEV float4 offboard_no_command() { return make_float4(1.0f / 0.0f, 0.0f, 0.0f, 0.0f); }
 AGF_DEV float4 offboard_idle_command() { return make_float4(0.0f / 0.0f, 0.0f, 0.0f, 0.0f); }
+AGF_DEV float4 offboard_kill_command() { return make_float4(-1.0f / 0.0f, 0.0f, 0.0f, 0.0f); }  // x = -inf: emergency kill
 // SingleAxisTrajectory::GetPosition / GetVelocity / GetAcceleration (SingleAxisTrajectory.hpp:57-63); q: p0 v0 a0 alpha beta gamma
 AGF_DEV double sat_pos(const double* q, double t) {
   return q[0] + q[1] * t + (1 / 2.0) * q[2] * t * t + (1 / 6.0) * q[5] * t * t * t + (1 / 24.0) * q[4] * t * t * t * t +
@@ -1695,6 +1696,23 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
   const int stage_in = stage;
   float4 out;
   double cmdYaw = ldg2(st + 15 * n);
+  // SafetyNet::UpdateWithEstimator + GetIsSafe (SafetyNet.hpp:70-106), on every Run()
+  bool safe = true;
+  if (c.safety_net) {
+    const double since = c.est.kind == AGF_OFFEST_MOCAP ? double(t_gen - uint64_t(ldg2(c.est.state + i + size_t(E_LASTGOOD) * n))) * 1e-6 : 0.0;
+    const bool notSeen = since > c.not_seen_timeout;
+    bool unsafePos = false;
+    const double ep[3] = {cp.x, cp.y, cp.z};
+    for (int a = 0; a < 3; a++) {
+      if (ep[a] < c.safe_min[a]) unsafePos = true;
+      if (ep[a] > c.safe_max[a]) unsafePos = true;
+    }
+    bool upsideDownAndLow = false;
+    if (cp.z < c.min_normal_height) {
+      if (qrot(ca, V3<double>(0, 0, 1)).z < 0) upsideDownAndLow = true;
+    }
+    safe = !(notSeen || unsafePos || upsideDownAndLow);
+  }
   switch (stage) {
     case AGF_STAGE_WAIT_FOR_START:
       if (shouldStart) stage = AGF_STAGE_SPOOL_UP;
@@ -1702,6 +1720,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
       predicted = 0;
       break;
     case AGF_STAGE_SPOOL_UP:
+      if (!safe) stage = AGF_STAGE_EMERGENCY;
       out = offboard_rates_packet(9.81 * 0.25, V3<float>(0.0f, 0.0f, 0.0f));
       predicted = 1;
       if (ts > 0.5) stage = AGF_STAGE_TAKEOFF;
@@ -1710,6 +1729,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
       if (stageChange) {
         st[3 * n] = double(cp.x); st[4 * n] = double(cp.y); st[5 * n] = double(cp.z);
       }
+      if (!safe) stage = AGF_STAGE_EMERGENCY;
       double frac = ts / 2.0;
       if (frac >= 1.0) {
         stage = AGF_STAGE_FLIGHT;
@@ -1720,6 +1740,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
       out = offboard_command<PARITY, P>(c, cp, cv, ca, cmdPos, zero3, zero3, cmdYaw, thrustOut, wOut);
     } break;
     case AGF_STAGE_FLIGHT: {
+      if (!safe) stage = AGF_STAGE_EMERGENCY;
       double cmdPos[3] = {0, 0, 0}, cmdVel[3] = {0, 0, 0}, cmdAcc[3] = {0, 0, 0};
       const double t = ts;
       const double frac = (t / 2.0 < 1.0) ? t / 2.0 : 1.0;  // min(t / getIntoActionTime, 1.0)
@@ -1781,6 +1802,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
       if (shouldStop) stage = AGF_STAGE_LANDING;
     } break;
     case AGF_STAGE_LANDING: {
+      if (!safe) stage = AGF_STAGE_EMERGENCY;
       const double LANDING_SPEED = 0.5;
       const double frac = (ts / 2.0 < 1.0) ? ts / 2.0 : 1.0;
       double lp[3], lv[3], la[3], cmdPos[3], dp[3], dv[3], da[3];
@@ -1797,9 +1819,13 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
       }
       out = offboard_command<PARITY, P>(c, cp, cv, ca, dp, dv, da, cmdYaw, thrustOut, wOut);
     } break;
-    default:
+    case AGF_STAGE_COMPLETE:
       out = offboard_idle_command();
       predicted = 1;
+      break;
+    default:  // AGF_STAGE_EMERGENCY (:350-363): kill, nothing told to the estimator
+      out = offboard_kill_command();
+      predicted = 0;
       break;
   }
   if (stage != stage_in) st[0] = double(stage);
@@ -2085,9 +2111,9 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     } else {
       c = sq_load(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_deliver_slot));
     }
-    if (c.x != c.x) {  // idle command (CreateIdleCommand): type and flags only
+    if (c.x != c.x || c.x < -3.0e38f) {  // idle / kill command (CreateIdleCommand, CreateKillCommand): type and flags only
       const float cf[4] = {s.radio_f[0], s.radio_f[1], s.radio_f[2], s.radio_f[3]};
-      radio_deliver(s, p.logic, AGF_RADIO_IDLE_CMD, p.off.flags, cf);
+      radio_deliver(s, p.logic, c.x != c.x ? AGF_RADIO_IDLE_CMD : AGF_RADIO_EMERGENCY_KILL, p.off.flags, cf);
     } else if (c.x <= 3.0e38f) {  // +inf: nothing was sent that round
       const float cf[4] = {c.x, c.y, c.z, c.w};
       radio_deliver(s, p.logic, AGF_RADIO_EXTERNAL_RATES_CMD, p.off.flags, cf);

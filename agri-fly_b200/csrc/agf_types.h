@@ -304,6 +304,8 @@ struct OffboardParams {
   int ref_kind, traj_id;
   uint64_t start_us, stop_us;
   double desired[3], desired_yaw;
+  int safety_net;  // Offboard::SafetyNet on the estimate (stages)
+  double safe_min[3], safe_max[3], min_normal_height, not_seen_timeout;
   double* state;       // device [AGF_OFFSTATE_DOUBLES][N]: stage machine state per vehicle
   const double* traj;  // device [AGF_OFFTRAJ_DOUBLES][N]: motion primitive per vehicle
   EstParams est;

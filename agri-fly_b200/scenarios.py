@@ -164,6 +164,14 @@ def stages_scenario(traj_id=3, nticks=7000):
     return sc
 
 
+def stages_emergency_scenario(nticks=4000):
+    """The flight stages with Offboard::SafetyNet on and a set-point outside the lab-space box (x = 2.5 m > 1.8 m): the
+    take-off ramp carries the estimate across the box, the stage machine latches its emergency stage and sends kill commands."""
+    sc = stages_scenario(3, nticks)
+    sc.update(name="stages3-emergency", ref=dict(sc["ref"], desired_pos=(2.5, 0.0, 1.0), safety_net=True))
+    return sc
+
+
 def tracking_scenario(nticks=3400):
     """Rappids_Simulator's tracking of a planned motion primitive (main.cpp:560-634): hover at 2 m with
     QuadcopterController::Run until 4 s, then RunTracking along a 2.5 s rest-to-rest quintic given in a frame yawed by

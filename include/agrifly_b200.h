@@ -360,7 +360,7 @@ int agf_batch_set_offboard_loop(agf_batch* b, const agf_offboard_cfg* cfg, const
  *   the z clamps behind the camera (:580-591). */
 enum { AGF_OFFREF_TARGETS = 0, AGF_OFFREF_STAGES = 1, AGF_OFFREF_TRAJECTORY = 2 };
 enum { AGF_STAGE_WAIT_FOR_START = 0, AGF_STAGE_SPOOL_UP = 1, AGF_STAGE_TAKEOFF = 2, AGF_STAGE_FLIGHT = 3,
-       AGF_STAGE_LANDING = 4, AGF_STAGE_COMPLETE = 5 }; /* ExampleVehicleStateMachine.hpp FlightStage */
+       AGF_STAGE_LANDING = 4, AGF_STAGE_COMPLETE = 5, AGF_STAGE_EMERGENCY = 6 }; /* ExampleVehicleStateMachine.hpp FlightStage */
 typedef struct agf_offboard_ref {
   int32_t kind;          /* AGF_OFFREF_* */
   int32_t traj_id;       /* STAGES: trajID of the flight stage (ExampleVehicleStateMachine.cpp:213), 0..5 */
@@ -368,7 +368,17 @@ typedef struct agf_offboard_ref {
   uint64_t stop_us;      /* STAGES: stop signal (UINT64_MAX: never) */
   double desired_pos[3]; /* _desiredPosition (QuadMocapRatesControl/main.cpp:82: (0,0,1)) / hover point (main.cpp:505) */
   double desired_yaw;    /* _desiredYawAngle [rad]; TRAJECTORY: desYawAngleDeg * pi / 180 (main.cpp:244) */
+  /* STAGES: Offboard::SafetyNet (Components/Offboard/SafetyNet.hpp:52-106), checked on the state estimate in the spool-up,
+   * take-off, flight and landing stages; a violation latches AGF_STAGE_EMERGENCY, which sends kill commands
+   * (ExampleVehicleStateMachine.cpp:126-129,167-170,195-198,304-307,350-363).  safety_net == 0: off. */
+  int32_t safety_net;
+  int32_t reserved;
+  double safe_min[3], safe_max[3]; /* lab-space corners: (-2.4,-3.1,-0.5) .. (1.8,3.1,4.5) */
+  double min_normal_height;        /* below it the vehicle must point upwards: 1.0 */
+  double not_seen_timeout;         /* [s] since the estimator's last accepted measurement: 0.5 */
 } agf_offboard_ref;
+/* SafetyNet's defaults into the four fields above, safety_net = 1 */
+void agf_offboard_ref_safety_default(agf_offboard_ref* ref);
 /* Needs agf_batch_set_offboard_loop first (period, delay, controller gains; its targets are ignored for the other
  * kinds, its per-vehicle offsets shift desired_pos).  ref == NULL: back to AGF_OFFREF_TARGETS. */
 int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref);

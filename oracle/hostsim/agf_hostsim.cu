@@ -197,6 +197,10 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
   o.stop_us = ref->stop_us;
   for (int k = 0; k < 3; k++) o.desired[k] = ref->desired_pos[k];
   o.desired_yaw = ref->desired_yaw;
+  o.safety_net = ref->kind == AGF_OFFREF_STAGES ? ref->safety_net : 0;
+  for (int k = 0; k < 3; k++) { o.safe_min[k] = ref->safe_min[k]; o.safe_max[k] = ref->safe_max[k]; }
+  o.min_normal_height = ref->min_normal_height;
+  o.not_seen_timeout = ref->not_seen_timeout;
   o.state = v->offstate.data();
   o.traj = v->offtraj.empty() ? nullptr : v->offtraj.data();
   v->sh.tc.off_first_target_us = 0;

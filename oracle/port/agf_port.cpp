@@ -1900,6 +1900,19 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
       }
     } else {
       const bool shouldStart = now >= ref->start_us, shouldStop = now >= ref->stop_us;
+      bool safe = true;  // SafetyNet::UpdateWithEstimator + IsSafe (Components/Offboard/SafetyNet.hpp:70-106)
+      if (ref->safety_net) {
+        const double since = v->est ? v->est->lastGood.seconds_d() : 0.0;
+        bool notSeen = since > ref->not_seen_timeout, unsafePos = false, upsideDownAndLow = false;
+        for (int a = 0; a < 3; a++) {
+          if (estPos.get(a) < ref->safe_min[a]) unsafePos = true;
+          if (estPos.get(a) > ref->safe_max[a]) unsafePos = true;
+        }
+        if (estPos.z < ref->min_normal_height) {
+          if (estAtt.rotate(V3d(0, 0, 1)).z < 0) upsideDownAndLow = true;
+        }
+        safe = !(notSeen || unsafePos || upsideDownAndLow);
+      }
       const bool stageChange = v->stage != v->lastStage;
       v->lastStage = v->stage;
       if (stageChange) v->stageStart = now;
@@ -1911,12 +1924,14 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           predicted = 0;
           break;
         case AGF_STAGE_SPOOL_UP:
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           predicted = 1;
           q.cmd = port::quantise_rates(9.81 * 0.25, zero);
           if (ts > 0.5) v->stage = AGF_STAGE_TAKEOFF;
           break;
         case AGF_STAGE_TAKEOFF: {
           if (stageChange) v->initPosition = estPos;
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           double frac = ts / 2.0;
           if (frac >= 1.0) {
             v->stage = AGF_STAGE_FLIGHT;
@@ -1926,6 +1941,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           q.cmd = port::offboard_rates_command(*cfg, estPos, estVel, estAtt, cmdPos, zero, zero, v->cmdYawAngle);
         } break;
         case AGF_STAGE_FLIGHT: {
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           V3d cmdPos(0, 0, 0), cmdVel(0, 0, 0), cmdAcc(0, 0, 0);
           const double t = ts;
           const double frac = std::min(t / 2.0, 1.0);
@@ -1977,6 +1993,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           if (shouldStop) v->stage = AGF_STAGE_LANDING;
         } break;
         case AGF_STAGE_LANDING: {
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           const double frac = std::min(ts / 2.0, 1.0);
           const V3d land(0, 0, -0.5);
           const V3d cmdPos = v->lastPos + ts * land;
@@ -1985,10 +2002,15 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
                                                (1 - frac) * v->lastVel + frac * land, (1 - frac) * v->lastAcc + frac * zero,
                                                v->cmdYawAngle);
         } break;
-        default:
+        case AGF_STAGE_COMPLETE:
           predicted = 1;
           q.type = AGF_RADIO_IDLE_CMD;
           for (int i = 0; i < 4; i++) q.cmd.f[i] = 35.0f * (0 - 32768) / float(32768);  // zero bytes decode to -limit; never read
+          break;
+        default:  // AGF_STAGE_EMERGENCY
+          predicted = 0;
+          q.type = AGF_RADIO_EMERGENCY_KILL;
+          for (int i = 0; i < 4; i++) q.cmd.f[i] = 35.0f * (0 - 32768) / float(32768);
           break;
       }
     }

@@ -41,6 +41,7 @@
 #include "Components/Simulation/CommunicationsDelay.hpp"
 #include "Components/Offboard/QuadcopterController.hpp"
 #include "Components/Offboard/MocapStateEstimator.hpp"
+#include "Components/Offboard/SafetyNet.hpp"
 #include "Components/TrajectoryGenerator/RapidTrajectoryGenerator.hpp"
 #include "ExampleVehicleStateMachine.hpp"  // AIFS_ROS/hiperlab_rostools/src/QuadMocapRatesControl, against oracle/shim/ros
 #undef private
@@ -360,6 +361,15 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
                                                           rawMsg.raw);
     } else {  // AGF_OFFREF_STAGES: ExampleVehicleStateMachine::Run(shouldStart, shouldStop)
       const bool shouldStart = now >= ref->start_us, shouldStop = now >= ref->stop_us;
+      bool safe = true;  // _safetyNet->UpdateWithEstimator(...) :104-105, the reference's own SafetyNet with the configured box
+      if (ref->safety_net) {
+        Offboard::SafetyNet net;
+        net.SetSafeCorners(Vec3d(ref->safe_min[0], ref->safe_min[1], ref->safe_min[2]),
+                           Vec3d(ref->safe_max[0], ref->safe_max[1], ref->safe_max[2]), ref->min_normal_height);
+        net._vehicleNotSeenTimeout = ref->not_seen_timeout;
+        net.UpdateWithEstimator(estState, v->est ? v->est->GetTimeSinceLastGoodMeasurement() : 0.0);
+        safe = net.GetIsSafe();
+      }
       bool stageChange = v->stage != v->lastStage;  // :96-100
       v->lastStage = v->stage;
       if (stageChange) v->stageTimer->Reset();
@@ -375,6 +385,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           predicted = 0;
           break;
         case AGF_STAGE_SPOOL_UP: {  // :122-160
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           double const motorSpoolUpTime = 0.5;
           double const spoolUpThrustByWeight = 0.25;
           predicted = 1;  // :134
@@ -386,6 +397,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
         } break;
         case AGF_STAGE_TAKEOFF: {  // :162-189
           if (stageChange) v->initPosition = estPos;
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           double const takeOffTime = 2.0;
           double frac = v->stageTimer->GetSeconds<double>() / takeOffTime;
           if (frac >= 1.0) {
@@ -396,6 +408,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           runController(cmdPos, Vec3d(0, 0, 0), Vec3d(0, 0, 0));
         } break;
         case AGF_STAGE_FLIGHT: {  // :191-298
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           Vec3d cmdPos(0, 0, 0), cmdVel(0, 0, 0), cmdAcc(0, 0, 0);
           double t = v->stageTimer->GetSeconds<double>();
           double const getIntoActionTime = 2.0;
@@ -454,6 +467,7 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           if (shouldStop) v->stage = AGF_STAGE_LANDING;
         } break;
         case AGF_STAGE_LANDING: {  // :300-324
+          if (!safe) v->stage = AGF_STAGE_EMERGENCY;
           double const LANDING_SPEED = 0.5;
           double const getIntoActionTime = 2.0;
           double frac = std::min(v->stageTimer->GetSeconds<double>() / getIntoActionTime, 1.0);
@@ -462,9 +476,13 @@ void orc_run_offboard_ref(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const
           runController((1 - frac) * v->lastPos + frac * cmdPos, (1 - frac) * v->lastVel + frac * Vec3d(0, 0, -LANDING_SPEED),
                         (1 - frac) * v->lastAcc + frac * Vec3d(0, 0, 0));
         } break;
-        default:  // AGF_STAGE_COMPLETE :326-343
+        case AGF_STAGE_COMPLETE:  // :326-343
           predicted = 1;  // :332
           RadioTypes::RadioMessageDecoded::CreateIdleCommand(uint8_t(cfg->radio_flags), rawMsg.raw);
+          break;
+        default:  // AGF_STAGE_EMERGENCY :350-363
+          predicted = 0;
+          RadioTypes::RadioMessageDecoded::CreateKillCommand(uint8_t(cfg->radio_flags), rawMsg.raw);
           break;
       }
     }
@@ -506,6 +524,14 @@ void orc_run_stages_node(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const 
     v->node->_est->_measRejectDist = e->meas_reject_dist;
     v->node->SetDesiredPosition(Vec3d(ref->desired_pos[0], ref->desired_pos[1], ref->desired_pos[2]));
     v->node->SetDesiredYaw(ref->desired_yaw);
+    if (ref->safety_net) {
+      v->node->_safetyNet->SetSafeCorners(Vec3d(ref->safe_min[0], ref->safe_min[1], ref->safe_min[2]),
+                                          Vec3d(ref->safe_max[0], ref->safe_max[1], ref->safe_max[2]), ref->min_normal_height);
+      v->node->_safetyNet->_vehicleNotSeenTimeout = ref->not_seen_timeout;
+    } else {  // switched off: a box nothing leaves, no time-out
+      v->node->_safetyNet->SetSafeCorners(Vec3d(-1e30, -1e30, -1e30), Vec3d(1e30, 1e30, 1e30), -1e30);
+      v->node->_safetyNet->_vehicleNotSeenTimeout = 1e30;
+    }
     v->nodeTimerMocap.reset(new Timer(&v->timer));
   }
   const double period = double(cfg->period_us) * 1e-6, periodMocap = double(e->mocap_period_us) * 1e-6;

@@ -63,16 +63,16 @@ def main():
             out[key + "/traj"] = tr[idx]
             out[key + "/offstate"] = v.offboard_state()
         # the UNMODIFIED flight-stage state machine of the ROS rates-control node in the loop (roscpp shim): pins the stage logic
-        sc = scen.stages_scenario(3)
-        v = O.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"],
-                                      motor_inertia=sc["motor_inertia"]), uwb_comm_period=0.0)
-        v.set_state(pos=sc["pos"], att=sc["att"])
-        tr = v.run_stages_node(sc["nticks"], agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), agf.offboard_estimator())
-        idx = sample_ticks(len(tr))
-        key = "%s/node/%s" % (flavour, sc["name"])
-        out[key + "/ticks"] = idx
-        out[key + "/traj"] = tr[idx]
-        out[key + "/offstate"] = v.stages_node_state()
+        for sc in (scen.stages_scenario(3), scen.stages_emergency_scenario()):
+            v = O.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"],
+                                          motor_inertia=sc["motor_inertia"]), uwb_comm_period=0.0)
+            v.set_state(pos=sc["pos"], att=sc["att"])
+            tr = v.run_stages_node(sc["nticks"], agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), agf.offboard_estimator())
+            idx = sample_ticks(len(tr))
+            key = "%s/node/%s" % (flavour, sc["name"])
+            out[key + "/ticks"] = idx
+            out[key + "/traj"] = tr[idx]
+            out[key + "/offstate"] = v.stages_node_state()
         # the offboard loop fed by the reference's MocapStateEstimator (+ measurement rejection and forced reset)
         for sc, jump in ((scen.offboard_scenario(), None), (scen.stages_scenario(1), None), (scen.tracking_scenario(), None),
                          (scen.offboard_scenario(2000), 1000)):

@@ -127,8 +127,8 @@ def test_offboard_reference_generators_device_code_on_host(agf, orc_mod, port_sh
     H = orc_mod.Oracle("hostsim-shared")
     if not hasattr(H.L, "orc_run_offboard_ref"):
         pytest.skip("stale hostsim build")
-    for name in ("stages1", "stages4", "tracking"):
-        sc = ref_scenario(agf, name)
+    for name in ("stages1", "stages4", "tracking", "emergency"):
+        sc = agf.scenarios.stages_emergency_scenario() if name == "emergency" else ref_scenario(agf, name)
         off = (0.3, -0.2, 0.1)
         a, va = run_oracle_offboard_ref(port_shared, agf, sc, offset=off)
         b, vb = run_oracle_offboard_ref(H, agf, sc, chunks=[1, 1, 13, 985, sc["nticks"] - 1000], offset=off)
@@ -167,14 +167,17 @@ def test_offboard_estimator_port_matches_reference(agf, orc_mod, math, name, jum
         assert bit_equal(a, tr) and bit_equal(ea, est)
 
 
+@pytest.mark.parametrize("case", ["nominal", "emergency"])
 @pytest.mark.parametrize("math", ["glibc", "shared"])
-def test_stage_logic_is_pinned_by_the_unmodified_ros_state_machine(agf, orc_mod, math):
+def test_stage_logic_is_pinned_by_the_unmodified_ros_state_machine(agf, orc_mod, math, case):
     """AIFS_ROS/hiperlab_rostools/src/QuadMocapRatesControl/ExampleVehicleStateMachine.cpp compiles UNMODIFIED
     into oracle/_ref against a roscpp / message shim; driven in the same loop (its own MocapStateEstimator, Run() at 100 Hz,
     the radio_command it publishes through the delay queue) it flies wait -> spool-up -> take-off -> circle -> landing ->
     idle.  The restated stage logic (port; and through it the device code) reproduces that trajectory and the machine's
-    final state bit for bit: golden vectors from the node, and the live node where the reference build exists."""
-    sc = agf.scenarios.stages_scenario(3)
+    final state bit for bit: golden vectors from the node, and the live node where the reference build exists.  The
+    emergency case switches the node's SafetyNet to a set-point outside its lab-space box: the stage machine latches
+    StageEmergency during take-off and kills the vehicle."""
+    sc = agf.scenarios.stages_scenario(3) if case == "nominal" else agf.scenarios.stages_emergency_scenario()
     P = oracle_or_skip(orc_mod, "port-" + math)
     v = P.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"],
                                   motor_inertia=sc["motor_inertia"]), uwb_comm_period=0.0)
@@ -184,7 +187,10 @@ def test_stage_logic_is_pinned_by_the_unmodified_ros_state_machine(agf, orc_mod,
     key = "ref-%s/node/%s" % (math, sc["name"])
     assert bit_equal(tr[GOLD[key + "/ticks"]], GOLD[key + "/traj"])
     assert bit_equal(v.offboard_state(), GOLD[key + "/offstate"])
-    assert v.offboard_state()[0] == agf.abi.STAGE_COMPLETE and tr[-1, 35] == 0 and abs(tr[2500, 2] - 1.0) < 0.05
+    if case == "nominal":
+        assert v.offboard_state()[0] == agf.abi.STAGE_COMPLETE and tr[-1, 35] == 0 and abs(tr[2500, 2] - 1.0) < 0.05
+    else:
+        assert v.offboard_state()[0] == agf.abi.STAGE_EMERGENCY and tr[-1, 34] == agf.abi.FS_KILLED and tr[-1, 2] < 0.01
     if orc_mod.available("ref-" + math):
         R = orc_mod.Oracle("ref-" + math)
         if hasattr(R.L, "orc_run_stages_node"):

@@ -305,12 +305,13 @@ def test_offboard_estimator_parity(agf, port_shared, name, jump):
     b2.close()
 
 
-def test_flight_stages_on_the_gpu_match_the_unmodified_ros_state_machine(agf):
+@pytest.mark.parametrize("case", ["nominal", "emergency"])
+def test_flight_stages_on_the_gpu_match_the_unmodified_ros_state_machine(agf, case):
     """the in-kernel stage machine + mocap estimator against golden vectors recorded from the UNMODIFIED
     ExampleVehicleStateMachine.cpp of the ROS rates-control node (oracle/_ref with the roscpp shim): the sampled
     trajectory of the 14 s flight and the machine's final state, bit for bit, for every vehicle of the batch."""
     gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
-    sc = agf.scenarios.stages_scenario(3)
+    sc = agf.scenarios.stages_scenario(3) if case == "nominal" else agf.scenarios.stages_emergency_scenario()  # SafetyNet -> kill
     key = "ref-shared/node/%s" % sc["name"]
     ticks, want = gold[key + "/ticks"], gold[key + "/traj"]
     b = make_batch_estimator(agf, sc, n=5)
