@@ -101,6 +101,20 @@ STAGE_WAIT_FOR_START, STAGE_SPOOL_UP, STAGE_TAKEOFF, STAGE_FLIGHT, STAGE_LANDING
 OFFTRAJ_DOUBLES, OFFSTATE_DOUBLES = 29, 16
 
 
+class MsgSimulatorTruth(C.Structure):
+    _fields_ = [("vehicleID", C.c_int64)] + [(k, C.c_double) for k in (
+        "posx", "posy", "posz", "velx", "vely", "velz", "attyaw", "attpitch", "attroll", "attq0", "attq1", "attq2", "attq3",
+        "angvelx", "angvely", "angvelz")]
+
+
+class MsgTelemetry(C.Structure):
+    _fields_ = [("vehicleID", C.c_uint8), ("type", C.c_uint8), ("packetNumber", C.c_uint8), ("seqNum", C.c_uint8),
+                ("accelerometer", C.c_double * 3), ("rateGyro", C.c_double * 3), ("position", C.c_double * 3),
+                ("attitude", C.c_double * 3), ("velocity", C.c_double * 3), ("attitudeYPR", C.c_double * 3),
+                ("motorForces", C.c_double * 4), ("debugVals", C.c_double * 6), ("batteryVoltage", C.c_double),
+                ("panicReason", C.c_uint8), ("warnings", C.c_uint8)]
+
+
 class CsvRecord(C.Structure):
     _fields_ = [("t", C.c_double), ("pos", C.c_double * 3), ("vel", C.c_double * 3), ("att", C.c_double * 4),
                 ("ang_vel", C.c_double * 3), ("motor_forces", C.c_float * 4), ("est_pos", C.c_float * 3),
@@ -212,6 +226,9 @@ PROTOTYPES = {
     "agf_batch_set_offboard_reference": (C.c_int, [C.c_void_p, _P(OffboardRef)]),
     "agf_batch_set_offboard_trajectories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_batch_get_offboard_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_msg_simulator_truth_fill": (None, [C.c_int64, _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_double),
+                                            _P(MsgSimulatorTruth)]),
+    "agf_msg_telemetry_fill": (None, [C.c_void_p, C.c_void_p, _P(MsgTelemetry)]),
     "agf_csv_header": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "agf_csv_format_row": (C.c_size_t, [_P(CsvRecord), C.c_char_p, C.c_size_t]),
     "agf_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),

@@ -413,4 +413,55 @@ size_t agf_csv_format_row(const agf_csv_record* r, char* buf, size_t cap) {
   return o.len;
 }
 
+// ---- ROS message fields (AIFS_ROS/hiperlab_rostools/src/Simulator/main.cpp:455-475, 501-546) -----------------------
+void agf_msg_simulator_truth_fill(int64_t vehicle_id, const double pos[3], const double vel[3], const double att[4],
+                                  const double ang_vel[3], agf_msg_simulator_truth* o) {
+  memset(o, 0, sizeof(*o));
+  o->vehicleID = vehicle_id;
+  o->posx = pos[0]; o->posy = pos[1]; o->posz = pos[2];
+  o->velx = vel[0]; o->vely = vel[1]; o->velz = vel[2];
+  o->attq0 = att[0]; o->attq1 = att[1]; o->attq2 = att[2]; o->attq3 = att[3];
+  const double* v = att;  // Rotationd::ToEulerYPR (Rotation.hpp:163-169)
+  o->attyaw = atan2(2.0 * v[1] * v[2] + 2.0 * v[0] * v[3], v[1] * v[1] + v[0] * v[0] - v[3] * v[3] - v[2] * v[2]);
+  o->attpitch = -asin(2.0 * v[1] * v[3] - 2.0 * v[0] * v[2]);
+  o->attroll = atan2(2.0 * v[2] * v[3] + 2.0 * v[0] * v[1], v[3] * v[3] - v[2] * v[2] - v[1] * v[1] + v[0] * v[0]);
+  o->angvelx = ang_vel[0]; o->angvely = ang_vel[1]; o->angvelz = ang_vel[2];
+}
+
+void agf_msg_telemetry_fill(const uint8_t* packet1, const uint8_t* packet2, agf_msg_telemetry* o) {
+  memset(o, 0, sizeof(*o));
+  agf_telemetry p1, p2;
+  agf_telemetry_decode(packet1, &p1);
+  agf_telemetry_decode(packet2, &p2);
+  o->packetNumber = p1.packet_number;
+  for (int i = 0; i < 3; i++) {
+    o->accelerometer[i] = p1.accel[i];
+    o->rateGyro[i] = p1.gyro[i];
+    o->position[i] = p1.position[i];
+  }
+  for (int i = 0; i < 4; i++) o->motorForces[i] = p1.motor_forces[i];
+  o->batteryVoltage = p1.batt_voltage;
+  for (int i = 0; i < 6; i++) o->debugVals[i] = p2.debug_vals[i];
+  // Rotationf::FromVectorPartOfQuaternion (Rotation.hpp:112-121; the unit vector's norm is a float, Vec3.hpp:126-129)
+  float vx = p2.attitude[0], vy = p2.attitude[1], vz = p2.attitude[2];
+  float tmp = vx * vx + vy * vy + vz * vz;
+  if (tmp > 1.0f) {
+    const float nrm = sqrtf(tmp);
+    vx = vx / nrm; vy = vy / nrm; vz = vz / nrm;
+    tmp = 1.0f;
+  }
+  const float q[4] = {float(sqrt(1 - tmp)), vx, vy, vz};
+  const float y = atan2f(2.0f * q[1] * q[2] + 2.0f * q[0] * q[3], q[1] * q[1] + q[0] * q[0] - q[3] * q[3] - q[2] * q[2]);
+  const float pch = -asinf(2.0f * q[1] * q[3] - 2.0f * q[0] * q[2]);
+  const float r = atan2f(2.0f * q[2] * q[3] + 2.0f * q[0] * q[1], q[3] * q[3] - q[2] * q[2] - q[1] * q[1] + q[0] * q[0]);
+  const float ypr[3] = {y, pch, r};
+  for (int i = 0; i < 3; i++) {
+    o->velocity[i] = p2.velocity[i];
+    o->attitude[i] = p2.attitude[i];
+    o->attitudeYPR[i] = ypr[i];
+  }
+  o->panicReason = p2.panic_reason;
+  o->warnings = p2.warnings;
+}
+
 }  // extern "C"

@@ -198,6 +198,26 @@ typedef struct agf_csv_record {
 size_t agf_csv_header(char* buf, size_t cap);
 size_t agf_csv_format_row(const agf_csv_record* r, char* buf, size_t cap);
 
+/* ---- ROS message fields: what the hiperlab_rostools Simulator node publishes per vehicle ----------
+ * simulator_truth (AIFS_ROS/hiperlab_rostools/msg/simulator_truth.msg, filled at Simulator/main.cpp:455-475) and telemetry
+ * (msg/telemetry.msg, filled at Simulator/main.cpp:501-546 from the two decoded downlink packets; attitudeYPR through
+ * Rotationf::FromVectorPartOfQuaternion + ToEulerYPR).  Plain structs with the messages' fields in order, headers left to the
+ * caller (there is no ROS here). */
+typedef struct agf_msg_simulator_truth {
+  int64_t vehicleID;
+  double posx, posy, posz, velx, vely, velz, attyaw, attpitch, attroll, attq0, attq1, attq2, attq3, angvelx, angvely, angvelz;
+} agf_msg_simulator_truth;
+typedef struct agf_msg_telemetry {
+  uint8_t vehicleID, type, packetNumber, seqNum;
+  double accelerometer[3], rateGyro[3], position[3], attitude[3], velocity[3], attitudeYPR[3], motorForces[4], debugVals[6],
+      batteryVoltage;
+  uint8_t panicReason, warnings;
+} agf_msg_telemetry;
+void agf_msg_simulator_truth_fill(int64_t vehicle_id, const double pos[3], const double vel[3], const double att[4],
+                                  const double ang_vel[3], agf_msg_simulator_truth* out);
+void agf_msg_telemetry_fill(const uint8_t packet1[AGF_TELEMETRY_PACKET_SIZE], const uint8_t packet2[AGF_TELEMETRY_PACKET_SIZE],
+                            agf_msg_telemetry* out);
+
 /* ---- the batched handle -------------------------------------------------- */
 typedef struct agf_batch agf_batch;
 

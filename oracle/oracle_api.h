@@ -98,6 +98,9 @@ void orc_get_stages_node_state(orc_vehicle* v, double* out /* [AGF_OFFSTATE_DOUB
 /* Offboard::MocapStateEstimator in the loop (agf_offboard_estimator); NULL: back to the true state */
 void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* est);
 void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* est13, double* counters4 /* or NULL */);
+/* ROS telemetry / simulator_truth message fields through the reference's own types (ref flavours only) */
+void orc_msg_telemetry(const uint8_t* raw1, const uint8_t* raw2, agf_msg_telemetry* out);
+void orc_msg_simulator_truth(orc_vehicle* v, agf_msg_simulator_truth* out);
 /* simulation.csv row through the reference's own stream operators and Euler conversion (ref flavours only) */
 size_t orc_csv_row(const agf_csv_record* r, char* buf, size_t cap);
 void orc_get_full(orc_vehicle* v, orc_full_state* out);

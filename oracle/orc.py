@@ -120,6 +120,9 @@ class Oracle:
             L.orc_run_stages_node.argtypes = [vp, C.c_uint32, C.c_uint32, P(abi.OffboardCfg), P(abi.OffboardRef),
                                               P(abi.OffboardEstimator), C.c_int, C.c_void_p]
             L.orc_get_stages_node_state.argtypes = [vp, C.c_void_p]
+        if hasattr(L, "orc_msg_telemetry"):
+            L.orc_msg_telemetry.argtypes = [C.c_void_p, C.c_void_p, P(abi.MsgTelemetry)]
+            L.orc_msg_simulator_truth.argtypes = [vp, P(abi.MsgSimulatorTruth)]
         if hasattr(L, "orc_csv_row"):
             L.orc_csv_row.restype = C.c_size_t
             L.orc_csv_row.argtypes = [P(abi.CsvRecord), C.c_char_p, C.c_size_t]

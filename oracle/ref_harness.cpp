@@ -47,6 +47,7 @@
 #undef private
 #undef protected
 
+#include "hiperlab_rostools/telemetry.h"
 #include "oracle_api.h"
 
 #ifndef ORC_FLAVOUR
@@ -650,6 +651,57 @@ size_t orc_csv_row(const agf_csv_record* r, char* buf, size_t cap) {
     buf[cap - 1] = 0;
   }
   return s.size();
+}
+
+// The telemetry and simulator_truth messages as the ROS Simulator node fills them (AIFS_ROS/hiperlab_rostools/src/Simulator/
+// main.cpp:455-475, 501-546; that file itself needs AirSim, Boost and cv_bridge): the same statements on the reference's own
+// TelemetryPacket / Rotation types and the shim's message structs.
+void orc_msg_telemetry(const uint8_t* raw1, const uint8_t* raw2, agf_msg_telemetry* o) {
+  TelemetryPacket::data_packet_t dataPacketRaw1, dataPacketRaw2;
+  memcpy(&dataPacketRaw1, raw1, AGF_TELEMETRY_PACKET_SIZE);
+  memcpy(&dataPacketRaw2, raw2, AGF_TELEMETRY_PACKET_SIZE);
+  TelemetryPacket::TelemetryPacket dataPacket1, dataPacket2;
+  TelemetryPacket::DecodeTelemetryPacket(dataPacketRaw1, dataPacket1);
+  TelemetryPacket::DecodeTelemetryPacket(dataPacketRaw2, dataPacket2);
+  hiperlab_rostools::telemetry telMsgOut;
+  telMsgOut.packetNumber = dataPacket1.packetNumber;
+  for (int i = 0; i < 3; i++) {
+    telMsgOut.accelerometer[i] = dataPacket1.accel[i];
+    telMsgOut.rateGyro[i] = dataPacket1.gyro[i];
+    telMsgOut.position[i] = dataPacket1.position[i];
+  }
+  for (int i = 0; i < 4; i++) telMsgOut.motorForces[i] = dataPacket1.motorForces[i];
+  telMsgOut.batteryVoltage = dataPacket1.battVoltage;
+  for (int i = 0; i < TelemetryPacket::TelemetryPacket::NUM_DEBUG_FLOATS; i++) telMsgOut.debugVals[i] = dataPacket2.debugVals[i];
+  Vec3f attYPR = Rotationf::FromVectorPartOfQuaternion(
+      Vec3f(dataPacket2.attitude[0], dataPacket2.attitude[1], dataPacket2.attitude[2])).ToEulerYPR();
+  for (int i = 0; i < 3; i++) {
+    telMsgOut.velocity[i] = dataPacket2.velocity[i];
+    telMsgOut.attitude[i] = dataPacket2.attitude[i];
+    telMsgOut.attitudeYPR[i] = attYPR[i];
+  }
+  telMsgOut.panicReason = dataPacket2.panicReason;
+  telMsgOut.warnings = dataPacket2.warnings;
+  memset(o, 0, sizeof(*o));
+  o->packetNumber = telMsgOut.packetNumber;
+  for (int i = 0; i < 3; i++) {
+    o->accelerometer[i] = telMsgOut.accelerometer[i]; o->rateGyro[i] = telMsgOut.rateGyro[i]; o->position[i] = telMsgOut.position[i];
+    o->attitude[i] = telMsgOut.attitude[i]; o->velocity[i] = telMsgOut.velocity[i]; o->attitudeYPR[i] = telMsgOut.attitudeYPR[i];
+  }
+  for (int i = 0; i < 4; i++) o->motorForces[i] = telMsgOut.motorForces[i];
+  for (int i = 0; i < 6; i++) o->debugVals[i] = telMsgOut.debugVals[i];
+  o->batteryVoltage = telMsgOut.batteryVoltage;
+  o->panicReason = telMsgOut.panicReason;
+  o->warnings = telMsgOut.warnings;
+}
+void orc_msg_simulator_truth(orc_vehicle* v, agf_msg_simulator_truth* o) {
+  memset(o, 0, sizeof(*o));
+  o->posx = v->quad->GetPosition().x; o->posy = v->quad->GetPosition().y; o->posz = v->quad->GetPosition().z;
+  o->velx = v->quad->GetVelocity().x; o->vely = v->quad->GetVelocity().y; o->velz = v->quad->GetVelocity().z;
+  o->attq0 = v->quad->GetAttitude()[0]; o->attq1 = v->quad->GetAttitude()[1];
+  o->attq2 = v->quad->GetAttitude()[2]; o->attq3 = v->quad->GetAttitude()[3];
+  v->quad->GetAttitude().ToEulerYPR(o->attyaw, o->attpitch, o->attroll);
+  o->angvelx = v->quad->GetAngularVelocity().x; o->angvely = v->quad->GetAngularVelocity().y; o->angvelz = v->quad->GetAngularVelocity().z;
 }
 
 void orc_get_full(orc_vehicle* v, orc_full_state* o) {

@@ -258,6 +258,33 @@ def test_simulation_csv_rows_match_reference_stream_output(agf, orc_mod):
     assert rows == 60
 
 
+def test_ros_message_fields_match_the_simulator_node_statements(agf, orc_mod):
+    """the fields of the hiperlab_rostools telemetry and simulator_truth messages.  agf_msg_*_fill against the
+    Simulator node's own statements (Simulator/main.cpp:455-475, 501-546) executed on the reference's TelemetryPacket /
+    Rotation types in the harness, byte for byte, on packets and states taken from a flight."""
+    import ctypes as C
+    R = oracle_or_skip(orc_mod, "ref-glibc")
+    sc = agf.scenarios.full_scenario(agf.codec, nticks=1500)
+    v = R.vehicle(agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"]),
+                  uwb_comm_period=sc["uwb_comm_period"])
+    v.set_state(pos=sc["pos"], att=sc["att"])
+    for i, p in sc["anchors"]:
+        v.add_anchor(i, p)
+    d3 = lambda a: (C.c_double * len(a))(*[float(x) for x in a])
+    for k in range(30):
+        tr = v.run(50, sched=[e for e in sc["sched"]])[-1]
+        p1, p2 = v.telemetry()
+        mine, ref = agf.abi.MsgTelemetry(), agf.abi.MsgTelemetry()
+        agf.lib().agf_msg_telemetry_fill(p1.ctypes.data, p2.ctypes.data, C.byref(mine))
+        R.L.orc_msg_telemetry(p1.ctypes.data, p2.ctypes.data, C.byref(ref))
+        assert bytes(mine) == bytes(ref), k
+        st_mine, st_ref = agf.abi.MsgSimulatorTruth(), agf.abi.MsgSimulatorTruth()
+        agf.lib().agf_msg_simulator_truth_fill(0, d3(tr[0:3]), d3(tr[3:6]), d3(tr[6:10]), d3(tr[10:13]), C.byref(st_mine))
+        R.L.orc_msg_simulator_truth(v.h, C.byref(st_ref))
+        assert bytes(st_mine) == bytes(st_ref), k
+    assert abs(mine.position[2] - tr[2]) < 0.1 and mine.motorForces[0] > 0.05  # it flies, and the fields are the flight's
+
+
 def test_reference_golden_still_reproducible(agf, orc_mod):
     """The committed vectors are what the reference build in this container produces today."""
     R = oracle_or_skip(orc_mod, "ref-glibc")
