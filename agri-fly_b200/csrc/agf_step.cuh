@@ -401,7 +401,10 @@ AGF_DEV void box_muller21(uint32_t f1, uint32_t f2, float& n0, float& n1) {
 // 6 standard normals for (vehicle, cycle, stream): ONE Philox4x32-10 block, its 128 bits cut into six 21-bit fields
 AGF_DEV void normals6(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream, float* n) {
   const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
-  const uint4 r = philox4x32<10>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream), key);
+#ifndef AGF_PHILOX_ROUNDS
+#define AGF_PHILOX_ROUNDS 10
+#endif
+  const uint4 r = philox4x32<AGF_PHILOX_ROUNDS>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream), key);
   const uint32_t m = 0x1FFFFFu;
   box_muller21(r.x & m, ((r.x >> 21) | (r.y << 11)) & m, n[0], n[1]);
   box_muller21((r.y >> 10) & m, r.z & m, n[2], n[3]);
