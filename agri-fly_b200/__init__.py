@@ -552,6 +552,15 @@ class Rappids:
         _check(lib().agf_rappids_get_tracking_primitives(self._h, out.ctypes.data, first, count))
         return out
 
+    def export_tracking_primitives(self, batch, att=None, offset=None, dst_first=0):
+        """Writes the planned primitives into `batch`'s trajectory table on the device (no host hop)."""
+        ptr, nv = C.c_void_p(), C.c_size_t()
+        _check(batch.L.agf_batch_offboard_trajectories_device_ptr(batch.h, C.byref(ptr), C.byref(nv)))
+        a = None if att is None else np.ascontiguousarray(att, dtype=np.float64).reshape(self.n, 4)
+        o = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64).reshape(self.n, 3)
+        _check(lib().agf_rappids_export_tracking_primitives(self._h, ptr, nv.value, dst_first, None if a is None else a.ctypes.data,
+                                                            None if o is None else o.ctypes.data))
+
     def candidate_flags(self, first=0, count=None):
         count = self._cnt(first, count)
         out = np.zeros((count, self.k), dtype=np.uint8)

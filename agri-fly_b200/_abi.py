@@ -189,6 +189,7 @@ PROTOTYPES = {
     "agf_rappids_get_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_rappids_get_candidate_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_rappids_get_tracking_primitives": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_rappids_export_tracking_primitives": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "agf_rappids_get_pyramids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_rappids_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "agf_rappids_reduce_stats_device": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -225,6 +226,7 @@ PROTOTYPES = {
     "agf_offboard_ref_safety_default": (None, [_P(OffboardRef)]),
     "agf_batch_set_offboard_reference": (C.c_int, [C.c_void_p, _P(OffboardRef)]),
     "agf_batch_set_offboard_trajectories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_batch_offboard_trajectories_device_ptr": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_size_t)]),
     "agf_batch_get_offboard_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_msg_simulator_truth_fill": (None, [C.c_int64, _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_double),
                                             _P(MsgSimulatorTruth)]),

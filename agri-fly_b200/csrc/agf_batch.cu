@@ -332,6 +332,7 @@ struct Batch {
   virtual int set_offboard_ref(const agf_offboard_ref* ref) = 0;
   virtual int set_offboard_traj(const double* traj, size_t first, size_t count) = 0;
   virtual int get_offboard_state(double* out, size_t first, size_t count) = 0;
+  virtual int offboard_traj_ptr(double** p, size_t* nv) = 0;
   virtual int set_offboard_estimator(const agf_offboard_estimator* e) = 0;
   virtual int get_offboard_estimate(double horizon, double* est13, double* counters4, size_t first, size_t count) = 0;
 
@@ -881,6 +882,18 @@ struct BatchImpl : Batch {
     }
     return AGF_OK;
   }
+  int offboard_traj_ptr(double** p, size_t* nv) override {
+    if (!p) return fail(AGF_EINVAL, "null output");
+    AGF_CUDA(cudaSetDevice(opts.device));
+    if (!d_off_traj) {
+      AGF_CUDA(cudaMalloc(&d_off_traj, size_t(AGF_OFFTRAJ_DOUBLES) * n * sizeof(double)));
+      AGF_CUDA(cudaMemset(d_off_traj, 0, size_t(AGF_OFFTRAJ_DOUBLES) * n * sizeof(double)));
+      sh.off.traj = d_off_traj;
+    }
+    *p = d_off_traj;
+    if (nv) *nv = n;
+    return AGF_OK;
+  }
   int get_offboard_state(double* out, size_t first, size_t count) override {
     if (!out) return fail(AGF_EINVAL, "null output");
     if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
@@ -1351,6 +1364,9 @@ int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref) 
 }
 int agf_batch_set_offboard_trajectories(agf_batch* b, const double* traj, size_t first, size_t count) {
   return b ? B(b)->set_offboard_traj(traj, first, count) : fail(AGF_EINVAL, "null handle");
+}
+int agf_batch_offboard_trajectories_device_ptr(agf_batch* b, double** dev_ptr, size_t* n_vehicles) {
+  return b ? B(b)->offboard_traj_ptr(dev_ptr, n_vehicles) : fail(AGF_EINVAL, "null handle");
 }
 int agf_batch_get_offboard_state(agf_batch* b, double* out, size_t first, size_t count) {
   return b ? B(b)->get_offboard_state(out, first, count) : fail(AGF_EINVAL, "null handle");

@@ -97,6 +97,29 @@ __global__ void groupmin_kernel(uint16_t* __restrict__ out, const uint16_t* __re
   }
 }
 
+// agf_rappids_export_tracking_primitives: one thread per vehicle, field-major destination
+__global__ void export_prims_kernel(const double* __restrict__ prims, const double* __restrict__ state,
+                                    const agf_rappids_result* __restrict__ res, const double* __restrict__ att,
+                                    const double* __restrict__ offset, size_t n, double* __restrict__ dst, size_t n_dst, size_t dst_first) {
+  const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  double r[AGF_OFFTRAJ_DOUBLES];
+  for (int a = 0; a < 3; a++) {
+    r[6 * a + 0] = 0.0;
+    r[6 * a + 1] = state[v * 12 + a];
+    r[6 * a + 2] = state[v * 12 + 3 + a];
+    r[6 * a + 3] = prims[v * 9 + 3 * a];
+    r[6 * a + 4] = prims[v * 9 + 3 * a + 1];
+    r[6 * a + 5] = prims[v * 9 + 3 * a + 2];
+    r[18 + a] = state[v * 12 + 6 + a];
+    r[26 + a] = offset ? offset[v * 3 + a] : 0.0;
+  }
+  r[21] = res[v].found ? res[v].best_tf : 0.0;
+  r[22] = att ? att[v * 4] : 1.0;
+  for (int a = 1; a < 4; a++) r[22 + a] = att ? att[v * 4 + a] : 0.0;
+  for (int k = 0; k < AGF_OFFTRAJ_DOUBLES; k++) dst[(size_t)k * n_dst + dst_first + v] = r[k];
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -613,6 +636,33 @@ int agf_rappids_get_tracking_primitives(agf_rappids* p, double* records, size_t 
     r[21] = res[i].found ? res[i].best_tf : 0.0;
     r[22] = 1.0; r[23] = r[24] = r[25] = 0.0;
   }
+  return AGF_OK;
+}
+
+int agf_rappids_export_tracking_primitives(agf_rappids* p, double* dev_dst, size_t n_dst, size_t dst_first, const double* att,
+                                           const double* offset) {
+  if (!p || !dev_dst) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (dst_first + h->n > n_dst) return fail(AGF_ERANGE, "destination table too small for this planner's vehicles");
+  AGFR_CUDA(cudaSetDevice(h->device));
+  const size_t ab = att ? h->n * 4 * sizeof(double) : 0, ob = offset ? h->n * 3 * sizeof(double) : 0;
+  double *d_att = nullptr, *d_off = nullptr;
+  if (ab + ob) {
+    if (int rc = h->ensure_stage(ab + ob)) return rc;
+    if (att) {
+      d_att = reinterpret_cast<double*>(h->stage);
+      AGFR_CUDA(cudaMemcpyAsync(d_att, att, ab, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (offset) {
+      d_off = reinterpret_cast<double*>(reinterpret_cast<char*>(h->stage) + ab);
+      AGFR_CUDA(cudaMemcpyAsync(d_off, offset, ob, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  export_prims_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, h->stream>>>(h->prims, h->state, h->results, d_att, d_off, h->n, dev_dst,
+                                                                            n_dst, dst_first);
+  AGFR_CUDA(cudaGetLastError());
+  h->launches += 1;
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
   return AGF_OK;
 }
 

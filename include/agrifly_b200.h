@@ -412,6 +412,9 @@ int agf_batch_set_offboard_reference(agf_batch* b, const agf_offboard_ref* ref);
  *   [26..28] trajOffset, world frame (main.cpp:522) */
 #define AGF_OFFTRAJ_DOUBLES 29
 int agf_batch_set_offboard_trajectories(agf_batch* b, const double* traj, size_t first, size_t count);
+/* Device pointer of the trajectory records, [AGF_OFFTRAJ_DOUBLES][n_vehicles] doubles (field-major), allocated on first use:
+ * for producers that already live on the GPU (agf_rappids_export_tracking_primitives, agrifly_b200_rappids.h). */
+int agf_batch_offboard_trajectories_device_ptr(agf_batch* b, double** dev_ptr, size_t* n_vehicles);
 /* Per-vehicle state of the reference generator, [count][AGF_OFFSTATE_DOUBLES]: stage, last stage, stage start
  * [us], position at take-off [3], last commanded position / velocity / acceleration [3 each], commanded yaw. */
 #define AGF_OFFSTATE_DOUBLES 16

@@ -121,6 +121,12 @@ int agf_rappids_get_results(agf_rappids* p, agf_rappids_result* out, size_t firs
  * gravity in the trajectory frame and the end time; trajAtt is written as identity and trajOffset as zero, to be filled in
  * by the caller (estState.att * depthCamAtt and estState.pos, main.cpp:519-522).  Vehicles without a trajectory get tf = 0. */
 int agf_rappids_get_tracking_primitives(agf_rappids* p, double* records, size_t first, size_t count);
+/* The same records written on the device, field-major [AGF_OFFTRAJ_DOUBLES][n_dst] (vehicle v of this planner -> column
+ * dst_first + v), straight into a step batch's trajectory table (agf_batch_offboard_trajectories_device_ptr): the planner's
+ * result reaches the tracking loop without a host hop.  att [n][4] / offset [n][3]: host arrays or NULL (identity / zero).
+ * Runs on the planner's stream; the call returns after the kernel has finished. */
+int agf_rappids_export_tracking_primitives(agf_rappids* p, double* dev_dst, size_t n_dst, size_t dst_first, const double* att,
+                                           const double* offset);
 /* TrajectoryTestResult of every candidate, [count][k] bytes (the `trajectories` vector of the reference call). */
 int agf_rappids_get_candidate_flags(agf_rappids* p, uint8_t* flags, size_t first, size_t count);
 /* GetPyramids(): [count][AGF_RAPPIDS_MAX_PYRAMIDS][AGF_RAPPIDS_PYRAMID_DOUBLES], depth order, unused records NaN. */

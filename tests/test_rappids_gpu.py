@@ -253,7 +253,7 @@ def test_planned_primitives_fly_in_the_tracking_loop(agf):
     polynomial exactly (alpha / 120 == t^5 coefficient, ...), and a population flying its planned primitives matches the
     oracle flying the same records bit for bit."""
     import orc
-    from common import cfg_for, make_batch_offboard_ref
+    from common import cfg_for, make_batch_offboard, make_batch_offboard_ref
     if not orc.available("port-shared"):
         pytest.skip("oracle port not built")
     n, k = 24, 256
@@ -266,6 +266,17 @@ def test_planned_primitives_fly_in_the_tracking_loop(agf):
         pl.sync()
         res = pl.results()
         rec = pl.tracking_primitives()
+        # the same records handed over on the device: planner -> the batch's trajectory table, no host hop
+        sc_dev = agf.scenarios.tracking_scenario(nticks=2600)
+        sc_dev["ref"] = dict(sc_dev["ref"], desired_pos=(0.0, 0.0, 2.0), start_us=3000000)
+        sc_dev["pos"] = (0.0, 0.0, 0.0)
+        sc_dev["primitive"] = None
+        bd = make_batch_offboard(agf, dict(sc_dev, targets=[(0, (0.0, 0.0, 0.0))]), n=n)
+        pl.export_tracking_primitives(bd, att=np.tile([0.5, -0.5, 0.5, -0.5], (n, 1)), offset=np.tile([0.0, 0.0, 2.0], (n, 1)))
+        bd.set_offboard_reference(**sc_dev["ref"])
+        bd.run(2600)
+        got_dev = bd.record()
+        bd.close()
     assert rec.shape == (n, agf.abi.OFFTRAJ_DOUBLES) and np.sum(res["found"]) >= n // 2
     for i in range(n):
         if not res[i]["found"]:
@@ -297,4 +308,5 @@ def test_planned_primitives_fly_in_the_tracking_loop(agf):
         v.set_state(pos=sc["pos"], att=sc["att"])
         ref = v.run_offboard_ref(2600, agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), trajectory=recs[j])
         assert bit_equal(got[j], ref[-1]), (j, got[j][0:3], ref[-1][0:3])
+        assert bit_equal(got_dev[fly[j]], ref[-1]), ("device hand-over", j)
         assert ref[-1, 35] == 0 and np.linalg.norm(ref[-1, 0:3] - np.array([0.0, 0.0, 2.0])) > 0.3  # it went somewhere
