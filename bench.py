@@ -311,7 +311,7 @@ def main():
         # ---- e2e: public API with host buffers -------------------------------------------------
         pin13 = torch.from_numpy(np.ascontiguousarray(init[:, 0:13])).pin_memory()  # the population's 6-DOF state, pinned host memory
         pos_out = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-        ke = max(2, min(K, 5))
+        ke = max(2, min(K, 20))
 
         def e2e_step():
             agf._check(b.L.agf_batch_set_state(b.h, pin13.data_ptr(), 0, n))  # H2D from pinned host memory, one copy
