@@ -34,15 +34,18 @@ def test_struct_sizes_match_header(agf, tmp_path):
     """ctypes mirrors have the layout the C compiler gives the header's structs."""
     import subprocess
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "agrifly_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "agrifly_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(agf_logic_consts),sizeof(agf_vehicle_cfg),sizeof(agf_cmd_entry),sizeof(agf_batch_opts),'
-                   'sizeof(agf_telemetry),sizeof(agf_offboard_cfg),sizeof(agf_offboard_target));return 0;}\n')
+                   'sizeof(agf_telemetry),sizeof(agf_offboard_cfg),sizeof(agf_offboard_target),sizeof(agf_offboard_ref),'
+                   'sizeof(agf_offboard_estimator),sizeof(agf_csv_record),sizeof(agf_msg_telemetry),'
+                   'sizeof(agf_msg_simulator_truth));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     A = agf.abi
     assert sizes == [C.sizeof(A.LogicConsts), C.sizeof(A.VehicleCfg), C.sizeof(A.CmdEntry), C.sizeof(A.BatchOpts),
-                     C.sizeof(A.Telemetry), C.sizeof(A.OffboardCfg), C.sizeof(A.OffboardTarget)]
+                     C.sizeof(A.Telemetry), C.sizeof(A.OffboardCfg), C.sizeof(A.OffboardTarget), C.sizeof(A.OffboardRef),
+                     C.sizeof(A.OffboardEstimator), C.sizeof(A.CsvRecord), C.sizeof(A.MsgTelemetry), C.sizeof(A.MsgSimulatorTruth)]
     assert agf.lib().agf_field_size(0) == 24 and agf.lib().agf_field_size(15) == 324
 
 
