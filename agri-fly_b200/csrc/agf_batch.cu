@@ -603,6 +603,8 @@ struct BatchImpl : Batch {
     L.log = d_log;
     L.log_stride = log_stride ? log_stride : 1;
     L.log_capacity = log_cap ? log_cap : 1;
+    L.log_first_off = L.log_stride - 1 - uint32_t(ticks % L.log_stride);
+    L.log_slot0 = uint32_t(((ticks + L.log_first_off + 1) / L.log_stride - 1) % L.log_capacity);
     L.first_global_index = opts.first_global_index;
     L.flags = d_flags;
     L.epoch = ++epoch;

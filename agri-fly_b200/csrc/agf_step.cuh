@@ -2407,8 +2407,9 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
     tick<P, PARITY, UWB, HK, OFFB>(s, sc, L.sh, pv, plan, L.now0_us + uint64_t(t) * L.dt_us, L.dt_us, abs_tick, gidx, i, L.n);
     if (L.log && --log_in == 0) {
       log_in = L.log_stride;
-      const uint64_t rec = (abs_tick + 1) / L.log_stride - 1;
-      P* base = L.log + (size_t(rec % L.log_capacity) * AGF_LOG_FIELDS) * L.n + i;
+      // ring slot from the launch-relative tick with 32-bit arithmetic (host: slot and tick offset of the launch's first record)
+      const uint32_t slot = (L.log_slot0 + (t - L.log_first_off) / L.log_stride) % L.log_capacity;
+      P* base = L.log + (size_t(slot) * AGF_LOG_FIELDS) * L.n + i;
 #pragma unroll
       for (int k = 0; k < 3; k++) { base[size_t(k) * L.n] = s.pos[k]; base[size_t(3 + k) * L.n] = s.vel[k]; base[size_t(10 + k) * L.n] = s.w[k]; }
 #pragma unroll

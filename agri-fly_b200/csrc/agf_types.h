@@ -384,6 +384,7 @@ struct StepLaunch {
   SlotArrays slots[AGF_MAX_CMD_SLOTS];
   P* log;  // [capacity][AGF_LOG_FIELDS][N] or null
   uint32_t log_stride, log_capacity;
+  uint32_t log_first_off, log_slot0;  // tick offset (within the launch) and ring slot of the launch's first record
   uint64_t first_global_index;
   // Work distribution (agf_step.cuh "balanced schedule"): the population is cut into nblocks vehicle blocks of
   // blockDim.x vehicles.  balanced == 0: CTA b steps block b for all nticks.  balanced == 1: the grid is one
