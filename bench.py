@@ -408,23 +408,27 @@ def main():
                                             traffic=None, vehicle_steps_per_s=sps,
                                             note="rates mode, %d vehicles, 17 floats logged per vehicle-step (68 B), ring of 32 records" % nl)
             bl.close()
-            # the in-kernel offboard loop: Rappids_Simulator's closed loop with the mocap estimator, FP32
-            try:
-                bo = agf.Batch(agf.vehicle_cfg(vehicle_id=1, motor_time_const=0.015), n, precision=agf.abi.PREC_FP32,
-                               math=agf.abi.MATH_FAST, device=local, stream=stream.cuda_stream, telemetry_warnings=False)
-                bo.set_offboard_loop(agf.offboard_cfg(5), [(0, (0.0, 0.0, 2.0)), (3000000, (1.0, -0.5, 2.5))])
-                bo.set_offboard_estimator(agf.offboard_estimator())
-                bo.run(S)
-                bo.sync()
-                bo.step_kernel_time()
-                bo.run(S)
-                bo.run(S)
-                k4, l4 = bo.step_kernel_time()
-                extras["fp32_offboard_loop_mocap"] = dict(vehicle_steps_per_s=n * S * l4 / (k4 * 1e-3), vehicles=n,
-                                                          note="rates mode + offboard position controller at 100 Hz + MocapStateEstimator at 200 Hz, in the kernel")
-                bo.close()
-            except Exception as ex:  # a secondary number must not take the headline down
-                extras["fp32_offboard_loop_mocap"] = dict(error=str(ex))
+            # the in-kernel offboard loop: Rappids_Simulator's closed loop, FP32, with the true state and with the
+            # mocap estimator feeding the controller
+            for key, with_est in (("fp32_offboard_loop_truth", False), ("fp32_offboard_loop_mocap", True)):
+                try:
+                    bo = agf.Batch(agf.vehicle_cfg(vehicle_id=1, motor_time_const=0.015), n, precision=agf.abi.PREC_FP32,
+                                   math=agf.abi.MATH_FAST, device=local, stream=stream.cuda_stream, telemetry_warnings=False)
+                    bo.set_offboard_loop(agf.offboard_cfg(5), [(0, (0.0, 0.0, 2.0)), (3000000, (1.0, -0.5, 2.5))])
+                    if with_est:
+                        bo.set_offboard_estimator(agf.offboard_estimator())
+                    bo.run(S)
+                    bo.sync()
+                    bo.step_kernel_time()
+                    bo.run(S)
+                    bo.run(S)
+                    k4, l4 = bo.step_kernel_time()
+                    extras[key] = dict(vehicle_steps_per_s=n * S * l4 / (k4 * 1e-3), vehicles=n,
+                                       note="rates mode + offboard position controller at 100 Hz in the kernel" +
+                                            (" + MocapStateEstimator at 200 Hz" if with_est else ", true state"))
+                    bo.close()
+                except Exception as ex:  # a secondary number must not take the headline down
+                    extras[key] = dict(error=str(ex))
         # C5: batched RAPPIDS planner (K6), HBM-latency-bound pixel scans
         try:
             nr, kr = 65536, 512  # BASELINE config 5: 64K vehicles
