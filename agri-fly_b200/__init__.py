@@ -428,6 +428,18 @@ class Batch:
         _check(self.L.agf_batch_reduce_stats(self.h, None if t is None else t.ctypes.data, out.ctypes.data))
         return out
 
+    def stats_nccl(self, comm, target=None):
+        """The population statistics over every rank of `comm` (an ncclComm_t as an int / c_void_p; None: this GPU only):
+        stats kernel + one all-gather + combine on the batch's stream, result on the host."""
+        out = np.zeros(abi.STATS_LEN)
+        t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
+        _check(self.L.agf_batch_reduce_stats_nccl(self.h, comm, None if t is None else t.ctypes.data, out.ctypes.data))
+        return out
+
+    def stats_nccl_device(self, comm, dev_ptr, target=None):
+        t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
+        _check(self.L.agf_batch_reduce_stats_nccl_device(self.h, comm, None if t is None else t.ctypes.data, dev_ptr))
+
     def stats_device(self, dev_ptr, target=None):
         t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
         _check(self.L.agf_batch_reduce_stats_device(self.h, None if t is None else t.ctypes.data, dev_ptr))
@@ -444,7 +456,8 @@ class Batch:
 
 RESULT_DTYPE = np.dtype([("found", "<i4"), ("best_index", "<i4"), ("n_generated", "<i4"), ("n_cost_checks", "<i4"),
                          ("n_collision_checks", "<i4"), ("n_velocity_checks", "<i4"), ("n_collision_free", "<i4"),
-                         ("n_pyramids", "<i4"), ("best_cost", "<f8"), ("best_coeffs", "<f8", (6, 3)), ("best_tf", "<f8")])
+                         ("n_pyramids", "<i4"), ("best_cost", "<f8"), ("best_coeffs", "<f8", (6, 3)), ("best_tf", "<f8"),
+                         ("pyramid_cap_hit", "<i4"), ("reserved_", "<i4")])
 assert RESULT_DTYPE.itemsize == C.sizeof(abi.RappidsResult)
 
 

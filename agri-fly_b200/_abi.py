@@ -7,7 +7,8 @@ MAX_CMD_SLOTS = 4
 STATS_LEN = 16
 LOG_FIELDS = 17
 
-OK, EINVAL, ENOMEM, ECUDA, EUNSUPPORTED, ERANGE, ENODEVICE, EFULL = 0, -1, -2, -3, -4, -5, -6, -7
+OK, EINVAL, ENOMEM, ECUDA, EUNSUPPORTED, ERANGE, ENODEVICE, EFULL, ENCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
+NCCL_UNIQUE_ID_BYTES = 128
 
 QC_TYPE_INVALID, QC_TYPE_CF_STANDARD, QC_TYPE_CF_BIGMOTORSPROPS, QC_TYPE_CF_FEEDTHROUGH, \
     QC_TYPE_CF_LARGEQUAD, QC_TYPE_CF_MINIQUAD = range(6)
@@ -165,7 +166,8 @@ class RappidsResult(C.Structure):
     _fields_ = [("found", C.c_int32), ("best_index", C.c_int32), ("n_generated", C.c_int32),
                 ("n_cost_checks", C.c_int32), ("n_collision_checks", C.c_int32), ("n_velocity_checks", C.c_int32),
                 ("n_collision_free", C.c_int32), ("n_pyramids", C.c_int32), ("best_cost", C.c_double),
-                ("best_coeffs", C.c_double * 18), ("best_tf", C.c_double)]
+                ("best_coeffs", C.c_double * 18), ("best_tf", C.c_double),
+                ("pyramid_cap_hit", C.c_int32), ("reserved_", C.c_int32)]
 
 
 # every symbol include/agrifly_b200.h and include/agrifly_b200_rappids.h declare: name -> (restype, argtypes)
@@ -247,6 +249,13 @@ PROTOTYPES = {
     "agf_batch_log_device_ptr": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_size_t)]),
     "agf_batch_reduce_stats_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "agf_batch_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agf_batch_reduce_stats_nccl_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agf_batch_reduce_stats_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agf_nccl_version": (C.c_int, [_P(C.c_int)]),
+    "agf_nccl_get_unique_id": (C.c_int, [C.c_void_p]),
+    "agf_nccl_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_void_p)]),
+    "agf_nccl_comm_init_all": (C.c_int, [C.c_int, _P(C.c_int), _P(C.c_void_p)]),
+    "agf_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
     "agf_batch_launch_count": (C.c_uint64, [C.c_void_p]),
     "agf_batch_step_kernel_time": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_uint64)]),
     "agf_last_error_string": (C.c_char_p, []),

@@ -34,8 +34,9 @@ UNITS = [
     ("agf_rappids_plan.cu", "agf_rappids_plan_fast", ["-DAGF_RAPPIDS_PARITY=0"]),
     ("agf_rappids.cu", "agf_rappids", ["-fmad=false"]),
     ("agf_config.cpp", "agf_config", []),
+    ("agf_nccl.cpp", "agf_nccl", []),
 ]
-HEADERS = ["agf_step.cuh", "agf_types.h", "agf_math.h", "agf_launch.h", "agf_host_params.h", "agf_rappids_plan.cuh",
+HEADERS = ["agf_step.cuh", "agf_types.h", "agf_math.h", "agf_launch.h", "agf_host_params.h", "agf_rappids_plan.cuh", "agf_nccl.h",
            os.path.join(ROOT, "include", "agrifly_b200.h"), os.path.join(ROOT, "include", "agrifly_b200_rappids.h")]
 
 
@@ -80,7 +81,7 @@ def build_native(verbose=False, force=False):
         res = [f.result() for f in futs]
     objs = [r[0] for r in res]
     if any(r[1] for r in res) or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
@@ -109,7 +110,7 @@ def build_variant(name, defines, units=("agf_kernels_fast_f32_uwb",)):
         else:
             objs.append(os.path.join(BUILD, stem + ".o"))
     out = os.path.join(vdir, "libagrifly_b200_%s.so" % name)
-    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-cudart", "static"], capture_output=True, text=True)
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-cudart", "static", "-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     for o in objs:

@@ -21,6 +21,7 @@
 #include "agf_host_params.h"
 #include "agf_launch.h"
 #include "agf_math.h"
+#include "agf_nccl.h"
 #include "agf_types.h"
 #include "agrifly_b200.h"
 
@@ -117,19 +118,21 @@ __global__ void field_set_kernel(FieldCtx<P> c, int field, int ncomp, size_t fir
   if (t >= count * ncomp) return;
   const size_t i = first + t / ncomp;
   const int comp = int(t % ncomp);
-  const double d = ((const double*)in)[t];
-  const float f = ((const float*)in)[t];
+  // the staged buffer holds doubles for the plant fields and floats for the logic fields (field_elem): read it with
+  // the element type of the field only -- a double read of a float-sized stage would run past its end
+  const double* ind = (const double*)in;
+  const float* inf = (const float*)in;
   switch (field) {
-    case AGF_F_POSITION: c.sp[sidx(SP_POS + comp, c.n, i, VP)] = P(d); break;
-    case AGF_F_VELOCITY: c.sp[sidx(SP_VEL + comp, c.n, i, VP)] = P(d); break;
-    case AGF_F_ATTITUDE: c.sp[sidx(SP_ATT + comp, c.n, i, VP)] = P(d); break;
-    case AGF_F_ANGULAR_VELOCITY: c.sp[sidx(SP_W + comp, c.n, i, VP)] = P(d); break;
-    case AGF_F_MOTOR_SPEED: c.sp[sidx(SP_MS + comp, c.n, i, VP)] = P(d); break;
-    case AGF_F_MOTOR_SPEED_CMD: c.sf[sidx(SF_CMD + comp, c.n, i, 4)] = f; break;
-    case AGF_F_EST_POSITION: c.sf[sidx(SF_KPOS + comp, c.n, i, 4)] = f; break;
-    case AGF_F_EST_VELOCITY: c.sf[sidx(SF_KVEL + comp, c.n, i, 4)] = f; break;
-    case AGF_F_EST_ATTITUDE: c.sf[sidx(SF_KATT + comp, c.n, i, 4)] = f; break;
-    case AGF_F_EST_ANGULAR_VELOCITY: c.sf[sidx(SF_KW + comp, c.n, i, 4)] = f; break;
+    case AGF_F_POSITION: c.sp[sidx(SP_POS + comp, c.n, i, VP)] = P(ind[t]); break;
+    case AGF_F_VELOCITY: c.sp[sidx(SP_VEL + comp, c.n, i, VP)] = P(ind[t]); break;
+    case AGF_F_ATTITUDE: c.sp[sidx(SP_ATT + comp, c.n, i, VP)] = P(ind[t]); break;
+    case AGF_F_ANGULAR_VELOCITY: c.sp[sidx(SP_W + comp, c.n, i, VP)] = P(ind[t]); break;
+    case AGF_F_MOTOR_SPEED: c.sp[sidx(SP_MS + comp, c.n, i, VP)] = P(ind[t]); break;
+    case AGF_F_MOTOR_SPEED_CMD: c.sf[sidx(SF_CMD + comp, c.n, i, 4)] = inf[t]; break;
+    case AGF_F_EST_POSITION: c.sf[sidx(SF_KPOS + comp, c.n, i, 4)] = inf[t]; break;
+    case AGF_F_EST_VELOCITY: c.sf[sidx(SF_KVEL + comp, c.n, i, 4)] = inf[t]; break;
+    case AGF_F_EST_ATTITUDE: c.sf[sidx(SF_KATT + comp, c.n, i, 4)] = inf[t]; break;
+    case AGF_F_EST_ANGULAR_VELOCITY: c.sf[sidx(SF_KW + comp, c.n, i, 4)] = inf[t]; break;
     default: break;
   }
 }
@@ -259,6 +262,18 @@ __device__ inline void atomic_max_double(double* addr, double v) {  // v >= 0
   } while (assumed != old);
 }
 
+// the all-gathered statistics vectors of every rank -> one vector, in rank order (deterministic, the same bits on every rank)
+__global__ void stats_combine_kernel(const double* gathered, int nranks, double* out) {
+  const int k = threadIdx.x;
+  if (k >= AGF_STATS_LEN) return;
+  double r = gathered[k];
+  for (int q = 1; q < nranks; q++) {
+    const double v = gathered[q * AGF_STATS_LEN + k];
+    r = k >= AGF_ST_MAX_ENORM ? fmax(r, v) : r + v;
+  }
+  out[k] = r;
+}
+
 template<typename P>
 __global__ void stats_kernel(const P* sp, const float* sf, const uint32_t* su, size_t n, const double* target, double* out) {
   constexpr int VP = VecOf<P>::lanes;
@@ -342,11 +357,153 @@ struct Batch {
   bool own_stream = false;
   uint64_t now_us = 0, ticks = 0, launches = 0;
   uint64_t log_records = 0;
+  // Step-kernel timing (agf_batch_step_kernel_time): a fixed ring of event pairs.  When the ring is full the oldest
+  // pair -- EVENT_RING launches old, long complete -- is folded into the running totals, so an object-API caller that
+  // steps one tick per launch for hours never grows the handle (round-1 advice: two events leaked per launch).
+  enum { EVENT_RING = 64 };
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
-  size_t events_used = 0;
+  size_t ev_head = 0, ev_count = 0;  // ring of pending pairs: [ev_head, ev_head + ev_count)
+  double timed_ms = 0;
+  uint64_t timed_launches = 0;
+
+  int fold_oldest_event() {
+    auto& e = events[ev_head];
+    float t = 0;
+    AGF_CUDA(cudaEventSynchronize(e.second));
+    AGF_CUDA(cudaEventElapsedTime(&t, e.first, e.second));
+    timed_ms += t;
+    timed_launches++;
+    ev_head = (ev_head + 1) % EVENT_RING;
+    ev_count--;
+    return AGF_OK;
+  }
+  // the pair that brackets the next launch
+  int next_event_pair(std::pair<cudaEvent_t, cudaEvent_t>** out) {
+    if (events.size() < size_t(EVENT_RING) && ev_count == events.size()) {
+      cudaEvent_t a, b;
+      AGF_CUDA(cudaEventCreate(&a));
+      AGF_CUDA(cudaEventCreate(&b));
+      events.push_back({a, b});
+    } else if (ev_count == size_t(EVENT_RING)) {
+      int rc = fold_oldest_event();
+      if (rc) return rc;
+    }
+    *out = &events[(ev_head + ev_count) % EVENT_RING];
+    ev_count++;
+    return AGF_OK;
+  }
+  int drain_events(double* ms, uint64_t* n_launches) {
+    while (ev_count) {
+      int rc = fold_oldest_event();
+      if (rc) return rc;
+    }
+    if (ms) *ms = timed_ms;
+    if (n_launches) *n_launches = timed_launches;
+    timed_ms = 0;
+    timed_launches = 0;
+    return AGF_OK;
+  }
 
   int sync() {
     AGF_CUDA(cudaStreamSynchronize(stream));
+    return AGF_OK;
+  }
+
+  // ---- statistics read-out buffers, allocated once per handle (no cudaMalloc on the read-out path) ----
+  double* d_stats_local = nullptr;   // this GPU's AGF_STATS_LEN doubles
+  double* d_stats_gather = nullptr;  // [nranks][AGF_STATS_LEN]
+  double* d_stats_out = nullptr;     // combined vector when the caller wants it on the host
+  double* h_stats = nullptr;         // pinned
+  int gather_ranks = 0;
+  // the captured read-out (stats kernel -> all-gather -> combine) and what it was captured for
+  cudaGraphExec_t stats_graph = nullptr;
+  void* graph_comm = nullptr;
+  double* graph_out = nullptr;
+  uint64_t nccl_readouts = 0;
+  bool graph_disabled = false;
+
+  int ensure_stats_buffers(int nranks) {
+    if (!d_stats_local) AGF_CUDA(cudaMalloc(&d_stats_local, sizeof(double) * AGF_STATS_LEN));
+    if (!d_stats_out) AGF_CUDA(cudaMalloc(&d_stats_out, sizeof(double) * AGF_STATS_LEN));
+    if (!h_stats) AGF_CUDA(cudaMallocHost(&h_stats, sizeof(double) * AGF_STATS_LEN));
+    if (nranks > gather_ranks) {
+      cudaFree(d_stats_gather);
+      d_stats_gather = nullptr;
+      gather_ranks = 0;
+      AGF_CUDA(cudaMalloc(&d_stats_gather, sizeof(double) * AGF_STATS_LEN * size_t(nranks)));
+      gather_ranks = nranks;
+    }
+    return AGF_OK;
+  }
+  void free_stats_buffers() {
+    if (stats_graph) cudaGraphExecDestroy(stats_graph);
+    cudaFree(d_stats_local);
+    cudaFree(d_stats_gather);
+    cudaFree(d_stats_out);
+    if (h_stats) cudaFreeHost(h_stats);
+  }
+
+  // stats kernel + ONE all-gather + combine on this handle's stream (include/agrifly_b200.h "multi-GPU")
+  int stats_nccl(void* comm, const double* target, double* dev_out) {
+    if (!comm) return stats(target, dev_out);
+    const char* why = "";
+    const NcclApi* api = nccl_api(&why);
+    if (!api) return fail(AGF_ENCCL, why);
+    AGF_CUDA(cudaSetDevice(opts.device));
+    int nranks = 0;
+    int rc = api->CommCount(reinterpret_cast<NcclComm>(comm), &nranks);
+    if (rc != kNcclSuccess || nranks < 1) return fail(AGF_ENCCL, "ncclCommCount failed");
+    int e = ensure_stats_buffers(nranks);
+    if (e) return e;
+    auto body = [&](const double* tgt) -> int {
+      int r = stats(tgt, d_stats_local);
+      if (r) return r;
+      const int nr = api->AllGather(d_stats_local, d_stats_gather, AGF_STATS_LEN, kNcclFloat64, reinterpret_cast<NcclComm>(comm), stream);
+      if (nr != kNcclSuccess) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "ncclAllGather: %s", api->GetErrorString(nr));
+        return fail(AGF_ENCCL, buf);
+      }
+      stats_combine_kernel<<<1, 32, 0, stream>>>(d_stats_gather, nranks, dev_out);
+      AGF_CUDA(cudaGetLastError());
+      launches++;
+      return AGF_OK;
+    };
+    nccl_readouts++;
+    if (target || graph_disabled) return body(target);  // a host target is staged per call: not captured
+    if (stats_graph && graph_comm == comm && graph_out == dev_out) {
+      AGF_CUDA(cudaGraphLaunch(stats_graph, stream));
+      launches += 2;
+      return AGF_OK;
+    }
+    if (nccl_readouts < 2) return body(nullptr);  // first read-out eagerly: NCCL sets its connections up outside a capture
+    // capture the three operations once; any refusal falls back to eager launches for good
+    if (stats_graph) {
+      cudaGraphExecDestroy(stats_graph);
+      stats_graph = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      graph_disabled = true;
+      return body(nullptr);
+    }
+    const uint64_t l0 = launches;
+    const int r = body(nullptr);
+    const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+    launches = l0;
+    if (r || ce != cudaSuccess || !g || cudaGraphInstantiate(&stats_graph, g, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      stats_graph = nullptr;
+      graph_disabled = true;
+      return body(nullptr);
+    }
+    cudaGraphDestroy(g);
+    graph_comm = comm;
+    graph_out = dev_out;
+    AGF_CUDA(cudaGraphLaunch(stats_graph, stream));
+    launches += 2;
     return AGF_OK;
   }
 };
@@ -424,6 +581,7 @@ struct BatchImpl : Batch {
     cudaFree(d_sched); cudaFree(d_log); cudaFree(d_stage); cudaFree(d_target); cudaFree(d_off_targets); cudaFree(d_off_offsets); cudaFree(d_off_state); cudaFree(d_off_traj); cudaFree(d_off_est); cudaFree(d_plans); cudaFree(st.sq);
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { cudaFree(d_slot_f[s]); cudaFree(d_slot_tf[s]); }
     for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    free_stats_buffers();
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 
@@ -609,18 +767,16 @@ struct BatchImpl : Batch {
     L.flags = d_flags;
     L.epoch = ++epoch;
 
-    if (events_used == events.size()) {
-      cudaEvent_t a, b;
-      AGF_CUDA(cudaEventCreate(&a));
-      AGF_CUDA(cudaEventCreate(&b));
-      events.push_back({a, b});
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    {
+      int rc = next_event_pair(&ev);
+      if (rc) return rc;
     }
     const int block = opts.block_threads > 0 ? std::min(opts.block_threads, AGF_BLOCK_THREADS) : AGF_BLOCK_THREADS;
-    AGF_CUDA(cudaEventRecord(events[events_used].first, stream));
+    AGF_CUDA(cudaEventRecord(ev->first, stream));
     cudaError_t e = do_launch(L, block);
     if (e != cudaSuccess) return fail(AGF_ECUDA, "step kernel launch", e);
-    AGF_CUDA(cudaEventRecord(events[events_used].second, stream));
-    events_used++;
+    AGF_CUDA(cudaEventRecord(ev->second, stream));
     launches++;
     // carry the clock-only stopwatches across the launch with the same function the device uses
     for (uint32_t t = 0; t < nticks; t++) {
@@ -1417,20 +1573,26 @@ int agf_batch_reduce_stats_device(agf_batch* b, const double* target, double* de
   if (!b || !dev_out) return fail(AGF_EINVAL, "null argument");
   return B(b)->stats(target, dev_out);
 }
-int agf_batch_reduce_stats(agf_batch* b, const double* target, double* host_out) {
+int agf_batch_reduce_stats_nccl_device(agf_batch* b, void* nccl_comm, const double* target, double* dev_out) {
+  if (!b || !dev_out) return fail(AGF_EINVAL, "null argument");
+  return B(b)->stats_nccl(nccl_comm, target, dev_out);
+}
+int agf_batch_reduce_stats_nccl(agf_batch* b, void* nccl_comm, const double* target, double* host_out) {
   if (!b || !host_out) return fail(AGF_EINVAL, "null argument");
-  cudaSetDevice(B(b)->opts.device);
-  double* d = nullptr;
-  cudaError_t e = cudaMalloc(&d, sizeof(double) * AGF_STATS_LEN);
-  if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaMalloc", e);
-  int rc = B(b)->stats(target, d);
+  Batch* x = B(b);
+  cudaSetDevice(x->opts.device);
+  int rc = x->ensure_stats_buffers(1);
+  if (!rc) rc = x->stats_nccl(nccl_comm, target, x->d_stats_out);
   if (!rc) {
-    e = cudaMemcpyAsync(host_out, d, sizeof(double) * AGF_STATS_LEN, cudaMemcpyDeviceToHost, B(b)->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(B(b)->stream);
-    if (e != cudaSuccess) rc = fail(AGF_ECUDA, "stats copy", e);
+    cudaError_t e = cudaMemcpyAsync(x->h_stats, x->d_stats_out, sizeof(double) * AGF_STATS_LEN, cudaMemcpyDeviceToHost, x->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(x->stream);
+    if (e != cudaSuccess) return fail(AGF_ECUDA, "stats copy", e);
+    memcpy(host_out, x->h_stats, sizeof(double) * AGF_STATS_LEN);
   }
-  cudaFree(d);
   return rc;
+}
+int agf_batch_reduce_stats(agf_batch* b, const double* target, double* host_out) {
+  return agf_batch_reduce_stats_nccl(b, nullptr, target, host_out);
 }
 
 uint64_t agf_batch_launch_count(const agf_batch* b) { return b ? B(b)->launches : 0; }
@@ -1441,17 +1603,7 @@ int agf_batch_step_kernel_time(agf_batch* b, double* ms, uint64_t* launches) {
   cudaSetDevice(x->opts.device);
   cudaError_t e = cudaStreamSynchronize(x->stream);
   if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaStreamSynchronize", e);
-  double total = 0;
-  for (size_t i = 0; i < x->events_used; i++) {
-    float t = 0;
-    e = cudaEventElapsedTime(&t, x->events[i].first, x->events[i].second);
-    if (e != cudaSuccess) return fail(AGF_ECUDA, "cudaEventElapsedTime", e);
-    total += t;
-  }
-  if (ms) *ms = total;
-  if (launches) *launches = x->events_used;
-  x->events_used = 0;
-  return AGF_OK;
+  return x->drain_events(ms, launches);
 }
 
 const char* agf_last_error_string(void) { return agf::g_last_error.c_str(); }

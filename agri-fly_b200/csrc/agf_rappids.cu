@@ -211,8 +211,25 @@ struct Handle {
   size_t stage_bytes = 0;
   int grid = 0, regs = 0, blocks_per_sm = 0;
   uint64_t launches = 0;
+  // planner-kernel timing: a fixed ring of event pairs; when it is full the oldest (long complete) pair is folded into
+  // the running totals, so a caller that plans at image rate for hours never grows the handle
+  enum { EVENT_RING = 32 };
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
-  size_t events_used = 0;
+  size_t ev_head = 0, ev_count = 0;
+  double timed_ms = 0;
+  uint64_t timed_launches = 0;
+  cudaError_t fold_oldest_event() {
+    auto& e = events[ev_head];
+    float t = 0;
+    cudaError_t r = cudaEventSynchronize(e.second);
+    if (r == cudaSuccess) r = cudaEventElapsedTime(&t, e.first, e.second);
+    if (r != cudaSuccess) return r;
+    timed_ms += t;
+    timed_launches++;
+    ev_head = (ev_head + 1) % EVENT_RING;
+    ev_count--;
+    return cudaSuccess;
+  }
 
   ~Handle() {
     cudaSetDevice(device);
@@ -335,8 +352,11 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   if (!h) return fail(AGF_ENOMEM, "host allocation");
   h->cfg = *cfg;
   h->cfg.device = dev;
-  if (h->cfg.max_pyramids <= 0 || h->cfg.max_pyramids > AGF_RAPPIDS_MAX_PYRAMIDS)
-    h->cfg.max_pyramids = AGF_RAPPIDS_MAX_PYRAMIDS;
+  if (h->cfg.max_pyramids > AGF_RAPPIDS_MAX_PYRAMIDS) {
+    delete h;
+    return fail(AGF_EUNSUPPORTED, "max_pyramids exceeds AGF_RAPPIDS_MAX_PYRAMIDS (device storage per vehicle)");
+  }
+  if (h->cfg.max_pyramids <= 0) h->cfg.max_pyramids = AGF_RAPPIDS_MAX_PYRAMIDS;  // "unlimited": see pyramid_cap_hit
   h->n = n;
   h->kcap = max_candidates;
   h->device = dev;
@@ -575,14 +595,17 @@ int agf_rappids_plan(agf_rappids* p) {
   P.edgeOff = (int)(c.focal_length * c.true_radius / c.min_checking_dist);
   P.ignore = (int)(uint16_t)(c.true_radius / c.depth_scale);
   P.num = (int)(c.focal_length * c.planning_radius / c.depth_scale);
-  if (h->events_used == h->events.size()) {
+  if (h->events.size() < size_t(Handle::EVENT_RING) && h->ev_count == h->events.size()) {
     cudaEvent_t a, b;
     AGFR_CUDA(cudaEventCreate(&a));
     AGFR_CUDA(cudaEventCreate(&b));
     h->events.emplace_back(a, b);
+  } else if (h->ev_count == size_t(Handle::EVENT_RING)) {
+    AGFR_CUDA(h->fold_oldest_event());
   }
   AGFR_CUDA(cudaMemsetAsync(h->next, 0, sizeof(int), h->stream));
-  auto& ev = h->events[h->events_used++];
+  auto& ev = h->events[(h->ev_head + h->ev_count) % Handle::EVENT_RING];
+  h->ev_count++;
   AGFR_CUDA(cudaEventRecord(ev.first, h->stream));
   cudaError_t e = (c.math == AGF_MATH_PARITY) ? agfr::launch_plan_parity(P, h->grid, h->stream)
                                               : agfr::launch_plan_fast(P, h->grid, h->stream);
@@ -715,15 +738,11 @@ int agf_rappids_plan_kernel_time(agf_rappids* p, double* ms, uint64_t* launches)
   Handle* h = H_(p);
   AGFR_CUDA(cudaSetDevice(h->device));
   AGFR_CUDA(cudaStreamSynchronize(h->stream));
-  double total = 0;
-  for (size_t i = 0; i < h->events_used; i++) {
-    float t = 0;
-    AGFR_CUDA(cudaEventElapsedTime(&t, h->events[i].first, h->events[i].second));
-    total += t;
-  }
-  *launches = h->events_used;
-  *ms = h->events_used ? total / (double)h->events_used : 0.0;
-  h->events_used = 0;
+  while (h->ev_count) AGFR_CUDA(h->fold_oldest_event());
+  *launches = h->timed_launches;
+  *ms = h->timed_launches ? h->timed_ms / (double)h->timed_launches : 0.0;
+  h->timed_ms = 0;
+  h->timed_launches = 0;
   return AGF_OK;
 }
 

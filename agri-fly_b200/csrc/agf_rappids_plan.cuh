@@ -69,6 +69,7 @@ struct ResultRec {  // == agf_rappids_result
   double best_cost;
   double best_coeffs[18];
   double best_tf;
+  int32_t pyramid_cap_hit, reserved_;
 };
 
 template<bool PARITY>
@@ -360,6 +361,7 @@ struct WarpCtx {
   double* pdepth;  // shared: [kMaxPyr] base-plane depths, ascending
   int4* pedge;     // shared: [kMaxPyr] (right, top, left, bottom)
   int npyr;
+  int capHit;  // a candidate needed a new pyramid when max_pyramids already existed (it was rejected, DepthImagePlanner.cpp:246-249)
   int lane;
 };
 
@@ -831,7 +833,10 @@ __device__ __noinline__ bool collision_free(const PlanParams& P, WarpCtx& w, con
         pdepth = w.pdepth[idx];
         pedge = w.pedge[idx];
       } else {
-        if (w.npyr >= P.maxPyr) return false;
+        if (w.npyr >= P.maxPyr) {
+          w.capHit = 1;
+          return false;
+        }
         // (int) of a double: the values reaching here are finite and small (the end point is deeper than minDist)
         if (!inflate(P, w, (int)px, (int)py, ez, pdepth, pedge)) return false;
         // insert in depth order (std::lower_bound on the new depth, :267-269)
@@ -922,6 +927,7 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
     w.gminR = P.gminR + (size_t)v * P.H * P.GW;
     w.gminC = P.gminC + (size_t)v * P.W * P.GH;
     w.npyr = 0;
+    w.capHit = 0;
     const double* st = P.state + (size_t)v * 12;
     Prim pr;
 #pragma unroll
@@ -1032,6 +1038,8 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
       out->n_pyramids = w.npyr;
       out->best_cost = best;
       out->best_tf = bestT;
+      out->pyramid_cap_hit = w.capHit;
+      out->reserved_ = 0;
     }
     if (lane < 18) out->best_coeffs[lane] = bestQ.c[lane / 3][lane % 3];
     if (P.prims) {  // the returned primitive in the generator's own variables: regenerated (same code, same inputs) rather than

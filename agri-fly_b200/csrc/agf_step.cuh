@@ -32,6 +32,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <mutex>
 
 #include "agf_math.h"
 #include "agf_types.h"
@@ -2498,44 +2500,57 @@ step_kernel(const __grid_constant__ StepLaunch<P> L) {
   }
 }
 
-// Host side of the schedule: one wave of co-resident CTAs when that is fewer than the vehicle blocks.
-// (CTAs are dispatched in index order and a CTA only ever waits, at the end of its work, for what its
-// lower-indexed neighbour does first, so the wait cannot deadlock even if the wave is not fully resident.)
+// Host side of the schedule: one wave of co-resident CTAs when that is fewer than the vehicle blocks.  A CTA waits, at
+// the end of its work, for what its lower-indexed neighbour does first; forward progress therefore needs the whole grid
+// resident, which only a COOPERATIVE launch guarantees (cudaLaunchCooperativeKernel refuses a grid that does not fit and
+// holds the launch back until it does, whatever else shares the GPU).  AGF_NO_BALANCED=1 in the environment, or a device
+// without cooperative launch, falls back to the plain one-CTA-per-block grid.
 template<typename P, typename K>
 static cudaError_t launch_step_kernel(K kernel, StepLaunch<P> L, int block, size_t smem, cudaStream_t stream) {
-  struct Cached { const void* fn; int block; size_t smem; int dev; int resident; int sms; };
-  static Cached cache[16];
+  struct Cached { const void* fn; int block; size_t smem; int dev; int resident; int sms; int coop; };
+  static Cached cache[32];
   static int ncached = 0;
+  static std::mutex cache_mutex;  // one host thread per GPU may launch concurrently (agrifly_b200.h "Threading")
+  static const bool no_balanced = [] { const char* e = getenv("AGF_NO_BALANCED"); return e && e[0] && e[0] != '0'; }();
   L.nblocks = uint32_t((L.n + block - 1) / block);
   L.balanced = 0;
   unsigned grid = L.nblocks;
-  if (L.flags && L.nticks > 1) {
+  if (L.flags && L.nticks > 1 && !no_balanced) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int resident = -1, sms = 0;
-    for (int k = 0; k < ncached; k++)
-      if (cache[k].fn == (const void*)kernel && cache[k].block == block && cache[k].smem == smem && cache[k].dev == dev) {
-        resident = cache[k].resident;
-        sms = cache[k].sms;
+    int resident = -1, sms = 0, coop = 0;
+    {
+      std::lock_guard<std::mutex> lock(cache_mutex);
+      for (int k = 0; k < ncached; k++)
+        if (cache[k].fn == (const void*)kernel && cache[k].block == block && cache[k].smem == smem && cache[k].dev == dev) {
+          resident = cache[k].resident;
+          sms = cache[k].sms;
+          coop = cache[k].coop;
+        }
+      if (resident < 0) {
+        int per_sm = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+        if (e != cudaSuccess) return e;
+        resident = sms * per_sm;
+        if (ncached < 32) cache[ncached++] = Cached{(const void*)kernel, block, smem, dev, resident, sms, coop};
       }
-    if (resident < 0) {
-      int per_sm = 0;
-      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
-      if (e != cudaSuccess) return e;
-      resident = sms * per_sm;
-      if (ncached < 16) cache[ncached++] = Cached{(const void*)kernel, block, smem, dev, resident, sms};
     }
-    if (resident > 0 && L.nblocks > unsigned(resident)) {
+    if (coop && resident > 0 && L.nblocks > unsigned(resident)) {
       L.balanced = 1;
       grid = unsigned(resident);
-    } else if (sms > 0 && L.nblocks > unsigned(sms) && L.nblocks % unsigned(sms) != 0) {
+    } else if (coop && sms > 0 && L.nblocks > unsigned(sms) && L.nblocks % unsigned(sms) != 0) {
       // fewer blocks than fit, but not a multiple of the SM count: the same number of CTAs on every SM, the block-ticks
       // dealt out evenly, instead of some SMs carrying one block more than the others for the whole launch
       L.balanced = 1;
       grid = (L.nblocks / unsigned(sms)) * unsigned(sms);
     }
+  }
+  if (L.balanced) {
+    void* args[] = {(void*)&L};
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(block), args, smem, stream);
   }
   kernel<<<grid, block, smem, stream>>>(L);
   return cudaGetLastError();

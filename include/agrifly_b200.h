@@ -41,6 +41,7 @@ extern "C" {
 #define AGF_EUNSUPPORTED (-4) /* valid request this build cannot serve          */
 #define AGF_ERANGE (-5)       /* index / count outside the batch                */
 #define AGF_ENODEVICE (-6)    /* no CUDA device: there is no CPU fallback       */
+#define AGF_ENCCL (-8)        /* NCCL unavailable or an NCCL call failed        */
 #define AGF_EFULL (-7)        /* table full (reference returns -1 likewise:
                                  QuadcopterLogic.hpp:224-227)                   */
 
@@ -507,6 +508,27 @@ enum {
  * torch.distributed / ncclAllReduce); asynchronous on the handle's stream. */
 int agf_batch_reduce_stats_device(agf_batch* b, const double* host_target, double* dev_out);
 int agf_batch_reduce_stats(agf_batch* b, const double* host_target, double host_out[AGF_STATS_LEN]);
+
+/* ---- multi-GPU: the statistics read-out over NCCL --------------------------------
+ * Vehicles shard by index range over one handle per GPU and nothing is exchanged inside the step; the one
+ * collective of the product is this read-out.  `nccl_comm` is an ncclComm_t (passed as void* so that this header
+ * needs no nccl.h) whose rank owns this batch's GPU, or NULL for a single GPU.  On the batch's stream: the
+ * statistics kernel, ONE ncclAllGather of the AGF_STATS_LEN doubles of every rank, and a combine kernel (entries
+ * below AGF_ST_MAX_ENORM are summed in rank order, the rest maximised), so every rank ends with the same bits.  From
+ * the second call on with the same (communicator, output pointer, no host target) the three are replayed as one
+ * captured CUDA graph.  Collective: every rank of the communicator must call it, one host thread per GPU. */
+int agf_batch_reduce_stats_nccl_device(agf_batch* b, void* nccl_comm, const double* host_target, double* dev_out);
+int agf_batch_reduce_stats_nccl(agf_batch* b, void* nccl_comm, const double* host_target, double host_out[AGF_STATS_LEN]);
+/* Communicator helpers for hosts that do not link NCCL themselves (libnccl.so.2 is resolved at run time; in a process
+ * that already carries an NCCL, e.g. torch's, that one is used).  agf_nccl_comm_init_rank = ncclCommInitRank on `device`
+ * with an id from agf_nccl_get_unique_id shared by the caller's own means (MPI, a file, torch.distributed);
+ * agf_nccl_comm_init_all = ncclCommInitAll for one process driving several GPUs with one thread each. */
+#define AGF_NCCL_UNIQUE_ID_BYTES 128
+int agf_nccl_version(int* version);
+int agf_nccl_get_unique_id(uint8_t id[AGF_NCCL_UNIQUE_ID_BYTES]);
+int agf_nccl_comm_init_rank(const uint8_t id[AGF_NCCL_UNIQUE_ID_BYTES], int nranks, int rank, int device, void** comm_out);
+int agf_nccl_comm_init_all(int ndev, const int* devices, void** comms_out /* [ndev] */);
+int agf_nccl_comm_destroy(void* comm);
 
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches claim) */
 uint64_t agf_batch_launch_count(const agf_batch* b);

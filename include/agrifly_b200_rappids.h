@@ -52,7 +52,10 @@ typedef struct agf_rappids_cfg {
   double focal_length, cx, cy;
   double true_radius, planning_radius, min_checking_dist;
   double min_thrust, max_thrust, max_angvel, min_section_time, max_velocity;
-  int32_t max_pyramids;                /* <= 0 or > AGF_RAPPIDS_MAX_PYRAMIDS: AGF_RAPPIDS_MAX_PYRAMIDS  */
+  int32_t max_pyramids;                /* 1 .. AGF_RAPPIDS_MAX_PYRAMIDS: SetMaxNumberOfPyramids; <= 0: the reference's default
+                                          (unlimited, DepthImagePlanner.cpp:52) -- device storage holds AGF_RAPPIDS_MAX_PYRAMIDS, and
+                                          agf_rappids_result.pyramid_cap_hit reports a vehicle that needed more (its result may
+                                          then differ from the reference's); > AGF_RAPPIDS_MAX_PYRAMIDS: AGF_EUNSUPPORTED      */
   int32_t cost_kind;                   /* AGF_RAPPIDS_COST_*                                            */
   double cost_vec[3];                  /* direction / goal shared by the population (agf_rappids_set_goals overrides per vehicle) */
   double sample_min_x, sample_max_x, sample_min_y, sample_max_y;   /* pixels  */
@@ -71,6 +74,10 @@ typedef struct agf_rappids_result {
   double best_cost;
   double best_coeffs[18];              /* RapidTrajectoryGenerator::GetTrajectory().GetCoeffs(): [6][3], t^5 first */
   double best_tf;
+  int32_t pyramid_cap_hit;             /* 1: a candidate needed a new pyramid when max_pyramids existed already and was rejected
+                                          as colliding (DepthImagePlanner.cpp:246-249); with max_pyramids <= 0 ("unlimited") this
+                                          marks a result that may differ from the reference's                                */
+  int32_t reserved_;
 } agf_rappids_result;
 
 typedef struct agf_rappids agf_rappids;

@@ -119,6 +119,13 @@ double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t
                           const agf_cmd_entry* sched, uint32_t nsched, const uint8_t* slot_raw /*[slots][n][23]*/,
                           uint32_t threads, double* final_out);
 
+/* the same with a trajectory: the record of every vehicle after every `stride` ticks ->
+ * traj_out [nticks / stride][n][ORC_NTRAJ] (oracle/orc_population_traj.inc) */
+double orc_run_population_traj(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t n, const orc_opts* opts,
+                               const double* init13, const float* anchors, uint32_t n_anchors, uint32_t dt_us,
+                               uint32_t nticks, const agf_cmd_entry* sched, uint32_t nsched, const uint8_t* slot_raw,
+                               uint32_t threads, uint32_t stride, double* traj_out);
+
 /* codec cross-checks against the reference's own RadioTypes / TelemetryPacket code */
 void orc_radio_encode_rates(uint8_t flags, float thrust, const float w[3], uint8_t raw[23]);
 void orc_radio_encode_position(uint8_t flags, const float p[3], const float v[3], const float a[3],
@@ -127,6 +134,9 @@ void orc_radio_encode_acceleration(uint8_t flags, const float a[3], float yaw_ra
 void orc_radio_decode(const uint8_t raw[23], uint8_t* type, uint8_t* flags, float floats[10]);
 void orc_telemetry_decode(const uint8_t packet[30], agf_telemetry* out);
 void orc_logic_consts(int quad_type, agf_logic_consts* out);
+/* ref flavours only: vehicle ID -> the constructor arguments as the reference's apps derive them (main.cpp:147-165) */
+int orc_vehicle_cfg_from_id(int vehicle_id, agf_vehicle_cfg* out);
+void orc_radio_encode_idle(uint8_t flags, uint8_t raw[23]);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,7 @@ class FullState(C.Structure):
 PATHS = {
     "ref-glibc": os.path.join(HERE, "_ref", "libagf_ref_glibc.so"),
     "ref-shared": os.path.join(HERE, "_ref", "libagf_ref_shared.so"),
+    "ref-fma": os.path.join(HERE, "_ref", "libagf_ref_fma.so"),
     "port-glibc": os.path.join(HERE, "libagf_port_glibc.so"),
     "port-shared": os.path.join(HERE, "libagf_port_shared.so"),
     "hostsim-shared": os.path.join(HERE, "libagf_hostsim_shared.so"),
@@ -139,12 +140,20 @@ class Oracle:
             L.orc_run_population.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
                                              C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),
                                              C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+            if hasattr(L, "orc_run_population_traj"):
+                L.orc_run_population_traj.restype = C.c_double
+                L.orc_run_population_traj.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
+                                                      C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),
+                                                      C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         if flavour.startswith("ref-"):  # codec cross-checks exist only against the real reference
             L.orc_radio_encode_rates.argtypes = [C.c_uint8, C.c_float, P(C.c_float), C.c_void_p]
             L.orc_radio_encode_position.argtypes = [C.c_uint8, P(C.c_float), P(C.c_float), P(C.c_float), C.c_void_p]
             L.orc_radio_encode_acceleration.argtypes = [C.c_uint8, P(C.c_float), C.c_float, C.c_void_p]
             L.orc_telemetry_decode.argtypes = [C.c_void_p, P(abi.Telemetry)]
             L.orc_logic_consts.argtypes = [C.c_int, P(abi.LogicConsts)]
+            if hasattr(L, "orc_vehicle_cfg_from_id"):
+                L.orc_vehicle_cfg_from_id.argtypes = [C.c_int, P(abi.VehicleCfg)]
+                L.orc_radio_encode_idle.argtypes = [C.c_uint8, C.c_void_p]
         if not flavour.startswith("hostsim"):
             L.orc_radio_decode.argtypes = [C.c_void_p, P(C.c_uint8), P(C.c_uint8), P(C.c_float)]
         self.L = L
@@ -173,6 +182,80 @@ class Oracle:
             None if anc is None else anc.ctypes.data, 0 if anc is None else len(anc), dt_us, nticks,
             sch, len(sched), None if sr is None else sr.ctypes.data, threads, out.ctypes.data)
         return out, secs
+
+    def run_population_traj(self, cfgs, n, stride, init13=None, anchors=None, dt_us=2000, nticks=1, sched=(),
+                            slot_raw=None, threads=1, onboard_logic_period=1.0 / 500.0, uwb_comm_period=0.0,
+                            sigma_acc=0.0, sigma_gyro=0.0):
+        """run_population with a trajectory: -> ([nticks // stride][n][NTRAJ], seconds)"""
+        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, 0.0)
+        if isinstance(cfgs, abi.VehicleCfg):
+            carr = (abi.VehicleCfg * 1)(cfgs)
+            ncfg = 1
+        else:
+            carr = (abi.VehicleCfg * len(cfgs))(*cfgs)
+            ncfg = len(cfgs)
+        out = np.zeros((nticks // stride, n, NTRAJ))
+        i13 = None if init13 is None else np.ascontiguousarray(init13, dtype=np.float64)
+        anc = None if anchors is None else np.ascontiguousarray(anchors, dtype=np.float32)
+        sr = None if slot_raw is None else np.ascontiguousarray(slot_raw, dtype=np.uint8)
+        sch = make_schedule(list(sched))
+        secs = self.L.orc_run_population_traj(
+            carr, ncfg, n, C.byref(opts), None if i13 is None else i13.ctypes.data,
+            None if anc is None else anc.ctypes.data, 0 if anc is None else len(anc), dt_us, nticks,
+            sch, len(sched), None if sr is None else sr.ctypes.data, threads, stride, out.ctypes.data)
+        return out, secs
+
+
+def reference_vehicle_cfg(O, vehicle_id=1, **overrides):
+    """agf_vehicle_cfg for `vehicle_id` built by the reference's own QuadcopterConstants inside the harness (ref flavours),
+    so that bench.py's reference arm loads no product library; the port has no table of its own and borrows the product's."""
+    c = abi.VehicleCfg()
+    if hasattr(O.L, "orc_vehicle_cfg_from_id"):
+        if O.L.orc_vehicle_cfg_from_id(int(vehicle_id), C.byref(c)) != 0:
+            raise ValueError("unknown vehicle id %r" % (vehicle_id,))
+    else:
+        import agrifly_b200
+        c = agrifly_b200.vehicle_cfg(vehicle_id=vehicle_id)
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+class RefCodec:
+    """The radio command encoders of the reference itself (RadioTypes.hpp through the harness), with the call signatures of
+    the product's codec object, for agrifly_b200.scenarios' schedule builders.  Port flavours fall back to the product codec."""
+
+    def __init__(self, O):
+        self.L = O.L
+        self.ref = hasattr(O.L, "orc_radio_encode_idle")
+        if not self.ref:
+            import agrifly_b200
+            self.fallback = agrifly_b200.codec
+
+    @staticmethod
+    def _f3(v):
+        return (C.c_float * 3)(*[float(x) for x in v])
+
+    def encode_position(self, flags, p, v=(0, 0, 0), a=(0, 0, 0)):
+        if not self.ref:
+            return self.fallback.encode_position(flags, p, v, a)
+        raw = (C.c_uint8 * abi.RADIO_PACKET_SIZE)()
+        self.L.orc_radio_encode_position(flags, self._f3(p), self._f3(v), self._f3(a), raw)
+        return bytes(raw)
+
+    def encode_rates(self, flags, thrust, w):
+        if not self.ref:
+            return self.fallback.encode_rates(flags, thrust, w)
+        raw = (C.c_uint8 * abi.RADIO_PACKET_SIZE)()
+        self.L.orc_radio_encode_rates(flags, float(thrust), self._f3(w), raw)
+        return bytes(raw)
+
+    def encode_idle(self, flags=0):
+        if not self.ref:
+            return self.fallback.encode_idle(flags)
+        raw = (C.c_uint8 * abi.RADIO_PACKET_SIZE)()
+        self.L.orc_radio_encode_idle(flags, raw)
+        return bytes(raw)
 
 
 class OracleVehicle:

@@ -2174,6 +2174,8 @@ double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t
   return secs;
 }
 
+#include "../orc_population_traj.inc"
+
 // codec entry points of the port are only the decode side (the product owns the encoders and is
 // checked against the reference's encoders through oracle/_ref)
 void orc_radio_decode(const uint8_t raw[23], uint8_t* type, uint8_t* flags, float floats[10]) {

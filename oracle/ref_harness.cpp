@@ -834,6 +834,9 @@ double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t
   return secs;
 }
 
+#define ORC_POP_SEED(v, i) (v)->quad->_generator.seed((i) + 1)
+#include "orc_population_traj.inc"
+
 void orc_radio_encode_rates(uint8_t flags, float thrust, const float w[3], uint8_t raw[23]) {
   memset(raw, 0, 23);
   RadioTypes::RadioMessageDecoded::CreateRatesCommand(flags, thrust, Vec3f(w[0], w[1], w[2]), raw);
@@ -899,6 +902,37 @@ void orc_logic_consts(int quad_type, agf_logic_consts* o) {
   o->motor_time_const = c.motorTimeConst; o->motor_inertia = c.motorInertia;
   o->motor_min_speed = c.motorMinSpeed; o->motor_max_speed = c.motorMaxSpeed;
   o->valid = c.valid;
+}
+
+// The vehicle configuration as the reference's apps build it (Simulator/Rappids_Simulator/main.cpp:147-165): vehicle ID ->
+// QuadcopterConstants::GetVehicleTypeFromID -> the float table entries widened to double, inertia_yy = inertia_xx,
+// propTorqueFromSpeedSqr = kTau * kF.  Lets bench.py's reference arm run without loading the product library.
+int orc_vehicle_cfg_from_id(int vehicle_id, agf_vehicle_cfg* c) {
+  const Onboard::QuadcopterConstants::QuadcopterType t = Onboard::QuadcopterConstants::GetVehicleTypeFromID(vehicle_id);
+  memset(c, 0, sizeof(*c));
+  orc_logic_consts(int(t), &c->logic);
+  Onboard::QuadcopterConstants k(t);
+  c->mass = k.mass;
+  c->inertia[0] = k.inertia_xx;
+  c->inertia[4] = k.inertia_xx;
+  c->inertia[8] = k.inertia_zz;
+  c->arm_length = k.armLength;
+  c->prop_thrust_from_speed_sqr = k.propellerThrustFromSpeedSqr;
+  c->prop_torque_from_speed_sqr = k.propellerTorqueFromThrust * k.propellerThrustFromSpeedSqr;
+  c->motor_time_const = k.motorTimeConst;
+  c->motor_inertia = k.motorInertia;
+  c->motor_min_speed = k.motorMinSpeed;
+  c->motor_max_speed = k.motorMaxSpeed;
+  c->lin_drag_coeff_b[0] = k.linDragCoeffBx;
+  c->lin_drag_coeff_b[1] = k.linDragCoeffBy;
+  c->lin_drag_coeff_b[2] = k.linDragCoeffBz;
+  c->vehicle_id = vehicle_id;
+  c->quad_type = int(t);
+  return k.valid ? 0 : -1;
+}
+void orc_radio_encode_idle(uint8_t flags, uint8_t raw[23]) {
+  memset(raw, 0, 23);
+  RadioTypes::RadioMessageDecoded::CreateIdleCommand(flags, raw);
 }
 
 }  // extern "C"

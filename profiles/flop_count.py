@@ -1,7 +1,7 @@
 """Workload for counting executed floating-point instructions per vehicle-step with ncu hardware counters
 (SURVEY.md 8d asks for an instrumented re-derivation of the hand count).
 
-    ncu --metrics <op counters> -k regex:step_kernel -s 1 -c 1 python profiles/flop_count.py parity|fast fp64|fp32 uwb|rates [n] [ticks]
+    ncu --metrics <op counters> -k regex:step_kernel -s 1 -c 1 python profiles/flop_count.py parity|fast fp64|fp32 uwb|rates [n] [ticks] [hk|nohk]
 
 The first launch (600 ticks: take-off, EKF initialised, ranging active) is skipped by `-s 1`; the second launch
 of `ticks` ticks is the one counted.  flop/step = (fadd + fmul + 2 ffma [+ dadd + dmul + 2 dfma]) / (n * ticks)."""
@@ -18,12 +18,13 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "fp64"
 uwb = (sys.argv[3] if len(sys.argv) > 3 else "uwb") == "uwb"
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
 ticks = int(sys.argv[5]) if len(sys.argv) > 5 else 300
+hk = (sys.argv[6] == "hk") if len(sys.argv) > 6 else (math == "parity")  # housekeeping: always on in the parity kernels
 s = agf.scenarios
 cfg = agf.vehicle_cfg(vehicle_id=1, motor_time_const=0.015)
 b = agf.Batch(cfg, n, precision=agf.abi.PREC_FP32 if prec == "fp32" else agf.abi.PREC_FP64,
               math=agf.abi.MATH_PARITY if math == "parity" else agf.abi.MATH_FAST,
               uwb_comm_period=0.004 if uwb else 0.0, sigma_gyro=0.1, sigma_acc=0.2, seed=7,
-              telemetry_warnings=(math == "parity"))
+              telemetry_warnings=hk)
 if uwb:
     for i, p in s.ANCHORS_8:
         b.add_anchor(i, p)
@@ -36,4 +37,4 @@ b.run(600)
 b.run(ticks)
 b.sync()
 st = b.stats()
-print("flop_count workload: %s %s %s n=%d ticks=%d panic=%d nonfinite=%d" % (math, prec, "uwb" if uwb else "rates", n, ticks, st[6], st[9]))
+print("flop_count workload: %s %s %s hk=%d n=%d ticks=%d panic=%d nonfinite=%d" % (math, prec, "uwb" if uwb else "rates", hk, n, ticks, st[6], st[9]))

@@ -1,5 +1,7 @@
 """Workload driver for the ncu captures in profiles/ (see profiles/README.md for the commands).
-Usage: python profiles/prof_step.py [fp32|fp64] [uwb|rates] [vehicles] [ticks] [launches]"""
+Usage: python profiles/prof_step.py [fp32|fp64] [uwb|rates] [vehicles] [ticks] [launches]
+Environment: AGF_PROF_HK=0|1 (housekeeping, default 1), AGF_PROF_MATH=fast|parity, AGF_PROF_C4=1 (per-vehicle parameter sweep +
+trajectory log every tick, ring of 32 records), AGF_NO_WARM=1 (no clock warm-up launches)."""
 import os
 import sys
 
@@ -17,7 +19,12 @@ launches = int(sys.argv[5]) if len(sys.argv) > 5 else 4
 import time  # noqa: E402
 
 warm = 0 if os.environ.get("AGF_NO_WARM") else 12  # extra warm-up launches: clocks ramp up over tens of ms
-b, _ = bench.workload(agf, n, 0, prec, ticks * (launches + warm + 1) + 600, uwb=uwb)
+hk = os.environ.get("AGF_PROF_HK", "1") != "0"
+c4 = os.environ.get("AGF_PROF_C4", "0") == "1"
+b, _ = bench.workload(agf, n, 0, prec, ticks * (launches + warm + 1) + 600, uwb=uwb, hk=hk, math=os.environ.get("AGF_PROF_MATH", "fast"),
+                      sweep=c4)
+if c4:
+    b.enable_log(1, 32)
 b.run(500)  # first launch: take-off, EKF initialised, UWB ranging active
 t0 = time.time()
 for _ in range(warm):

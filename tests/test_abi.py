@@ -181,3 +181,24 @@ def test_shared_libm_accuracy(tmp_path_factory):
     xf = rng.uniform(-3, 3, 2000).astype(np.float32)
     got = np.array([L.w_sinf(float(v)) for v in xf], np.float32)
     assert np.max(np.abs(got.astype(np.float64) - np.sin(xf.astype(np.float64)))) < 6e-8
+
+
+def test_nccl_is_bound_at_run_time_not_link_time(agf):
+    """The statistics collective lives in the C ABI (agf_batch_reduce_stats_nccl); libnccl.so.2 is resolved with dlopen on
+    first use, so the library loads on hosts without NCCL and has no link-time dependency on it."""
+    import subprocess
+    from agrifly_b200 import LIB_PATH
+    needed = subprocess.check_output(["readelf", "-d", LIB_PATH], text=True)
+    assert "libnccl" not in needed
+    L = agf.lib()
+    v = C.c_int(0)
+    rc = L.agf_nccl_version(C.byref(v))
+    if rc == agf.abi.ENCCL:
+        pytest.skip("no libnccl.so.2 on this host: " + L.agf_last_error_string().decode())
+    assert rc == 0 and v.value >= 20400
+    uid = (C.c_uint8 * agf.abi.NCCL_UNIQUE_ID_BYTES)()
+    assert L.agf_nccl_get_unique_id(uid) == 0 and any(bytes(uid))
+    # argument checking happens before any device work
+    comm = C.c_void_p()
+    assert L.agf_nccl_comm_init_rank(uid, 2, 5, 0, C.byref(comm)) == agf.abi.EINVAL
+    assert L.agf_batch_reduce_stats_nccl(None, None, None, None) == agf.abi.EINVAL

@@ -37,7 +37,13 @@ def _worker(rank, world, port, n_total, q):
     v[15] = 2 * e.max()
     t = torch.from_numpy(v.copy())
     sharding.combine_stats(t, dist)
-    q.put((rank, first, count, t.numpy().copy()))
+    # the read-out as the C ABI does it on the GPUs: ONE all-gather of the 16 doubles of every rank, combined in rank order
+    # (agf_batch_reduce_stats_nccl); and the hand-over of rank 0's communicator id through torch.distributed
+    g = [torch.zeros(16, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(g, torch.from_numpy(v.copy()))
+    gathered = sharding.combine_gathered(np.stack([x.numpy() for x in g]))
+    uid = sharding.exchange_unique_id(lambda: bytes(range(128)), dist)
+    q.put((rank, first, count, t.numpy().copy(), gathered, uid))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,7 +72,9 @@ def test_stats_allreduce_gloo_world2(agf):
         p.join(timeout=60)
         assert p.exitcode == 0
     e = np.arange(n_total, dtype=np.float64) * 1e-3
-    for rank, first, count, v in res:
+    for rank, first, count, v, gathered, uid in res:
+        assert np.array_equal(gathered, v)      # one all-gather + rank-order combine == the two all-reduces
+        assert uid == bytes(range(128))         # every rank holds rank 0's id
         assert v[0] == n_total
         assert abs(v[4] - np.sum(e * e)) < 1e-9 and abs(v[5] - np.sum(e)) < 1e-9
         assert v[14] == e.max() and v[15] == 2 * e.max()

@@ -374,3 +374,39 @@ def test_time_base_latencies(agf, port_glibc):
     """Run() before Advance(): tick 0 is a no-op, logic first runs at tick 2."""
     tr, _ = run_oracle(port_glibc, agf, scenario(agf, "rates"), nticks=10)
     assert list(tr[:5, 36]) == [0, 0, 1, 2, 3]
+
+
+def test_population_trajectories_port_equals_reference_and_envelope_exists(agf, orc_mod):
+    """oracle/orc_population_traj.inc: the population helper with a trajectory (every 50th tick).  The port reproduces
+    the unmodified reference bit for bit at trajectory level for a randomized full-mode population, with either libm; and
+    the reference's own sensitivity envelope -- the same sources rebuilt with FMA contraction (ref-fma) -- is non-zero in
+    full mode, which is what tests/test_fast_population_gpu.py measures the fast kernels against."""
+    n, nt, stride = 48, 2500, 50
+    s = agf.scenarios
+    sc = s.full_scenario(agf.codec, nticks=nt)
+    init = s.monte_carlo_initial_states(n, seed=1234)
+    idle = agf.codec.encode_idle(0)
+    slot = np.array([np.frombuffer(agf.codec.encode_position(0, (p[0], p[1], 1.5)), np.uint8) for p in init])
+    sched = [(d, idle, -1) if sl == -2 else (d, None, 0) for d, _, sl in s.hover_slot_schedule(nt)]
+    cfg = agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"])
+    anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
+    slots = np.zeros((4, n, 23), np.uint8)
+    slots[0] = slot
+    tr = {}
+    for fl in ("port-glibc", "port-shared", "ref-glibc", "ref-shared", "ref-fma"):
+        if not orc_mod.available(fl):
+            continue
+        tr[fl], _ = orc_mod.Oracle(fl).run_population_traj(cfg, n, stride, init13=init, anchors=anchors, nticks=nt, sched=sched,
+                                                           slot_raw=slots, threads=4, uwb_comm_period=sc["uwb_comm_period"])
+        assert tr[fl].shape == (nt // stride, n, 40)
+    # record r of the trajectory helper == the final record of a plain run of (r + 1) * stride ticks
+    fin, _ = orc_mod.Oracle("port-glibc").run_population(cfg, n, init13=init, anchors=anchors, nticks=nt, sched=sched, slot_raw=slots,
+                                                         threads=4, uwb_comm_period=sc["uwb_comm_period"])
+    assert np.array_equal(tr["port-glibc"][-1], fin, equal_nan=True)
+    if "ref-glibc" not in tr:
+        pytest.skip("oracle/_ref not built here")
+    assert np.array_equal(tr["port-glibc"], tr["ref-glibc"], equal_nan=True)
+    assert np.array_equal(tr["port-shared"], tr["ref-shared"], equal_nan=True)
+    d = np.abs(tr["ref-fma"][..., 0:3] - tr["ref-glibc"][..., 0:3]).max(axis=(0, 2))
+    assert np.median(d) > 1e-7 and np.isfinite(d).all()   # the reference moves under a benign rebuild ...
+    assert np.median(d) < 5e-2                            # ... but remains the same flight
