@@ -123,8 +123,9 @@ __global__ void field_set_kernel(FieldCtx<P> c, int field, int ncomp, size_t fir
   const double* ind = (const double*)in;
   const float* inf = (const float*)in;
   switch (field) {
-    case AGF_F_POSITION: c.sp[sidx(SP_POS + comp, c.n, i, VP)] = P(ind[t]); break;
-    case AGF_F_VELOCITY: c.sp[sidx(SP_VEL + comp, c.n, i, VP)] = P(ind[t]); break;
+    // a position / velocity written from outside starts its compensated sum afresh (FP32 fast variants, agf_step.cuh tick())
+    case AGF_F_POSITION: c.sp[sidx(SP_POS + comp, c.n, i, VP)] = P(ind[t]); c.sp[sidx(SP_CPOS + comp, c.n, i, VP)] = P(0); break;
+    case AGF_F_VELOCITY: c.sp[sidx(SP_VEL + comp, c.n, i, VP)] = P(ind[t]); c.sp[sidx(SP_CVEL + comp, c.n, i, VP)] = P(0); break;
     case AGF_F_ATTITUDE: c.sp[sidx(SP_ATT + comp, c.n, i, VP)] = P(ind[t]); break;
     case AGF_F_ANGULAR_VELOCITY: c.sp[sidx(SP_W + comp, c.n, i, VP)] = P(ind[t]); break;
     case AGF_F_MOTOR_SPEED: c.sp[sidx(SP_MS + comp, c.n, i, VP)] = P(ind[t]); break;
@@ -147,6 +148,7 @@ __global__ void state13_set_kernel(FieldCtx<P> c, size_t first, size_t count, co
   const int comp = int(t % 13);
   const int slot = comp < 3 ? SP_POS + comp : (comp < 6 ? SP_VEL + comp - 3 : (comp < 10 ? SP_ATT + comp - 6 : SP_W + comp - 10));
   c.sp[sidx(slot, c.n, i, VP)] = P(in[t]);
+  if (comp < 6) c.sp[sidx(comp < 3 ? SP_CPOS + comp : SP_CVEL + comp - 3, c.n, i, VP)] = P(0);
 }
 
 // SetCommandRadioMsg now (QuadcopterLogic.hpp:110-116), outside the step kernel
@@ -379,12 +381,16 @@ struct Batch {
   }
   // the pair that brackets the next launch
   int next_event_pair(std::pair<cudaEvent_t, cudaEvent_t>** out) {
-    if (events.size() < size_t(EVENT_RING) && ev_count == events.size()) {
-      cudaEvent_t a, b;
-      AGF_CUDA(cudaEventCreate(&a));
-      AGF_CUDA(cudaEventCreate(&b));
-      events.push_back({a, b});
-    } else if (ev_count == size_t(EVENT_RING)) {
+    if (events.empty()) {  // the whole ring at first use: the ring indices below run modulo EVENT_RING
+      events.reserve(EVENT_RING);
+      for (int k = 0; k < EVENT_RING; k++) {
+        cudaEvent_t a, b;
+        AGF_CUDA(cudaEventCreate(&a));
+        AGF_CUDA(cudaEventCreate(&b));
+        events.push_back({a, b});
+      }
+    }
+    if (ev_count == size_t(EVENT_RING)) {
       int rc = fold_oldest_event();
       if (rc) return rc;
     }

@@ -595,14 +595,16 @@ int agf_rappids_plan(agf_rappids* p) {
   P.edgeOff = (int)(c.focal_length * c.true_radius / c.min_checking_dist);
   P.ignore = (int)(uint16_t)(c.true_radius / c.depth_scale);
   P.num = (int)(c.focal_length * c.planning_radius / c.depth_scale);
-  if (h->events.size() < size_t(Handle::EVENT_RING) && h->ev_count == h->events.size()) {
-    cudaEvent_t a, b;
-    AGFR_CUDA(cudaEventCreate(&a));
-    AGFR_CUDA(cudaEventCreate(&b));
-    h->events.emplace_back(a, b);
-  } else if (h->ev_count == size_t(Handle::EVENT_RING)) {
-    AGFR_CUDA(h->fold_oldest_event());
+  if (h->events.empty()) {  // the whole ring at first use: the ring indices below run modulo EVENT_RING
+    h->events.reserve(Handle::EVENT_RING);
+    for (int k = 0; k < Handle::EVENT_RING; k++) {
+      cudaEvent_t a, b;
+      AGFR_CUDA(cudaEventCreate(&a));
+      AGFR_CUDA(cudaEventCreate(&b));
+      h->events.emplace_back(a, b);
+    }
   }
+  if (h->ev_count == size_t(Handle::EVENT_RING)) AGFR_CUDA(h->fold_oldest_event());
   AGFR_CUDA(cudaMemsetAsync(h->next, 0, sizeof(int), h->stream));
   auto& ev = h->events[(h->ev_head + h->ev_count) % Handle::EVENT_RING];
   h->ev_count++;

@@ -428,6 +428,8 @@ template<typename P, bool PARITY, bool UWB, bool HK>
 struct VState {
   // plant
   P pos[3], vel[3], att[4], w[3], ms[4];
+  // FP32 fast variants: compensation terms of the position / velocity sums (compensated integration in tick())
+  P cpos[(!PARITY && sizeof(P) == 4) ? 3 : 1], cvel[(!PARITY && sizeof(P) == 4) ? 3 : 1];
   // logic
   float cmd[4];      // _desMotorSpeeds == _motorSpeedCommands after every logic run
   float dforce[(PARITY || HK) ? 4 : 1];   // _desMotorForcesForTelemetry (fast, no HK: derived from cmd)
@@ -558,14 +560,19 @@ template<typename P, bool PARITY, bool UWB, bool HK>
 AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i, const Scratch& sc) {
   typedef typename VecOf<P>::type PV;
   constexpr int VP = VecOf<P>::lanes;
+  constexpr bool COMP = !PARITY && sizeof(P) == 4;  // compensated FP32 integration: two more triples of plant scalars
   P rp[NP_PAD];
 #pragma unroll
-  for (int q = 0; q < NP_PAD / VP; q++) {
+  for (int q = 0; q < (COMP ? NP_PAD : NP_REF) / VP; q++) {
     PV v = ldcg_(&a.sp[size_t(q) * n + i]);
     VecOf<P>::unpack(v, &rp[q * VP]);
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) { s.pos[k] = rp[SP_POS + k]; s.vel[k] = rp[SP_VEL + k]; s.w[k] = rp[SP_W + k]; }
+  if constexpr (COMP) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { s.cpos[k] = rp[SP_CPOS + k]; s.cvel[k] = rp[SP_CVEL + k]; }
+  }
 #pragma unroll
   for (int k = 0; k < 4; k++) { s.att[k] = rp[SP_ATT + k]; s.ms[k] = rp[SP_MS + k]; }
   if constexpr (UWB) {
@@ -664,9 +671,15 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
 #pragma unroll
     for (int k = 0; k < 3; k++) rp[SP_RPOS + k] = s.rpos[k];
   }
+  constexpr bool COMP = !PARITY && sizeof(P) == 4;
+  if constexpr (COMP) {
 #pragma unroll
-  for (int q = 0; q < NP_PAD / VP; q++) {
-    if (!UWB && q * VP >= SP_RPOS) break;  // nothing beyond the plant proper changes
+    for (int k = 0; k < 3; k++) { rp[SP_CPOS + k] = s.cpos[k]; rp[SP_CVEL + k] = s.cvel[k]; }
+  }
+#pragma unroll
+  for (int q = 0; q < (COMP ? NP_PAD : NP_REF) / VP; q++) {
+    const bool radio_quad = q * VP >= SP_RPOS && q * VP < SP_CVEL;
+    if (!UWB && radio_quad) continue;  // the radio's latched position only exists with ranging
     a.sp[size_t(q) * n + i] = VecOf<P>::pack(&rp[q * VP]);
   }
   float rf[NF_PAD];
@@ -2193,15 +2206,47 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       acc = acc + (c3 * F.z + extF) * pv.inv_mass;
     }
     const V3<P> pos(s.pos[0], s.pos[1], s.pos[2]), vel(s.vel[0], s.vel[1], s.vel[2]);
-    V3<P> npos = (pos + vel * dt) + ((P(0.5) * acc) * dt) * dt;
-    V3<P> nvel = vel + acc * dt;
-    const Q4<P> natt = q_apply_rotvec<PARITY>(att, w * dt);
+    V3<P> npos, nvel;
+    Q4<P> natt = q_apply_rotvec<PARITY>(att, w * dt);
+    if constexpr (!PARITY && sizeof(P) == 4) {
+      // FP32 mode is not the reference's arithmetic; what it owes the reference is its trajectory (north star: 1e-4 over
+      // 10 s).  Two places where plain FP32 loses that over 5 000 ticks, both measured against the reference population
+      // (tests/test_fast_population_gpu.py, rates mode: worst vehicle 1.7e-4 without, < 5e-5 with):
+      //  * the position and velocity sums: millimetre increments into metre-sized accumulators, thousands of times ->
+      //    compensated (Kahan) summation, the running compensation is part of the stored state;
+      //  * the attitude quaternion: the reference never normalises it, but in double it stays a unit quaternion to
+      //    1e-16, while a float one is off by ~6e-8 from the first conversion on and scales the thrust it rotates
+      //    -> one Newton step of 1/|q| per tick keeps |q| = 1 to second order.
+      const P pp[3] = {pos.x, pos.y, pos.z}, vv[3] = {vel.x, vel.y, vel.z}, aa[3] = {acc.x, acc.y, acc.z};
+      P np_[3], nv_[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const P inc = vv[k] * dt + ((P(0.5) * aa[k]) * dt) * dt;
+        const P y = inc - s.cpos[k];
+        const P t = pp[k] + y;
+        s.cpos[k] = (t - pp[k]) - y;
+        np_[k] = t;
+        const P yv = aa[k] * dt - s.cvel[k];
+        const P tv = vv[k] + yv;
+        s.cvel[k] = (tv - vv[k]) - yv;
+        nv_[k] = tv;
+      }
+      npos = V3<P>(np_[0], np_[1], np_[2]);
+      nvel = V3<P>(nv_[0], nv_[1], nv_[2]);
+      const P n2 = natt.w * natt.w + natt.x * natt.x + natt.y * natt.y + natt.z * natt.z;
+      const P kn = P(1.5) - P(0.5) * n2;
+      natt = Q4<P>(natt.w * kn, natt.x * kn, natt.y * kn, natt.z * kn);
+    } else {
+      npos = (pos + vel * dt) + ((P(0.5) * acc) * dt) * dt;
+      nvel = vel + acc * dt;
+    }
     V3<P> nw = w + angAcc * dt;
     if ((npos.z <= 0) && (nvel.z < 0)) {  // ground contact :146-151
       npos.z = 0;
       nvel.z = 0;
       acc.z = 0;
       nw = V3<P>(P(0), P(0), P(0));
+      if constexpr (!PARITY && sizeof(P) == 4) { s.cpos[2] = 0; s.cvel[2] = 0; }
     }
     s.pos[0] = npos.x; s.pos[1] = npos.y; s.pos[2] = npos.z;
     s.vel[0] = nvel.x; s.vel[1] = nvel.y; s.vel[2] = nvel.z;

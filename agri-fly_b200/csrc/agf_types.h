@@ -25,9 +25,11 @@ namespace agf {
 
 // ---- flat state tables ------------------------------------------------------------------------
 enum {  // plant scalars (precision P)
-  SP_POS = 0, SP_VEL = 3, SP_ATT = 6, SP_W = 10, SP_MS = 13, /* 17..19 pad */
-  SP_RPOS = 20,  // UWB radio's latched true position (UWBRadio::_uwbTruePosition)
-  NP_CORE = 20, NP_PAD = 24
+  SP_POS = 0, SP_VEL = 3, SP_ATT = 6, SP_W = 10, SP_MS = 13,
+  SP_CPOS = 17,  // FP32 fast variants: running compensation of the position sum (see tick(): compensated integration)
+  SP_RPOS = 20,  // UWB radio's latched true position (UWBRadio::_uwbTruePosition); 23 pad
+  SP_CVEL = 24,  // FP32 fast variants: running compensation of the velocity sum; 27 pad
+  NP_CORE = 20, NP_REF = 24 /* what the FP64-plant variants load and store */, NP_PAD = 28
 };
 enum {  // logic floats; the HK block follows the core block
   SF_CMD = 0, SF_DFORCE = 4, SF_RADIO = 8, SF_KATT = 12, SF_GYRO_LP = 16, SF_ACC_LP = 28,

@@ -75,6 +75,8 @@ PATHS = {
     "port-glibc": os.path.join(HERE, "libagf_port_glibc.so"),
     "port-shared": os.path.join(HERE, "libagf_port_shared.so"),
     "hostsim-shared": os.path.join(HERE, "libagf_hostsim_shared.so"),
+    "hostsim-fast32": os.path.join(HERE, "libagf_hostsim_fast32.so"),
+    "hostsim-fast64": os.path.join(HERE, "libagf_hostsim_fast64.so"),
 }
 
 
@@ -140,7 +142,8 @@ class Oracle:
             L.orc_run_population.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
                                              C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),
                                              C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
-            if hasattr(L, "orc_run_population_traj"):
+        if hasattr(L, "orc_run_population_traj"):
+            if True:
                 L.orc_run_population_traj.restype = C.c_double
                 L.orc_run_population_traj.argtypes = [P(abi.VehicleCfg), C.c_uint32, C.c_uint32, P(OrcOpts), C.c_void_p,
                                                       C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(abi.CmdEntry),

@@ -150,5 +150,7 @@ def test_fast_kernels_population_trajectory_parity_rates(agf, orc_mod):
         t = table(got, ref, ok)
         for k, v in t.items():
             print("%-10s %-9s %-5s median %.2e p90 %.2e p99 %.2e max %.2e" % ((name,) + k + tuple(v)))
-        # north star, FP32 mode: position, velocity, attitude, motor speed within 1e-4 relative over 10 s -- every vehicle
+        # north star, FP32 mode: position, velocity, attitude, motor speed within 1e-4 relative over 10 s -- every vehicle;
+        # the typical vehicle an order of magnitude better (compensated FP32 integration, agf_step.cuh tick())
         assert t[("plant17", "0-10s")][3] <= tol, (name, t[("plant17", "0-10s")])
+        assert t[("plant17", "0-10s")][0] <= 2e-5, (name, t[("plant17", "0-10s")])

@@ -410,3 +410,29 @@ def test_population_trajectories_port_equals_reference_and_envelope_exists(agf, 
     d = np.abs(tr["ref-fma"][..., 0:3] - tr["ref-glibc"][..., 0:3]).max(axis=(0, 2))
     assert np.median(d) > 1e-7 and np.isfinite(d).all()   # the reference moves under a benign rebuild ...
     assert np.median(d) < 5e-2                            # ... but remains the same flight
+
+
+def test_fast_formulation_on_the_host_holds_the_fp32_tolerance_in_rates_mode(agf, orc_mod):
+    """oracle/hostsim/agf_hostsim_fast.cu: the FAST instantiations of the device step header compiled for the host (a
+    development aid; the host compiler's FMA contraction and libm are not the GPU's, so this is indicative -- the binding
+    check is tests/test_fast_population_gpu.py on the GPU).  Rates mode, randomized initial attitudes, 10 s: the FP32 plant
+    (compensated position / velocity sums, quaternion kept at unit norm) stays within the north star's 1e-4 of the
+    reference for every vehicle and within 2e-5 for the typical one; the FP64 plant within the reference's own FMA
+    sensitivity (1e-5)."""
+    import shutil
+    if not (orc_mod.available("hostsim-fast32") and orc_mod.available("hostsim-fast64")):
+        if not shutil.which("nvcc") and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+            pytest.skip("nvcc not available to build oracle/hostsim")
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hostsim-fast"], stdout=subprocess.DEVNULL)
+    n, nt, stride = 64, 5000, 50
+    s = agf.scenarios
+    sc = s.rates_scenario(agf.codec, nticks=nt)
+    init = s.monte_carlo_initial_states(n, seed=77)
+    cfg = agf.vehicle_cfg(sc["quad_type"], sc["vehicle_id"], motor_time_const=sc["motor_time_const"], motor_inertia=sc["motor_inertia"])
+    tr = {}
+    for fl in ("port-glibc", "hostsim-fast32", "hostsim-fast64"):
+        tr[fl], _ = orc_mod.Oracle(fl).run_population_traj(cfg, n, stride, init13=init, nticks=nt, sched=sc["sched"], threads=4)
+    ref = tr["port-glibc"]
+    for fl, tol_max, tol_med in (("hostsim-fast32", 1e-4, 2e-5), ("hostsim-fast64", 1e-5, 2e-6)):
+        e = (np.abs(tr[fl][..., 0:17] - ref[..., 0:17]) / np.maximum(np.abs(ref[..., 0:17]), 1.0)).max(axis=(0, 2))
+        assert e.max() <= tol_max and np.median(e) <= tol_med, (fl, np.median(e), e.max())
