@@ -153,6 +153,31 @@ AGF_DEV float pmax_(float a, float b) { return ::fmaxf(a, b); }
 AGF_DEV double pmax_(double a, double b) { return ::fmax(a, b); }
 AGF_DEV float rabs_(float x) { return ::fabsf(x); }
 AGF_DEV double rabs_(double x) { return ::fabs(x); }
+// Packed FP32 (sm_100: fma.rn.f32x2 / mul.f32x2 / add.f32x2 -> FFMA2 / FMUL2 / FADD2, two lanes per issued instruction; a
+// scalar operand is broadcast for free).  Used by the fast variants where two lanes share their coefficients.
+AGF_DEV float2 f2_fma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(::fmaf(a.x, b.x, c.x), ::fmaf(a.y, b.y, c.y));
+#endif
+}
+AGF_DEV float2 f2_mul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+AGF_DEV float2 f2_add(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+AGF_DEV float2 f2_fma(float2 a, float s, float2 c) { return f2_fma(a, make_float2(s, s), c); }
+AGF_DEV float2 f2_mul(float2 a, float s) { return f2_mul(a, make_float2(s, s)); }
 
 // ---------------------------------------------------------------------------------------------
 // Vec3 / Rotation with the reference's operation order
@@ -529,13 +554,34 @@ AGF_DEV void cov_store(const Scratch& sc, const float* P) {
 #pragma unroll
   for (int q = 0; q < 12; q++) sq_store(sc, SQ_COV + q, make_float4(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3]));
 }
-AGF_DEV float lpf2_scratch(const Lpf2Coef& c, const Scratch& sc, int quad, float in) {
-  const float4 st = sq_load(sc, SQ_LPF + quad);  // {xm0, xm1, ym0, ym1}
-  float out = c.b2 * in;
-  out = out + (c.b0 * st.x + c.b1 * st.y);
-  out = out + ((-c.a1) * st.z - c.a2 * st.w);
-  sq_store(sc, SQ_LPF + quad, make_float4(st.y, in, st.w, out));
-  return out;
+// The three components of one sensor through the same filter (fast variants).  Scratch quads q0 .. q0+2:
+//   {xm0.x, xm0.y, xm1.x, xm1.y}, {ym0.x, ym0.y, ym1.x, ym1.y} (x and y as packed pairs), {xm0, xm1, ym0, ym1} of z;
+// one multiply-add chain per output, the x/y pair on the packed FP32 path.
+AGF_DEV V3<float> lpf2_scratch3(const Lpf2Coef& c, const Scratch& sc, int q0, const V3<float>& in) {
+  const float4 X = sq_load(sc, q0), Y = sq_load(sc, q0 + 1), Z = sq_load(sc, q0 + 2);
+  const float2 inxy = make_float2(in.x, in.y);
+  float2 o = f2_mul(inxy, c.b2);
+  o = f2_fma(make_float2(X.x, X.y), c.b0, o);
+  o = f2_fma(make_float2(X.z, X.w), c.b1, o);
+  o = f2_fma(make_float2(Y.x, Y.y), -c.a1, o);
+  o = f2_fma(make_float2(Y.z, Y.w), -c.a2, o);
+  sq_store(sc, q0, make_float4(X.z, X.w, inxy.x, inxy.y));
+  sq_store(sc, q0 + 1, make_float4(Y.z, Y.w, o.x, o.y));
+  const float oz = ::fmaf(-c.a2, Z.w, ::fmaf(-c.a1, Z.z, ::fmaf(c.b1, Z.y, ::fmaf(c.b0, Z.x, c.b2 * in.z))));
+  sq_store(sc, q0 + 2, make_float4(Z.y, in.z, Z.w, oz));
+  return V3<float>(o.x, o.y, oz);
+}
+// HBM keeps the filter states component-major ([4 * c + k], k = xm0 xm1 ym0 ym1): conversion to / from the scratch layout
+AGF_DEV void lpf_scratch_put(const Scratch& sc, int q0, const float* f) {
+  sq_store(sc, q0, make_float4(f[0], f[4], f[1], f[5]));
+  sq_store(sc, q0 + 1, make_float4(f[2], f[6], f[3], f[7]));
+  sq_store(sc, q0 + 2, make_float4(f[8], f[9], f[10], f[11]));
+}
+AGF_DEV void lpf_scratch_get(const Scratch& sc, int q0, float* f) {
+  const float4 X = sq_load(sc, q0), Y = sq_load(sc, q0 + 1), Z = sq_load(sc, q0 + 2);
+  f[0] = X.x; f[4] = X.y; f[1] = X.z; f[5] = X.w;
+  f[2] = Y.x; f[6] = Y.y; f[3] = Y.z; f[7] = Y.w;
+  f[8] = Z.x; f[9] = Z.y; f[10] = Z.z; f[11] = Z.w;
 }
 
 // State is read once per work item and may have been written by another CTA of the same launch (balanced
@@ -596,11 +642,8 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
 #pragma unroll
     for (int k = 0; k < 12; k++) { s.gyro_lp[k] = rf[SF_GYRO_LP + k]; s.acc_lp[k] = rf[SF_ACC_LP + k]; }
   } else {
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      sq_store(sc, SQ_LPF + c, make_float4(rf[SF_GYRO_LP + 4 * c], rf[SF_GYRO_LP + 4 * c + 1], rf[SF_GYRO_LP + 4 * c + 2], rf[SF_GYRO_LP + 4 * c + 3]));
-      sq_store(sc, SQ_LPF + 3 + c, make_float4(rf[SF_ACC_LP + 4 * c], rf[SF_ACC_LP + 4 * c + 1], rf[SF_ACC_LP + 4 * c + 2], rf[SF_ACC_LP + 4 * c + 3]));
-    }
+    lpf_scratch_put(sc, SQ_LPF, &rf[SF_GYRO_LP]);
+    lpf_scratch_put(sc, SQ_LPF + 3, &rf[SF_ACC_LP]);
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) { s.kpos[k] = rf[SF_KPOS + k]; s.kvel[k] = rf[SF_KVEL + k]; s.kw[k] = rf[SF_KW + k]; s.kcorr[k] = rf[SF_KCORR + k]; }
@@ -696,12 +739,8 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
 #pragma unroll
     for (int k = 0; k < 12; k++) { rf[SF_GYRO_LP + k] = s.gyro_lp[k]; rf[SF_ACC_LP + k] = s.acc_lp[k]; }
   } else {
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float4 g = sq_load(sc, SQ_LPF + c), a4 = sq_load(sc, SQ_LPF + 3 + c);
-      rf[SF_GYRO_LP + 4 * c] = g.x; rf[SF_GYRO_LP + 4 * c + 1] = g.y; rf[SF_GYRO_LP + 4 * c + 2] = g.z; rf[SF_GYRO_LP + 4 * c + 3] = g.w;
-      rf[SF_ACC_LP + 4 * c] = a4.x; rf[SF_ACC_LP + 4 * c + 1] = a4.y; rf[SF_ACC_LP + 4 * c + 2] = a4.z; rf[SF_ACC_LP + 4 * c + 3] = a4.w;
-    }
+    lpf_scratch_get(sc, SQ_LPF, &rf[SF_GYRO_LP]);
+    lpf_scratch_get(sc, SQ_LPF + 3, &rf[SF_ACC_LP]);
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) { rf[SF_KPOS + k] = s.kpos[k]; rf[SF_KVEL + k] = s.kvel[k]; rf[SF_KW + k] = s.kw[k]; rf[SF_KCORR + k] = s.kcorr[k]; }
@@ -920,9 +959,16 @@ AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const 
     float A[3][3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-      A[r][0] = dt * (+acc.y * Rm[3 * r + 2] - acc.z * Rm[3 * r + 1]);
-      A[r][1] = dt * (-acc.x * Rm[3 * r + 2] + acc.z * Rm[3 * r + 0]);
-      A[r][2] = dt * (+acc.x * Rm[3 * r + 1] - acc.y * Rm[3 * r + 0]);
+      if constexpr (PARITY) {
+        A[r][0] = dt * (+acc.y * Rm[3 * r + 2] - acc.z * Rm[3 * r + 1]);
+        A[r][1] = dt * (-acc.x * Rm[3 * r + 2] + acc.z * Rm[3 * r + 0]);
+        A[r][2] = dt * (+acc.x * Rm[3 * r + 1] - acc.y * Rm[3 * r + 0]);
+      } else {  // dt folded into the measured acceleration once
+        const float ax = dt * acc.x, ay = dt * acc.y, az = dt * acc.z;
+        A[r][0] = ::fmaf(ay, Rm[3 * r + 2], -(az * Rm[3 * r + 1]));
+        A[r][1] = ::fmaf(az, Rm[3 * r + 0], -(ax * Rm[3 * r + 2]));
+        A[r][2] = ::fmaf(ax, Rm[3 * r + 1], -(ay * Rm[3 * r + 0]));
+      }
     }
     // att <- att block, :212-228   S[r][c]
     const float gx = dt * gyro.x + s.kcorr[0] / 2.0f;
@@ -942,7 +988,7 @@ AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const 
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = i; j < 3; j++) PS(i, j) = PS(i, j) + dt * ((PS(i, 3 + j) + PS(j, 3 + i)) + dt * PS(3 + i, 3 + j));
+        for (int j = i; j < 3; j++) PS(i, j) = ::fmaf(dt, ::fmaf(dt, PS(3 + i, 3 + j), PS(i, 3 + j) + PS(j, 3 + i)), PS(i, j));
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -950,41 +996,50 @@ AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const 
           PS(i, 3 + j) = PS(i, 3 + j) + dt * PS(3 + i, 3 + j);
           PS(i, 6 + j) = PS(i, 6 + j) + dt * PS(3 + i, 6 + j);
         }
-      // F2: T = Pva + A Paa ; U = Pva A^T ; Pvv += U^T + T A^T
+      // F2: T = Pva + A Paa ; U = Pva A^T ; Pvv += U^T + T A^T.  Every entry is one multiply-add chain onto its
+      // starting value (this variant is not pinned to the reference's parenthesisation; a chain is one instruction per term).
       float T[3][3], U[3][3];
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          T[i][j] = PS(3 + i, 6 + j) + (A[i][0] * PS(6, 6 + j) + A[i][1] * PS(7, 6 + j) + A[i][2] * PS(8, 6 + j));
-          U[i][j] = PS(3 + i, 6) * A[j][0] + PS(3 + i, 7) * A[j][1] + PS(3 + i, 8) * A[j][2];
+          T[i][j] = ::fmaf(A[i][2], PS(8, 6 + j), ::fmaf(A[i][1], PS(7, 6 + j), ::fmaf(A[i][0], PS(6, 6 + j), PS(3 + i, 6 + j))));
+          U[i][j] = ::fmaf(PS(3 + i, 8), A[j][2], ::fmaf(PS(3 + i, 7), A[j][1], PS(3 + i, 6) * A[j][0]));
         }
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = i; j < 3; j++)
-          PS(3 + i, 3 + j) = PS(3 + i, 3 + j) + U[j][i] + (T[i][0] * A[j][0] + T[i][1] * A[j][1] + T[i][2] * A[j][2]);
-      // Ppv += Ppa A^T ; Ppa = Ppa S^T ; Pva = T S^T
+          PS(3 + i, 3 + j) = ::fmaf(T[i][2], A[j][2], ::fmaf(T[i][1], A[j][1], ::fmaf(T[i][0], A[j][0], PS(3 + i, 3 + j) + U[j][i])));
+      // Ppv += Ppa A^T ; Ppa = Ppa S^T ; Pva = T S^T   (S has a unit diagonal: two terms onto the diagonal one)
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        const float a0 = PS(i, 6), a1 = PS(i, 7), a2 = PS(i, 8);
+        const float a[3] = {PS(i, 6), PS(i, 7), PS(i, 8)};
 #pragma unroll
-        for (int j = 0; j < 3; j++) PS(i, 3 + j) = PS(i, 3 + j) + (a0 * A[j][0] + a1 * A[j][1] + a2 * A[j][2]);
+        for (int j = 0; j < 3; j++) PS(i, 3 + j) = ::fmaf(a[2], A[j][2], ::fmaf(a[1], A[j][1], ::fmaf(a[0], A[j][0], PS(i, 3 + j))));
 #pragma unroll
-        for (int j = 0; j < 3; j++) PS(i, 6 + j) = a0 * S[j][0] + a1 * S[j][1] + a2 * S[j][2];
-#pragma unroll
-        for (int j = 0; j < 3; j++) PS(3 + i, 6 + j) = T[i][0] * S[j][0] + T[i][1] * S[j][1] + T[i][2] * S[j][2];
+        for (int j = 0; j < 3; j++) {
+          const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+          PS(i, 6 + j) = ::fmaf(a[j2], S[j][j2], ::fmaf(a[j1], S[j][j1], a[j]));
+          PS(3 + i, 6 + j) = ::fmaf(T[i][j2], S[j][j2], ::fmaf(T[i][j1], S[j][j1], T[i][j]));
+        }
       }
       // Paa = S Paa S^T
       float W[3][3];
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) W[i][j] = PS(6 + i, 6) * S[j][0] + PS(6 + i, 7) * S[j][1] + PS(6 + i, 8) * S[j][2];
+        for (int j = 0; j < 3; j++) {
+          const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+          W[i][j] = ::fmaf(PS(6 + i, 6 + j2), S[j][j2], ::fmaf(PS(6 + i, 6 + j1), S[j][j1], PS(6 + i, 6 + j)));
+        }
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = i; j < 3; j++) PS(6 + i, 6 + j) = S[i][0] * W[0][j] + S[i][1] * W[1][j] + S[i][2] * W[2][j];
+        for (int j = i; j < 3; j++) {
+          const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+          PS(6 + i, 6 + j) = ::fmaf(S[i][i2], W[i2][j], ::fmaf(S[i][i1], W[i1][j], W[i][j]));
+        }
 #pragma unroll
       for (int k = 0; k < 3; k++) { PS(3 + k, 3 + k) += qa; PS(6 + k, 6 + k) += qg; }
 #undef PS
@@ -1924,8 +1979,8 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
     gf = V3<float>(lpf2(k.lp_gyro, &s.gyro_lp[0], 1, g.x), lpf2(k.lp_gyro, &s.gyro_lp[4], 1, g.y), lpf2(k.lp_gyro, &s.gyro_lp[8], 1, g.z));
     af = V3<float>(lpf2(k.lp_acc, &s.acc_lp[0], 1, a.x), lpf2(k.lp_acc, &s.acc_lp[4], 1, a.y), lpf2(k.lp_acc, &s.acc_lp[8], 1, a.z));
   } else {
-    gf = V3<float>(lpf2_scratch(k.lp_gyro, sc, 0, g.x), lpf2_scratch(k.lp_gyro, sc, 1, g.y), lpf2_scratch(k.lp_gyro, sc, 2, g.z));
-    af = V3<float>(lpf2_scratch(k.lp_acc, sc, 3, a.x), lpf2_scratch(k.lp_acc, sc, 4, a.y), lpf2_scratch(k.lp_acc, sc, 5, a.z));
+    gf = lpf2_scratch3(k.lp_gyro, sc, SQ_LPF, g);
+    af = lpf2_scratch3(k.lp_acc, sc, SQ_LPF + 3, a);
   }
 
   uint32_t fs = bget(s.bits, B_FS_SHIFT, B_FS_MASK);
