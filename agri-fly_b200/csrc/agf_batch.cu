@@ -666,6 +666,15 @@ struct BatchImpl : Batch {
 
   void set_noise_params(uint64_t seed, double sg, double sa, double bg, double ba, double su_) {
     sh.seed = seed;
+    {  // Philox4x32-10 round keys, read by the kernels from the constant bank (agf_step.cuh philox_round_keys)
+      uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+      for (int r = 0; r < 10; r++) {
+        sh.philox_rk[2 * r] = k0;
+        sh.philox_rk[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+      }
+    }
     sh.sigma_gyro = float(sg);
     sh.sigma_acc = float(sa);
     sh.bias_sigma_gyro = float(bg);

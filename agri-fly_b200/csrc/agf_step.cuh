@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 
 #include "agf_math.h"
@@ -387,6 +388,15 @@ AGF_DEV float lpf2(const Lpf2Coef& c, float* st, int stride, float in) {
 // Philox4x32-10 counter-based generator and Box-Muller normals (replaces the per-object
 // std::default_random_engine of Quadcopter_T.hpp:122-123 and the global mt19937 of UWBNetwork.cpp:4)
 // ---------------------------------------------------------------------------------------------
+AGF_DEV float bits_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
 AGF_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
   return __umulhi(a, b);
@@ -394,15 +404,27 @@ AGF_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
   return uint32_t((uint64_t(a) * uint64_t(b)) >> 32);
 #endif
 }
+// Round keys key + r * (0x9E3779B9, 0xBB67AE85) are the same for every draw of a batch: the host tabulates them
+// (philox_round_keys, StepShared::philox_rk) and the rounds read them from the constant bank.
+#ifndef AGF_PHILOX_ROUNDS
+#define AGF_PHILOX_ROUNDS 10
+#endif
+AGF_HDI void philox_round_keys(uint64_t seed, uint32_t* rk /* [2 * AGF_PHILOX_ROUNDS] */) {
+  uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+  for (int r = 0; r < AGF_PHILOX_ROUNDS; r++) {
+    rk[2 * r] = k0;
+    rk[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
 template<int ROUNDS>
-AGF_DEV uint4 philox4x32(uint4 ctr, uint2 key) {
+AGF_DEV uint4 philox4x32(uint4 ctr, const uint32_t* rk) {
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++) {
     const uint32_t hi0 = mulhi32(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
     const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
+    ctr = make_uint4(hi1 ^ ctr.y ^ rk[2 * r], lo1, hi0 ^ ctr.w ^ rk[2 * r + 1], lo0);
   }
   return ctr;
 }
@@ -426,12 +448,8 @@ AGF_DEV void box_muller21(uint32_t f1, uint32_t f2, float& n0, float& n1) {
   n1 = r * sn;
 }
 // 6 standard normals for (vehicle, cycle, stream): ONE Philox4x32-10 block, its 128 bits cut into six 21-bit fields
-AGF_DEV void normals6(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream, float* n) {
-  const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
-#ifndef AGF_PHILOX_ROUNDS
-#define AGF_PHILOX_ROUNDS 10
-#endif
-  const uint4 r = philox4x32<AGF_PHILOX_ROUNDS>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream), key);
+AGF_DEV void normals6(const uint32_t* rk, uint64_t vehicle, uint32_t cycle, uint32_t stream, float* n) {
+  const uint4 r = philox4x32<AGF_PHILOX_ROUNDS>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), cycle, stream), rk);
   const uint32_t m = 0x1FFFFFu;
   box_muller21(r.x & m, ((r.x >> 21) | (r.y << 11)) & m, n[0], n[1]);
   box_muller21((r.y >> 10) & m, r.z & m, n[2], n[3]);
@@ -442,7 +460,9 @@ struct Normals6 {
 };
 static AGF_COLD Normals6 normals6_cold(uint64_t seed, uint64_t vehicle, uint32_t cycle, uint32_t stream) {
   Normals6 o;
-  normals6(seed, vehicle, cycle, stream, o.n);
+  uint32_t rk[2 * AGF_PHILOX_ROUNDS];
+  philox_round_keys(seed, rk);
+  normals6(rk, vehicle, cycle, stream, o.n);
   return o;
 }
 
@@ -2155,6 +2175,9 @@ AGF_DEV void radio_deliver(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, 
 }
 
 AGF_DEV uint32_t sat_add(uint32_t a, uint32_t d) { return a > 0xF0000000u ? a : a + d; }
+// the same stopwatch for the fast variants: add, then clamp -- two instructions; it differs from sat_add only in the value a
+// saturated counter holds (exactly the cap instead of up to cap + d), far above every threshold the logic compares it with
+AGF_DEV uint32_t sat_add_fast(uint32_t a, uint32_t d) { return min(a + d, 0xF0000000u); }
 
 // ---------------------------------------------------------------------------------------------
 // one tick: [radio delivery] -> Quadcopter_T::Run -> UWBNetwork::Run -> clock advance
@@ -2193,7 +2216,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     }
   }
   if (plan.run_plant) {
-    const P dt = P(double(plan.plant_dt_us) * 1e-6);
+    const P dt = sizeof(P) == 4 ? P(plan.plant_dt_f32) : P(double(plan.plant_dt_us) * 1e-6);
     const P inv_dt = PARITY ? P(0) : P(1) / dt;
     // ---- motors (Motor.cpp:39-84).  Axes are (0,0,+-1) and thrust is (0,0,f): the products with
     // the exact-zero components are dropped, the rest keeps the reference's order.
@@ -2318,7 +2341,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       }
       if (p.noise_on) {
         float nrm[6];
-        normals6(p.seed, gidx, s.cycle, 0u, nrm);
+        normals6(p.philox_rk, gidx, s.cycle, 0u, nrm);
         g = g + V3<float>(nrm[0], nrm[1], nrm[2]) * p.sigma_gyro;
         a = a + V3<float>(nrm[3], nrm[4], nrm[5]) * p.sigma_acc;
         if (AGF_UNLIKELY(p.bias_on)) {  // constant per vehicle: counter (vehicle, 0xFFFFFFFF, 1)
@@ -2327,7 +2350,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
           a = a + V3<float>(b.n[3], b.n[4], b.n[5]) * p.bias_sigma_acc;
         }
       }
-      logic_run<PARITY>(s, sc, p, g, a, float(plan.kf_dt_us) * 1e-6f);
+      logic_run<PARITY>(s, sc, p, g, a, plan.kf_dt_f32);
       if constexpr (UWB) {  // radio exchange :191-199
         s.rpos[0] = s.pos[0]; s.rpos[1] = s.pos[1]; s.rpos[2] = s.pos[2];
         if (s.bits & B_RADIO_MEAS_NEW) {  // SetUWBMeasurement (QuadcopterLogic.hpp:61-69)
@@ -2388,12 +2411,22 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       sq_store(sc, (UWB ? SQ_QUADS_UWB : SQ_QUADS_NOUWB) + int(plan.off_gen_slot), c);
     }
   }
-  s.age_radio = sat_add(s.age_radio, dt_us);
-  s.age_uwb = sat_add(s.age_uwb, dt_us);
-  if (HK) {
-    s.age_est_reset = sat_add(s.age_est_reset, dt_us);
-    s.age_mon_cmd = sat_add(s.age_mon_cmd, dt_us);
-    s.age_mon_loop = sat_add(s.age_mon_loop, dt_us);
+  if constexpr (PARITY) {
+    s.age_radio = sat_add(s.age_radio, dt_us);
+    s.age_uwb = sat_add(s.age_uwb, dt_us);
+    if (HK) {
+      s.age_est_reset = sat_add(s.age_est_reset, dt_us);
+      s.age_mon_cmd = sat_add(s.age_mon_cmd, dt_us);
+      s.age_mon_loop = sat_add(s.age_mon_loop, dt_us);
+    }
+  } else {
+    s.age_radio = sat_add_fast(s.age_radio, dt_us);
+    s.age_uwb = sat_add_fast(s.age_uwb, dt_us);
+    if (HK) {
+      s.age_est_reset = sat_add_fast(s.age_est_reset, dt_us);
+      s.age_mon_cmd = sat_add_fast(s.age_mon_cmd, dt_us);
+      s.age_mon_loop = sat_add_fast(s.age_mon_loop, dt_us);
+    }
   }
 }
 
@@ -2504,7 +2537,7 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
       si++;
       next_cmd = si < L.sched_end ? uint32_t(L.sched[si].tick - L.tick0) : 0xFFFFFFFFu;
     }
-    const TickPlan plan = unpack_plan(pp.x, pp.y, pp.z);
+    const TickPlan plan = unpack_plan(pp.x, pp.y, bits_float(pp.z), bits_float(pp.w));
     if (t + 1 < t1) pp = ldro_(L.plans + t + 1);
     tick<P, PARITY, UWB, HK, OFFB>(s, sc, L.sh, pv, plan, L.now0_us + uint64_t(t) * L.dt_us, L.dt_us, abs_tick, gidx, i, L.n);
     if (L.log && --log_in == 0) {

@@ -166,6 +166,7 @@ AGF_HDI void off_wait_set(Timing& ts, uint32_t slot, uint32_t value) {
 
 struct TickPlan {
   uint32_t plant_dt_us, kf_dt_us;
+  float plant_dt_f32, kf_dt_f32;  // the same intervals in seconds as the FP32 code needs them, converted once per launch on the host
   bool run_plant, run_logic, run_net, net_start, net_complete, net_reset, has_target;
   bool off_deliver, off_generate, mocap_update;
   uint32_t off_deliver_slot, off_gen_slot;
@@ -176,6 +177,8 @@ AGF_HDI TickPlan timing_plan(const Timing& ts, const TimingConsts& tc, uint32_t 
   TickPlan p;
   p.plant_dt_us = ts.integ_age;
   p.kf_dt_us = ts.kf_age;
+  p.kf_dt_f32 = float(ts.kf_age) * 1e-6f;
+  p.plant_dt_f32 = float(double(ts.integ_age) * 1e-6);
   // Quadcopter_T.cpp:87-90: dt = GetSeconds<double>(); if (dt < 1e-6) return;
   p.run_plant = ts.integ_age >= tc.plant_min_age_us;
   // Quadcopter_T.cpp:159: if (_timerOnboardLogic.GetSeconds<double>() > _onboardLogicPeriod)
@@ -246,7 +249,9 @@ AGF_HDI void timing_advance(Timing& ts, const TimingConsts& tc, const TickPlan& 
 enum { PP_RUN_PLANT = 1u, PP_RUN_LOGIC = 2u, PP_NET_START = 4u, PP_NET_COMPLETE = 8u, PP_OFF_DELIVER = 16u, PP_OFF_GENERATE = 32u,
        PP_MOCAP = 64u, PP_DSLOT_SHIFT = 8, PP_GSLOT_SHIFT = 12 };
 struct PackedPlan {
-  uint32_t flags, plant_dt_us, kf_dt_us, pad;
+  uint32_t flags, plant_dt_us;
+  float kf_dt_f32;     // float(kf_dt_us) * 1e-6f          (KalmanFilter6DOF's dt, QuadcopterLogic.cpp:229)
+  float plant_dt_f32;  // float(double(plant_dt_us) * 1e-6) (Quadcopter_T.cpp:87 in the FP32 plant)
 };
 inline PackedPlan pack_plan(const TickPlan& p) {
   PackedPlan q;
@@ -254,14 +259,16 @@ inline PackedPlan pack_plan(const TickPlan& p) {
             (p.net_complete ? PP_NET_COMPLETE : 0u) | (p.off_deliver ? PP_OFF_DELIVER : 0u) | (p.off_generate ? PP_OFF_GENERATE : 0u) |
             (p.mocap_update ? PP_MOCAP : 0u) | (p.off_deliver_slot << PP_DSLOT_SHIFT) | (p.off_gen_slot << PP_GSLOT_SHIFT);
   q.plant_dt_us = p.plant_dt_us;
-  q.kf_dt_us = p.kf_dt_us;
-  q.pad = 0;
+  q.kf_dt_f32 = float(p.kf_dt_us) * 1e-6f;
+  q.plant_dt_f32 = float(double(p.plant_dt_us) * 1e-6);
   return q;
 }
-AGF_HDI TickPlan unpack_plan(uint32_t flags, uint32_t plant_dt_us, uint32_t kf_dt_us) {
+AGF_HDI TickPlan unpack_plan(uint32_t flags, uint32_t plant_dt_us, float kf_dt_f32, float plant_dt_f32) {
   TickPlan p;
   p.plant_dt_us = plant_dt_us;
-  p.kf_dt_us = kf_dt_us;
+  p.kf_dt_us = 0;  // host-side bookkeeping only
+  p.kf_dt_f32 = kf_dt_f32;
+  p.plant_dt_f32 = plant_dt_f32;
   p.run_plant = (flags & PP_RUN_PLANT) != 0;
   p.run_logic = (flags & PP_RUN_LOGIC) != 0;
   p.net_start = (flags & PP_NET_START) != 0;
@@ -327,6 +334,7 @@ struct StepShared {
   AnchorDev anchors[AGF_MAX_UWB_ANCHORS];
   uint32_t n_anchors;
   uint64_t seed;
+  uint32_t philox_rk[20];  // Philox4x32-10 round keys of `seed` (agf_step.cuh philox_round_keys)
   int noise_on, bias_on, uwb_noise_on;
   float sigma_gyro, sigma_acc, bias_sigma_gyro, bias_sigma_acc, uwb_sigma;
 };
