@@ -409,6 +409,10 @@ class Batch:
         _check(self.L.agf_batch_set_noise(self.h, seed, sigma_gyro, sigma_acc, bias_sigma_gyro, bias_sigma_acc))
 
     # logging / statistics
+    def set_uwb_noise(self, noise_std_dev, outlier_probability=0.0, outlier_std_dev=0.0):
+        """UWBNetwork::SetNoiseProperties (UWBNetwork.hpp:28-33)"""
+        _check(self.L.agf_batch_set_uwb_noise(self.h, float(noise_std_dev), float(outlier_probability), float(outlier_std_dev)))
+
     def enable_log(self, stride, capacity):
         _check(self.L.agf_batch_enable_log(self.h, stride, capacity))
 

@@ -25,7 +25,7 @@ FIELDS = {
     "est_angular_velocity": (9, "f4", 3), "accelerometer": (10, "f4", 3), "rate_gyro": (11, "f4", 3),
     "flight_state": (12, "i4", 1), "panic_reason": (13, "i4", 1), "motor_force": (14, "f8", 4),
     "est_covariance": (15, "f4", 81), "cycle_counter": (16, "i4", 1), "kf_counters": (17, "i4", 4),
-    "des_motor_force": (18, "f4", 4),
+    "des_motor_force": (18, "f4", 4), "uwb_measurement": (19, "f4", 2),
 }
 
 
@@ -256,6 +256,7 @@ PROTOTYPES = {
     "agf_nccl_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_void_p)]),
     "agf_nccl_comm_init_all": (C.c_int, [C.c_int, _P(C.c_int), _P(C.c_void_p)]),
     "agf_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
+    "agf_batch_set_uwb_noise": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "agf_batch_launch_count": (C.c_uint64, [C.c_void_p]),
     "agf_batch_step_kernel_time": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_uint64)]),
     "agf_last_error_string": (C.c_char_p, []),

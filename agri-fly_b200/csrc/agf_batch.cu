@@ -81,6 +81,10 @@ __device__ inline double f_get(const FieldCtx<P>& c, int field, size_t i, int co
     case AGF_F_ACCELEROMETER: *kind = 1; *as_float = c.sf[sidx(SF_ACC_LP + 4 * comp + 3, c.n, i, 4)]; return 0;
     case AGF_F_RATE_GYRO: *kind = 1; *as_float = c.sf[sidx(SF_GYRO_LP + 4 * comp + 3, c.n, i, 4)]; return 0;
     case AGF_F_EST_COVARIANCE: *kind = 1; *as_float = c.sc ? c.sc[sidx(comp, c.n, i, 4)] : 0.0f; return 0;
+    case AGF_F_UWB_MEASUREMENT:
+      *kind = 1;
+      *as_float = comp == 0 ? c.sf[sidx(SF_UWB_RANGE, c.n, i, 4)] : float((c.su[sidx(SU_UWBW, c.n, i, 4)] >> 8) & 0xFFu);
+      return 0;
     case AGF_F_FLIGHT_STATE: *kind = 2; *as_int = int(c.su[sidx(SU_BITS, c.n, i, 4)] & 0x7u); return 0;
     case AGF_F_PANIC_REASON: *kind = 2; *as_int = int((c.su[sidx(SU_BITS, c.n, i, 4)] >> 3) & 0x7u); return 0;
     case AGF_F_CYCLE_COUNTER: *kind = 2; *as_int = int(c.su[sidx(SU_CYCLE, c.n, i, 4)]); return 0;
@@ -524,6 +528,8 @@ static size_t field_ncomp(int field) {
       return 4;
     case AGF_F_FLIGHT_STATE: case AGF_F_PANIC_REASON: case AGF_F_CYCLE_COUNTER:
       return 1;
+    case AGF_F_UWB_MEASUREMENT:
+      return 2;
     case AGF_F_EST_COVARIANCE:
       return 81;
   }
@@ -682,7 +688,14 @@ struct BatchImpl : Batch {
     sh.uwb_sigma = float(su_);
     sh.bias_on = (bg != 0.0 || ba != 0.0) ? 1 : 0;
     sh.noise_on = (sg != 0.0 || sa != 0.0 || sh.bias_on) ? 1 : 0;
-    sh.uwb_noise_on = su_ != 0.0 ? 1 : 0;
+    sh.uwb_noise_on = (su_ != 0.0 || sh.uwb_outlier_prob > 0.0f) ? 1 : 0;
+  }
+  void set_uwb_noise(double noise, double p_out, double s_out) {
+    opts.uwb_noise_std_dev = noise;
+    sh.uwb_sigma = float(noise);
+    sh.uwb_outlier_prob = float(p_out);
+    sh.uwb_outlier_sigma = float(s_out);
+    sh.uwb_noise_on = (noise != 0.0 || p_out > 0.0) ? 1 : 0;
   }
 
   // constructor-time state (SimulationObject6DOF.hpp:14-19, QuadcopterLogic::ResetCounters/Initialise,
@@ -1568,6 +1581,16 @@ int agf_batch_set_noise(agf_batch* b, uint64_t seed, double sg, double sa, doubl
   } else {
     auto* x = static_cast<agf::BatchImpl<float>*>(B(b));
     x->set_noise_params(seed, sg, sa, bg, ba, x->opts.uwb_noise_std_dev);
+  }
+  return AGF_OK;
+}
+int agf_batch_set_uwb_noise(agf_batch* b, double noise, double p_out, double s_out) {
+  if (!b) return fail(AGF_EINVAL, "null handle");
+  if (!(noise >= 0.0) || !(p_out >= 0.0 && p_out <= 1.0) || !(s_out >= 0.0)) return fail(AGF_EINVAL, "bad UWB noise properties");
+  if (B(b)->opts.precision == AGF_PREC_FP64) {
+    static_cast<agf::BatchImpl<double>*>(B(b))->set_uwb_noise(noise, p_out, s_out);
+  } else {
+    static_cast<agf::BatchImpl<float>*>(B(b))->set_uwb_noise(noise, p_out, s_out);
   }
   return AGF_OK;
 }

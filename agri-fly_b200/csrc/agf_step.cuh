@@ -466,6 +466,22 @@ static AGF_COLD Normals6 normals6_cold(uint64_t seed, uint64_t vehicle, uint32_t
   return o;
 }
 
+// One completed UWB range (UWBNetwork.cpp:62-75): the uniform that decides "outlier?", the normal of the additive range
+// noise and the normal of an outlier, from ONE Philox block of stream 2, counter (vehicle, tick).
+struct UwbDraw {
+  float u, n_noise, n_outlier;
+};
+static AGF_COLD UwbDraw uwb_draw_cold(uint64_t seed, uint64_t vehicle, uint32_t tick) {
+  uint32_t rk[2 * AGF_PHILOX_ROUNDS];
+  philox_round_keys(seed, rk);
+  const uint4 r = philox4x32<AGF_PHILOX_ROUNDS>(make_uint4(uint32_t(vehicle), uint32_t(vehicle >> 32), tick, 2u), rk);
+  const uint32_t m = 0x1FFFFFu;
+  UwbDraw d;
+  box_muller21(r.x & m, ((r.x >> 21) | (r.y << 11)) & m, d.n_noise, d.n_outlier);
+  d.u = float(r.w >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // register-resident vehicle state
 // ---------------------------------------------------------------------------------------------
@@ -2377,9 +2393,13 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
       const V3<P> d = V3<P>(s.rpos[0], s.rpos[1], s.rpos[2]) -
                       V3<P>(P(p.anchors[resp].x), P(p.anchors[resp].y), P(p.anchors[resp].z));
       P r = norm(d);
-      if (AGF_UNLIKELY(p.uwb_noise_on)) {
-        const Normals6 nrm = normals6_cold(p.seed, gidx, uint32_t(abs_tick), 2u);
-        r = r + P(nrm.n[0]) * P(p.uwb_sigma);
+      if (AGF_UNLIKELY(p.uwb_noise_on)) {  // :62-72
+        const UwbDraw dr = uwb_draw_cold(p.seed, gidx, uint32_t(abs_tick));
+        if (dr.u < p.uwb_outlier_prob) {
+          r = P(dr.n_outlier) * P(p.uwb_outlier_sigma);
+        } else {
+          r = r + P(dr.n_noise) * P(p.uwb_sigma);
+        }
       } else {
         r = r + P(0);
       }

@@ -337,6 +337,7 @@ struct StepShared {
   uint32_t philox_rk[20];  // Philox4x32-10 round keys of `seed` (agf_step.cuh philox_round_keys)
   int noise_on, bias_on, uwb_noise_on;
   float sigma_gyro, sigma_acc, bias_sigma_gyro, bias_sigma_acc, uwb_sigma;
+  float uwb_outlier_prob, uwb_outlier_sigma;  // UWBNetwork::SetNoiseProperties (UWBNetwork.hpp:28-33)
 };
 
 // plant parameters that may vary per vehicle (parameter sweeps)

@@ -239,7 +239,7 @@ typedef struct agf_batch_opts {
    * reference's values; a noise-free run sets both to 0.  Bias is an extension (0 = reference). */
   double sigma_acc, sigma_gyro;
   double bias_sigma_acc, bias_sigma_gyro;
-  double uwb_noise_std_dev; /* UWBNetwork::SetNoiseProperties (UWBNetwork.hpp:28); outliers unsupported */
+  double uwb_noise_std_dev; /* UWBNetwork::SetNoiseProperties' noiseStdDev (UWBNetwork.hpp:28); outliers: agf_batch_set_uwb_noise */
   uint64_t seed;            /* Philox key                                                       */
   uint64_t first_global_index; /* index of vehicle 0 of this shard in the whole population (RNG counter) */
   void* stream;             /* cudaStream_t to launch on; NULL = a stream owned by the handle   */
@@ -293,6 +293,8 @@ enum {
   AGF_F_CYCLE_COUNTER = 16, /* int32[1]  QuadcopterLogic::GetCycleCounter                 */
   AGF_F_KF_COUNTERS = 17,  /* int32[4]  {numResets, numMeasRejected, uwbMeasCount, imuInit|uwbInit<<1} (read only) */
   AGF_F_DES_MOTOR_FORCE = 18, /* float[4] _desMotorForcesForTelemetry (read only)          */
+  AGF_F_UWB_MEASUREMENT = 19, /* float[2] UWBRadio::_meas of the vehicle's radio: {range [m], index of the responding anchor in
+                                 AddUWBRadioTarget order} (UWBRadio.hpp:17-94; read only)                       */
   AGF_F_COUNT_
 };
 int agf_batch_get_field(agf_batch* b, int field, void* host_dst, size_t first, size_t count);
@@ -302,6 +304,13 @@ int agf_batch_set_field(agf_batch* b, int field, const void* host_src, size_t fi
 int agf_batch_set_state(agf_batch* b, const double* state13, size_t first, size_t count);
 /* bytes per vehicle of a field's host representation */
 size_t agf_field_size(int field);
+
+/* UWBNetwork::SetNoiseProperties(noiseStdDev, outlierProbability, outlierStdDev) (UWBNetwork.hpp:28-33) for every vehicle's
+ * private ranging network, with the reference's measurement model (UWBNetwork.cpp:62-75): with probability
+ * outlier_probability a completed range is an outlier, range = N(0,1) * outlier_std_dev (NOT centred on the true distance),
+ * otherwise range = true distance + N(0,1) * noise_std_dev.  Draws are counter-based Philox (vehicle, tick, stream 2), so they
+ * do not depend on sharding or launch chunking; the reference's single global std::mt19937 is not reproduced. */
+int agf_batch_set_uwb_noise(agf_batch* b, double noise_std_dev, double outlier_probability, double outlier_std_dev);
 
 /* SimulationObject6DOF::SetCommandRadioMsg (SimulationObject6DOF.hpp:64): deliver now, i.e. before
  * the next Run().  raw is [count][23], or one packet for all vehicles in [first, first+count) when

@@ -31,6 +31,7 @@ typedef struct orc_opts {
   double uwb_comm_period;      /* <= 0: no UWB network  */
   double sigma_acc, sigma_gyro; /* IMU noise std dev (reference: 0.2 / 0.1, Quadcopter_T.cpp:5-6) */
   double uwb_noise_std_dev;
+  double uwb_outlier_probability, uwb_outlier_std_dev; /* UWBNetwork::SetNoiseProperties (ref flavours only) */
 } orc_opts;
 
 /* everything observable, for deep parity checks */

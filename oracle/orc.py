@@ -36,7 +36,7 @@ COL = dict(pos=slice(0, 3), vel=slice(3, 6), att=slice(6, 10), angvel=slice(10, 
 class OrcOpts(C.Structure):
     _fields_ = [("onboard_logic_period", C.c_double), ("uwb_comm_period", C.c_double),
                 ("sigma_acc", C.c_double), ("sigma_gyro", C.c_double),
-                ("uwb_noise_std_dev", C.c_double)]
+                ("uwb_noise_std_dev", C.c_double), ("uwb_outlier_probability", C.c_double), ("uwb_outlier_std_dev", C.c_double)]
 
 
 class FullState(C.Structure):
@@ -167,8 +167,9 @@ class Oracle:
 
     def run_population(self, cfgs, n, init13=None, anchors=None, dt_us=2000, nticks=1, sched=(),
                        slot_raw=None, threads=1, onboard_logic_period=1.0 / 500.0, uwb_comm_period=0.0,
-                       sigma_acc=0.0, sigma_gyro=0.0):
-        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, 0.0)
+                       sigma_acc=0.0, sigma_gyro=0.0, uwb_noise_std_dev=0.0, uwb_outlier_probability=0.0, uwb_outlier_std_dev=0.0):
+        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, uwb_noise_std_dev, uwb_outlier_probability,
+                       uwb_outlier_std_dev)
         if isinstance(cfgs, abi.VehicleCfg):
             carr = (abi.VehicleCfg * 1)(cfgs)
             ncfg = 1
@@ -263,10 +264,11 @@ class RefCodec:
 
 class OracleVehicle:
     def __init__(self, orc, cfg, onboard_logic_period=1.0 / 500.0, uwb_comm_period=0.0,
-                 sigma_acc=0.0, sigma_gyro=0.0, uwb_noise_std_dev=0.0):
+                 sigma_acc=0.0, sigma_gyro=0.0, uwb_noise_std_dev=0.0, uwb_outlier_probability=0.0, uwb_outlier_std_dev=0.0):
         self.orc = orc
         self.L = orc.L
-        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, uwb_noise_std_dev)
+        opts = OrcOpts(onboard_logic_period, uwb_comm_period, sigma_acc, sigma_gyro, uwb_noise_std_dev, uwb_outlier_probability,
+                       uwb_outlier_std_dev)
         self.h = self.L.orc_create(C.byref(cfg), C.byref(opts))
 
     def close(self):

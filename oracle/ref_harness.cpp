@@ -132,7 +132,7 @@ orc_vehicle* orc_create(const agf_vehicle_cfg* cfg, const orc_opts* opts) {
   v->quad->_stdDevRateGyroNoise = opts->sigma_gyro;
   if (opts->uwb_comm_period > 0) {
     v->net.reset(new Simulation::UWBNetwork(&v->timer, opts->uwb_comm_period));
-    v->net->SetNoiseProperties(opts->uwb_noise_std_dev, 0, 0);
+    v->net->SetNoiseProperties(opts->uwb_noise_std_dev, opts->uwb_outlier_probability, opts->uwb_outlier_std_dev);
     v->net->AddRadio(v->quad->GetRadio());
   }
   return v;

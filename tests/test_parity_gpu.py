@@ -738,3 +738,140 @@ def test_trajectory_log_ring(agf):
     with pytest.raises(agf.AgfError):
         b.read_log(0)  # overwritten
     b.close()
+
+
+def _collect_ranges(agf, b, nticks):
+    """steps one tick at a time and returns, per vehicle, every NEW range its radio received: (tick, range, anchor index)"""
+    prev = b.get("uwb_measurement")
+    out = []
+    for k in range(nticks):
+        b.run(1)
+        m = b.get("uwb_measurement")
+        new = m[:, 0] != prev[:, 0]
+        out.append((new, m.copy()))
+        prev = m
+    return out
+
+
+def test_uwb_range_noise_matches_the_stated_distribution(agf):
+    """UWBNetwork::SetNoiseProperties(noiseStdDev, 0, 0) (UWBNetwork.hpp:28, .cpp:68-72): range = true distance + N(0,1) * sigma.
+    4 096 vehicles at rest on the ground, every completed range of every vehicle: zero mean, sigma, white in time,
+    independent across vehicles, normal (Kolmogorov-Smirnov)."""
+    from scipy import stats as sps
+    n, sigma = 4096, 0.1
+    s = agf.scenarios
+    b = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, uwb_comm_period=0.004, uwb_noise_std_dev=sigma, seed=31)
+    for i, p in s.ANCHORS_8:
+        b.add_anchor(i, p)
+    init = s.monte_carlo_initial_states(n, seed=5)
+    b.set_state13(init)
+    anchors = np.array([p for _, p in s.ANCHORS_8])
+    recs = _collect_ranges(agf, b, 240)
+    b.close()
+    err = []   # [sample][vehicle] range - true distance, in the order the ranges arrived
+    for new, m in recs:
+        if new.mean() < 0.5:
+            continue
+        assert new.all()  # the network's timing is the clock's: every vehicle receives its range at the same tick
+        true = np.linalg.norm(init[:, 0:3] - anchors[m[:, 1].astype(int)], axis=1)
+        err.append(m[:, 0] - true)
+    err = np.array(err)
+    k = err.shape[0]
+    assert k >= 70  # one range every 3 ticks (commPeriod 4 ms + 1 tick)
+    flat = err.ravel()
+    assert abs(flat.mean()) < 4 * sigma / np.sqrt(flat.size)
+    assert abs(flat.std() / sigma - 1) < 0.01
+    lag1 = np.mean(err[1:] * err[:-1]) / sigma**2
+    cross = np.mean(err[:, 1:] * err[:, :-1]) / sigma**2
+    assert abs(lag1) < 5 / np.sqrt(flat.size) and abs(cross) < 5 / np.sqrt(flat.size)
+    assert sps.kstest(flat[::7] / sigma, "norm").pvalue > 1e-3
+    print("uwb noise: %d ranges, mean %.2e, sigma %.5f, lag-1 %.2e, cross-vehicle %.2e" % (flat.size, flat.mean(), flat.std(), lag1, cross))
+
+
+def test_uwb_outlier_model_rate_and_distribution(agf):
+    """UWBNetwork.cpp:62-67: with probability outlierProbability the range is N(0,1) * outlierStdDev -- not centred on the
+    true distance.  Rate (binomial, exact expectation including the outliers that happen to land near the truth) and
+    distribution of the outlier values."""
+    from scipy import stats as sps
+    n, sigma, p_out, s_out = 4096, 0.02, 0.25, 4.0
+    s = agf.scenarios
+    b = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, uwb_comm_period=0.004, seed=77)
+    b.set_uwb_noise(sigma, p_out, s_out)
+    for i, p in s.ANCHORS_8:
+        b.add_anchor(i, p)
+    init = s.monte_carlo_initial_states(n, seed=6)
+    b.set_state13(init)
+    anchors = np.array([p for _, p in s.ANCHORS_8])
+    recs = _collect_ranges(agf, b, 150)
+    b.close()
+    thr = 10 * sigma
+    n_flag = n_all = 0
+    expect = 0.0
+    vals = []
+    for new, m in recs:
+        if not new.any():
+            continue
+        true = np.linalg.norm(init[:, 0:3] - anchors[m[:, 1].astype(int)], axis=1)[new]
+        r = m[new, 0]
+        flag = np.abs(r - true) > thr
+        n_flag += flag.sum()
+        n_all += flag.size
+        # an outlier within +-thr of the truth is not flagged
+        q = sps.norm.cdf((true + thr) / s_out) - sps.norm.cdf((true - thr) / s_out)
+        expect += np.sum(p_out * (1 - q))
+        vals.append(r[flag])
+    vals = np.concatenate(vals)
+    z = (n_flag - expect) / np.sqrt(expect * (1 - p_out))
+    print("uwb outliers: %d of %d ranges flagged, expected %.1f (z = %.2f); outlier mean %.3f sigma %.3f" %
+          (n_flag, n_all, expect, z, vals.mean(), vals.std()))
+    assert n_all > 100000 and abs(z) < 4.5
+    assert abs(vals.mean()) < 5 * s_out / np.sqrt(vals.size) + 0.05 and abs(vals.std() / s_out - 1) < 0.03
+
+
+def test_ekf_gate_under_uwb_outliers_matches_reference_population(agf, orc_mod):
+    """The EKF's 3-sigma gate and reset logic (KalmanFilter6DOF.cpp:272-284) exercised the way the reference intends:
+    hover with range noise AND outliers.  Noise realisations differ (Philox vs the reference's global mt19937), so the
+    comparison is between populations flown by the CUDA path and by the unmodified reference: rejection rate, accepted
+    ranges, tracking error."""
+    from scipy import stats as sps
+    if not orc_mod.available("ref-glibc"):
+        pytest.skip("oracle/_ref was not built (needs the reference tree at build time)")
+    R = orc_mod.Oracle("ref-glibc")
+    n, nt = 1024, 2500
+    sigma, p_out, s_out = 0.05, 0.05, 10.0  # outliers far from the truth: the gate rejects nearly all of them (43 of 832 ranges)
+    s = agf.scenarios
+    sc = s.full_scenario(agf.codec, nticks=nt)
+    init = s.monte_carlo_initial_states(n, seed=4321, yaw_max=np.pi / 3)
+    idle = agf.codec.encode_idle(0)
+    slot = np.array([np.frombuffer(agf.codec.encode_position(0, (p[0], p[1], 1.5)), np.uint8) for p in init])
+    sched = [(d, idle, -1) if sl == -2 else (d, None, 0) for d, _, sl in s.hover_slot_schedule(nt)]
+    cfg = cfg_for(agf, sc)
+    anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
+    slots = np.zeros((4, n, 23), np.uint8)
+    slots[0] = slot
+    ref, _ = R.run_population(cfg, n, init13=init, anchors=anchors, nticks=nt, sched=sched, slot_raw=slots,
+                              threads=os.cpu_count() or 1, uwb_comm_period=sc["uwb_comm_period"], uwb_noise_std_dev=sigma,
+                              uwb_outlier_probability=p_out, uwb_outlier_std_dev=s_out)
+    tgt = np.column_stack([init[:, 0], init[:, 1], np.full(n, 1.5)])
+    e_ref = np.linalg.norm(ref[:, 0:3] - tgt, axis=1)
+    for name, kw in (("fp64-parity", {}), ("fp32-fast", dict(precision=agf.abi.PREC_FP32, math=agf.abi.MATH_FAST))):
+        b = agf.Batch(cfg, n, uwb_comm_period=sc["uwb_comm_period"], seed=9, **kw)
+        b.set_uwb_noise(sigma, p_out, s_out)
+        for i, p in sc["anchors"]:
+            b.add_anchor(i, p)
+        b.set_state13(init)
+        b.set_slot(0, slot)
+        b.set_schedule(sched)
+        b.run(nt)
+        got = b.record()
+        b.close()
+        e = np.linalg.norm(got[:, 0:3] - tgt, axis=1)
+        rej, rej_ref = got[:, 38].mean(), ref[:, 38].mean()
+        print("%s: rejected per vehicle %.2f (reference %.2f) of %.0f ranges, resets %.3f (%.3f), tracking error %.4f (%.4f), panics %d (%d)" %
+              (name, rej, rej_ref, got[:, 39].mean(), got[:, 37].mean(), ref[:, 37].mean(), e.mean(), e_ref.mean(),
+               np.sum(got[:, 35] != 0), np.sum(ref[:, 35] != 0)))
+        assert np.array_equal(got[:, 39], ref[:, 39])              # the network's timing is the clock's
+        assert rej_ref > 20 and abs(rej / rej_ref - 1) < 0.10      # the gate sees the outliers at the reference's rate
+        assert abs(got[:, 37].mean() - ref[:, 37].mean()) < 0.15   # and does not reset more often (2 resets at start-up + ~0.2)
+        assert abs(np.median(e) / np.median(e_ref) - 1) < 0.15 and sps.ks_2samp(e, e_ref).pvalue > 1e-4
+        assert abs(int(np.sum(got[:, 35] != 0)) - int(np.sum(ref[:, 35] != 0))) <= 8
