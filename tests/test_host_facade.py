@@ -109,3 +109,50 @@ def test_fleet_example_writes_the_reference_csv(agf, orc_mod):
     np.testing.assert_allclose(rows[:, 10:13], want[:, 10:13], rtol=2e-5, atol=1e-9)  # angular velocity
     assert rows[:, 3].max() > 0.9 and rows[-1, 3] < 0.05 and np.all(rows[:, 35] == 0)   # took off, landed, no panic
     assert np.max(np.abs(rows[:, 17:20] - rows[:, 1:4])) < 0.1                           # estimate follows the truth
+
+
+MC = os.path.join(ROOT, "examples", "monte_carlo_fleet.cpp")
+MC_BIN = os.path.join(ROOT, "examples", "monte_carlo_fleet")
+
+
+def build_mc():
+    lib_dir = os.path.join(ROOT, "agri-fly_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-pthread", INC[0], MC, "-L" + lib_dir, "-lagrifly_b200",
+                        "-Wl,-rpath," + lib_dir, "-o", MC_BIN], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return MC_BIN
+
+
+def test_monte_carlo_fleet_example_compiles_against_the_c_abi_only(agf):
+    """examples/monte_carlo_fleet.cpp: the multi-GPU host path in C++ -- one thread and one batch per GPU, the statistics
+    read-out over NCCL through agf_batch_reduce_stats_nccl; the program links the C ABI only (no NCCL, no CUDA runtime)."""
+    build_mc()
+    needed = subprocess.check_output(["readelf", "-d", MC_BIN], text=True)
+    assert "libnccl" not in needed and "libcudart" not in needed and "libagrifly_b200" in needed
+
+
+@pytest.mark.gpu
+def test_monte_carlo_fleet_sharded_equals_unsharded(agf):
+    """The C3 population stepped by the C++ example: sharded over the GPUs of the node (one host thread per GPU, statistics
+    all-gathered over NCCL inside the C ABI) against the same population in one batch.  Noise streams are keyed by the
+    population-wide vehicle index, so every vehicle flies the same trajectory either way: the combined statistics agree
+    (sums to rounding -- the order of the additions differs --, maxima and counts exactly).  With one visible GPU the
+    sharded run degenerates to a single rank (the NCCL path is then covered by the 2-GPU bench runs under profiles/)."""
+    import torch
+    build_mc()
+    g = min(2, torch.cuda.device_count())
+    n = 8192
+
+    def run(gpus, per):
+        r = subprocess.run([MC_BIN, str(gpus), str(per), "5", "fp32"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("STATS")][-1].split()
+        return [float(x) for x in line[1:]], r.stdout
+
+    whole, out = run(1, n)
+    parts, out2 = run(g, n // g)
+    print(out2)
+    assert whole[0] == n and parts[0] == n
+    assert whole[3] == parts[3] and whole[4] == parts[4] and whole[2] == parts[2]   # panics, non-finite, max error
+    assert abs(whole[5] / parts[5] - 1) < 1e-12                                       # sum of squared errors
+    assert whole[1] < 0.5 and whole[3] < 0.02 * n                                     # the population tracks its square
