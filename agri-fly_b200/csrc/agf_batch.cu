@@ -7,6 +7,7 @@
 // touches vehicle state runs on the GPU; there is no CPU execution path for the step.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -45,6 +46,14 @@ int fail_from(int code, const char* what, int cuda_error) { return fail(code, wh
     cudaError_t e_ = (call);                                \
     if (e_ != cudaSuccess) return fail(AGF_ECUDA, #call, e_); \
   } while (0)
+
+// Batches that hold a captured read-out graph (stats kernel -> ncclAllGather -> combine).  NCCL keeps a communicator alive
+// while a graph that captured one of its collectives exists -- ncclCommDestroy would wait for ever -- so
+// agf_nccl_comm_destroy first drops the graphs captured with that communicator (release_stats_graphs_for).
+struct Batch;
+static std::mutex g_graph_mutex;
+static std::vector<Batch*> g_graph_owners;
+void release_stats_graphs_for(void* comm);
 
 // ---------------------------------------------------------------------------------------------
 // small kernels around the step: field gather/scatter, immediate radio delivery, telemetry, stats
@@ -445,8 +454,18 @@ struct Batch {
     }
     return AGF_OK;
   }
-  void free_stats_buffers() {
+  void drop_stats_graph() {  // under g_graph_mutex
     if (stats_graph) cudaGraphExecDestroy(stats_graph);
+    stats_graph = nullptr;
+    graph_comm = nullptr;
+    graph_out = nullptr;
+  }
+  void free_stats_buffers() {
+    {
+      std::lock_guard<std::mutex> lock(g_graph_mutex);
+      drop_stats_graph();
+      g_graph_owners.erase(std::remove(g_graph_owners.begin(), g_graph_owners.end(), this), g_graph_owners.end());
+    }
     cudaFree(d_stats_local);
     cudaFree(d_stats_gather);
     cudaFree(d_stats_out);
@@ -480,7 +499,8 @@ struct Batch {
       return AGF_OK;
     };
     nccl_readouts++;
-    if (target || graph_disabled) return body(target);  // a host target is staged per call: not captured
+    static const bool no_graph = [] { const char* e = getenv("AGF_STATS_GRAPH"); return e && e[0] == '0'; }();  // AGF_STATS_GRAPH=0: eager launches
+    if (target || graph_disabled || no_graph) return body(target);  // a host target is staged per call: not captured
     if (stats_graph && graph_comm == comm && graph_out == dev_out) {
       AGF_CUDA(cudaGraphLaunch(stats_graph, stream));
       launches += 2;
@@ -510,13 +530,27 @@ struct Batch {
       return body(nullptr);
     }
     cudaGraphDestroy(g);
-    graph_comm = comm;
-    graph_out = dev_out;
+    {
+      std::lock_guard<std::mutex> lock(g_graph_mutex);
+      graph_comm = comm;
+      graph_out = dev_out;
+      if (std::find(g_graph_owners.begin(), g_graph_owners.end(), this) == g_graph_owners.end()) g_graph_owners.push_back(this);
+    }
     AGF_CUDA(cudaGraphLaunch(stats_graph, stream));
     launches += 2;
     return AGF_OK;
   }
 };
+
+void release_stats_graphs_for(void* comm) {
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  for (Batch* b : g_graph_owners)
+    if (b->graph_comm == comm) {
+      cudaSetDevice(b->opts.device);
+      cudaStreamSynchronize(b->stream);
+      b->drop_stats_graph();
+    }
+}
 
 static size_t field_ncomp(int field) {
   switch (field) {

@@ -14,6 +14,7 @@
 namespace agf {
 
 int fail_from(int code, const char* what, int cuda_error);
+void release_stats_graphs_for(void* comm);  // agf_batch.cu: CUDA graphs that captured a collective of this communicator
 
 const NcclApi* nccl_api(const char** why) {
   static NcclApi api;
@@ -117,6 +118,7 @@ int agf_nccl_comm_destroy(void* comm) {
   const char* why = "";
   const NcclApi* a = agf::nccl_api(&why);
   if (!a) return agf::fail_from(AGF_ENCCL, why, 0);
+  agf::release_stats_graphs_for(comm);  // NCCL would otherwise wait for those graphs to be destroyed
   const int rc = a->CommDestroy(reinterpret_cast<NcclComm>(comm));
   return rc == agf::kNcclSuccess ? AGF_OK : agf::nccl_fail(a, "ncclCommDestroy", rc);
 }

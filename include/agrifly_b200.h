@@ -525,7 +525,10 @@ int agf_batch_reduce_stats(agf_batch* b, const double* host_target, double host_
  * statistics kernel, ONE ncclAllGather of the AGF_STATS_LEN doubles of every rank, and a combine kernel (entries
  * below AGF_ST_MAX_ENORM are summed in rank order, the rest maximised), so every rank ends with the same bits.  From
  * the second call on with the same (communicator, output pointer, no host target) the three are replayed as one
- * captured CUDA graph.  Collective: every rank of the communicator must call it, one host thread per GPU. */
+ * captured CUDA graph.  Collective: every rank of the communicator must call it, one host thread per GPU.  NCCL keeps a
+ * communicator alive while a graph that captured one of its collectives exists: destroy the batch (or use
+ * agf_nccl_comm_destroy, which drops such graphs) BEFORE calling ncclCommDestroy on a communicator of your own.
+ * AGF_STATS_GRAPH=0 in the environment keeps the read-out as three eager launches. */
 int agf_batch_reduce_stats_nccl_device(agf_batch* b, void* nccl_comm, const double* host_target, double* dev_out);
 int agf_batch_reduce_stats_nccl(agf_batch* b, void* nccl_comm, const double* host_target, double host_out[AGF_STATS_LEN]);
 /* Communicator helpers for hosts that do not link NCCL themselves (libnccl.so.2 is resolved at run time; in a process
@@ -537,6 +540,8 @@ int agf_nccl_version(int* version);
 int agf_nccl_get_unique_id(uint8_t id[AGF_NCCL_UNIQUE_ID_BYTES]);
 int agf_nccl_comm_init_rank(const uint8_t id[AGF_NCCL_UNIQUE_ID_BYTES], int nranks, int rank, int device, void** comm_out);
 int agf_nccl_comm_init_all(int ndev, const int* devices, void** comms_out /* [ndev] */);
+/* ncclCommDestroy; first drops the read-out graphs that batches captured with this communicator (no read-out of those
+ * batches may be in flight).  Destroy communicators created here before or after their batches, in any order. */
 int agf_nccl_comm_destroy(void* comm);
 
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches claim) */
