@@ -2,14 +2,21 @@
 // MUST be compiled with -fmad=false (no FMA contraction), default -prec-div/-prec-sqrt (IEEE).
 #include <stdio.h>
 
+#define AGF_MATH_OUTLINE 1  // agf_math.h: the shared libm as real calls (code size; same arithmetic)
 #include "agf_launch.h"
 #include "agf_step.cuh"
 
 namespace agf {
 
+// The in-kernel offboard loop is a template axis here as in the fast kernels: batches without it run kernels that do
+// not contain it (half the code).
 cudaError_t launch_step_parity(const StepLaunch<double>& L, bool uwb, int block, cudaStream_t stream) {
-  if (uwb) return launch_step_kernel<double>(step_kernel<double, true, true, true, false, true>, L, block, 0, stream);
-  return launch_step_kernel<double>(step_kernel<double, true, false, true, false, true>, L, block, 0, stream);
+  if (L.sh.tc.off_enabled) {
+    if (uwb) return launch_step_kernel<double>(step_kernel<double, true, true, true, false, true>, L, block, 0, stream);
+    return launch_step_kernel<double>(step_kernel<double, true, false, true, false, true>, L, block, 0, stream);
+  }
+  if (uwb) return launch_step_kernel<double>(step_kernel<double, true, true, true, false, false>, L, block, 0, stream);
+  return launch_step_kernel<double>(step_kernel<double, true, false, true, false, false>, L, block, 0, stream);
 }
 
 // offboard main loop outside the step kernel (split Run()/advance stepping): same arithmetic as tick()'s
@@ -82,8 +89,10 @@ static int attr_line(char* buf, size_t n, const char* name, K kernel) {
 }
 
 void kernel_attrs_parity(char* buf, size_t n) {
-  int o = attr_line(buf, n, "step<f64,parity,uwb>", step_kernel<double, true, true, true, false, true>);
-  if (o > 0 && size_t(o) < n) attr_line(buf + o, n - o, "step<f64,parity,nouwb>", step_kernel<double, true, false, true, false, true>);
+  int o = attr_line(buf, n, "step<f64,parity,uwb>", step_kernel<double, true, true, true, false, false>);
+  if (o > 0 && size_t(o) < n) o += attr_line(buf + o, n - o, "step<f64,parity,nouwb>", step_kernel<double, true, false, true, false, false>);
+  if (o > 0 && size_t(o) < n) o += attr_line(buf + o, n - o, "step<f64,parity,uwb>+offboard", step_kernel<double, true, true, true, false, true>);
+  if (o > 0 && size_t(o) < n) attr_line(buf + o, n - o, "step<f64,parity,nouwb>+offboard", step_kernel<double, true, false, true, false, true>);
 }
 
 }  // namespace agf

@@ -33,6 +33,14 @@
 #else
 #define AGF_HD static inline
 #endif
+// Entry points (sin, cos, asin, acos, atan2, exp, cbrt).  AGF_MATH_OUTLINE (defined by the parity kernels' translation
+// unit) makes them real device calls: the same arithmetic, one copy each instead of one per call site -- the parity step
+// kernel was 32 000 instructions (0.5 MB) with them inlined and spent most of its time waiting for instruction fetches.
+#if defined(__CUDACC__) && defined(AGF_MATH_OUTLINE)
+#define AGF_HDX static __host__ __device__ __noinline__
+#else
+#define AGF_HDX AGF_HD
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define AGF_DADD(a, b) __dadd_rn((a), (b))
@@ -110,7 +118,7 @@ AGF_HD double agf_kcos(double r) {
   return AGF_DADD(w, tail);
 }
 
-AGF_HD double agf_sin(double x) {
+AGF_HDX double agf_sin(double x) {
   if (!(x == x) || x - x != 0.0) return x - x;  // NaN, +-inf -> NaN
   double r;
   int q = agf_rem_pio2(x, &r);
@@ -122,7 +130,7 @@ AGF_HD double agf_sin(double x) {
   }
 }
 
-AGF_HD double agf_cos(double x) {
+AGF_HDX double agf_cos(double x) {
   if (!(x == x) || x - x != 0.0) return x - x;
   double r;
   int q = agf_rem_pio2(x, &r);
@@ -162,7 +170,7 @@ AGF_HD double agf_asin_R(double z) {
 }
 
 // returns NaN for |x| > 1 (callers that emulate errno test the argument themselves)
-AGF_HD double agf_asin(double x) {
+AGF_HDX double agf_asin(double x) {
   const double pio2_hi = 1.57079632679489655800e+00;
   const double pio2_lo = 6.12323399573676603587e-17;
   double ax = x < 0 ? -x : x;
@@ -180,7 +188,7 @@ AGF_HD double agf_asin(double x) {
   return x < 0 ? -res : res;
 }
 
-AGF_HD double agf_acos(double x) {
+AGF_HDX double agf_acos(double x) {
   const double pio2_hi = 1.57079632679489655800e+00;
   const double pio2_lo = 6.12323399573676603587e-17;
   double ax = x < 0 ? -x : x;
@@ -259,7 +267,7 @@ AGF_HD double agf_atan(double x) {
   return x < 0 ? -res : res;
 }
 
-AGF_HD double agf_atan2(double y, double x) {
+AGF_HDX double agf_atan2(double y, double x) {
   const double pi = 3.14159265358979311600e+00;
   const double pi_lo = 1.22464679914735317723e-16;
   const double pio2 = 1.57079632679489655800e+00;
@@ -324,7 +332,7 @@ AGF_HD double agf_bits2d(long long b) {
   return x;
 #endif
 }
-AGF_HD double agf_cbrt_pos(double x) {
+AGF_HDX double agf_cbrt_pos(double x) {
   if (!(x > 0.0) || x > 1.7976931348623157e308) return x;  // 0, NaN and +inf pass through
   int eadj = 0;
   if (x < 2.2250738585072014e-308) {  // subnormal: scale by 2^54 (exact)
@@ -349,7 +357,7 @@ AGF_HD double agf_cbrt_pos(double x) {
 // the same routine on both sides.  x = k ln2 + r with |r| <= ln2 / 2 (two-part ln2, the products with
 // k are exact), exp(r) = 1 + 2 r / (2 - c(r)) - r ... in the rational form R(r^2), result scaled by 2^k.
 // ---------------------------------------------------------------------------
-AGF_HD double agf_exp(double x) {
+AGF_HDX double agf_exp(double x) {
   if (x != x) return x;
   if (x > 709.0) return 1.0e308 * 10.0;  // overflow (+inf)
   if (x < -745.0) return 0.0;

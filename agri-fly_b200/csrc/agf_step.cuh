@@ -1501,21 +1501,40 @@ struct EstMsg {
   V3<double> acc, w;
   bool ballistic;
 };
+// The activation times of the queued prediction messages, fetched in one go: the scans below then run on registers
+// instead of a chain of dependent L2 round trips (the estimator state is read through L2, see ldg2).
+struct EstPipe {
+  int cnt;
+  double ta[AGF_OFFEST_PIPE];
+};
+AGF_DEV void est_pipe_load(const double* st, size_t n, EstPipe& p) {
+  p.cnt = int(ldg2(st + E_NPIPE * n));
+#pragma unroll
+  for (int k = 0; k < AGF_OFFEST_PIPE; k++) p.ta[k] = ldg2(st + size_t(E_PIPE + E_MSG * k) * n);
+}
 // PredictionPipe::GetActiveMessage (PredictionPipe.hpp:32-53) + the "no messages" default of its callers
-AGF_DEV void est_fetch(const double* st, size_t n, double t, EstMsg& m, double& timeRemaining) {
-  const int cnt = int(ldg2(st + E_NPIPE * n));
+AGF_DEV void est_fetch(const double* st, size_t n, const EstPipe& pipe, double t, EstMsg& m, double& timeRemaining) {
   double tLast = 1e10;
-  for (int k = cnt - 1; k >= 0; k--) {
-    const double* q = st + size_t(E_PIPE + E_MSG * k) * n;
-    const double ta = ldg2(q);
-    if ((t + 1e-6) >= ta) {
-      m.acc = V3<double>(ldg2(q + 1 * n), ldg2(q + 2 * n), ldg2(q + 3 * n));
-      m.w = V3<double>(ldg2(q + 4 * n), ldg2(q + 5 * n), ldg2(q + 6 * n));
-      m.ballistic = ldg2(q + 7 * n) != 0.0;
-      timeRemaining = tLast - ta;
-      return;
+  int hit = -1;
+  double taHit = 0.0;
+#pragma unroll
+  for (int k = AGF_OFFEST_PIPE - 1; k >= 0; k--) {
+    if (k < pipe.cnt && hit < 0) {
+      if ((t + 1e-6) >= pipe.ta[k]) {
+        hit = k;
+        taHit = pipe.ta[k];
+      } else {
+        tLast = pipe.ta[k];
+      }
     }
-    tLast = ta;
+  }
+  if (hit >= 0) {
+    const double* q = st + size_t(E_PIPE + E_MSG * hit) * n;
+    m.acc = V3<double>(ldg2(q + 1 * n), ldg2(q + 2 * n), ldg2(q + 3 * n));
+    m.w = V3<double>(ldg2(q + 4 * n), ldg2(q + 5 * n), ldg2(q + 6 * n));
+    m.ballistic = ldg2(q + 7 * n) != 0.0;
+    timeRemaining = tLast - taHit;
+    return;
   }
   m.acc = V3<double>(0, 0, 0);
   m.w = V3<double>(0, 0, 0);
@@ -1542,13 +1561,15 @@ AGF_DEV void mocap_predict(const EstParams& ep, size_t i, size_t n, uint64_t now
   const double tEnd = dt + double(now_us - ep.t0_us) * 1e-6;
   const double tStart = double(uint64_t(ldg2(st + E_TEST * n))) * 1e-6;
   EstCore m;
+  EstPipe pipe;
+  est_pipe_load(st, n, pipe);
   est_load(st, n, m);
   o = m;
   double t = tStart;
   while ((t + 1e-6) < tEnd) {
     EstMsg cmd;
     double predictionTime;
-    est_fetch(st, n, t, cmd, predictionTime);
+    est_fetch(st, n, pipe, t, cmd, predictionTime);
     double dtInt = tEnd - t;
     if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
     const V3<double> newPos = (o.pos + m.vel * dtInt) + ((cmd.acc * dtInt) * dtInt) / 2.0;  // sic: _vel (:90)
@@ -1607,6 +1628,8 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
     st[E_LASTGOOD * n] = double(now_us);
     return;
   }
+  EstPipe pipe;
+  est_pipe_load(st, n, pipe);
   est_load(st, n, e);
   for (int k = 0; k < 4; k++) {
     vp[k] = ldg2(st + (E_VP + k) * n);
@@ -1621,7 +1644,7 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
       if ((tNow + 1e-6) >= tEnd) break;
       EstMsg p;
       double predictionTime;
-      est_fetch(st, n, tNow, p, predictionTime);
+      est_fetch(st, n, pipe, tNow, p, predictionTime);
       double dtInt = tEnd - tNow;
       if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
       const EstCore c = e;
@@ -1701,18 +1724,23 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   st[E_NREJ * n] = nrej;
   st[E_NREJC * n] = nrejc;
   {  // PredictionPipe::ClearExpiredMessages(estimate time) (PredictionPipe.hpp:55-68)
+    // The loop erases the front message while the second one is already active: `drop` leading messages go, decided on the
+    // preloaded activation times, and the survivors move down in ONE pass (same final queue as erasing one at a time).
     const double cur = double(est_us) * 1e-6;
-    int cnt = int(ldg2(st + E_NPIPE * n));
-    const int N = cnt;
+    const int N = pipe.cnt;
+    int drop = 0;
     for (int it = 0; it < N; it++) {
-      if (cnt < 2) break;
-      if (ldg2(st + size_t(E_PIPE + E_MSG) * n) <= cur) {  // _messages[1].timeActive
-        for (int k = 0; k + 1 < cnt; k++)
-          for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = ldg2(st + size_t(E_PIPE + E_MSG * (k + 1) + f) * n);
-        cnt--;
-      }
+      if (N - drop < 2) break;
+      double t1 = pipe.ta[AGF_OFFEST_PIPE - 1];
+#pragma unroll
+      for (int k = 0; k < AGF_OFFEST_PIPE - 1; k++) t1 = (drop + 1 == k) ? pipe.ta[k] : t1;  // _messages[1].timeActive of the current queue
+      if (t1 <= cur) drop++;
     }
-    st[E_NPIPE * n] = double(cnt);
+    if (drop > 0) {
+      for (int k = 0; k + drop < N; k++)
+        for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = ldg2(st + size_t(E_PIPE + E_MSG * (k + drop) + f) * n);
+      st[E_NPIPE * n] = double(N - drop);
+    }
   }
 }
 // MocapStateEstimator::SetPredictedValues -> PredictionPipe::AddMessage (hpp:74-80, PredictionPipe.hpp:25-30)
