@@ -866,12 +866,16 @@ def test_ekf_gate_under_uwb_outliers_matches_reference_population(agf, orc_mod):
         got = b.record()
         b.close()
         e = np.linalg.norm(got[:, 0:3] - tgt, axis=1)
-        rej, rej_ref = got[:, 38].mean(), ref[:, 38].mean()
-        print("%s: rejected per vehicle %.2f (reference %.2f) of %.0f ranges, resets %.3f (%.3f), tracking error %.4f (%.4f), panics %d (%d)" %
-              (name, rej, rej_ref, got[:, 39].mean(), got[:, 37].mean(), ref[:, 37].mean(), e.mean(), e_ref.mean(),
-               np.sum(got[:, 35] != 0), np.sum(ref[:, 35] != 0)))
+        # vehicles that fly to the end; the handful that panic (an accepted outlier right after a reset) lie on the ground and
+        # reset at every further rejection -- hundreds of times each --, so they are compared as a count, not inside the means
+        ok, ok_ref = got[:, 35] == 0, ref[:, 35] == 0
+        rej, rej_ref = got[ok, 38].mean(), ref[ok_ref, 38].mean()
+        rst, rst_ref = got[ok, 37].mean(), ref[ok_ref, 37].mean()
+        print("%s: rejected per vehicle %.2f (reference %.2f) of %.0f ranges, resets %.3f (%.3f), median tracking error %.4f (%.4f), "
+              "panics %d (%d)" % (name, rej, rej_ref, got[:, 39].mean(), rst, rst_ref, np.median(e[ok]), np.median(e_ref[ok_ref]),
+                                  np.sum(~ok), np.sum(~ok_ref)))
         assert np.array_equal(got[:, 39], ref[:, 39])              # the network's timing is the clock's
         assert rej_ref > 20 and abs(rej / rej_ref - 1) < 0.10      # the gate sees the outliers at the reference's rate
-        assert abs(got[:, 37].mean() - ref[:, 37].mean()) < 0.15   # and does not reset more often (2 resets at start-up + ~0.2)
-        assert abs(np.median(e) / np.median(e_ref) - 1) < 0.15 and sps.ks_2samp(e, e_ref).pvalue > 1e-4
-        assert abs(int(np.sum(got[:, 35] != 0)) - int(np.sum(ref[:, 35] != 0))) <= 8
+        assert abs(rst - rst_ref) < 0.15                           # and does not reset more often (2 resets at start-up + ~0.2)
+        assert abs(np.median(e[ok]) / np.median(e_ref[ok_ref]) - 1) < 0.15 and sps.ks_2samp(e[ok], e_ref[ok_ref]).pvalue > 1e-4
+        assert abs(int(np.sum(~ok)) - int(np.sum(~ok_ref))) <= 8
