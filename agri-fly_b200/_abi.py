@@ -246,7 +246,7 @@ PROTOTYPES = {
     "agf_batch_enable_log": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "agf_batch_log_count": (C.c_uint64, [C.c_void_p]),
     "agf_batch_read_log": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
-    "agf_batch_log_device_ptr": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_size_t)]),
+    "agf_batch_log_device_ptr": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_size_t)]),
     "agf_batch_reduce_stats_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "agf_batch_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "agf_batch_reduce_stats_nccl_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

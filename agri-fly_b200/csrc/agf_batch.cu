@@ -278,6 +278,17 @@ __device__ inline void atomic_max_double(double* addr, double v) {  // v >= 0
 }
 
 // the all-gathered statistics vectors of every rank -> one vector, in rank order (deterministic, the same bits on every rank)
+// one record of the trajectory log ([quad][log_n] vectors + [log_n] scalars, agf_types.h StepLaunch::log) -> double[count][17]
+template<typename P>
+__global__ void log_gather_kernel(const P* __restrict__ rec, size_t log_n, size_t first, size_t count, double* __restrict__ out) {
+  constexpr int VP = VecOf<P>::lanes;
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count * AGF_LOG_FIELDS) return;
+  const size_t i = first + t / AGF_LOG_FIELDS;
+  const int f = int(t % AGF_LOG_FIELDS);
+  out[t] = double(f < AGF_LOG_FIELDS - 1 ? rec[(size_t(f / VP) * log_n + i) * VP + f % VP] : rec[size_t(AGF_LOG_FIELDS - 1) * log_n + i]);
+}
+
 __global__ void stats_combine_kernel(const double* gathered, int nranks, double* out) {
   const int k = threadIdx.x;
   if (k >= AGF_STATS_LEN) return;
@@ -356,7 +367,7 @@ struct Batch {
   virtual int add_anchor(uint8_t id, const float pos[3]) = 0;
   virtual int enable_log(uint32_t stride, uint32_t cap) = 0;
   virtual int read_log(uint64_t rec, double* dst, size_t first, size_t count) = 0;
-  virtual int log_ptr(void** p, size_t* es) = 0;
+  virtual int log_ptr(void** p, size_t* es, size_t* ln) = 0;
   virtual int stats(const double* target, double* dev_out) = 0;
   virtual int set_offboard(const agf_offboard_cfg* cfg, const agf_offboard_target* targets, size_t n_targets, const double* offsets) = 0;
   virtual int set_offboard_ref(const agf_offboard_ref* ref) = 0;
@@ -597,6 +608,7 @@ struct BatchImpl : Batch {
   uint32_t* d_slot_tf[AGF_MAX_CMD_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   P* d_log = nullptr;
   uint32_t log_stride = 0, log_cap = 0;
+  size_t log_n = 0;  // vehicles per log array: n rounded up to whole 128-byte lines
   uint64_t log_base_tick = 0;
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -821,6 +833,7 @@ struct BatchImpl : Batch {
       if (it->slot >= 0 && !d_slot_f[it->slot]) return fail(AGF_EINVAL, "schedule references a command slot that was never set");
     for (int s = 0; s < AGF_MAX_CMD_SLOTS; s++) { L.slots[s].f = d_slot_f[s]; L.slots[s].tf = d_slot_tf[s]; }
     L.log = d_log;
+    L.log_n = log_n;
     L.log_stride = log_stride ? log_stride : 1;
     L.log_capacity = log_cap ? log_cap : 1;
     L.log_first_off = L.log_stride - 1 - uint32_t(ticks % L.log_stride);
@@ -1354,7 +1367,8 @@ struct BatchImpl : Batch {
     log_stride = log_cap = 0;
     log_records = 0;
     if (!stride || !cap) return AGF_OK;  // disable
-    const size_t bytes = sizeof(P) * size_t(cap) * AGF_LOG_FIELDS * n;
+    log_n = (n + 31) / 32 * 32;
+    const size_t bytes = sizeof(P) * size_t(cap) * AGF_LOG_FIELDS * log_n;
     cudaError_t e = cudaMalloc(&d_log, bytes);
     if (e != cudaSuccess) {
       d_log = nullptr;
@@ -1373,19 +1387,21 @@ struct BatchImpl : Batch {
     AGF_CUDA(cudaSetDevice(opts.device));
     // absolute record index in the kernel's numbering
     const uint64_t abs_rec = log_base_tick / log_stride + rec;
-    std::vector<P> h(count);
-    for (int f = 0; f < AGF_LOG_FIELDS; f++) {
-      const P* src = d_log + (size_t(abs_rec % log_cap) * AGF_LOG_FIELDS + f) * n + first;
-      AGF_CUDA(cudaMemcpyAsync(h.data(), src, count * sizeof(P), cudaMemcpyDeviceToHost, stream));
-      AGF_CUDA(cudaStreamSynchronize(stream));
-      for (size_t i = 0; i < count; i++) dst[i * AGF_LOG_FIELDS + f] = double(h[i]);
-    }
+    const size_t total = count * AGF_LOG_FIELDS;
+    if (int rc = ensure_stage(total * sizeof(double))) return rc;
+    const P* rec_ptr = d_log + size_t(abs_rec % log_cap) * AGF_LOG_FIELDS * log_n;
+    log_gather_kernel<P><<<unsigned((total + 255) / 256), 256, 0, stream>>>(rec_ptr, log_n, first, count, (double*)d_stage);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaMemcpyAsync(dst, d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    AGF_CUDA(cudaStreamSynchronize(stream));
     return AGF_OK;
   }
 
-  int log_ptr(void** p, size_t* es) override {
+  int log_ptr(void** p, size_t* es, size_t* ln) override {
     if (p) *p = d_log;
     if (es) *es = sizeof(P);
+    if (ln) *ln = log_n;
     return d_log ? AGF_OK : fail(AGF_EINVAL, "logging is not enabled");
   }
 
@@ -1637,9 +1653,9 @@ int agf_batch_read_log(agf_batch* b, uint64_t rec, double* dst, size_t first, si
   if (!b || !dst) return fail(AGF_EINVAL, "null argument");
   return B(b)->read_log(rec, dst, first, count);
 }
-int agf_batch_log_device_ptr(agf_batch* b, void** p, size_t* es) {
+int agf_batch_log_device_ptr(agf_batch* b, void** p, size_t* es, size_t* ln) {
   if (!b) return fail(AGF_EINVAL, "null handle");
-  return B(b)->log_ptr(p, es);
+  return B(b)->log_ptr(p, es, ln);
 }
 int agf_batch_reduce_stats_device(agf_batch* b, const double* target, double* dev_out) {
   if (!b || !dev_out) return fail(AGF_EINVAL, "null argument");

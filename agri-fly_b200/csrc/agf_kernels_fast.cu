@@ -33,12 +33,26 @@ static constexpr bool kUwb = false;
 template<bool HK, bool PV, bool OFFB>
 static cudaError_t go(const StepLaunch<FastP>& L, cudaStream_t stream) {
   auto kernel = step_kernel<FastP, false, kUwb, HK, PV, OFFB>;
+  const size_t smem = step_smem_bytes<false, kUwb>(AGF_BLOCK_THREADS, L.st.sq != nullptr);
   static bool carveout_set = false;
-  if (!carveout_set) {  // the scratch of the resident blocks needs most of the SM's shared memory
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (!carveout_set) {
+    // shared-memory carve-out = what the resident blocks' scratch needs (+1 KB per block the runtime reserves), not the
+    // maximum: the rest of the 228 KB stays L1, which holds the tick plans, the schedule and the few spilled words of
+    // the loop -- with the trajectory log streaming through it, a minimal L1 misses on those (profiles/r2 C4 captures)
+#if AGF_CARVEOUT_MAX
+    int pct = cudaSharedmemCarveoutMaxShared;
+#else
+    int dev = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    const size_t need = size_t(step_min_blocks<FastP, false, kUwb, OFFB>()) * (smem + 1024);
+    int pct = per_sm > 0 ? int((need * 100 + size_t(per_sm) - 1) / size_t(per_sm)) : 100;
+    if (pct > 100) pct = 100;
+#endif
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     carveout_set = true;
   }
-  return launch_step_kernel<FastP>(kernel, L, AGF_BLOCK_THREADS, step_smem_bytes<false, kUwb>(AGF_BLOCK_THREADS, L.st.sq != nullptr), stream);
+  return launch_step_kernel<FastP>(kernel, L, AGF_BLOCK_THREADS, smem, stream);
 }
 
 // launch_step_fast_{f32,f64}_{uwb,rates}

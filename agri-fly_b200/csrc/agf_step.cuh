@@ -2565,9 +2565,18 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
   uint32_t si = L.sched_begin;
   while (si < L.sched_end && L.sched[si].tick < L.tick0 + t0) si++;
   uint32_t next_cmd = si < L.sched_end ? uint32_t(L.sched[si].tick - L.tick0) : 0xFFFFFFFFu;
-  // ticks until the next log record
-  uint32_t log_in = 0;
-  if (L.log) log_in = L.log_stride - uint32_t((L.tick0 + t0) % L.log_stride);
+  // trajectory log: ticks until the next record, this vehicle's place in that record, records left before the ring wraps
+  // (all the index arithmetic of the ring happens here, once per work item; the loop only adds)
+  constexpr int VP = VecOf<P>::lanes, LOGQ = (AGF_LOG_FIELDS - 1) / VP;
+  typedef typename VecOf<P>::type LogVec;
+  uint32_t log_in = 0, log_left = 0;
+  LogVec* logp = nullptr;
+  if (L.log) {
+    log_in = L.log_stride - uint32_t((L.tick0 + t0) % L.log_stride);
+    const uint32_t slot = (L.log_slot0 + (t0 + log_in - 1 - L.log_first_off) / L.log_stride) % L.log_capacity;
+    logp = reinterpret_cast<LogVec*>(L.log + size_t(slot) * AGF_LOG_FIELDS * L.log_n) + i;
+    log_left = L.log_capacity - slot;
+  }
   const uint64_t gidx = L.first_global_index + i;
   for (uint32_t t = t0; t < t1; t++) {
     const uint64_t abs_tick = L.tick0 + t;
@@ -2590,13 +2599,17 @@ AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc
     tick<P, PARITY, UWB, HK, OFFB>(s, sc, L.sh, pv, plan, L.now0_us + uint64_t(t) * L.dt_us, L.dt_us, abs_tick, gidx, i, L.n);
     if (L.log && --log_in == 0) {
       log_in = L.log_stride;
-      // ring slot from the launch-relative tick with 32-bit arithmetic (host: slot and tick offset of the launch's first record)
-      const uint32_t slot = (L.log_slot0 + (t - L.log_first_off) / L.log_stride) % L.log_capacity;
-      P* base = L.log + (size_t(slot) * AGF_LOG_FIELDS) * L.n + i;
+      // record = LOGQ vectors [quad][vehicle] (16-byte stores, a warp writes 512 contiguous bytes) + the 17th value [vehicle]
+      const P f[AGF_LOG_FIELDS - 1] = {s.pos[0], s.pos[1], s.pos[2], s.vel[0], s.vel[1], s.vel[2], s.att[0], s.att[1],
+                                       s.att[2], s.att[3], s.w[0],   s.w[1],   s.w[2],   s.ms[0],  s.ms[1],  s.ms[2]};
 #pragma unroll
-      for (int k = 0; k < 3; k++) { base[size_t(k) * L.n] = s.pos[k]; base[size_t(3 + k) * L.n] = s.vel[k]; base[size_t(10 + k) * L.n] = s.w[k]; }
-#pragma unroll
-      for (int k = 0; k < 4; k++) { base[size_t(6 + k) * L.n] = s.att[k]; base[size_t(13 + k) * L.n] = s.ms[k]; }
+      for (int q = 0; q < LOGQ; q++) logp[size_t(q) * L.log_n] = VecOf<P>::pack(&f[q * VP]);
+      reinterpret_cast<P*>(logp + size_t(LOGQ) * L.log_n - i)[i] = s.ms[3];
+      logp += (size_t(AGF_LOG_FIELDS) * L.log_n) / VP;  // log_n: the vehicle count padded to whole lines
+      if (--log_left == 0) {
+        log_left = L.log_capacity;
+        logp -= (size_t(L.log_capacity) * AGF_LOG_FIELDS * L.log_n) / VP;
+      }
     }
   }
   state_store(s, L.st, L.n, i, sc, L.sh.logic.mix_kf);

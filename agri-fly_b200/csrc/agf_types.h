@@ -393,7 +393,10 @@ struct StepLaunch {
   const SchedEntryDev* sched;
   uint32_t sched_begin, sched_end;
   SlotArrays slots[AGF_MAX_CMD_SLOTS];
-  P* log;  // [capacity][AGF_LOG_FIELDS][N] or null
+  // trajectory log ring or null: [capacity] records; a record is (AGF_LOG_FIELDS - 1) / lanes vectors [quad][log_n] holding the
+  // first 16 values of every vehicle, then the 17th value as [log_n] scalars; log_n = N rounded up to whole 128-byte lines
+  P* log;
+  size_t log_n;
   uint32_t log_stride, log_capacity;
   uint32_t log_first_off, log_slot0;  // tick offset (within the launch) and ring slot of the launch's first record
   uint64_t first_global_index;

@@ -478,18 +478,22 @@ int agf_batch_set_noise(agf_batch* b, uint64_t seed, double sigma_gyro, double s
                         double bias_sigma_gyro, double bias_sigma_acc);
 
 /* Trajectory logging to HBM (new capability; replaces the CSV logger of main.cpp:676-733).
- * Every `stride` ticks the step kernel appends one record per vehicle:
- * 17 values {pos3 vel3 att4 angvel3 motorspeed4} in the plant precision, laid out
- * [record][field][vehicle] so that each store instruction is a coalesced 128-byte line.
- * capacity_records bounds the ring; agf_batch_read_log copies records out. */
+ * Every `stride` ticks the step kernel appends one record per vehicle: 17 values {pos3 vel3 att4 angvel3 motorspeed4}
+ * in the plant precision.  Device layout of a record (agf_batch_log_device_ptr): the first 16 values of a vehicle as
+ * 16-byte vectors [quad][stride_vehicles] (float4: 4 quads; double2: 8), so that a warp's store instruction writes 512
+ * contiguous bytes, followed by the 17th value as [stride_vehicles] scalars; value f of vehicle i of ring slot r is
+ *   f < 16:  base[(r*17 + (f/L)*L) * stride_vehicles + i*L + f%L]   (L = 16 / elem_size lanes per vector)
+ *   f == 16: base[(r*17 + 16) * stride_vehicles + i]
+ * with stride_vehicles = the vehicle count rounded up to a multiple of 32.
+ * capacity_records bounds the ring; agf_batch_read_log gathers a record on the device and copies it out. */
 #define AGF_LOG_FIELDS 17
 int agf_batch_enable_log(agf_batch* b, uint32_t stride_ticks, uint32_t capacity_records);
 /* number of records written since enable (may exceed capacity: ring) */
 uint64_t agf_batch_log_count(const agf_batch* b);
 /* copies record `rec` (absolute index) for vehicles [first, first+count) as double[count][17] */
 int agf_batch_read_log(agf_batch* b, uint64_t rec, double* host_dst, size_t first, size_t count);
-/* raw device pointer + element size of the log ring, for consumers that stay on the GPU */
-int agf_batch_log_device_ptr(agf_batch* b, void** dev_ptr, size_t* elem_size);
+/* raw device pointer, element size and stride_vehicles of the log ring, for consumers that stay on the GPU (any may be NULL) */
+int agf_batch_log_device_ptr(agf_batch* b, void** dev_ptr, size_t* elem_size, size_t* stride_vehicles);
 
 /* Monte-Carlo statistics (new capability): one launch reduces, over the vehicles of this handle,
  * the tracking error e = position - target, with warp shuffles -> one atomic per block.

@@ -23,7 +23,7 @@ hk = os.environ.get("AGF_PROF_HK", "1") != "0"
 c4 = os.environ.get("AGF_PROF_C4", "0") == "1"
 b, _ = bench.workload(agf, n, 0, prec, ticks * (launches + warm + 1) + 600, uwb=uwb, hk=hk, math=os.environ.get("AGF_PROF_MATH", "fast"),
                       sweep=c4)
-if c4:
+if c4 and os.environ.get("AGF_PROF_LOG", "1") != "0":  # AGF_PROF_LOG=0: the sweep without the log
     b.enable_log(1, 32)
 b.run(500)  # first launch: take-off, EKF initialised, UWB ranging active
 t0 = time.time()
