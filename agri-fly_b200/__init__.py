@@ -307,6 +307,13 @@ class Batch:
         s13 = np.ascontiguousarray(s13, dtype=np.float64).reshape(-1, 13)
         _check(self.L.agf_batch_set_state(self.h, s13.ctypes.data, first, len(s13)))
 
+    def get_state13(self, first=0, count=None):
+        """the way back (agf_batch_get_state): [count][13] doubles"""
+        count = self.n - first if count is None else count
+        out = np.empty((count, 13), np.float64)
+        _check(self.L.agf_batch_get_state(self.h, out.ctypes.data, first, count))
+        return out
+
     def record(self):
         """[n][40] in the oracle's trajectory-record column order (oracle/oracle_api.h)."""
         r = np.zeros((self.n, 40))

@@ -236,6 +236,7 @@ PROTOTYPES = {
     "agf_csv_header": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "agf_csv_format_row": (C.c_size_t, [_P(CsvRecord), C.c_char_p, C.c_size_t]),
     "agf_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "agf_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_offboard_estimator_default": (C.c_int, [_P(OffboardEstimator)]),
     "agf_batch_set_offboard_estimator": (C.c_int, [C.c_void_p, _P(OffboardEstimator)]),
     "agf_batch_get_offboard_estimate": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),

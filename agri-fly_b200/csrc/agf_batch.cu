@@ -164,6 +164,18 @@ __global__ void state13_set_kernel(FieldCtx<P> c, size_t first, size_t count, co
   if (comp < 6) c.sp[sidx(comp < 3 ? SP_CPOS + comp : SP_CVEL + comp - 3, c.n, i, VP)] = P(0);
 }
 
+// ... and the way back: out = [count][13] doubles
+template<typename P>
+__global__ void state13_get_kernel(FieldCtx<P> c, size_t first, size_t count, double* __restrict__ out) {
+  constexpr int VP = VecOf<P>::lanes;
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count * 13) return;
+  const size_t i = first + t / 13;
+  const int comp = int(t % 13);
+  const int slot = comp < 3 ? SP_POS + comp : (comp < 6 ? SP_VEL + comp - 3 : (comp < 10 ? SP_ATT + comp - 6 : SP_W + comp - 10));
+  out[t] = double(c.sp[sidx(slot, c.n, i, VP)]);
+}
+
 // SetCommandRadioMsg now (QuadcopterLogic.hpp:110-116), outside the step kernel
 struct RadioNow {
   uint32_t type, flags;
@@ -359,6 +371,7 @@ struct Batch {
   virtual int get_field(int field, void* dst, size_t first, size_t count) = 0;
   virtual int set_field(int field, const void* src, size_t first, size_t count) = 0;
   virtual int set_state13(const double* src, size_t first, size_t count) = 0;
+  virtual int get_state13(double* dst, size_t first, size_t count) = 0;
   virtual int set_radio(const uint8_t* raw, size_t first, size_t count, int broadcast) = 0;
   virtual int set_schedule(const agf_cmd_entry* e, size_t n) = 0;
   virtual int set_slot(int slot, const uint8_t* raw) = 0;
@@ -619,7 +632,7 @@ struct BatchImpl : Batch {
   std::vector<PackedPlan> h_plans;
   PackedPlan* d_plans = nullptr;
   uint32_t plans_cap = 0;
-  double* d_off_est = nullptr;  // [E_FIELDS][n] estimator state
+  double* d_off_est = nullptr;  // estimator state, est_doubles(n) values blocked by warp (agf_types.h est_index)
   double* d_off_state = nullptr;  // [AGF_OFFSTATE_DOUBLES][n]
   double* d_off_traj = nullptr;   // [AGF_OFFTRAJ_DOUBLES][n]
 
@@ -1048,12 +1061,14 @@ struct BatchImpl : Batch {
     if (!(e->mocap_period_us > 0) || !(e->angvel_time_const > 0) || !(e->prediction_delay >= 0))
       return fail(AGF_EINVAL, "estimator: mocap period and angular-velocity time constant must be positive");
     // MocapStateEstimator::MocapStateEstimator -> Reset() (MocapStateEstimator.cpp:9-50) for every vehicle
-    std::vector<double> h(size_t(E_FIELDS) * n, 0.0);
+    std::vector<double> h(est_doubles(n), 0.0);
     for (size_t i = 0; i < n; i++) {
-      h[(E_ATT + 0) * n + i] = 1.0;
-      h[(E_VP + 0) * n + i] = 25.0; h[(E_VP + 3) * n + i] = 25.0;
-      h[(E_VA + 0) * n + i] = 1.0; h[(E_VA + 3) * n + i] = 400.0;
-      h[E_LASTGOOD * n + i] = double(now_us);
+      double* e0 = h.data() + est_index(i);  // field k at e0[k * E_LANES]
+      e0[(E_ATT + 0) * E_LANES] = 1.0;
+      e0[(E_VP + 0) * E_LANES] = 25.0; e0[(E_VP + 3) * E_LANES] = 25.0;
+      e0[(E_VA + 0) * E_LANES] = 1.0; e0[(E_VA + 3) * E_LANES] = 400.0;
+      e0[E_LASTGOOD * E_LANES] = double(now_us);
+      for (int k = 0; k < AGF_OFFEST_PIPE; k++) e0[(E_PIPE + E_MSG * k) * E_LANES] = E_SLOT_FREE;  // empty prediction pipe
     }
     if (!d_off_est) AGF_CUDA(cudaMalloc(&d_off_est, h.size() * sizeof(double)));
     AGF_CUDA(cudaMemcpy(d_off_est, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1089,12 +1104,11 @@ struct BatchImpl : Batch {
     for (size_t k = 0; k < count; k++)
       for (int f = 0; f < 13; f++) est13[k * 13 + f] = h[size_t(f) * count + k];
     if (counters4) {
-      const int fields[4] = {E_INIT, E_NREJ, E_NREJC, E_NPIPE};
-      std::vector<double> col(count);
-      for (int f = 0; f < 4; f++) {
-        AGF_CUDA(cudaMemcpy(col.data(), d_off_est + size_t(fields[f]) * n + first, count * sizeof(double), cudaMemcpyDeviceToHost));
-        for (size_t k = 0; k < count; k++) counters4[k * 4 + f] = col[k];
-      }
+      if (int rc = ensure_stage(4 * count * sizeof(double))) return rc;
+      AGF_CUDA(launch_offboard_counters(d_off_est, first, count, (double*)d_stage, stream));
+      launches++;
+      AGF_CUDA(cudaMemcpyAsync(counters4, d_stage, 4 * count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      AGF_CUDA(cudaStreamSynchronize(stream));
     }
     return AGF_OK;
   }
@@ -1212,6 +1226,23 @@ struct BatchImpl : Batch {
     AGF_CUDA(cudaGetLastError());
     launches++;
     AGF_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its buffer
+    return AGF_OK;
+  }
+
+  int get_state13(double* dst, size_t first, size_t count) override {
+    if (!dst) return fail(AGF_EINVAL, "null state array");
+    if (first + count > n) return fail(AGF_ERANGE, "vehicle range outside the batch");
+    if (!count) return AGF_OK;
+    AGF_CUDA(cudaSetDevice(opts.device));
+    const size_t bytes = count * 13 * sizeof(double);
+    int rc = ensure_stage(bytes);
+    if (rc) return rc;
+    const size_t total = count * 13;
+    state13_get_kernel<P><<<unsigned((total + 255) / 256), 256, 0, stream>>>(ctx(), first, count, reinterpret_cast<double*>(d_stage));
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaMemcpyAsync(dst, d_stage, bytes, cudaMemcpyDeviceToHost, stream));
+    AGF_CUDA(cudaStreamSynchronize(stream));
     return AGF_OK;
   }
 
@@ -1583,6 +1614,9 @@ int agf_batch_set_offboard_estimator(agf_batch* b, const agf_offboard_estimator*
 }
 int agf_batch_get_offboard_estimate(agf_batch* b, double horizon, double* est13, double* counters4, size_t first, size_t count) {
   return b ? B(b)->get_offboard_estimate(horizon, est13, counters4, first, count) : fail(AGF_EINVAL, "null handle");
+}
+int agf_batch_get_state(agf_batch* b, double* state13, size_t first, size_t count) {
+  return b ? B(b)->get_state13(state13, first, count) : fail(AGF_EINVAL, "null handle");
 }
 int agf_batch_set_state(agf_batch* b, const double* state13, size_t first, size_t count) {
   return b ? B(b)->set_state13(state13, first, count) : fail(AGF_EINVAL, "null handle");

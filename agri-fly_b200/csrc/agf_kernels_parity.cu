@@ -41,7 +41,7 @@ __global__ void offboard_mocap_kernel(StateArrays<P> st, size_t n, EstParams ep,
   P r[12];
 #pragma unroll
   for (int q = 0; q < 12 / VP; q++) VecOf<P>::unpack(st.sp[size_t(q) * n + i], &r[q * VP]);
-  mocap_update<true>(ep, i, n, now_us, V3<double>(double(r[SP_POS]), double(r[SP_POS + 1]), double(r[SP_POS + 2])),
+  mocap_update<true>(ep, i, now_us, V3<double>(double(r[SP_POS]), double(r[SP_POS + 1]), double(r[SP_POS + 2])),
                      Q4<double>(double(r[SP_ATT]), double(r[SP_ATT + 1]), double(r[SP_ATT + 2]), double(r[SP_ATT + 3])));
 }
 cudaError_t launch_offboard_mocap(const StateArrays<double>& st, size_t n, const EstParams& ep, uint64_t now_us, cudaStream_t stream) {
@@ -52,12 +52,27 @@ cudaError_t launch_offboard_mocap(const StateArrays<float>& st, size_t n, const 
   offboard_mocap_kernel<float><<<unsigned((n + 127) / 128), 128, 0, stream>>>(st, n, ep, now_us);
   return cudaGetLastError();
 }
+// initialised flag, rejection counters and message count of vehicles first .. first+count-1 -> out [count][4]
+__global__ void offboard_counters_kernel(const double* state, size_t first, size_t count, double* out) {
+  const size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double* st = state + est_index(first + k);
+  out[4 * k + 0] = st[size_t(E_INIT) * E_LANES];
+  out[4 * k + 1] = st[size_t(E_NREJ) * E_LANES];
+  out[4 * k + 2] = st[size_t(E_NREJC) * E_LANES];
+  out[4 * k + 3] = st[size_t(E_NPIPE) * E_LANES];
+}
+cudaError_t launch_offboard_counters(const double* state, size_t first, size_t count, double* out, cudaStream_t stream) {
+  offboard_counters_kernel<<<unsigned((count + 127) / 128), 128, 0, stream>>>(state, first, count, out);
+  return cudaGetLastError();
+}
 // MocapStateEstimator::GetPrediction(horizon) for vehicles first .. first+count-1 -> out [13][count]
 __global__ void offboard_estimate_kernel(EstParams ep, size_t n, size_t first, size_t count, uint64_t now_us, double horizon, double* out) {
   const size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= count) return;
   EstCore e;
-  mocap_predict<true>(ep, first + k, n, now_us, horizon, e);
+  EstPipe pipe;
+  mocap_predict<true>(ep, first + k, now_us, horizon, e, pipe);
   const double v[13] = {e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z, e.att.w, e.att.x, e.att.y, e.att.z, e.w.x, e.w.y, e.w.z};
   for (int f = 0; f < 13; f++) out[size_t(f) * count + k] = v[f];
 }

@@ -33,6 +33,8 @@ cudaError_t launch_offboard_mocap(const StateArrays<float>& st, size_t n, const 
 cudaError_t launch_offboard_estimate(const EstParams& ep, size_t n, size_t first, size_t count, uint64_t now_us, double horizon,
                                      double* out, cudaStream_t stream);
 
+cudaError_t launch_offboard_counters(const double* state, size_t first, size_t count, double* out, cudaStream_t stream);
+
 // registers per thread / local memory of each instantiation, for agf_build_info()
 void kernel_attrs_parity(char* buf, size_t n);
 void kernel_attrs_fast_f64_uwb(char* buf, size_t n);

@@ -575,9 +575,33 @@ AGF_DEV void sq_store(const Scratch& sc, int quad, const float4& v) {
   sc.q[quad * SQ_STRIDE] = v;
 #endif
 }
-// packed upper triangle of a symmetric 9x9
-AGF_DEV constexpr int SI(int i, int j) {
-  return i <= j ? (i * 9 - (i * (i - 1)) / 2 + (j - i)) : (j * 9 - (j * (j - 1)) / 2 + (i - j));
+// Packed symmetric 9x9 covariance of the fast variants: 48 floats = 12 scratch quads, arranged for the packed FP32 path
+// (FFMA2: two lanes per instruction, operands in even-aligned register pairs).  Blocks p (position), v (velocity),
+// a (attitude error).  Rows 0 and 1 of a 3x3 block are interleaved, one pair per column:
+//   pairs 0-2  (Ppv[0][c], Ppv[1][c])    pairs 3-5  (Ppa[0][c], Ppa[1][c])    pairs 6-8   (Pva[0][c], Pva[1][c])
+//   pairs 9-11 (Pvv[0][c], Pvv[1][c])    pairs 12-14 (Paa[0][c], Paa[1][c])   (pair k = floats 2k, 2k+1)
+// then row 2 of Ppv, Ppa, Pva (floats 30-38), Pvv[2][2], Paa[2][2] (39, 40) and the upper triangle of Ppp (41-46).
+// Row 2 of the symmetric blocks Pvv / Paa is read from the column-2 pair; their (1,0) entry exists twice, as the
+// upper half of the column-0 pair and as the lower half of the column-1 pair (CI_VV10 mirrors (3,4), CI_AA10 mirrors (6,7)).
+enum { CP_PV = 0, CP_PA = 3, CP_VA = 6, CP_VV = 9, CP_AA = 12, CI_PV2 = 30, CI_PA2 = 33, CI_VA2 = 36, CI_VV22 = 39, CI_AA22 = 40,
+       CI_PP = 41, CI_VV10 = 2 * CP_VV + 1, CI_AA10 = 2 * CP_AA + 1 };
+AGF_DEV constexpr int SI_rect(int pair0, int row2, int r, int c) { return r < 2 ? 2 * (pair0 + c) + r : row2 + c; }
+AGF_DEV constexpr int SI_sym(int pair0, int s22, int r, int c) {  // r <= c
+  return c < 2 ? 2 * (pair0 + c) + r : (r < 2 ? 2 * (pair0 + 2) + r : s22);
+}
+AGF_DEV constexpr int SI(int i, int j) {  // any (i, j); the canonical place of a symmetric block's entry is its upper one
+  if (i > j) { const int t = i; i = j; j = t; }
+  const int bi = i / 3, bj = j / 3, r = i % 3, c = j % 3;
+  if (bi == 0 && bj == 0) return CI_PP + (r == 0 ? c : (r == 1 ? 2 + c : 5));
+  if (bi == 0 && bj == 1) return SI_rect(CP_PV, CI_PV2, r, c);
+  if (bi == 0) return SI_rect(CP_PA, CI_PA2, r, c);
+  if (bi == 1 && bj == 2) return SI_rect(CP_VA, CI_VA2, r, c);
+  if (bi == 1) return SI_sym(CP_VV, CI_VV22, r, c);
+  return SI_sym(CP_AA, CI_AA22, r, c);
+}
+AGF_DEV void cov_fill_mirrors(float* P) {
+  P[CI_VV10] = P[SI(3, 4)];
+  P[CI_AA10] = P[SI(6, 7)];
 }
 AGF_DEV void cov_load(const Scratch& sc, float* P) {
 #pragma unroll
@@ -725,11 +749,12 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
     } else {
       float Ps[48];
 #pragma unroll
-      for (int k = 45; k < 48; k++) Ps[k] = 0.0f;
+      Ps[47] = 0.0f;
 #pragma unroll
       for (int r = 0; r < 9; r++)
 #pragma unroll
         for (int c = r; c < 9; c++) Ps[SI(r, c)] = full[9 * r + c];
+      cov_fill_mirrors(Ps);
       cov_store(sc, Ps);
     }
   }
@@ -1014,71 +1039,123 @@ AGF_DEV void kf_predict(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const 
     s.kcorr[0] = 0; s.kcorr[1] = 0; s.kcorr[2] = 0;
     const float qa = 5.0f * 5.0f * dt * dt, qg = 0.1f * 0.1f * dt * dt;  // process noise :234-239
     if constexpr (!PARITY) {
-      // Fast variants: P is kept exactly symmetric (packed upper triangle, 45 values) and propagated block-wise,
-      // f = [[I, dt I, 0], [0, I, A], [0, 0, S]] = F2 * F1 with F1 the position/velocity coupling.  Same algebra
-      // as the dense f P f^T of KalmanFilter6DOF.cpp:232 up to rounding (about half the multiply-adds).
+      // Fast variants: P is kept exactly symmetric (packed, 47 values, see SI) and propagated block-wise,
+      // f = [[I, dt I, 0], [0, I, A], [0, 0, S]] = F2 * F1 with F1 the position/velocity coupling.  Same algebra as the
+      // dense f P f^T of KalmanFilter6DOF.cpp:232 up to rounding, in about a third of its multiply-adds: rows 0 and 1 of
+      // every 3x3 block ride in the two lanes of the packed FP32 instructions (FFMA2: pair x broadcast scalar + pair),
+      // row 2 is scalar.  Right-multiplications (X M^T) take the pair from X and the scalar from M; left-multiplications
+      // (M X) take the pair from a column of M and the scalar from X, so nothing is ever transposed or shuffled.
       float Pm[48];
       cov_load(sc, Pm);
-#define PS(i, j) Pm[SI((i), (j))]
-      // F1: Ppp += dt (Ppv + Ppv^T) + dt^2 Pvv ; Ppv += dt Pvv ; Ppa += dt Pva
+#define PR(k) make_float2(Pm[2 * (k)], Pm[2 * (k) + 1])
+#define PRSET(k, v) { const float2 v_ = (v); Pm[2 * (k)] = v_.x; Pm[2 * (k) + 1] = v_.y; }
+#define PVS(r, c) Pm[SI_rect(CP_PV, CI_PV2, (r), (c))]
+#define PAS(r, c) Pm[SI_rect(CP_PA, CI_PA2, (r), (c))]
+#define VAS(r, c) Pm[SI_rect(CP_VA, CI_VA2, (r), (c))]
+#define VVS(r, c) Pm[(r) <= (c) ? SI_sym(CP_VV, CI_VV22, (r), (c)) : SI_sym(CP_VV, CI_VV22, (c), (r))]
+#define AAS(r, c) Pm[(r) <= (c) ? SI_sym(CP_AA, CI_AA22, (r), (c)) : SI_sym(CP_AA, CI_AA22, (c), (r))]
+#define PPS(r, c) Pm[SI((r), (c))]
+      float2 Acol[3], Scol[3];  // columns of A and S, rows 0 and 1
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+      for (int k = 0; k < 3; k++) { Acol[k] = make_float2(A[0][k], A[1][k]); Scol[k] = make_float2(S[0][k], S[1][k]); }
+      // F1: Ppv += dt Pvv ; Ppp += dt (Ppv_new + Ppv_old^T) ; Ppa += dt Pva
+      float2 Vn[3];
+      float v2n[3];
 #pragma unroll
-        for (int j = i; j < 3; j++) PS(i, j) = ::fmaf(dt, ::fmaf(dt, PS(3 + i, 3 + j), PS(i, 3 + j) + PS(j, 3 + i)), PS(i, j));
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          PS(i, 3 + j) = PS(i, 3 + j) + dt * PS(3 + i, 3 + j);
-          PS(i, 6 + j) = PS(i, 6 + j) + dt * PS(3 + i, 6 + j);
-        }
-      // F2: T = Pva + A Paa ; U = Pva A^T ; Pvv += U^T + T A^T.  Every entry is one multiply-add chain onto its
-      // starting value (this variant is not pinned to the reference's parenthesisation; a chain is one instruction per term).
-      float T[3][3], U[3][3];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          T[i][j] = ::fmaf(A[i][2], PS(8, 6 + j), ::fmaf(A[i][1], PS(7, 6 + j), ::fmaf(A[i][0], PS(6, 6 + j), PS(3 + i, 6 + j))));
-          U[i][j] = ::fmaf(PS(3 + i, 8), A[j][2], ::fmaf(PS(3 + i, 7), A[j][1], PS(3 + i, 6) * A[j][0]));
-        }
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = i; j < 3; j++)
-          PS(3 + i, 3 + j) = ::fmaf(T[i][2], A[j][2], ::fmaf(T[i][1], A[j][1], ::fmaf(T[i][0], A[j][0], PS(3 + i, 3 + j) + U[j][i])));
-      // Ppv += Ppa A^T ; Ppa = Ppa S^T ; Pva = T S^T   (S has a unit diagonal: two terms onto the diagonal one)
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const float a[3] = {PS(i, 6), PS(i, 7), PS(i, 8)};
-#pragma unroll
-        for (int j = 0; j < 3; j++) PS(i, 3 + j) = ::fmaf(a[2], A[j][2], ::fmaf(a[1], A[j][1], ::fmaf(a[0], A[j][0], PS(i, 3 + j))));
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-          PS(i, 6 + j) = ::fmaf(a[j2], S[j][j2], ::fmaf(a[j1], S[j][j1], a[j]));
-          PS(3 + i, 6 + j) = ::fmaf(T[i][j2], S[j][j2], ::fmaf(T[i][j1], S[j][j1], T[i][j]));
-        }
+      for (int c = 0; c < 3; c++) {
+        Vn[c] = f2_fma(PR(CP_VV + c), dt, PR(CP_PV + c));
+        v2n[c] = ::fmaf(dt, VVS(2, c), PVS(2, c));
       }
-      // Paa = S Paa S^T
-      float W[3][3];
+#define VN(r, c) ((r) == 0 ? Vn[c].x : ((r) == 1 ? Vn[c].y : v2n[c]))
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-          W[i][j] = ::fmaf(PS(6 + i, 6 + j2), S[j][j2], ::fmaf(PS(6 + i, 6 + j1), S[j][j1], PS(6 + i, 6 + j)));
+        for (int j = i; j < 3; j++) PPS(i, j) = ::fmaf(dt, VN(i, j) + PVS(j, i), PPS(i, j));
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        PRSET(CP_PA + c, f2_fma(PR(CP_VA + c), dt, PR(CP_PA + c)));
+        PAS(2, c) = ::fmaf(dt, VAS(2, c), PAS(2, c));
+      }
+      // F2: T = Pva + A Paa
+      float2 Tp[3];
+      float t2[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        Tp[j] = f2_fma(Acol[2], AAS(2, j), f2_fma(Acol[1], AAS(1, j), f2_fma(Acol[0], AAS(0, j), PR(CP_VA + j))));
+        t2[j] = ::fmaf(A[2][2], AAS(2, j), ::fmaf(A[2][1], AAS(1, j), ::fmaf(A[2][0], AAS(0, j), VAS(2, j))));
+      }
+      // Pvv += A Pva^T + T A^T   (rows 0, 1 for every column; (2,2) scalar; (2,0), (2,1) are the column-2 pair)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float2 acc = PR(CP_VV + j);
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc = f2_fma(Acol[k], VAS(j, k), acc);
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc = f2_fma(Tp[k], A[j][k], acc);
+        PRSET(CP_VV + j, acc);
+      }
+      {
+        float acc = Pm[CI_VV22];
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc = ::fmaf(A[2][k], VAS(2, k), acc);
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc = ::fmaf(t2[k], A[2][k], acc);
+        Pm[CI_VV22] = acc + qa;
+      }
+      Pm[CI_VV10] = Pm[SI(3, 4)];  // keep P exactly symmetric
+      Pm[SI(3, 3)] += qa;
+      Pm[SI(4, 4)] += qa;
+      // Ppv = Ppv_new + Ppa A^T
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float2 acc = Vn[j];
+        float a2 = v2n[j];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          acc = f2_fma(PR(CP_PA + k), A[j][k], acc);
+          a2 = ::fmaf(PAS(2, k), A[j][k], a2);
         }
+        PRSET(CP_PV + j, acc);
+        PVS(2, j) = a2;
+      }
+#undef VN
+      // Ppa = Ppa S^T ; Pva = T S^T ; W = Paa S^T   (S has a unit diagonal: two terms onto the diagonal one)
+      float2 An[3], Wp[3];
+      float a2n[3], w2[3];
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        An[j] = f2_fma(PR(CP_PA + j2), S[j][j2], f2_fma(PR(CP_PA + j1), S[j][j1], PR(CP_PA + j)));
+        a2n[j] = ::fmaf(PAS(2, j2), S[j][j2], ::fmaf(PAS(2, j1), S[j][j1], PAS(2, j)));
+        Wp[j] = f2_fma(PR(CP_AA + j2), S[j][j2], f2_fma(PR(CP_AA + j1), S[j][j1], PR(CP_AA + j)));
+        w2[j] = ::fmaf(AAS(2, j2), S[j][j2], ::fmaf(AAS(2, j1), S[j][j1], AAS(2, j)));
+      }
 #pragma unroll
-        for (int j = i; j < 3; j++) {
-          const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-          PS(6 + i, 6 + j) = ::fmaf(S[i][i2], W[i2][j], ::fmaf(S[i][i1], W[i1][j], W[i][j]));
-        }
+      for (int j = 0; j < 3; j++) {
+        const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        PRSET(CP_PA + j, An[j]);
+        PAS(2, j) = a2n[j];
+        PRSET(CP_VA + j, f2_fma(Tp[j2], S[j][j2], f2_fma(Tp[j1], S[j][j1], Tp[j])));
+        VAS(2, j) = ::fmaf(t2[j2], S[j][j2], ::fmaf(t2[j1], S[j][j1], t2[j]));
+      }
+      // Paa = S W   (rows 0, 1: pair from the columns of S, scalar from W; (2,2) scalar)
+#define WS(r, c) ((r) == 0 ? Wp[c].x : ((r) == 1 ? Wp[c].y : w2[c]))
 #pragma unroll
-      for (int k = 0; k < 3; k++) { PS(3 + k, 3 + k) += qa; PS(6 + k, 6 + k) += qg; }
-#undef PS
+      for (int j = 0; j < 3; j++)
+        PRSET(CP_AA + j, f2_fma(Scol[2], WS(2, j), f2_fma(Scol[1], WS(1, j), f2_mul(Scol[0], WS(0, j)))));
+      Pm[CI_AA22] = ::fmaf(S[2][1], WS(1, 2), ::fmaf(S[2][0], WS(0, 2), w2[2])) + qg;
+#undef WS
+      Pm[CI_AA10] = Pm[SI(6, 7)];
+      Pm[SI(6, 6)] += qg;
+      Pm[SI(7, 7)] += qg;
+#undef PR
+#undef PRSET
+#undef PVS
+#undef PAS
+#undef VAS
+#undef VVS
+#undef AAS
+#undef PPS
       cov_store(sc, Pm);
     } else {
 
@@ -1148,10 +1225,30 @@ AGF_DEV void kf_update_range(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, c
     Q4<float> att(s.katt[0], s.katt[1], s.katt[2], s.katt[3]);
     att = q_apply_rotvec<PARITY>(att, V3<float>(s.kcorr[0], s.kcorr[1], s.kcorr[2]));
     s.katt[0] = att.w; s.katt[1] = att.x; s.katt[2] = att.y; s.katt[3] = att.z;
+    // rows 0 and 1 of every block on the packed FP32 path (pair of gains x broadcast PHt + pair), row 2 and Ppp scalar
+    const float2 nLp = make_float2(-L[0], -L[1]), nLv = make_float2(-L[3], -L[4]), nLa = make_float2(-L[6], -L[7]);
+#define PR(k) make_float2(Pm[2 * (k)], Pm[2 * (k) + 1])
+#define PRSET(k, v) { const float2 v_ = (v); Pm[2 * (k)] = v_.x; Pm[2 * (k) + 1] = v_.y; }
 #pragma unroll
-    for (int i = 0; i < 9; i++)
+    for (int c = 0; c < 3; c++) {
+      PRSET(CP_PV + c, f2_fma(nLp, PHt[3 + c], PR(CP_PV + c)));
+      PRSET(CP_PA + c, f2_fma(nLp, PHt[6 + c], PR(CP_PA + c)));
+      PRSET(CP_VA + c, f2_fma(nLv, PHt[6 + c], PR(CP_VA + c)));
+      PRSET(CP_VV + c, f2_fma(nLv, PHt[3 + c], PR(CP_VV + c)));
+      PRSET(CP_AA + c, f2_fma(nLa, PHt[6 + c], PR(CP_AA + c)));
+      Pm[CI_PV2 + c] = ::fmaf(-L[2], PHt[3 + c], Pm[CI_PV2 + c]);
+      Pm[CI_PA2 + c] = ::fmaf(-L[2], PHt[6 + c], Pm[CI_PA2 + c]);
+      Pm[CI_VA2 + c] = ::fmaf(-L[5], PHt[6 + c], Pm[CI_VA2 + c]);
+    }
+#undef PR
+#undef PRSET
+    Pm[CI_VV22] = ::fmaf(-L[5], PHt[5], Pm[CI_VV22]);
+    Pm[CI_AA22] = ::fmaf(-L[8], PHt[8], Pm[CI_AA22]);
 #pragma unroll
-      for (int j = i; j < 9; j++) PS(i, j) = PS(i, j) - L[i] * PHt[j];
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = i; j < 3; j++) PS(i, j) = ::fmaf(-L[i], PHt[j], PS(i, j));
+    cov_fill_mirrors(Pm);  // the two lanes of (1,0) / (0,1) may round differently: keep P exactly symmetric
 #undef PS
     cov_store(sc, Pm);
   } else {
@@ -1501,30 +1598,40 @@ struct EstMsg {
   V3<double> acc, w;
   bool ballistic;
 };
-// The activation times of the queued prediction messages, fetched in one go: the scans below then run on registers
-// instead of a chain of dependent L2 round trips (the estimator state is read through L2, see ldg2).
+// The activation times of all message slots, fetched in one go: the scans below then run on registers instead of a
+// chain of dependent L2 round trips (the estimator state is read through L2, see ldg2).  A free slot reads E_SLOT_FREE.
 struct EstPipe {
-  int cnt;
   double ta[AGF_OFFEST_PIPE];
 };
 AGF_DEV void est_pipe_load(const double* st, size_t n, EstPipe& p) {
-  p.cnt = int(ldg2(st + E_NPIPE * n));
 #pragma unroll
   for (int k = 0; k < AGF_OFFEST_PIPE; k++) p.ta[k] = ldg2(st + size_t(E_PIPE + E_MSG * k) * n);
 }
-// PredictionPipe::GetActiveMessage (PredictionPipe.hpp:32-53) + the "no messages" default of its callers
+AGF_DEV int est_pipe_count(const EstPipe& p) {
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < AGF_OFFEST_PIPE; k++) c += p.ta[k] < E_SLOT_FREE ? 1 : 0;
+  return c;
+}
+// PredictionPipe::GetActiveMessage (PredictionPipe.hpp:32-53) + the "no messages" default of its callers.  The reference
+// walks from the newest message to the first one whose activation time has passed; activation times increase with the
+// order of arrival, so that message is the active one with the largest time, and the `tLast` it has when it stops is
+// the smallest time among the not-yet-active ones (agf_types.h: the slots are an unordered set).
 AGF_DEV void est_fetch(const double* st, size_t n, const EstPipe& pipe, double t, EstMsg& m, double& timeRemaining) {
   double tLast = 1e10;
   int hit = -1;
-  double taHit = 0.0;
+  double taHit = -1e300;
 #pragma unroll
-  for (int k = AGF_OFFEST_PIPE - 1; k >= 0; k--) {
-    if (k < pipe.cnt && hit < 0) {
-      if ((t + 1e-6) >= pipe.ta[k]) {
-        hit = k;
-        taHit = pipe.ta[k];
-      } else {
-        tLast = pipe.ta[k];
+  for (int k = 0; k < AGF_OFFEST_PIPE; k++) {
+    const double ta = pipe.ta[k];
+    if (ta < E_SLOT_FREE) {
+      if ((t + 1e-6) >= ta) {
+        if (ta > taHit) {
+          taHit = ta;
+          hit = k;
+        }
+      } else if (ta < tLast) {
+        tLast = ta;
       }
     }
   }
@@ -1556,12 +1663,12 @@ AGF_DEV V3<double> est_q_to_rotvec(const Q4<double>& q) {  // Rotation.hpp:144-1
 }
 // MocapStateEstimator::GetPrediction (MocapStateEstimator.cpp:61-118)
 template<bool PARITY>
-AGF_DEV void mocap_predict(const EstParams& ep, size_t i, size_t n, uint64_t now_us, double dt, EstCore& o) {
-  const double* st = ep.state + i;
+AGF_DEV void mocap_predict(const EstParams& ep, size_t i, uint64_t now_us, double dt, EstCore& o, EstPipe& pipe) {
+  constexpr size_t n = E_LANES;
+  const double* st = ep.state + est_index(i);
   const double tEnd = dt + double(now_us - ep.t0_us) * 1e-6;
   const double tStart = double(uint64_t(ldg2(st + E_TEST * n))) * 1e-6;
   EstCore m;
-  EstPipe pipe;
   est_pipe_load(st, n, pipe);
   est_load(st, n, m);
   o = m;
@@ -1609,11 +1716,24 @@ AGF_DEV void est_propagate_var(double* v, double dtInt, double proc) {  // A V A
 }
 // MocapStateEstimator::UpdateWithMeasurement (:120-265)
 template<bool PARITY>
-AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_us, const V3<double>& measPos, const Q4<double>& measAtt) {
-  double* st = ep.state + i;
+AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const V3<double>& measPos, const Q4<double>& measAtt) {
+  constexpr size_t n = E_LANES;
+  double* st = ep.state + est_index(i);
   EstCore e;
   double vp[4], va[4];
-  if (ldg2(st + E_INIT * n) == 0.0) {
+  // everything the update reads, requested before the first use (one L2 round trip instead of one per group)
+  const double inited = ldg2(st + E_INIT * n);
+  EstPipe pipe;
+  est_pipe_load(st, n, pipe);
+  est_load(st, n, e);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    vp[k] = ldg2(st + (E_VP + k) * n);
+    va[k] = ldg2(st + (E_VA + k) * n);
+  }
+  uint64_t est_us = uint64_t(ldg2(st + E_TEST * n));
+  double nrej = ldg2(st + E_NREJ * n), nrejc = ldg2(st + E_NREJC * n);
+  if (inited == 0.0) {
     e.pos = measPos;
     e.vel = V3<double>(0, 0, 0);
     e.att = measAtt;
@@ -1628,14 +1748,6 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
     st[E_LASTGOOD * n] = double(now_us);
     return;
   }
-  EstPipe pipe;
-  est_pipe_load(st, n, pipe);
-  est_load(st, n, e);
-  for (int k = 0; k < 4; k++) {
-    vp[k] = ldg2(st + (E_VP + k) * n);
-    va[k] = ldg2(st + (E_VA + k) * n);
-  }
-  uint64_t est_us = uint64_t(ldg2(st + E_TEST * n));
   const double t0 = double(est_us) * 1e-6;
   const double tEnd = double(now_us - ep.t0_us) * 1e-6;
   if (tEnd > t0) {
@@ -1665,7 +1777,6 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   const Q4<double> dq = qmul(qinv(measAtt), e.att);
   const double distA = (Mf<PARITY>::acos(::fabs(dq.w)) * 2.0) / ::sqrt(innovA);  // Rotation::GetAngle
   const bool reject = (distP > ep.reject) || (distA > ep.reject);
-  double nrej = ldg2(st + E_NREJ * n), nrejc = ldg2(st + E_NREJC * n);
   if (reject && nrejc < 10.0) {
     nrej += 1.0;
     nrejc += 1.0;
@@ -1723,36 +1834,45 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, size_t n, uint64_t now_
   st[E_TEST * n] = double(est_us);
   st[E_NREJ * n] = nrej;
   st[E_NREJC * n] = nrejc;
-  {  // PredictionPipe::ClearExpiredMessages(estimate time) (PredictionPipe.hpp:55-68)
-    // The loop erases the front message while the second one is already active: `drop` leading messages go, decided on the
-    // preloaded activation times, and the survivors move down in ONE pass (same final queue as erasing one at a time).
+  {  // PredictionPipe::ClearExpiredMessages(estimate time) (PredictionPipe.hpp:55-68): the front message goes while the
+    // second one is already active, i.e. every active message but the newest is freed (agf_types.h)
     const double cur = double(est_us) * 1e-6;
-    const int N = pipe.cnt;
-    int drop = 0;
-    for (int it = 0; it < N; it++) {
-      if (N - drop < 2) break;
-      double t1 = pipe.ta[AGF_OFFEST_PIPE - 1];
+    double newest = -1e300;
 #pragma unroll
-      for (int k = 0; k < AGF_OFFEST_PIPE - 1; k++) t1 = (drop + 1 == k) ? pipe.ta[k] : t1;  // _messages[1].timeActive of the current queue
-      if (t1 <= cur) drop++;
-    }
-    if (drop > 0) {
-      for (int k = 0; k + drop < N; k++)
-        for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = ldg2(st + size_t(E_PIPE + E_MSG * (k + drop) + f) * n);
-      st[E_NPIPE * n] = double(N - drop);
-    }
+    for (int k = 0; k < AGF_OFFEST_PIPE; k++)
+      if (pipe.ta[k] <= cur && pipe.ta[k] > newest) newest = pipe.ta[k];
+    int drop = 0;
+#pragma unroll
+    for (int k = 0; k < AGF_OFFEST_PIPE; k++)
+      if (pipe.ta[k] < newest) {
+        st[size_t(E_PIPE + E_MSG * k) * n] = E_SLOT_FREE;
+        drop++;
+      }
+    if (drop > 0) st[E_NPIPE * n] = double(est_pipe_count(pipe) - drop);
   }
 }
 // MocapStateEstimator::SetPredictedValues -> PredictionPipe::AddMessage (hpp:74-80, PredictionPipe.hpp:25-30)
-AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, size_t n, uint64_t now_us, const V3<double>& w, const V3<double>& acc) {
-  double* st = ep.state + i;
-  int cnt = int(ldg2(st + E_NPIPE * n));
-  if (cnt >= AGF_OFFEST_PIPE) {  // cannot happen while measurements arrive; keep the newest messages
-    for (int k = 0; k + 1 < cnt; k++)
-      for (int f = 0; f < E_MSG; f++) st[size_t(E_PIPE + E_MSG * k + f) * n] = ldg2(st + size_t(E_PIPE + E_MSG * (k + 1) + f) * n);
+AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, uint64_t now_us, const EstPipe& pipe, const V3<double>& w,
+                                    const V3<double>& acc) {
+  constexpr size_t n = E_LANES;
+  double* st = ep.state + est_index(i);
+  // `pipe`: the slots as mocap_predict read them for this command (nothing touches them in between)
+  int cnt = 0, slot = -1, oldest = 0;
+  double t_oldest = E_SLOT_FREE;
+#pragma unroll
+  for (int k = AGF_OFFEST_PIPE - 1; k >= 0; k--) {
+    if (pipe.ta[k] < E_SLOT_FREE) cnt++;
+    else slot = k;
+    if (pipe.ta[k] <= t_oldest) {
+      t_oldest = pipe.ta[k];
+      oldest = k;
+    }
+  }
+  if (slot < 0) {  // full: cannot happen while measurements arrive; keep the newest messages
+    slot = oldest;
     cnt--;
   }
-  double* q = st + size_t(E_PIPE + E_MSG * cnt) * n;
+  double* q = st + size_t(E_PIPE + E_MSG * slot) * n;
   q[0] = double(now_us - ep.t0_us) * 1e-6 + ep.delay;
   q[1 * n] = acc.x; q[2 * n] = acc.y; q[3 * n] = acc.z;
   q[4 * n] = w.x; q[5 * n] = w.y; q[6 * n] = w.z;
@@ -1760,8 +1880,8 @@ AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, size_t n, uint64
   st[E_NPIPE * n] = double(cnt + 1);
 }
 template<typename P>
-static AGF_COLD void mocap_update_cold(const EstParams* ep, size_t i, size_t n, uint64_t now_us, V3<P> p, Q4<P> a) {
-  mocap_update<false>(*ep, i, n, now_us, V3<double>(double(p.x), double(p.y), double(p.z)),
+static AGF_COLD void mocap_update_cold(const EstParams* ep, size_t i, uint64_t now_us, V3<P> p, Q4<P> a) {
+  mocap_update<false>(*ep, i, now_us, V3<double>(double(p.x), double(p.y), double(p.z)),
                       Q4<double>(double(a.w), double(a.x), double(a.y), double(a.z)));
 }
 
@@ -1836,7 +1956,7 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
   // SafetyNet::UpdateWithEstimator + GetIsSafe (SafetyNet.hpp:70-106), on every Run()
   bool safe = true;
   if (c.safety_net) {
-    const double since = c.est.kind == AGF_OFFEST_MOCAP ? double(t_gen - uint64_t(ldg2(c.est.state + i + size_t(E_LASTGOOD) * n))) * 1e-6 : 0.0;
+    const double since = c.est.kind == AGF_OFFEST_MOCAP ? double(t_gen - uint64_t(ldg2(c.est.state + est_index(i) + size_t(E_LASTGOOD) * E_LANES))) * 1e-6 : 0.0;
     const bool notSeen = since > c.not_seen_timeout;
     bool unsafePos = false;
     const double ep[3] = {cp.x, cp.y, cp.z};
@@ -1975,8 +2095,9 @@ template<bool PARITY, typename P>
 AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, uint64_t t_gen, const V3<P>& cp, const V3<P>& cv,
                                  const Q4<P>& ca) {
   EstCore e;
+  EstPipe pipe;
   if (c.est.kind == AGF_OFFEST_MOCAP) {
-    mocap_predict<PARITY>(c.est, i, n, t_gen, c.est.delay, e);
+    mocap_predict<PARITY>(c.est, i, t_gen, c.est.delay, e, pipe);
   } else {
     e.pos = V3<double>(double(cp.x), double(cp.y), double(cp.z));
     e.vel = V3<double>(double(cv.x), double(cv.y), double(cv.z));
@@ -1987,8 +2108,8 @@ AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, ui
   V3<double> w(0, 0, 0);
   const float4 out = offboard_generate_core<PARITY>(c, i, n, t_gen, e.pos, e.vel, e.att, predicted, thrust, w);
   if (c.est.kind == AGF_OFFEST_MOCAP) {
-    if (predicted == 1) mocap_set_predicted(c.est, i, n, t_gen, V3<double>(0, 0, 0), V3<double>(0, 0, 0));
-    if (predicted == 2) mocap_set_predicted(c.est, i, n, t_gen, w, qrot(e.att, V3<double>(0, 0, 1)) * thrust - V3<double>(0, 0, 9.81));
+    if (predicted == 1) mocap_set_predicted(c.est, i, t_gen, pipe, V3<double>(0, 0, 0), V3<double>(0, 0, 0));
+    if (predicted == 2) mocap_set_predicted(c.est, i, t_gen, pipe, w, qrot(e.att, V3<double>(0, 0, 1)) * thrust - V3<double>(0, 0, 9.81));
   }
   return out;
 }
@@ -2440,10 +2561,10 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     const V3<P> mp(s.pos[0], s.pos[1], s.pos[2]);
     const Q4<P> ma(s.att[0], s.att[1], s.att[2], s.att[3]);
     if constexpr (PARITY) {
-      mocap_update<true>(p.off.est, i, n, now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
+      mocap_update<true>(p.off.est, i, now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
                          Q4<double>(double(ma.w), double(ma.x), double(ma.y), double(ma.z)));
     } else {
-      mocap_update_cold<P>(&p.off.est, i, n, now_us + dt_us, mp, ma);
+      mocap_update_cold<P>(&p.off.est, i, now_us + dt_us, mp, ma);
     }
   }
   if (OFFB && plan.off_generate) {  // offboard main loop (main.cpp:471-673), after the clock advance

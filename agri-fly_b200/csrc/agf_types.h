@@ -288,16 +288,26 @@ struct AnchorDev {
 };
 
 // Offboard::MocapStateEstimator of the in-kernel offboard loop (agrifly_b200.h "offboard loop: state estimator")
-// state fields [field][N]: position, velocity, angular velocity, attitude, 2x2 variances (row-major), estimate time
-// [us], time of the last accepted measurement, initialised flag, rejection counters, prediction pipe (count, then
-// AGF_OFFEST_PIPE messages of time-active, acceleration, angular velocity, ballistic flag)
+// state fields: position, velocity, angular velocity, attitude, 2x2 variances (row-major), estimate time [us], time of
+// the last accepted measurement, initialised flag, rejection counters, prediction pipe (message count, then
+// AGF_OFFEST_PIPE message slots of time-active, acceleration, angular velocity, ballistic flag).
+// Storage is blocked by warp, [vehicle / 32][field][vehicle % 32]: field k of vehicle i sits at
+// state[est_index(i) + k * E_LANES], so every access of the device code is base register + immediate (no index
+// arithmetic) and a warp's access is 256 contiguous bytes.
+// The pipe is an unordered set of slots: a free slot holds time-active = E_SLOT_FREE.  Activation times are strictly
+// increasing in the order messages are added (PredictionPipe.hpp:25-30 stamps them with the clock), so "the newest
+// message that is already active" and "the oldest one that is not yet" (GetActiveMessage, :32-53) are a maximum and a
+// minimum over the slots, and ClearExpiredMessages (:55-68) frees every active message but the newest: no message ever moves.
 enum { E_POS = 0, E_VEL = 3, E_W = 6, E_ATT = 9, E_VP = 13, E_VA = 17, E_TEST = 21, E_LASTGOOD = 22, E_INIT = 23, E_NREJ = 24,
-       E_NREJC = 25, E_NPIPE = 26, E_PIPE = 27, E_MSG = 8, E_FIELDS = E_PIPE + E_MSG * AGF_OFFEST_PIPE };
+       E_NREJC = 25, E_NPIPE = 26, E_PIPE = 27, E_MSG = 8, E_FIELDS = E_PIPE + E_MSG * AGF_OFFEST_PIPE, E_LANES = 32 };
+#define E_SLOT_FREE 1e300
+AGF_HDI size_t est_index(size_t i) { return (i / E_LANES) * (size_t(E_FIELDS) * E_LANES) + (i % E_LANES); }
+AGF_HDI size_t est_doubles(size_t n) { return ((n + E_LANES - 1) / E_LANES) * (size_t(E_FIELDS) * E_LANES); }
 struct EstParams {
   int kind;
   uint64_t t0_us;  // clock reading at construction: origin of the estimator's and its pipe's Timer
   double delay, reject, tc_angvel, meas_pos, meas_att, proc_pos, proc_att;
-  double* state;   // device [E_FIELDS][N]
+  double* state;   // device, est_doubles(N) values, see est_index
 };
 // Offboard::QuadcopterController + radio link of the in-kernel offboard loop (agrifly_b200.h "offboard rates loop")
 struct OffboardParams {

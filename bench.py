@@ -19,8 +19,9 @@ communicator when N > 1 -- agf_batch_reduce_stats_comm).  Vehicles shard by cont
 communication inside the step (weak scaling).
 
 value   = vehicle-steps/s over all GPUs, state resident in HBM, CUDA events on the launching stream, max over ranks.
-e2e     = the same through the public C ABI with HOST buffers: every step copies the population's 6-DOF state in from
-          pinned host memory, runs the ticks, and copies positions (C4: the last logged record) and the statistics back.
+e2e     = the same through the public C ABI with HOST buffers: the population's 6-DOF state lives in pinned host memory
+          between steps; every step copies it in (agf_batch_set_state), runs the ticks, and copies the state (C4: and
+          the last logged record) and the statistics back out.
 roofline  C3 is ALU-bound (nothing is a contraction; state stays in registers).  FLOP per vehicle-step, three ways:
             frac               SURVEY.md 8(d)'s contract figure (2 900 full mode: the sparsity-aware hand count)
             frac_instrumented  hardware-counted on the literal restatement of the reference's algorithm (parity kernel, HK on)
@@ -396,10 +397,13 @@ def main():
         final_stats = stats.cpu().numpy().copy()
 
         # ---- e2e: public API with host buffers -------------------------------------------------
-        pin13 = torch.from_numpy(np.ascontiguousarray(init[:, 0:13])).pin_memory()  # the population's 6-DOF state, pinned host memory
+        # the population's 6-DOF state lives in pinned host memory between steps: read back at the end of a step, handed in
+        # again at the start of the next (a host-owned state, as with the reference's objects; teleporting the vehicles to
+        # some fixed state every step instead would throw the onboard estimators off and change the workload)
+        pin13 = torch.empty((n, 13), dtype=torch.float64).pin_memory()
+        agf._check(b.L.agf_batch_get_state(b.h, pin13.data_ptr(), 0, n))
         if c4:
             rec_out = torch.empty((n, 17), dtype=torch.float64).pin_memory()
-        pos_out = torch.empty((n, 3), dtype=torch.float64).pin_memory()
         ke = max(2, min(K, 10))
 
         def e2e_step():
@@ -407,8 +411,7 @@ def main():
             b.run(S)
             if c4:  # D2H: the newest logged record of every vehicle
                 agf._check(b.L.agf_batch_read_log(b.h, b.log_count - 1, rec_out.data_ptr(), 0, n))
-            else:   # D2H positions
-                agf._check(b.L.agf_batch_get_field(b.h, 0, pos_out.data_ptr(), 0, n))
+            agf._check(b.L.agf_batch_get_state(b.h, pin13.data_ptr(), 0, n))  # D2H: the state, into the same pinned buffer
             return comm.reduce_host() if comm is not None else b.stats()  # D2H statistics vector
 
         e2e_step()
@@ -460,8 +463,9 @@ def main():
                     l2_flush="256 MiB memset between timed steps (inside the timed region); state stays in registers "
                              "during a step, HBM is touched only at launch boundaries" + (" and by the trajectory log" if c4 else "")),
         e2e=dict(value=e2e_value, unit="vehicle-steps/s", h2d_bytes_per_step=int(n * 13 * 8),
-                 d2h_bytes_per_step=int(n * (17 if c4 else 3) * 8 + 128), steps=ke,
-                 note="per GPU bytes; state set from pinned host memory, %s + statistics read back" % ("newest log record" if c4 else "positions")),
+                 d2h_bytes_per_step=int(n * (13 + (17 if c4 else 0)) * 8 + 128), steps=ke,
+                 note="per GPU bytes; every step: the population's 6-DOF state in from pinned host memory (agf_batch_set_state), the "
+                      "ticks, %sthe state (agf_batch_get_state) and the statistics vector back out" % ("the newest log record, " if c4 else "")),
         gpu_launches=int(launches), roofline=roof, wall_ms=t_wall * 1e3, stats=sharding.summarize_stats(final_stats),
     )
     if rank == 0 and clocks is not None:

@@ -299,9 +299,13 @@ enum {
 };
 int agf_batch_get_field(agf_batch* b, int field, void* host_dst, size_t first, size_t count);
 int agf_batch_set_field(agf_batch* b, int field, const void* host_src, size_t first, size_t count);
-/* SetPosition + SetVelocity + SetAttitude + SetAngularVelocity (SimulationObject6DOF.hpp:26-56) of a vehicle range in one
+/* SetPosition + SetVelocity + SetAttitude + SetAngularVelocity (SimulationObject6DOF.hpp:42-56) of a vehicle range in one
  * call and one host-to-device copy: state13 = [count][13] doubles, position 3, velocity 3, attitude w x y z, angular velocity 3. */
 int agf_batch_set_state(agf_batch* b, const double* state13, size_t first, size_t count);
+/* GetPosition + GetVelocity + GetAttitude + GetAngularVelocity (SimulationObject6DOF.hpp:26-40) of a vehicle range in one
+ * call and one device-to-host copy, same [count][13] layout: a host that owns the population's state between steps reads
+ * it with this and hands it back with agf_batch_set_state. */
+int agf_batch_get_state(agf_batch* b, double* state13, size_t first, size_t count);
 /* bytes per vehicle of a field's host representation */
 size_t agf_field_size(int field);
 

@@ -216,11 +216,12 @@ void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e)
     v->sh.tc.mocap_enabled = 0;
     return;
   }
-  v->offest.assign(E_FIELDS, 0.0);
-  v->offest[E_ATT] = 1.0;
-  v->offest[E_VP] = 25.0; v->offest[E_VP + 3] = 25.0;
-  v->offest[E_VA] = 1.0; v->offest[E_VA + 3] = 400.0;
-  v->offest[E_LASTGOOD] = double(v->now_us);
+  v->offest.assign(est_doubles(1), 0.0);  // vehicle 0 of a warp-blocked array: field k at [k * E_LANES]
+  v->offest[E_ATT * E_LANES] = 1.0;
+  v->offest[E_VP * E_LANES] = 25.0; v->offest[(E_VP + 3) * E_LANES] = 25.0;
+  v->offest[E_VA * E_LANES] = 1.0; v->offest[(E_VA + 3) * E_LANES] = 400.0;
+  v->offest[E_LASTGOOD * E_LANES] = double(v->now_us);
+  for (int k = 0; k < AGF_OFFEST_PIPE; k++) v->offest[(E_PIPE + E_MSG * k) * E_LANES] = E_SLOT_FREE;
   p.kind = AGF_OFFEST_MOCAP;
   p.t0_us = v->now_us;
   p.delay = e->prediction_delay;
@@ -236,11 +237,12 @@ void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e)
 
 void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* o, double* c4) {
   EstCore e;
-  mocap_predict<true>(v->sh.off.est, 0, 1, v->now_us, horizon, e);
+  EstPipe pipe;
+  mocap_predict<true>(v->sh.off.est, 0, v->now_us, horizon, e, pipe);
   const double x[13] = {e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z, e.att.w, e.att.x, e.att.y, e.att.z, e.w.x, e.w.y, e.w.z};
   for (int k = 0; k < 13; k++) o[k] = x[k];
   if (c4) {
-    c4[0] = v->offest[E_INIT]; c4[1] = v->offest[E_NREJ]; c4[2] = v->offest[E_NREJC]; c4[3] = v->offest[E_NPIPE];
+    c4[0] = v->offest[E_INIT * E_LANES]; c4[1] = v->offest[E_NREJ * E_LANES]; c4[2] = v->offest[E_NREJC * E_LANES]; c4[3] = v->offest[E_NPIPE * E_LANES];
   }
 }
 
