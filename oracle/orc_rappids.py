@@ -100,6 +100,20 @@ class Planner:
         L.orc_rappids_primitive.argtypes = [_dp] * 4 + [C.c_double] * 6 + [_dp, C.POINTER(C.c_int32),
                                                                             C.POINTER(C.c_int32)]
 
+    def ground_truth(self, cfg, image, vel0, acc0, grav, candidates):
+        """DepthImagePlanner::IsCollisionFreeGroundTruth for each candidate [n][4] -> bool[n]."""
+        L = self.lib
+        L.orc_rappids_ground_truth.restype = C.c_int
+        L.orc_rappids_ground_truth.argtypes = [C.POINTER(Cfg), C.c_void_p, _dp, _dp, _dp, C.c_int32, _dp, C.c_void_p]
+        image = np.ascontiguousarray(image, dtype=np.uint16)
+        v, a, g = (np.ascontiguousarray(x, dtype=np.float64) for x in (vel0, acc0, grav))
+        candidates = np.ascontiguousarray(candidates, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros(len(candidates), dtype=np.uint8)
+        rc = L.orc_rappids_ground_truth(C.byref(cfg), image.ctypes.data, _d(v), _d(a), _d(g), len(candidates), _d(candidates),
+                                        out.ctypes.data)
+        assert rc == 0
+        return out.astype(bool)
+
     def plan(self, cfg, image, vel0, acc0, grav, n=None, candidates=None, seed=0, sampler=None, max_pyr=256):
         """-> dict(out fields..., results[n] u8, candidates[n,4], pyramids[n_pyr,17])."""
         image = np.ascontiguousarray(image, dtype=np.uint16)

@@ -1051,6 +1051,59 @@ int orc_rappids_plan_many(const orc_rappids_cfg* cfg, int32_t n, const uint16_t*
   return 0;
 }
 
+// DepthImagePlanner::IsCollisionFreeGroundTruth (DepthImagePlanner.cpp:1031-1097), restated
+int orc_rappids_ground_truth(const orc_rappids_cfg* cfg, const uint16_t* image, const double vel0[3], const double acc0[3],
+                             const double grav[3], int32_t n, const double* cands, uint8_t* free_out) {
+  const int W = cfg->width, H = cfg->height;
+  const double f = cfg->focal_length, cx = cfg->cx, cy = cfg->cy;
+  const double timestep = 0.1;
+  const uint16_t ignoreDist = uint16_t(cfg->true_radius / cfg->depth_scale);
+  const int edge = f * cfg->true_radius / cfg->min_checking_dist;
+  for (int i = 0; i < n; i++) {
+    const double* c = cands + 4 * i;
+    Prim p;
+    p.init(vel0, acc0, grav);
+    p.generate(c, c[3]);
+    Poly P;
+    p.coeffs(P.c);
+    const double T = c[3];
+    bool ok = true;
+    for (double t = 0; t < T && ok; t += timestep) {  // field of view first (:1042-1057)
+      const double x = P.axis(0, t), y = P.axis(1, t), z = P.axis(2, t);
+      if (z < cfg->min_checking_dist) continue;
+      const double px = x * f / z + cx, py = y * f / z + cy;
+      if (px <= edge || px > W - edge || py <= edge || py > H - edge) ok = false;
+    }
+    for (double t = 0; t < T && ok; t += timestep) {  // every pixel's ray against the vehicle sphere (:1060-1094)
+      const double tp[3] = {P.axis(0, t), P.axis(1, t), P.axis(2, t)};
+      if (tp[2] < cfg->min_checking_dist) continue;
+      const double n2 = tp[0] * tp[0] + tp[1] * tp[1] + tp[2] * tp[2];
+      for (int yy = 0; yy < H && ok; yy++)
+        for (int xx = 0; xx < W; xx++) {
+          const uint16_t d = image[yy * W + xx];
+          if (!(d > ignoreDist)) continue;
+          const double v[3] = {(xx - cx) / f, (yy - cy) / f, 1.0};
+          const float nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);  // GetUnitVector: the norm is a float (Vec3.hpp:127)
+          const double e[3] = {v[0] / nrm, v[1] / nrm, v[2] / nrm};
+          const double te = tp[0] * e[0] + tp[1] * e[1] + tp[2] * e[2];
+          const double under = pow(te, 2) - n2 + pow(cfg->planning_radius, 2);
+          if (under >= 0) {
+            const double second = (e[0] * tp[0] + e[1] * tp[1] + e[2] * tp[2]) + sqrt(under);
+            const double depth = d * cfg->depth_scale;
+            const double q[3] = {depth * ((xx - cx) / f), depth * ((yy - cy) / f), depth * 1};
+            const double pd = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+            if (pd < second) {
+              ok = false;
+              break;
+            }
+          }
+        }
+    }
+    free_out[i] = ok ? 1 : 0;
+  }
+  return 0;
+}
+
 int orc_rappids_solve_cubic(double a, double b, double c, double roots[3]) { return (int)cubic(a, b, c, roots); }
 int orc_rappids_solve_quartic(double a, double b, double c, double d, double roots[4]) {
   return (int)quartic(a, b, c, d, roots);

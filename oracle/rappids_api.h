@@ -73,6 +73,14 @@ int orc_rappids_plan_many(const orc_rappids_cfg* cfg, int32_t n, const uint16_t*
                           int32_t n_candidates, const double* candidates, orc_rappids_out* out,
                           uint8_t* results, int32_t threads);
 
+/* The reference's own, algorithm-independent check of the collision test (DepthImagePlanner::IsCollisionFreeGroundTruth,
+ * DepthImagePlanner.cpp:1031-1097: the trajectory sampled every 0.1 s, field-of-view test, then every pixel's ray against
+ * the sphere around the vehicle; used by MeasureConservativeness, :972-1003).  candidates [n][4] as above;
+ * free_out[i] = 1 when the ground truth finds candidate i collision free. */
+int orc_rappids_ground_truth(const orc_rappids_cfg* cfg, const uint16_t* image, const double vel0[3],
+                             const double acc0[3], const double grav[3], int32_t n_candidates,
+                             const double* candidates, uint8_t* free_out);
+
 /* pieces, for unit pins */
 int orc_rappids_solve_cubic(double a, double b, double c, double roots[3]);
 int orc_rappids_solve_quartic(double a, double b, double c, double d, double roots[4]);

@@ -194,6 +194,28 @@ int orc_rappids_plan_many(const orc_rappids_cfg* cfg, int32_t n, const uint16_t*
   return 0;
 }
 
+int orc_rappids_ground_truth(const orc_rappids_cfg* cfg, const uint16_t* image, const double vel0[3], const double acc0[3],
+                             const double grav[3], int32_t n, const double* cands, uint8_t* free_out) {
+  cv::Mat img;
+  img.rows = cfg->height;
+  img.cols = cfg->width;
+  img.data = (unsigned char*)image;
+  DepthImagePlanner planner(img, cfg->depth_scale, cfg->focal_length, cfg->cx, cfg->cy, cfg->true_radius,
+                            cfg->planning_radius, cfg->min_checking_dist);
+  configure(planner, cfg);
+  for (int i = 0; i < n; i++) {
+    const double* c = cands + 4 * i;
+    RapidTrajectoryGenerator traj(Vec3d(0, 0, 0), Vec3d(vel0[0], vel0[1], vel0[2]), Vec3d(acc0[0], acc0[1], acc0[2]),
+                                  Vec3d(grav[0], grav[1], grav[2]));
+    traj.SetGoalPosition(Vec3d(c[0], c[1], c[2]));
+    traj.SetGoalVelocity(Vec3d(0, 0, 0));
+    traj.SetGoalAcceleration(Vec3d(0, 0, 0));
+    traj.Generate(c[3]);
+    free_out[i] = planner.IsCollisionFreeGroundTruth(traj.GetTrajectory()) ? 1 : 0;
+  }
+  return 0;
+}
+
 int orc_rappids_solve_cubic(double a, double b, double c, double roots[3]) {
   return (int)RootFinder::solve_cubic<double>(a, b, c, roots);
 }

@@ -59,6 +59,26 @@ def port_glibc(orc_mod):
     return oracle_or_skip(orc_mod, "port-glibc")
 
 
+# The checker of the GPU parity tests: the UNMODIFIED reference sources (oracle/_ref, built where /root/reference exists and
+# shipped to the GPU box) when present, else the port (bit-identical to it: tests/test_oracle.py).  AGF_TEST_ORACLE=port forces
+# the port.
+def _checker(orc, flavour):
+    import os
+    if os.environ.get("AGF_TEST_ORACLE", "") != "port" and orc.available("ref-" + flavour):
+        return orc.Oracle("ref-" + flavour)
+    return oracle_or_skip(orc, "port-" + flavour)
+
+
+@pytest.fixture(scope="session")
+def checker_shared(orc_mod):
+    return _checker(orc_mod, "shared")
+
+
+@pytest.fixture(scope="session")
+def checker_glibc(orc_mod):
+    return _checker(orc_mod, "glibc")
+
+
 def has_cuda():
     try:
         import torch

@@ -53,14 +53,14 @@ def test_facade_has_no_cpu_fallback(agf):
 
 
 @pytest.mark.gpu
-def test_object_api_loop_matches_oracle(agf, port_shared):
+def test_object_api_loop_matches_oracle(agf, checker_shared):
     build_example()
     sc = agf.scenarios.rates_scenario(agf.codec)
     r = subprocess.run([BIN, str(sc["nticks"])], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     rows = np.array([[float(x) for x in ln.split()] for ln in r.stdout.strip().splitlines()])
     assert len(rows) == 5
-    ref, _ = run_oracle(port_shared, agf, sc)
+    ref, _ = run_oracle(checker_shared, agf, sc)
     for row in rows:
         k = int(row[0])
         assert bit_equal(row[1:18], ref[k, 0:17]), (k, row[1:18] - ref[k, 0:17])

@@ -48,9 +48,9 @@ def gpu_traj(agf, sc, n=1, sample_every=250, **kw):
 
 
 @pytest.mark.parametrize("name", ["rates", "full", "accel"])
-def test_parity_variant_is_bit_identical_to_oracle(agf, port_shared, name):
+def test_parity_variant_is_bit_identical_to_oracle(agf, checker_shared, name):
     sc = scenario(agf, name)
-    ref, v = run_oracle(port_shared, agf, sc)
+    ref, v = run_oracle(checker_shared, agf, sc)
     b, log, ticks, samples = gpu_traj(agf, sc, n=3)
     for veh in range(3):  # identical vehicles must stay identical
         # stated tolerance first (1e-9 relative), then the stronger bit-level claim
@@ -98,7 +98,7 @@ def test_launch_chunking_is_invisible(agf):
     b2.close()
 
 
-def test_balanced_schedule_parity_variant(agf, port_shared):
+def test_balanced_schedule_parity_variant(agf, checker_shared):
     """More vehicle blocks than resident CTAs: the launch deals block-ticks out evenly and hands a block's
     state from one CTA to its neighbour in mid-launch (agf_step.cuh "balanced schedule").  Every vehicle
     gets the same inputs, so every one of them must equal the oracle's single trajectory bit for bit."""
@@ -109,7 +109,7 @@ def test_balanced_schedule_parity_variant(agf, port_shared):
     b.run(3)      # odd launch lengths: the cut points fall inside blocks
     b.run(697)
     got = b.record()
-    ref, _ = run_oracle(port_shared, agf, sc)
+    ref, _ = run_oracle(checker_shared, agf, sc)
     assert bit_equal(got, np.tile(ref[-1], (n, 1)))
     cov = b.get("est_covariance")
     assert bit_equal(cov, np.tile(cov[0], (n, 1)))
@@ -139,7 +139,7 @@ def test_balanced_schedule_fast_variant_with_noise(agf):
     assert bit_equal(out[0][1][:2000], out[1][1])
 
 
-def test_offboard_loop_parity(agf, port_shared):
+def test_offboard_loop_parity(agf, checker_shared):
     """Rappids_Simulator's closed loop (offboard position controller -> 16-bit rates commands -> 30 ms
     uplink delay -> onboard rate controller; estimate = truth) inside the kernel, per vehicle with its own set-point
     offset.  Parity variant == oracle bit for bit for every vehicle, across launch boundaries."""
@@ -151,7 +151,7 @@ def test_offboard_loop_parity(agf, port_shared):
         b.run(c)
     got = b.record()
     for i in range(n):
-        ref, _ = run_oracle_offboard(port_shared, agf, sc, offset=offs[i])
+        ref, _ = run_oracle_offboard(checker_shared, agf, sc, offset=offs[i])
         assert bit_equal(got[i], ref[-1]), (i, got[i][0:3], ref[-1][0:3])
     # the population flew: everybody near its own set-point, rates mode, no panic
     tgt = np.array(sc["targets"][2][1]) + offs  # 1 s after the last set-point change: still descending
@@ -160,13 +160,13 @@ def test_offboard_loop_parity(agf, port_shared):
     b.close()
 
 
-def test_offboard_loop_fast_variants_and_object_api(agf, port_glibc):
+def test_offboard_loop_fast_variants_and_object_api(agf, checker_glibc):
     """Fast FP64/FP32 kernels fly the same loop within the stated tolerance (position 1e-3 / 5e-3 relative, whole plant state
     incl. body rates and motor speeds 1e-2: closed loop through float controllers and a 16-bit quantiser whose
     rounding boundaries amplify last-bit differences into one-LSB command differences), also when a big
     population takes the balanced schedule; and the split Run()/advance path (object facade) equals the fused path."""
     sc = agf.scenarios.offboard_scenario(nticks=3000)
-    ref, _ = run_oracle_offboard(port_glibc, agf, sc)
+    ref, _ = run_oracle_offboard(checker_glibc, agf, sc)
     for prec in (agf.abi.PREC_FP64, agf.abi.PREC_FP32):
         b = make_batch_offboard(agf, sc, n=3, precision=prec, math=agf.abi.MATH_FAST)
         b.run(sc["nticks"])
@@ -196,7 +196,7 @@ def test_offboard_loop_fast_variants_and_object_api(agf, port_glibc):
 
 
 @pytest.mark.parametrize("name", ["stages1", "stages3", "stages4", "tracking"])
-def test_offboard_reference_generators_parity(agf, port_shared, name):
+def test_offboard_reference_generators_parity(agf, checker_shared, name):
     """the flight-stage state machine of the ROS rates-control node and Rappids_Simulator's primitive
     tracking (RunTracking with thrust / angular-velocity feed-forward) evaluated per vehicle inside the kernel.
     Parity variant == oracle bit for bit for every vehicle (own set-point offset / own primitive), across launch
@@ -221,11 +221,11 @@ def test_offboard_reference_generators_parity(agf, port_shared, name):
         sci = dict(sc)
         if prims is not None:
             sci["primitive"] = None
-            v = port_shared.vehicle(cfg_for(agf, sc), uwb_comm_period=0.0)
+            v = checker_shared.vehicle(cfg_for(agf, sc), uwb_comm_period=0.0)
             v.set_state(pos=sc["pos"], att=sc["att"])
             ref = v.run_offboard_ref(sc["nticks"], agf.offboard_cfg(sc["quad_type"]), agf.offboard_ref(**sc["ref"]), trajectory=prims[i])
         else:
-            ref, v = run_oracle_offboard_ref(port_shared, agf, sc, offset=offs[i])
+            ref, v = run_oracle_offboard_ref(checker_shared, agf, sc, offset=offs[i])
             assert bit_equal(b.offboard_state(i, 1)[0], v.offboard_state()), i
         assert bit_equal(got[i], ref[-1]), (name, i, got[i][0:3], ref[-1][0:3])
     assert np.all(got[:, 35] == 0)
@@ -241,12 +241,12 @@ def test_offboard_reference_generators_parity(agf, port_shared, name):
     b2.close()
 
 
-def test_offboard_reference_generators_fast_variants(agf, port_glibc):
+def test_offboard_reference_generators_fast_variants(agf, checker_glibc):
     """Fast FP64 / FP32 kernels fly the stages and the tracked primitive within the offboard loop's stated tolerance
     (position 1e-3 / 5e-3 relative to the oracle with glibc libm), also for a population on the balanced schedule."""
     s = agf.scenarios
     for sc, nt in ((s.stages_scenario(3), 4000), (s.tracking_scenario(), 3400)):
-        ref, _ = run_oracle_offboard_ref(port_glibc, agf, sc, nticks=nt)
+        ref, _ = run_oracle_offboard_ref(checker_glibc, agf, sc, nticks=nt)
         for prec in (agf.abi.PREC_FP64, agf.abi.PREC_FP32):
             b = make_batch_offboard_ref(agf, sc, n=3, precision=prec, math=agf.abi.MATH_FAST)
             b.run(nt)
@@ -267,7 +267,7 @@ def test_offboard_reference_generators_fast_variants(agf, port_glibc):
 
 
 @pytest.mark.parametrize("name,jump", [("offboard", None), ("stages1", None), ("tracking", None), ("offboard", 1000)])
-def test_offboard_estimator_parity(agf, port_shared, name, jump):
+def test_offboard_estimator_parity(agf, checker_shared, name, jump):
     """SURVEY 8f N1: Offboard::MocapStateEstimator per vehicle inside the kernel (mocap packets every 5 ms of simulation
     time, prediction through the queued commands, GetPrediction feeding the offboard controller).  Parity variant ==
     oracle bit for bit: trajectory, estimates at two horizons and counters, across launch boundaries; the jump case
@@ -275,7 +275,7 @@ def test_offboard_estimator_parity(agf, port_shared, name, jump):
     s = agf.scenarios
     sc = s.offboard_scenario(2000 if jump else 3000) if name == "offboard" else (
         s.tracking_scenario() if name == "tracking" else s.stages_scenario(int(name[-1]), nticks=5500))
-    ref, eref = run_oracle_estimator(port_shared, agf, sc, jump_at=jump)
+    ref, eref = run_oracle_estimator(checker_shared, agf, sc, jump_at=jump)
     b = make_batch_estimator(agf, sc, n=3)
     left = sc["nticks"]
     if jump:
@@ -325,11 +325,11 @@ def test_flight_stages_on_the_gpu_match_the_unmodified_ros_state_machine(agf, ca
     b.close()
 
 
-def test_offboard_estimator_fast_variants(agf, port_glibc):
+def test_offboard_estimator_fast_variants(agf, checker_glibc):
     """Fast FP64 / FP32 kernels with the estimator in the loop: position within the offboard loop's stated tolerance of the
     oracle (1e-3 / 5e-3 relative), estimate within 2 cm of the truth, for a population on the balanced schedule too."""
     sc = agf.scenarios.offboard_scenario(3000)
-    ref, _ = run_oracle_estimator(port_glibc, agf, sc)
+    ref, _ = run_oracle_estimator(checker_glibc, agf, sc)
     for prec in (agf.abi.PREC_FP64, agf.abi.PREC_FP32):
         b = make_batch_estimator(agf, sc, n=3, precision=prec, math=agf.abi.MATH_FAST)
         b.run(sc["nticks"])
@@ -350,7 +350,7 @@ def test_offboard_estimator_fast_variants(agf, port_glibc):
 
 
 @pytest.mark.parametrize("n,nt", [(192, 2500), (4096, 5000)])
-def test_monte_carlo_population_parity(agf, port_shared, n, nt):
+def test_monte_carlo_population_parity(agf, checker_shared, n, nt):
     """BASELINE config 2 -- at a small size and at its FULL size (4 096 vehicles, 10 s at 500 Hz; the oracle needs a few
     seconds on all host cores): randomized initial states, per-vehicle hover set-points (command slot), full onboard
     mode, noise-free, FP64 parity -> bit-identical for every vehicle."""
@@ -364,7 +364,7 @@ def test_monte_carlo_population_parity(agf, port_shared, n, nt):
     anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
     slots = np.zeros((4, n, 23), np.uint8)
     slots[0] = slot
-    ref, _ = port_shared.run_population(cfg, n, init13=init, anchors=anchors, nticks=nt, sched=sched, slot_raw=slots,
+    ref, _ = checker_shared.run_population(cfg, n, init13=init, anchors=anchors, nticks=nt, sched=sched, slot_raw=slots,
                                         threads=os.cpu_count() or 1, uwb_comm_period=sc["uwb_comm_period"])
     b = agf.Batch(cfg, n, uwb_comm_period=sc["uwb_comm_period"])
     for i, p in sc["anchors"]:
@@ -435,7 +435,7 @@ def test_monte_carlo_hover_with_noise_matches_reference_population(agf, orc_mod)
         assert ks_e.pvalue > 1e-3 and ks_est.pvalue > 1e-3
 
 
-def test_per_vehicle_parameter_sweep_parity(agf, port_shared):
+def test_per_vehicle_parameter_sweep_parity(agf, checker_shared):
     """BASELINE config 4's parameter sweep (mass, inertia, motor constants per vehicle), FP64 parity."""
     n = 24
     sc = scenario(agf, "rates")
@@ -457,13 +457,13 @@ def test_per_vehicle_parameter_sweep_parity(agf, port_shared):
     b.run(sc["nticks"])
     got = b.record()
     for i in (0, 1, 7, n - 1):
-        ref, _ = run_oracle(port_shared, agf, sc, cfg=cfgs[i])
+        ref, _ = run_oracle(checker_shared, agf, sc, cfg=cfgs[i])
         assert bit_equal(got[i], ref[-1]), i
     assert np.std(got[:, 2]) > 0.05  # the sweep really produced different vehicles
     b.close()
 
 
-def test_full_size_parameter_sweep_with_logging(agf, port_shared):
+def test_full_size_parameter_sweep_with_logging(agf, checker_shared):
     """BASELINE config 4's per-GPU shard at full size (16 M vehicles over 8 GPUs = 2 097 152 per GPU): every vehicle its own
     mass, inertia and motor constants, the trajectory log switched on.  Parity arithmetic: 32 vehicles picked at random are
     bit-identical to the oracle built from their own configuration, the logged records equal the state at the logged
@@ -485,19 +485,19 @@ def test_full_size_parameter_sweep_with_logging(agf, port_shared):
     b.close()
     sc["nticks"] = nt
     for j, i in enumerate(pick):
-        ref, _ = run_oracle(port_shared, agf, sc, cfg=agf.cfg_at(cfgs, int(i)))
+        ref, _ = run_oracle(checker_shared, agf, sc, cfg=agf.cfg_at(cfgs, int(i)))
         assert bit_equal(got[i], ref[-1]), i
         if j == 0:
             assert bit_equal(rec3[0], ref[399, 0:17])
     assert np.all(np.isfinite(got[:, 0:17])) and np.std(got[:, 2]) > 0.02
 
 
-def test_immediate_radio_command_and_external_wrench(agf, port_shared):
+def test_immediate_radio_command_and_external_wrench(agf, checker_shared):
     sc = scenario(agf, "rates")
     cfg = cfg_for(agf, sc)
     raw1 = agf.codec.encode_rates(0, 10.5, (0.1, -0.2, 0.05))
     raw2 = agf.codec.encode_rates(0, 9.0, (0.0, 0.0, 0.0))
-    v = port_shared.vehicle(cfg)
+    v = checker_shared.vehicle(cfg)
     v.set_state(pos=(0, 0, 2.0))
     b = agf.Batch(cfg, 2)
     b.set("position", [[0, 0, 2.0], [0, 0, 2.0]])
@@ -516,11 +516,11 @@ def test_immediate_radio_command_and_external_wrench(agf, port_shared):
     b.close()
 
 
-def test_radio_timeout_panic_and_kill_latch(agf, port_shared):
+def test_radio_timeout_panic_and_kill_latch(agf, checker_shared):
     """1.5 s without a radio command while motors run -> FS_PANIC (QuadcopterLogic.cpp:372-376)."""
     cfg = agf.vehicle_cfg(vehicle_id=1)
     raw = agf.codec.encode_rates(0, 10.0, (0, 0, 0))
-    v = port_shared.vehicle(cfg)
+    v = checker_shared.vehicle(cfg)
     b = agf.Batch(cfg, 4)
     for who in (v, b):
         who.set_radio(raw)
@@ -557,7 +557,7 @@ def test_field_get_set_round_trip(agf):
     b.close()
 
 
-def test_fast_variants_tolerance(agf, port_glibc):
+def test_fast_variants_tolerance(agf, checker_glibc):
     """Fast arithmetic (FMA contraction, CUDA libm) in FP64 and FP32 plant precision against the oracle.
     Stated tolerances: rates mode is open loop in attitude and errors integrate; the onboard logic is float
     in both precisions, so FMA contraction and the CUDA float libm move the 10 s position by ~1e-5 relative
@@ -572,7 +572,7 @@ def test_fast_variants_tolerance(agf, port_glibc):
     out = {}
     for name, tol64, tol32 in (("rates", 1e-4, 1e-4), ("full", 5e-3, 5e-3)):
         sc = scenario(agf, name)
-        ref, _ = run_oracle(port_glibc, agf, sc)
+        ref, _ = run_oracle(checker_glibc, agf, sc)
         for prec, tol in ((agf.abi.PREC_FP64, tol64), (agf.abi.PREC_FP32, tol32)):
             b = make_batch(agf, sc, n=2, precision=prec, math=agf.abi.MATH_FAST)
             b.run(sc["nticks"])
@@ -694,7 +694,7 @@ def test_full_size_population_properties(agf):
     b.close()
 
 
-def test_full_size_waypoint_population_spot_check_against_oracle(agf, port_shared):
+def test_full_size_waypoint_population_spot_check_against_oracle(agf, checker_shared):
     """BASELINE config 3's per-GPU shard at full size and full length (131 072 vehicles, 4-waypoint square, 10 s at 500 Hz) in
     the parity arithmetic, noise-free: 64 vehicles picked at random are bit-identical to the oracle flying the same
     initial states and command schedule ("parity spot-check: 64 random vehicles vs oracle in noise-free replay")."""
@@ -715,7 +715,7 @@ def test_full_size_waypoint_population_spot_check_against_oracle(agf, port_share
     b.close()
     pick = np.sort(np.random.default_rng(11).choice(n, k, replace=False))
     anchors = np.array([[i, *p] for i, p in sc["anchors"]], np.float32)
-    ref, _ = port_shared.run_population(cfg, k, init13=init[pick], anchors=anchors, nticks=nt, sched=sched,
+    ref, _ = checker_shared.run_population(cfg, k, init13=init[pick], anchors=anchors, nticks=nt, sched=sched,
                                         threads=os.cpu_count() or 1, uwb_comm_period=sc["uwb_comm_period"])
     assert bit_equal(got[pick], ref)
     assert np.all(got[:, 35] == 0) and np.all(np.isfinite(got))

@@ -174,6 +174,42 @@ def test_fast_variant_agrees_with_glibc_oracle(agf):
     assert same >= 0.97 * n, same
 
 
+@pytest.mark.parametrize("family", ["easy", "hard"])
+def test_collision_verdicts_against_the_reference_ground_truth(agf, family):
+    """A second, algorithm-independent check of K6 on the GPU scenes: the reference's own ray-traced collision test
+    (DepthImagePlanner::IsCollisionFreeGroundTruth, DepthImagePlanner.cpp:1031-1097, the yardstick of its
+    MeasureConservativeness, :972-1003) run on every candidate that reached the collision test of the THROUGHPUT variant.
+    The pyramid method is conservative: what it calls free must be free for the ray tracer (no unsafe accept, ever), and
+    what it wrongly calls colliding stays at the reference planner's own rate on the same scenes."""
+    import orc_rappids as R
+    fl = "ref-glibc" if R.available("ref-glibc") else "port-glibc"
+    if not R.available(fl):
+        pytest.skip("no planner oracle built")
+    P = R.Planner(fl)
+    n, k = 32, 256
+    pop = agf.scenarios.rappids_population(n, seed=91, **(HARD if family == "hard" else {}))
+    imgs = agf.scenarios.rappids_render(pop["row_bg"], pop["boxes"], 320)
+    cands = agf.scenarios.rappids_candidates(n, k, seed=92)
+    g = run_gpu(agf, pop, cands, agf.abi.MATH_FAST)
+    ocfg = R.default_cfg(max_pyramids=32)
+    tab, tab_ref = np.zeros((2, 2), int), np.zeros((2, 2), int)  # [planner says free][ground truth says free]
+    for i in range(n):
+        e = P.plan(ocfg, imgs[i], pop["vel0"][i], pop["acc0"][i], pop["grav"][i], candidates=cands[i])
+        chk = np.nonzero((g["flags"][i] & 4) | (e["results"] & 4))[0]
+        if len(chk) == 0:
+            continue
+        gt = P.ground_truth(ocfg, imgs[i], pop["vel0"][i], pop["acc0"][i], pop["grav"][i], cands[i][chk])
+        for j, t in zip(chk, gt):
+            if g["flags"][i][j] & 4:
+                tab[int(bool(g["flags"][i][j] & 8)), int(t)] += 1
+            if e["results"][j] & 4:
+                tab_ref[int(bool(e["results"][j] & 8)), int(t)] += 1
+    print("%s (%s): GPU fast [planner free][truth free] = %s, reference planner = %s" % (family, fl, tab.tolist(), tab_ref.tolist()))
+    assert tab.sum() > 100 and tab[1].sum() > 20
+    assert tab[1, 0] == 0 and tab_ref[1, 0] == 0              # never free for the planner and colliding for the ray tracer
+    assert abs(int(tab[0, 1]) - int(tab_ref[0, 1])) <= 2 + 0.05 * tab_ref[0, 1]   # same conservativeness as the reference
+
+
 def test_device_sampler(agf):
     """agf_rappids_sample_candidates: draws lie in the sampling box (RandomTrajectoryGenerator, DepthImagePlanner.hpp:
     334-393: uniform pixel, depth, duration; end point = depth * back-projected pixel), are uniform, and do not

@@ -184,6 +184,33 @@ def test_flags_mean_what_they_say(agf):
     assert n_free >= 6
 
 
+def test_ground_truth_collision_check_port_matches_reference_and_planner_is_conservative(agf):
+    """DepthImagePlanner::IsCollisionFreeGroundTruth (DepthImagePlanner.cpp:1031-1097): the restatement equals the
+    unmodified reference on every candidate that reached the collision test, and the pyramid method never calls a
+    trajectory free that the ray tracer finds colliding (Section IV.A of the RAPPIDS paper, MeasureConservativeness)."""
+    import orc_rappids as R
+    if not R.available("ref-glibc"):
+        pytest.skip("oracle/_ref not built")
+    ref, port = R.Planner("ref-glibc"), R.Planner("port-glibc")
+    n, k = 6, 192
+    for fam, kw in (("easy", {}), ("hard", dict(speed_max=4.5, acc_max=3.0, box_depth=(1.0, 3.0), n_boxes=(2, 4)))):
+        pop = agf.scenarios.rappids_population(n, seed=55, **kw)
+        imgs = agf.scenarios.rappids_render(pop["row_bg"], pop["boxes"], 320)
+        cfg = R.default_cfg(max_pyramids=32)
+        checked = unsafe = 0
+        for i in range(n):
+            e = ref.plan(cfg, imgs[i], pop["vel0"][i], pop["acc0"][i], pop["grav"][i], n=k, seed=900 + i)
+            chk = np.nonzero(e["results"] & 4)[0]
+            if len(chk) == 0:
+                continue
+            args = (cfg, imgs[i], pop["vel0"][i], pop["acc0"][i], pop["grav"][i], e["candidates"][chk])
+            g_ref, g_port = ref.ground_truth(*args), port.ground_truth(*args)
+            assert np.array_equal(g_ref, g_port), (fam, i)
+            checked += len(chk)
+            unsafe += int(np.sum(((e["results"][chk] & 8) != 0) & ~g_ref))
+        assert checked > 20 and unsafe == 0, (fam, checked, unsafe)
+
+
 def test_edge_cases(agf):
     """Empty candidate list, a wall closer than the minimum checking distance, an empty (far) scene, saturated pixels."""
     import orc_rappids as R
