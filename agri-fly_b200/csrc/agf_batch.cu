@@ -1078,6 +1078,7 @@ struct BatchImpl : Batch {
     p.delay = e->prediction_delay;
     p.reject = e->meas_reject_dist;
     p.tc_angvel = e->angvel_time_const;
+    p.inv_tc_angvel = 1.0 / e->angvel_time_const;
     p.meas_pos = e->meas_noise_pos; p.meas_att = e->meas_noise_att;
     p.proc_pos = e->proc_noise_pos; p.proc_att = e->proc_noise_att;
     p.state = d_off_est;

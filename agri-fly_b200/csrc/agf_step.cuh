@@ -1661,6 +1661,52 @@ AGF_DEV V3<double> est_q_to_rotvec(const Q4<double>& q) {  // Rotation.hpp:144-1
   if (angle < 4.84813681e-6) return V3<double>(0, 0, 0);
   return nv * (angle / nn);
 }
+// Fast variants of the estimator's pieces.  The estimator stays in double, but what the reference computes through libm
+// (sin / cos / asin / acos / exp / sqrt of doubles, ~50-150 instructions each on the GPU) is evaluated where the values
+// live: per-step rotation increments and measurement errors are small angles (polynomials in the squared angle, general
+// routine out of line beyond their range), the 6-sigma gates compare squares, the first-order lag of the angular
+// velocity takes a float exponential.  Tolerance: tests/test_parity_gpu.py::test_offboard_estimator_fast_variants.
+template<bool PARITY>
+AGF_DEV Q4<double> est_apply_rotvec(const Q4<double>& a, const V3<double>& rv) {  // a * Rotationd::FromRotationVector(rv)
+  if constexpr (PARITY) return qmul(a, est_rotvec_q<true>(rv));
+  else return q_apply_rotvec<false>(a, rv);
+}
+static AGF_COLD V3<double> est_q_to_rotvec_general(Q4<double> q) { return est_q_to_rotvec<false>(q); }
+AGF_DEV V3<double> est_q_to_rotvec_fast(const Q4<double>& q) {
+  const V3<double> nv = q.w > 0 ? V3<double>(q.x, q.y, q.z) : V3<double>(-q.x, -q.y, -q.z);
+  const double x2 = dot(nv, nv);  // sin^2(angle / 2)
+  if (AGF_UNLIKELY(x2 > 0.01)) return est_q_to_rotvec_general(q);
+  if (x2 < 5.8761074e-12) return V3<double>(0, 0, 0);  // angle < MIN_ANGLE (Rotation.hpp:150)
+  // angle / |nv| = 2 asin(x) / x = 2 (1 + x^2/6 + 3x^4/40 + 15x^6/336 + 105x^8/3456 + 945x^10/42240 + ...), |error| < 2e-14 here
+  double p = ::fma(x2, 0.017352764423076924, 0.022372159090909092);
+  p = ::fma(x2, p, 0.030381944444444444);
+  p = ::fma(x2, p, 0.044642857142857144);
+  p = ::fma(x2, p, 0.075);
+  p = ::fma(x2, p, 0.16666666666666666);
+  p = ::fma(x2, p, 1.0);
+  return nv * (2.0 * p);
+}
+template<bool PARITY>
+AGF_DEV double est_lag_factor(const EstParams& ep, double dtInt) {  // exp(-dt / tau) of the angular-velocity model (:95, :156)
+  if constexpr (PARITY) {
+    return Mf<true>::exp(-dtInt / ep.tc_angvel);
+  } else {
+#if defined(__CUDA_ARCH__)
+    return double(__expf(float(-dtInt * ep.inv_tc_angvel)));
+#else
+    return double(::expf(float(-dtInt * ep.inv_tc_angvel)));
+#endif
+  }
+}
+// A V A^T + Q with A = [[1, dt], [0, 1]] (:171-186), written out (fast variants)
+AGF_DEV void est_propagate_var_fast(double* v, double dtInt, double proc) {
+  const double d2 = dtInt * dtInt;
+  v[0] = ::fma(dtInt, (v[1] + v[2]) + dtInt * v[3], v[0]) + d2 * d2 * proc * 0.25;
+  v[1] = ::fma(dtInt, v[3], v[1]);
+  v[2] = ::fma(dtInt, v[3], v[2]);
+  v[3] = ::fma(d2, proc, v[3]);
+}
+
 // MocapStateEstimator::GetPrediction (MocapStateEstimator.cpp:61-118)
 template<bool PARITY>
 AGF_DEV void mocap_predict(const EstParams& ep, size_t i, uint64_t now_us, double dt, EstCore& o, EstPipe& pipe) {
@@ -1681,8 +1727,8 @@ AGF_DEV void mocap_predict(const EstParams& ep, size_t i, uint64_t now_us, doubl
     if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
     const V3<double> newPos = (o.pos + m.vel * dtInt) + ((cmd.acc * dtInt) * dtInt) / 2.0;  // sic: _vel (:90)
     const V3<double> newVel = o.vel + cmd.acc * dtInt;
-    const Q4<double> newAtt = qmul(o.att, est_rotvec_q<PARITY>(m.w * dtInt));  // sic: _angVel (:92)
-    double discrete = Mf<PARITY>::exp(-dtInt / ep.tc_angvel);
+    const Q4<double> newAtt = est_apply_rotvec<PARITY>(o.att, m.w * dtInt);  // sic: _angVel (:92)
+    double discrete = est_lag_factor<PARITY>(ep, dtInt);
     if (cmd.ballistic) discrete = 1;
     const V3<double> newW = discrete * o.w + (1 - discrete) * cmd.w;
     o.pos = newPos; o.vel = newVel; o.att = newAtt; o.w = newW;
@@ -1762,21 +1808,35 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
       const EstCore c = e;
       e.pos = c.pos + c.vel * dtInt;
       e.vel = c.vel + p.acc * dtInt;
-      e.att = qmul(c.att, est_rotvec_q<PARITY>(c.w * dtInt));
-      double discrete = Mf<PARITY>::exp(-dtInt / ep.tc_angvel);
+      e.att = est_apply_rotvec<PARITY>(c.att, c.w * dtInt);
+      double discrete = est_lag_factor<PARITY>(ep, dtInt);
       if (p.ballistic) discrete = 1;
       e.w = discrete * c.w + (1 - discrete) * p.w;
       est_us += uint64_t(0.5 + dtInt * 1e6);
-      est_propagate_var(vp, dtInt, ep.proc_pos);
-      est_propagate_var(va, dtInt, ep.proc_att);
+      if constexpr (PARITY) {
+        est_propagate_var(vp, dtInt, ep.proc_pos);
+        est_propagate_var(va, dtInt, ep.proc_att);
+      } else {
+        est_propagate_var_fast(vp, dtInt, ep.proc_pos);
+        est_propagate_var_fast(va, dtInt, ep.proc_att);
+      }
     }
   }
   double innovP = vp[0] + ep.meas_pos * ep.meas_pos;
   double innovA = va[0] + ep.meas_att * ep.meas_att;
-  const double distP = norm(measPos - e.pos) / ::sqrt(3 * innovP);
-  const Q4<double> dq = qmul(qinv(measAtt), e.att);
-  const double distA = (Mf<PARITY>::acos(::fabs(dq.w)) * 2.0) / ::sqrt(innovA);  // Rotation::GetAngle
-  const bool reject = (distP > ep.reject) || (distA > ep.reject);
+  bool reject;
+  if constexpr (PARITY) {
+    const double distP = norm(measPos - e.pos) / ::sqrt(3 * innovP);
+    const Q4<double> dq = qmul(qinv(measAtt), e.att);
+    const double distA = (Mf<PARITY>::acos(::fabs(dq.w)) * 2.0) / ::sqrt(innovA);  // Rotation::GetAngle
+    reject = (distP > ep.reject) || (distA > ep.reject);
+  } else {
+    // the same two gates without square roots and acos: |d|^2 > r^2 * 3 S_p ; angle/2 > r sqrt(S_a)/2 <=> |dq.w| < cos(..)
+    const V3<double> d = measPos - e.pos;
+    const double dqw = ::fabs(measAtt.w * e.att.w + measAtt.x * e.att.x + measAtt.y * e.att.y + measAtt.z * e.att.z);
+    const float half = 0.5f * float(ep.reject) * ::sqrtf(float(innovA));
+    reject = (dot(d, d) > (ep.reject * ep.reject) * (3 * innovP)) || (half < 1.5707963f && float(dqw) < ::cosf(half));
+  }
   if (reject && nrejc < 10.0) {
     nrej += 1.0;
     nrejc += 1.0;
@@ -1808,17 +1868,24 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
     const V3<double> errP = measPos - e.pos;
     e.pos = e.pos + gP[0] * errP;
     e.vel = e.vel + gP[1] * errP;
-    const V3<double> errA = est_q_to_rotvec<PARITY>(qmul(qinv(e.att), measAtt));
-    e.att = qmul(e.att, est_rotvec_q<PARITY>(gA[0] * errA));
+    const Q4<double> qerr = qmul(qinv(e.att), measAtt);
+    const V3<double> errA = PARITY ? est_q_to_rotvec<PARITY>(qerr) : est_q_to_rotvec_fast(qerr);
+    e.att = est_apply_rotvec<PARITY>(e.att, gA[0] * errA);
     e.w = e.w + gA[1] * errA;
-    const double Ip[4] = {1.0 - gP[0] * 1.0, 0.0 - gP[0] * 0.0, 0.0 - gP[1] * 1.0, 1.0 - gP[1] * 0.0};
-    const double Ia[4] = {1.0 - gA[0] * 1.0, 0.0 - gA[0] * 0.0, 0.0 - gA[1] * 1.0, 1.0 - gA[1] * 0.0};
-    double np_[4], na_[4];
-    est_mm2(Ip, vp, np_);
-    est_mm2(Ia, va, na_);
-    for (int k = 0; k < 4; k++) {
-      vp[k] = np_[k];
-      va[k] = na_[k];
+    if constexpr (PARITY) {
+      const double Ip[4] = {1.0 - gP[0] * 1.0, 0.0 - gP[0] * 0.0, 0.0 - gP[1] * 1.0, 1.0 - gP[1] * 0.0};
+      const double Ia[4] = {1.0 - gA[0] * 1.0, 0.0 - gA[0] * 0.0, 0.0 - gA[1] * 1.0, 1.0 - gA[1] * 0.0};
+      double np_[4], na_[4];
+      est_mm2(Ip, vp, np_);
+      est_mm2(Ia, va, na_);
+      for (int k = 0; k < 4; k++) {
+        vp[k] = np_[k];
+        va[k] = na_[k];
+      }
+    } else {  // (I - K H) V with H = [1 0], written out
+      const double p0 = vp[0], p1 = vp[1], a0 = va[0], a1 = va[1];
+      vp[0] = (1.0 - gP[0]) * p0; vp[1] = (1.0 - gP[0]) * p1; vp[2] = ::fma(-gP[1], p0, vp[2]); vp[3] = ::fma(-gP[1], p1, vp[3]);
+      va[0] = (1.0 - gA[0]) * a0; va[1] = (1.0 - gA[0]) * a1; va[2] = ::fma(-gA[1], a0, va[2]); va[3] = ::fma(-gA[1], a1, va[3]);
     }
   }
   {  // symmetry (:257-261)

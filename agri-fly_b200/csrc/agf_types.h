@@ -306,7 +306,7 @@ AGF_HDI size_t est_doubles(size_t n) { return ((n + E_LANES - 1) / E_LANES) * (s
 struct EstParams {
   int kind;
   uint64_t t0_us;  // clock reading at construction: origin of the estimator's and its pipe's Timer
-  double delay, reject, tc_angvel, meas_pos, meas_att, proc_pos, proc_att;
+  double delay, reject, tc_angvel, inv_tc_angvel, meas_pos, meas_att, proc_pos, proc_att;
   double* state;   // device, est_doubles(N) values, see est_index
 };
 // Offboard::QuadcopterController + radio link of the in-kernel offboard loop (agrifly_b200.h "offboard rates loop")

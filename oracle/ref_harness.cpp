@@ -781,6 +781,15 @@ void orc_get_imu(orc_vehicle* v, double acc[3], double gyro[3]) {
 
 uint64_t orc_time_us(orc_vehicle* v) { return v->timer.GetMicroSeconds(); }
 
+// The reference's UWB range noise comes from ONE file-scope generator (UWBNetwork.cpp:4, thread_local here: ref_tls_rng.h)
+// that every UWBNetwork constructor re-seeds with 0 (:19).  Left alone, the vehicles of a population stepped on T threads
+// would replay the same T-fold copies of one stream; a Monte-Carlo population needs independent realisations, so the
+// generator is seeded per vehicle right before that vehicle runs (no reference source is touched; vehicle 0 keeps seed 0).
+}  // extern "C"
+extern std::mt19937 rng;  // thread_local through the forced include (the -include of ref_tls_rng.h covers every file of the command)
+extern "C" {
+static void seed_range_noise(uint32_t vehicle) { rng.seed(vehicle); }
+
 double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t n,
                           const orc_opts* opts, const double* init13, const float* anchors,
                           uint32_t n_anchors, uint32_t dt_us, uint32_t nticks,
@@ -812,6 +821,7 @@ double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t
                  slot_raw + (size_t(s) * n + i) * AGF_RADIO_PACKET_SIZE, AGF_RADIO_PACKET_SIZE);
         sr = mine;
       }
+      seed_range_noise(i);
       orc_run(vs[i], dt_us, nticks, sched, nsched, sr, nullptr);
     }
   };
@@ -834,7 +844,7 @@ double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t
   return secs;
 }
 
-#define ORC_POP_SEED(v, i) (v)->quad->_generator.seed((i) + 1)
+#define ORC_POP_SEED(v, i) ((v)->quad->_generator.seed((i) + 1), seed_range_noise(i))
 #include "orc_population_traj.inc"
 
 void orc_radio_encode_rates(uint8_t flags, float thrust, const float w[3], uint8_t raw[23]) {
