@@ -564,15 +564,25 @@ def rappids_extra(agf, pk):
         pl.sync()
         pms, pcnt = pl.plan_kernel_time()
         st = pl.stats()
-        bytes_per_plan = 1.06e6  # algorithmic: bytes of the pixels the reference scans per plan of this workload (profiles/r1/rappids_plan_fast_summary_v0.txt)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc_rappids
+        # algorithmic bytes per plan: the depth pixels (2 B) InflatePyramid reads in the reference's scan order, COUNTED by the
+        # CPU restatement on a sample of this very workload (oracle/port: orc_rappids_pixels_read)
+        nsamp = 256
+        port = orc_rappids.Planner("port-glibc")
+        port.pixels_read()
+        port.plan_many(orc_rappids.default_cfg(), pl.get_images(0, nsamp), pop["vel0"][:nsamp], pop["acc0"][:nsamp], pop["grav"][:nsamp],
+                       pl.get_candidates(0, nsamp), threads=os.cpu_count() or 1, want_results=False)
+        bytes_per_plan = 2.0 * port.pixels_read() / nsamp
         gbs = nr * bytes_per_plan / (pms * 1e-3) / 1e9
         r = dict(plans_per_s=nr / (pms * 1e-3), candidates_per_s=nr * kr / (pms * 1e-3), vehicles=nr, candidates=kr, ms_per_launch=pms,
                  found_fraction=st["found"] / nr,
                  roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=gbs / pk["hbm_gbs"],
-                               note="pixel scans of InflatePyramid: %.2f MB of pixels per plan in the reference algorithm; latency-bound" % (bytes_per_plan / 1e6)))
+                               algorithmic_bytes_per_plan=bytes_per_plan,
+                               note="pixel scans of InflatePyramid: %.3f MB of depth pixels per plan in the reference's scan order, counted "
+                                    "by the CPU restatement on %d plans of this workload; the kernel is latency-bound, not bandwidth-bound"
+                                    % (bytes_per_plan / 1e6, nsamp)))
         # the reference planner on the host cores, same images / states / candidates (bounded sample)
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import orc_rappids
         fl = "ref-glibc" if orc_rappids.available("ref-glibc") else "port-glibc"
         ns = min(nr, 128 * (os.cpu_count() or 1))
         imgs = pl.get_images(0, ns)

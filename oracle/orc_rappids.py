@@ -100,6 +100,11 @@ class Planner:
         L.orc_rappids_primitive.argtypes = [_dp] * 4 + [C.c_double] * 6 + [_dp, C.POINTER(C.c_int32),
                                                                             C.POINTER(C.c_int32)]
 
+    def pixels_read(self):
+        """port only: pixels InflatePyramid read (reference scan order) in all plans since the last call"""
+        self.lib.orc_rappids_pixels_read.restype = C.c_uint64
+        return int(self.lib.orc_rappids_pixels_read())
+
     def ground_truth(self, cfg, image, vel0, acc0, grav, candidates):
         """DepthImagePlanner::IsCollisionFreeGroundTruth for each candidate [n][4] -> bool[n]."""
         L = self.lib

@@ -24,6 +24,7 @@
 
 #include <limits>
 #include <thread>
+#include <atomic>
 #include <vector>
 
 #include "../rappids_api.h"
@@ -543,7 +544,19 @@ struct Shrink {
   int right, left, top, bottom;  // the four "shrunk" edges
 };
 
+// every depth-image read of InflatePyramid goes through PX, which counts it: the algorithmic pixel traffic of a plan
+// (orc_rappids_pixels_read, the numerator of K6's roofline in bench.py)
+static std::atomic<uint64_t> g_pixels_read{0};
+static thread_local uint64_t t_pixels_read = 0;
+struct CountedImage {
+  const uint16_t* p;
+  uint16_t operator[](int i) const {
+    t_pixels_read++;
+    return p[i];
+  }
+};
 bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
+  const CountedImage PX{img};
   const double f = cfg->focal_length, rTrue = cfg->true_radius, rPlan = cfg->planning_radius;
   const double scale = cfg->depth_scale;
   int edgeOff = f * rTrue / cfg->min_checking_dist;
@@ -574,7 +587,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
   uint16_t ignore = uint16_t(rTrue / scale);
   for (int y = top; y < bottom; y++)
     for (int x = left; x < right; x++) {
-      uint16_t p = img[y * W + x];
+      uint16_t p = PX[y * W + x];
       if (p <= minPyrDepth && p > ignore) return false;
     }
 
@@ -585,7 +598,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     if (rf) {
       if (right < W - edgeOff - 1) {
         for (int y = top; y <= bottom; y++) {
-          uint16_t p = img[y * W + right + 1];
+          uint16_t p = PX[y * W + right + 1];
           if (p > ignore) {
             if (p < minPyrDepth) {
               rf = false;
@@ -603,7 +616,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     if (tf) {
       if (top > edgeOff) {
         for (int x = left; x <= right; x++) {
-          uint16_t p = img[(top - 1) * W + x];
+          uint16_t p = PX[(top - 1) * W + x];
           if (p > ignore) {
             if (p < minPyrDepth) {
               tf = false;
@@ -621,7 +634,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     if (lf) {
       if (left > edgeOff) {
         for (int y = top; y <= bottom; y++) {
-          uint16_t p = img[y * W + left - 1];
+          uint16_t p = PX[y * W + left - 1];
           if (p > ignore) {
             if (p < minPyrDepth) {
               lf = false;
@@ -639,7 +652,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     if (bf) {
       if (bottom < H - edgeOff - 1) {
         for (int x = left; x <= right; x++) {
-          uint16_t p = img[(bottom + 1) * W + x];
+          uint16_t p = PX[(bottom + 1) * W + x];
           if (p > ignore) {
             if (p < minPyrDepth) {
               bf = false;
@@ -663,7 +676,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
   // --- right band: columns right..W-1 (outer), rows top..bottom (inner)
   for (int x = right; x < W; x++)
     for (int y = top; y <= bottom; y++) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && num > (x - rS) * p) {
         int rT = x - int(num / p);
         if (x0 > rT - kBuf) {
@@ -688,7 +701,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
   // --- left band: columns left..0 (outer, descending), rows top..bottom
   for (int x = left; x >= 0; x--)
     for (int y = top; y <= bottom; y++) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && (lS - x) * p < num) {
         int lT = x + int(num / p);
         if (x0 < lT + kBuf) {
@@ -714,7 +727,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
   // --- top band: rows top..0 (outer, descending), columns left..right
   for (int y = top; y >= 0; y--)
     for (int x = left; x <= right; x++) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && (tS - y) * p < num) {
         int tT = y + int(num / p);
         if (y0 < tT + kBuf) {
@@ -739,7 +752,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
   // --- bottom band: rows bottom..H-1, columns left..right
   for (int y = bottom; y < H; y++)
     for (int x = left; x <= right; x++) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && num > (y - bS) * p) {
         int bT = y - int(num / p);
         if (y0 > bT - kBuf) {
@@ -765,7 +778,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
   // --- corners: top right, bottom right, top left, bottom left
   for (int y = top; y >= 0; y--)
     for (int x = right; x < W; x++) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && num > (x - rS) * p && (tS - y) * p < num) {
         int rT = x - int(num / p), tT = y + int(num / p);
         if (x0 > rT - kBuf && y0 < tT + kBuf) return false;
@@ -784,7 +797,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     }
   for (int y = bottom; y < H; y++)
     for (int x = right; x < W; x++) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && num > (x - rS) * p && num > (y - bS) * p) {
         int rT = x - int(num / p), bT = y - int(num / p);
         if (x0 > rT - kBuf && y0 > bT - kBuf) return false;
@@ -803,7 +816,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     }
   for (int y = top; y >= 0; y--)
     for (int x = left; x >= 0; x--) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && (lS - x) * p < num && (tS - y) * p < num) {
         int lT = x + int(num / p), tT = y + int(num / p);
         if (x0 < lT + kBuf && y0 < tT + kBuf) return false;
@@ -822,7 +835,7 @@ bool Planner::inflate(int x0, int y0, double minimumDepth, Pyr& out) const {
     }
   for (int y = bottom; y < H; y++)
     for (int x = left; x >= 0; x--) {
-      int p = img[y * W + x];
+      int p = PX[y * W + x];
       if (p > ignore && p < maxDepth && (lS - x) * p < num && num > (y - bS) * p) {
         int lT = x + int(num / p), bT = y - int(num / p);
         if (x0 < lT + kBuf && y0 > bT - kBuf) return false;
@@ -997,6 +1010,8 @@ int plan_one(const orc_rappids_cfg* cfg, const uint16_t* image, const double* ve
   }
   out->found = found ? 1 : 0;
   if (!found) out->best_cost = std::numeric_limits<double>::max();
+  g_pixels_read += t_pixels_read;
+  t_pixels_read = 0;
   out->n_generated = pl.nGenerated;
   out->n_cost_checks = pl.nCost;
   out->n_collision_checks = pl.nColl;
@@ -1103,6 +1118,9 @@ int orc_rappids_ground_truth(const orc_rappids_cfg* cfg, const uint16_t* image, 
   }
   return 0;
 }
+
+// pixels read by InflatePyramid in all plans since the last call (port only)
+uint64_t orc_rappids_pixels_read(void) { return g_pixels_read.exchange(0); }
 
 int orc_rappids_solve_cubic(double a, double b, double c, double roots[3]) { return (int)cubic(a, b, c, roots); }
 int orc_rappids_solve_quartic(double a, double b, double c, double d, double roots[4]) {

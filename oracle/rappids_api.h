@@ -81,6 +81,9 @@ int orc_rappids_ground_truth(const orc_rappids_cfg* cfg, const uint16_t* image, 
                              const double acc0[3], const double grav[3], int32_t n_candidates,
                              const double* candidates, uint8_t* free_out);
 
+/* PORT ONLY: depth-image pixels read by InflatePyramid (in the reference's scan order) over all plans since the last call */
+uint64_t orc_rappids_pixels_read(void);
+
 /* pieces, for unit pins */
 int orc_rappids_solve_cubic(double a, double b, double c, double roots[3]);
 int orc_rappids_solve_quartic(double a, double b, double c, double d, double roots[4]);
