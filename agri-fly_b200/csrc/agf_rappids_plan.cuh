@@ -533,24 +533,51 @@ static __device__ __noinline__ bool shrink_region(const int REGION, const PlanPa
   const uint16_t* plane = colWalk ? w.imgT : w.img;
   const uint16_t* gplane = colWalk ? w.gminC : w.gminR;
   const int g0 = lo >> 5, g1 = hi >> 5;
-  for (int oc = 0; oc < nOuter; oc++) {
-    const int o = o0 + dO * oc;
-    const uint16_t* gl = gplane + (size_t)o * G;
-    for (int gb = 0; gb <= g1 - g0; gb += 32) {  // 32 groups (1024 pixels) per step, in scan order
-      const int k = gb + w.lane;
-      const int g = dI > 0 ? g0 + k : g1 - k;
-      const bool in = k <= g1 - g0;
-      const unsigned gm = in ? ld16(gl + g) : 65535u;
-      unsigned need = __ballot_sync(AGFR_FULL, in && (int)gm < maxDepth &&
-                                                   group_may_trigger(REGION, s, P.num, o, max(lo, g << 5), min(hi, (g << 5) + 31), (int)gm));
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int gs = dI > 0 ? g0 + gb + src : g1 - gb - src;
-        const int a = max(lo, gs << 5), b = min(hi, (gs << 5) + 31);
-        if (!shrink_span(REGION, P, w, s, maxDepth, x0, y0, o, plane + (size_t)o * pitch, dI > 0 ? a : b, dI, b - a + 1))
-          return false;
+  // Several lines per step: a line's range touches ng <= 10 groups, so the 32 lanes take 32 / ng consecutive lines at once,
+  // lane = line-in-step * ng + group-in-scan-order -- ascending lanes are the reference's scan order (line by line, then
+  // along the line).  One load of group minima and one ballot then cover up to 32 lines (corner regions: 1-2 groups per
+  // line) instead of one.  Groups flagged by the ballot are replayed pixel by pixel in lane order with the CURRENT bounds;
+  // a flag computed with bounds that an earlier replay of the same step has since moved inwards is merely conservative
+  // (group_may_trigger: inward bounds only rule more pixels out), so the result stays the sequential one.
+  const int ng = g1 - g0 + 1;
+  if (ng > 32) {  // images wider than 1024 pixels: one line per step, 32 groups at a time
+    for (int oc = 0; oc < nOuter; oc++) {
+      const int o = o0 + dO * oc;
+      const uint16_t* gl = gplane + (size_t)o * G;
+      for (int gb = 0; gb < ng; gb += 32) {
+        const int k = gb + w.lane;
+        const int g = dI > 0 ? g0 + k : g1 - k;
+        const bool in = k < ng;
+        const unsigned gm = in ? ld16(gl + g) : 65535u;
+        unsigned need = __ballot_sync(AGFR_FULL, in && (int)gm < maxDepth &&
+                                                     group_may_trigger(REGION, s, P.num, o, max(lo, g << 5), min(hi, (g << 5) + 31), (int)gm));
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int gs = dI > 0 ? g0 + gb + src : g1 - gb - src;
+          const int a = max(lo, gs << 5), b = min(hi, (gs << 5) + 31);
+          if (!shrink_span(REGION, P, w, s, maxDepth, x0, y0, o, plane + (size_t)o * pitch, dI > 0 ? a : b, dI, b - a + 1))
+            return false;
+        }
       }
+    }
+    return true;
+  }
+  const int lps = 32 / ng;                      // lines per step (320-pixel rows: ng <= 10, at least 3)
+  const int ll = w.lane / ng, k = w.lane - ll * ng;
+  const int g = dI > 0 ? g0 + k : g1 - k;
+  const int ga = max(lo, g << 5), gb_ = min(hi, (g << 5) + 31);
+  for (int oc = 0; oc < nOuter; oc += lps) {
+    const bool in = ll < lps && oc + ll < nOuter;
+    const int o = o0 + dO * (oc + ll);
+    const unsigned gm = in ? ld16(gplane + (size_t)o * G + g) : 65535u;
+    unsigned need = __ballot_sync(AGFR_FULL, in && (int)gm < maxDepth && group_may_trigger(REGION, s, P.num, o, ga, gb_, (int)gm));
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const int os = __shfl_sync(AGFR_FULL, o, src), a = __shfl_sync(AGFR_FULL, ga, src), b = __shfl_sync(AGFR_FULL, gb_, src);
+      if (!shrink_span(REGION, P, w, s, maxDepth, x0, y0, os, plane + (size_t)os * pitch, dI > 0 ? a : b, dI, b - a + 1))
+        return false;
     }
   }
   return true;
