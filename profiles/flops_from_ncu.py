@@ -23,7 +23,10 @@ for path in sys.argv[1:]:
         vals[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
     g = lambda op: vals.get("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % op, 0.0)
     steps = float(n * ticks)
-    out[key] = {"fp32": round((g("fadd") + g("fmul") + 2 * g("ffma")) / steps, 1),
+    # packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2): one thread-instruction carries two lanes
+    packed = 2 * g("fadd2") + 2 * g("fmul2") + 4 * g("ffma2")
+    out[key] = {"fp32": round((g("fadd") + g("fmul") + 2 * g("ffma") + packed) / steps, 1),
+                "fp32_packed": round(packed / steps, 1),
                 "fp64": round((g("dadd") + g("dmul") + 2 * g("dfma")) / steps, 1),
                 "warp_inst_per_vehicle_tick": round(vals.get("smsp__inst_executed.sum", 0.0) * 32 / steps, 1) if "smsp__inst_executed.sum" in vals else None,
                 "source": "profiles/r2/" + name}
