@@ -176,6 +176,18 @@ __global__ void state13_get_kernel(FieldCtx<P> c, size_t first, size_t count, do
   out[t] = double(c.sp[sidx(slot, c.n, i, VP)]);
 }
 
+// SetExternalForce / SetExternalTorque of a vehicle range: in = [count][3] doubles (either may be null), dst = [3][n]
+template<typename P>
+__global__ void wrench_set_kernel(P* __restrict__ dst_f, P* __restrict__ dst_t, size_t n, size_t first, size_t count,
+                                  const double* __restrict__ in_f, const double* __restrict__ in_t) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count * 3) return;
+  const size_t i = first + t / 3;
+  const int k = int(t % 3);
+  if (in_f) dst_f[size_t(k) * n + i] = P(in_f[t]);
+  if (in_t) dst_t[size_t(k) * n + i] = P(in_t[t]);
+}
+
 // SetCommandRadioMsg now (QuadcopterLogic.hpp:110-116), outside the step kernel
 struct RadioNow {
   uint32_t type, flags;
@@ -1364,17 +1376,19 @@ struct BatchImpl : Batch {
       AGF_CUDA(cudaMemsetAsync(d_ext_force, 0, sizeof(P) * 3 * n, stream));
       AGF_CUDA(cudaMemsetAsync(d_ext_torque, 0, sizeof(P) * 3 * n, stream));
     }
-    std::vector<P> h(count);
-    for (int pass = 0; pass < 2; pass++) {
-      const double* src = pass ? t : f;
-      P* dst = pass ? d_ext_torque : d_ext_force;
-      if (!src) continue;
-      for (int k = 0; k < 3; k++) {
-        for (size_t i = 0; i < count; i++) h[i] = P(src[3 * i + k]);
-        AGF_CUDA(cudaMemcpyAsync(dst + size_t(k) * n + first, h.data(), count * sizeof(P), cudaMemcpyHostToDevice, stream));
-        AGF_CUDA(cudaStreamSynchronize(stream));
-      }
-    }
+    if (!count || (!f && !t)) return AGF_OK;
+    // one staged copy per array and one kernel (the reference's setters are per vehicle; a range costs one round trip)
+    const size_t bytes = count * 3 * sizeof(double);
+    if (int rc = ensure_stage(2 * bytes)) return rc;
+    double* sf_ = (double*)d_stage;
+    double* st_ = sf_ + count * 3;
+    if (f) AGF_CUDA(cudaMemcpyAsync(sf_, f, bytes, cudaMemcpyHostToDevice, stream));
+    if (t) AGF_CUDA(cudaMemcpyAsync(st_, t, bytes, cudaMemcpyHostToDevice, stream));
+    wrench_set_kernel<P><<<unsigned((count * 3 + 255) / 256), 256, 0, stream>>>(d_ext_force, d_ext_torque, n, first, count,
+                                                                                f ? sf_ : nullptr, t ? st_ : nullptr);
+    AGF_CUDA(cudaGetLastError());
+    launches++;
+    AGF_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its buffers
     return AGF_OK;
   }
 

@@ -743,6 +743,45 @@ def test_trajectory_log_ring(agf):
     b.close()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+def test_trajectory_log_ragged_population_uneven_launches_and_state_round_trip(agf, prec):
+    """The log's running ring pointer and vector records at their edges: a vehicle count that is not a multiple of the
+    32-vehicle line (nor of the 128-vehicle block), launches whose lengths are unrelated to the stride and wrap the ring in
+    the middle of a launch, both plant precisions (float4 x 4 / double2 x 8 records); every record still in the ring equals
+    the state recorded at that tick.  And agf_batch_get_state == the four getters, set_state(get_state()) changes nothing."""
+    n = 333
+    P = agf.abi.PREC_FP32 if prec == "fp32" else agf.abi.PREC_FP64
+    b = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, precision=P, math=agf.abi.MATH_FAST)
+    b.set_radio(agf.codec.encode_rates(0, 10.5, (0.2, -0.1, 0.3)))
+    b.run(4)
+    b.enable_log(3, 5)   # every 3rd tick, ring of 5 records
+    want = {}
+    ref = agf.Batch(agf.vehicle_cfg(vehicle_id=1), n, precision=P, math=agf.abi.MATH_FAST)   # the same flight, tick by tick
+    ref.set_radio(agf.codec.encode_rates(0, 10.5, (0.2, -0.1, 0.3)))
+    ref.run(4)
+    for chunk in (1, 7, 2, 13, 29, 3, 1, 1, 40):
+        b.run(chunk)
+        for _ in range(chunk):
+            ref.run(1)
+            if ref.ticks % 3 == 0:
+                want[ref.ticks // 3 - 4 // 3 - 1] = ref.record()[:, 0:17]
+    assert b.log_count == (4 + 97) // 3 - 4 // 3 and b.log_count - 1 in want
+    for rec in range(b.log_count - 5, b.log_count):
+        assert np.array_equal(b.read_log(rec), want[rec]), rec
+        assert np.array_equal(b.read_log(rec, first=301, count=32), want[rec][301:333]), rec
+    s13 = b.get_state13()
+    assert np.array_equal(s13[:, 0:3], b.get("position")) and np.array_equal(s13[:, 3:6], b.get("velocity"))
+    assert np.array_equal(s13[:, 6:10], b.get("attitude")) and np.array_equal(s13[:, 10:13], b.get("angular_velocity"))
+    assert np.array_equal(b.get_state13(first=100, count=17), s13[100:117])
+    if prec == "fp64":   # FP32 mode restarts its compensated sums at a set_state; the FP64 plant has nothing to restart
+        b.set_state13(s13)
+        b.run(25)
+        ref.run(25)
+        assert np.array_equal(b.record()[:, 0:17], ref.record()[:, 0:17])
+    b.close()
+    ref.close()
+
+
 def _collect_ranges(agf, b, nticks):
     """steps one tick at a time and returns, per vehicle, every NEW range its radio received: (tick, range, anchor index)"""
     prev = b.get("uwb_measurement")

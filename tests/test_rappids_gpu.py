@@ -152,6 +152,46 @@ def test_edge_cases(agf):
             pl.set_candidates(cands)
 
 
+@pytest.mark.parametrize("size", [(640, 480), (1088, 400), (96, 64)])
+def test_other_image_sizes(agf, size):
+    """Images that are not 320 x 240: twice the size (20 / 15 groups of 32 pixels per line), wider than 1 024 pixels (more
+    than 32 groups per row: the one-line-per-step form of the shrink scans), and smaller than three groups.  Synthetic scenes:
+    a background whose depth varies by row and by column, boxes in front of it; parity variant against the oracle, bit for bit."""
+    R, P = oracle("port-shared")
+    W, H = size
+    n, k = 6, 160
+    rng = np.random.default_rng(W + H)
+    scale = 10.0 / 256.0
+    imgs = np.zeros((n, H, W), dtype=np.uint16)
+    for i in range(n):
+        bg = (rng.uniform(3.0, 6.0) - 1.5 * np.linspace(0, 1, H)[:, None] + 0.5 * np.linspace(0, 1, W)[None, :]) / scale
+        im = bg.copy()
+        for _ in range(rng.integers(1, 4)):
+            x0, y0 = rng.integers(0, W - 8), rng.integers(0, H - 8)
+            w_, h_ = rng.integers(4, max(5, W // 4)), rng.integers(4, max(5, H // 3))
+            im[y0:y0 + h_, x0:x0 + w_] = rng.uniform(0.8, 2.5) / scale
+        imgs[i] = np.clip(im, 0, 65535).astype(np.uint16)
+    v = np.column_stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n), rng.uniform(0.0, 1.5, n)])
+    a = rng.uniform(-0.5, 0.5, (n, 3))
+    g = np.tile([0.0, 9.81, 0.0], (n, 1))
+    cands = agf.scenarios.rappids_candidates(n, k, seed=11, width=W, height=H)
+    cfg = agf.rappids_cfg(width=W, height=H, math=agf.abi.MATH_PARITY)
+    with agf.Rappids(cfg, n, k) as pl:
+        pl.set_images(imgs)
+        pl.set_states(v, a, g)
+        pl.set_candidates(cands)
+        pl.plan()
+        pl.sync()
+        res, flags, pyr = pl.results(), pl.candidate_flags(), pl.pyramids()
+    ocfg = R.default_cfg(width=W, height=H, max_pyramids=32)
+    npyr = 0
+    for i in range(n):
+        e = P.plan(ocfg, imgs[i], v[i], a[i], g[i], candidates=cands[i])
+        assert_vehicle_equal(i, res, flags, pyr, e)
+        npyr += e["n_pyramids"]
+    assert npyr > 0 or min(size) < 100
+
+
 def test_fast_variant_agrees_with_glibc_oracle(agf):
     """Throughput variant (FMA contraction, CUDA libm) against the pure-reference arithmetic.  Stated tolerance:
     at least 97 % of the vehicles get exactly the same flags for all candidates and the same returned candidate;
