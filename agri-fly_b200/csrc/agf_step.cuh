@@ -1572,7 +1572,7 @@ AGF_DEV V3<double> rtg_omega(const double* tr, double t, double timeStep) {
 
 // ---------------------------------------------------------------------------------------------
 // Offboard::MocapStateEstimator + PredictionPipe per vehicle (agrifly_b200.h "offboard loop: state estimator";
-// Components/Offboard/MocapStateEstimator.cpp, PredictionPipe.hpp).  State [field][N] doubles in HBM, touched on
+// Components/Offboard/MocapStateEstimator.cpp, PredictionPipe.hpp).  State blocked by warp in HBM (agf_types.h est_index), touched on
 // mocap packets (every 2-3 ticks) and at command generation only; everything here is double as in the reference.
 // ---------------------------------------------------------------------------------------------
 // The per-vehicle arrays of the offboard loop are read through L2 (ld.global.cg), like the vehicle state: with the
@@ -2669,7 +2669,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
 
 // ---------------------------------------------------------------------------------------------
 // K1/K2/K3: the step kernel.  One vehicle per thread; many ticks per launch with the state in
-// registers; optional trajectory log [record][field][vehicle] (every store a coalesced line).
+// registers; optional trajectory log (a ring of records of 16-byte vectors [quad][vehicle], StepLaunch::log).
 //
 // Balanced schedule.  Every vehicle-tick costs the same, so a launch is nblocks x nticks equal units of
 // work ("block-ticks").  A plain grid of nblocks CTAs runs them in ceil(nblocks / resident CTAs) waves and
@@ -2731,7 +2731,7 @@ AGF_DEV void plant_params_load(PlantPVDiag<P>& pv, const StepLaunch<P>& L, size_
 #endif
 template<typename P, bool PARITY, bool UWB, bool OFFB = false>
 constexpr int step_min_blocks() {
-  return PARITY ? 1
+  return PARITY ? (UWB ? 1 : 3)  // parity full mode wants its 255 registers (3.7e9 vs 2.8e9 at 168); parity rates 168 (7.2e9 vs 6.5e9)
                 : (sizeof(P) == 4 ? (UWB ? AGF_MINB_F32_UWB : AGF_MINB_F32_RATES) : (UWB ? AGF_MINB_F64_UWB : AGF_MINB_F64_RATES)) -
                       (OFFB ? AGF_OFFB_MINB_DELTA : 0);
 }
