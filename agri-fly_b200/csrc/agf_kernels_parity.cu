@@ -41,7 +41,7 @@ __global__ void offboard_mocap_kernel(StateArrays<P> st, size_t n, EstParams ep,
   P r[12];
 #pragma unroll
   for (int q = 0; q < 12 / VP; q++) VecOf<P>::unpack(st.sp[size_t(q) * n + i], &r[q * VP]);
-  mocap_update<true>(ep, i, now_us, V3<double>(double(r[SP_POS]), double(r[SP_POS + 1]), double(r[SP_POS + 2])),
+  mocap_update<true, double>(ep, i, now_us, V3<double>(double(r[SP_POS]), double(r[SP_POS + 1]), double(r[SP_POS + 2])),
                      Q4<double>(double(r[SP_ATT]), double(r[SP_ATT + 1]), double(r[SP_ATT + 2]), double(r[SP_ATT + 3])));
 }
 cudaError_t launch_offboard_mocap(const StateArrays<double>& st, size_t n, const EstParams& ep, uint64_t now_us, cudaStream_t stream) {
@@ -72,7 +72,7 @@ __global__ void offboard_estimate_kernel(EstParams ep, size_t n, size_t first, s
   if (k >= count) return;
   EstCore e;
   EstPipe pipe;
-  mocap_predict<true>(ep, first + k, now_us, horizon, e, pipe);
+  mocap_predict<true, double>(ep, first + k, now_us, horizon, e, pipe);
   const double v[13] = {e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z, e.att.w, e.att.x, e.att.y, e.att.z, e.w.x, e.w.y, e.w.z};
   for (int f = 0; f < 13; f++) out[size_t(f) * count + k] = v[f];
 }

@@ -32,6 +32,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
@@ -1578,24 +1579,32 @@ AGF_DEV V3<double> rtg_omega(const double* tr, double t, double timeStep) {
 // The per-vehicle arrays of the offboard loop are read through L2 (ld.global.cg), like the vehicle state: with the
 // balanced schedule another CTA may have written them earlier in the same launch, and L1 is not coherent.
 AGF_DEV double ldg2(const double* p) { return ldcg_(p); }
-struct EstCore {
-  V3<double> pos, vel, w;
-  Q4<double> att;
+// E: the type the estimator COMPUTES in.  double = the reference's (parity variants, and the fast variants with an FP64
+// plant); float in the FP32 fast variants ("FP32 mode": the plant it estimates is float as well) -- the state is stored in
+// double either way, and every time (estimate time, activation times, integration steps) stays double.
+template<typename E>
+struct EstCoreT {
+  V3<E> pos, vel, w;
+  Q4<E> att;
 };
-AGF_DEV void est_load(const double* st, size_t n, EstCore& e) {
-  e.pos = V3<double>(ldg2(st + (E_POS + 0) * n), ldg2(st + (E_POS + 1) * n), ldg2(st + (E_POS + 2) * n));
-  e.vel = V3<double>(ldg2(st + (E_VEL + 0) * n), ldg2(st + (E_VEL + 1) * n), ldg2(st + (E_VEL + 2) * n));
-  e.w = V3<double>(ldg2(st + (E_W + 0) * n), ldg2(st + (E_W + 1) * n), ldg2(st + (E_W + 2) * n));
-  e.att = Q4<double>(ldg2(st + (E_ATT + 0) * n), ldg2(st + (E_ATT + 1) * n), ldg2(st + (E_ATT + 2) * n), ldg2(st + (E_ATT + 3) * n));
+typedef EstCoreT<double> EstCore;
+template<typename E>
+AGF_DEV void est_load(const double* st, size_t n, EstCoreT<E>& e) {
+  e.pos = V3<E>(E(ldg2(st + (E_POS + 0) * n)), E(ldg2(st + (E_POS + 1) * n)), E(ldg2(st + (E_POS + 2) * n)));
+  e.vel = V3<E>(E(ldg2(st + (E_VEL + 0) * n)), E(ldg2(st + (E_VEL + 1) * n)), E(ldg2(st + (E_VEL + 2) * n)));
+  e.w = V3<E>(E(ldg2(st + (E_W + 0) * n)), E(ldg2(st + (E_W + 1) * n)), E(ldg2(st + (E_W + 2) * n)));
+  e.att = Q4<E>(E(ldg2(st + (E_ATT + 0) * n)), E(ldg2(st + (E_ATT + 1) * n)), E(ldg2(st + (E_ATT + 2) * n)), E(ldg2(st + (E_ATT + 3) * n)));
 }
-AGF_DEV void est_store(double* st, size_t n, const EstCore& e) {
+template<typename E>
+AGF_DEV void est_store(double* st, size_t n, const EstCoreT<E>& e) {
   st[(E_POS + 0) * n] = e.pos.x; st[(E_POS + 1) * n] = e.pos.y; st[(E_POS + 2) * n] = e.pos.z;
   st[(E_VEL + 0) * n] = e.vel.x; st[(E_VEL + 1) * n] = e.vel.y; st[(E_VEL + 2) * n] = e.vel.z;
   st[(E_W + 0) * n] = e.w.x; st[(E_W + 1) * n] = e.w.y; st[(E_W + 2) * n] = e.w.z;
   st[(E_ATT + 0) * n] = e.att.w; st[(E_ATT + 1) * n] = e.att.x; st[(E_ATT + 2) * n] = e.att.y; st[(E_ATT + 3) * n] = e.att.z;
 }
-struct EstMsg {
-  V3<double> acc, w;
+template<typename E>
+struct EstMsgT {
+  V3<E> acc, w;
   bool ballistic;
 };
 // The activation times of all message slots, fetched in one go: the scans below then run on registers instead of a
@@ -1617,7 +1626,8 @@ AGF_DEV int est_pipe_count(const EstPipe& p) {
 // walks from the newest message to the first one whose activation time has passed; activation times increase with the
 // order of arrival, so that message is the active one with the largest time, and the `tLast` it has when it stops is
 // the smallest time among the not-yet-active ones (agf_types.h: the slots are an unordered set).
-AGF_DEV void est_fetch(const double* st, size_t n, const EstPipe& pipe, double t, EstMsg& m, double& timeRemaining) {
+template<typename E>
+AGF_DEV void est_fetch(const double* st, size_t n, const EstPipe& pipe, double t, EstMsgT<E>& m, double& timeRemaining) {
   double tLast = 1e10;
   int hit = -1;
   double taHit = -1e300;
@@ -1637,14 +1647,14 @@ AGF_DEV void est_fetch(const double* st, size_t n, const EstPipe& pipe, double t
   }
   if (hit >= 0) {
     const double* q = st + size_t(E_PIPE + E_MSG * hit) * n;
-    m.acc = V3<double>(ldg2(q + 1 * n), ldg2(q + 2 * n), ldg2(q + 3 * n));
-    m.w = V3<double>(ldg2(q + 4 * n), ldg2(q + 5 * n), ldg2(q + 6 * n));
+    m.acc = V3<E>(E(ldg2(q + 1 * n)), E(ldg2(q + 2 * n)), E(ldg2(q + 3 * n)));
+    m.w = V3<E>(E(ldg2(q + 4 * n)), E(ldg2(q + 5 * n)), E(ldg2(q + 6 * n)));
     m.ballistic = ldg2(q + 7 * n) != 0.0;
     timeRemaining = tLast - taHit;
     return;
   }
-  m.acc = V3<double>(0, 0, 0);
-  m.w = V3<double>(0, 0, 0);
+  m.acc = V3<E>(0, 0, 0);
+  m.w = V3<E>(0, 0, 0);
   m.ballistic = true;
   timeRemaining = 1e10;
 }
@@ -1666,76 +1676,83 @@ AGF_DEV V3<double> est_q_to_rotvec(const Q4<double>& q) {  // Rotation.hpp:144-1
 // live: per-step rotation increments and measurement errors are small angles (polynomials in the squared angle, general
 // routine out of line beyond their range), the 6-sigma gates compare squares, the first-order lag of the angular
 // velocity takes a float exponential.  Tolerance: tests/test_parity_gpu.py::test_offboard_estimator_fast_variants.
-template<bool PARITY>
-AGF_DEV Q4<double> est_apply_rotvec(const Q4<double>& a, const V3<double>& rv) {  // a * Rotationd::FromRotationVector(rv)
+template<bool PARITY, typename E>
+AGF_DEV Q4<E> est_apply_rotvec(const Q4<E>& a, const V3<E>& rv) {  // a * Rotationd::FromRotationVector(rv)
   if constexpr (PARITY) return qmul(a, est_rotvec_q<true>(rv));
   else return q_apply_rotvec<false>(a, rv);
 }
 static AGF_COLD V3<double> est_q_to_rotvec_general(Q4<double> q) { return est_q_to_rotvec<false>(q); }
-AGF_DEV V3<double> est_q_to_rotvec_fast(const Q4<double>& q) {
-  const V3<double> nv = q.w > 0 ? V3<double>(q.x, q.y, q.z) : V3<double>(-q.x, -q.y, -q.z);
-  const double x2 = dot(nv, nv);  // sin^2(angle / 2)
-  if (AGF_UNLIKELY(x2 > 0.01)) return est_q_to_rotvec_general(q);
-  if (x2 < 5.8761074e-12) return V3<double>(0, 0, 0);  // angle < MIN_ANGLE (Rotation.hpp:150)
+template<typename E>
+AGF_DEV V3<E> est_q_to_rotvec_fast(const Q4<E>& q) {
+  const V3<E> nv = q.w > 0 ? V3<E>(q.x, q.y, q.z) : V3<E>(-q.x, -q.y, -q.z);
+  const E x2 = dot(nv, nv);  // sin^2(angle / 2)
+  if (AGF_UNLIKELY(x2 > E(0.01))) {
+    const V3<double> r = est_q_to_rotvec_general(Q4<double>(double(q.w), double(q.x), double(q.y), double(q.z)));
+    return V3<E>(E(r.x), E(r.y), E(r.z));
+  }
+  if (x2 < E(5.8761074e-12)) return V3<E>(0, 0, 0);  // angle < MIN_ANGLE (Rotation.hpp:150)
   // angle / |nv| = 2 asin(x) / x = 2 (1 + x^2/6 + 3x^4/40 + 15x^6/336 + 105x^8/3456 + 945x^10/42240 + ...), |error| < 2e-14 here
-  double p = ::fma(x2, 0.017352764423076924, 0.022372159090909092);
-  p = ::fma(x2, p, 0.030381944444444444);
-  p = ::fma(x2, p, 0.044642857142857144);
-  p = ::fma(x2, p, 0.075);
-  p = ::fma(x2, p, 0.16666666666666666);
-  p = ::fma(x2, p, 1.0);
-  return nv * (2.0 * p);
+  E p = x2 * E(0.017352764423076924) + E(0.022372159090909092);
+  p = x2 * p + E(0.030381944444444444);
+  p = x2 * p + E(0.044642857142857144);
+  p = x2 * p + E(0.075);
+  p = x2 * p + E(0.16666666666666666);
+  p = x2 * p + E(1.0);
+  return nv * (E(2.0) * p);
 }
-template<bool PARITY>
-AGF_DEV double est_lag_factor(const EstParams& ep, double dtInt) {  // exp(-dt / tau) of the angular-velocity model (:95, :156)
+template<bool PARITY, typename E>
+AGF_DEV E est_lag_factor(const EstParams& ep, double dtInt) {  // exp(-dt / tau) of the angular-velocity model (:95, :156)
   if constexpr (PARITY) {
     return Mf<true>::exp(-dtInt / ep.tc_angvel);
   } else {
 #if defined(__CUDA_ARCH__)
-    return double(__expf(float(-dtInt * ep.inv_tc_angvel)));
+    return E(__expf(float(-dtInt * ep.inv_tc_angvel)));
 #else
-    return double(::expf(float(-dtInt * ep.inv_tc_angvel)));
+    return E(::expf(float(-dtInt * ep.inv_tc_angvel)));
 #endif
   }
 }
 // A V A^T + Q with A = [[1, dt], [0, 1]] (:171-186), written out (fast variants)
-AGF_DEV void est_propagate_var_fast(double* v, double dtInt, double proc) {
-  const double d2 = dtInt * dtInt;
-  v[0] = ::fma(dtInt, (v[1] + v[2]) + dtInt * v[3], v[0]) + d2 * d2 * proc * 0.25;
-  v[1] = ::fma(dtInt, v[3], v[1]);
-  v[2] = ::fma(dtInt, v[3], v[2]);
-  v[3] = ::fma(d2, proc, v[3]);
+template<typename E>
+AGF_DEV void est_propagate_var_fast(E* v, E dtInt, E proc) {
+  const E d2 = dtInt * dtInt;
+  v[0] = (v[0] + dtInt * ((v[1] + v[2]) + dtInt * v[3])) + d2 * d2 * proc * E(0.25);
+  v[1] = v[1] + dtInt * v[3];
+  v[2] = v[2] + dtInt * v[3];
+  v[3] = v[3] + d2 * proc;
 }
 
 // MocapStateEstimator::GetPrediction (MocapStateEstimator.cpp:61-118)
-template<bool PARITY>
-AGF_DEV void mocap_predict(const EstParams& ep, size_t i, uint64_t now_us, double dt, EstCore& o, EstPipe& pipe) {
+template<bool PARITY, typename E>
+AGF_DEV void mocap_predict(const EstParams& ep, size_t i, uint64_t now_us, double dt, EstCoreT<E>& o, EstPipe& pipe) {
   constexpr size_t n = E_LANES;
   const double* st = ep.state + est_index(i);
   const double tEnd = dt + double(now_us - ep.t0_us) * 1e-6;
   const double tStart = double(uint64_t(ldg2(st + E_TEST * n))) * 1e-6;
-  EstCore m;
+  EstCoreT<E> m;
   est_pipe_load(st, n, pipe);
   est_load(st, n, m);
   o = m;
   double t = tStart;
   while ((t + 1e-6) < tEnd) {
-    EstMsg cmd;
+    EstMsgT<E> cmd;
     double predictionTime;
     est_fetch(st, n, pipe, t, cmd, predictionTime);
     double dtInt = tEnd - t;
     if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
-    const V3<double> newPos = (o.pos + m.vel * dtInt) + ((cmd.acc * dtInt) * dtInt) / 2.0;  // sic: _vel (:90)
-    const V3<double> newVel = o.vel + cmd.acc * dtInt;
-    const Q4<double> newAtt = est_apply_rotvec<PARITY>(o.att, m.w * dtInt);  // sic: _angVel (:92)
-    double discrete = est_lag_factor<PARITY>(ep, dtInt);
+    const E h = E(dtInt);
+    const V3<E> newPos = (o.pos + m.vel * h) + ((cmd.acc * h) * h) / E(2.0);  // sic: _vel (:90)
+    const V3<E> newVel = o.vel + cmd.acc * h;
+    const Q4<E> newAtt = est_apply_rotvec<PARITY>(o.att, m.w * h);  // sic: _angVel (:92)
+    E discrete = est_lag_factor<PARITY, E>(ep, dtInt);
     if (cmd.ballistic) discrete = 1;
-    const V3<double> newW = discrete * o.w + (1 - discrete) * cmd.w;
+    const V3<E> newW = discrete * o.w + (E(1) - discrete) * cmd.w;
     o.pos = newPos; o.vel = newVel; o.att = newAtt; o.w = newW;
     t += dtInt;
   }
 }
-AGF_DEV void est_reset_variance(double* vp, double* va) {  // :52-60
+template<typename E>
+AGF_DEV void est_reset_variance(E* vp, E* va) {  // :52-60
   vp[0] = 25.0; vp[3] = 25.0; vp[1] = vp[2] = 0.0;
   va[0] = 1.0; va[3] = 400; va[1] = va[2] = 0.0;
 }
@@ -1761,12 +1778,12 @@ AGF_DEV void est_propagate_var(double* v, double dtInt, double proc) {  // A V A
   v[3] = t2[3] + dtInt * dtInt * proc;
 }
 // MocapStateEstimator::UpdateWithMeasurement (:120-265)
-template<bool PARITY>
-AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const V3<double>& measPos, const Q4<double>& measAtt) {
+template<bool PARITY, typename E>
+AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const V3<E>& measPos, const Q4<E>& measAtt) {
   constexpr size_t n = E_LANES;
   double* st = ep.state + est_index(i);
-  EstCore e;
-  double vp[4], va[4];
+  EstCoreT<E> e;
+  E vp[4], va[4];
   // everything the update reads, requested before the first use (one L2 round trip instead of one per group)
   const double inited = ldg2(st + E_INIT * n);
   EstPipe pipe;
@@ -1774,16 +1791,16 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
   est_load(st, n, e);
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    vp[k] = ldg2(st + (E_VP + k) * n);
-    va[k] = ldg2(st + (E_VA + k) * n);
+    vp[k] = E(ldg2(st + (E_VP + k) * n));
+    va[k] = E(ldg2(st + (E_VA + k) * n));
   }
   uint64_t est_us = uint64_t(ldg2(st + E_TEST * n));
   double nrej = ldg2(st + E_NREJ * n), nrejc = ldg2(st + E_NREJC * n);
   if (inited == 0.0) {
     e.pos = measPos;
-    e.vel = V3<double>(0, 0, 0);
+    e.vel = V3<E>(0, 0, 0);
     e.att = measAtt;
-    e.w = V3<double>(0, 0, 0);
+    e.w = V3<E>(0, 0, 0);
     est_store(st, n, e);
     est_reset_variance(vp, va);
     for (int k = 0; k < 4; k++) {
@@ -1800,30 +1817,31 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
     for (;;) {
       const double tNow = double(est_us) * 1e-6;
       if ((tNow + 1e-6) >= tEnd) break;
-      EstMsg p;
+      EstMsgT<E> p;
       double predictionTime;
       est_fetch(st, n, pipe, tNow, p, predictionTime);
       double dtInt = tEnd - tNow;
       if (dtInt > (predictionTime + 1e-6)) dtInt = predictionTime;
-      const EstCore c = e;
-      e.pos = c.pos + c.vel * dtInt;
-      e.vel = c.vel + p.acc * dtInt;
-      e.att = est_apply_rotvec<PARITY>(c.att, c.w * dtInt);
-      double discrete = est_lag_factor<PARITY>(ep, dtInt);
+      const EstCoreT<E> c = e;
+      const E h = E(dtInt);
+      e.pos = c.pos + c.vel * h;
+      e.vel = c.vel + p.acc * h;
+      e.att = est_apply_rotvec<PARITY>(c.att, c.w * h);
+      E discrete = est_lag_factor<PARITY, E>(ep, dtInt);
       if (p.ballistic) discrete = 1;
-      e.w = discrete * c.w + (1 - discrete) * p.w;
+      e.w = discrete * c.w + (E(1) - discrete) * p.w;
       est_us += uint64_t(0.5 + dtInt * 1e6);
       if constexpr (PARITY) {
         est_propagate_var(vp, dtInt, ep.proc_pos);
         est_propagate_var(va, dtInt, ep.proc_att);
       } else {
-        est_propagate_var_fast(vp, dtInt, ep.proc_pos);
-        est_propagate_var_fast(va, dtInt, ep.proc_att);
+        est_propagate_var_fast(vp, h, E(ep.proc_pos));
+        est_propagate_var_fast(va, h, E(ep.proc_att));
       }
     }
   }
-  double innovP = vp[0] + ep.meas_pos * ep.meas_pos;
-  double innovA = va[0] + ep.meas_att * ep.meas_att;
+  E innovP = vp[0] + E(ep.meas_pos * ep.meas_pos);
+  E innovA = va[0] + E(ep.meas_att * ep.meas_att);
   bool reject;
   if constexpr (PARITY) {
     const double distP = norm(measPos - e.pos) / ::sqrt(3 * innovP);
@@ -1832,44 +1850,46 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
     reject = (distP > ep.reject) || (distA > ep.reject);
   } else {
     // the same two gates without square roots and acos: |d|^2 > r^2 * 3 S_p ; angle/2 > r sqrt(S_a)/2 <=> |dq.w| < cos(..)
-    const V3<double> d = measPos - e.pos;
-    const double dqw = ::fabs(measAtt.w * e.att.w + measAtt.x * e.att.x + measAtt.y * e.att.y + measAtt.z * e.att.z);
+    const V3<E> d = measPos - e.pos;
+    const E dqw = rabs_(measAtt.w * e.att.w + measAtt.x * e.att.x + measAtt.y * e.att.y + measAtt.z * e.att.z);
     const float half = 0.5f * float(ep.reject) * ::sqrtf(float(innovA));
-    reject = (dot(d, d) > (ep.reject * ep.reject) * (3 * innovP)) || (half < 1.5707963f && float(dqw) < ::cosf(half));
+    reject = (dot(d, d) > E(ep.reject * ep.reject) * (E(3) * innovP)) || (half < 1.5707963f && float(dqw) < ::cosf(half));
   }
   if (reject && nrejc < 10.0) {
     nrej += 1.0;
     nrejc += 1.0;
   } else {
     if (nrejc >= 10.0) {  // forced acceptance: Reset() (:37-50), then the update against the zeroed state
-      e.pos = V3<double>(0, 0, 0);
-      e.vel = V3<double>(0, 0, 0);
-      e.att = Q4<double>(1, 0, 0, 0);
-      e.w = V3<double>(0, 0, 0);
+      e.pos = V3<E>(0, 0, 0);
+      e.vel = V3<E>(0, 0, 0);
+      e.att = Q4<E>(1, 0, 0, 0);
+      e.w = V3<E>(0, 0, 0);
       est_reset_variance(vp, va);
       est_us = now_us - ep.t0_us;
       st[E_INIT * n] = 0.0;
-      innovP = vp[0] + ep.meas_pos * ep.meas_pos;
-      innovA = va[0] + ep.meas_att * ep.meas_att;
+      innovP = vp[0] + E(ep.meas_pos * ep.meas_pos);
+      innovA = va[0] + E(ep.meas_att * ep.meas_att);
     }
     nrejc = 0.0;
     st[E_LASTGOOD * n] = double(now_us);
-    const double sP = 1 / innovP, sA = 1 / innovA;
-    double gP[2], gA[2];
+    const E sP = 1 / innovP, sA = 1 / innovA;
+    E gP[2], gA[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {  // V * H^T * (1 / S), H = [1 0]
-      double a = vp[2 * r] * 1.0;
-      a += vp[2 * r + 1] * 0.0;
+      E a = vp[2 * r] * E(1.0);
+      a += vp[2 * r + 1] * E(0.0);
       gP[r] = a * sP;
-      double b = va[2 * r] * 1.0;
-      b += va[2 * r + 1] * 0.0;
+      E b = va[2 * r] * E(1.0);
+      b += va[2 * r + 1] * E(0.0);
       gA[r] = b * sA;
     }
-    const V3<double> errP = measPos - e.pos;
+    const V3<E> errP = measPos - e.pos;
     e.pos = e.pos + gP[0] * errP;
     e.vel = e.vel + gP[1] * errP;
-    const Q4<double> qerr = qmul(qinv(e.att), measAtt);
-    const V3<double> errA = PARITY ? est_q_to_rotvec<PARITY>(qerr) : est_q_to_rotvec_fast(qerr);
+    const Q4<E> qerr = qmul(qinv(e.att), measAtt);
+    V3<E> errA;
+    if constexpr (PARITY) errA = est_q_to_rotvec<true>(qerr);
+    else errA = est_q_to_rotvec_fast(qerr);
     e.att = est_apply_rotvec<PARITY>(e.att, gA[0] * errA);
     e.w = e.w + gA[1] * errA;
     if constexpr (PARITY) {
@@ -1883,15 +1903,15 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
         va[k] = na_[k];
       }
     } else {  // (I - K H) V with H = [1 0], written out
-      const double p0 = vp[0], p1 = vp[1], a0 = va[0], a1 = va[1];
-      vp[0] = (1.0 - gP[0]) * p0; vp[1] = (1.0 - gP[0]) * p1; vp[2] = ::fma(-gP[1], p0, vp[2]); vp[3] = ::fma(-gP[1], p1, vp[3]);
-      va[0] = (1.0 - gA[0]) * a0; va[1] = (1.0 - gA[0]) * a1; va[2] = ::fma(-gA[1], a0, va[2]); va[3] = ::fma(-gA[1], a1, va[3]);
+      const E p0 = vp[0], p1 = vp[1], a0 = va[0], a1 = va[1];
+      vp[0] = (E(1) - gP[0]) * p0; vp[1] = (E(1) - gP[0]) * p1; vp[2] = vp[2] - gP[1] * p0; vp[3] = vp[3] - gP[1] * p1;
+      va[0] = (E(1) - gA[0]) * a0; va[1] = (E(1) - gA[0]) * a1; va[2] = va[2] - gA[1] * a0; va[3] = va[3] - gA[1] * a1;
     }
   }
   {  // symmetry (:257-261)
-    const double p01 = (vp[1] + vp[2]) * 0.5, p10 = (vp[2] + vp[1]) * 0.5, a01 = (va[1] + va[2]) * 0.5, a10 = (va[2] + va[1]) * 0.5;
-    vp[0] = (vp[0] + vp[0]) * 0.5; vp[3] = (vp[3] + vp[3]) * 0.5; vp[1] = p01; vp[2] = p10;
-    va[0] = (va[0] + va[0]) * 0.5; va[3] = (va[3] + va[3]) * 0.5; va[1] = a01; va[2] = a10;
+    const E p01 = (vp[1] + vp[2]) * E(0.5), p10 = (vp[2] + vp[1]) * E(0.5), a01 = (va[1] + va[2]) * E(0.5), a10 = (va[2] + va[1]) * E(0.5);
+    vp[0] = (vp[0] + vp[0]) * E(0.5); vp[3] = (vp[3] + vp[3]) * E(0.5); vp[1] = p01; vp[2] = p10;
+    va[0] = (va[0] + va[0]) * E(0.5); va[3] = (va[3] + va[3]) * E(0.5); va[1] = a01; va[2] = a10;
   }
   est_store(st, n, e);
   for (int k = 0; k < 4; k++) {
@@ -1919,8 +1939,9 @@ AGF_DEV void mocap_update(const EstParams& ep, size_t i, uint64_t now_us, const 
   }
 }
 // MocapStateEstimator::SetPredictedValues -> PredictionPipe::AddMessage (hpp:74-80, PredictionPipe.hpp:25-30)
-AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, uint64_t now_us, const EstPipe& pipe, const V3<double>& w,
-                                    const V3<double>& acc) {
+template<typename E>
+AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, uint64_t now_us, const EstPipe& pipe, const V3<E>& w,
+                                    const V3<E>& acc) {
   constexpr size_t n = E_LANES;
   double* st = ep.state + est_index(i);
   // `pipe`: the slots as mocap_predict read them for this command (nothing touches them in between)
@@ -1946,10 +1967,13 @@ AGF_DEV void mocap_set_predicted(const EstParams& ep, size_t i, uint64_t now_us,
   q[7 * n] = 0.0;
   st[E_NPIPE * n] = double(cnt + 1);
 }
+// compute type of the fast variants' estimator: float with an FP32 plant, double with an FP64 plant (see EstCoreT)
+template<typename P> struct EstOf { typedef double type; };
+template<> struct EstOf<float> { typedef float type; };
 template<typename P>
 static AGF_COLD void mocap_update_cold(const EstParams* ep, size_t i, uint64_t now_us, V3<P> p, Q4<P> a) {
-  mocap_update<false>(*ep, i, now_us, V3<double>(double(p.x), double(p.y), double(p.z)),
-                      Q4<double>(double(a.w), double(a.x), double(a.y), double(a.z)));
+  typedef typename EstOf<P>::type E;
+  mocap_update<false, E>(*ep, i, now_us, V3<E>(E(p.x), E(p.y), E(p.z)), Q4<E>(E(a.w), E(a.x), E(a.y), E(a.z)));
 }
 
 // One round of the offboard main loop for vehicle i at clock reading t_gen: desired state from the configured
@@ -2161,22 +2185,27 @@ AGF_DEV float4 offboard_generate_core(const OffboardParams& c, size_t i, size_t 
 template<bool PARITY, typename P>
 AGF_DEV float4 offboard_generate(const OffboardParams& c, size_t i, size_t n, uint64_t t_gen, const V3<P>& cp, const V3<P>& cv,
                                  const Q4<P>& ca) {
-  EstCore e;
+  typedef typename std::conditional<PARITY, double, typename EstOf<P>::type>::type E;  // what the estimator computes in
+  EstCoreT<E> e;
   EstPipe pipe;
   if (c.est.kind == AGF_OFFEST_MOCAP) {
-    mocap_predict<PARITY>(c.est, i, t_gen, c.est.delay, e, pipe);
+    mocap_predict<PARITY, E>(c.est, i, t_gen, c.est.delay, e, pipe);
   } else {
-    e.pos = V3<double>(double(cp.x), double(cp.y), double(cp.z));
-    e.vel = V3<double>(double(cv.x), double(cv.y), double(cv.z));
-    e.att = Q4<double>(double(ca.w), double(ca.x), double(ca.y), double(ca.z));
+    e.pos = V3<E>(E(cp.x), E(cp.y), E(cp.z));
+    e.vel = V3<E>(E(cv.x), E(cv.y), E(cv.z));
+    e.att = Q4<E>(E(ca.w), E(ca.x), E(ca.y), E(ca.z));
   }
   int predicted;
   double thrust = 0.0;
   V3<double> w(0, 0, 0);
-  const float4 out = offboard_generate_core<PARITY>(c, i, n, t_gen, e.pos, e.vel, e.att, predicted, thrust, w);
+  const float4 out = offboard_generate_core<PARITY>(c, i, n, t_gen, V3<double>(double(e.pos.x), double(e.pos.y), double(e.pos.z)),
+                                                    V3<double>(double(e.vel.x), double(e.vel.y), double(e.vel.z)),
+                                                    Q4<double>(double(e.att.w), double(e.att.x), double(e.att.y), double(e.att.z)), predicted,
+                                                    thrust, w);
   if (c.est.kind == AGF_OFFEST_MOCAP) {
-    if (predicted == 1) mocap_set_predicted(c.est, i, t_gen, pipe, V3<double>(0, 0, 0), V3<double>(0, 0, 0));
-    if (predicted == 2) mocap_set_predicted(c.est, i, t_gen, pipe, w, qrot(e.att, V3<double>(0, 0, 1)) * thrust - V3<double>(0, 0, 9.81));
+    if (predicted == 1) mocap_set_predicted(c.est, i, t_gen, pipe, V3<E>(0, 0, 0), V3<E>(0, 0, 0));
+    if (predicted == 2)
+      mocap_set_predicted(c.est, i, t_gen, pipe, V3<E>(E(w.x), E(w.y), E(w.z)), qrot(e.att, V3<E>(0, 0, 1)) * E(thrust) - V3<E>(0, 0, E(9.81)));
   }
   return out;
 }
@@ -2628,7 +2657,7 @@ AGF_DEV void tick(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const StepSh
     const V3<P> mp(s.pos[0], s.pos[1], s.pos[2]);
     const Q4<P> ma(s.att[0], s.att[1], s.att[2], s.att[3]);
     if constexpr (PARITY) {
-      mocap_update<true>(p.off.est, i, now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
+      mocap_update<true, double>(p.off.est, i, now_us + dt_us, V3<double>(double(mp.x), double(mp.y), double(mp.z)),
                          Q4<double>(double(ma.w), double(ma.x), double(ma.y), double(ma.z)));
     } else {
       mocap_update_cold<P>(&p.off.est, i, now_us + dt_us, mp, ma);

@@ -239,7 +239,7 @@ void orc_set_offboard_estimator(orc_vehicle* v, const agf_offboard_estimator* e)
 void orc_get_offboard_estimate(orc_vehicle* v, double horizon, double* o, double* c4) {
   EstCore e;
   EstPipe pipe;
-  mocap_predict<true>(v->sh.off.est, 0, v->now_us, horizon, e, pipe);
+  mocap_predict<true, double>(v->sh.off.est, 0, v->now_us, horizon, e, pipe);
   const double x[13] = {e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z, e.att.w, e.att.x, e.att.y, e.att.z, e.w.x, e.w.y, e.w.z};
   for (int k = 0; k < 13; k++) o[k] = x[k];
   if (c4) {
