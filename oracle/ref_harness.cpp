@@ -785,10 +785,16 @@ uint64_t orc_time_us(orc_vehicle* v) { return v->timer.GetMicroSeconds(); }
 // that every UWBNetwork constructor re-seeds with 0 (:19).  Left alone, the vehicles of a population stepped on T threads
 // would replay the same T-fold copies of one stream; a Monte-Carlo population needs independent realisations, so the
 // generator is seeded per vehicle right before that vehicle runs (no reference source is touched; vehicle 0 keeps seed 0).
+// The distribution objects next to it (:5-6) stay shared file-scope state: populations WITH range noise are stepped on one
+// thread by the tests (threads = 1), which makes them reproducible.
 }  // extern "C"
 extern std::mt19937 rng;  // thread_local through the forced include (the -include of ref_tls_rng.h covers every file of the command)
+extern std::normal_distribution<double> distNormal;  // UWBNetwork.cpp:6: keeps the second value of every pair it draws
 extern "C" {
-static void seed_range_noise(uint32_t vehicle) { rng.seed(vehicle); }
+static void seed_range_noise(uint32_t vehicle) {
+  rng.seed(vehicle);
+  distNormal.reset();
+}
 
 double orc_run_population(const agf_vehicle_cfg* cfgs, uint32_t n_cfgs, uint32_t n,
                           const orc_opts* opts, const double* init13, const float* anchors,
