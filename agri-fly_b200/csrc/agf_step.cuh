@@ -510,7 +510,11 @@ struct VState {
   uint32_t uwbw;      // anchor indices: network responder | radio meas responder | logic meas target | next target
   uint32_t age_radio, age_uwb, age_est_reset;
   // housekeeping (HK)
-  float temp_lp[4], batt_lp[4];
+  // battery-voltage and temperature low-pass states: parity variants only.  Both filters have a CONSTANT input and are
+  // initialised at their fixed point (QuadcopterLogic.cpp:138-139; 25 C), so the fast variants take the fixed point -- the
+  // filtered voltage is the supply voltage -- instead of iterating two second-order filters per tick towards where they
+  // already are (the float recursion only dithers in the last bits); their stored states are left untouched.
+  float temp_lp[PARITY ? 4 : 1], batt_lp[PARITY ? 4 : 1];
   float batt_vfilt, mon_cmd_lpdt, mon_loop_lpdt;
   float pc_accum[4], pc_corr[4];
   uint32_t pc_count, age_mon_cmd, age_mon_loop;
@@ -712,7 +716,11 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
   s.logic_range = rf[SF_LOGIC_RANGE];
   if constexpr (HK) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { s.temp_lp[k] = rf[SF_TEMP_LP + k]; s.batt_lp[k] = rf[SF_BATT_LP + k]; s.pc_accum[k] = rf[SF_PC_ACCUM + k]; s.pc_corr[k] = rf[SF_PC_CORR + k]; }
+    for (int k = 0; k < 4; k++) { s.pc_accum[k] = rf[SF_PC_ACCUM + k]; s.pc_corr[k] = rf[SF_PC_CORR + k]; }
+    if constexpr (PARITY) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { s.temp_lp[k] = rf[SF_TEMP_LP + k]; s.batt_lp[k] = rf[SF_BATT_LP + k]; }
+    }
     s.batt_vfilt = rf[SF_BATT_VFILT]; s.mon_cmd_lpdt = rf[SF_MON_CMD]; s.mon_loop_lpdt = rf[SF_MON_LOOP];
   }
   uint32_t ru[NU_PAD];
@@ -810,12 +818,17 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
   rf[SF_LOGIC_RANGE] = s.logic_range;
   if constexpr (HK) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { rf[SF_TEMP_LP + k] = s.temp_lp[k]; rf[SF_BATT_LP + k] = s.batt_lp[k]; rf[SF_PC_ACCUM + k] = s.pc_accum[k]; rf[SF_PC_CORR + k] = s.pc_corr[k]; }
+    for (int k = 0; k < 4; k++) { rf[SF_PC_ACCUM + k] = s.pc_accum[k]; rf[SF_PC_CORR + k] = s.pc_corr[k]; }
+    if constexpr (PARITY) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { rf[SF_TEMP_LP + k] = s.temp_lp[k]; rf[SF_BATT_LP + k] = s.batt_lp[k]; }
+    }
     rf[SF_BATT_VFILT] = s.batt_vfilt; rf[SF_MON_CMD] = s.mon_cmd_lpdt; rf[SF_MON_LOOP] = s.mon_loop_lpdt;
   }
 #pragma unroll
   for (int q = 0; q < NF_PAD / 4; q++) {
     if (!HK && q >= NF_CORE / 4) break;
+    if (!PARITY && (q == SF_TEMP_LP / 4 || q == SF_BATT_LP / 4)) continue;  // fixed-point filters: stored states stay as they are
     a.sf[size_t(q) * n + i] = make_float4(rf[4 * q], rf[4 * q + 1], rf[4 * q + 2], rf[4 * q + 3]);
   }
   uint32_t ru[NU_PAD];
@@ -2249,8 +2262,12 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
   const LogicParams& k = p.logic;
   // --- intake (QuadcopterLogic.hpp:32-59) ---
   if constexpr (HK) {
-    s.batt_vfilt = lpf2(k.lp_batt, s.batt_lp, 1, k.batt_voltage);
-    lpf2(k.lp_temp, s.temp_lp, 1, 25.0f);
+    if constexpr (PARITY) {
+      s.batt_vfilt = lpf2(k.lp_batt, s.batt_lp, 1, k.batt_voltage);
+      lpf2(k.lp_temp, s.temp_lp, 1, 25.0f);
+    } else {
+      s.batt_vfilt = k.batt_voltage;  // the filter's fixed point (VState)
+    }
   }
   V3<float> g = gyroMeas, a = accMeas;
   if (!k.imu_identity) {
