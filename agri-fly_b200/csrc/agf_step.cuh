@@ -516,7 +516,7 @@ struct VState {
   // already are (the float recursion only dithers in the last bits); their stored states are left untouched.
   float temp_lp[PARITY ? 4 : 1], batt_lp[PARITY ? 4 : 1];
   float batt_vfilt, mon_cmd_lpdt, mon_loop_lpdt;
-  float pc_accum[4], pc_corr[4];
+  float pc_accum[PARITY ? 4 : 1], pc_corr[PARITY ? 4 : 1];  // fast variants: in the scratch (SQ_PC_*)
   uint32_t pc_count, age_mon_cmd, age_mon_loop;
   // estimator covariance (UWB): full 9x9 in registers in the parity variant (the reference's predict step
   // does not keep it exactly symmetric); packed upper triangle in shared-memory scratch in the fast variants
@@ -557,7 +557,11 @@ struct Scratch {
 // threads per block of the variants that use the scratch: a compile-time stride turns every scratch address
 // into base register + immediate and lets the compiler tell the quads apart (no false LDS/STS dependencies)
 enum { SQ_STRIDE = AGF_BLOCK_THREADS };
-enum { SQ_LPF = 0, SQ_COV = 6, SQ_QUADS_NOUWB = 6, SQ_QUADS_UWB = 18 };  // + AGF_OFFQ quads (offboard queue) behind, when the loop is on
+// after the filters / covariance: three quads of propeller-calibration state (per-motor thrust correction, its derived
+// 1 / (correction * kF), the calibration accumulators) -- read once per tick or rarer, so not worth nine registers;
+// then AGF_OFFQ quads (offboard queue) when the loop is on
+enum { SQ_LPF = 0, SQ_COV = 6, SQ_PC_NOUWB = 6, SQ_PC_UWB = 18, SQ_QUADS_NOUWB = 9, SQ_QUADS_UWB = 21 };
+enum { SQ_PC_CORR = 0, SQ_PC_INV = 1, SQ_PC_ACCUM = 2 };
 // Scratch accesses are volatile 128-bit shared-memory instructions: with the compile-time stride the compiler
 // could otherwise forward a tick's stores to the next tick's loads, i.e. keep the whole scratch in registers
 // across the loop -- the opposite of what the scratch is for (measured: 3x the local-memory spill traffic).
@@ -668,7 +672,7 @@ template<typename T> AGF_DEV T ldcg_(const T* p) {
 
 // --- flat (de)serialisation order; the host get/set kernels use the same tables (agf_types.h) ---
 template<typename P, bool PARITY, bool UWB, bool HK>
-AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i, const Scratch& sc) {
+AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, size_t n, size_t i, const Scratch& sc, float mix_kf) {
   typedef typename VecOf<P>::type PV;
   constexpr int VP = VecOf<P>::lanes;
   constexpr bool COMP = !PARITY && sizeof(P) == 4;  // compensated FP32 integration: two more triples of plant scalars
@@ -716,10 +720,17 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
   s.logic_range = rf[SF_LOGIC_RANGE];
   if constexpr (HK) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { s.pc_accum[k] = rf[SF_PC_ACCUM + k]; s.pc_corr[k] = rf[SF_PC_CORR + k]; }
     if constexpr (PARITY) {
 #pragma unroll
+      for (int k = 0; k < 4; k++) { s.pc_accum[k] = rf[SF_PC_ACCUM + k]; s.pc_corr[k] = rf[SF_PC_CORR + k]; }
+#pragma unroll
       for (int k = 0; k < 4; k++) { s.temp_lp[k] = rf[SF_TEMP_LP + k]; s.batt_lp[k] = rf[SF_BATT_LP + k]; }
+    } else {
+      const int q0 = UWB ? SQ_PC_UWB : SQ_PC_NOUWB;
+      sq_store(sc, q0 + SQ_PC_CORR, make_float4(rf[SF_PC_CORR], rf[SF_PC_CORR + 1], rf[SF_PC_CORR + 2], rf[SF_PC_CORR + 3]));
+      sq_store(sc, q0 + SQ_PC_INV, make_float4(1.0f / (rf[SF_PC_CORR] * mix_kf), 1.0f / (rf[SF_PC_CORR + 1] * mix_kf),
+                                               1.0f / (rf[SF_PC_CORR + 2] * mix_kf), 1.0f / (rf[SF_PC_CORR + 3] * mix_kf)));
+      sq_store(sc, q0 + SQ_PC_ACCUM, make_float4(rf[SF_PC_ACCUM], rf[SF_PC_ACCUM + 1], rf[SF_PC_ACCUM + 2], rf[SF_PC_ACCUM + 3]));
     }
     s.batt_vfilt = rf[SF_BATT_VFILT]; s.mon_cmd_lpdt = rf[SF_MON_CMD]; s.mon_loop_lpdt = rf[SF_MON_LOOP];
   }
@@ -818,10 +829,16 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
   rf[SF_LOGIC_RANGE] = s.logic_range;
   if constexpr (HK) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { rf[SF_PC_ACCUM + k] = s.pc_accum[k]; rf[SF_PC_CORR + k] = s.pc_corr[k]; }
     if constexpr (PARITY) {
 #pragma unroll
+      for (int k = 0; k < 4; k++) { rf[SF_PC_ACCUM + k] = s.pc_accum[k]; rf[SF_PC_CORR + k] = s.pc_corr[k]; }
+#pragma unroll
       for (int k = 0; k < 4; k++) { rf[SF_TEMP_LP + k] = s.temp_lp[k]; rf[SF_BATT_LP + k] = s.batt_lp[k]; }
+    } else {
+      const int q0 = UWB ? SQ_PC_UWB : SQ_PC_NOUWB;
+      const float4 c4 = sq_load(sc, q0 + SQ_PC_CORR), a4 = sq_load(sc, q0 + SQ_PC_ACCUM);
+      rf[SF_PC_CORR] = c4.x; rf[SF_PC_CORR + 1] = c4.y; rf[SF_PC_CORR + 2] = c4.z; rf[SF_PC_CORR + 3] = c4.w;
+      rf[SF_PC_ACCUM] = a4.x; rf[SF_PC_ACCUM + 1] = a4.y; rf[SF_PC_ACCUM + 2] = a4.z; rf[SF_PC_ACCUM + 3] = a4.w;
     }
     rf[SF_BATT_VFILT] = s.batt_vfilt; rf[SF_MON_CMD] = s.mon_cmd_lpdt; rf[SF_MON_LOOP] = s.mon_loop_lpdt;
   }
@@ -1375,7 +1392,7 @@ AGF_DEV V3<float> ctl_att(const LogicParams& k, const Q4<float>& desAtt, const Q
 
 // QuadcopterMixer::GetMotorForces + PropellerSpeedsFromThrust (:63-99)
 template<typename P, bool PARITY, bool UWB, bool HK>
-AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float totF, const V3<float>& t) {
+AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const LogicParams& k, float totF, const V3<float>& t) {
   const float desF = totF > k.max_cmd_total ? k.max_cmd_total : totF;
   float f[4];
   if (PARITY) {
@@ -1390,6 +1407,11 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float 
     f[2] = (+tx + ty - tz + desF) * 0.25f;
     f[3] = (+tx - ty + tz + desF) * 0.25f;
   }
+  float inv_ck[4] = {k.inv_mix_kf, k.inv_mix_kf, k.inv_mix_kf, k.inv_mix_kf};  // 1 / (calibration correction * kF), fast variants
+  if constexpr (!PARITY && HK) {
+    const float4 v = sq_load(sc, (UWB ? SQ_PC_UWB : SQ_PC_NOUWB) + SQ_PC_INV);
+    inv_ck[0] = v.x; inv_ck[1] = v.y; inv_ck[2] = v.z; inv_ck[3] = v.w;
+  }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     if constexpr (PARITY) {
@@ -1402,12 +1424,11 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const LogicParams& k, float 
       f[i] = ::fminf(::fmaxf(f[i], k.min_thrust), k.max_thrust);
     }
     if constexpr (PARITY || HK) s.dforce[i] = f[i];
-    float corr = 1.0f;
-    if constexpr (HK) corr = s.pc_corr[i];
-    if (PARITY || HK) {
+    if constexpr (PARITY) {
+      const float corr = HK ? s.pc_corr[i] : 1.0f;
       s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(fdiv<PARITY>(f[i], corr * k.mix_kf));
     } else {
-      s.cmd[i] = ::sqrtf(::fmaxf(f[i], 0.0f) * k.inv_mix_kf);  // sqrt(0) = 0: no branch for f <= 0
+      s.cmd[i] = ::sqrtf(::fmaxf(f[i], 0.0f) * inv_ck[i]);  // sqrt(0) = 0: no branch for f <= 0
     }
   }
 }
@@ -2401,7 +2422,7 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
     }
   }
   if (powered) {
-    ctl_mix(s, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
+    ctl_mix(s, sc, k, thrust * k.mass, ctl_torques<PARITY>(k, desW, estW));
   } else {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -2411,27 +2432,63 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
   }
   if constexpr (HK) {  // propeller calibration, rates mode only (:553-587)
     if (fs == AGF_FS_EXTERNAL_RATES_CONTROL) {
-      if (rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) {
-        if (!(s.bits & B_PC_RUNNING)) {
-          s.bits |= B_PC_RUNNING;
-          s.pc_count = 0;
+      if constexpr (PARITY) {
+        if (rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) {
+          if (!(s.bits & B_PC_RUNNING)) {
+            s.bits |= B_PC_RUNNING;
+            s.pc_count = 0;
 #pragma unroll
-          for (int i = 0; i < 4; i++) s.pc_accum[i] = 0;
+            for (int i = 0; i < 4; i++) s.pc_accum[i] = 0;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) s.pc_accum[i] += k.mix_kf * s.cmd[i] * s.cmd[i];
+          s.pc_count++;
+        } else if (s.bits & B_PC_RUNNING) {
+          s.bits &= ~B_PC_RUNNING;
+          if (s.pc_count >= 750u) {
+            const float truePer = k.mass * 9.81f / 4.0f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              float f = (s.pc_count * truePer) / s.pc_accum[i];
+              const float fmin = 0.7f, fmax = 1.0f / fmin;
+              if (f > fmax) f = fmax;
+              if (f < fmin) f = fmin;
+              s.pc_corr[i] = f;
+            }
+          }
         }
+      } else if (AGF_UNLIKELY((rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) || (s.bits & B_PC_RUNNING))) {
+        // the same on the scratch copies (accumulators, correction and its derived 1 / (correction * kF))
+        const int q0 = UWB ? SQ_PC_UWB : SQ_PC_NOUWB;
+        const float4 a4 = sq_load(sc, q0 + SQ_PC_ACCUM);
+        float acc[4] = {a4.x, a4.y, a4.z, a4.w};
+        if (rflags & AGF_RADIO_FLAG_CALIBRATE_MOTORS) {
+          if (!(s.bits & B_PC_RUNNING)) {
+            s.bits |= B_PC_RUNNING;
+            s.pc_count = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) s.pc_accum[i] += k.mix_kf * s.cmd[i] * s.cmd[i];
-        s.pc_count++;
-      } else if (s.bits & B_PC_RUNNING) {
-        s.bits &= ~B_PC_RUNNING;
-        if (s.pc_count >= 750u) {
-          const float truePer = k.mass * 9.81f / 4.0f;
+            for (int i = 0; i < 4; i++) acc[i] = 0;
+          }
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            float f = (s.pc_count * truePer) / s.pc_accum[i];
-            const float fmin = 0.7f, fmax = 1.0f / fmin;
-            if (f > fmax) f = fmax;
-            if (f < fmin) f = fmin;
-            s.pc_corr[i] = f;
+          for (int i = 0; i < 4; i++) acc[i] += k.mix_kf * s.cmd[i] * s.cmd[i];
+          s.pc_count++;
+          sq_store(sc, q0 + SQ_PC_ACCUM, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        } else {
+          s.bits &= ~B_PC_RUNNING;
+          if (s.pc_count >= 750u) {
+            const float truePer = k.mass * 9.81f / 4.0f;
+            float c[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              float f = (s.pc_count * truePer) / acc[i];
+              const float fmin = 0.7f, fmax = 1.0f / fmin;
+              if (f > fmax) f = fmax;
+              if (f < fmin) f = fmin;
+              c[i] = f;
+            }
+            sq_store(sc, q0 + SQ_PC_CORR, make_float4(c[0], c[1], c[2], c[3]));
+            sq_store(sc, q0 + SQ_PC_INV, make_float4(1.0f / (c[0] * k.mix_kf), 1.0f / (c[1] * k.mix_kf), 1.0f / (c[2] * k.mix_kf),
+                                                     1.0f / (c[3] * k.mix_kf)));
           }
         }
       }
@@ -2793,7 +2850,7 @@ constexpr size_t step_smem_bytes(int block, bool offboard) {
 template<typename P, bool PARITY, bool UWB, bool HK, bool OFFB, typename PVT>
 AGF_DEV void step_ticks(const StepLaunch<P>& L, const PVT& pv, const Scratch& sc, size_t i, uint32_t t0, uint32_t t1) {
   VState<P, PARITY, UWB, HK> s;
-  state_load(s, L.st, L.n, i, sc);
+  state_load(s, L.st, L.n, i, sc, L.sh.logic.mix_kf);
   // what each tick does (plant step, logic, ranging, offboard loop) depends on the clock only: the host evaluated the
   // stopwatch recurrence (agf_types.h timing_plan / timing_advance) for every tick of the launch; one 16-byte word per tick,
   // the same address for the whole grid, the next one requested a tick ahead

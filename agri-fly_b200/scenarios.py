@@ -41,6 +41,19 @@ def rates_scenario(codec, nticks=5000):
                 sched=sched, nticks=nticks)
 
 
+def calibration_scenario(codec, nticks=2600, flag_until=1900):
+    """Propeller calibration (QuadcopterLogic.cpp:553-587): rates commands with the CALIBRATE_MOTORS flag set for more
+    than 750 logic cycles (thrust 1.08 g, a gentle constant body rate so that the four motors differ), then the flag
+    cleared -- the logic turns the accumulated thrusts into per-motor correction factors and the mixer uses them."""
+    sched = []
+    for g, d in command_ticks(nticks, 5, 15):
+        flags = 0x01 if d < flag_until else 0x00
+        sched.append((d, codec.encode_rates(flags, np.float32(1.08 * 9.81), (0.05, -0.03, 0.1)), -1))
+    return dict(name="calibration", quad_type=5, vehicle_id=1, motor_time_const=0.015, motor_inertia=0.0,
+                pos=(0.0, 0.0, 0.0), att=(1.0, 0.0, 0.0, 0.0), anchors=[], uwb_comm_period=0.0,
+                sched=sched, nticks=nticks)
+
+
 ANCHORS_8 = [(101 + i, (x, y, z)) for i, (x, y, z) in enumerate(
     [(sx * 3.0, sy * 3.0, z) for z in (0.1, 3.0) for sx in (1, -1) for sy in (1, -1)])]
 

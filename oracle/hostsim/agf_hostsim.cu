@@ -56,7 +56,7 @@ static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_
   Scratch sc;
   sc.q = nullptr;
 
-  state_load(s, a, 1, 0, sc);
+  state_load(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   v->sh.ext_force = v->ext_f.empty() ? nullptr : v->ext_f.data();
   v->sh.ext_torque = v->ext_t.empty() ? nullptr : v->ext_t.data();
   uint32_t si = 0;
@@ -143,10 +143,10 @@ void orc_set_radio(orc_vehicle* v, const uint8_t raw[23]) {
   memcpy(e.raw, raw, 23);
   // deliver through a zero-tick run: load, deliver, store
   if (v->uwb) {
-    VState<double, true, true, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr}; state_load(s, a, 1, 0, sc);
+    VState<double, true, true, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr}; state_load(s, a, 1, 0, sc, v->sh.logic.mix_kf);
     uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   } else {
-    VState<double, true, false, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr}; state_load(s, a, 1, 0, sc);
+    VState<double, true, false, true> s; StateArrays<double> a = v->arrays(); Scratch sc{nullptr}; state_load(s, a, 1, 0, sc, v->sh.logic.mix_kf);
     uint8_t ty, fl; float f[10]; agf_radio_decode(raw, &ty, &fl, f); radio_deliver(s, v->sh.logic, ty, fl, f); state_store(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   }
 }

@@ -65,7 +65,7 @@ static void run_impl(orc_vehicle* v, uint32_t dt_us, uint32_t nticks, const agf_
   StateArrays<HP> a = v->arrays();
   Scratch sc;
   sc.q = v->scratch.data();
-  state_load(s, a, 1, 0, sc);
+  state_load(s, a, 1, 0, sc, v->sh.logic.mix_kf);
   uint32_t si = 0;
   while (si < nsched && sched[si].tick < v->tick) si++;
   for (uint32_t k = 0; k < nticks; k++) {

@@ -310,6 +310,22 @@ def test_full_mode_counters(agf, port_glibc):
     assert np.linalg.norm(tr[-1, 0:3] - np.array([1.5, 0.7, 2.0])) < 0.02
 
 
+def test_propeller_calibration_port_and_device_code_match_reference(agf, orc_mod, port_shared):
+    """QuadcopterLogic.cpp:553-587: rates commands with the CALIBRATE_MOTORS flag for > 750 logic cycles, then the flag
+    cleared: the per-motor thrust corrections change the motor commands (thrust 1.08 g -> correction 1 / 1.08).  The port and
+    the device step compiled for the host reproduce the unmodified reference bit for bit, every tick."""
+    sc = agf.scenarios.calibration_scenario(agf.codec)
+    a, _ = run_oracle(port_shared, agf, sc)
+    plain, _ = run_oracle(port_shared, agf, agf.scenarios.calibration_scenario(agf.codec, flag_until=0))
+    assert np.allclose(a[1800, 13:17], plain[1800, 13:17], rtol=1e-6)          # no effect while calibrating
+    assert np.all(a[-1, 13:17] > 1.03 * plain[-1, 13:17])                       # corrections at work afterwards
+    for fl in ("ref-shared", "hostsim-shared"):
+        if not orc_mod.available(fl):
+            continue
+        b, _ = run_oracle(orc_mod.Oracle(fl), agf, sc)
+        assert bit_equal(a, b), fl
+
+
 def test_hostsim_matches_port(agf, orc_mod, port_shared):
     """The product's device step header compiled for the host == the literal port, bit for bit."""
     if not orc_mod.available("hostsim-shared"):

@@ -66,6 +66,31 @@ def test_parity_variant_is_bit_identical_to_oracle(agf, checker_shared, name):
     b.close()
 
 
+def test_propeller_calibration(agf, checker_shared, checker_glibc):
+    """QuadcopterLogic.cpp:553-587 (housekeeping): calibrate for > 750 logic cycles, then fly with the corrections.  Parity
+    variant bit-identical to the reference every tick; the fast variants (calibration state in the shared-memory scratch)
+    within the rates-mode tolerance, with the corrections visibly at work."""
+    sc = agf.scenarios.calibration_scenario(agf.codec)
+    ref, _ = run_oracle(checker_shared, agf, sc)
+    b, log, ticks, samples = gpu_traj(agf, sc, n=2)
+    assert bit_equal(log[:, 0, :], ref[:, PLANT_COLS]) and bit_equal(samples[:, 0, :], ref[ticks])
+    b.close()
+    refg, _ = run_oracle(checker_glibc, agf, sc)
+    plain, _ = run_oracle(checker_glibc, agf, agf.scenarios.calibration_scenario(agf.codec, flag_until=0))
+    for prec in (agf.abi.PREC_FP32, agf.abi.PREC_FP64):
+        f = make_batch(agf, sc, n=160, precision=prec, math=agf.abi.MATH_FAST, telemetry_warnings=True)
+        f.run(1800)
+        mid = f.record()[7]
+        f.run(50)      # a launch boundary in the middle of the flight with corrections
+        f.run(sc["nticks"] - 1850)
+        got = f.record()
+        f.close()
+        assert rel_err(mid[0:17], refg[1799, 0:17]) <= 1e-4
+        assert np.all(got[:, 13:17] > 1.03 * plain[-1, 13:17])
+        for veh in (0, 77, 159):
+            assert rel_err(got[veh, 0:17], refg[-1, 0:17]) <= 1e-4, (prec, veh, rel_err(got[veh, 0:17], refg[-1, 0:17]))
+
+
 @pytest.mark.parametrize("name", ["rates", "full", "accel"])
 def test_parity_variant_matches_reference_golden(agf, name):
     """Same check against vectors recorded from the unmodified reference (sharedmath build)."""
