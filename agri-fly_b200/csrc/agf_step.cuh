@@ -494,7 +494,7 @@ struct VState {
   P cpos[(!PARITY && sizeof(P) == 4) ? 3 : 1], cvel[(!PARITY && sizeof(P) == 4) ? 3 : 1];
   // logic
   float cmd[4];      // _desMotorSpeeds == _motorSpeedCommands after every logic run
-  float dforce[(PARITY || HK) ? 4 : 1];   // _desMotorForcesForTelemetry (fast, no HK: derived from cmd)
+  float dforce[PARITY ? 4 : 1];   // _desMotorForcesForTelemetry (fast variants: derived from cmd at the end of a launch)
   float radio_f[4];  // floats[0..3] of the last radio message (the only ones any controller reads)
   // IMU low-pass states [xm0 xm1 ym0 ym1] x 3 components, component-major [4*c + k]: in registers in the
   // parity variant, in the thread's shared-memory scratch in the fast variants (Scratch below)
@@ -703,7 +703,7 @@ AGF_DEV void state_load(VState<P, PARITY, UWB, HK>& s, const StateArrays<P>& a, 
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) { s.cmd[k] = rf[SF_CMD + k]; s.radio_f[k] = rf[SF_RADIO + k]; s.katt[k] = rf[SF_KATT + k]; }
-  if constexpr (PARITY || HK) {
+  if constexpr (PARITY) {
 #pragma unroll
     for (int k = 0; k < 4; k++) s.dforce[k] = rf[SF_DFORCE + k];
   }
@@ -812,9 +812,14 @@ AGF_DEV void state_store(const VState<P, PARITY, UWB, HK>& s, const StateArrays<
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     rf[SF_CMD + k] = s.cmd[k]; rf[SF_RADIO + k] = s.radio_f[k]; rf[SF_KATT + k] = s.katt[k];
-    // fast variant without housekeeping: the commanded force is not carried, it is the mixer's thrust<->speed map inverted
-    if constexpr (PARITY || HK) rf[SF_DFORCE + k] = s.dforce[k];
+    // fast variants: the commanded force is not carried, it is the mixer's thrust<->speed map inverted (times the
+    // calibration correction, below, with housekeeping)
+    if constexpr (PARITY) rf[SF_DFORCE + k] = s.dforce[k];
     else rf[SF_DFORCE + k] = mix_kf * s.cmd[k] * s.cmd[k];
+  }
+  if constexpr (!PARITY && HK) {
+    const float4 c4 = sq_load(sc, (UWB ? SQ_PC_UWB : SQ_PC_NOUWB) + SQ_PC_CORR);
+    rf[SF_DFORCE] *= c4.x; rf[SF_DFORCE + 1] *= c4.y; rf[SF_DFORCE + 2] *= c4.z; rf[SF_DFORCE + 3] *= c4.w;
   }
   if constexpr (PARITY) {
 #pragma unroll
@@ -1423,7 +1428,7 @@ AGF_DEV void ctl_mix(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const Log
     } else {
       f[i] = ::fminf(::fmaxf(f[i], k.min_thrust), k.max_thrust);
     }
-    if constexpr (PARITY || HK) s.dforce[i] = f[i];
+    if constexpr (PARITY) s.dforce[i] = f[i];
     if constexpr (PARITY) {
       const float corr = HK ? s.pc_corr[i] : 1.0f;
       s.cmd[i] = f[i] <= 0 ? 0.0f : ::sqrtf(fdiv<PARITY>(f[i], corr * k.mix_kf));
@@ -2427,7 +2432,7 @@ AGF_DEV void logic_run(VState<P, PARITY, UWB, HK>& s, const Scratch& sc, const S
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       s.cmd[i] = 0;
-      if constexpr (PARITY || HK) s.dforce[i] = 0;
+      if constexpr (PARITY) s.dforce[i] = 0;
     }
   }
   if constexpr (HK) {  // propeller calibration, rates mode only (:553-587)
