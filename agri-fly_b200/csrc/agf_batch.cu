@@ -644,6 +644,7 @@ struct BatchImpl : Batch {
   std::vector<PackedPlan> h_plans;
   PackedPlan* d_plans = nullptr;
   uint32_t plans_cap = 0;
+  uint32_t off_period_us = 0;  // periodOffboardMainLoop of the loop that was set (sizes the estimator's prediction pipe)
   double* d_off_est = nullptr;  // estimator state, est_doubles(n) values blocked by warp (agf_types.h est_index)
   double* d_off_state = nullptr;  // [AGF_OFFSTATE_DOUBLES][n]
   double* d_off_traj = nullptr;   // [AGF_OFFTRAJ_DOUBLES][n]
@@ -973,6 +974,7 @@ struct BatchImpl : Batch {
     TimingConsts tc = sh.tc;
     const char* why = fill_offboard(*cfg, off, tc);
     if (why) return fail(AGF_EINVAL, why);
+    off_period_us = cfg->period_us;
     cudaFree(d_off_targets);
     d_off_targets = nullptr;
     AGF_CUDA(cudaMalloc(&d_off_targets, n_targets * sizeof(agf_offboard_target)));
@@ -1072,6 +1074,16 @@ struct BatchImpl : Batch {
     if (e->kind != AGF_OFFEST_MOCAP) return fail(AGF_EINVAL, "unknown estimator kind");
     if (!(e->mocap_period_us > 0) || !(e->angvel_time_const > 0) || !(e->prediction_delay >= 0))
       return fail(AGF_EINVAL, "estimator: mocap period and angular-velocity time constant must be positive");
+    {
+      // The reference's PredictionPipe is unbounded; here it has AGF_OFFEST_PIPE slots.  In flight at most: the messages that
+      // become active within the prediction delay, those added between two mocap packets, the active one and the newest.
+      const uint64_t per = off_period_us ? off_period_us : 1;
+      const uint64_t delay_us = uint64_t(e->prediction_delay * 1e6 + 0.5);
+      const uint64_t need = (delay_us + per - 1) / per + (uint64_t(e->mocap_period_us) + per - 1) / per + 2;
+      if (need > uint64_t(AGF_OFFEST_PIPE))
+        return fail(AGF_EUNSUPPORTED, "estimator: ceil(prediction_delay / loop period) + ceil(mocap period / loop period) + 2 prediction "
+                                      "messages in flight exceed AGF_OFFEST_PIPE");
+    }
     // MocapStateEstimator::MocapStateEstimator -> Reset() (MocapStateEstimator.cpp:9-50) for every vehicle
     std::vector<double> h(est_doubles(n), 0.0);
     for (size_t i = 0; i < n; i++) {

@@ -445,7 +445,8 @@ int agf_batch_get_offboard_state(agf_batch* b, double* out, size_t first, size_t
  * angular velocity for the position and attitude increments); after each command SetPredictedValues(cmdAngVel,
  * att * e3 * cmdThrust - g) queues it with the pipe's delay. */
 enum { AGF_OFFEST_TRUTH = 0, AGF_OFFEST_MOCAP = 1 };
-#define AGF_OFFEST_PIPE 8 /* prediction messages kept per vehicle (steady state: delay / period + 2) */
+#define AGF_OFFEST_PIPE 8 /* prediction messages kept per vehicle; agf_batch_set_offboard_estimator returns AGF_EUNSUPPORTED when
+                            ceil(prediction_delay / loop period) + ceil(mocap period / loop period) + 2 exceeds it (the reference's pipe is unbounded) */
 typedef struct agf_offboard_estimator {
   int32_t kind;             /* AGF_OFFEST_* */
   uint32_t mocap_period_us; /* periodMocapSystem, main.cpp:174: 5000 */

@@ -350,6 +350,20 @@ def test_flight_stages_on_the_gpu_match_the_unmodified_ros_state_machine(agf, ca
     b.close()
 
 
+def test_offboard_estimator_refuses_a_pipe_that_cannot_hold_the_messages(agf):
+    """The reference's PredictionPipe is unbounded, the device one has AGF_OFFEST_PIPE slots: a configuration whose messages
+    in flight would not fit is refused (AGF_EUNSUPPORTED) instead of silently dropping the oldest ones."""
+    sc = agf.scenarios.offboard_scenario(100)
+    b = make_batch_offboard(agf, sc, n=4)
+    b.set_offboard_estimator(agf.offboard_estimator())                      # Rappids_Simulator's 30 ms / 5 ms / 10 ms: fits
+    for kw in (dict(prediction_delay=0.2), dict(mocap_period_us=80000)):
+        with pytest.raises(agf.AgfError) as ei:
+            b.set_offboard_estimator(agf.offboard_estimator(**kw))
+        assert ei.value.code == agf.abi.EUNSUPPORTED
+    b.run(50)   # the accepted configuration is still in place
+    b.close()
+
+
 def test_offboard_estimator_fast_variants(agf, checker_glibc):
     """Fast FP64 / FP32 kernels with the estimator in the loop: position within the offboard loop's stated tolerance of the
     oracle (1e-3 / 5e-3 relative), estimate within 2 cm of the truth, for a population on the balanced schedule too."""
