@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #include "agf_math.h"
@@ -29,6 +30,9 @@ namespace agfr {
 // the per-candidate pieces (primitive generation, feasibility tests, pyramid geometry) run once per candidate or pyramid,
 // lane parallel, and are a small share of the executed instructions but most of the kernel's code when inlined at every
 // call site; as real calls the kernel is 122 KB instead of 155 KB and 1.2 % faster (AGFR_COLD_CALLS=0 inlines them again)
+#ifndef AGFR_PHASE_CLOCKS
+#define AGFR_PHASE_CLOCKS 0  // tuning builds: per-phase clock64() totals of a few warps, printed at the end of the kernel
+#endif
 #ifndef AGFR_COLD_CALLS
 #define AGFR_COLD_CALLS 1
 #endif
@@ -376,6 +380,9 @@ struct WarpCtx {
   int npyr;
   int capHit;  // a candidate needed a new pyramid when max_pyramids already existed (it was rejected, DepthImagePlanner.cpp:246-249)
   int lane;
+#if AGFR_PHASE_CLOCKS
+  unsigned long long* clk;  // [0] candidates [1] expansion [2] shrink [3] collision test outside inflate [4] initial rectangle
+#endif
 };
 
 AGFR_DEV unsigned ld16(const uint16_t* p) { return (unsigned)__ldg(p); }
@@ -672,6 +679,9 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     right = min(W - edgeOff - 1, x0 + initR);
     left = right - 2 * initR;
   }
+#if AGFR_PHASE_CLOCKS
+  long long c0_ = clock64();
+#endif
   // the initial rectangle must be free (:509-517; order independent)
   {
     bool bad = false;
@@ -685,6 +695,9 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
       }
     if (__any_sync(AGFR_FULL, bad)) return false;
   }
+#if AGFR_PHASE_CLOCKS
+  { long long c1_ = clock64(); w.clk[4] += c1_ - c0_; c0_ = c1_; }
+#endif
   // spiral expansion (:519-599)
   int maxDepth = 65535;
   bool rf = true, tf = true, lf = true, bf = true;
@@ -734,6 +747,9 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
       }
     }
   }
+#if AGFR_PHASE_CLOCKS
+  { long long c1_ = clock64(); w.clk[1] += c1_ - c0_; c0_ = c1_; }
+#endif
   // shrink by the projected vehicle radius (:601-939)
   Shrink s;
   s.rS = W - 1 - edgeOff;
@@ -768,6 +784,9 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     if (r == R_LEFT && s.lS + kBuf > s.rS - kBuf) return false;
     if (r == R_BOTTOM && s.tS + kBuf > s.bS - kBuf) return false;
   }
+#if AGFR_PHASE_CLOCKS
+  w.clk[2] += clock64() - c0_;
+#endif
   outDepth = maxDepth * P.scale - P.rPlan;
   outEdge = make_int4(s.rS, s.tS, s.lS, s.bS);
   return true;
@@ -957,6 +976,12 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
   w.lane = lane;
   w.pdepth = s_depth[wid];
   w.pedge = s_edge[wid];
+#if AGFR_PHASE_CLOCKS
+  unsigned long long clk[6] = {0, 0, 0, 0, 0, 0};
+  w.clk = clk;
+  const long long cstart_ = clock64();
+  int nplans_ = 0;
+#endif
   for (;;) {
     int v = 0;
     if (lane == 0) v = atomicAdd(P.next, 1);
@@ -988,7 +1013,13 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
 #pragma unroll
       for (int a = 0; a < 3; a++) bestQ.c[k][a] = 0;
 
+#if AGFR_PHASE_CLOCKS
+    nplans_++;
+#endif
     for (int i0 = 0; i0 < P.k; i0 += 32) {
+#if AGFR_PHASE_CLOCKS
+      const long long cc0_ = clock64();
+#endif
       const int i = i0 + lane;
       const bool valid = i < P.k;
       double goal[3] = {0, 0, 1}, T = 1;
@@ -1019,6 +1050,9 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
       }
       unsigned pend = __ballot_sync(AGFR_FULL, low0);
       unsigned flag = 0;
+#if AGFR_PHASE_CLOCKS
+      clk[0] += clock64() - cc0_;
+#endif
       while (pend) {
         const int src = __ffs(pend) - 1;
         pend &= pend - 1;
@@ -1050,7 +1084,15 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
               Q.c[4][a] = ax.vel(0.0);
               Q.c[5][a] = ax.pos(0.0);
             }
+#if AGFR_PHASE_CLOCKS
+            const long long cf0_ = clock64();
+            const unsigned long long in0_ = clk[1] + clk[2] + clk[4];
+            const bool cfree_ = collision_free<PARITY>(P, w, Q, Ts);
+            clk[3] += (clock64() - cf0_) - (clk[1] + clk[2] + clk[4] - in0_);
+            if (cfree_) {
+#else
             if (collision_free<PARITY>(P, w, Q, Ts)) {
+#endif
               f |= 8;
               found = 1;
               best = csrc;
@@ -1117,6 +1159,10 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
     }
     __syncwarp();
   }
+#if AGFR_PHASE_CLOCKS
+  if (lane == 0 && wid == 0 && blockIdx.x % 97 == 0)
+    printf("phase cycles block %d: plans %d total %lld | candidates %llu  initial-rect %llu  expansion %llu  shrink %llu  collision-test %llu\n", blockIdx.x, nplans_, clock64() - cstart_, clk[0], clk[4], clk[1], clk[2], clk[3]);
+#endif
 }
 
 }  // namespace agfr
