@@ -205,6 +205,7 @@ struct Handle {
   }
   double *state = nullptr, *cands = nullptr, *pyr = nullptr, *stats = nullptr, *prims = nullptr;
   uint8_t* flags = nullptr;
+  double* ccost = nullptr;  // candidate pass -> planning pass (agf_rappids_plan.cuh)
   agf_rappids_result* results = nullptr;
   int* next = nullptr;
   void* stage = nullptr;  // device staging for scene descriptions
@@ -248,6 +249,7 @@ struct Handle {
     cudaFree(pyr);
     cudaFree(stats);
     cudaFree(flags);
+    cudaFree(ccost);
     cudaFree(results);
     cudaFree(next);
     cudaFree(stage);
@@ -381,6 +383,7 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   AGFR_ALLOC(h->state, n * 12 * sizeof(double));
   AGFR_ALLOC(h->cands, n * (size_t)h->kcap * 4 * sizeof(double));
   AGFR_ALLOC(h->flags, n * (size_t)h->kcap);
+  AGFR_ALLOC(h->ccost, n * (size_t)h->kcap * sizeof(double));
   AGFR_ALLOC(h->results, n * sizeof(agf_rappids_result));
   AGFR_ALLOC(h->pyr, n * (size_t)AGF_RAPPIDS_MAX_PYRAMIDS * AGF_RAPPIDS_PYRAMID_DOUBLES * sizeof(double));
   AGFR_ALLOC(h->stats, 8 * sizeof(double));
@@ -568,6 +571,7 @@ int agf_rappids_plan(agf_rappids* p) {
   P.state = h->state;
   P.cands = h->cands;
   P.flags = h->flags;
+  P.ccost = h->ccost;
   P.results = h->results;
   P.pyramids = h->pyr;
   P.prims = h->prims;
@@ -613,7 +617,7 @@ int agf_rappids_plan(agf_rappids* p) {
                                               : agfr::launch_plan_fast(P, h->grid, h->stream);
   if (e != cudaSuccess) return fail(AGF_ECUDA, "planner kernel launch", e);
   AGFR_CUDA(cudaEventRecord(ev.second, h->stream));
-  h->launches += 1;
+  h->launches += 2;
   return AGF_OK;
 }
 

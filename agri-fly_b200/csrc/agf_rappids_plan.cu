@@ -19,6 +19,14 @@ namespace agfr {
 #endif
 
 cudaError_t AGFR_LAUNCH(const PlanParams& P, int grid, cudaStream_t stream) {
+  // candidate pass: one thread per candidate
+  const size_t total = (size_t)P.n * (size_t)P.k;
+  const size_t cap = (size_t)148 * 64;
+  const int cgrid = (int)((total + 127) / 128 < cap ? (total + 127) / 128 : cap);
+  rappids_candidates_kernel<AGF_RAPPIDS_PARITY != 0><<<cgrid, 128, 0, stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // planning pass: one warp per vehicle, one resident wave
   rappids_plan_kernel<AGF_RAPPIDS_PARITY != 0><<<grid, kBlock, 0, stream>>>(P);
   return cudaGetLastError();
 }

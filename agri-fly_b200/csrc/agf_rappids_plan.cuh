@@ -48,12 +48,13 @@ namespace agfr {
 constexpr int kBlock = 128;           // 4 warps = 4 vehicles per CTA
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxPyr = 32;
-// CTAs per SM the register allocation aims at (tuning: profiles/r1_rappids2.sh; 5 measured best for the fast variant)
+// CTAs per SM the register allocation aims at (round 1, fused kernel: 5 measured best; the planning pass alone, without the
+// candidates' primitive in registers: 5 / 6 / 8 / 10 / 12 -> 74.8 / 73.2 / 70.5 / 69.6 / 71.6 ms, profiles/r2/rappids_variants_split.log)
 #ifndef AGFR_MIN_BLOCKS
 #if defined(AGF_RAPPIDS_PARITY) && AGF_RAPPIDS_PARITY
 #define AGFR_MIN_BLOCKS 3
 #else
-#define AGFR_MIN_BLOCKS 5
+#define AGFR_MIN_BLOCKS 8
 #endif
 #endif
 constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
@@ -66,7 +67,8 @@ struct PlanParams {
   const uint16_t* gminC;  // [n][W][GH] the same per column
   const double* state;    // [n][12]: vel0, acc0, grav, cost vector
   const double* cands;    // [n][kcap][4]
-  uint8_t* flags;         // [n][kcap]
+  uint8_t* flags;         // [n][kcap]: the candidate pass leaves its verdict code here, the planning pass replaces it by the flags
+  double* ccost;          // [n][kcap]: cost of every candidate (candidate pass -> planning pass)
   void* results;          // agf_rappids_result [n]
   double* pyramids;       // [n][kMaxPyr][17]
   double* prims;          // [n][9]: alpha, beta, gamma of the returned primitive per axis (SingleAxisTrajectory state), or null
@@ -965,8 +967,57 @@ __device__ __noinline__ bool collision_free(const PlanParams& P, WarpCtx& w, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel: one warp per vehicle, vehicles handed out through a counter
+// The kernels.  A planner call is two launches:
+//   rappids_candidates_kernel  one THREAD per candidate: motion primitive, cost, and the recursive input-feasibility and
+//                              velocity tests (RapidTrajectoryGenerator.cpp:75-205).  All of it is a pure function of the
+//                              candidate and the vehicle's state, so it is evaluated for every candidate up front, all 32
+//                              lanes busy, and leaves 9 bytes per candidate (cost, verdict code).
+//   rappids_plan_kernel        one WARP per vehicle, vehicles handed out through a counter: the reference's sequential loop
+//                              (DepthImagePlanner.cpp:91-214) over the precomputed costs / verdicts -- pruning against the best
+//                              collision-free cost so far, the counters, and the collision test with its pyramids.
+// Until round 2 both lived in one kernel (the tests ran speculatively for the lanes that beat the best cost at the start of
+// a batch of 32).  Split, the planning kernel no longer carries the 100 KB of FP64 feasibility code next to InflatePyramid's
+// scans (instruction fetch was a top stall) nor the primitive's registers across the collision test.
 // ---------------------------------------------------------------------------------------------
+enum { CODE_IN_MASK = 7, CODE_VEL_OK = 8 };  // verdict code: input-feasibility result | velocity test passed
+
+template<bool PARITY>
+__global__ void __launch_bounds__(128) rappids_candidates_kernel(const __grid_constant__ PlanParams P) {
+  const size_t total = (size_t)P.n * (size_t)P.k;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = idx / (size_t)P.k;
+    const int i = (int)(idx - v * (size_t)P.k);
+    const double* st = P.state + v * 12;
+    Prim pr;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      pr.ax[a].v0 = __ldg(st + a);
+      pr.ax[a].a0 = __ldg(st + 3 + a);
+      pr.g[a] = __ldg(st + 6 + a);
+    }
+    const double cv0 = __ldg(st + 9), cv1 = __ldg(st + 10), cv2 = __ldg(st + 11);
+    const double4 c4 = *reinterpret_cast<const double4*>(P.cands + (v * P.kcap + i) * 4);
+    const double T = c4.w;
+    pr.tf = T;
+    pr.ax[0].generate(c4.x, T);
+    pr.ax[1].generate(c4.y, T);
+    pr.ax[2].generate(c4.z, T);
+    const double pe0 = pr.ax[0].pos(T), pe1 = pr.ax[1].pos(T), pe2 = pr.ax[2].pos(T);
+    double cost;
+    if (P.costKind == 0) {
+      cost = -(cv0 * pe0 + cv1 * pe1 + cv2 * pe2) / T;
+    } else {
+      const double sg = sqrt((cv0 - 0) * (cv0 - 0) + (cv1 - 0) * (cv1 - 0) + (cv2 - 0) * (cv2 - 0));
+      const double dx = cv0 - pe0, dy = cv1 - pe1, dz = cv2 - pe2;
+      cost = -(sg - sqrt(dx * dx + dy * dy + dz * dz)) / T;
+    }
+    int code = pr.input_feasibility(P);
+    if (code == IN_FEASIBLE && pr.template velocity_feasibility<PARITY>(P.vmax) == 0) code |= CODE_VEL_OK;
+    P.ccost[v * P.kcap + i] = cost;
+    P.flags[v * P.kcap + i] = (uint8_t)code;
+  }
+}
+
 template<bool PARITY>
 __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(const __grid_constant__ PlanParams P) {
   __shared__ double s_depth[kWarps][kMaxPyr + 1];
@@ -994,24 +1045,10 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
     w.npyr = 0;
     w.capHit = 0;
     const double* st = P.state + (size_t)v * 12;
-    Prim pr;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      pr.ax[a].v0 = __ldg(st + a);
-      pr.ax[a].a0 = __ldg(st + 3 + a);
-      pr.g[a] = __ldg(st + 6 + a);
-    }
-    const double cv0 = __ldg(st + 9), cv1 = __ldg(st + 10), cv2 = __ldg(st + 11);
-    const double sg = sqrt((cv0 - 0) * (cv0 - 0) + (cv1 - 0) * (cv1 - 0) + (cv2 - 0) * (cv2 - 0));
 
     double best = DBL_MAX;
     int found = 0, bestIdx = -1, nCost = 0, nColl = 0, nVel = 0, nFree = 0;
-    Poly bestQ;
     double bestT = 0;
-#pragma unroll
-    for (int k = 0; k < 6; k++)
-#pragma unroll
-      for (int a = 0; a < 3; a++) bestQ.c[k][a] = 0;
 
 #if AGFR_PHASE_CLOCKS
     nplans_++;
@@ -1022,33 +1059,14 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
 #endif
       const int i = i0 + lane;
       const bool valid = i < P.k;
-      double goal[3] = {0, 0, 1}, T = 1;
+      double cost = DBL_MAX;
+      int code = 0;
       if (valid) {
-        const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + i) * 4);
-        goal[0] = c4.x;
-        goal[1] = c4.y;
-        goal[2] = c4.z;
-        T = c4.w;
+        cost = P.ccost[(size_t)v * P.kcap + i];
+        code = P.flags[(size_t)v * P.kcap + i];
       }
-      pr.tf = T;
-#pragma unroll
-      for (int a = 0; a < 3; a++) pr.ax[a].generate(goal[a], T);
-      const double pe0 = pr.ax[0].pos(T), pe1 = pr.ax[1].pos(T), pe2 = pr.ax[2].pos(T);
-      double cost;
-      if (P.costKind == 0) {
-        cost = -(cv0 * pe0 + cv1 * pe1 + cv2 * pe2) / T;
-      } else {
-        const double dx = cv0 - pe0, dy = cv1 - pe1, dz = cv2 - pe2;
-        cost = -(sg - sqrt(dx * dx + dy * dy + dz * dz)) / T;
-      }
-      // speculative feasibility for the lanes that beat the best cost so far (it can only get lower)
-      const bool low0 = valid && cost < best;
-      int inRes = -2, velRes = -2;
-      if (low0) {
-        inRes = pr.input_feasibility(P);
-        if (inRes == IN_FEASIBLE) velRes = pr.template velocity_feasibility<PARITY>(P.vmax);
-      }
-      unsigned pend = __ballot_sync(AGFR_FULL, low0);
+      // the lanes that beat the best cost at the start of the batch (it can only get lower)
+      unsigned pend = __ballot_sync(AGFR_FULL, valid && cost < best);
       unsigned flag = 0;
 #if AGFR_PHASE_CLOCKS
       clk[0] += clock64() - cc0_;
@@ -1060,26 +1078,27 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
         if (!(csrc < best)) continue;
         unsigned f = 1;  // LowCost
         nCost++;
-        const int ir = __shfl_sync(AGFR_FULL, inRes, src), vr = __shfl_sync(AGFR_FULL, velRes, src);
-        if (ir == IN_FEASIBLE) {
+        const int cs = __shfl_sync(AGFR_FULL, code, src);
+        if ((cs & CODE_IN_MASK) == IN_FEASIBLE) {
           f |= 2;
           nColl++;
-          if (vr == 0) {
+          if (cs & CODE_VEL_OK) {
             f |= 4;
             nVel++;
+            // the survivor's primitive again (same routine, same inputs as the candidate pass), warp-uniform
             Poly Q;
-            const double Ts = __shfl_sync(AGFR_FULL, T, src);
+            const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + i0 + src) * 4);
+            const double goal[3] = {c4.x, c4.y, c4.z};
+            const double Ts = c4.w;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
-              const double al = __shfl_sync(AGFR_FULL, pr.ax[a].al, src), be = __shfl_sync(AGFR_FULL, pr.ax[a].be, src),
-                           ga = __shfl_sync(AGFR_FULL, pr.ax[a].ga, src);
-              Axis ax = pr.ax[a];  // v0, a0 are the vehicle's
-              ax.al = al;
-              ax.be = be;
-              ax.ga = ga;
-              Q.c[0][a] = al / 120;
-              Q.c[1][a] = be / 24;
-              Q.c[2][a] = ga / 6;
+              Axis ax;
+              ax.v0 = __ldg(st + a);
+              ax.a0 = __ldg(st + 3 + a);
+              ax.generate(goal[a], Ts);
+              Q.c[0][a] = ax.al / 120;
+              Q.c[1][a] = ax.be / 24;
+              Q.c[2][a] = ax.ga / 6;
               Q.c[3][a] = ax.acc(0.0) / 2;
               Q.c[4][a] = ax.vel(0.0);
               Q.c[5][a] = ax.pos(0.0);
@@ -1098,7 +1117,6 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
               best = csrc;
               nFree++;
               bestIdx = i0 + src;
-              bestQ = Q;
               bestT = Ts;
             }
           }
@@ -1123,23 +1141,29 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
       out->pyramid_cap_hit = w.capHit;
       out->reserved_ = 0;
     }
-    if (lane < 18) out->best_coeffs[lane] = bestQ.c[lane / 3][lane % 3];
-    if (P.prims) {  // the returned primitive in the generator's own variables: regenerated (same code, same inputs) rather than
-                    // carried through the candidate loop in registers
-      double abg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      if (found) {
+    {  // the returned primitive -- polynomial coefficients, and the generator's own variables for the tracking loop --
+       // regenerated from the winning candidate (same routine, same inputs) rather than carried through the candidate loop:
+       // lane 3k+a holds coefficient k of axis a
+      const int a = lane % 3, kq = lane / 3;
+      double coef = 0, al = 0, be = 0, ga = 0;
+      if (found && lane < 18) {
         const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + bestIdx) * 4);
-        const double goal[3] = {c4.x, c4.y, c4.z};
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-          pr.ax[a].generate(goal[a], c4.w);
-          abg[3 * a] = pr.ax[a].al;
-          abg[3 * a + 1] = pr.ax[a].be;
-          abg[3 * a + 2] = pr.ax[a].ga;
-        }
+        const double goal = a == 0 ? c4.x : (a == 1 ? c4.y : c4.z);
+        Axis ax;
+        ax.v0 = __ldg(st + a);
+        ax.a0 = __ldg(st + 3 + a);
+        ax.generate(goal, c4.w);
+        al = ax.al;
+        be = ax.be;
+        ga = ax.ga;
+        coef = kq == 0 ? al / 120 : kq == 1 ? be / 24 : kq == 2 ? ga / 6 : kq == 3 ? ax.acc(0.0) / 2 : kq == 4 ? ax.vel(0.0) : ax.pos(0.0);
       }
-      if (lane == 0)
-        for (int q = 0; q < 9; q++) P.prims[(size_t)v * 9 + q] = abg[q];
+      if (lane < 18) out->best_coeffs[lane] = coef;
+      if (P.prims && lane < 3) {
+        P.prims[(size_t)v * 9 + 3 * lane] = al;
+        P.prims[(size_t)v * 9 + 3 * lane + 1] = be;
+        P.prims[(size_t)v * 9 + 3 * lane + 2] = ga;
+      }
     }
     {
       double* rec = P.pyramids + ((size_t)v * kMaxPyr + lane) * 17;
