@@ -562,6 +562,17 @@ class Rappids:
     def sync(self):
         _check(lib().agf_rappids_sync(self._h))
 
+    def set_dispatch(self, by_last_work=True):
+        """Dispatch order of the planning pass: by the previous plan's work per vehicle (default) or index order."""
+        _check(lib().agf_rappids_set_dispatch(self._h, 1 if by_last_work else 0))
+
+    def plan_work(self, first=0, count=None):
+        """Device clock cycles the last plan spent on each vehicle."""
+        count = self._cnt(first, count)
+        out = np.zeros(count, dtype=np.uint32)
+        _check(lib().agf_rappids_get_plan_work(self._h, out.ctypes.data, first, count))
+        return out
+
     def results(self, first=0, count=None):
         count = self._cnt(first, count)
         out = np.zeros(count, dtype=RESULT_DTYPE)

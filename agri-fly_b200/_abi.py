@@ -197,6 +197,8 @@ PROTOTYPES = {
     "agf_rappids_reduce_stats_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "agf_rappids_plan_kernel_time": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_uint64)]),
     "agf_rappids_launch_count": (C.c_uint64, [C.c_void_p]),
+    "agf_rappids_set_dispatch": (C.c_int, [C.c_void_p, C.c_int32]),
+    "agf_rappids_get_plan_work": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "agf_quad_type_from_id": (C.c_int, [C.c_uint]),
     "agf_logic_consts_from_type": (C.c_int, [C.c_int, _P(LogicConsts)]),
     "agf_vehicle_cfg_from_type": (C.c_int, [C.c_int, C.c_int, _P(VehicleCfg)]),

@@ -41,7 +41,7 @@ static_assert(AGF_RAPPIDS_MAX_PYRAMIDS == agfr::kMaxPyr, "pyramid capacity");
 // thread index running along the contiguous dimension of the destination in both cases
 template<bool T>
 __global__ void render_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ row_bg,
-                              const int32_t* __restrict__ boxes, int W, int H, size_t count) {
+                              const int32_t* __restrict__ boxes, int W, int H, size_t count, size_t vstride) {
   const size_t npix = (size_t)W * H;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count * npix;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -56,16 +56,16 @@ __global__ void render_kernel(uint16_t* __restrict__ dst, const uint16_t* __rest
       const int x0 = b[5 * k], x1 = b[5 * k + 1], y0 = b[5 * k + 2], y1 = b[5 * k + 3], bv = b[5 * k + 4];
       if (bv > 0 && x >= x0 && x < x1 && y >= y0 && y < y1) val = min(val, (unsigned)bv);
     }
-    dst[idx] = (uint16_t)val;
+    dst[v * vstride + r] = (uint16_t)val;
   }
 }
 
-// [count][H][W] -> [count][W][H] through 32x32 shared-memory tiles (both sides coalesced)
-__global__ void transpose_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ src, int W, int H) {
+// [H][W] -> [W][H] of every vehicle's scene record through 32x32 shared-memory tiles (both sides coalesced)
+__global__ void transpose_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ src, int W, int H, size_t vstride) {
   __shared__ uint16_t tile[32][34];
   const size_t v = blockIdx.z;
-  const uint16_t* s = src + v * (size_t)W * H;
-  uint16_t* d = dst + v * (size_t)W * H;
+  const uint16_t* s = src + v * vstride;
+  uint16_t* d = dst + v * vstride;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int x = bx + threadIdx.x, y = by + j;
@@ -78,23 +78,57 @@ __global__ void transpose_kernel(uint16_t* __restrict__ dst, const uint16_t* __r
   }
 }
 
-// Minimum of every group of 32 consecutive pixels of every line of `plane` ([lines][pitch]); pixels <= ignore count as
-// 65535 (they are never "seen" by the planner, DepthImagePlanner.cpp:506).  One thread per (line, group).
-__global__ void groupmin_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ plane, int pitch, int G, size_t lines,
-                                int ignore) {
+// Minimum of every group of 32 consecutive pixels of every line of `plane` ([L lines][pitch] per vehicle, vehicles `vstride`
+// apart in both the plane and the table); pixels <= ignore count as 65535 (they are never "seen" by the planner,
+// DepthImagePlanner.cpp:506).  One thread per (line, group).
+__global__ void groupmin_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ plane, int pitch, int G, int L, size_t lines,
+                                int ignore, size_t vstride) {
   const size_t total = lines * (size_t)G;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t line = idx / G;
     const int g = (int)(idx - line * G);
-    const uint16_t* src = plane + line * pitch + (size_t)g * 32;
+    const size_t v = line / L;
+    const int l = (int)(line - v * L);
+    const uint16_t* src = plane + v * vstride + (size_t)l * pitch + (size_t)g * 32;
     const int cnt = min(32, pitch - g * 32);
     unsigned m = 65535u;
     for (int k = 0; k < cnt; k++) {
       const unsigned p = src[k];
       if ((int)p > ignore) m = min(m, p);
     }
-    out[idx] = (uint16_t)m;
+    out[v * vstride + (size_t)l * G + g] = (uint16_t)m;
   }
+}
+
+// Dispatch order of the planning pass: vehicles by DESCENDING work of their previous plan (clock cycles, written by the
+// planning kernel), 2048 linear buckets, one block.  Plans differ in length by an order of magnitude (pyramids inflated);
+// handed out in index order the launch ends with a tail in which a few warps finish long plans on an otherwise empty GPU
+// (ncu, round 2: SMs active 42 % of a 16 384-plan launch), and a planner runs at image rate on scenes that change little
+// between frames, so the last frame's work is a good forecast.  Only the order changes -- results do not depend on it.
+__global__ void __launch_bounds__(1024) dispatch_order_kernel(const unsigned* __restrict__ work, int n, int* __restrict__ order) {
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned wmax;
+  const int t = threadIdx.x;
+  if (t == 0) wmax = 1;
+  for (int i = t; i < 2048; i += 1024) hist[i] = 0;
+  __syncthreads();
+  unsigned m = 0;
+  for (int v = t; v < n; v += 1024) m = max(m, work[v]);
+  atomicMax(&wmax, m);
+  __syncthreads();
+  const unsigned long long mx = wmax;
+  for (int v = t; v < n; v += 1024) atomicAdd(&hist[2047 - (unsigned)((unsigned long long)work[v] * 2047ull / mx)], 1u);
+  __syncthreads();
+  if (t == 0) {
+    unsigned acc = 0;
+    for (int i = 0; i < 2048; i++) {
+      const unsigned c = hist[i];
+      hist[i] = acc;
+      acc += c;
+    }
+  }
+  __syncthreads();
+  for (int v = t; v < n; v += 1024) order[atomicAdd(&hist[2047 - (unsigned)((unsigned long long)work[v] * 2047ull / mx)], 1u)] = v;
 }
 
 // agf_rappids_export_tracking_primitives: one thread per vehicle, field-major destination
@@ -188,8 +222,13 @@ struct Handle {
   int kcap = 0, k = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  uint16_t *img = nullptr, *imgT = nullptr;
-  uint16_t *gminR = nullptr, *gminC = nullptr;  // group minima of the rows / columns (agf_rappids_plan.cuh)
+  // One SCENE RECORD per vehicle: image [H][W] | transposed image [W][H] | group minima of the rows [H][GW] | of the columns
+  // [W][GH] (agf_rappids_plan.cuh), records `vstride` elements apart in one allocation.  A planning warp works on one vehicle
+  // at a time and touches all four planes; as four population-wide arrays they lay on four different 2 MB pages per warp.
+  uint16_t* scene = nullptr;
+  size_t vstride = 0;  // in uint16 elements, a multiple of 64 (128 bytes)
+  uint16_t *img = nullptr, *imgT = nullptr;     // = scene + plane offset; vehicle v's plane starts at + v * vstride
+  uint16_t *gminR = nullptr, *gminC = nullptr;
   int GW() const { return (cfg.width + 31) / 32; }
   int GH() const { return (cfg.height + 31) / 32; }
   int ignore_value() const { return (int)(uint16_t)(cfg.true_radius / cfg.depth_scale); }
@@ -198,8 +237,8 @@ struct Handle {
     const size_t tr = count * (size_t)H * GW(), tc = count * (size_t)W * GH();
     const int gr = (int)((tr + 255) / 256 < 148 * 16 ? (tr + 255) / 256 : 148 * 16);
     const int gc = (int)((tc + 255) / 256 < 148 * 16 ? (tc + 255) / 256 : 148 * 16);
-    groupmin_kernel<<<gr, 256, 0, stream>>>(gminR + first * (size_t)H * GW(), img + first * npix(), W, GW(), count * (size_t)H, ignore_value());
-    groupmin_kernel<<<gc, 256, 0, stream>>>(gminC + first * (size_t)W * GH(), imgT + first * npix(), H, GH(), count * (size_t)W, ignore_value());
+    groupmin_kernel<<<gr, 256, 0, stream>>>(gminR + first * vstride, img + first * vstride, W, GW(), H, count * (size_t)H, ignore_value(), vstride);
+    groupmin_kernel<<<gc, 256, 0, stream>>>(gminC + first * vstride, imgT + first * vstride, H, GH(), W, count * (size_t)W, ignore_value(), vstride);
     launches += 2;
     return cudaGetLastError() == cudaSuccess ? AGF_OK : AGF_ECUDA;
   }
@@ -208,6 +247,10 @@ struct Handle {
   double* ccost = nullptr;  // candidate pass -> planning pass (agf_rappids_plan.cuh)
   agf_rappids_result* results = nullptr;
   int* next = nullptr;
+  int* order = nullptr;      // dispatch order of the planning pass (dispatch_order_kernel)
+  unsigned* work = nullptr;  // cycles per vehicle of the last plan
+  bool have_work = false;
+  int dispatch = 1;          // 1: by the previous plan's work (default), 0: index order
   void* stage = nullptr;  // device staging for scene descriptions
   size_t stage_bytes = 0;
   int grid = 0, regs = 0, blocks_per_sm = 0;
@@ -239,11 +282,8 @@ struct Handle {
       cudaEventDestroy(e.first);
       cudaEventDestroy(e.second);
     }
-    cudaFree(img);
-    cudaFree(imgT);
-    cudaFree(gminR);
+    cudaFree(scene);
     cudaFree(prims);
-    cudaFree(gminC);
     cudaFree(state);
     cudaFree(cands);
     cudaFree(pyr);
@@ -252,6 +292,8 @@ struct Handle {
     cudaFree(ccost);
     cudaFree(results);
     cudaFree(next);
+    cudaFree(order);
+    cudaFree(work);
     cudaFree(stage);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -275,7 +317,7 @@ struct Handle {
     while (done < count) {  // gridDim.z <= 65535
       const size_t c = count - done < 32768 ? count - done : 32768;
       dim3 g((W + 31) / 32, (H + 31) / 32, (unsigned)c), b(32, 8);
-      transpose_kernel<<<g, b, 0, stream>>>(imgT + (first + done) * npix(), img + (first + done) * npix(), W, H);
+      transpose_kernel<<<g, b, 0, stream>>>(imgT + (first + done) * vstride, img + (first + done) * vstride, W, H, vstride);
       done += c;
     }
     AGFR_CUDA(cudaGetLastError());
@@ -376,10 +418,13 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
     delete h;
     return fail(AGF_ECUDA, "cudaStreamCreate", e);
   }
-  AGFR_ALLOC(h->img, n * npix * sizeof(uint16_t));
-  AGFR_ALLOC(h->imgT, n * npix * sizeof(uint16_t));
-  AGFR_ALLOC(h->gminR, n * (size_t)cfg->height * ((cfg->width + 31) / 32) * sizeof(uint16_t));
-  AGFR_ALLOC(h->gminC, n * (size_t)cfg->width * ((cfg->height + 31) / 32) * sizeof(uint16_t));
+  const size_t nGR = (size_t)cfg->height * ((cfg->width + 31) / 32), nGC = (size_t)cfg->width * ((cfg->height + 31) / 32);
+  h->vstride = (2 * npix + nGR + nGC + 63) / 64 * 64;
+  AGFR_ALLOC(h->scene, n * h->vstride * sizeof(uint16_t));
+  h->img = h->scene;
+  h->imgT = h->scene + npix;
+  h->gminR = h->scene + 2 * npix;
+  h->gminC = h->scene + 2 * npix + nGR;
   AGFR_ALLOC(h->state, n * 12 * sizeof(double));
   AGFR_ALLOC(h->cands, n * (size_t)h->kcap * 4 * sizeof(double));
   AGFR_ALLOC(h->flags, n * (size_t)h->kcap);
@@ -389,13 +434,13 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   AGFR_ALLOC(h->stats, 8 * sizeof(double));
   AGFR_ALLOC(h->prims, n * 9 * sizeof(double));
   AGFR_ALLOC(h->next, sizeof(int));
+  AGFR_ALLOC(h->order, n * sizeof(int));
+  AGFR_ALLOC(h->work, n * sizeof(unsigned));
 #undef AGFR_ALLOC
   // images start empty (everything at the far plane would be 65535; zero = "ignored" pixels), states zero with
   // the shared cost vector
-  cudaMemsetAsync(h->img, 0, n * npix * sizeof(uint16_t), h->stream);
-  cudaMemsetAsync(h->imgT, 0, n * npix * sizeof(uint16_t), h->stream);
-  cudaMemsetAsync(h->gminR, 0xFF, n * (size_t)cfg->height * ((cfg->width + 31) / 32) * sizeof(uint16_t), h->stream);  // nothing seen
-  cudaMemsetAsync(h->gminC, 0xFF, n * (size_t)cfg->width * ((cfg->height + 31) / 32) * sizeof(uint16_t), h->stream);
+  cudaMemsetAsync(h->scene, 0, n * h->vstride * sizeof(uint16_t), h->stream);
+  cudaMemset2DAsync(h->gminR, h->vstride * sizeof(uint16_t), 0xFF, (nGR + nGC) * sizeof(uint16_t), n, h->stream);  // nothing seen
   cudaMemsetAsync(h->results, 0, n * sizeof(agf_rappids_result), h->stream);
   cudaMemsetAsync(h->flags, 0, n * (size_t)h->kcap, h->stream);
   {
@@ -440,8 +485,9 @@ int agf_rappids_set_images(agf_rappids* p, const uint16_t* images, size_t first,
   Handle* h = H_(p);
   if (int rc = h->range(first, count)) return rc;
   AGFR_CUDA(cudaSetDevice(h->device));
-  AGFR_CUDA(cudaMemcpyAsync(h->img + first * h->npix(), images, count * h->npix() * sizeof(uint16_t),
-                            cudaMemcpyHostToDevice, h->stream));
+  if (count)
+    AGFR_CUDA(cudaMemcpy2DAsync(h->img + first * h->vstride, h->vstride * sizeof(uint16_t), images, h->npix() * sizeof(uint16_t),
+                                h->npix() * sizeof(uint16_t), count, cudaMemcpyHostToDevice, h->stream));
   if (int rc = h->retranspose(first, count)) return rc;
   h->launches += 1;
   if (int rc = h->rebuild_groupmin(first, count)) return fail(rc, "group-minimum kernel launch");
@@ -464,8 +510,8 @@ int agf_rappids_render_scenes(agf_rappids* p, const uint16_t* row_bg, const int3
   AGFR_CUDA(cudaMemcpyAsync(d_box, boxes, box_bytes, cudaMemcpyHostToDevice, h->stream));
   const size_t total = count * h->npix();
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  render_kernel<false><<<grid, 256, 0, h->stream>>>(h->img + first * h->npix(), d_bg, d_box, W, Hh, count);
-  render_kernel<true><<<grid, 256, 0, h->stream>>>(h->imgT + first * h->npix(), d_bg, d_box, W, Hh, count);
+  render_kernel<false><<<grid, 256, 0, h->stream>>>(h->img + first * h->vstride, d_bg, d_box, W, Hh, count, h->vstride);
+  render_kernel<true><<<grid, 256, 0, h->stream>>>(h->imgT + first * h->vstride, d_bg, d_box, W, Hh, count, h->vstride);
   AGFR_CUDA(cudaGetLastError());
   h->launches += 2;
   if (int rc = h->rebuild_groupmin(first, count)) return fail(rc, "group-minimum kernel launch");
@@ -478,8 +524,9 @@ int agf_rappids_get_images(agf_rappids* p, uint16_t* images, size_t first, size_
   Handle* h = H_(p);
   if (int rc = h->range(first, count)) return rc;
   AGFR_CUDA(cudaSetDevice(h->device));
-  AGFR_CUDA(cudaMemcpyAsync(images, h->img + first * h->npix(), count * h->npix() * sizeof(uint16_t),
-                            cudaMemcpyDeviceToHost, h->stream));
+  if (count)
+    AGFR_CUDA(cudaMemcpy2DAsync(images, h->npix() * sizeof(uint16_t), h->img + first * h->vstride, h->vstride * sizeof(uint16_t),
+                                h->npix() * sizeof(uint16_t), count, cudaMemcpyDeviceToHost, h->stream));
   AGFR_CUDA(cudaStreamSynchronize(h->stream));
   return AGF_OK;
 }
@@ -566,6 +613,7 @@ int agf_rappids_plan(agf_rappids* p) {
   P.imgT = h->imgT;
   P.gminR = h->gminR;
   P.gminC = h->gminC;
+  P.vstride = h->vstride;
   P.GW = h->GW();
   P.GH = h->GH();
   P.state = h->state;
@@ -576,6 +624,8 @@ int agf_rappids_plan(agf_rappids* p) {
   P.pyramids = h->pyr;
   P.prims = h->prims;
   P.next = h->next;
+  P.work = h->work;
+  P.order = nullptr;
   P.n = (int)h->n;
   P.k = h->k;
   P.kcap = h->kcap;
@@ -613,11 +663,36 @@ int agf_rappids_plan(agf_rappids* p) {
   auto& ev = h->events[(h->ev_head + h->ev_count) % Handle::EVENT_RING];
   h->ev_count++;
   AGFR_CUDA(cudaEventRecord(ev.first, h->stream));
+  if (h->dispatch == 1 && h->have_work) {  // inside the timed region
+    dispatch_order_kernel<<<1, 1024, 0, h->stream>>>(h->work, (int)h->n, h->order);
+    AGFR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    P.order = h->order;
+  }
   cudaError_t e = (c.math == AGF_MATH_PARITY) ? agfr::launch_plan_parity(P, h->grid, h->stream)
                                               : agfr::launch_plan_fast(P, h->grid, h->stream);
   if (e != cudaSuccess) return fail(AGF_ECUDA, "planner kernel launch", e);
   AGFR_CUDA(cudaEventRecord(ev.second, h->stream));
   h->launches += 2;
+  h->have_work = true;
+  return AGF_OK;
+}
+
+int agf_rappids_set_dispatch(agf_rappids* p, int32_t mode) {
+  if (!p) return fail(AGF_EINVAL, "null handle");
+  if (mode != AGF_RAPPIDS_DISPATCH_INDEX && mode != AGF_RAPPIDS_DISPATCH_BY_LAST_WORK) return fail(AGF_EINVAL, "unknown dispatch mode");
+  H_(p)->dispatch = mode;
+  return AGF_OK;
+}
+
+int agf_rappids_get_plan_work(agf_rappids* p, uint32_t* cycles, size_t first, size_t count) {
+  if (!p || !cycles) return fail(AGF_EINVAL, "null argument");
+  Handle* h = H_(p);
+  if (int rc = h->range(first, count)) return rc;
+  if (!h->have_work) return fail(AGF_EINVAL, "no plan yet");
+  AGFR_CUDA(cudaSetDevice(h->device));
+  AGFR_CUDA(cudaMemcpyAsync(cycles, h->work + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  AGFR_CUDA(cudaStreamSynchronize(h->stream));
   return AGF_OK;
 }
 

@@ -33,6 +33,12 @@ namespace agfr {
 #ifndef AGFR_PHASE_CLOCKS
 #define AGFR_PHASE_CLOCKS 0  // tuning builds: per-phase clock64() totals of a few warps, printed at the end of the kernel
 #endif
+#ifndef AGFR_EXPAND_SPEC
+#define AGFR_EXPAND_SPEC 0
+#endif
+#ifndef AGFR_EXPAND_PF
+#define AGFR_EXPAND_PF 0
+#endif
 #ifndef AGFR_COLD_CALLS
 #define AGFR_COLD_CALLS 1
 #endif
@@ -60,11 +66,12 @@ constexpr int kMaxPyr = 32;
 constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
 
 struct PlanParams {
-  // images
-  const uint16_t* img;    // [n][H][W]
-  const uint16_t* imgT;   // [n][W][H]
-  const uint16_t* gminR;  // [n][H][GW] minimum of each group of 32 pixels of a row (pixels <= ignore count as 65535)
-  const uint16_t* gminC;  // [n][W][GH] the same per column
+  // images: four planes of one scene record per vehicle, vehicle v's planes at + v * vstride (agf_rappids.cu, Handle)
+  const uint16_t* img;    // [H][W]
+  const uint16_t* imgT;   // [W][H]
+  const uint16_t* gminR;  // [H][GW] minimum of each group of 32 pixels of a row (pixels <= ignore count as 65535)
+  const uint16_t* gminC;  // [W][GH] the same per column
+  size_t vstride;         // elements between the records of consecutive vehicles
   const double* state;    // [n][12]: vel0, acc0, grav, cost vector
   const double* cands;    // [n][kcap][4]
   uint8_t* flags;         // [n][kcap]: the candidate pass leaves its verdict code here, the planning pass replaces it by the flags
@@ -73,6 +80,8 @@ struct PlanParams {
   double* pyramids;       // [n][kMaxPyr][17]
   double* prims;          // [n][9]: alpha, beta, gamma of the returned primitive per axis (SingleAxisTrajectory state), or null
   int* next;              // work counter
+  const int* order;       // dispatch order: the k-th vehicle handed out is order[k] (null: index order)
+  unsigned* work;         // [n] clock cycles this call spent on each vehicle (the next call's dispatch order)
   int n, k, kcap;
   int W, H, GW, GH;       // GW = ceil(W / 32), GH = ceil(H / 32)
   double scale, f, cx, cy, rPlan, minDist;
@@ -388,6 +397,12 @@ struct WarpCtx {
 };
 
 AGFR_DEV unsigned ld16(const uint16_t* p) { return (unsigned)__ldg(p); }
+// a load the compiler keeps where it is written (issued ahead of the test that decides whether its value is needed)
+AGFR_DEV unsigned ld16_spec(const uint16_t* p) {
+  unsigned short r;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return (unsigned)r;
+}
 AGFR_DEV unsigned lanes_after(int src) { return 0xfffffffeu << src; }
 
 // DepthImagePlanner::InflatePyramid (DepthImagePlanner.cpp:456-970), warp cooperative.
@@ -411,7 +426,16 @@ AGFR_DEV bool shrink_trigger(const int REGION, const Shrink& s, int num, int x, 
 }
 // applies the update of one triggering pixel; false = "the pyramid cannot contain the sample point"
 AGFR_DEV bool shrink_apply(const int REGION, Shrink& s, int num, int x, int y, int p, int x0, int y0) {
-  const int q = num / p;
+  // num / p (p >= 1): a float quotient corrected to the exact floor is a third of the instructions of the 32-bit integer
+  // division (which was 6 % of the planning pass's instructions); exact for num < 2^20, where the quotient's error is < 1
+  int q;
+  if (num < (1 << 20)) {
+    q = (int)__fdividef((float)num, (float)p);
+    q -= (q * p > num);
+    q += ((q + 1) * p <= num);
+  } else {
+    q = num / p;
+  }
   const int rT = x - q, lT = x + q, tT = y + q, bT = y - q;
   if (REGION == R_RIGHT || REGION == R_LEFT) {
     const bool blocked = (REGION == R_RIGHT) ? (x0 > rT - kBuf) : (x0 < lT + kBuf);
@@ -609,12 +633,20 @@ static __device__ __noinline__ bool shrink_region(const int REGION, const PlanPa
 // pyramid's minimum depth blocks the side; folds the depths seen before it into maxDepth.
 // `plane` + idx * pitch is the pixel line, `gplane` + idx * G its group minima.
 static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* plane, const uint16_t* gplane,
-                                                int pitch, int G, int idx, int a, int b, int minPyr, int& maxDepth) {
+                                                int pitch, int G, int idx, int dir, int nlines, int a, int b, int minPyr, int& maxDepth) {
   const uint16_t* line = plane + (size_t)idx * pitch;
   const uint16_t* gl = gplane + (size_t)idx * G;
   unsigned mn = 65535u;
   bool blocked = false;
   const int g0 = a >> 5, g1 = b >> 5;
+#if AGFR_EXPAND_SPEC
+  // Only the two end groups of a range can be covered partly, and in scenes whose depth varies along the line they need their
+  // pixels on almost every line: their pixels are requested TOGETHER with the group minima (one memory round trip per line
+  // instead of two dependent ones; the planning pass waits on exactly these loads -- ncu, round 2: 18 % of its stall samples).
+  const int e0b = min(b, (g0 << 5) + 31);
+  const int pe0 = (a + w.lane <= e0b) ? (int)ld16_spec(line + a + w.lane) : 0;
+  const int pe1 = (g1 > g0 && (g1 << 5) + w.lane <= b) ? (int)ld16_spec(line + (g1 << 5) + w.lane) : 0;
+#endif
   for (int gb = g0; gb <= g1 && !blocked; gb += 32) {
     const int g = gb + w.lane;
     const bool in = g <= g1;
@@ -632,7 +664,11 @@ static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpC
       const int ca = max(a, gs << 5), cb = min(b, (gs << 5) + 31);
       const int vv = ca + w.lane;
       const bool valid = vv <= cb;
+#if AGFR_EXPAND_SPEC
+      const int p = (gs == g0) ? pe0 : (gs == g1) ? pe1 : (valid ? (int)ld16(line + vv) : 0);
+#else
       const int p = valid ? (int)ld16(line + vv) : 0;
+#endif
       const bool sees = valid && p > P.ignore;
       const bool blk = sees && p < minPyr;
       const unsigned bm = __ballot_sync(AGFR_FULL, blk);
@@ -647,6 +683,16 @@ static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpC
     // whole groups without a blocking pixel, before the blocking group: their minimum is the minimum of their seen pixels
     if (full && !cand && w.lane < blockLane) mn = min(mn, gm);
   }
+#if AGFR_EXPAND_PF
+  // the line this side reaches next (four calls from now): its group minima and end-group pixels towards L1
+  if (!blocked && (unsigned)(idx + dir) < (unsigned)nlines && w.lane < 6) {
+    const uint16_t* nl = line + dir * pitch;
+    const uint16_t* q = w.lane == 0 ? gl + dir * G + g0 : w.lane == 1 ? gl + dir * G + g1 :
+                        w.lane == 2 ? nl + max(a - 1, 0) : w.lane == 3 ? nl + min(a + 15, pitch - 1) :
+                        w.lane == 4 ? nl + min(b + 1, pitch - 1) : nl + max(b - 15, 0);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+  }
+#endif
   mn = __reduce_min_sync(AGFR_FULL, mn);
   if ((int)mn < maxDepth) maxDepth = (int)mn;
   return blocked;
@@ -706,7 +752,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
   while (rf || tf || lf || bf) {
     if (rf) {
       if (right < W - edgeOff - 1) {
-        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, right + 1, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, right + 1, 1, W, top, bottom, minPyr, maxDepth)) {
           rf = false;
           right--;
         }
@@ -717,7 +763,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (tf) {
       if (top > edgeOff) {
-        if (expand_line(P, w, w.img, w.gminR, W, P.GW, top - 1, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, w.gminR, W, P.GW, top - 1, -1, H, left, right, minPyr, maxDepth)) {
           tf = false;
           top++;
         }
@@ -728,7 +774,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (lf) {
       if (left > edgeOff) {
-        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, left - 1, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, left - 1, -1, W, top, bottom, minPyr, maxDepth)) {
           lf = false;
           left++;
         }
@@ -739,7 +785,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (bf) {
       if (bottom < H - edgeOff - 1) {
-        if (expand_line(P, w, w.img, w.gminR, W, P.GW, bottom + 1, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, w.gminR, W, P.GW, bottom + 1, 1, H, left, right, minPyr, maxDepth)) {
           bf = false;
           bottom--;
         }
@@ -1035,13 +1081,17 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
 #endif
   for (;;) {
     int v = 0;
-    if (lane == 0) v = atomicAdd(P.next, 1);
+    if (lane == 0) {
+      v = atomicAdd(P.next, 1);
+      if (v < P.n && P.order) v = P.order[v];
+    }
     v = __shfl_sync(AGFR_FULL, v, 0);
     if (v >= P.n) break;
-    w.img = P.img + (size_t)v * P.W * P.H;
-    w.imgT = P.imgT + (size_t)v * P.W * P.H;
-    w.gminR = P.gminR + (size_t)v * P.H * P.GW;
-    w.gminC = P.gminC + (size_t)v * P.W * P.GH;
+    const long long work0 = clock64();
+    w.img = P.img + (size_t)v * P.vstride;
+    w.imgT = P.imgT + (size_t)v * P.vstride;
+    w.gminR = P.gminR + (size_t)v * P.vstride;
+    w.gminC = P.gminC + (size_t)v * P.vstride;
     w.npyr = 0;
     w.capHit = 0;
     const double* st = P.state + (size_t)v * 12;
@@ -1140,6 +1190,8 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
       out->best_tf = bestT;
       out->pyramid_cap_hit = w.capHit;
       out->reserved_ = 0;
+      const long long dt = clock64() - work0;
+      P.work[v] = dt > 0xffffffffLL ? 0xffffffffu : (unsigned)dt;
     }
     {  // the returned primitive -- polynomial coefficients, and the generator's own variables for the tracking loop --
        // regenerated from the winning candidate (same routine, same inputs) rather than carried through the candidate loop:

@@ -120,6 +120,16 @@ int agf_rappids_get_candidates(agf_rappids* p, double* candidates, size_t first,
 /* The planner call for every vehicle: evaluates the current candidate lists.  Asynchronous on the handle's stream. */
 int agf_rappids_plan(agf_rappids* p);
 int agf_rappids_sync(agf_rappids* p);
+/* Order in which the planning pass hands vehicles to its warps.  BY_LAST_WORK (default): descending device time of each
+ * vehicle's previous plan on this handle (index order on the first call) -- plans differ in length by an order of magnitude
+ * and a planner runs at image rate on slowly changing scenes, so starting the long plans first removes the tail of a launch.
+ * INDEX: vehicle index order.  Results do not depend on the order (the reference has no counterpart: one planner object
+ * per vehicle, DepthImagePlanner.cpp:91). */
+#define AGF_RAPPIDS_DISPATCH_INDEX 0
+#define AGF_RAPPIDS_DISPATCH_BY_LAST_WORK 1
+int agf_rappids_set_dispatch(agf_rappids* p, int32_t mode);
+/* Device clock cycles the last plan spent on each vehicle (what BY_LAST_WORK sorts by), [count] uint32. */
+int agf_rappids_get_plan_work(agf_rappids* p, uint32_t* cycles, size_t first, size_t count);
 
 int agf_rappids_get_results(agf_rappids* p, agf_rappids_result* out, size_t first, size_t count);
 /* The returned trajectories as records for the in-kernel tracking loop, [count][AGF_OFFTRAJ_DOUBLES] (agrifly_b200.h,

@@ -23,6 +23,8 @@ def main():
         pl.render_scenes(pop["row_bg"], pop["boxes"])
         pl.set_states(pop["vel0"], pop["acc0"], pop["grav"])
         pl.sample_candidates(k, seed=7)
+        if os.environ.get("AGF_PROF_DISPATCH") == "index":
+            pl.set_dispatch(False)
         pl.plan()  # warm-up: the first launch carries the lazy module load between its timing events
         pl.sync()
         pl.plan_kernel_time()
