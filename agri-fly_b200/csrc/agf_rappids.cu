@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -251,6 +252,7 @@ struct Handle {
   unsigned* work = nullptr;  // cycles per vehicle of the last plan
   bool have_work = false;
   int dispatch = 1;          // 1: by the previous plan's work (default), 0: index order
+  int frame_jump = 8;        // PlanParams::frameJump; AGF_RAPPIDS_FRAME_JUMP=<k> at create time overrides (0: line by line only)
   void* stage = nullptr;  // device staging for scene descriptions
   size_t stage_bytes = 0;
   int grid = 0, regs = 0, blocks_per_sm = 0;
@@ -403,6 +405,7 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   if (h->cfg.max_pyramids <= 0) h->cfg.max_pyramids = AGF_RAPPIDS_MAX_PYRAMIDS;  // "unlimited": see pyramid_cap_hit
   h->n = n;
   h->kcap = max_candidates;
+  if (const char* fj = getenv("AGF_RAPPIDS_FRAME_JUMP")) h->frame_jump = atoi(fj);
   h->device = dev;
   const size_t npix = h->npix();
 #define AGFR_ALLOC(ptr, bytes)                                  \
@@ -644,6 +647,7 @@ int agf_rappids_plan(agf_rappids* p) {
   P.vmax = c.max_velocity;
   P.maxPyr = c.max_pyramids;
   P.costKind = c.cost_kind;
+  P.frameJump = (c.width % 8 == 0 && c.height % 8 == 0) ? h->frame_jump : 0;  // frame_strip reads 16-byte vectors of pixel lines
   // the integer constants of InflatePyramid, evaluated in double on the host exactly as the reference does
   // (DepthImagePlanner.cpp:460,506,608)
   P.edgeOff = (int)(c.focal_length * c.true_radius / c.min_checking_dist);

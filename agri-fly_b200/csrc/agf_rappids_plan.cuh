@@ -30,11 +30,20 @@ namespace agfr {
 // the per-candidate pieces (primitive generation, feasibility tests, pyramid geometry) run once per candidate or pyramid,
 // lane parallel, and are a small share of the executed instructions but most of the kernel's code when inlined at every
 // call site; as real calls the kernel is 122 KB instead of 155 KB and 1.2 % faster (AGFR_COLD_CALLS=0 inlines them again)
+#ifndef AGFR_FRAME_UNROLL
+#define AGFR_FRAME_UNROLL 1
+#endif
 #ifndef AGFR_PHASE_CLOCKS
 #define AGFR_PHASE_CLOCKS 0  // tuning builds: per-phase clock64() totals of a few warps, printed at the end of the kernel
 #endif
 #ifndef AGFR_EXPAND_SPEC
 #define AGFR_EXPAND_SPEC 0
+#endif
+#ifndef AGFR_FLOAT_QUOT
+#define AGFR_FLOAT_QUOT 0
+#endif
+#ifndef AGFR_FRAME_JUMP
+#define AGFR_FRAME_JUMP 1  // frame jumps of the spiral expansion compiled in (their length is PlanParams::frameJump)
 #endif
 #ifndef AGFR_EXPAND_PF
 #define AGFR_EXPAND_PF 0
@@ -63,6 +72,7 @@ constexpr int kMaxPyr = 32;
 #define AGFR_MIN_BLOCKS 8
 #endif
 #endif
+constexpr int kFrameUnroll = AGFR_FRAME_UNROLL;
 constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
 
 struct PlanParams {
@@ -87,6 +97,7 @@ struct PlanParams {
   double scale, f, cx, cy, rPlan, minDist;
   double fminA, fmaxA, wmaxA, minSec, vmax;
   int maxPyr, costKind;
+  int frameJump;          // iterations of the spiral expansion taken in one step when their frame holds no blocker (< 2: off)
   int edgeOff, num;       // int(f * rTrue / minDist), int(f * rPlan / scale)   (DepthImagePlanner.cpp:460,608)
   int ignore;             // uint16(rTrue / scale)                               (:506)
 };
@@ -429,7 +440,7 @@ AGFR_DEV bool shrink_apply(const int REGION, Shrink& s, int num, int x, int y, i
   // num / p (p >= 1): a float quotient corrected to the exact floor is a third of the instructions of the 32-bit integer
   // division (which was 6 % of the planning pass's instructions); exact for num < 2^20, where the quotient's error is < 1
   int q;
-  if (num < (1 << 20)) {
+  if (AGFR_FLOAT_QUOT && num < (1 << 20)) {
     q = (int)__fdividef((float)num, (float)p);
     q -= (q * p > num);
     q += ((q + 1) * p <= num);
@@ -698,6 +709,79 @@ static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpC
   return blocked;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame jumps.  The spiral scans one pixel line per side and iteration, and every line is two dependent memory round trips
+// (group minima, then the pixels of the partly covered end groups): the planning pass spent its time waiting on exactly
+// those (ncu, round 2: expand_line 39 % of the stall samples).  K iterations in which no side is blocked scan, taken
+// together, exactly the frame between the rectangle and the rectangle grown by K on every active side (line j of a side
+// spans what the neighbouring sides reached before it; the union over j is the full frame, corners included), they leave
+// every flag unchanged and fold every seen pixel of the frame into maxDepth -- in any order.  So a frame whose pixels
+// hold no blocker (ignore < p < minPyr) is taken in ONE step: the group minima of a strip's interior groups and the
+// pixels of its end groups are requested together.  A frame that holds a blocker -- or
+// might (only its group minimum is known) -- is not jumped: the caller runs the line-by-line iterations there, so a refused
+// jump costs time, never exactness.
+// frame_pair: two opposite strips of the frame.  Returns false when they hold a blocking pixel; otherwise folds their seen
+// depths into mn.  Needs 16-byte aligned pixel lines (W, H
+// multiples of 8; the host switches jumps off otherwise).
+// ---------------------------------------------------------------------------------------------
+static __device__ __noinline__ bool frame_pair(const PlanParams& P, const WarpCtx& w, const uint16_t* plane, const uint16_t* gplane,
+                                               int pitch, int G, int lineA, int lineB, bool useA, bool useB, int nl, int a, int b,
+                                               int minPyr, unsigned& mnOut) {
+  // Two opposite strips of the frame (rows above and below, or columns left and right): nl <= 8 lines each from lineA / lineB,
+  // the same inner range [a, b].  Interior groups (always covered completely) are settled by their minima; the two end groups
+  // -- the only ones a range can cover partly -- by their pixels: an end group of nl lines is a block of nl x 32 pixels, ONE
+  // 16-byte load per lane (lane = 4 * line + quarter).  Every load of the pair is independent of every other: one memory round
+  // trip.  A blocker is a seen pixel below minPyr, so the pair is free of blockers iff the minimum over its seen pixels is
+  // not below minPyr: only that minimum is formed.
+  const int g0 = a >> 5, g1 = b >> 5;
+  const int ni = g1 - g0 - 1;            // interior groups per line
+  const int per = ni > 0 ? nl * ni : 0;  // interior items per strip
+  if (2 * per > 128) return false;       // wider images than four chunks cover: no jump
+  const int row = w.lane >> 2, qtr = w.lane & 3;
+  const bool inRow = row < nl, two = g1 > g0;
+  const uint4 none = make_uint4(0, 0, 0, 0);  // 0 <= ignore: never seen
+  const uint16_t* la = plane + (size_t)(lineA + row) * pitch + qtr * 8;
+  const uint16_t* lb = plane + (size_t)(lineB + row) * pitch + qtr * 8;
+  uint4 q[4];
+  q[0] = (inRow && useA) ? __ldg(reinterpret_cast<const uint4*>(la + (g0 << 5))) : none;
+  q[1] = (inRow && useA && two) ? __ldg(reinterpret_cast<const uint4*>(la + (g1 << 5))) : none;
+  q[2] = (inRow && useB) ? __ldg(reinterpret_cast<const uint4*>(lb + (g0 << 5))) : none;
+  q[3] = (inRow && useB && two) ? __ldg(reinterpret_cast<const uint4*>(lb + (g1 << 5))) : none;
+  unsigned mn = 65535u;
+  if (per > 0) {
+    const unsigned rni = 65536u / (unsigned)ni + 1u;  // it / ni == (it * rni) >> 16 for it < 128, ni <= 32
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int it = w.lane + 32 * j;
+      const bool second = it >= per;
+      if (second) it -= per;
+      if (it < per && (second ? useB : useA)) {
+        const int l = (int)(((unsigned)it * rni) >> 16), k = it - l * ni;
+        mn = min(mn, ld16(gplane + (size_t)((second ? lineB : lineA) + l) * G + g0 + 1 + k));
+      }
+    }
+  }
+  // pixels outside [a, b] and pixels not seen (<= ignore) count as 65535
+  const int ign = P.ignore;
+  // (a rolled loop: straight-line code for the 32 pixels of a lane was fetched once per call and the planning pass waited on
+  // instruction fetch more than on anything else -- ncu, round 2: no-instruction 15.7 stall cycles per issue)
+#pragma unroll kFrameUnroll
+  for (int e = 0; e < 4; e++) {
+    const int base = (((e & 1) ? g1 : g0) << 5) + qtr * 8;
+    const int lo = a - base, hi = b - base;  // covered: lo <= i <= hi
+    const unsigned wd[4] = {q[e].x, q[e].y, q[e].z, q[e].w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int p = (int)((i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu));
+      if (p > ign && i >= lo && i <= hi) mn = min(mn, (unsigned)p);
+    }
+  }
+  mn = __reduce_min_sync(AGFR_FULL, mn);
+  if ((int)mn < minPyr) return false;
+  mnOut = min(mnOut, mn);
+  return true;
+}
+
 static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& w, int x0, int y0, double minimumDepth,
                                      double& outDepth, int4& outEdge) {
   const int W = P.W, H = P.H, edgeOff = P.edgeOff;
@@ -749,7 +833,47 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
   // spiral expansion (:519-599)
   int maxDepth = 65535;
   bool rf = true, tf = true, lf = true, bf = true;
+#if AGFR_FRAME_JUMP
+  int cool = 0;  // line-by-line iterations to run before the next jump is tried
+#endif
   while (rf || tf || lf || bf) {
+#if AGFR_FRAME_JUMP
+    if (cool == 0) {
+      int K = min(P.frameJump, 8);
+      if (rf) K = min(K, W - edgeOff - 1 - right);
+      if (tf) K = min(K, top - edgeOff);
+      if (lf) K = min(K, left - edgeOff);
+      if (bf) K = min(K, H - edgeOff - 1 - bottom);
+      if (K >= 2) {
+        const int r2 = right + (rf ? K : 0), t2 = top - (tf ? K : 0), l2 = left - (lf ? K : 0), b2 = bottom + (bf ? K : 0);
+        unsigned mn = 65535u;
+        // rows above and below span the grown width (corners included), columns left and right the old height
+        bool ok = true;
+        if (tf || bf) ok = frame_pair(P, w, w.img, w.gminR, W, P.GW, t2, bottom + 1, tf, bf, K, l2, r2, minPyr, mn);
+        if (ok && (lf || rf)) ok = frame_pair(P, w, w.imgT, w.gminC, H, P.GH, l2, right + 1, lf, rf, K, top, bottom, minPyr, mn);
+        if (ok) {
+          if ((int)mn < maxDepth) maxDepth = (int)mn;
+          right = r2;
+          top = t2;
+          left = l2;
+          bottom = b2;
+#if AGFR_PHASE_CLOCKS
+          w.clk[5] += 1;
+#endif
+          continue;
+        }
+#if AGFR_PHASE_CLOCKS
+        w.clk[6] += 1;
+#endif
+        cool = K;  // a blocker within K lines of some side: line by line until a side stops (or K iterations)
+      }
+    }
+    if (cool > 0) cool--;
+    const bool rf0 = rf, tf0 = tf, lf0 = lf, bf0 = bf;
+#endif
+#if AGFR_PHASE_CLOCKS
+    w.clk[7] += 1;
+#endif
     if (rf) {
       if (right < W - edgeOff - 1) {
         if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, right + 1, 1, W, top, bottom, minPyr, maxDepth)) {
@@ -794,6 +918,9 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
         bf = false;
       }
     }
+#if AGFR_FRAME_JUMP
+    if (rf != rf0 || tf != tf0 || lf != lf0 || bf != bf0) cool = 0;
+#endif
   }
 #if AGFR_PHASE_CLOCKS
   { long long c1_ = clock64(); w.clk[1] += c1_ - c0_; c0_ = c1_; }
@@ -1074,7 +1201,7 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
   w.pdepth = s_depth[wid];
   w.pedge = s_edge[wid];
 #if AGFR_PHASE_CLOCKS
-  unsigned long long clk[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   w.clk = clk;
   const long long cstart_ = clock64();
   int nplans_ = 0;
@@ -1237,7 +1364,7 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
   }
 #if AGFR_PHASE_CLOCKS
   if (lane == 0 && wid == 0 && blockIdx.x % 97 == 0)
-    printf("phase cycles block %d: plans %d total %lld | candidates %llu  initial-rect %llu  expansion %llu  shrink %llu  collision-test %llu\n", blockIdx.x, nplans_, clock64() - cstart_, clk[0], clk[4], clk[1], clk[2], clk[3]);
+    printf("phase cycles block %d: plans %d total %lld | candidates %llu  initial-rect %llu  expansion %llu  shrink %llu  collision-test %llu | jumps taken %llu refused %llu, line-by-line iterations %llu\n", blockIdx.x, nplans_, clock64() - cstart_, clk[0], clk[4], clk[1], clk[2], clk[3], clk[5], clk[6], clk[7]);
 #endif
 }
 

@@ -563,6 +563,14 @@ def rappids_extra(agf, pk):
             pl.plan()
         pl.sync()
         pms, pcnt = pl.plan_kernel_time()
+        # the same launch with vehicles handed out in index order instead of by their previous plan's work (the first plan of a
+        # handle, or scenes that share nothing with the last frame)
+        pl.set_dispatch(False)
+        for _ in range(2):
+            pl.plan()
+        pl.sync()
+        pms_index, _ = pl.plan_kernel_time()
+        pl.set_dispatch(True)
         st = pl.stats()
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import orc_rappids
@@ -576,7 +584,9 @@ def rappids_extra(agf, pk):
         bytes_per_plan = 2.0 * port.pixels_read() / nsamp
         gbs = nr * bytes_per_plan / (pms * 1e-3) / 1e9
         r = dict(plans_per_s=nr / (pms * 1e-3), candidates_per_s=nr * kr / (pms * 1e-3), vehicles=nr, candidates=kr, ms_per_launch=pms,
-                 found_fraction=st["found"] / nr,
+                 found_fraction=st["found"] / nr, plans_per_s_index_order=nr / (pms_index * 1e-3), ms_per_launch_index_order=pms_index,
+                 dispatch="candidate pass (one thread per candidate) + planning pass (one warp per vehicle), vehicles handed out by "
+                          "descending device time of their previous plan; *_index_order: handed out in index order",
                  roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=gbs / pk["hbm_gbs"],
                                algorithmic_bytes_per_plan=bytes_per_plan,
                                note="pixel scans of InflatePyramid: %.3f MB of depth pixels per plan in the reference's scan order, counted "

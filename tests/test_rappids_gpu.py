@@ -386,3 +386,37 @@ def test_planned_primitives_fly_in_the_tracking_loop(agf):
         assert bit_equal(got[j], ref[-1]), (j, got[j][0:3], ref[-1][0:3])
         assert bit_equal(got_dev[fly[j]], ref[-1]), ("device hand-over", j)
         assert ref[-1, 35] == 0 and np.linalg.norm(ref[-1, 0:3] - np.array([0.0, 0.0, 2.0])) > 0.3  # it went somewhere
+
+
+@pytest.mark.parametrize("family", ["easy", "hard"])
+def test_frame_jumps_and_dispatch_order_do_not_change_results(agf, family, monkeypatch):
+    """The planning pass takes K iterations of InflatePyramid's spiral expansion in one step where their frame holds no
+    blocker, and hands vehicles out by their previous plan's work: neither may change a bit of any output.  8 192 vehicles
+    (about 30 000 pyramids), both scene families: line-by-line expansion in index order against jumps of 8 and of 3
+    iterations and against the second plan of a handle (dispatch by work)."""
+    n, k = 8192, 256
+    pop = agf.scenarios.rappids_population(n, seed=909, **(HARD if family == "hard" else {}))
+    cands = agf.scenarios.rappids_candidates(n, k, seed=910)
+    out = {}
+    for jump in (0, 8, 3):
+        monkeypatch.setenv("AGF_RAPPIDS_FRAME_JUMP", str(jump))
+        with agf.Rappids(agf.rappids_cfg(math=agf.abi.MATH_PARITY), n, k) as pl:
+            pl.render_scenes(pop["row_bg"], pop["boxes"])
+            pl.set_states(pop["vel0"], pop["acc0"], pop["grav"])
+            pl.set_candidates(cands)
+            pl.plan()
+            pl.sync()
+            out[jump] = (pl.results(), pl.candidate_flags(), pl.pyramids())
+            if jump == 8:
+                work = pl.plan_work()
+                pl.plan()  # handed out by the work of the first plan
+                pl.sync()
+                out["second"] = (pl.results(), pl.candidate_flags(), pl.pyramids())
+                assert work.min() > 0
+    ref = out[0]
+    assert ref[0]["n_pyramids"].sum() > n
+    for key in (8, 3, "second"):
+        res, flags, pyr = out[key]
+        assert res.tobytes() == ref[0].tobytes(), key
+        assert np.array_equal(flags, ref[1]), key
+        assert pyr.tobytes() == ref[2].tobytes(), key
