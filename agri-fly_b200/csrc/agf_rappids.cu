@@ -252,6 +252,7 @@ struct Handle {
   unsigned* work = nullptr;  // cycles per vehicle of the last plan
   bool have_work = false;
   int dispatch = 1;          // 1: by the previous plan's work (default), 0: index order
+  int shrink_fold = 1;       // PlanParams::shrinkFold; AGF_RAPPIDS_SHRINK_FOLD=0 at create time: one update per pixel
   int frame_jump = 8;        // PlanParams::frameJump; AGF_RAPPIDS_FRAME_JUMP=<k> at create time overrides (0: line by line only)
   void* stage = nullptr;  // device staging for scene descriptions
   size_t stage_bytes = 0;
@@ -406,6 +407,7 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   h->n = n;
   h->kcap = max_candidates;
   if (const char* fj = getenv("AGF_RAPPIDS_FRAME_JUMP")) h->frame_jump = atoi(fj);
+  if (const char* sf = getenv("AGF_RAPPIDS_SHRINK_FOLD")) h->shrink_fold = atoi(sf) != 0;
   h->device = dev;
   const size_t npix = h->npix();
 #define AGFR_ALLOC(ptr, bytes)                                  \
@@ -647,6 +649,7 @@ int agf_rappids_plan(agf_rappids* p) {
   P.vmax = c.max_velocity;
   P.maxPyr = c.max_pyramids;
   P.costKind = c.cost_kind;
+  P.shrinkFold = h->shrink_fold;
   P.frameJump = (c.width % 8 == 0 && c.height % 8 == 0) ? h->frame_jump : 0;  // frame_strip reads 16-byte vectors of pixel lines
   // the integer constants of InflatePyramid, evaluated in double on the host exactly as the reference does
   // (DepthImagePlanner.cpp:460,506,608)

@@ -39,6 +39,9 @@ namespace agfr {
 #ifndef AGFR_EXPAND_SPEC
 #define AGFR_EXPAND_SPEC 0
 #endif
+#ifndef AGFR_SHRINK_FOLD
+#define AGFR_SHRINK_FOLD 1
+#endif
 #ifndef AGFR_FLOAT_QUOT
 #define AGFR_FLOAT_QUOT 0
 #endif
@@ -97,6 +100,7 @@ struct PlanParams {
   double scale, f, cx, cy, rPlan, minDist;
   double fminA, fmaxA, wmaxA, minSec, vmax;
   int maxPyr, costKind;
+  int shrinkFold;         // fold the unblocked updates of a span of an edge region into one reduction (shrink_span)
   int frameJump;          // iterations of the spiral expansion taken in one step when their frame holds no blocker (< 2: off)
   int edgeOff, num;       // int(f * rTrue / minDist), int(f * rPlan / scale)   (DepthImagePlanner.cpp:460,608)
   int ignore;             // uint16(rTrue / scale)                               (:506)
@@ -563,6 +567,32 @@ AGFR_DEV bool shrink_span(const int REGION, const PlanParams& P, const WarpCtx& 
     const bool pre = valid && p > P.ignore && p < maxDepth;
     unsigned todo = __ballot_sync(AGFR_FULL, pre);
     const int x = colWalk ? o : i, y = colWalk ? i : o;
+#if AGFR_SHRINK_FOLD
+    // The four edge regions, when no triggering pixel of the span is "blocked" by the sample point: every update is an
+    // assignment bound = f(pixel) that only ever moves the bound inwards, a pixel that no longer triggers once the bound has
+    // moved would have moved it less, and whether a pixel is blocked does not depend on the bounds -- so the sequential result
+    // is the extremum of f over the pixels that trigger with the bounds at the start of the span: one reduction instead of up
+    // to 32 dependent updates (shrink_apply was 18 % of the planning pass's instructions).
+    if (P.shrinkFold && REGION <= R_BOTTOM && todo) {
+      const bool trig0 = pre && shrink_trigger(REGION, s, P.num, x, y, p);
+      if (!__any_sync(AGFR_FULL, trig0)) continue;
+      const int q = trig0 ? P.num / p : 0;
+      const bool inward = (REGION == R_RIGHT || REGION == R_BOTTOM);  // bound decreases: x - q / y - q
+      const int cand = REGION == R_RIGHT ? x - q : REGION == R_LEFT ? x + q : REGION == R_TOP ? y + q : y - q;
+      const int ref0 = (REGION == R_RIGHT || REGION == R_LEFT) ? x0 : y0;
+      const bool blocked = inward ? (ref0 > cand - kBuf) : (ref0 < cand + kBuf);
+      if (!__any_sync(AGFR_FULL, trig0 && blocked)) {
+        if (inward) {
+          const int m = __reduce_min_sync(AGFR_FULL, trig0 ? cand : INT_MAX);
+          if (REGION == R_RIGHT) s.rS = m; else s.bS = m;
+        } else {
+          const int m = __reduce_max_sync(AGFR_FULL, trig0 ? cand : INT_MIN);
+          if (REGION == R_LEFT) s.lS = m; else s.tS = m;
+        }
+        continue;
+      }
+    }
+#endif
     while (todo) {
       const bool trig = ((todo >> w.lane) & 1u) && shrink_trigger(REGION, s, P.num, x, y, p);
       const unsigned tm = __ballot_sync(AGFR_FULL, trig);

@@ -391,7 +391,8 @@ def test_planned_primitives_fly_in_the_tracking_loop(agf):
 @pytest.mark.parametrize("family", ["easy", "hard"])
 def test_frame_jumps_and_dispatch_order_do_not_change_results(agf, family, monkeypatch):
     """The planning pass takes K iterations of InflatePyramid's spiral expansion in one step where their frame holds no
-    blocker, and hands vehicles out by their previous plan's work: neither may change a bit of any output.  8 192 vehicles
+    blocker, folds the unblocked shrink updates of a 32-pixel span into one reduction, and hands vehicles out by their
+    previous plan's work: none of it may change a bit of any output.  8 192 vehicles
     (about 30 000 pyramids), both scene families: line-by-line expansion in index order against jumps of 8 and of 3
     iterations and against the second plan of a handle (dispatch by work)."""
     n, k = 8192, 256
@@ -400,6 +401,7 @@ def test_frame_jumps_and_dispatch_order_do_not_change_results(agf, family, monke
     out = {}
     for jump in (0, 8, 3):
         monkeypatch.setenv("AGF_RAPPIDS_FRAME_JUMP", str(jump))
+        monkeypatch.setenv("AGF_RAPPIDS_SHRINK_FOLD", "0" if jump == 0 else "1")  # the reference's one update per pixel / folded spans
         with agf.Rappids(agf.rappids_cfg(math=agf.abi.MATH_PARITY), n, k) as pl:
             pl.render_scenes(pop["row_bg"], pop["boxes"])
             pl.set_states(pop["vel0"], pop["acc0"], pop["grav"])
