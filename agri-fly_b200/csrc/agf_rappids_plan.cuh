@@ -39,6 +39,22 @@ namespace agfr {
 #ifndef AGFR_EXPAND_SPEC
 #define AGFR_EXPAND_SPEC 0
 #endif
+#ifndef AGFR_AXIS_CALLS
+#define AGFR_AXIS_CALLS 0
+#endif
+#if AGFR_AXIS_CALLS == 1
+#define AGFR_AXIS_FN __device__ __noinline__
+#define AGFR_SECTION_FN __device__ __forceinline__
+#elif AGFR_AXIS_CALLS == 2
+#define AGFR_AXIS_FN __device__ __forceinline__
+#define AGFR_SECTION_FN static __device__ __noinline__
+#else
+#define AGFR_AXIS_FN __device__ __forceinline__
+#define AGFR_SECTION_FN __device__ __forceinline__
+#endif
+#ifndef AGFR_DIV_CALLS
+#define AGFR_DIV_CALLS 1
+#endif
 #ifndef AGFR_SHRINK_FOLD
 #define AGFR_SHRINK_FOLD 1
 #endif
@@ -125,35 +141,46 @@ struct Mth {
 // ---------------------------------------------------------------------------------------------
 // closed-form roots (Common/Common/Math/RootFinder.hpp:60-174; float 2*pi and float eps as there)
 // ---------------------------------------------------------------------------------------------
+// FP64 division and square root as real calls in the code the planning pass runs once per candidate or section: inline, the
+// 47 divisions and 11 roots were a quarter of that code, all of it fetched from beyond the SM's 32 KB instruction cache every
+// time (the planning pass is bound by instruction fetch, DESIGN K6).  Same operation, same result.
+#if AGFR_DIV_CALLS
+static __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+static __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+#else
+AGFR_DEV double ddiv(double a, double b) { return a / b; }
+AGFR_DEV double dsqrt(double a) { return sqrt(a); }
+#endif
+
 template<bool PARITY>
 __device__ __noinline__ unsigned cubic(double a, double b, double c, double* x) {
   const float piF = 3.141592653589793238463;
   const float twoPiF = 2 * piF;
   const float epsF = 1e-12;
   const double a2 = a * a;
-  double q = (a2 - 3 * b) / 9;
-  const double r = (a * (2 * a2 - 9 * b) + 27 * c) / 54;
+  double q = ddiv(a2 - 3 * b, 9);
+  const double r = ddiv(a * (2 * a2 - 9 * b) + 27 * c, 54);
   const double r2 = r * r;
   const double q3 = q * q * q;
   if (r2 < q3) {
-    double t = r / sqrt(q3);
+    double t = ddiv(r, dsqrt(q3));
     if (t < -1) t = -1;
     if (t > 1) t = 1;
     t = Mth<PARITY>::acos(t);
-    a /= 3;
-    q = -2 * sqrt(q);
-    x[0] = q * Mth<PARITY>::cos(t / 3) - a;
-    x[1] = q * Mth<PARITY>::cos((t + double(twoPiF)) / 3.0) - a;
-    x[2] = q * Mth<PARITY>::cos((t - double(twoPiF)) / 3.0) - a;
+    a = ddiv(a, 3);
+    q = -2 * dsqrt(q);
+    x[0] = q * Mth<PARITY>::cos(ddiv(t, 3)) - a;
+    x[1] = q * Mth<PARITY>::cos(ddiv(t + double(twoPiF), 3.0)) - a;
+    x[2] = q * Mth<PARITY>::cos(ddiv(t - double(twoPiF), 3.0)) - a;
     return 3;
   }
-  double A = -Mth<PARITY>::cbrt(fabs(r) + sqrt(r2 - q3));
+  double A = -Mth<PARITY>::cbrt(fabs(r) + dsqrt(r2 - q3));
   if (r < 0) A = -A;
-  const double B = (fabs(A) < double(epsF) ? 0 : q / A);
-  a /= 3;
+  const double B = (fabs(A) < double(epsF) ? 0 : ddiv(q, A));
+  a = ddiv(a, 3);
   x[0] = (A + B) - a;
   x[1] = -0.5 * (A + B) - a;
-  x[2] = 0.5 * sqrt(3.0) * (A - B);
+  x[2] = 0.5 * sqrt(3.0) * (A - B);  // constant-folded root
   if (fabs(x[2]) < double(epsF)) {
     x[2] = x[1];
     return 2;
@@ -183,26 +210,26 @@ __device__ __noinline__ unsigned quartic(double a, double b, double c, double d,
     if (fabs(D) < double(epsF)) {
       p1 = p2 = a * 0.5;
     } else {
-      sqD = sqrt(D);
+      sqD = dsqrt(D);
       p1 = (a + sqD) * 0.5;
       p2 = (a - sqD) * 0.5;
     }
   } else {
-    sqD = sqrt(D);
+    sqD = dsqrt(D);
     q1 = (y + sqD) * 0.5;
     q2 = (y - sqD) * 0.5;
-    p1 = (a * q1 - c) / (q1 - q2);
-    p2 = (c - a * q2) / (q1 - q2);
+    p1 = ddiv(a * q1 - c, q1 - q2);
+    p2 = ddiv(c - a * q2, q1 - q2);
   }
   D = p1 * p1 - 4 * q1;
   if (!(D < 0.0)) {
-    sqD = sqrt(D);
+    sqD = dsqrt(D);
     root[n++] = (-p1 + sqD) * 0.5;
     root[n++] = (-p1 - sqD) * 0.5;
   }
   D = p2 * p2 - 4 * q2;
   if (!(D < 0.0)) {
-    sqD = sqrt(D);
+    sqD = dsqrt(D);
     root[n++] = (-p2 + sqD) * 0.5;
     root[n++] = (-p2 - sqD) * 0.5;
   }
@@ -213,8 +240,8 @@ __device__ __noinline__ unsigned quartic(double a, double b, double c, double d,
 // DepthImagePlanner.cpp:318-325,412-419
 template<bool PARITY>
 AGFR_PIECE_FN unsigned poly_roots(const double* c, double* roots) {
-  if (fabs(c[0]) > 1e-6) return quartic<PARITY>(c[1] / c[0], c[2] / c[0], c[3] / c[0], c[4] / c[0], roots);
-  return cubic<PARITY>(c[2] / c[1], c[3] / c[1], c[4] / c[1], roots);
+  if (fabs(c[0]) > 1e-6) return quartic<PARITY>(ddiv(c[1], c[0]), ddiv(c[2], c[0]), ddiv(c[3], c[0]), ddiv(c[4], c[0]), roots);
+  return cubic<PARITY>(ddiv(c[2], c[1]), ddiv(c[3], c[1]), ddiv(c[4], c[1]), roots);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -386,7 +413,7 @@ struct Prim {
 // ---------------------------------------------------------------------------------------------
 struct Poly {
   double c[6][3];  // GetTrajectory(): t^5 first (RapidTrajectoryGenerator.hpp:232-241)
-  AGFR_DEV double axis(int i, double t) const {
+  AGFR_AXIS_FN double axis(int i, double t) const {
     return c[0][i] * t * t * t * t * t + c[1][i] * t * t * t * t + c[2][i] * t * t * t + c[3][i] * t * t + c[4][i] * t +
            c[5][i];
   }
@@ -1001,8 +1028,8 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
 AGFR_PIECE_FN void pyr_corner(const PlanParams& P, double depth, const int4& e, int k, double* c) {
   const int ex = (k == 0 || k == 3) ? e.x : e.z;  // right : left
   const int ey = (k < 2) ? e.y : e.w;             // top : bottom
-  c[0] = depth * (((double)ex - P.cx) / P.f);
-  c[1] = depth * (((double)ey - P.cy) / P.f);
+  c[0] = depth * ddiv((double)ex - P.cx, P.f);
+  c[1] = depth * ddiv((double)ey - P.cy, P.f);
   c[2] = depth * 1;
 }
 // unit normal of lateral face `f` (Pyramid.hpp:55-58; the norm is truncated to float, Vec3.hpp:126-129)
@@ -1013,20 +1040,20 @@ AGFR_PIECE_FN void pyr_normal(const PlanParams& P, double depth, const int4& e, 
   const double x = a[1] * b[2] - a[2] * b[1];
   const double y = a[2] * b[0] - a[0] * b[2];
   const double z = a[0] * b[1] - a[1] * b[0];
-  const float nrm = (float)sqrt(x * x + y * y + z * z);
-  n[0] = x / nrm;
-  n[1] = y / nrm;
-  n[2] = z / nrm;
+  const float nrm = (float)dsqrt(x * x + y * y + z * z);
+  n[0] = ddiv(x, nrm);
+  n[1] = ddiv(y, nrm);
+  n[2] = ddiv(z, nrm);
 }
 
-AGFR_DEV Section make_section(const Poly& Q, double t0, double t1) {
+AGFR_SECTION_FN Section make_section(const Poly& Q, double t0, double t1) {
   Section s;
   s.t0 = t0;
   s.t1 = t1;
   s.inc = Q.axis(2, t0) < Q.axis(2, t1);
   return s;
 }
-AGFR_DEV double deepest(const Poly& Q, const Section& s) { return Q.axis(2, s.inc ? s.t1 : s.t0); }
+AGFR_SECTION_FN double deepest(const Poly& Q, const Section& s) { return Q.axis(2, s.inc ? s.t1 : s.t0); }
 
 // DepthImagePlanner::IsCollisionFree (DepthImagePlanner.cpp:216-301) for one candidate; all lanes hold the same Q
 template<bool PARITY>
@@ -1079,8 +1106,8 @@ __device__ __noinline__ bool collision_free(const PlanParams& P, WarpCtx& w, con
     const double startZ = Q.axis(2, ts);
     const double ex = Q.axis(0, te), ey = Q.axis(1, te), ez = Q.axis(2, te);
     if (startZ < P.minDist && ez < P.minDist) continue;
-    const double px = ex * P.f / ez + P.cx;
-    const double py = ey * P.f / ez + P.cy;
+    const double px = ddiv(ex * P.f, ez) + P.cx;
+    const double py = ddiv(ey * P.f, ez) + P.cy;
     // FindContainingPyramid (:356-380): first pyramid in depth order, not shallower than the point, that contains it
     double pdepth;
     int4 pedge;
@@ -1303,10 +1330,10 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
               ax.v0 = __ldg(st + a);
               ax.a0 = __ldg(st + 3 + a);
               ax.generate(goal[a], Ts);
-              Q.c[0][a] = ax.al / 120;
-              Q.c[1][a] = ax.be / 24;
-              Q.c[2][a] = ax.ga / 6;
-              Q.c[3][a] = ax.acc(0.0) / 2;
+              Q.c[0][a] = ddiv(ax.al, 120);
+              Q.c[1][a] = ddiv(ax.be, 24);
+              Q.c[2][a] = ddiv(ax.ga, 6);
+              Q.c[3][a] = ax.acc(0.0) * 0.5;  // == / 2
               Q.c[4][a] = ax.vel(0.0);
               Q.c[5][a] = ax.pos(0.0);
             }
@@ -1365,7 +1392,7 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
         al = ax.al;
         be = ax.be;
         ga = ax.ga;
-        coef = kq == 0 ? al / 120 : kq == 1 ? be / 24 : kq == 2 ? ga / 6 : kq == 3 ? ax.acc(0.0) / 2 : kq == 4 ? ax.vel(0.0) : ax.pos(0.0);
+        coef = kq == 0 ? ddiv(al, 120) : kq == 1 ? ddiv(be, 24) : kq == 2 ? ddiv(ga, 6) : kq == 3 ? ax.acc(0.0) * 0.5 : kq == 4 ? ax.vel(0.0) : ax.pos(0.0);
       }
       if (lane < 18) out->best_coeffs[lane] = coef;
       if (P.prims && lane < 3) {
