@@ -85,11 +85,7 @@ constexpr int kMaxPyr = 32;
 // CTAs per SM the register allocation aims at (round 1, fused kernel: 5 measured best; the planning pass alone, without the
 // candidates' primitive in registers: 5 / 6 / 8 / 10 / 12 -> 74.8 / 73.2 / 70.5 / 69.6 / 71.6 ms, profiles/r2/rappids_variants_split.log)
 #ifndef AGFR_MIN_BLOCKS
-#if defined(AGF_RAPPIDS_PARITY) && AGF_RAPPIDS_PARITY
-#define AGFR_MIN_BLOCKS 3
-#else
-#define AGFR_MIN_BLOCKS 8
-#endif
+#define AGFR_MIN_BLOCKS 8  // the parity variant too: 3 / 5 / 6 / 8 -> 66.1 / 66.7 / 65.5 / 61.1 ms (rappids_variants_parity_occupancy.log)
 #endif
 constexpr int kFrameUnroll = AGFR_FRAME_UNROLL;
 constexpr int kBuf = 2;               // _pyramidSearchPixelBuffer (DepthImagePlanner.cpp:60)
