@@ -128,6 +128,10 @@ int agf_rappids_sync(agf_rappids* p);
 #define AGF_RAPPIDS_DISPATCH_INDEX 0
 #define AGF_RAPPIDS_DISPATCH_BY_LAST_WORK 1
 int agf_rappids_set_dispatch(agf_rappids* p, int32_t mode);
+/* Validation knobs, read from the environment when a handle is created (results are bit-identical for every setting; the
+ * GPU tests compare them): AGF_RAPPIDS_FRAME_JUMP=<k> -- iterations of InflatePyramid's spiral expansion taken in one step
+ * when their frame holds no blocking pixel (default 8, 0 = line by line as the reference scans); AGF_RAPPIDS_SHRINK_FOLD=0 --
+ * one shrink update per pixel instead of one reduction per 32-pixel span of an edge region. */
 /* Device clock cycles the last plan spent on each vehicle (what BY_LAST_WORK sorts by), [count] uint32. */
 int agf_rappids_get_plan_work(agf_rappids* p, uint32_t* cycles, size_t first, size_t count);
 
