@@ -106,23 +106,48 @@ __global__ void groupmin_kernel(uint16_t* __restrict__ out, const uint16_t* __re
 // handed out in index order the launch ends with a tail in which a few warps finish long plans on an otherwise empty GPU
 // (ncu, round 2: SMs active 42 % of a 16 384-plan launch), and a planner runs at image rate on scenes that change little
 // between frames, so the last frame's work is a good forecast.  Only the order changes -- results do not depend on it.
-__global__ void __launch_bounds__(1024) dispatch_order_kernel(const unsigned* __restrict__ work, int n, int* __restrict__ order) {
+// *nlong = the number of vehicles at the head of the order whose work was at least `coop_factor` times the launch's ideal
+// length (total work / warp slots of the grid; whole buckets): only those can stretch the launch beyond what the rest of the
+// population needs anyway, and they are planned by a whole CTA each (agf_rappids_plan.cuh, plan_vehicle).
+__global__ void __launch_bounds__(1024) dispatch_order_kernel(const unsigned* __restrict__ work, int n, int* __restrict__ order,
+                                                              int* __restrict__ nlong, float coop_factor, float coop_cap, int slots) {
   __shared__ unsigned hist[2048];
   __shared__ unsigned wmax;
+  __shared__ unsigned long long wsum;
   const int t = threadIdx.x;
-  if (t == 0) wmax = 1;
+  if (t == 0) { wmax = 1; wsum = 0; }
   for (int i = t; i < 2048; i += 1024) hist[i] = 0;
   __syncthreads();
   unsigned m = 0;
-  for (int v = t; v < n; v += 1024) m = max(m, work[v]);
+  unsigned long long sum = 0;
+  for (int v = t; v < n; v += 1024) {
+    m = max(m, work[v]);
+    sum += work[v];
+  }
   atomicMax(&wmax, m);
+  atomicAdd(&wsum, sum);
   __syncthreads();
   const unsigned long long mx = wmax;
   for (int v = t; v < n; v += 1024) atomicAdd(&hist[2047 - (unsigned)((unsigned long long)work[v] * 2047ull / mx)], 1u);
   __syncthreads();
   if (t == 0) {
+    // buckets 0 .. cut-1 hold work >= (2048 - cut) / 2047 * max >= coop_factor * mean
+    int cut = 0;
+    if (coop_factor > 0.0f) {
+      const double thr = (double)coop_factor * (double)wsum / (double)slots;
+      const double b = thr * 2047.0 / (double)mx;  // bin = 2047 - floor(work * 2047 / max) < cut  <=>  floor(..) > 2047 - cut
+      cut = b >= 2047.0 ? 0 : 2047 - (int)b;       // floor(work * 2047 / max) >= floor(b) + 1 > b
+      if (cut < 0) cut = 0;
+      // ... unless together they hold more than `coop_cap` of the total work: then the launch is bound by its total work, not
+      // by its longest plan (many long plans pack well), and speculation -- which spends about twice the warp time of the
+      // sequential loop on a vehicle -- would only cost (measured on the hard scene family: 245 -> 260-277 ms)
+      double accw = 0.0;
+      for (int i = 0; i < cut; i++) accw += (double)hist[i] * ((double)(2047 - i) + 0.5) / 2047.0 * (double)mx;
+      if (accw > (double)coop_cap * (double)wsum) cut = 0;
+    }
     unsigned acc = 0;
     for (int i = 0; i < 2048; i++) {
+      if (i == cut) *nlong = (int)acc;
       const unsigned c = hist[i];
       hist[i] = acc;
       acc += c;
@@ -249,6 +274,10 @@ struct Handle {
   agf_rappids_result* results = nullptr;
   int* next = nullptr;
   int* order = nullptr;      // dispatch order of the planning pass (dispatch_order_kernel)
+  int* nlong = nullptr;      // [0] vehicles at the head of the order planned by a whole CTA each, [1] their work counter
+  float coop_factor = 0.3f;  // a vehicle is "long" when its previous plan took this fraction of (total work / warp slots);
+                             // AGF_RAPPIDS_COOP_FACTOR at create time overrides, 0: off
+  float coop_cap = 0.04f;    // ... provided all of them together hold at most this share of the total work (AGF_RAPPIDS_COOP_CAP)
   unsigned* work = nullptr;  // cycles per vehicle of the last plan
   bool have_work = false;
   int dispatch = 1;          // 1: by the previous plan's work (default), 0: index order
@@ -296,6 +325,7 @@ struct Handle {
     cudaFree(results);
     cudaFree(next);
     cudaFree(order);
+    cudaFree(nlong);
     cudaFree(work);
     cudaFree(stage);
     if (stream) cudaStreamDestroy(stream);
@@ -408,6 +438,8 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   h->kcap = max_candidates;
   if (const char* fj = getenv("AGF_RAPPIDS_FRAME_JUMP")) h->frame_jump = atoi(fj);
   if (const char* sf = getenv("AGF_RAPPIDS_SHRINK_FOLD")) h->shrink_fold = atoi(sf) != 0;
+  if (const char* cf = getenv("AGF_RAPPIDS_COOP_FACTOR")) h->coop_factor = (float)atof(cf);
+  if (const char* cc = getenv("AGF_RAPPIDS_COOP_CAP")) h->coop_cap = (float)atof(cc);
   h->device = dev;
   const size_t npix = h->npix();
 #define AGFR_ALLOC(ptr, bytes)                                  \
@@ -440,6 +472,7 @@ int agf_rappids_create(const agf_rappids_cfg* cfg, size_t n, int32_t max_candida
   AGFR_ALLOC(h->prims, n * 9 * sizeof(double));
   AGFR_ALLOC(h->next, sizeof(int));
   AGFR_ALLOC(h->order, n * sizeof(int));
+  AGFR_ALLOC(h->nlong, 2 * sizeof(int));
   AGFR_ALLOC(h->work, n * sizeof(unsigned));
 #undef AGFR_ALLOC
   // images start empty (everything at the far plane would be 65535; zero = "ignored" pixels), states zero with
@@ -631,6 +664,8 @@ int agf_rappids_plan(agf_rappids* p) {
   P.next = h->next;
   P.work = h->work;
   P.order = nullptr;
+  P.nlong = nullptr;
+  P.nextLong = h->nlong + 1;
   P.n = (int)h->n;
   P.k = h->k;
   P.kcap = h->kcap;
@@ -671,10 +706,12 @@ int agf_rappids_plan(agf_rappids* p) {
   h->ev_count++;
   AGFR_CUDA(cudaEventRecord(ev.first, h->stream));
   if (h->dispatch == 1 && h->have_work) {  // inside the timed region
-    dispatch_order_kernel<<<1, 1024, 0, h->stream>>>(h->work, (int)h->n, h->order);
+    AGFR_CUDA(cudaMemsetAsync(h->nlong, 0, 2 * sizeof(int), h->stream));
+    dispatch_order_kernel<<<1, 1024, 0, h->stream>>>(h->work, (int)h->n, h->order, h->nlong, h->coop_factor, h->coop_cap, h->grid * agfr::kWarps);
     AGFR_CUDA(cudaGetLastError());
     h->launches += 1;
     P.order = h->order;
+    if (h->coop_factor > 0.0f) P.nlong = h->nlong;
   }
   cudaError_t e = (c.math == AGF_MATH_PARITY) ? agfr::launch_plan_parity(P, h->grid, h->stream)
                                               : agfr::launch_plan_fast(P, h->grid, h->stream);

@@ -106,6 +106,8 @@ struct PlanParams {
   double* prims;          // [n][9]: alpha, beta, gamma of the returned primitive per axis (SingleAxisTrajectory state), or null
   int* next;              // work counter
   const int* order;       // dispatch order: the k-th vehicle handed out is order[k] (null: index order)
+  const int* nlong;       // *nlong vehicles at the head of `order` are planned by a whole CTA each (null: none)
+  int* nextLong;          // work counter of those
   unsigned* work;         // [n] clock cycles this call spent on each vehicle (the next call's dispatch order)
   int n, k, kcap;
   int W, H, GW, GH;       // GW = ceil(W / 32), GH = ceil(H / 32)
@@ -1244,119 +1246,195 @@ __global__ void __launch_bounds__(128) rappids_candidates_kernel(const __grid_co
   }
 }
 
+// One vehicle's planning loop.  coop == false: this warp alone, the reference's sequential loop.  coop == true: the four warps
+// of the CTA on ONE vehicle (the vehicles whose previous plan was long -- a 65 536-plan launch is as long as its longest plan):
+// every warp runs the same loop over the candidates with identical copies of the loop state; the next up to four candidates
+// that reach the collision test are tested SPECULATIVELY, one per warp, each against its own copy of the pyramid list as it
+// stood at the start of the round; the results are then committed in candidate order -- a result is valid as long as no
+// earlier candidate of the round added a pyramid or became the best, the first one that does ends the round, its list becomes
+// every warp's list and the candidates behind it are tested again.  A test is a deterministic function of (candidate, pyramid
+// list), so what is committed is exactly what the sequential loop computes.
 template<bool PARITY>
-__global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(const __grid_constant__ PlanParams P) {
-  __shared__ double s_depth[kWarps][kMaxPyr + 1];
-  __shared__ int4 s_edge[kWarps][kMaxPyr + 1];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  WarpCtx w;
-  w.lane = lane;
-  w.pdepth = s_depth[wid];
-  w.pedge = s_edge[wid];
+__device__ __noinline__ void plan_vehicle(const PlanParams& P, WarpCtx& w, const int v, const bool coop, const int wid,
+                                          double (*s_depth)[kMaxPyr + 1], int4 (*s_edge)[kMaxPyr + 1], volatile int (*s_res)[4]
 #if AGFR_PHASE_CLOCKS
-  unsigned long long clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  w.clk = clk;
-  const long long cstart_ = clock64();
-  int nplans_ = 0;
+                                          , unsigned long long* clk
 #endif
-  for (;;) {
-    int v = 0;
-    if (lane == 0) {
-      v = atomicAdd(P.next, 1);
-      if (v < P.n && P.order) v = P.order[v];
+) {
+  const int lane = w.lane;
+  const int nw = coop ? kWarps : 1, me = coop ? wid : 0;
+  const long long work0 = clock64();
+  w.img = P.img + (size_t)v * P.vstride;
+  w.imgT = P.imgT + (size_t)v * P.vstride;
+  w.gminR = P.gminR + (size_t)v * P.vstride;
+  w.gminC = P.gminC + (size_t)v * P.vstride;
+  w.npyr = 0;
+  w.capHit = 0;
+  const double* st = P.state + (size_t)v * 12;
+
+  double best = DBL_MAX;
+  int found = 0, bestIdx = -1, nCost = 0, nColl = 0, nVel = 0, nFree = 0, capHit = 0;
+
+  for (int i0 = 0; i0 < P.k; i0 += 32) {
+#if AGFR_PHASE_CLOCKS
+    const long long cc0_ = clock64();
+#endif
+    const int i = i0 + lane;
+    const bool valid = i < P.k;
+    double cost = DBL_MAX;
+    int code = 0;
+    if (valid) {
+      cost = P.ccost[(size_t)v * P.kcap + i];
+      code = P.flags[(size_t)v * P.kcap + i];
     }
-    v = __shfl_sync(AGFR_FULL, v, 0);
-    if (v >= P.n) break;
-    const long long work0 = clock64();
-    w.img = P.img + (size_t)v * P.vstride;
-    w.imgT = P.imgT + (size_t)v * P.vstride;
-    w.gminR = P.gminR + (size_t)v * P.vstride;
-    w.gminC = P.gminC + (size_t)v * P.vstride;
-    w.npyr = 0;
-    w.capHit = 0;
-    const double* st = P.state + (size_t)v * 12;
-
-    double best = DBL_MAX;
-    int found = 0, bestIdx = -1, nCost = 0, nColl = 0, nVel = 0, nFree = 0;
-    double bestT = 0;
-
+    if (coop) __syncthreads();  // every warp has read the verdict codes of this batch before warp 0 replaces them by the flags
+    // the lanes that beat the best cost at the start of the batch (it can only get lower)
+    unsigned pend = __ballot_sync(AGFR_FULL, valid && cost < best);
+    unsigned flag = 0;
 #if AGFR_PHASE_CLOCKS
-    nplans_++;
+    clk[0] += clock64() - cc0_;
 #endif
-    for (int i0 = 0; i0 < P.k; i0 += 32) {
-#if AGFR_PHASE_CLOCKS
-      const long long cc0_ = clock64();
-#endif
-      const int i = i0 + lane;
-      const bool valid = i < P.k;
-      double cost = DBL_MAX;
-      int code = 0;
-      if (valid) {
-        cost = P.ccost[(size_t)v * P.kcap + i];
-        code = P.flags[(size_t)v * P.kcap + i];
+    while (pend) {
+      // --- the next up to nw candidates that reach the collision test, in candidate order
+      int slot[kWarps];
+      int ns = 0;
+      {
+        unsigned walk = pend;
+        while (walk && ns < nw) {
+          const int src = __ffs(walk) - 1;
+          walk &= walk - 1;
+          if (!(__shfl_sync(AGFR_FULL, cost, src) < best)) continue;
+          const int cs = __shfl_sync(AGFR_FULL, code, src);
+          if ((cs & CODE_IN_MASK) == IN_FEASIBLE && (cs & CODE_VEL_OK)) slot[ns++] = src;
+        }
       }
-      // the lanes that beat the best cost at the start of the batch (it can only get lower)
-      unsigned pend = __ballot_sync(AGFR_FULL, valid && cost < best);
-      unsigned flag = 0;
+      // --- test: warp `me` takes slot `me`
+      const int npyr0 = w.npyr;
+      int myFree = 0;
+      if (me < ns) {
+        // the survivor's primitive again (same routine, same inputs as the candidate pass), warp-uniform
+        Poly Q;
+        const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + i0 + slot[me]) * 4);
+        const double goal[3] = {c4.x, c4.y, c4.z};
+        const double Ts = c4.w;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          Axis ax;
+          ax.v0 = __ldg(st + a);
+          ax.a0 = __ldg(st + 3 + a);
+          ax.generate(goal[a], Ts);
+          Q.c[0][a] = ddiv(ax.al, 120);
+          Q.c[1][a] = ddiv(ax.be, 24);
+          Q.c[2][a] = ddiv(ax.ga, 6);
+          Q.c[3][a] = ax.acc(0.0) * 0.5;  // == / 2
+          Q.c[4][a] = ax.vel(0.0);
+          Q.c[5][a] = ax.pos(0.0);
+        }
+        w.capHit = 0;
 #if AGFR_PHASE_CLOCKS
-      clk[0] += clock64() - cc0_;
+        const long long cf0_ = clock64();
+        const unsigned long long in0_ = clk[1] + clk[2] + clk[4];
+        myFree = collision_free<PARITY>(P, w, Q, Ts) ? 1 : 0;
+        clk[3] += (clock64() - cf0_) - (clk[1] + clk[2] + clk[4] - in0_);
+#else
+        myFree = collision_free<PARITY>(P, w, Q, Ts) ? 1 : 0;
 #endif
-      while (pend) {
+      }
+      if (coop) {
+        if (me < ns && lane == 0) {
+          s_res[me][0] = myFree;
+          s_res[me][1] = w.npyr;
+          s_res[me][2] = w.capHit;
+        }
+        __syncthreads();
+      }
+      // --- commit in candidate order (every warp computes the same)
+      int s = 0, adopt = -1;
+      bool stop = false;
+      while (pend && !stop) {
         const int src = __ffs(pend) - 1;
-        pend &= pend - 1;
         const double csrc = __shfl_sync(AGFR_FULL, cost, src);
-        if (!(csrc < best)) continue;
+        if (!(csrc < best)) {
+          pend &= pend - 1;
+          continue;
+        }
+        const int cs = __shfl_sync(AGFR_FULL, code, src);
+        const bool tested = (cs & CODE_IN_MASK) == IN_FEASIBLE && (cs & CODE_VEL_OK);
+        if (tested && s >= ns) break;  // not tested in this round: the next one
         unsigned f = 1;  // LowCost
         nCost++;
-        const int cs = __shfl_sync(AGFR_FULL, code, src);
         if ((cs & CODE_IN_MASK) == IN_FEASIBLE) {
           f |= 2;
           nColl++;
           if (cs & CODE_VEL_OK) {
             f |= 4;
             nVel++;
-            // the survivor's primitive again (same routine, same inputs as the candidate pass), warp-uniform
-            Poly Q;
-            const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + i0 + src) * 4);
-            const double goal[3] = {c4.x, c4.y, c4.z};
-            const double Ts = c4.w;
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-              Axis ax;
-              ax.v0 = __ldg(st + a);
-              ax.a0 = __ldg(st + 3 + a);
-              ax.generate(goal[a], Ts);
-              Q.c[0][a] = ddiv(ax.al, 120);
-              Q.c[1][a] = ddiv(ax.be, 24);
-              Q.c[2][a] = ddiv(ax.ga, 6);
-              Q.c[3][a] = ax.acc(0.0) * 0.5;  // == / 2
-              Q.c[4][a] = ax.vel(0.0);
-              Q.c[5][a] = ax.pos(0.0);
-            }
-#if AGFR_PHASE_CLOCKS
-            const long long cf0_ = clock64();
-            const unsigned long long in0_ = clk[1] + clk[2] + clk[4];
-            const bool cfree_ = collision_free<PARITY>(P, w, Q, Ts);
-            clk[3] += (clock64() - cf0_) - (clk[1] + clk[2] + clk[4] - in0_);
-            if (cfree_) {
-#else
-            if (collision_free<PARITY>(P, w, Q, Ts)) {
-#endif
+            const int rFree = coop ? s_res[s][0] : myFree;
+            const int rNpyr = coop ? s_res[s][1] : w.npyr;
+            capHit |= coop ? s_res[s][2] : w.capHit;
+            if (rFree) {
               f |= 8;
               found = 1;
               best = csrc;
               nFree++;
               bestIdx = i0 + src;
-              bestT = Ts;
+              stop = true;  // the cost bound moved: what was tested behind it is void
             }
+            if (rNpyr != npyr0) {
+              adopt = s;
+              stop = true;  // the pyramid list grew: what was tested behind it is void
+            }
+            s++;
           }
         }
+        pend &= pend - 1;
         if (lane == src) flag = f;
       }
-      if (valid) P.flags[(size_t)v * P.kcap + i] = (uint8_t)flag;
+      if (coop && ns > 0) {
+        // every warp continues with the committed list: that of the slot that changed it, else slot 0's (unchanged)
+        const int from = adopt >= 0 ? adopt : 0;
+        const int npyrT = s_res[from][1];
+        if (me != from) {
+          for (int q = lane; q < npyrT; q += 32) {
+            s_depth[me][q] = s_depth[from][q];
+            s_edge[me][q] = s_edge[from][q];
+          }
+          w.npyr = npyrT;
+        }
+        __syncthreads();
+      }
     }
-    // results
-    ResultRec* out = reinterpret_cast<ResultRec*>(P.results) + v;
+    if (valid && me == 0) P.flags[(size_t)v * P.kcap + i] = (uint8_t)flag;
+  }
+  if (me != 0) return;
+  // results
+  ResultRec* out = reinterpret_cast<ResultRec*>(P.results) + v;
+  {  // the returned primitive -- polynomial coefficients, and the generator's own variables for the tracking loop --
+     // regenerated from the winning candidate (same routine, same inputs) rather than carried through the candidate loop:
+     // lane 3k+a holds coefficient k of axis a
+    const int a = lane % 3, kq = lane / 3;
+    double coef = 0, al = 0, be = 0, ga = 0, bestT = 0;
+    if (found) {
+      const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + bestIdx) * 4);
+      bestT = c4.w;
+      if (lane < 18) {
+        const double goal = a == 0 ? c4.x : (a == 1 ? c4.y : c4.z);
+        Axis ax;
+        ax.v0 = __ldg(st + a);
+        ax.a0 = __ldg(st + 3 + a);
+        ax.generate(goal, c4.w);
+        al = ax.al;
+        be = ax.be;
+        ga = ax.ga;
+        coef = kq == 0 ? ddiv(al, 120) : kq == 1 ? ddiv(be, 24) : kq == 2 ? ddiv(ga, 6) : kq == 3 ? ax.acc(0.0) * 0.5 : kq == 4 ? ax.vel(0.0) : ax.pos(0.0);
+      }
+    }
+    if (lane < 18) out->best_coeffs[lane] = coef;
+    if (P.prims && lane < 3) {
+      P.prims[(size_t)v * 9 + 3 * lane] = al;
+      P.prims[(size_t)v * 9 + 3 * lane + 1] = be;
+      P.prims[(size_t)v * 9 + 3 * lane + 2] = ga;
+    }
     if (lane == 0) {
       out->found = found;
       out->best_index = bestIdx;
@@ -1368,52 +1446,77 @@ __global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(c
       out->n_pyramids = w.npyr;
       out->best_cost = best;
       out->best_tf = bestT;
-      out->pyramid_cap_hit = w.capHit;
+      out->pyramid_cap_hit = capHit;
       out->reserved_ = 0;
       const long long dt = clock64() - work0;
       P.work[v] = dt > 0xffffffffLL ? 0xffffffffu : (unsigned)dt;
     }
-    {  // the returned primitive -- polynomial coefficients, and the generator's own variables for the tracking loop --
-       // regenerated from the winning candidate (same routine, same inputs) rather than carried through the candidate loop:
-       // lane 3k+a holds coefficient k of axis a
-      const int a = lane % 3, kq = lane / 3;
-      double coef = 0, al = 0, be = 0, ga = 0;
-      if (found && lane < 18) {
-        const double4 c4 = *reinterpret_cast<const double4*>(P.cands + ((size_t)v * P.kcap + bestIdx) * 4);
-        const double goal = a == 0 ? c4.x : (a == 1 ? c4.y : c4.z);
-        Axis ax;
-        ax.v0 = __ldg(st + a);
-        ax.a0 = __ldg(st + 3 + a);
-        ax.generate(goal, c4.w);
-        al = ax.al;
-        be = ax.be;
-        ga = ax.ga;
-        coef = kq == 0 ? ddiv(al, 120) : kq == 1 ? ddiv(be, 24) : kq == 2 ? ddiv(ga, 6) : kq == 3 ? ax.acc(0.0) * 0.5 : kq == 4 ? ax.vel(0.0) : ax.pos(0.0);
-      }
-      if (lane < 18) out->best_coeffs[lane] = coef;
-      if (P.prims && lane < 3) {
-        P.prims[(size_t)v * 9 + 3 * lane] = al;
-        P.prims[(size_t)v * 9 + 3 * lane + 1] = be;
-        P.prims[(size_t)v * 9 + 3 * lane + 2] = ga;
-      }
+  }
+  {
+    double* rec = P.pyramids + ((size_t)v * kMaxPyr + lane) * 17;
+    if (lane < w.npyr) {
+      const double d = w.pdepth[lane];
+      const int4 e = w.pedge[lane];
+      rec[0] = d;
+      rec[1] = e.x;
+      rec[2] = e.y;
+      rec[3] = e.z;
+      rec[4] = e.w;
+      for (int f = 0; f < 4; f++) pyr_normal(P, d, e, f, rec + 5 + 3 * f);
+    } else {
+      const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+      for (int q = 0; q < 17; q++) rec[q] = nanv;
     }
-    {
-      double* rec = P.pyramids + ((size_t)v * kMaxPyr + lane) * 17;
-      if (lane < w.npyr) {
-        const double d = w.pdepth[lane];
-        const int4 e = w.pedge[lane];
-        rec[0] = d;
-        rec[1] = e.x;
-        rec[2] = e.y;
-        rec[3] = e.z;
-        rec[4] = e.w;
-        for (int f = 0; f < 4; f++) pyr_normal(P, d, e, f, rec + 5 + 3 * f);
-      } else {
-        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-        for (int q = 0; q < 17; q++) rec[q] = nanv;
-      }
+  }
+  __syncwarp();
+}
+
+template<bool PARITY>
+__global__ void __launch_bounds__(kBlock, AGFR_MIN_BLOCKS) rappids_plan_kernel(const __grid_constant__ PlanParams P) {
+  __shared__ double s_depth[kWarps][kMaxPyr + 1];
+  __shared__ int4 s_edge[kWarps][kMaxPyr + 1];
+  __shared__ int s_res[kWarps][4];
+  __shared__ int s_v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  WarpCtx w;
+  w.lane = lane;
+  w.pdepth = s_depth[wid];
+  w.pedge = s_edge[wid];
+#if AGFR_PHASE_CLOCKS
+  unsigned long long clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  w.clk = clk;
+  const long long cstart_ = clock64();
+  int nplans_ = 0;
+#define AGFR_CLK_ARG , clk
+#else
+#define AGFR_CLK_ARG
+#endif
+  // the vehicles whose previous plan was long (the head of the dispatch order): one CTA per vehicle
+  int base = 0;
+  if (P.nlong) {
+    base = *P.nlong;
+    for (;;) {
+      if (threadIdx.x == 0) s_v = atomicAdd(P.nextLong, 1);
+      __syncthreads();
+      const int kq = s_v;
+      __syncthreads();
+      if (kq >= base) break;
+      plan_vehicle<PARITY>(P, w, P.order[kq], true, wid, s_depth, s_edge, s_res AGFR_CLK_ARG);
     }
-    __syncwarp();
+  }
+  // all others: one warp per vehicle, vehicles handed out through a counter
+  for (;;) {
+    int v = 0;
+    if (lane == 0) {
+      v = atomicAdd(P.next, 1) + base;
+      if (v < P.n && P.order) v = P.order[v];
+    }
+    v = __shfl_sync(AGFR_FULL, v, 0);
+    if (v >= P.n) break;
+#if AGFR_PHASE_CLOCKS
+    nplans_++;
+#endif
+    plan_vehicle<PARITY>(P, w, v, false, wid, s_depth, s_edge, s_res AGFR_CLK_ARG);
   }
 #if AGFR_PHASE_CLOCKS
   if (lane == 0 && wid == 0 && blockIdx.x % 97 == 0)

@@ -415,9 +415,23 @@ def test_frame_jumps_and_dispatch_order_do_not_change_results(agf, family, monke
                 pl.sync()
                 out["second"] = (pl.results(), pl.candidate_flags(), pl.pyramids())
                 assert work.min() > 0
+    # the vehicles whose previous plan was long are planned by a whole CTA each (speculative collision tests committed in
+    # order): with the threshold at 0.0002 x the launch's ideal length that is most of the population
+    monkeypatch.setenv("AGF_RAPPIDS_FRAME_JUMP", "8")
+    monkeypatch.setenv("AGF_RAPPIDS_SHRINK_FOLD", "1")
+    monkeypatch.setenv("AGF_RAPPIDS_COOP_FACTOR", "0.0002")
+    monkeypatch.setenv("AGF_RAPPIDS_COOP_CAP", "1.0")
+    with agf.Rappids(agf.rappids_cfg(math=agf.abi.MATH_PARITY), n, k) as pl:
+        pl.render_scenes(pop["row_bg"], pop["boxes"])
+        pl.set_states(pop["vel0"], pop["acc0"], pop["grav"])
+        pl.set_candidates(cands)
+        for _ in range(2):
+            pl.plan()
+        pl.sync()
+        out["coop"] = (pl.results(), pl.candidate_flags(), pl.pyramids())
     ref = out[0]
     assert ref[0]["n_pyramids"].sum() > n
-    for key in (8, 3, "second"):
+    for key in (8, 3, "second", "coop"):
         res, flags, pyr = out[key]
         assert res.tobytes() == ref[0].tobytes(), key
         assert np.array_equal(flags, ref[1]), key
