@@ -1,17 +1,17 @@
 // agf_rappids_plan.cuh -- K6: the batched RAPPIDS planner kernel (C5 / N3).
 //
-// One warp plans for one vehicle: FindLowestCostTrajectory (Components/Components/DepthImagePlanner/
-// DepthImagePlanner.cpp:91-214) on that vehicle's depth image, with the reference's sequential semantics kept
-// exactly (candidates in order, cost pruning against the best collision-free candidate so far, pyramids
-// generated on demand and reused) and the 32 lanes used where the algorithm is data parallel:
-//   * 32 candidates at a time: motion primitive (TrajectoryGenerator/SingleAxisTrajectory.cpp:59-103), cost,
-//     and -- speculatively, for the lanes that beat the best cost at the start of the batch -- the recursive
-//     input-feasibility test (RapidTrajectoryGenerator.cpp:75-160) and the velocity test (:163-205);
-//   * the survivors are collision checked one after the other in candidate order (DepthImagePlanner.cpp:216-301)
-//     with the whole warp on each: the four lateral faces of a pyramid on four lanes (:382-454), the pyramid
-//     list searched with one ballot (:356-380), the pixel scans of InflatePyramid (:456-970) 32 pixels per step
-//     in the reference's scan order -- a ballot finds the first pixel that changes the state, the update is
-//     applied warp-uniformly and the lanes behind it are re-evaluated, so the result is the sequential one.
+// FindLowestCostTrajectory (Components/Components/DepthImagePlanner/DepthImagePlanner.cpp:91-214) for every vehicle of a
+// population, each on its own depth image, with the reference's sequential semantics kept exactly (candidates in order, cost
+// pruning against the best collision-free candidate so far, pyramids generated on demand and reused).  Two kernels per call:
+//   * rappids_candidates_kernel, one thread per candidate: motion primitive (TrajectoryGenerator/SingleAxisTrajectory.cpp:59-103),
+//     cost, the recursive input-feasibility test (RapidTrajectoryGenerator.cpp:75-160) and the velocity test (:163-205);
+//   * rappids_plan_kernel, one warp per vehicle (a whole CTA for the vehicles whose previous plan was long): the loop over
+//     the candidates; the survivors are collision checked in candidate order (DepthImagePlanner.cpp:216-301) with the whole
+//     warp on each: the four lateral faces of a pyramid on four lanes (:382-454), the pyramid list searched with one ballot
+//     (:356-380), the pixel scans of InflatePyramid (:456-970) 32 pixels per step in the reference's scan order -- a ballot
+//     finds the first pixel that changes the state, the update is applied warp-uniformly and the lanes behind it are
+//     re-evaluated, so the result is the sequential one; stretches of the scan whose outcome does not depend on the order
+//     (frames of the spiral expansion without a blocker, unblocked shrink spans) are taken in one step.
 // Row walks read the image [H][W]; column walks read a transposed copy [W][H] so that both are coalesced.
 //
 // Compiled twice (agf_rappids_plan.cu): PARITY (-fmad=false, agf_math.h: bit-comparable with the oracle) and
@@ -36,36 +36,14 @@ namespace agfr {
 #ifndef AGFR_PHASE_CLOCKS
 #define AGFR_PHASE_CLOCKS 0  // tuning builds: per-phase clock64() totals of a few warps, printed at the end of the kernel
 #endif
-#ifndef AGFR_EXPAND_SPEC
-#define AGFR_EXPAND_SPEC 0
-#endif
-#ifndef AGFR_AXIS_CALLS
-#define AGFR_AXIS_CALLS 0
-#endif
-#if AGFR_AXIS_CALLS == 1
-#define AGFR_AXIS_FN __device__ __noinline__
-#define AGFR_SECTION_FN __device__ __forceinline__
-#elif AGFR_AXIS_CALLS == 2
-#define AGFR_AXIS_FN __device__ __forceinline__
-#define AGFR_SECTION_FN static __device__ __noinline__
-#else
-#define AGFR_AXIS_FN __device__ __forceinline__
-#define AGFR_SECTION_FN __device__ __forceinline__
-#endif
 #ifndef AGFR_DIV_CALLS
 #define AGFR_DIV_CALLS 1
 #endif
 #ifndef AGFR_SHRINK_FOLD
 #define AGFR_SHRINK_FOLD 1
 #endif
-#ifndef AGFR_FLOAT_QUOT
-#define AGFR_FLOAT_QUOT 0
-#endif
 #ifndef AGFR_FRAME_JUMP
 #define AGFR_FRAME_JUMP 1  // frame jumps of the spiral expansion compiled in (their length is PlanParams::frameJump)
-#endif
-#ifndef AGFR_EXPAND_PF
-#define AGFR_EXPAND_PF 0
 #endif
 #ifndef AGFR_COLD_CALLS
 #define AGFR_COLD_CALLS 1
@@ -411,7 +389,7 @@ struct Prim {
 // ---------------------------------------------------------------------------------------------
 struct Poly {
   double c[6][3];  // GetTrajectory(): t^5 first (RapidTrajectoryGenerator.hpp:232-241)
-  AGFR_AXIS_FN double axis(int i, double t) const {
+  AGFR_DEV double axis(int i, double t) const {
     return c[0][i] * t * t * t * t * t + c[1][i] * t * t * t * t + c[2][i] * t * t * t + c[3][i] * t * t + c[4][i] * t +
            c[5][i];
   }
@@ -437,12 +415,6 @@ struct WarpCtx {
 };
 
 AGFR_DEV unsigned ld16(const uint16_t* p) { return (unsigned)__ldg(p); }
-// a load the compiler keeps where it is written (issued ahead of the test that decides whether its value is needed)
-AGFR_DEV unsigned ld16_spec(const uint16_t* p) {
-  unsigned short r;
-  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(r) : "l"(p));
-  return (unsigned)r;
-}
 AGFR_DEV unsigned lanes_after(int src) { return 0xfffffffeu << src; }
 
 // DepthImagePlanner::InflatePyramid (DepthImagePlanner.cpp:456-970), warp cooperative.
@@ -466,16 +438,7 @@ AGFR_DEV bool shrink_trigger(const int REGION, const Shrink& s, int num, int x, 
 }
 // applies the update of one triggering pixel; false = "the pyramid cannot contain the sample point"
 AGFR_DEV bool shrink_apply(const int REGION, Shrink& s, int num, int x, int y, int p, int x0, int y0) {
-  // num / p (p >= 1): a float quotient corrected to the exact floor is a third of the instructions of the 32-bit integer
-  // division (which was 6 % of the planning pass's instructions); exact for num < 2^20, where the quotient's error is < 1
-  int q;
-  if (AGFR_FLOAT_QUOT && num < (1 << 20)) {
-    q = (int)__fdividef((float)num, (float)p);
-    q -= (q * p > num);
-    q += ((q + 1) * p <= num);
-  } else {
-    q = num / p;
-  }
+  const int q = num / p;
   const int rT = x - q, lT = x + q, tT = y + q, bT = y - q;
   if (REGION == R_RIGHT || REGION == R_LEFT) {
     const bool blocked = (REGION == R_RIGHT) ? (x0 > rT - kBuf) : (x0 < lT + kBuf);
@@ -699,20 +662,12 @@ static __device__ __noinline__ bool shrink_region(const int REGION, const PlanPa
 // pyramid's minimum depth blocks the side; folds the depths seen before it into maxDepth.
 // `plane` + idx * pitch is the pixel line, `gplane` + idx * G its group minima.
 static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpCtx& w, const uint16_t* plane, const uint16_t* gplane,
-                                                int pitch, int G, int idx, int dir, int nlines, int a, int b, int minPyr, int& maxDepth) {
+                                                int pitch, int G, int idx, int a, int b, int minPyr, int& maxDepth) {
   const uint16_t* line = plane + (size_t)idx * pitch;
   const uint16_t* gl = gplane + (size_t)idx * G;
   unsigned mn = 65535u;
   bool blocked = false;
   const int g0 = a >> 5, g1 = b >> 5;
-#if AGFR_EXPAND_SPEC
-  // Only the two end groups of a range can be covered partly, and in scenes whose depth varies along the line they need their
-  // pixels on almost every line: their pixels are requested TOGETHER with the group minima (one memory round trip per line
-  // instead of two dependent ones; the planning pass waits on exactly these loads -- ncu, round 2: 18 % of its stall samples).
-  const int e0b = min(b, (g0 << 5) + 31);
-  const int pe0 = (a + w.lane <= e0b) ? (int)ld16_spec(line + a + w.lane) : 0;
-  const int pe1 = (g1 > g0 && (g1 << 5) + w.lane <= b) ? (int)ld16_spec(line + (g1 << 5) + w.lane) : 0;
-#endif
   for (int gb = g0; gb <= g1 && !blocked; gb += 32) {
     const int g = gb + w.lane;
     const bool in = g <= g1;
@@ -730,11 +685,7 @@ static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpC
       const int ca = max(a, gs << 5), cb = min(b, (gs << 5) + 31);
       const int vv = ca + w.lane;
       const bool valid = vv <= cb;
-#if AGFR_EXPAND_SPEC
-      const int p = (gs == g0) ? pe0 : (gs == g1) ? pe1 : (valid ? (int)ld16(line + vv) : 0);
-#else
       const int p = valid ? (int)ld16(line + vv) : 0;
-#endif
       const bool sees = valid && p > P.ignore;
       const bool blk = sees && p < minPyr;
       const unsigned bm = __ballot_sync(AGFR_FULL, blk);
@@ -749,16 +700,6 @@ static __device__ __noinline__ bool expand_line(const PlanParams& P, const WarpC
     // whole groups without a blocking pixel, before the blocking group: their minimum is the minimum of their seen pixels
     if (full && !cand && w.lane < blockLane) mn = min(mn, gm);
   }
-#if AGFR_EXPAND_PF
-  // the line this side reaches next (four calls from now): its group minima and end-group pixels towards L1
-  if (!blocked && (unsigned)(idx + dir) < (unsigned)nlines && w.lane < 6) {
-    const uint16_t* nl = line + dir * pitch;
-    const uint16_t* q = w.lane == 0 ? gl + dir * G + g0 : w.lane == 1 ? gl + dir * G + g1 :
-                        w.lane == 2 ? nl + max(a - 1, 0) : w.lane == 3 ? nl + min(a + 15, pitch - 1) :
-                        w.lane == 4 ? nl + min(b + 1, pitch - 1) : nl + max(b - 15, 0);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-  }
-#endif
   mn = __reduce_min_sync(AGFR_FULL, mn);
   if ((int)mn < maxDepth) maxDepth = (int)mn;
   return blocked;
@@ -931,7 +872,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
 #endif
     if (rf) {
       if (right < W - edgeOff - 1) {
-        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, right + 1, 1, W, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, right + 1, top, bottom, minPyr, maxDepth)) {
           rf = false;
           right--;
         }
@@ -942,7 +883,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (tf) {
       if (top > edgeOff) {
-        if (expand_line(P, w, w.img, w.gminR, W, P.GW, top - 1, -1, H, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, w.gminR, W, P.GW, top - 1, left, right, minPyr, maxDepth)) {
           tf = false;
           top++;
         }
@@ -953,7 +894,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (lf) {
       if (left > edgeOff) {
-        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, left - 1, -1, W, top, bottom, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.imgT, w.gminC, H, P.GH, left - 1, top, bottom, minPyr, maxDepth)) {
           lf = false;
           left++;
         }
@@ -964,7 +905,7 @@ static __device__ __noinline__ bool inflate(const PlanParams& P, const WarpCtx& 
     }
     if (bf) {
       if (bottom < H - edgeOff - 1) {
-        if (expand_line(P, w, w.img, w.gminR, W, P.GW, bottom + 1, 1, H, left, right, minPyr, maxDepth)) {
+        if (expand_line(P, w, w.img, w.gminR, W, P.GW, bottom + 1, left, right, minPyr, maxDepth)) {
           bf = false;
           bottom--;
         }
@@ -1044,14 +985,14 @@ AGFR_PIECE_FN void pyr_normal(const PlanParams& P, double depth, const int4& e, 
   n[2] = ddiv(z, nrm);
 }
 
-AGFR_SECTION_FN Section make_section(const Poly& Q, double t0, double t1) {
+AGFR_DEV Section make_section(const Poly& Q, double t0, double t1) {
   Section s;
   s.t0 = t0;
   s.t1 = t1;
   s.inc = Q.axis(2, t0) < Q.axis(2, t1);
   return s;
 }
-AGFR_SECTION_FN double deepest(const Poly& Q, const Section& s) { return Q.axis(2, s.inc ? s.t1 : s.t0); }
+AGFR_DEV double deepest(const Poly& Q, const Section& s) { return Q.axis(2, s.inc ? s.t1 : s.t0); }
 
 // DepthImagePlanner::IsCollisionFree (DepthImagePlanner.cpp:216-301) for one candidate; all lanes hold the same Q
 template<bool PARITY>
