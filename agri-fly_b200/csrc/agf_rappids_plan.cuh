@@ -36,6 +36,9 @@ namespace agfr {
 #ifndef AGFR_PHASE_CLOCKS
 #define AGFR_PHASE_CLOCKS 0  // tuning builds: per-phase clock64() totals of a few warps, printed at the end of the kernel
 #endif
+#ifndef AGFR_CAND_MIN_BLOCKS
+#define AGFR_CAND_MIN_BLOCKS 8  // CTAs per SM the candidate pass aims at: 4 (110 registers) / 6 / 8 / 12 -> 8.0 / 7.5 / 7.1 / 7.2 ms
+#endif
 #ifndef AGFR_DIV_CALLS
 #define AGFR_DIV_CALLS 1
 #endif
@@ -1151,7 +1154,7 @@ __device__ __noinline__ bool collision_free(const PlanParams& P, WarpCtx& w, con
 enum { CODE_IN_MASK = 7, CODE_VEL_OK = 8 };  // verdict code: input-feasibility result | velocity test passed
 
 template<bool PARITY>
-__global__ void __launch_bounds__(128) rappids_candidates_kernel(const __grid_constant__ PlanParams P) {
+__global__ void __launch_bounds__(128, AGFR_CAND_MIN_BLOCKS) rappids_candidates_kernel(const __grid_constant__ PlanParams P) {
   const size_t total = (size_t)P.n * (size_t)P.k;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t v = idx / (size_t)P.k;
