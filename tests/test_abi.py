@@ -202,3 +202,13 @@ def test_nccl_is_bound_at_run_time_not_link_time(agf):
     comm = C.c_void_p()
     assert L.agf_nccl_comm_init_rank(uid, 2, 5, 0, C.byref(comm)) == agf.abi.EINVAL
     assert L.agf_batch_reduce_stats_nccl(None, None, None, None) == agf.abi.EINVAL
+
+
+def test_planner_dispatch_entry_points_check_their_arguments_before_any_device_work(agf):
+    """agf_rappids_set_dispatch / agf_rappids_get_plan_work (the work-ordered dispatch of the planning pass): argument errors are
+    reported without a device."""
+    L = agf.lib()
+    assert L.agf_rappids_set_dispatch(None, 1) == agf.abi.EINVAL
+    assert L.agf_rappids_get_plan_work(None, None, 0, 0) == agf.abi.EINVAL
+    assert L.agf_rappids_plan(None) == agf.abi.EINVAL
+    assert b"null" in L.agf_last_error_string()
