@@ -1,5 +1,5 @@
-"""The two order-independence arguments the planning pass of the batched RAPPIDS planner relies on
-(agri-fly_b200/csrc/agf_rappids_plan.cuh: frame_pair / inflate, shrink_span), checked on the CPU with small
+"""The order-independence arguments the planning pass of the batched RAPPIDS planner relies on
+(agri-fly_b200/csrc/agf_rappids_plan.cuh: frame_pair / inflate, shrink_span, plan_vehicle), checked on the CPU with small
 restatements of InflatePyramid's scans (Components/Components/DepthImagePlanner/DepthImagePlanner.cpp:519-599 spiral
 expansion, :601-939 shrink updates of the four edge regions) -- pure Python, no device:
 
@@ -8,6 +8,9 @@ expansion, :601-939 shrink updates of the four edge regions) -- pure Python, no 
     that frame; a frame with a blocker is refused and the line-by-line iterations decide.
   * the unblocked shrink updates of a span of an edge region equal one reduction over the pixels that trigger with the
     bounds at the start of the span.
+  * rounds of up to four collision tests against copies of the pyramid list, committed in candidate order until the
+    first result that moves the cost bound or grows the list, produce exactly the sequential plan (a toy deterministic
+    test function stands in for IsCollisionFree).
 
 The GPU tests (tests/test_rappids_gpu.py) compare the device code itself bit for bit with the line-by-line / per-pixel
 variants and with the reference; these tests pin the ARGUMENT, so that it can be checked where there is no GPU.
@@ -293,3 +296,108 @@ def test_folded_shrink_span_equals_the_sequential_updates(region):
         folded += 1
         assert f == span_sequential(region, s, num, xs, ys, ps, x0, y0), (region, s, num, xs, ys, ps, x0, y0)
     assert folded > 1000 and fallback > 50  # both paths occur
+
+
+# ------------------------------------------------------------------------------------------------
+# speculative planning of a long vehicle by a whole CTA (plan_vehicle, coop): rounds of up to four collision tests against
+# copies of the pyramid list, committed in candidate order
+# ------------------------------------------------------------------------------------------------
+IN_FEASIBLE, CODE_VEL_OK = 0, 8
+
+
+def toy_collision_test(cand, pyramids, rng_seed):
+    """A deterministic function of (candidate, pyramid list) standing in for IsCollisionFree: may append pyramids to the
+    list it is given (in place) and returns whether the candidate is free."""
+    h = hash((rng_seed, cand, tuple(pyramids))) & 0xFFFFFFFF
+    r = np.random.default_rng(h)
+    for _ in range(int(r.integers(0, 3))):
+        if r.random() < 0.25 and len(pyramids) < 32:
+            pyramids.append(int(r.integers(0, 1 << 20)))
+    return bool(r.random() < 0.08)
+
+
+def plan_sequential(costs, codes, seed):
+    best, pyr = float("inf"), []
+    flags, cnt = [0] * len(costs), dict(cost=0, coll=0, vel=0, free=0)
+    best_idx = -1
+    for i, (c, code) in enumerate(zip(costs, codes)):
+        if not c < best:
+            continue
+        f = 1
+        cnt["cost"] += 1
+        if (code & 7) == IN_FEASIBLE:
+            f |= 2
+            cnt["coll"] += 1
+            if code & CODE_VEL_OK:
+                f |= 4
+                cnt["vel"] += 1
+                if toy_collision_test(i, pyr, seed):
+                    f |= 8
+                    best, best_idx = c, i
+                    cnt["free"] += 1
+        flags[i] = f
+    return flags, cnt, pyr, best_idx
+
+
+def plan_speculative(costs, codes, seed, nw=4):
+    """The device's loop: batches of 32 candidates; per round select up to nw tested candidates, test each against its own
+    copy of the list, commit in order until the first result that moves the cost bound or grows the list."""
+    best, truth = float("inf"), []
+    flags, cnt = [0] * len(costs), dict(cost=0, coll=0, vel=0, free=0)
+    best_idx, rounds, voided = -1, 0, 0
+    for i0 in range(0, len(costs), 32):
+        idx = list(range(i0, min(i0 + 32, len(costs))))
+        pend = [i for i in idx if costs[i] < best]
+        while pend:
+            tested = lambda i: (codes[i] & 7) == IN_FEASIBLE and bool(codes[i] & CODE_VEL_OK)
+            slots = [i for i in pend if costs[i] < best and tested(i)][:nw]
+            results = []
+            for i in slots:  # one warp each, its own copy of the list as it stood at the start of the round
+                mine = list(truth)
+                results.append((toy_collision_test(i, mine, seed), mine))
+            rounds += 1
+            s, stop, npyr0 = 0, False, len(truth)
+            while pend and not stop:
+                i = pend[0]
+                if not costs[i] < best:
+                    pend.pop(0)
+                    continue
+                if tested(i) and s >= len(slots):
+                    break
+                f = 1
+                cnt["cost"] += 1
+                if (codes[i] & 7) == IN_FEASIBLE:
+                    f |= 2
+                    cnt["coll"] += 1
+                    if codes[i] & CODE_VEL_OK:
+                        f |= 4
+                        cnt["vel"] += 1
+                        free, mine = results[s]
+                        if free:
+                            f |= 8
+                            best, best_idx = costs[i], i
+                            cnt["free"] += 1
+                            stop = True
+                        if len(mine) != npyr0:
+                            truth = mine
+                            stop = True
+                        s += 1
+                pend.pop(0)
+                flags[i] = f
+            voided += len(slots) - s
+    return flags, cnt, truth, best_idx, rounds, voided
+
+
+def test_speculative_rounds_commit_exactly_the_sequential_plan():
+    rng = np.random.default_rng(5)
+    voided = rounds = 0
+    for trial in range(300):
+        k = int(rng.integers(1, 200))
+        costs = list(rng.normal(size=k) - np.linspace(0, rng.random() * 2, k))  # a drifting bound: many pass the cost check
+        codes = [int(rng.choice([IN_FEASIBLE | CODE_VEL_OK] * 8 + [IN_FEASIBLE, 1, 2, 3])) for _ in range(k)]
+        a = plan_sequential(costs, codes, trial)
+        b = plan_speculative(costs, codes, trial)
+        assert a == b[:4], trial
+        rounds += b[4]
+        voided += b[5]
+    assert rounds > 1000 and voided > 100  # speculation both holds and is voided in this test
